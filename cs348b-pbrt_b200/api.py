@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's PhotonShooter + PhotonVolumeIntegrator over the C ABI.
+
+Names follow the reference: `Preprocess` (core/photonshooter.cpp:457-526), `Li`
+and `Transmittance` (integrators/photonvolume.cpp:15-30,112-222), `LPhoton`
+(:65-108), `Lookup` (core/kdtree.h:150-183), `Intersect`/`IntersectP`
+(accelerators/bvh.cpp:585-685).  Everything forwards to csrc/libpv.so; nothing
+is computed here.
+"""
+import ctypes as C
+import os
+import numpy as np
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PVError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pv error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "csrc", "libpv.so")
+
+
+def load_library():
+    """Load csrc/libpv.so.  Raises if it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise PVError(A.PV_ESTATE, "CUDA library %s is missing: run `python __graft_entry__.py` (build()) first" % path)
+    L = C.CDLL(path)
+    L.pv_last_error.restype = C.c_char_p
+    L.pv_last_error.argtypes = [C.c_void_p]
+    L.pv_stream.restype = C.c_void_p
+    L.pv_stream.argtypes = [C.c_void_p]
+    L.pv_destroy.argtypes = [C.c_void_p]
+    L.pv_destroy.restype = None
+    _LIB = L
+    return L
+
+
+def _vp(a):
+    """void* of a numpy array (host) or a torch tensor / int (device)."""
+    if a is None:
+        return C.c_void_p(None)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class PhotonVolume:
+    """One pv_ctx: scene + photon map + the integrator parameters."""
+
+    def __init__(self, device=0, stepsize=1.0, nused=250, maxdist=0.1, seed=0):
+        # defaults == CreatePhotonVolumeIntegrator (integrators/photonvolume.cpp:224-229)
+        self.lib = load_library()
+        self.ctx = C.c_void_p(None)
+        rc = self.lib.pv_create(C.byref(self.ctx), C.c_int(device))
+        if rc != 0:
+            raise PVError(rc, (self.lib.pv_last_error(None) or b"").decode())
+        self.stepsize, self.nused, self.maxdist, self.seed = float(stepsize), int(nused), float(maxdist), int(seed)
+        self.scene = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.pv_destroy(self.ctx)
+            self.ctx = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PVError(rc, (self.lib.pv_last_error(self.ctx) or b"").decode())
+
+    # ---- scene ---------------------------------------------------------
+    def set_scene(self, scene):
+        self.scene = scene
+        d = scene.desc()
+        self._chk(self.lib.pv_set_scene(self.ctx, C.byref(d)))
+
+    # ---- photon map ----------------------------------------------------
+    def set_photons(self, pos, wi, alpha):
+        pos, wi, alpha = _f32(pos), _f32(wi), _f32(alpha)
+        n = pos.size // 3
+        self._chk(self.lib.pv_set_photons(self.ctx, _vp(pos), _vp(wi), _vp(alpha), C.c_uint64(n)))
+
+    def set_photons_dev(self, pos, wi, alpha, n):
+        self._chk(self.lib.pv_set_photons_dev(self.ctx, _vp(pos), _vp(wi), _vp(alpha), C.c_uint64(n)))
+
+    def photon_count(self):
+        n = C.c_uint64(0)
+        self._chk(self.lib.pv_photon_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def get_photons(self):
+        n = self.photon_count()
+        pos = np.zeros((n, 3), np.float32); wi = np.zeros((n, 3), np.float32)
+        alpha = np.zeros((n, A.NSPEC), np.float32); ids = np.zeros(n, np.uint64)
+        got = C.c_uint64(0)
+        self._chk(self.lib.pv_get_photons(self.ctx, _vp(pos), _vp(wi), _vp(alpha), _vp(ids), C.c_uint64(n), C.byref(got)))
+        return pos, wi, alpha, ids
+
+    def get_photons_dev(self, pos, wi, alpha, ids, capacity):
+        got = C.c_uint64(0)
+        self._chk(self.lib.pv_get_photons_dev(self.ctx, _vp(pos), _vp(wi), _vp(alpha), _vp(ids), C.c_uint64(capacity), C.byref(got)))
+        return got.value
+
+    def build(self, cell_size=0.0):
+        self._chk(self.lib.pv_build(self.ctx, C.c_float(cell_size)))
+
+    # ---- PhotonShooter::Preprocess ---------------------------------------
+    def Preprocess(self, n_volume_wanted, stepsize=0.1, max_photon_depth=5, rank=0, world=1, max_paths=0,
+                   build=True, integrator_stepsize=None):
+        prm = A.ShootParams(float(stepsize), float(self.stepsize if integrator_stepsize is None else integrator_stepsize),
+                            int(max_photon_depth), self.seed, rank, world, max_paths, 0.0)
+        st = A.ShootStats()
+        self._chk(self.lib.pv_shoot(self.ctx, C.c_uint64(n_volume_wanted), C.byref(prm), C.byref(st)))
+        if build and world == 1:
+            self.build()
+        return st
+
+    # ---- KdTree::Lookup --------------------------------------------------
+    def Lookup(self, pts, k=None, r2=None):
+        pts = _f32(pts).reshape(-1, 3); n = len(pts)
+        k = self.nused if k is None else int(k)
+        r2 = self.maxdist * self.maxdist if r2 is None else float(r2)
+        idx = np.zeros((n, k), np.uint32); d2 = np.zeros((n, k), np.float32); nf = np.zeros(n, np.uint32)
+        self._chk(self.lib.pv_knn(self.ctx, _vp(pts), C.c_uint64(n), C.c_uint32(k), C.c_float(r2), _vp(idx), _vp(d2), _vp(nf)))
+        return nf, idx, d2
+
+    def LPhoton(self, pts, w):
+        pts = _f32(pts).reshape(-1, 3); w = _f32(w).reshape(-1, 3); n = len(pts)
+        L = np.zeros((n, A.NSPEC), np.float32)
+        self._chk(self.lib.pv_lphoton(self.ctx, _vp(pts), _vp(w), C.c_uint64(n), C.c_uint32(self.nused), C.c_float(self.maxdist), _vp(L)))
+        return L
+
+    # ---- Scene::Intersect / IntersectP -----------------------------------
+    def Intersect(self, rays):
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        prim = np.zeros(n, np.uint32); t = np.zeros(n, np.float32)
+        self._chk(self.lib.pv_intersect(self.ctx, _vp(rays), C.c_uint64(n), _vp(prim), _vp(t)))
+        return prim, t
+
+    def IntersectP(self, rays):
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        hit = np.zeros(n, np.uint8)
+        self._chk(self.lib.pv_occluded(self.ctx, _vp(rays), C.c_uint64(n), _vp(hit)))
+        return hit
+
+    # ---- PhotonVolumeIntegrator::Transmittance / Li ------------------------
+    def Transmittance(self, rays, offset_u, step=None):
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        u = _f32(offset_u)
+        T = np.zeros((n, A.NSPEC), np.float32)
+        step = 4.0 * self.stepsize if step is None else float(step)   # sample == NULL branch, photonvolume.cpp:24-27
+        self._chk(self.lib.pv_transmittance(self.ctx, _vp(rays), C.c_uint64(n), C.c_float(step), _vp(u), _vp(T)))
+        return T
+
+    def gather_params(self, ray_index_base=0, flags=0):
+        return A.GatherParams(self.stepsize, self.nused, self.maxdist, self.seed, ray_index_base, flags)
+
+    def Li(self, rays, ray_index_base=0, flags=0):
+        """Host buffers in, host buffers out (copies inside)."""
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        L = np.zeros((n, A.NSPEC), np.float32); T = np.zeros((n, A.NSPEC), np.float32)
+        prm = self.gather_params(ray_index_base, flags)
+        self._chk(self.lib.pv_gather(self.ctx, _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
+        return L, T
+
+    def Li_into(self, rays, n, L, T, ray_index_base=0, flags=0):
+        """Host pointers (e.g. pinned torch tensors / numpy) -- no allocation."""
+        prm = self.gather_params(ray_index_base, flags)
+        self._chk(self.lib.pv_gather(self.ctx, _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
+
+    def Li_dev(self, rays, n, L, T, ray_index_base=0, flags=0):
+        """Device pointers (torch CUDA tensors or ints)."""
+        prm = self.gather_params(ray_index_base, flags)
+        self._chk(self.lib.pv_gather_dev(self.ctx, _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
+
+    def gather_stats(self, reset=False):
+        st = A.GatherStats()
+        self._chk(self.lib.pv_gather_stats_get(self.ctx, C.byref(st), C.c_int(1 if reset else 0)))
+        return st
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        self._chk(self.lib.pv_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def stream(self):
+        return self.lib.pv_stream(self.ctx)

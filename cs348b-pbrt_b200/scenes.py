@@ -1,0 +1,105 @@
+"""Synthetic workloads named by BASELINE.json configs 2, 3 and 5.
+
+The geometry/light/medium SPECTRA of these scenes come from the reference's own
+RGB->spectrum conversion, so they are exported once by oracle/ref_harness
+(--export-scene) into tests/golden/*.scn; this module only adds what is closed
+form: the density grid, the camera rays and the synthetic photon sets.
+"""
+import numpy as np
+
+CORNELL_TEMPLATE = """# {title}
+Film "image" "string filename" "{outfile}"
+ "integer xresolution" [{xres}] "integer yresolution" [{yres}]
+Sampler "lowdiscrepancy" "integer pixelsamples" [1]
+PixelFilter "box"
+SurfaceIntegrator "photonmap" "integer nused" [50] "bool finalgather" ["false"]
+  "float maxdist" [.1] "integer indirectphotons" [0] "integer causticphotons" [0]
+  "float stepsize" [{shoot_step}] "integer maxphotondepth" [5]
+VolumeIntegrator "photonvolume" "float stepsize" [{stepsize}] "integer nused" [{nused}] "float maxdist" [{maxdist}]
+  "integer volumephotons" [{nphotons}]
+LookAt 0 0 -3.4  0 0 0  0 1 0
+Camera "perspective" "float fov" [40]
+WorldBegin
+{volume}
+LightSource "point" "point from" [0 0.8 0] "color I" [20 20 20]
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -1  1 -1 -1  1 -1 1  -1 -1 1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 1 -1  1 1 -1  1 1 1  -1 1 1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 1  1 -1 1  1 1 1  -1 1 1]
+Material "matte" "color Kd" [.6 .1 .1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -1  -1 -1 1  -1 1 1  -1 1 -1]
+Material "matte" "color Kd" [.1 .6 .1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [1 -1 -1  1 -1 1  1 1 1  1 1 -1]
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -4  1 -1 -4  1 1 -4  -1 1 -4]
+WorldEnd
+"""
+
+HOMOG_VOLUME = ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s" [.15 .15 .15] "float g" [0]\n'
+                '  "point p0" [-1 -1 -1] "point p1" [1 1 1]')
+
+
+def blob_density(n, seed=348, nblobs=8, floor=0.05):
+    """Config-3 density: 8 seeded Gaussian blobs + floor, float32, index z*n*n + y*n + x
+    (volumes/volumegrid.h:64).  Evaluated at voxel centres of [-1,1]^3."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(-0.7, 0.7, size=(nblobs, 3)).astype(np.float32)
+    widths = rng.uniform(0.15, 0.4, size=nblobs).astype(np.float32)
+    amps = rng.uniform(0.5, 1.5, size=nblobs).astype(np.float32)
+    c = ((np.arange(n, dtype=np.float32) + np.float32(0.5)) / np.float32(n)) * np.float32(2) - np.float32(1)
+    out = np.full((n, n, n), np.float32(floor), dtype=np.float32)       # [z, y, x]
+    for b in range(nblobs):
+        dz = (c - centres[b, 2])[:, None, None]; dy = (c - centres[b, 1])[None, :, None]; dx = (c - centres[b, 0])[None, None, :]
+        r2 = (dx * dx + dy * dy + dz * dz).astype(np.float32)
+        out += (amps[b] * np.exp(-r2 / (np.float32(2) * widths[b] * widths[b]))).astype(np.float32)
+    return np.ascontiguousarray(out.reshape(-1), dtype=np.float32)
+
+
+def grid_volume_text(n, density, sigma_a=1.0, sigma_s=2.0, g=0.3):
+    vals = " ".join("%.9g" % v for v in density)
+    return ('Volume "volumegrid" "color sigma_a" [%g %g %g] "color sigma_s" [%g %g %g] "float g" [%g]\n'
+            '  "point p0" [-1 -1 -1] "point p1" [1 1 1] "integer nx" [%d] "integer ny" [%d] "integer nz" [%d]\n'
+            '  "float density" [%s]' % (sigma_a, sigma_a, sigma_a, sigma_s, sigma_s, sigma_s, g, n, n, n, vals))
+
+
+def cornell_pbrt(volume_text, nphotons, xres=64, yres=64, stepsize=0.05, nused=50, maxdist=0.25, shoot_step=0.05,
+                 outfile="cornell_vol.pfm", title="synthetic Cornell box (SURVEY.md Appendix C)"):
+    return CORNELL_TEMPLATE.format(title=title, outfile=outfile, xres=xres, yres=yres, shoot_step=shoot_step,
+                                   stepsize=stepsize, nused=nused, maxdist=maxdist, nphotons=nphotons, volume=volume_text)
+
+
+def camera_rays(xres, yres, fov_deg=40.0, eye=(0.0, 0.0, -3.4), look=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0),
+                u_scatter=0.5, y0=0, y1=None):
+    """Pinhole rays through pixel centres (fov spans the shorter image axis, like
+    cameras/perspective.cpp).  Rows y0..y1 only, row-major."""
+    from .sceneio import make_rays
+    y1 = yres if y1 is None else y1
+    eye = np.asarray(eye, np.float64); look = np.asarray(look, np.float64); upv = np.asarray(up, np.float64)
+    fwd = look - eye; fwd /= np.linalg.norm(fwd)
+    right = np.cross(upv / np.linalg.norm(upv), fwd); right /= np.linalg.norm(right)
+    upn = np.cross(fwd, right)
+    aspect = xres / yres
+    t = np.tan(np.radians(fov_deg) / 2)
+    sx, sy = (aspect, 1.0) if aspect > 1 else (1.0, 1.0 / aspect)
+    px = ((np.arange(xres) + 0.5) / xres * 2 - 1) * sx * t
+    py = (1 - (np.arange(y0, y1) + 0.5) / yres * 2) * sy * t
+    X, Y = np.meshgrid(px, py)
+    d = X[..., None] * right + Y[..., None] * upn + fwd
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    d = d.reshape(-1, 3).astype(np.float32)
+    o = np.broadcast_to(eye.astype(np.float32), d.shape)
+    return make_rays(o, d, 0.0, np.inf, 0.0, u_scatter)
+
+
+def synthetic_photons(n, seed=0x5EED, lo=-1.0, hi=1.0):
+    """Kernel-isolated photon set: positions uniform in the medium box,
+    wi uniform on the sphere, alpha a gently coloured spectrum of total weight ~1/n."""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    z = rng.uniform(-1, 1, size=n); phi = rng.uniform(0, 2 * np.pi, size=n)
+    r = np.sqrt(np.maximum(0, 1 - z * z))
+    wi = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(np.float32)
+    base = (1.0 + 0.01 * np.arange(30, dtype=np.float32))[None, :]
+    scale = rng.uniform(0.5, 1.5, size=(n, 1)).astype(np.float32)
+    alpha = (base * scale / np.float32(n)).astype(np.float32)
+    return pos, wi, alpha

@@ -1,0 +1,220 @@
+/* pv.h -- C ABI of the B200-native volumetric photon-mapping path.
+ *
+ * This is the drop-in boundary for the hot path of piwell/CS348B-pbrt (a pbrt-v2
+ * fork): photon shooting (core/photonshooter.cpp:47-357), the photon map
+ * (core/kdtree.h:99-183) and the per-camera-ray gather
+ * (integrators/photonvolume.cpp:15-222).  The reference has no FFI; the host
+ * adapter classes that keep the PhotonShooter / PhotonVolumeIntegrator C++
+ * signatures (core/photonshooter.h:81-116, integrators/photonvolume.h:14-38)
+ * call exactly these entry points.
+ *
+ * Conventions
+ *  - plain C types, host pointers unless the name ends in _dev (then the
+ *    pointers are CUDA device addresses on the context's device);
+ *  - every call returns 0 on success or a negative PV_E* code; the message is
+ *    available from pv_last_error(); nothing throws;
+ *  - a pv_ctx owns all device memory; calls on one ctx are serialised by an
+ *    internal mutex (the reference calls Li/Transmittance from N pthreads,
+ *    core/parallel.cpp:728-737);
+ *  - there is NO CPU fallback: without a CUDA device pv_create fails.
+ *  - spectra are the reference's 30-bin SampledSpectrum coefficients
+ *    (core/spectrum.h:44-46), WITHOUT the fork's lambda/intensity members.
+ */
+#ifndef PV_H
+#define PV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_NSPEC 30
+
+#define PV_OK          0
+#define PV_EINVAL     -1   /* bad argument / missing scene or map            */
+#define PV_ECUDA      -2   /* CUDA runtime error (message has the detail)    */
+#define PV_ENOMEM     -3
+#define PV_ESTATE     -4   /* call order: e.g. gather before build           */
+#define PV_ENOPHOTONS -5   /* reference's "Unable to store enough photons"   */
+
+typedef struct pv_ctx pv_ctx;
+
+/* accelerators/bvh.cpp:154-164 LinearBVHNode, same 32-byte layout. */
+typedef struct pv_bvh_node {
+    float    bounds[6];      /* pMin.xyz, pMax.xyz                           */
+    uint32_t offset;         /* leaf: primitivesOffset; interior: secondChildOffset */
+    uint8_t  n_primitives;   /* 0 -> interior                                */
+    uint8_t  axis;
+    uint8_t  pad[2];
+} pv_bvh_node;
+
+/* core/geometry.h:322-345 Ray (+ the scatter jitter sample->oneD[..][0] that
+ * integrators/photonvolume.cpp:135 reads). 40 bytes. */
+typedef struct pv_ray {
+    float o[3];
+    float d[3];
+    float mint, maxt;
+    float time;
+    float u_scatter;
+} pv_ray;
+
+enum { PV_LIGHT_POINT = 0, PV_LIGHT_SPOT = 1, PV_LIGHT_DISTANT = 2 };
+typedef struct pv_light {
+    int32_t type;
+    float   pos[3];                 /* point/spot lightPos (lights/point.cpp:43) */
+    float   dir[3];                 /* distant lightDir (lights/distant.cpp:43)  */
+    float   cos_total_width;        /* spot (lights/spot.cpp:45-46)              */
+    float   cos_falloff_start;
+    float   intensity[PV_NSPEC];    /* I (point/spot) or L (distant)             */
+    float   light_to_world[16];     /* row-major Matrix4x4, spot only            */
+    float   world_to_light[16];
+    float   power_y;                /* Light::Power(scene).y(), for the CDF
+                                       (core/integrator.cpp:261-268)             */
+} pv_light;
+
+enum { PV_MEDIUM_NONE = 0, PV_MEDIUM_HOMOGENEOUS = 1, PV_MEDIUM_GRID = 2,
+       PV_MEDIUM_RAINBOW = 3 };
+typedef struct pv_medium {
+    int32_t type;
+    float   world_to_volume[16];    /* row-major                                  */
+    float   p0[3], p1[3];           /* extent (volumes/homogeneous.h:87)          */
+    float   sigma_a[PV_NSPEC], sigma_s[PV_NSPEC], le[PV_NSPEC];
+    float   g;
+    int32_t nx, ny, nz;             /* grid only (volumes/volumegrid.h:66-70)     */
+    const float *density;           /* host, nx*ny*nz, index z*nx*ny + y*nx + x   */
+} pv_medium;
+
+enum { PV_MAT_MATTE = 0, PV_MAT_GLASS = 1 };
+typedef struct pv_material {
+    int32_t type;
+    float   kd[PV_NSPEC];           /* matte Kd (materials/matte.cpp:42-63), sigma==0 only */
+    float   kr[PV_NSPEC], kt[PV_NSPEC];
+    float   index, vn;              /* glass (materials/glass.cpp:42-70)          */
+} pv_material;
+
+/* Flattened scene, exported from the unchanged host objects. */
+typedef struct pv_scene_desc {
+    const pv_bvh_node *nodes;       uint32_t n_nodes;
+    const float       *tri_verts;   /* 9 floats per primitive, world space, in the
+                                       BVH's reordered primitive order            */
+    const uint32_t    *prim_material;
+    uint32_t           n_prims;
+    const pv_material *materials;   uint32_t n_materials;
+    const pv_light    *lights;      uint32_t n_lights;
+    const pv_medium   *medium;      /* NULL -> no volume region                   */
+    float              world_bound[6];
+    float              cie_y[PV_NSPEC];  /* SampledSpectrum::Y bin averages
+                                            (core/spectrum.h:368-381)             */
+} pv_scene_desc;
+
+/* PhotonVolumeIntegrator ctor params (integrators/photonvolume.h:17-20) +
+ * the counter-based RNG key that replaces the per-task MT19937 stream. */
+typedef struct pv_gather_params {
+    float    stepsize;
+    uint32_t nused;
+    float    maxdist;
+    uint64_t seed;
+    uint64_t ray_index_base;   /* global index of rays[0]; keeps RNG streams
+                                  identical however the image is sharded        */
+    uint32_t flags;            /* PV_GATHER_* */
+} pv_gather_params;
+#define PV_GATHER_NO_DIRECT   1u   /* skip the single-scattering term           */
+#define PV_GATHER_NO_INDIRECT 2u   /* skip LPhoton                               */
+
+/* PhotonShooter params (core/photonshooter.cpp:529-548), volume branch. */
+typedef struct pv_shoot_params {
+    float    stepsize;             /* shooter march step (SurfaceIntegrator "stepsize") */
+    float    integrator_stepsize;  /* PhotonVolumeIntegrator stepSize (x4 in Transmittance) */
+    int32_t  max_photon_depth;
+    uint64_t seed;
+    uint32_t rank, world;          /* emission sharding: this rank takes 4096-path
+                                      blocks b with (b-1) % world == rank          */
+    uint64_t max_paths;            /* safety cap on global light paths (0 = 2^40) */
+    float    time;                 /* camera shutterOpen                           */
+} pv_shoot_params;
+
+typedef struct pv_shoot_stats {
+    uint64_t paths;          /* global nshot when the target was met             */
+    uint64_t paths_local;    /* light paths this rank traced                     */
+    uint64_t photons_local;  /* volume photons this rank kept                    */
+    uint64_t blocks;         /* global number of 4096-path blocks used           */
+    uint64_t nodes_visited, tri_tests, density_samples, segments;
+    uint64_t stack_overflows;
+    double   seconds;        /* device time of the trace kernels                 */
+} pv_shoot_stats;
+
+typedef struct pv_gather_stats {
+    uint64_t rays, lookups, photons_found, candidates_tested, heap_lookups;
+    uint64_t shadow_rays, density_samples;
+} pv_gather_stats;
+
+/* ---- lifecycle --------------------------------------------------------- */
+int         pv_create(pv_ctx **out, int device);
+void        pv_destroy(pv_ctx *ctx);
+const char *pv_last_error(pv_ctx *ctx);          /* ctx may be NULL             */
+int         pv_version(void);
+
+/* ---- scene (replaces the const Scene* the reference passes around) ------ */
+int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *scene);
+
+/* ---- photon map: KdTree<Photon> ctor (core/kdtree.h:99-147) ------------- */
+/* Inject a photon set (golden sets, checkpoints, the allgathered map).
+ * SoA planes: pos[3n], wi[3n], alpha[30n].  Photon i keeps index i.          */
+int pv_set_photons(pv_ctx *ctx, const float *pos, const float *wi,
+                   const float *alpha, uint64_t n);
+int pv_set_photons_dev(pv_ctx *ctx, const float *pos, const float *wi,
+                       const float *alpha, uint64_t n);
+int pv_get_photons(pv_ctx *ctx, float *pos, float *wi, float *alpha,
+                   uint64_t *ids, uint64_t capacity, uint64_t *n);
+int pv_get_photons_dev(pv_ctx *ctx, float *pos, float *wi, float *alpha,
+                       uint64_t *ids, uint64_t capacity, uint64_t *n);
+int pv_photon_count(pv_ctx *ctx, uint64_t *n);
+/* Morton-sort the photons into the hashed uniform grid.  cell_size <= 0
+ * picks one from the photon density.                                        */
+int pv_build(pv_ctx *ctx, float cell_size);
+
+/* ---- KdTree::Lookup + PhotonProcess (core/kdtree.h:150-183,
+ *      core/photonshooter.h:186-203) --------------------------------------- */
+/* For each query point: the photons with dist^2 < r2, or if more than k of
+ * them the k smallest by (dist^2, photon index).  idx/d2 are n*k, ascending
+ * by (d2, idx), padded with 0xFFFFFFFF / +inf.                               */
+int pv_knn(pv_ctx *ctx, const float *pts, uint64_t n, uint32_t k, float r2,
+           uint32_t *idx, float *d2, uint32_t *nfound);
+
+/* ---- Scene::Intersect / IntersectP (accelerators/bvh.cpp:585-685,
+ *      shapes/trianglemesh.cpp:127-281) ------------------------------------ */
+/* prim = index into the BVH's reordered primitive array or 0xFFFFFFFF.      */
+int pv_intersect(pv_ctx *ctx, const pv_ray *rays, uint64_t n,
+                 uint32_t *prim, float *t);
+int pv_occluded(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint8_t *hit);
+
+/* ---- PhotonVolumeIntegrator::Transmittance (photonvolume.cpp:15-30) ----- */
+/* step is the tau() step (stepSize or 4*stepSize), offset_u[n] the jitter.  */
+int pv_transmittance(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step,
+                     const float *offset_u, float *T);
+
+/* ---- PhotonVolumeIntegrator::Li (photonvolume.cpp:112-222) -------------- */
+/* L[30n], T[30n].                                                           */
+int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n,
+              const pv_gather_params *params, float *L, float *T);
+int pv_gather_dev(pv_ctx *ctx, const pv_ray *rays, uint64_t n,
+                  const pv_gather_params *params, float *L, float *T);
+/* LPhoton only (photonvolume.cpp:65-108): pts[3n], w[3n] -> L[30n].         */
+int pv_lphoton(pv_ctx *ctx, const float *pts, const float *w, uint64_t n,
+               uint32_t nused, float maxdist, float *L);
+int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset);
+/* device time (ms) of the last gather kernel launch, CUDA events on its stream */
+int pv_last_kernel_ms(pv_ctx *ctx, float *ms);
+
+/* ---- PhotonShooter::Preprocess, volume branch (photonshooter.cpp:457-526) */
+int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted,
+             const pv_shoot_params *params, pv_shoot_stats *stats);
+
+/* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
+void *pv_stream(pv_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PV_H */

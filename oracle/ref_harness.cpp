@@ -1,0 +1,499 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Links the UNMODIFIED reference (oracle/_ref/libpbrt_ref.a, built by
+// oracle/Makefile from /root/reference) and drives its own classes to produce
+// golden vectors for the volumetric photon-mapping path:
+//   * KdTree<Photon>::Lookup + PhotonProcess      (core/kdtree.h:150-183,
+//                                                  core/photonshooter.h:186-203)
+//   * PhotonVolumeIntegrator::LPhoton / Li / Transmittance
+//                                                 (integrators/photonvolume.cpp)
+//   * Scene::Intersect / IntersectP               (accelerators/bvh.cpp:585-685)
+//   * PhotonShootingTask::Run                     (core/photonshooter.cpp:232-357)
+//   * the flattened scene the C ABI consumes      
+//
+// It reaches private members with `#define private public` and reaches the
+// file-static RenderOptions by #including the reference's core/api.cpp as part
+// of this translation unit (which therefore replaces core_api.o at link time).
+// The parser's call to pbrtWorldEnd() lands in the harness version below.
+// No reference source is copied or modified.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <map>
+#include <set>
+#include <list>
+#include <algorithm>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <memory>
+#include <typeinfo>
+#include <sys/time.h>
+
+#define private public
+#define protected public
+#define pbrtWorldEnd pbrtWorldEnd_reference
+#include "core/api.cpp"
+#undef pbrtWorldEnd
+#include "core/photonshooter.h"
+#include "core/kdtree.h"
+#include "core/parser.h"
+#include "core/scene.h"
+#include "core/light.h"
+#include "core/sampler.h"
+#include "core/camera.h"
+#include "core/intersection.h"
+#include "accelerators/bvh.h"
+#include "shapes/trianglemesh.h"
+#include "lights/point.h"
+#include "lights/spot.h"
+#include "lights/distant.h"
+#include "volumes/homogeneous.h"
+#include "volumes/volumegrid.h"
+#include "volumes/rainbow.h"
+#include "materials/matte.h"
+#include "materials/glass.h"
+#include "integrators/photonvolume.h"
+#include "renderers/samplerrenderer.h"
+#undef private
+#undef protected
+
+#include "../include/pv.h"
+
+// Layout of accelerators/bvh.cpp:154-164 (defined in the .cpp, so re-declared).
+struct LinearBVHNode {
+    BBox bounds;
+    union { uint32_t primitivesOffset; uint32_t secondChildOffset; };
+    uint8_t nPrimitives, axis, pad[2];
+};
+
+static std::vector<std::string> g_ops;
+static int g_rc = 0;
+
+static double now_s() {
+    struct timeval tv; gettimeofday(&tv, NULL);
+    return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+template <typename T> static void wr(FILE *f, const T *p, size_t n) {
+    if (n && fwrite(p, sizeof(T), n, f) != n) { perror("fwrite"); exit(3); }
+}
+template <typename T> static void rd(FILE *f, T *p, size_t n) {
+    if (n && fread(p, sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(3); }
+}
+static FILE *xopen(const std::string &fn, const char *mode) {
+    FILE *f = fopen(fn.c_str(), mode);
+    if (!f) { perror(fn.c_str()); exit(3); }
+    return f;
+}
+static uint64_t read_header(FILE *f, const char *magic) {
+    char m[8]; uint64_t n;
+    rd(f, m, 8); rd(f, &n, 1);
+    if (memcmp(m, magic, 8)) { fprintf(stderr, "bad magic, want %s\n", magic); exit(3); }
+    return n;
+}
+static void write_header(FILE *f, const char *magic, uint64_t n) {
+    wr(f, magic, 8); wr(f, &n, 1);
+}
+static void spec_out(const Spectrum &s, float *dst) {
+    memcpy(dst, s.c, sizeof(float) * nSpectralSamples);
+}
+static void mat_out(const Transform &t, float *dst, bool inverse) {
+    const Matrix4x4 &m = inverse ? t.mInv : t.m;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) dst[4*i+j] = m.m[i][j];
+}
+
+// ---------------------------------------------------------------- scene export
+static void export_scene(const Scene *scene, const std::string &fn) {
+    BVHAccel *bvh = dynamic_cast<BVHAccel *>(scene->aggregate);
+    if (!bvh) { fprintf(stderr, "aggregate is not a BVHAccel\n"); exit(4); }
+    uint32_t nPrims = bvh->primitives.size();
+    // count nodes by walking the flattened array
+    const LinearBVHNode *nodes = (const LinearBVHNode *)bvh->nodes;
+    uint32_t nNodes = 0;
+    if (nodes) {
+        // depth-first layout: the last node reachable is the max index visited
+        std::vector<uint32_t> todo; todo.push_back(0);
+        while (!todo.empty()) {
+            uint32_t i = todo.back(); todo.pop_back();
+            nNodes = std::max(nNodes, i + 1);
+            if (nodes[i].nPrimitives == 0) { todo.push_back(i + 1); todo.push_back(nodes[i].secondChildOffset); }
+        }
+    }
+    std::vector<float> tri(9 * (size_t)nPrims);
+    std::vector<uint32_t> primMat(nPrims);
+    std::vector<pv_material> mats;
+    std::map<const Material *, uint32_t> matIndex;
+    DifferentialGeometry dummy;
+    for (uint32_t i = 0; i < nPrims; ++i) {
+        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
+        if (!gp) { fprintf(stderr, "primitive %u is not a GeometricPrimitive\n", i); exit(4); }
+        const Triangle *t = dynamic_cast<const Triangle *>(gp->shape.GetPtr());
+        if (!t) { fprintf(stderr, "primitive %u is not a Triangle\n", i); exit(4); }
+        for (int k = 0; k < 3; ++k) {
+            const Point &p = t->mesh->p[t->v[k]];
+            tri[9*i + 3*k + 0] = p.x; tri[9*i + 3*k + 1] = p.y; tri[9*i + 3*k + 2] = p.z;
+        }
+        const Material *m = gp->material.GetPtr();
+        if (!matIndex.count(m)) {
+            pv_material pm; memset(&pm, 0, sizeof(pm));
+            if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
+                pm.type = PV_MAT_MATTE;
+                spec_out(mm->Kd->Evaluate(dummy).Clamp(), pm.kd);
+                if (mm->sigma->Evaluate(dummy) != 0.f) fprintf(stderr, "warning: matte sigma != 0 (OrenNayar) not exported\n");
+            } else if (const GlassMaterial *gm = dynamic_cast<const GlassMaterial *>(m)) {
+                pm.type = PV_MAT_GLASS;
+                spec_out(gm->Kr->Evaluate(dummy).Clamp(), pm.kr);
+                spec_out(gm->Kt->Evaluate(dummy).Clamp(), pm.kt);
+                pm.index = gm->index->Evaluate(dummy);
+                pm.vn = gm->Vn;
+            } else {
+                fprintf(stderr, "warning: unsupported material on prim %u, exported as black matte\n", i);
+                pm.type = PV_MAT_MATTE;
+            }
+            matIndex[m] = mats.size(); mats.push_back(pm);
+        }
+        primMat[i] = matIndex[m];
+    }
+    std::vector<pv_light> lights;
+    for (size_t i = 0; i < scene->lights.size(); ++i) {
+        pv_light pl; memset(&pl, 0, sizeof(pl));
+        Light *l = scene->lights[i];
+        mat_out(l->LightToWorld, pl.light_to_world, false);
+        mat_out(l->WorldToLight, pl.world_to_light, false);
+        pl.power_y = l->Power(scene).y();
+        if (PointLight *p = dynamic_cast<PointLight *>(l)) {
+            pl.type = PV_LIGHT_POINT;
+            pl.pos[0] = p->lightPos.x; pl.pos[1] = p->lightPos.y; pl.pos[2] = p->lightPos.z;
+            spec_out(p->Intensity, pl.intensity);
+        } else if (SpotLight *s = dynamic_cast<SpotLight *>(l)) {
+            pl.type = PV_LIGHT_SPOT;
+            pl.pos[0] = s->lightPos.x; pl.pos[1] = s->lightPos.y; pl.pos[2] = s->lightPos.z;
+            spec_out(s->Intensity, pl.intensity);
+            pl.cos_total_width = s->cosTotalWidth; pl.cos_falloff_start = s->cosFalloffStart;
+        } else if (DistantLight *d = dynamic_cast<DistantLight *>(l)) {
+            pl.type = PV_LIGHT_DISTANT;
+            pl.dir[0] = d->lightDir.x; pl.dir[1] = d->lightDir.y; pl.dir[2] = d->lightDir.z;
+            spec_out(d->L, pl.intensity);
+        } else { fprintf(stderr, "unsupported light %zu\n", i); exit(4); }
+        lights.push_back(pl);
+    }
+    FILE *f = xopen(fn, "wb");
+    wr(f, "PVSCN001", 8);
+    VolumeRegion *vr = scene->volumeRegion;
+    uint32_t hdr[8] = { nNodes, nPrims, (uint32_t)mats.size(), (uint32_t)lights.size(), vr ? 1u : 0u, 0, 0, 0 };
+    wr(f, hdr, 8);
+    const BBox &wb = scene->WorldBound();
+    float wbf[6] = { wb.pMin.x, wb.pMin.y, wb.pMin.z, wb.pMax.x, wb.pMax.y, wb.pMax.z };
+    wr(f, wbf, 6);
+    wr(f, SampledSpectrum::Y.c, nSpectralSamples);
+    wr(f, (const char *)nodes, 32 * (size_t)nNodes);
+    wr(f, tri.data(), tri.size());
+    wr(f, primMat.data(), primMat.size());
+    wr(f, mats.data(), mats.size());
+    wr(f, lights.data(), lights.size());
+    if (vr) {
+        int32_t type = 0, dims[3] = {0, 0, 0};
+        float w2v[16], p0[3], p1[3], sa[30], ss[30], le[30], g = 0;
+        const float *density = NULL;
+        // RainbowVolume derives from HomogeneousVolumeDensity: test it first.
+        if (RainbowVolume *rv = dynamic_cast<RainbowVolume *>(vr)) {
+            type = PV_MEDIUM_RAINBOW;
+            HomogeneousVolumeDensity *h = rv;
+            mat_out(h->WorldToVolume, w2v, false);
+            p0[0]=h->extent.pMin.x; p0[1]=h->extent.pMin.y; p0[2]=h->extent.pMin.z;
+            p1[0]=h->extent.pMax.x; p1[1]=h->extent.pMax.y; p1[2]=h->extent.pMax.z;
+            spec_out(h->sig_a, sa); spec_out(h->sig_s, ss); spec_out(h->le, le); g = h->g;
+        } else if (HomogeneousVolumeDensity *h = dynamic_cast<HomogeneousVolumeDensity *>(vr)) {
+            type = PV_MEDIUM_HOMOGENEOUS;
+            mat_out(h->WorldToVolume, w2v, false);
+            p0[0]=h->extent.pMin.x; p0[1]=h->extent.pMin.y; p0[2]=h->extent.pMin.z;
+            p1[0]=h->extent.pMax.x; p1[1]=h->extent.pMax.y; p1[2]=h->extent.pMax.z;
+            spec_out(h->sig_a, sa); spec_out(h->sig_s, ss); spec_out(h->le, le); g = h->g;
+        } else if (VolumeGridDensity *gd = dynamic_cast<VolumeGridDensity *>(vr)) {
+            type = PV_MEDIUM_GRID;
+            mat_out(gd->WorldToVolume, w2v, false);
+            p0[0]=gd->extent.pMin.x; p0[1]=gd->extent.pMin.y; p0[2]=gd->extent.pMin.z;
+            p1[0]=gd->extent.pMax.x; p1[1]=gd->extent.pMax.y; p1[2]=gd->extent.pMax.z;
+            spec_out(gd->sig_a, sa); spec_out(gd->sig_s, ss); spec_out(gd->le, le); g = gd->g;
+            dims[0] = gd->nx; dims[1] = gd->ny; dims[2] = gd->nz; density = gd->density;
+        } else { fprintf(stderr, "unsupported volume region\n"); exit(4); }
+        wr(f, &type, 1); wr(f, w2v, 16); wr(f, p0, 3); wr(f, p1, 3);
+        wr(f, sa, 30); wr(f, ss, 30); wr(f, le, 30); wr(f, &g, 1); wr(f, dims, 3);
+        if (density) wr(f, density, (size_t)dims[0] * dims[1] * dims[2]);
+    }
+    fclose(f);
+    fprintf(stderr, "[harness] exported scene: %u nodes, %u prims, %zu materials, %zu lights -> %s\n",
+            nNodes, nPrims, mats.size(), lights.size(), fn.c_str());
+}
+
+// ---------------------------------------------------------------- photons
+static std::vector<Photon> g_photons;       // original (merge) order
+static uint32_t g_nshot = 0;
+static double g_shoot_seconds = 0;
+
+static void stash_indices(std::vector<Photon> &v) {
+    // The fork's Spectrum carries an unused `intensity` float; park the
+    // original index there (bit pattern) so kd-tree node order can be mapped back.
+    for (uint32_t i = 0; i < v.size(); ++i) memcpy(&v[i].alpha.intensity, &i, 4);
+}
+static uint32_t photon_index(const Photon *p) {
+    uint32_t i; memcpy(&i, &p->alpha.intensity, 4); return i;
+}
+static void install_volume_map(PhotonShooter *sh) {
+    stash_indices(g_photons);
+    delete sh->volumeMap; sh->volumeMap = NULL;
+    if (g_photons.size()) sh->volumeMap = new KdTree<Photon>(g_photons);
+}
+
+// Restates only the DRIVER part of PhotonShooter::Preprocess
+// (core/photonshooter.cpp:457-503) so that nshot and the pre-kd-tree photon
+// order are observable; the tasks themselves are the reference's own.
+static void shoot(PhotonShooter *sh, const Scene *scene, const Camera *camera, const Renderer *renderer) {
+    if (scene->lights.size() == 0) return;
+    Mutex *mutex = Mutex::Create();
+    int nDirectPaths = 0;
+    vector<Photon> causticPhotons, directPhotons, indirectPhotons, volumePhotons;
+    vector<RadiancePhoton> radiancePhotons;
+    vector<Spectrum> rpReflectances, rpTransmittances;
+    bool abortTasks = false;
+    uint32_t nshot = 0;
+    Distribution1D *lightDistribution = ComputeLightSamplingCDF(scene);
+    ProgressReporter progress(sh->nCausticPhotonsWanted + sh->nIndirectPhotonsWanted + sh->nVolumePhotonsWanted, "Shooting photons");
+    vector<Task *> tasks;
+    int nTasks = NumSystemCores();
+    for (int i = 0; i < nTasks; ++i)
+        tasks.push_back(new PhotonShootingTask(i, camera ? camera->shutterOpen : 0.f, *mutex, sh, progress,
+            abortTasks, nDirectPaths, directPhotons, indirectPhotons, causticPhotons, volumePhotons,
+            radiancePhotons, rpReflectances, rpTransmittances, nshot, lightDistribution, scene, renderer));
+    double t0 = now_s();
+    EnqueueTasks(tasks);
+    WaitForAllTasks();
+    g_shoot_seconds = now_s() - t0;
+    for (size_t i = 0; i < tasks.size(); ++i) delete tasks[i];
+    Mutex::Destroy(mutex);
+    progress.Done();
+    if (causticPhotons.size()) sh->causticMap = new KdTree<Photon>(causticPhotons);
+    if (indirectPhotons.size()) sh->indirectMap = new KdTree<Photon>(indirectPhotons);
+    g_photons.swap(volumePhotons);
+    g_nshot = nshot;
+    install_volume_map(sh);
+    fprintf(stderr, "[harness] shot: nshot=%u volume=%zu caustic=%zu indirect=%zu tasks=%d seconds=%.3f\n",
+            nshot, g_photons.size(), causticPhotons.size(), indirectPhotons.size(), nTasks, g_shoot_seconds);
+}
+
+static void load_photons(const std::string &fn) {
+    FILE *f = xopen(fn, "rb");
+    uint64_t n = read_header(f, "PVPHOT01");
+    g_photons.resize(n);
+    std::vector<float> rec(36);
+    for (uint64_t i = 0; i < n; ++i) {
+        rd(f, rec.data(), 36);
+        Photon &p = g_photons[i];
+        p.p = Point(rec[0], rec[1], rec[2]);
+        p.wi = Vector(rec[3], rec[4], rec[5]);
+        p.alpha = Spectrum(0.f);
+        memcpy(p.alpha.c, &rec[6], 30 * sizeof(float));
+        p.alpha.lambda = -1.f;
+    }
+    fclose(f);
+}
+static void dump_photons(const std::string &fn) {
+    FILE *f = xopen(fn, "wb");
+    write_header(f, "PVPHOT01", g_photons.size());
+    for (size_t i = 0; i < g_photons.size(); ++i) {
+        float rec[36];
+        const Photon &p = g_photons[i];
+        rec[0] = p.p.x; rec[1] = p.p.y; rec[2] = p.p.z;
+        rec[3] = p.wi.x; rec[4] = p.wi.y; rec[5] = p.wi.z;
+        memcpy(&rec[6], p.alpha.c, 30 * sizeof(float));
+        wr(f, rec, 36);
+    }
+    fclose(f);
+}
+
+struct IdxD2 { uint32_t idx; float d2; };
+static bool idxd2_less(const IdxD2 &a, const IdxD2 &b) { return a.d2 == b.d2 ? a.idx < b.idx : a.d2 < b.d2; }
+
+static void knn(PhotonShooter *sh, const std::string &qfn, uint32_t k, float r2, const std::string &ofn) {
+    FILE *f = xopen(qfn, "rb");
+    uint64_t n = read_header(f, "PVQRY001");
+    std::vector<float> q(6 * n); rd(f, q.data(), q.size()); fclose(f);
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVKNN001", n);
+    wr(o, &k, 1);
+    std::vector<ClosePhoton> buf(k);
+    std::vector<IdxD2> res;
+    std::vector<uint32_t> idx(k); std::vector<float> d2(k);
+    double t0 = now_s();
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t nFound = 0;
+        res.clear();
+        if (sh->volumeMap) {
+            PhotonProcess proc(k, buf.data());
+            float md2 = r2;
+            sh->volumeMap->Lookup(Point(q[6*i], q[6*i+1], q[6*i+2]), proc, md2);
+            nFound = proc.nFound;
+            for (uint32_t j = 0; j < nFound; ++j) {
+                IdxD2 e = { photon_index(buf[j].photon), buf[j].distanceSquared };
+                res.push_back(e);
+            }
+            std::sort(res.begin(), res.end(), idxd2_less);
+        }
+        for (uint32_t j = 0; j < k; ++j) {
+            idx[j] = j < nFound ? res[j].idx : 0xFFFFFFFFu;
+            d2[j] = j < nFound ? res[j].d2 : INFINITY;
+        }
+        wr(o, &nFound, 1); wr(o, idx.data(), k); wr(o, d2.data(), k);
+    }
+    fprintf(stderr, "[harness] knn: %llu queries k=%u in %.3f s\n", (unsigned long long)n, k, now_s() - t0);
+    fclose(o);
+}
+
+static void lphoton(PhotonVolumeIntegrator *vi, const Scene *scene, const std::string &qfn, const std::string &ofn) {
+    FILE *f = xopen(qfn, "rb");
+    uint64_t n = read_header(f, "PVQRY001");
+    std::vector<float> q(6 * n); rd(f, q.data(), q.size()); fclose(f);
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVSPEC01", n);
+    for (uint64_t i = 0; i < n; ++i) {
+        Spectrum L = vi->LPhoton(vi->photonShooter->volumeMap, vi->nUsed, NULL,
+                                 Vector(q[6*i+3], q[6*i+4], q[6*i+5]), Point(q[6*i], q[6*i+1], q[6*i+2]),
+                                 scene->volumeRegion, vi->maxDistSquared, 0.f);
+        wr(o, L.c, 30);
+    }
+    fclose(o);
+}
+
+static std::vector<pv_ray> read_rays(const std::string &fn) {
+    FILE *f = xopen(fn, "rb");
+    uint64_t n = read_header(f, "PVRAY001");
+    std::vector<pv_ray> r(n); rd(f, r.data(), n); fclose(f);
+    return r;
+}
+static Ray to_ray(const pv_ray &r) {
+    return Ray(Point(r.o[0], r.o[1], r.o[2]), Vector(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, r.time);
+}
+
+static void intersect(const Scene *scene, const std::string &rfn, const std::string &ofn) {
+    std::vector<pv_ray> rays = read_rays(rfn);
+    BVHAccel *bvh = dynamic_cast<BVHAccel *>(scene->aggregate);
+    std::map<const Primitive *, uint32_t> index;
+    for (uint32_t i = 0; i < bvh->primitives.size(); ++i) index[bvh->primitives[i].GetPtr()] = i;
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVHIT001", rays.size());
+    for (size_t i = 0; i < rays.size(); ++i) {
+        Ray r = to_ray(rays[i]);
+        Intersection isect;
+        uint32_t prim = 0xFFFFFFFFu; float t = INFINITY;
+        if (scene->Intersect(r, &isect)) { prim = index[isect.primitive]; t = r.maxt; }
+        Ray r2 = to_ray(rays[i]);
+        uint32_t occl = scene->IntersectP(r2) ? 1 : 0;
+        wr(o, &prim, 1); wr(o, &t, 1); wr(o, &occl, 1);
+    }
+    fclose(o);
+}
+
+static void li(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
+    std::vector<pv_ray> rays = read_rays(rfn);
+    PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(ren->volumeIntegrator);
+    if (!vi) { fprintf(stderr, "volume integrator is not photonvolume\n"); exit(4); }
+    Sample *sample = new Sample(ren->sampler, ren->surfaceIntegrator, ren->volumeIntegrator, scene);
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVLI0001", rays.size());
+    MemoryArena arena;
+    double t0 = now_s();
+    for (size_t i = 0; i < rays.size(); ++i) {
+        RayDifferential r(to_ray(rays[i]));
+        RNG rng(seed + (uint32_t)i);
+        sample->oneD[vi->scatterSampleOffset][0] = rays[i].u_scatter;
+        sample->oneD[vi->tauSampleOffset][0] = 0.5f;
+        Spectrum T(1.f);
+        Spectrum L = vi->Li(scene, ren, r, sample, rng, &T, arena);
+        wr(o, L.c, 30); wr(o, T.c, 30);
+        arena.FreeAll();
+    }
+    fprintf(stderr, "[harness] li: %zu rays in %.3f s\n", rays.size(), now_s() - t0);
+    fclose(o);
+}
+
+static void transmittance(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
+    // sample == NULL branch of photonvolume.cpp:24-27: step = 4*stepSize, offset = rng.RandomFloat().
+    // The offset used is written next to T so the caller can replay it.
+    std::vector<pv_ray> rays = read_rays(rfn);
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVTR0001", rays.size());
+    MemoryArena arena;
+    for (size_t i = 0; i < rays.size(); ++i) {
+        RayDifferential r(to_ray(rays[i]));
+        RNG rng(seed + (uint32_t)i), rng2(seed + (uint32_t)i);
+        float u = rng2.RandomFloat();
+        Spectrum T = ren->volumeIntegrator->Transmittance(scene, ren, r, NULL, rng, arena);
+        wr(o, &u, 1); wr(o, T.c, 30);
+    }
+    fclose(o);
+}
+
+// ---------------------------------------------------------------- WorldEnd hook
+void pbrtWorldEnd() {
+    VERIFY_WORLD("WorldEnd");
+    Renderer *renderer = renderOptions->MakeRenderer();
+    Scene *scene = renderOptions->MakeScene();
+    SamplerRenderer *sr = dynamic_cast<SamplerRenderer *>(renderer);
+    if (!scene || !sr) { fprintf(stderr, "harness needs the sampler renderer\n"); g_rc = 4; return; }
+    PhotonShooter *sh = sr->photonShooter;
+    PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(sr->volumeIntegrator);
+    for (size_t i = 0; i < g_ops.size(); ++i) {
+        const std::string &op = g_ops[i];
+        #define ARG(k) (i + (k) < g_ops.size() ? g_ops[i + (k)] : (fprintf(stderr, "missing arg for %s\n", op.c_str()), exit(2), g_ops[0]))
+        if (op == "--export-scene") { export_scene(scene, ARG(1)); i += 1; }
+        else if (op == "--shoot") { shoot(sh, scene, sr->camera, sr); }
+        else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }
+        else if (op == "--dump-photons") { dump_photons(ARG(1)); i += 1; }
+        else if (op == "--knn") { knn(sh, ARG(1), atoi(ARG(2).c_str()), (float)atof(ARG(3).c_str()), ARG(4)); i += 4; }
+        else if (op == "--lphoton") { lphoton(vi, scene, ARG(1), ARG(2)); i += 2; }
+        else if (op == "--intersect") { intersect(scene, ARG(1), ARG(2)); i += 2; }
+        else if (op == "--li") { li(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
+        else if (op == "--transmittance") { transmittance(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
+        else if (op == "--stats") {
+            FILE *f = xopen(ARG(1), "w");
+            fprintf(f, "{\"nshot\": %u, \"volume_photons\": %zu, \"shoot_seconds\": %.6f, \"cores\": %d}\n",
+                    g_nshot, g_photons.size(), g_shoot_seconds, NumSystemCores());
+            fclose(f); i += 1;
+        }
+        else if (op == "--render") { renderer->Render(scene); }
+        else { fprintf(stderr, "unknown op %s\n", op.c_str()); g_rc = 2; }
+        #undef ARG
+    }
+    TasksCleanup();
+    // like the reference's pbrtWorldEnd (core/api.cpp:1176-1193) minus the render
+    graphicsState = GraphicsState();
+    transformCache.Clear();
+    currentApiState = STATE_OPTIONS_BLOCK;
+    for (int i = 0; i < MAX_TRANSFORMS; ++i) curTransform[i] = Transform();
+    activeTransformBits = ALL_TRANSFORMS_BITS;
+    namedCoordinateSystems.erase(namedCoordinateSystems.begin(), namedCoordinateSystems.end());
+}
+
+int main(int argc, char *argv[]) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: ref_harness scene.pbrt [--ncores N] ops...\n");
+        return 2;
+    }
+    Options options;
+    options.nCores = 1;
+    options.quiet = true;
+    std::string scene = argv[1];
+    for (int i = 2; i < argc; ++i) {
+        if (!strcmp(argv[i], "--ncores") && i + 1 < argc) options.nCores = atoi(argv[++i]);
+        else g_ops.push_back(argv[i]);
+    }
+    pbrtInit(options);
+    if (!ParseFile(scene)) { fprintf(stderr, "could not parse %s\n", scene.c_str()); return 2; }
+    pbrtCleanup();
+    return g_rc;
+}

@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz and *.scn by running the REAL reference.
+
+Needs /root/reference (this container only): builds oracle/_ref/ref_harness with
+`make -C oracle ref`, runs it single-threaded (--ncores 1 => deterministic,
+SURVEY.md 8c) and stores what it returns.  The GPU box never runs this script;
+it only reads the committed outputs.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+pkg = load_package()
+from cs348b_pbrt_b200 import sceneio, scenes  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+def run(scene_file, *ops):
+    cmd = [HARNESS, scene_file] + [str(o) for o in ops]
+    print("+", " ".join(cmd[:6]), "...")
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+
+
+def query_points(rays, stepsize, n_per_ray, lo=-1.0, hi=1.0):
+    """March points of camera rays inside the medium box (like Li's sample points)."""
+    pts, ws = [], []
+    for r in rays:
+        o, d = r["o"].astype(np.float64), r["d"].astype(np.float64)
+        with np.errstate(divide="ignore"):
+            t0 = ((lo - o) / d); t1 = ((hi - o) / d)
+        tn = np.minimum(t0, t1).max(); tf = np.maximum(t0, t1).min()
+        if tn >= tf:
+            continue
+        for k in range(n_per_ray):
+            t = tn + (k + 0.5) * (tf - tn) / n_per_ray
+            pts.append(o + d * t); ws.append(-d)
+    return np.asarray(pts, np.float32), np.asarray(ws, np.float32)
+
+
+def aggregate_test_rays(n, seed, bound=(-1.2, 1.2)):
+    """Ray set in the spirit of renderers/aggregatetest.cpp:61-119: random origins, sphere-uniform and
+    axis-aligned directions, finite and infinite extents."""
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(bound[0], bound[1], size=(n, 3)).astype(np.float32)
+    z = rng.uniform(-1, 1, size=n); phi = rng.uniform(0, 2 * np.pi, size=n); r = np.sqrt(1 - z * z)
+    d = np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1).astype(np.float32)
+    axis = rng.integers(0, 3, size=n); sign = rng.choice([-1.0, 1.0], size=n)
+    ax = rng.random(n) < 0.15
+    d[ax] = 0; d[ax, axis[ax]] = sign[ax]
+    d *= rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)          # non-unit directions too
+    rays = sceneio.make_rays(o, d, 0.0, np.inf)
+    fin = rng.random(n) < 0.3
+    rays["maxt"][fin] = rng.uniform(0.1, 2.0, size=fin.sum()).astype(np.float32)
+    rays["mint"][rng.random(n) < 0.2] = np.float32(1e-3)
+    # some rays start exactly on a wall
+    on = rng.random(n) < 0.1
+    rays["o"][on, 1] = np.float32(-1.0)
+    return rays
+
+
+def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays, li_res, knn_k_list):
+    out = {}
+    scn = os.path.join(HERE, name + ".scn")
+    pho = os.path.join(tmp, name + ".pho")
+    stats = os.path.join(tmp, name + ".json")
+    run(scene_file, "--export-scene", scn, "--shoot", "--dump-photons", pho, "--stats", stats)
+    pos, wi, alpha = sceneio.read_photons(pho)
+    st = json.load(open(stats))
+    out["shot_pos"], out["shot_wi"], out["shot_alpha"] = pos, wi, alpha
+    out["nshot"] = np.array([st["nshot"]], np.uint64)
+    print("  %s: %d photons from %d paths" % (name, len(pos), st["nshot"]))
+
+    # camera rays (+ jittered scatter sample) and query points along them
+    rays = scenes.camera_rays(li_res, li_res)
+    rng = np.random.default_rng(7)
+    sel = rng.choice(len(rays), size=n_li_rays, replace=False)
+    rays = rays[np.sort(sel)]
+    rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
+    rays["u_scatter"][:8] = np.float32(0.5)
+    out["li_rays"] = rays
+    pts, ws = query_points(rays[::4], stepsize, 6)
+    out["q_pts"], out["q_w"] = pts, ws
+
+    rf = os.path.join(tmp, "rays.bin"); qf = os.path.join(tmp, "q.bin")
+    sceneio.write_rays(rf, rays); sceneio.write_queries(qf, pts, ws)
+    ops = ["--load-photons", pho]
+    for k, r2 in knn_k_list:
+        ops += ["--knn", qf, k, repr(float(np.float32(r2))), os.path.join(tmp, "knn_%d.bin" % k)]
+    ops += ["--lphoton", qf, os.path.join(tmp, "lph.bin"), "--li", rf, 1000, os.path.join(tmp, "li.bin"),
+            "--transmittance", rf, 77, os.path.join(tmp, "tr.bin")]
+    run(scene_file, *ops)
+    for k, r2 in knn_k_list:
+        nf, idx, d2 = sceneio.read_knn(os.path.join(tmp, "knn_%d.bin" % k))
+        out["knn%d_nfound" % k], out["knn%d_idx" % k], out["knn%d_d2" % k] = nf, idx, d2
+        out["knn%d_r2" % k] = np.array([r2], np.float32)
+    out["lphoton_L"] = sceneio.read_spectra(os.path.join(tmp, "lph.bin"), b"PVSPEC01")[:, 0]
+    li = sceneio.read_spectra(os.path.join(tmp, "li.bin"), b"PVLI0001", per=2)
+    out["li_L"], out["li_T"] = li[:, 0], li[:, 1]
+    with open(os.path.join(tmp, "tr.bin"), "rb") as f:
+        buf = f.read()
+    n = len(rays)
+    tr = np.frombuffer(buf, np.float32, count=n * 31, offset=16).reshape(n, 31)
+    out["tr_u"], out["tr_T"] = tr[:, 0].copy(), tr[:, 1:].copy()
+    out["params"] = np.array([nused, maxdist, stepsize], np.float64)
+
+    # BVH hit ids
+    arays = aggregate_test_rays(3000, 11)
+    af = os.path.join(tmp, "arays.bin"); sceneio.write_rays(af, arays)
+    run(scene_file, "--intersect", af, os.path.join(tmp, "hits.bin"))
+    prim, t, occ = sceneio.read_hits(os.path.join(tmp, "hits.bin"))
+    out["hit_rays"], out["hit_prim"], out["hit_t"], out["hit_occluded"] = arays, prim, t, occ
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return out
+
+
+def golden_synthetic_knn(tmp, scene_file):
+    """Kernel-isolated k-NN / LPhoton golden on a uniform synthetic photon set."""
+    n = 20000
+    pos, wi, alpha = scenes.synthetic_photons(n)
+    pho = os.path.join(tmp, "syn.pho"); sceneio.write_photons(pho, pos, wi, alpha)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1.05, 1.05, size=(600, 3)).astype(np.float32)
+    pts[:16] = pos[:16]                      # queries sitting exactly on photons (d2 == 0)
+    w = np.tile(np.array([[0, 0, -1]], np.float32), (len(pts), 1))
+    qf = os.path.join(tmp, "synq.bin"); sceneio.write_queries(qf, pts, w)
+    out = dict(pos=pos, wi=wi, q_pts=pts)
+    ops = ["--load-photons", pho]
+    cases = [(50, 0.25 ** 2), (8, 0.05 ** 2), (300, 0.5 ** 2), (64, 0.08 ** 2), (1, 1.0)]
+    for k, r2 in cases:
+        ops += ["--knn", qf, k, repr(float(np.float32(r2))), os.path.join(tmp, "synknn_%d.bin" % k)]
+    run(scene_file, *ops)
+    for k, r2 in cases:
+        nf, idx, d2 = sceneio.read_knn(os.path.join(tmp, "synknn_%d.bin" % k))
+        out["knn%d_nfound" % k], out["knn%d_idx" % k], out["knn%d_d2" % k] = nf, idx, d2
+        out["knn%d_r2" % k] = np.array([r2], np.float32)
+    np.savez_compressed(os.path.join(HERE, "synthetic_knn.npz"), **out)
+
+
+def main():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+    with tempfile.TemporaryDirectory() as tmp:
+        homog = os.path.join(tmp, "cornell_homog.pbrt")
+        open(homog, "w").write(scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 6000))
+        golden_for_scene(tmp, "cornell_homog", homog, 50, 0.25, 0.05, 96, 64, [(50, 0.25 ** 2), (16, 0.1 ** 2)])
+        golden_synthetic_knn(tmp, homog)
+
+        n = 32
+        dens = scenes.blob_density(n)
+        grid = os.path.join(tmp, "cornell_grid.pbrt")
+        open(grid, "w").write(scenes.cornell_pbrt(scenes.grid_volume_text(n, dens), 2500, stepsize=0.0625, nused=50,
+                                                  maxdist=0.25, shoot_step=0.05))
+        golden_for_scene(tmp, "cornell_grid32", grid, 50, 0.25, 0.0625, 64, 64, [(50, 0.25 ** 2)])
+        g = sceneio.read_scene(os.path.join(HERE, "cornell_grid32.scn"))
+        assert np.array_equal(g.density, dens), "density grid did not survive the text round trip"
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+"""ctypes binding of oracle/_ref/libpv_oracle.so -- the CPU checker.
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package never
+imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+pkg = load_package()
+A = pkg._abi
+
+_LIB = None
+PHILOX, MT = 0, 1
+
+
+class Photons(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("pos", C.POINTER(C.c_float)), ("wi", C.POINTER(C.c_float)),
+                ("alpha", C.POINTER(C.c_float)), ("ids", C.POINTER(C.c_uint64)), ("nshot", C.c_uint64),
+                ("blocks", C.c_uint64), ("nodes_visited", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("density_samples", C.c_uint64), ("segments", C.c_uint64)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(ROOT, "oracle", "_ref", "libpv_oracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.pvo_kdtree_build.restype = C.c_void_p
+        L.pvo_kdtree_build.argtypes = [C.c_void_p, C.c_uint64]
+        L.pvo_kdtree_free.argtypes = [C.c_void_p]
+        L.pvo_spectrum_y.restype = C.c_float
+        L.pvo_van_der_corput.restype = C.c_float
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class KdTree:
+    def __init__(self, pos):
+        self.pos = f32(pos).reshape(-1, 3)
+        self.h = lib().pvo_kdtree_build(_p(self.pos), C.c_uint64(len(self.pos)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().pvo_kdtree_free(C.c_void_p(self.h)); self.h = None
+
+    def knn(self, pts, k, r2):
+        pts = f32(pts).reshape(-1, 3); n = len(pts)
+        idx = np.zeros((n, k), np.uint32); d2 = np.zeros((n, k), np.float32); nf = np.zeros(n, np.uint32)
+        ties = C.c_uint64(0)
+        lib().pvo_knn(C.c_void_p(self.h), _p(pts), C.c_uint64(n), C.c_uint32(k), C.c_float(r2), _p(idx), _p(d2), _p(nf), C.byref(ties))
+        return nf, idx, d2, ties.value
+
+
+def knn_brute(pos, pts, k, r2):
+    pos = f32(pos).reshape(-1, 3); pts = f32(pts).reshape(-1, 3); n = len(pts)
+    idx = np.zeros((n, k), np.uint32); d2 = np.zeros((n, k), np.float32); nf = np.zeros(n, np.uint32)
+    lib().pvo_knn_brute(_p(pos), C.c_uint64(len(pos)), _p(pts), C.c_uint64(n), C.c_uint32(k), C.c_float(r2), _p(idx), _p(d2), _p(nf))
+    return nf, idx, d2
+
+
+def lphoton(scene, tree, wi, alpha, pts, w, nused, maxdist):
+    pts = f32(pts).reshape(-1, 3); w = f32(w).reshape(-1, 3); n = len(pts)
+    wi = f32(wi); alpha = f32(alpha)
+    L = np.zeros((n, A.NSPEC), np.float32)
+    d = scene.desc()
+    lib().pvo_lphoton(C.byref(d), C.c_void_p(tree.h), _p(wi), _p(alpha), _p(pts), _p(w), C.c_uint64(n), C.c_uint32(nused), C.c_float(maxdist), _p(L))
+    return L
+
+
+def intersect(scene, rays):
+    n = len(rays); rays = np.ascontiguousarray(rays)
+    prim = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); occ = np.zeros(n, np.uint8)
+    d = scene.desc()
+    lib().pvo_intersect(C.byref(d), _p(rays), C.c_uint64(n), _p(prim), _p(t))
+    lib().pvo_occluded(C.byref(d), _p(rays), C.c_uint64(n), _p(occ))
+    return prim, t, occ
+
+
+def transmittance(scene, rays, step, offset_u):
+    n = len(rays); rays = np.ascontiguousarray(rays); u = f32(offset_u)
+    T = np.zeros((n, A.NSPEC), np.float32)
+    d = scene.desc()
+    lib().pvo_transmittance(C.byref(d), _p(rays), C.c_uint64(n), C.c_float(step), _p(u), _p(T))
+    return T
+
+
+def gather(scene, tree, wi, alpha, rays, stepsize, nused, maxdist, seed=0, ray_index_base=0, flags=0,
+           rng_mode=PHILOX, mt_seed=0, nthreads=1):
+    n = len(rays); rays = np.ascontiguousarray(rays)
+    wi = f32(wi); alpha = f32(alpha)
+    L = np.zeros((n, A.NSPEC), np.float32); T = np.zeros((n, A.NSPEC), np.float32)
+    prm = A.GatherParams(stepsize, nused, maxdist, seed, ray_index_base, flags)
+    st = A.GatherStats()
+    d = scene.desc()
+    lib().pvo_gather(C.byref(d), C.c_void_p(tree.h if tree is not None else None), _p(wi), _p(alpha), _p(rays), C.c_uint64(n),
+                     C.byref(prm), C.c_int(rng_mode), C.c_uint32(mt_seed), C.c_int(nthreads), _p(L), _p(T), C.byref(st))
+    return L, T, st
+
+
+def shoot(scene, n_wanted, stepsize, integrator_stepsize, max_photon_depth=5, seed=0, rng_mode=PHILOX, nthreads=1,
+          max_paths=0):
+    prm = A.ShootParams(stepsize, integrator_stepsize, max_photon_depth, seed, 0, 1, max_paths, 0.0)
+    out = Photons()
+    d = scene.desc()
+    rc = lib().pvo_shoot(C.byref(d), C.c_uint64(n_wanted), C.byref(prm), C.c_int(rng_mode), C.c_int(nthreads), C.byref(out))
+    n = out.n
+    res = dict(rc=rc, n=n, nshot=out.nshot, blocks=out.blocks, nodes_visited=out.nodes_visited, tri_tests=out.tri_tests,
+               density_samples=out.density_samples, segments=out.segments)
+    if n:
+        res["pos"] = np.ctypeslib.as_array(out.pos, shape=(n, 3)).copy()
+        res["wi"] = np.ctypeslib.as_array(out.wi, shape=(n, 3)).copy()
+        res["alpha"] = np.ctypeslib.as_array(out.alpha, shape=(n, A.NSPEC)).copy()
+        res["ids"] = np.ctypeslib.as_array(out.ids, shape=(n,)).copy()
+    else:
+        res["pos"] = np.zeros((0, 3), np.float32); res["wi"] = np.zeros((0, 3), np.float32)
+        res["alpha"] = np.zeros((0, A.NSPEC), np.float32); res["ids"] = np.zeros(0, np.uint64)
+    lib().pvo_photons_free(C.byref(out))
+    return res
