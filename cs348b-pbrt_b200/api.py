@@ -120,8 +120,10 @@ class PhotonVolume:
         self._chk(self.lib.pv_get_photons_dev(self.ctx, _vp(pos), _vp(wi), _vp(alpha), _vp(ids), C.c_uint64(capacity), C.byref(got)))
         return got.value
 
-    def build(self, cell_size=0.0):
-        self._chk(self.lib.pv_build(self.ctx, C.c_float(cell_size)))
+    def build(self, maxdist=None, nused=None):
+        maxdist = self.maxdist if maxdist is None else float(maxdist)
+        nused = self.nused if nused is None else int(nused)
+        self._chk(self.lib.pv_build(self.ctx, C.c_float(maxdist), C.c_uint32(nused)))
 
     # ---- PhotonShooter::Preprocess ---------------------------------------
     def Preprocess(self, n_volume_wanted, stepsize=0.1, max_photon_depth=5, rank=0, world=1, max_paths=0,

@@ -1,0 +1,380 @@
+// pv_api.cu -- the extern "C" layer of include/pv.h: argument checks, host<->device staging,
+// context lifetime.  No arithmetic of the path lives here.
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include "pv_ctx.h"
+
+static thread_local std::string g_err;
+
+int pv_ensure(pv_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *p) return PV_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e); *p = nullptr; return PV_ENOMEM; }
+    *cap = want;
+    return PV_OK;
+}
+
+#define LOCK(ctx) if (!(ctx)) { g_err = "null context"; return PV_EINVAL; } std::lock_guard<std::mutex> lock__((ctx)->mu); \
+    { cudaError_t e__ = cudaSetDevice((ctx)->device); if (e__ != cudaSuccess) { (ctx)->err = cudaGetErrorString(e__); return PV_ECUDA; } }
+
+extern "C" {
+
+int pv_version(void) { return 100; }
+
+const char *pv_last_error(pv_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int pv_create(pv_ctx **out, int device) {
+    if (!out) { g_err = "pv_create: null out"; return PV_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_err = std::string("pv_create: no CUDA device (") + cudaGetErrorString(e) + "); this path has no CPU fallback";
+        return PV_ECUDA;
+    }
+    if (device < 0 || device >= ndev) { g_err = "pv_create: bad device index"; return PV_EINVAL; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return PV_ECUDA; }
+    pv_ctx *ctx = new pv_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dscene, sizeof(DevScene)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->d_stats, sizeof(pv_gather_stats)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->d_counters, 64 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->d_stats, 0, sizeof(pv_gather_stats)) == cudaSuccess;
+    if (!ok) { g_err = std::string("pv_create: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return PV_ECUDA; }
+    *out = ctx;
+    return PV_OK;
+}
+
+void pv_destroy(pv_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_pos, ctx->d_wi,
+                    ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
+                    ctx->d_stats, ctx->d_counters};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void *pv_stream(pv_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+static int upload(pv_ctx *ctx, void **dst, const void *src, size_t bytes) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (!bytes) return PV_OK;
+    PV_CUDA_CHECK(ctx, cudaMalloc(dst, bytes));
+    PV_CUDA_CHECK(ctx, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return PV_OK;
+}
+
+int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
+    LOCK(ctx);
+    if (!s) { ctx->err = "pv_set_scene: null scene"; return PV_EINVAL; }
+    if (s->n_lights > PV_MAX_LIGHTS) { ctx->err = "pv_set_scene: more than 16 lights"; return PV_EINVAL; }
+    if (s->n_prims && (!s->tri_verts || !s->prim_material || !s->materials)) { ctx->err = "pv_set_scene: null geometry arrays"; return PV_EINVAL; }
+    for (uint32_t i = 0; i < s->n_prims; ++i)
+        if (s->prim_material[i] >= s->n_materials) { ctx->err = "pv_set_scene: material index out of range"; return PV_EINVAL; }
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_scene = false; ctx->built = false;
+    int rc;
+    if ((rc = upload(ctx, &ctx->d_nodes, s->nodes, sizeof(pv_bvh_node) * (size_t)s->n_nodes))) return rc;
+    if ((rc = upload(ctx, &ctx->d_tri, s->tri_verts, sizeof(float) * 9 * (size_t)s->n_prims))) return rc;
+    if ((rc = upload(ctx, &ctx->d_prim_mat, s->prim_material, sizeof(uint32_t) * (size_t)s->n_prims))) return rc;
+    if ((rc = upload(ctx, &ctx->d_mats, s->materials, sizeof(pv_material) * (size_t)s->n_materials))) return rc;
+    if ((rc = upload(ctx, &ctx->d_lights, s->lights, sizeof(pv_light) * (size_t)s->n_lights))) return rc;
+    DevScene &h = ctx->hscene;
+    memset(&h, 0, sizeof(h));
+    h.nodes = (const pv_bvh_node *)ctx->d_nodes; h.n_nodes = s->n_nodes;
+    h.tri = (const float *)ctx->d_tri; h.prim_mat = (const uint32_t *)ctx->d_prim_mat; h.n_prims = s->n_prims;
+    h.mats = (const pv_material *)ctx->d_mats; h.n_mats = s->n_materials;
+    h.lights = (const pv_light *)ctx->d_lights; h.n_lights = s->n_lights;
+    memcpy(h.world_bound, s->world_bound, sizeof(h.world_bound));
+    memcpy(h.cie_y, s->cie_y, sizeof(h.cie_y));
+    if (s->medium && s->medium->type != PV_MEDIUM_NONE) {
+        const pv_medium *m = s->medium;
+        DevMedium &d = h.med;
+        d.type = m->type;
+        memcpy(d.w2v, m->world_to_volume, sizeof(d.w2v));
+        memcpy(d.p0, m->p0, sizeof(d.p0)); memcpy(d.p1, m->p1, sizeof(d.p1));
+        memcpy(d.sigma_a, m->sigma_a, sizeof(d.sigma_a)); memcpy(d.sigma_s, m->sigma_s, sizeof(d.sigma_s)); memcpy(d.le, m->le, sizeof(d.le));
+        d.g = m->g; d.nx = m->nx; d.ny = m->ny; d.nz = m->nz;
+        static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        d.identity = memcmp(d.w2v, ident, sizeof(ident)) == 0;
+        if (m->type == PV_MEDIUM_GRID) {
+            if (!m->density || m->nx < 1 || m->ny < 1 || m->nz < 1) { ctx->err = "pv_set_scene: grid medium without density"; return PV_EINVAL; }
+            if ((rc = upload(ctx, &ctx->d_density, m->density, sizeof(float) * (size_t)m->nx * m->ny * m->nz))) return rc;
+            d.density = (const float *)ctx->d_density;
+        }
+    } else h.med.type = PV_MEDIUM_NONE;
+    // light power CDF: ComputeLightSamplingCDF (core/integrator.cpp:261-268) + Distribution1D (core/montecarlo.h:55-83)
+    {
+        int n = (int)s->n_lights;
+        h.light_cdf[0] = 0.f;
+        for (int i = 0; i < n; ++i) h.light_func[i] = s->lights[i].power_y;
+        for (int i = 1; i < n + 1; ++i) h.light_cdf[i] = h.light_cdf[i - 1] + h.light_func[i - 1] / n;
+        h.light_func_int = n ? h.light_cdf[n] : 0.f;
+        if (n) {
+            if (h.light_func_int == 0.f) for (int i = 1; i < n + 1; ++i) h.light_cdf[i] = float(i) / float(n);
+            else for (int i = 1; i < n + 1; ++i) h.light_cdf[i] /= h.light_func_int;
+        }
+    }
+    PV_CUDA_CHECK(ctx, cudaMemcpy(ctx->dscene, &h, sizeof(h), cudaMemcpyHostToDevice));
+    ctx->has_scene = true;
+    return PV_OK;
+}
+
+static int reserve_photons(pv_ctx *ctx, uint64_t n) {
+    if (n <= ctx->cap_photons) return PV_OK;
+    uint64_t cap = std::max<uint64_t>(n, 1024);
+    float *np, *nw, *na; uint64_t *ni;
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&np, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&nw, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&na, cap * 32 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ni, cap * sizeof(uint64_t)));
+    if (ctx->n_photons) {
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(np, ctx->d_pos, ctx->n_photons * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(nw, ctx->d_wi, ctx->n_photons * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(na, ctx->d_alpha, ctx->n_photons * 32 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ni, ctx->d_ids, ctx->n_photons * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->d_pos) cudaFree(ctx->d_pos);
+    if (ctx->d_wi) cudaFree(ctx->d_wi);
+    if (ctx->d_alpha) cudaFree(ctx->d_alpha);
+    if (ctx->d_ids) cudaFree(ctx->d_ids);
+    ctx->d_pos = np; ctx->d_wi = nw; ctx->d_alpha = na; ctx->d_ids = ni; ctx->cap_photons = cap;
+    return PV_OK;
+}
+}  // extern "C"
+int pvi_reserve_photons(pv_ctx *ctx, uint64_t n) { return reserve_photons(ctx, n); }
+extern "C" {
+
+__global__ void iota_ids_kernel(uint64_t *ids, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = i;
+}
+// ABI planes carry 30 floats per photon; the context keeps 32 (one 128-byte line)
+__global__ void alpha_30_to_32_kernel(const float *__restrict__ a30, float *__restrict__ a32, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 32) return;
+    uint64_t ph = i >> 5; uint32_t b = (uint32_t)(i & 31);
+    a32[i] = b < PV_NSPEC ? a30[ph * PV_NSPEC + b] : 0.f;
+}
+__global__ void alpha_32_to_30_kernel(const float *__restrict__ a32, float *__restrict__ a30, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * PV_NSPEC) return;
+    uint64_t ph = i / PV_NSPEC; uint32_t b = (uint32_t)(i % PV_NSPEC);
+    a30[i] = a32[ph * 32 + b];
+}
+
+static int set_photons_impl(pv_ctx *ctx, const float *pos, const float *wi, const float *alpha, uint64_t n, cudaMemcpyKind kind) {
+    if (n && (!pos || !wi || !alpha)) { ctx->err = "pv_set_photons: null plane"; return PV_EINVAL; }
+    ctx->built = false;
+    ctx->n_photons = 0;
+    int rc = reserve_photons(ctx, n); if (rc) return rc;
+    if (n) {
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pos, pos, n * 3 * sizeof(float), kind, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_wi, wi, n * 3 * sizeof(float), kind, ctx->stream));
+        const float *a30 = alpha;
+        if (kind == cudaMemcpyHostToDevice) {
+            int rc2 = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * PV_NSPEC * sizeof(float)); if (rc2) return rc2;
+            PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io, alpha, n * PV_NSPEC * sizeof(float), kind, ctx->stream));
+            a30 = (const float *)ctx->io;
+        }
+        alpha_30_to_32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(a30, ctx->d_alpha, n);
+        iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ids, n);
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->n_photons = n;
+    return PV_OK;
+}
+int pv_set_photons(pv_ctx *ctx, const float *pos, const float *wi, const float *alpha, uint64_t n) {
+    LOCK(ctx);
+    return set_photons_impl(ctx, pos, wi, alpha, n, cudaMemcpyHostToDevice);
+}
+int pv_set_photons_dev(pv_ctx *ctx, const float *pos, const float *wi, const float *alpha, uint64_t n) {
+    LOCK(ctx);
+    return set_photons_impl(ctx, pos, wi, alpha, n, cudaMemcpyDeviceToDevice);
+}
+static int get_photons_impl(pv_ctx *ctx, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t capacity, uint64_t *n, cudaMemcpyKind kind) {
+    uint64_t m = std::min<uint64_t>(capacity, ctx->n_photons);
+    if (n) *n = m;
+    if (!m) return PV_OK;
+    if (pos) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(pos, ctx->d_pos, m * 3 * sizeof(float), kind, ctx->stream));
+    if (wi) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(wi, ctx->d_wi, m * 3 * sizeof(float), kind, ctx->stream));
+    if (alpha) {
+        if (kind == cudaMemcpyDeviceToHost) {
+            int rc2 = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, m * PV_NSPEC * sizeof(float)); if (rc2) return rc2;
+            alpha_32_to_30_kernel<<<(unsigned)((m * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_alpha, (float *)ctx->io, m);
+            PV_CUDA_CHECK(ctx, cudaMemcpyAsync(alpha, ctx->io, m * PV_NSPEC * sizeof(float), kind, ctx->stream));
+        } else {
+            alpha_32_to_30_kernel<<<(unsigned)((m * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_alpha, alpha, m);
+        }
+    }
+    if (ids) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ids, ctx->d_ids, m * sizeof(uint64_t), kind, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_get_photons(pv_ctx *ctx, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t capacity, uint64_t *n) {
+    LOCK(ctx);
+    return get_photons_impl(ctx, pos, wi, alpha, ids, capacity, n, cudaMemcpyDeviceToHost);
+}
+int pv_get_photons_dev(pv_ctx *ctx, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t capacity, uint64_t *n) {
+    LOCK(ctx);
+    return get_photons_impl(ctx, pos, wi, alpha, ids, capacity, n, cudaMemcpyDeviceToDevice);
+}
+int pv_photon_count(pv_ctx *ctx, uint64_t *n) {
+    LOCK(ctx);
+    if (!n) { ctx->err = "pv_photon_count: null out"; return PV_EINVAL; }
+    *n = ctx->n_photons;
+    return PV_OK;
+}
+int pv_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
+    LOCK(ctx);
+    return pvi_build(ctx, maxdist, nused);
+}
+
+// host-pointer staging helpers
+static int stage_in(pv_ctx *ctx, void **buf, size_t *cap, const void *src, size_t bytes) {
+    int rc = pv_ensure(ctx, buf, cap, bytes); if (rc) return rc;
+    if (bytes) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(*buf, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PV_OK;
+}
+
+int pv_knn(pv_ctx *ctx, const float *pts, uint64_t n, uint32_t k, float r2, uint32_t *idx, float *d2, uint32_t *nfound) {
+    LOCK(ctx);
+    if (n && (!pts || !idx || !d2 || !nfound)) { ctx->err = "pv_knn: null pointer"; return PV_EINVAL; }
+    if (!ctx->built) { ctx->err = "pv_knn: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (!n || !k) return PV_OK;
+    int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, pts, n * 3 * sizeof(float)); if (rc) return rc;
+    size_t ob = n * k * 8 + n * 4;
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, ob); if (rc) return rc;
+    uint32_t *d_idx = (uint32_t *)ctx->io2; float *d_d2 = (float *)(d_idx + n * k); uint32_t *d_nf = (uint32_t *)(d_d2 + n * k);
+    rc = pvi_knn(ctx, (const float *)ctx->io, n, k, r2, d_idx, d_d2, d_nf); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(idx, d_idx, n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d2, d_d2, n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(nfound, d_nf, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+int pv_lphoton(pv_ctx *ctx, const float *pts, const float *w, uint64_t n, uint32_t nused, float maxdist, float *L) {
+    LOCK(ctx);
+    if (n && (!pts || !w || !L)) { ctx->err = "pv_lphoton: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * 6 * sizeof(float)); if (rc) return rc;
+    float *d_pts = (float *)ctx->io, *d_w = d_pts + n * 3;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pts, pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_w, w, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+    rc = pvi_lphoton(ctx, d_pts, d_w, n, nused, maxdist, (float *)ctx->io2); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, ctx->io2, n * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+int pv_intersect(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint32_t *prim, float *t) {
+    LOCK(ctx);
+    if (n && (!rays || !prim || !t)) { ctx->err = "pv_intersect: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, rays, n * sizeof(pv_ray)); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, n * 8); if (rc) return rc;
+    uint32_t *d_prim = (uint32_t *)ctx->io2; float *d_t = (float *)(d_prim + n);
+    rc = pvi_intersect(ctx, (const pv_ray *)ctx->io, n, d_prim, d_t); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(prim, d_prim, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_occluded(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint8_t *hit) {
+    LOCK(ctx);
+    if (n && (!rays || !hit)) { ctx->err = "pv_occluded: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, rays, n * sizeof(pv_ray)); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, n); if (rc) return rc;
+    rc = pvi_occluded(ctx, (const pv_ray *)ctx->io, n, (uint8_t *)ctx->io2); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(hit, ctx->io2, n, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_transmittance(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step, const float *offset_u, float *T) {
+    LOCK(ctx);
+    if (n && (!rays || !T)) { ctx->err = "pv_transmittance: null pointer"; return PV_EINVAL; }
+    if (!(step > 0.f)) { ctx->err = "pv_transmittance: step must be > 0"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    size_t rb = n * sizeof(pv_ray), ub = n * sizeof(float);
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, rb + ub); if (rc) return rc;
+    pv_ray *d_rays = (pv_ray *)ctx->io; float *d_u = (float *)((char *)ctx->io + rb);
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
+    if (offset_u) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_u, offset_u, ub, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+    rc = pvi_transmittance(ctx, d_rays, n, step, offset_u ? d_u : nullptr, (float *)ctx->io2); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, ctx->io2, n * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+int pv_gather_dev(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
+    LOCK(ctx);
+    if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_gather_dev: null pointer"; return PV_EINVAL; }
+    int rc = pvi_gather(ctx, rays, n, params, L, T); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n) cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return PV_OK;
+}
+int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
+    LOCK(ctx);
+    if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_gather: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, rays, n * sizeof(pv_ray)); if (rc) return rc;
+    size_t sb = n * PV_NSPEC * sizeof(float);
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 2 * sb); if (rc) return rc;
+    float *d_L = (float *)ctx->io2, *d_T = d_L + n * PV_NSPEC;
+    rc = pvi_gather(ctx, (const pv_ray *)ctx->io, n, params, d_L, d_T); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, d_L, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, d_T, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return PV_OK;
+}
+int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset) {
+    LOCK(ctx);
+    if (!out) { ctx->err = "pv_gather_stats_get: null out"; return PV_EINVAL; }
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpy(out, ctx->d_stats, sizeof(*out), cudaMemcpyDeviceToHost));
+    if (reset) PV_CUDA_CHECK(ctx, cudaMemset(ctx->d_stats, 0, sizeof(*out)));
+    return PV_OK;
+}
+int pv_last_kernel_ms(pv_ctx *ctx, float *ms) {
+    LOCK(ctx);
+    if (!ms) { ctx->err = "pv_last_kernel_ms: null out"; return PV_EINVAL; }
+    *ms = ctx->last_ms;
+    return PV_OK;
+}
+int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted, const pv_shoot_params *params, pv_shoot_stats *stats) {
+    LOCK(ctx);
+    if (!params) { ctx->err = "pv_shoot: null params"; return PV_EINVAL; }
+    return pvi_shoot(ctx, n_volume_wanted, params, stats);
+}
+int pv_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *params, uint32_t *counts,
+                    pv_shoot_stats *stats) {
+    LOCK(ctx);
+    if (!params || (n_blocks && !counts)) { ctx->err = "pv_shoot_blocks: null pointer"; return PV_EINVAL; }
+    return pvi_shoot_blocks(ctx, first_block, n_blocks, params, counts, stats);
+}
+int pv_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
+    LOCK(ctx);
+    return pvi_shoot_finish(ctx, last_block);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// pv_ctx.h -- host-side context behind the C ABI (include/pv.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "pv_device.cuh"
+
+// Uniform grid of photon cells.  Sort key of a cell = (morton2(cy, cz) << xbits) | cx:
+// rows of cells along x are contiguous in memory (a (2s+1)-cell run of a lookup block is ONE
+// contiguous photon range), rows themselves follow a Morton (Z-order) curve over (y, z).
+struct GridParams {
+    float origin[3];
+    float h, inv_h;
+    int dims[3];
+    int xbits, yzbits;      // key bits: xbits + 2*yzbits
+    uint32_t table_size;    // number of keys (cell_start has table_size + 1 entries)
+    float margin;           // conservative slack subtracted from the guaranteed search radius
+};
+
+struct pv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+
+    // scene
+    DevScene hscene{};
+    DevScene *dscene = nullptr;
+    void *d_nodes = nullptr, *d_tri = nullptr, *d_prim_mat = nullptr, *d_mats = nullptr, *d_lights = nullptr, *d_density = nullptr;
+    bool has_scene = false;
+
+    // photons in deposit order, SoA planes: pos[3n], wi[3n], alpha[32n] (30 bins + 2 pad = one 128-byte line,
+    // so the shooter stores and the map build moves it with 128-bit accesses), ids[n]
+    float *d_pos = nullptr, *d_wi = nullptr, *d_alpha = nullptr;
+    uint64_t *d_ids = nullptr;
+    uint64_t n_photons = 0, cap_photons = 0;
+
+    // the map: photons sorted by cell key
+    float4 *m_pos4 = nullptr;      // x, y, z, original index (bits)
+    float4 *m_wi4 = nullptr;       // wi.xyz, 0
+    float *m_alpha32 = nullptr;    // 32 floats per photon: alpha[30], 0, 0  (one 128-byte line)
+    uint32_t *cell_start = nullptr;
+    uint64_t map_cap = 0; uint32_t table_cap = 0;
+    GridParams grid{};
+    bool built = false;
+
+    // scratch for sort / staging
+    void *scratch = nullptr; size_t scratch_bytes = 0;
+    void *io = nullptr; size_t io_bytes = 0;       // device staging for host-pointer entry points
+    void *io2 = nullptr; size_t io2_bytes = 0;
+
+    pv_gather_stats *d_stats = nullptr;
+    unsigned long long *d_counters = nullptr;      // work-distribution counters
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int sm_count = 148;
+};
+
+#define PV_CUDA_CHECK(ctx, call)                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return PV_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+int pv_ensure(pv_ctx *ctx, void **p, size_t *cap, size_t bytes);
+
+// pv_build.cu
+int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused);
+int pvi_sort_pairs_u32(pv_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int key_bits,
+                       uint32_t **keys_out, uint32_t **vals_out);
+int pvi_sort_pairs_u64(pv_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int key_bits,
+                       uint64_t **keys_out, uint32_t **vals_out);
+// pv_gather.cu
+int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, uint32_t *d_idx, float *d_d2, uint32_t *d_nfound);
+int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L);
+int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T);
+// pv_trace.cu
+int pvi_intersect(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint32_t *d_prim, float *d_t);
+int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit);
+int pvi_transmittance(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, const float *d_u, float *d_T);
+// pv_api.cu
+int pvi_reserve_photons(pv_ctx *ctx, uint64_t n);
+// pv_shoot.cu
+int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats);
+int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block);
+int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm, pv_shoot_stats *stats);

@@ -1,0 +1,613 @@
+// pv_gather.cu -- the per-camera-ray gather (K5): PhotonVolumeIntegrator::Li
+// (integrators/photonvolume.cpp:112-222) with LPhoton (:65-108), KdTree::Lookup
+// (core/kdtree.h:150-183) and PhotonProcess (core/photonshooter.h:186-203) fused into one
+// persistent sm_100a kernel.
+//
+// Mapping: ONE WARP PER RAY.
+//  * spectral math runs with lane == spectral bin (30 of 32 lanes busy, one register per spectrum);
+//  * the per-step scalar work of 32 consecutive march steps (positions, density taps, shadow rays through
+//    the LinearBVHNode array, shadow-ray optical depth, Philox draws) runs with lane == step;
+//  * a lookup scans the photons of the (2s+1)^3 cell block around the query with lane == candidate:
+//    128-bit loads of {x,y,z,index}, ballot/popc compaction of accepted candidates into a per-warp
+//    shared-memory list, radix-select (shared-memory histogram) when more than nused are in range;
+//  * the flux sum reads each accepted photon's 128-byte alpha line with 8 lanes x float4, four photons
+//    per warp iteration.
+// Results: neighbour sets are bit-exact (distances use the reference's unfused (dx*dx+dy*dy)+dz*dz on
+// identical fp32 positions, ties by photon index); radiance is within 1e-4 relative of the reference
+// (summation order and libm differ), see tests/test_gpu_parity.py.
+#include <algorithm>
+#include "pv_grid.cuh"
+
+#define GW_WARPS 4                       // warps per CTA
+#define GW_THREADS (GW_WARPS * 32)
+
+struct MapView {
+    const float4 *pos4; const float4 *wi4; const float *alpha32; const uint32_t *cell_start;
+    GridParams g;
+    uint64_t n;
+};
+struct WarpBuf { float *d2; uint32_t *pos; uint32_t *hist; uint32_t cap; };
+struct WarpStats { uint32_t lookups, found, cand, heap, shadow, dens; };
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(PV_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(PV_FULL, v, o));
+    return v;
+}
+
+// Keep the k smallest (d2, original index) entries of buf[0..count); returns the new count (== k) and the
+// k-th distance.  count > k on entry.  MSB radix select over the fp32 bit pattern (non-negative floats order
+// like unsigned ints), 8-bit digits, histogram in shared memory.
+__device__ uint32_t warp_select_k(const MapView &m, WarpBuf b, uint32_t count, uint32_t k, uint32_t lane, float *kth) {
+    uint32_t prefix = 0, need = k, m_in_bucket = 0;
+    int shift = 24;
+    for (int pass = 0; pass < 4; ++pass, shift -= 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b.hist[lane * 8 + i] = 0;
+        __syncwarp();
+        for (uint32_t e = lane; e < count; e += 32) {
+            uint32_t bits = __float_as_uint(b.d2[e]);
+            if (pass == 0 || (bits >> (shift + 8)) == prefix) atomicAdd(&b.hist[(bits >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t loc[8], s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = b.hist[lane * 8 + i]; s += loc[i]; }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
+        uint32_t owner = __ffs(__ballot_sync(PV_FULL, inc >= need)) - 1;      // first lane whose inclusive sum reaches need
+        uint32_t digit = 0, before = 0, mcount = 0;
+        if (lane == owner) {
+            uint32_t run = inc - s;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (mcount == 0) {
+                    if (run + loc[i] >= need) { digit = lane * 8 + i; before = run; mcount = loc[i]; }
+                    else run += loc[i];
+                }
+            }
+        }
+        digit = __shfl_sync(PV_FULL, digit, owner); before = __shfl_sync(PV_FULL, before, owner);
+        mcount = __shfl_sync(PV_FULL, mcount, owner);
+        need -= before; prefix = (prefix << 8) | digit; m_in_bucket = mcount;
+        __syncwarp();
+        if (m_in_bucket == need) break;                 // the whole bucket is selected: no need to refine further
+    }
+    if (shift < 0) shift = 0;
+    // m_in_bucket > need can only happen after all four passes: ties in d2 straddle the k-th place.
+    // Resolve by original photon index (ClosePhoton::operator< tie rule, photonshooter.h:44-47).
+    uint32_t tie_idx = 0xFFFFFFFFu;
+    if (m_in_bucket != need) {
+        uint32_t last = 0; bool first = true;
+        for (uint32_t t = 0; t < need; ++t) {
+            uint32_t best = 0xFFFFFFFFu;
+            for (uint32_t e = lane; e < count; e += 32) {
+                if (__float_as_uint(b.d2[e]) == prefix) {
+                    uint32_t oi = __float_as_uint(__ldg(&m.pos4[b.pos[e]].w));
+                    if ((first || oi > last) && oi < best) best = oi;
+                }
+            }
+            last = warp_min_u32(best); first = false;
+        }
+        tie_idx = last;
+    }
+    // stable in-place compaction
+    uint32_t out = 0; float mx = 0.f;
+    for (uint32_t e0 = 0; e0 < count; e0 += 32) {
+        uint32_t e = e0 + lane;
+        bool keep = false; float d = 0.f; uint32_t p = 0;
+        if (e < count) {
+            d = b.d2[e]; p = b.pos[e];
+            uint32_t v = __float_as_uint(d) >> shift;
+            if (v < prefix) keep = true;
+            else if (v == prefix) {
+                if (m_in_bucket == need) keep = true;
+                else keep = __float_as_uint(__ldg(&m.pos4[p].w)) <= tie_idx;
+            }
+        }
+        uint32_t mask = __ballot_sync(PV_FULL, keep);
+        __syncwarp();
+        if (keep) { uint32_t slot = out + __popc(mask & lanemask_lt()); b.d2[slot] = d; b.pos[slot] = p; mx = fmaxf(mx, d); }
+        out += __popc(mask);
+        __syncwarp();
+    }
+    *kth = warp_max(mx);
+    return out;
+}
+
+// KdTree::Lookup + PhotonProcess semantics on the grid: leaves in buf the photons with d2 < r2, or, when more
+// than k of them exist, the k smallest by (d2, original index).  Returns their number.
+__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf b, uint32_t lane, WarpStats *st) {
+    const GridParams &g = m.g;
+    if (m.n == 0 || k == 0) return 0;
+    // no photon can be within r if the query is farther than r from the grid
+    float ext[3] = {g.origin[0] + g.dims[0] * g.h, g.origin[1] + g.dims[1] * g.h, g.origin[2] + g.dims[2] * g.h};
+    float slack = r + g.margin;
+    if (q.x < g.origin[0] - slack || q.x > ext[0] + slack || q.y < g.origin[1] - slack || q.y > ext[1] + slack ||
+        q.z < g.origin[2] - slack || q.z > ext[2] + slack)
+        return 0;
+    const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
+    const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
+    uint32_t count = 0, cand = 0;
+    bool have_k = false;
+    float boundk = INFINITY;
+    for (int s = 1;; ++s) {
+        const int side = 2 * s + 1, rows = side * side;
+        const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
+        for (int j0 = 0; j0 < rows; j0 += 32) {
+            int j = j0 + (int)lane;
+            uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
+            if (j < rows) {
+                int dy = j % side - s, dz = j / side - s;
+                int y = cy + dy, z = cz + dz;
+                if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
+                    bool full = (s == 1) || max(abs(dy), abs(dz)) == s;
+                    uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                    if (full) {
+                        sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
+                        ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
+                    } else {
+                        if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
+                        if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t rs = half ? sb : sa, re = half ? eb : ea;
+                uint32_t live = __ballot_sync(PV_FULL, re > rs);
+                while (live) {
+                    int src = __ffs(live) - 1; live &= live - 1;
+                    uint32_t start = __shfl_sync(PV_FULL, rs, src), end = __shfl_sync(PV_FULL, re, src);
+                    cand += end - start;
+                    for (uint32_t base = start; base < end; base += 32) {
+                        uint32_t p = base + lane;
+                        bool acc = false; float d2 = 0.f;
+                        if (p < end) {
+                            float4 pp = __ldg(m.pos4 + p);
+                            float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
+                            d2 = dx * dx + dy * dy + dz * dz;                 // (p1 - p2).LengthSquared(), geometry.h:116,526
+                            acc = d2 < r2 && d2 <= boundk;
+                        }
+                        uint32_t mask = __ballot_sync(PV_FULL, acc);
+                        if (mask) {
+                            if (acc) { uint32_t slot = count + __popc(mask & lanemask_lt()); b.d2[slot] = d2; b.pos[slot] = p; }
+                            count += __popc(mask);
+                            __syncwarp();
+                            if (count + 32 > b.cap) { count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true; }
+                        }
+                    }
+                }
+            }
+        }
+        // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon
+        float gr = INFINITY;
+        {
+            const float qq[3] = {q.x, q.y, q.z}; const int cc[3] = {cx, cy, cz};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                int lo = cc[a] - s, hi = cc[a] + s;
+                if (lo > 0) gr = fminf(gr, qq[a] - (g.origin[a] + lo * g.h));
+                if (hi < g.dims[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
+            }
+        }
+        if (count > k) { count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true; }
+        if (gr == INFINITY) break;                       // the block covers the whole grid
+        gr -= g.margin;
+        if (gr >= r) break;                              // everything with d2 < r2 has been seen
+        if (count == k) {
+            if (!have_k) {                               // exactly k so far: the bound is their max distance
+                float mx = 0.f;
+                for (uint32_t e = lane; e < count; e += 32) mx = fmaxf(mx, b.d2[e]);
+                boundk = warp_max(mx); have_k = true;
+            }
+            if (gr > 0.f && boundk < gr * gr) break;     // strict: an unseen photon cannot even tie
+        }
+    }
+    if (st) { st->lookups++; st->found += count; st->cand += cand; if (count == k) st->heap++; }
+    return count;
+}
+
+// LPhoton tail (photonvolume.cpp:83-104): returns totalFlux[lane] / (4/3 pi r^3 sigma_s[lane]) in lane == bin layout.
+__device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf b, uint32_t count, v3 w, float dens_pt, float sig_s_bin,
+                               uint32_t lane) {
+    if (count < 10) return 0.f;
+    const uint32_t grp = lane >> 3, sub = lane & 7;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float mx = 0.f;
+    const bool iso = med.g == 0.f;
+    const float ph0 = phase_hg(V3(0.f, 0.f, 1.f), V3(0.f, 0.f, 1.f), 0.f);       // 1/(4 pi): PhaseHG with g == 0
+    const v3 nw = -w;
+    for (uint32_t e0 = 0; e0 < count; e0 += 4) {
+        uint32_t e = e0 + grp;
+        if (e < count) {
+            uint32_t p = b.pos[e];
+            mx = fmaxf(mx, b.d2[e]);
+            float ph = ph0;
+            if (!iso) { float4 wv = __ldg(m.wi4 + p); ph = phase_hg(V3(wv.x, wv.y, wv.z), nw, med.g); }
+            float4 a = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)p * 32) + sub);
+            acc.x += a.x * ph; acc.y += a.y * ph; acc.z += a.z * ph; acc.w += a.w * ph;
+        }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(PV_FULL, acc.x, o); acc.y += __shfl_xor_sync(PV_FULL, acc.y, o);
+        acc.z += __shfl_xor_sync(PV_FULL, acc.z, o); acc.w += __shfl_xor_sync(PV_FULL, acc.w, o);
+    }
+    mx = warp_max(mx);
+    // transpose {8 lanes x 4 bins} -> lane == bin
+    int srcl = (lane >> 2) & 7;
+    float f0 = __shfl_sync(PV_FULL, acc.x, srcl), f1 = __shfl_sync(PV_FULL, acc.y, srcl);
+    float f2 = __shfl_sync(PV_FULL, acc.z, srcl), f3 = __shfl_sync(PV_FULL, acc.w, srcl);
+    int c = lane & 3;
+    float flux = c == 0 ? f0 : (c == 1 ? f1 : (c == 2 ? f2 : f3));
+    float dV = mx * __fsqrt_rn(mx);
+    float scale = sig_s_bin * dens_pt;                                  // sigma_s(pt): density * sig_s (or inside ? sig_s : 0)
+    bool any_scale = __ballot_sync(PV_FULL, lane < PV_NSPEC && scale != 0.f) != 0;
+    if (dV != 0.f && any_scale) {
+        float f = (float)(4.0 / 3.0 * (double)PV_PI_F * (double)dV);   // 4.0/3.0*M_PI*dV is a double expression
+        return __fdiv_rn(flux, scale * f);
+    }
+    return 0.f;
+}
+
+// ------------------------------------------------------------------ kernels
+__device__ __forceinline__ WarpBuf carve(unsigned char *smem, uint32_t cap, uint32_t warp) {
+    size_t per = (size_t)cap * 8 + 1024;
+    unsigned char *base = smem + per * warp;
+    WarpBuf b; b.d2 = (float *)base; b.pos = (uint32_t *)(base + (size_t)cap * 4); b.hist = (uint32_t *)(base + (size_t)cap * 8); b.cap = cap;
+    return b;
+}
+__device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpStats &st, uint32_t rays, uint32_t lane) {
+    if (lane == 0 && gs) {
+        atomicAdd((unsigned long long *)&gs->rays, (unsigned long long)rays);
+        atomicAdd((unsigned long long *)&gs->lookups, (unsigned long long)st.lookups);
+        atomicAdd((unsigned long long *)&gs->photons_found, (unsigned long long)st.found);
+        atomicAdd((unsigned long long *)&gs->candidates_tested, (unsigned long long)st.cand);
+        atomicAdd((unsigned long long *)&gs->heap_lookups, (unsigned long long)st.heap);
+        atomicAdd((unsigned long long *)&gs->shadow_rays, (unsigned long long)st.shadow);
+        atomicAdd((unsigned long long *)&gs->density_samples, (unsigned long long)st.dens);
+    }
+}
+
+// bitonic sort of buf[0..n2) by (d2, original index); n2 is a power of two >= count, padding = +inf
+__device__ void warp_sort_entries(const MapView &m, WarpBuf b, uint32_t count, uint32_t n2, uint32_t *oidx, uint32_t lane) {
+    for (uint32_t e = lane; e < n2; e += 32) {
+        if (e < count) oidx[e] = __float_as_uint(__ldg(&m.pos4[b.pos[e]].w));
+        else { b.d2[e] = INFINITY; oidx[e] = 0xFFFFFFFFu; }
+    }
+    __syncwarp();
+    for (uint32_t size = 2; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < n2 / 2; t += 32) {
+                uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
+                bool up = (i & size) == 0;
+                float di = b.d2[i], dj = b.d2[j]; uint32_t oi = oidx[i], oj = oidx[j];
+                bool gt = di > dj || (di == dj && oi > oj);
+                if (gt == up) { b.d2[i] = dj; b.d2[j] = di; oidx[i] = oj; oidx[j] = oi; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GW_THREADS) knn_kernel(MapView m, const float *__restrict__ pts, uint64_t n, uint32_t k, float r2, uint32_t cap,
+                                                        uint32_t *__restrict__ idx, float *__restrict__ d2out, uint32_t *__restrict__ nfound,
+                                                        unsigned long long *counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, cap, warp);
+    const float r = __fsqrt_rn(r2);
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1ull);
+        q = __shfl_sync(PV_FULL, q, 0);
+        if (q >= n) break;
+        v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
+        uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, nullptr);
+        __syncwarp();
+        uint32_t n2 = 1; while (n2 < cnt) n2 <<= 1;
+        if (n2 < 2) n2 = 2;
+        // original indices live after the entries: pos[] is reused as the index array via hist-free space
+        uint32_t *oidx = b.pos + (b.cap - n2);          // upper part of pos[]: the host sizes cap >= 2*n2 + 64
+        warp_sort_entries(m, b, cnt, n2, oidx, lane);
+        for (uint32_t e = lane; e < k; e += 32) {
+            idx[q * k + e] = e < cnt ? oidx[e] : 0xFFFFFFFFu;
+            d2out[q * k + e] = e < cnt ? b.d2[e] : INFINITY;
+        }
+        if (lane == 0) nfound[q] = cnt;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(GW_THREADS) lphoton_kernel(MapView m, const DevScene *__restrict__ sc, const float *__restrict__ pts,
+                                                            const float *__restrict__ ws, uint64_t n, uint32_t k, float maxdist, uint32_t cap,
+                                                            float *__restrict__ L, unsigned long long *counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, cap, warp);
+    const DevMedium &med = sc->med;
+    const float r2 = maxdist * maxdist;
+    const float sig_s = lane < PV_NSPEC ? med.sigma_s[lane] : 0.f;
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1ull);
+        q = __shfl_sync(PV_FULL, q, 0);
+        if (q >= n) break;
+        v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), w = V3(ws[3 * q], ws[3 * q + 1], ws[3 * q + 2]);
+        uint32_t cnt = warp_lookup(m, p, r2, maxdist, k, b, lane, nullptr);
+        __syncwarp();
+        float dens = med_density(med, p, nullptr);
+        float l = warp_estimate(m, med, b, cnt, w, dens, sig_s, lane);
+        if (lane < PV_NSPEC) L[q * PV_NSPEC + lane] = l;
+        __syncwarp();
+    }
+}
+
+// RainbowVolume::rainbowReflection (volumes/rainbow.cpp:41-78) for bin `lane`
+__device__ __forceinline__ float lerp_or_zero(float x, float x0, float x1, float y0, float y1) {
+    if (x < x0 || x1 < x) return 0.f;
+    return y0 + __fdiv_rn((x - x0) * (y1 - y0), x1 - x0);
+}
+__device__ float rainbow_bin(float Ld, v3 w, v3 wi, uint32_t lane) {
+    float cosTheta = vdot(wi, -w);
+    float theta = 57.2957f * acosf(cosTheta);
+    float I = __fdiv_rn(0.5f + 4.5f * powf((float)(0.5 * (double)(1.f + cosTheta)), 8.f), 4.f * PV_PI_F);
+    float innerGlow = theta <= 40.4f ? 1.0f : (theta >= 40.45f ? 0.9f : 1.0f + __fdiv_rn((theta - 40.4f) * (0.9f - 1.0f), 40.45f - 40.4f));
+    I *= innerGlow;
+    float rainbowI = 1.0f;
+    const float primaryRainbowI = 0.92f, secondaryRainbowI = (float)(0.42 * (double)0.92f), mistI = 0.08f;
+    float lambda = lerp_or_zero(theta, 40.4f, 42.3f, 400.0f, 700.0f);
+    if (lambda != 0.f) rainbowI *= primaryRainbowI;
+    else {
+        lambda = lerp_or_zero(theta, 51.0f, 54.4f, 700.0f, 400.0f);
+        if (lambda != 0.f) rainbowI *= secondaryRainbowI;
+    }
+    if (lambda == 0.f) return Ld * (I * mistI);
+    float deltaLambda = 300.f / PV_NSPEC;
+    float iwd = __fdiv_rn(lambda - 400.f, deltaLambda);
+    int index = (int)iwd;
+    float tt = iwd - index;
+    float rb = 0.f;
+    if ((int)lane == index) rb = Ld * tt;
+    if ((int)lane == index + 1 && index + 1 < PV_NSPEC) rb = Ld * (1 - tt);
+    return (Ld * mistI + rb * rainbowI) * I;
+}
+
+struct GatherArgs {
+    MapView m;
+    const DevScene *sc;
+    const pv_ray *rays;
+    uint64_t n;
+    float stepsize, maxdist;
+    uint32_t nused, flags, cap;
+    uint32_t k0, k1;               // Philox key
+    uint64_t ray_index_base;
+    float *L, *T;
+    pv_gather_stats *stats;
+    unsigned long long *counter;
+};
+
+__global__ void __launch_bounds__(GW_THREADS) gather_kernel(GatherArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, a.cap, warp);
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    const bool bin = lane < PV_NSPEC;
+    // spectra in lane == bin layout
+    const float sig_a = bin ? med.sigma_a[lane] : 0.f, sig_s = bin ? med.sigma_s[lane] : 0.f, le = bin ? med.le[lane] : 0.f;
+    const float sig_t = sig_a + sig_s;
+    const float cie = bin ? sc.cie_y[lane] : 0.f;
+    float sig_t_max = warp_max(sig_t);
+    float y_sig_a = 0.f, y_sig_s = 0.f;
+    for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
+    const float r2 = a.maxdist * a.maxdist;
+    const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
+    const int nLights = (int)sc.n_lights;
+    WarpStats st = {0, 0, 0, 0, 0, 0};
+    uint32_t nrays = 0;
+    for (;;) {
+        unsigned long long ri = 0;
+        if (lane == 0) ri = atomicAdd(a.counter, 1ull);
+        ri = __shfl_sync(PV_FULL, ri, 0);
+        if (ri >= a.n) break;
+        nrays++;
+        const pv_ray ray = a.rays[ri];
+        const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
+        float Tr = 1.f, Lv = 0.f;
+        float t0, t1;
+        bool hit = med.type != PV_MEDIUM_NONE && med_intersectp(med, ro, rd, ray.mint, ray.maxt, &t0, &t1) && (t1 - t0) != 0.f;
+        if (hit) {
+            const int nSamples = (int)ceilf(__fdiv_rn(t1 - t0, a.stepsize));
+            const float step = __fdiv_rn(t1 - t0, (float)nSamples);
+            const v3 p_first = ray_at(ro, rd, t0);
+            const v3 w = -rd;
+            float tbase = t0 + ray.u_scatter * step;            // t0 += u * step
+            float t_carry = tbase;
+            const uint64_t gidx = a.ray_index_base + ri;
+            uint32_t rw[4];
+            pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
+            bool stop = false;
+            for (int c0 = 0; c0 < nSamples && !stop; c0 += 32) {
+                // ---------------- lane == step: everything that does not depend on the recurrence
+                const int si = c0 + (int)lane;
+                const bool live = si < nSamples;
+                float t = tbase;
+                for (uint32_t j = 0; j < lane; ++j) t += step;     // the reference accumulates t0 += step (photonvolume.cpp:147)
+                float tprev = t_carry;                             // t of the previous step (lane 0: last step of the previous chunk)
+                if (lane > 0) { tprev = tbase; for (uint32_t j = 0; j + 1 < lane; ++j) tprev += step; }
+                const v3 p = ray_at(ro, rd, t);
+                const v3 pPrev = (si == 0) ? p_first : ray_at(ro, rd, tprev);
+                float tau_s = 0.f, dens = 0.f, u_rr = 0.f, sh_tau = 0.f, ph_d = 0.f, fall = 0.f, ld2 = 1.f;
+                int ln = 0, vis = 0, rr = 0;
+                v3 wo = V3(0.f, 0.f, 1.f);
+                uint32_t sw[4] = {0, 0, 0, 0};
+                if (live) {
+                    pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_STEP, a.k0, a.k1, sw);
+                }
+                if (live) {
+                    uint32_t ns = 0;
+                    tau_s = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
+                    u_rr = pv_u32_to_float(sw[1]);
+                    // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau_s) bounds every bin from below; y(1) ~ 1
+                    if (sig_t_max * tau_s > 6.0f) {
+                        float yy = 0.f;
+                        for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * tau_s));
+                        rr = __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f;
+                    }
+                    dens = med_density(med, p, &ns);
+                    if (dens != 0.f && nLights > 0 && !(a.flags & PV_GATHER_NO_DIRECT)) {
+                        float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
+                        ln = min((int)floorf(u_l * nLights), nLights - 1);
+                        LightQuery lq;
+                        light_query(sc.lights[ln], p, &lq);
+                        wo = lq.wi; fall = lq.falloff; ld2 = lq.point_like ? lq.inv_mode_d2 : -1.f;
+                        // L.IsBlack() is decided per bin in the spectral pass; the shadow ray is traced whenever it could matter
+                        if (fall != 0.f) {
+                            st.shadow++;
+                            float mt = lq.vis_maxt;
+                            vis = bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0;
+                            if (vis) {
+                                sh_tau = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize,
+                                                        pv_u32_to_float(sw[2]), &ns);
+                                ph_d = med_phase(med, p, w, -wo);
+                            }
+                        }
+                    }
+                    st.dens += ns;
+                }
+                t_carry = __shfl_sync(PV_FULL, t, 31);
+                // ---------------- lane == bin: the recurrence, one step at a time
+                const int nthis = min(32, nSamples - c0);
+                for (int i = 0; i < nthis; ++i) {
+                    const float s_tau = __shfl_sync(PV_FULL, tau_s, i);
+                    const int s_rr = __shfl_sync(PV_FULL, rr, i);
+                    Tr = expf(-(sig_t * s_tau));                          // Exp(-stepTau): per-step, not cumulative (:155)
+                    if (s_rr) {
+                        const float s_u = __shfl_sync(PV_FULL, u_rr, i);
+                        if (s_u > .5f) { Tr = 0.f; stop = true; break; }
+                        Tr = __fdiv_rn(Tr, .5f);
+                    }
+                    const float s_dens = __shfl_sync(PV_FULL, dens, i);
+                    const v3 sp = V3(__shfl_sync(PV_FULL, p.x, i), __shfl_sync(PV_FULL, p.y, i), __shfl_sync(PV_FULL, p.z, i));
+                    const float ss = sig_s * s_dens, sa = sig_a * s_dens;
+                    float L_d = 0.f, L_ii = 0.f;
+                    const int s_vis = __shfl_sync(PV_FULL, vis, i);
+                    if (s_vis) {
+                        const int s_ln = __shfl_sync(PV_FULL, ln, i);
+                        const float s_fall = __shfl_sync(PV_FULL, fall, i), s_ld2 = __shfl_sync(PV_FULL, ld2, i);
+                        const float s_sh = __shfl_sync(PV_FULL, sh_tau, i), s_ph = __shfl_sync(PV_FULL, ph_d, i);
+                        const pv_light &lt = sc.lights[s_ln];
+                        const float I = bin ? lt.intensity[lane] : 0.f;
+                        float Lb;
+                        if (s_ld2 < 0.f) Lb = I;
+                        else if (lt.type == PV_LIGHT_SPOT) Lb = __fdiv_rn(I * s_fall, s_ld2);
+                        else Lb = __fdiv_rn(I, s_ld2);
+                        const bool black = __ballot_sync(PV_FULL, bin && Lb != 0.f) == 0;
+                        const bool ss_black = __ballot_sync(PV_FULL, bin && ss != 0.f) == 0;
+                        if (!black && !ss_black) {
+                            const float Ld = Lb * expf(-(sig_t * s_sh));
+                            if (rainbow) {
+                                const v3 swo = V3(__shfl_sync(PV_FULL, wo.x, i), __shfl_sync(PV_FULL, wo.y, i), __shfl_sync(PV_FULL, wo.z, i));
+                                L_d = rainbow_bin(Ld, rd, swo, lane);
+                            } else {
+                                L_d = __fdiv_rn((Ld * s_ph) * (float)nLights, 1.f);
+                            }
+                        }
+                    }
+                    if (!rainbow && !(a.flags & PV_GATHER_NO_INDIRECT)) {
+                        uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, &st);
+                        __syncwarp();
+                        L_ii = warp_estimate(a.m, med, b, cnt, w, s_dens, sig_s, lane);
+                        __syncwarp();
+                    }
+                    // sa.y() != 0 || ss.y() != 0  (photonvolume.cpp:210): y(sig * density) vanishes with the density or with y(sig)
+                    const bool y_a = s_dens != 0.f && y_sig_a != 0.f, y_s = s_dens != 0.f && y_sig_s != 0.f;
+                    float L_i;
+                    if (y_a || y_s) L_i = L_d + __fdiv_rn(ss, sa + ss) * L_ii;
+                    else L_i = L_d;
+                    Lv = ((sa * (le * s_dens)) * step) + ((ss * L_i) * step) + (Tr * Lv);
+                }
+                tbase = t_carry + step;
+            }
+        }
+        if (bin) { a.L[ri * PV_NSPEC + lane] = hit ? Lv : 0.f; a.T[ri * PV_NSPEC + lane] = hit ? Tr : 1.f; }
+    }
+    flush_stats(a.stats, st, nrays, lane);
+}
+
+// ------------------------------------------------------------------ host side
+static uint32_t lookup_cap(uint32_t k) {
+    uint32_t cap = k + std::max<uint32_t>(k, 128u);
+    cap = (cap + 63u) & ~63u;
+    return std::max<uint32_t>(cap, 256u);
+}
+static MapView map_view(pv_ctx *ctx) {
+    MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.g = ctx->grid;
+    m.n = ctx->n_photons;
+    return m;
+}
+template <typename Kern>
+static int launch_cfg(pv_ctx *ctx, Kern kern, uint32_t cap, int *blocks, size_t *smem) {
+    *smem = ((size_t)cap * 8 + 1024) * GW_WARPS;
+    if (*smem > 200 * 1024) { ctx->err = "nused too large for the shared-memory candidate list"; return PV_EINVAL; }
+    PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    int per_sm = 0;
+    PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GW_THREADS, *smem));
+    if (per_sm < 1) per_sm = 1;
+    *blocks = ctx->sm_count * per_sm;              // persistent grid: a whole number of CTAs per SM
+    return PV_OK;
+}
+
+int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, uint32_t *d_idx, float *d_d2, uint32_t *d_nfound) {
+    if (!ctx->built) { ctx->err = "pv_knn: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (n == 0 || k == 0) return PV_OK;
+    uint32_t n2 = 2; while (n2 < k) n2 <<= 1;
+    uint32_t cap = std::max(lookup_cap(k), 2 * n2 + 64);
+    int blocks; size_t smem;
+    int rc = launch_cfg(ctx, knn_kernel, cap, &blocks, &smem); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    knn_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(map_view(ctx), d_pts, n, k, r2, cap, d_idx, d_d2, d_nfound, ctx->d_counters);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L) {
+    if (!ctx->built) { ctx->err = "pv_lphoton: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (!ctx->has_scene || ctx->hscene.med.type == PV_MEDIUM_NONE) { ctx->err = "pv_lphoton: scene has no medium"; return PV_ESTATE; }
+    if (n == 0) return PV_OK;
+    uint32_t cap = lookup_cap(nused);
+    int blocks; size_t smem;
+    int rc = launch_cfg(ctx, lphoton_kernel, cap, &blocks, &smem); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(map_view(ctx), ctx->dscene, d_pts, d_w, n, nused, maxdist, cap, d_L, ctx->d_counters);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T) {
+    if (!ctx->has_scene) { ctx->err = "pv_gather: no scene"; return PV_ESTATE; }
+    bool need_map = !(prm->flags & PV_GATHER_NO_INDIRECT) && ctx->hscene.med.type != PV_MEDIUM_RAINBOW && ctx->hscene.med.type != PV_MEDIUM_NONE;
+    if (need_map && !ctx->built) { ctx->err = "pv_gather: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
+    if (n == 0) return PV_OK;
+    GatherArgs a;
+    a.m = map_view(ctx); a.sc = ctx->dscene; a.rays = d_rays; a.n = n; a.stepsize = prm->stepsize; a.maxdist = prm->maxdist;
+    a.nused = prm->nused; a.flags = prm->flags | (need_map ? 0u : PV_GATHER_NO_INDIRECT); a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
+    a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32); a.ray_index_base = prm->ray_index_base;
+    a.L = d_L; a.T = d_T; a.stats = ctx->d_stats; a.counter = ctx->d_counters;
+    int blocks; size_t smem;
+    int rc = launch_cfg(ctx, gather_kernel, a.cap, &blocks, &smem); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    gather_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}

@@ -1,0 +1,655 @@
+// pv_shoot.cu -- photon shooting (K1-K3): PhotonShootingTask::Run / followPhoton
+// (core/photonshooter.cpp:47-357), volume-photon branch, as one persistent-thread sm_100a kernel.
+//
+// Each thread is a small state machine {NEWPATH, TRACE, SURFACE}; all lanes of a warp meet at the head of the
+// same loop every iteration (path regeneration happens in-loop), so divergence is confined to one iteration.
+// The reference's recursion -- including its quirks Q1 (inverted scatter test), Q2 (after a scattered sub-path
+// returns, control falls through into the surface code with the scattered ray and the ORIGINAL hit), Q3
+// (transmittance re-marched from the segment start at every step, fresh offset), Q5, Q6 -- is unrolled onto an
+// explicit per-thread stack of continuation frames that preserves the depth-first draw order, so a path consumes
+// its Philox stream in exactly the order the CPU oracle does (tests compare the photon sets one to one).
+// Light paths are dealt in the reference's blocks of 4096; a deposit of global block b is divided by
+// nshot = 4096*b (Q4), independent of the number of ranks.  Deposits are appended with warp-aggregated atomics
+// (one atomicAdd per coalesced group) into SoA planes; the 30-bin alpha goes out as one 128-byte line (8 x float4).
+#include <algorithm>
+#include <vector>
+#include <cooperative_groups.h>
+#include "pv_ctx.h"
+namespace cg = cooperative_groups;
+
+#define SH_THREADS 128
+#define SH_MAXDEPTH 24
+#define SH_BLOCK 4096
+
+enum { ST_NEWPATH = 0, ST_TRACE = 1, ST_SURFACE = 2 };
+
+struct Frame {
+    float o[3], d[3], mint, maxt;
+    float ip[3], inn[3], idpdu[3], ieps;      // hit: dg.p, dg.nn, dg.dpdu, rayEpsilon
+    int prim, nI, spec, loop_i;
+    float alpha[PV_NSPEC];
+};
+
+struct ShootArgs {
+    const DevScene *sc;
+    uint64_t b_start;               // first global block (1-based) of this rank in the wave
+    uint32_t n_local_blocks, world;
+    uint64_t first_block;           // wave origin, for block_counts indexing
+    float stepsize, istep4;
+    int max_depth;
+    uint32_t k0, k1;
+    uint32_t perm[41];              // PermutedHalton tables of task 0 (RNG(31*0)), montecarlo.cpp:380-397
+    float *pos, *wi, *alpha32; uint64_t *ids;
+    unsigned long long *n_out; uint64_t cap;
+    uint32_t *block_counts;
+    unsigned long long *work, *stats;     // stats: nodes, tris, density samples, segments, overflows, paths
+};
+
+struct PathRng {
+    uint32_t c0, c1, j, pos, k0, k1, buf[4];
+    __device__ __forceinline__ void reset(uint64_t path, uint32_t key0, uint32_t key1) {
+        c0 = (uint32_t)path; c1 = (uint32_t)(path >> 32); j = 0; pos = 4; k0 = key0; k1 = key1;
+    }
+    __device__ __forceinline__ float next() {
+        if (pos == 4) { pv_philox4x32_10(c0, c1, j++, PV_RNG_PATH, k0, k1, buf); pos = 0; }
+        uint32_t v = pos == 0 ? buf[0] : (pos == 1 ? buf[1] : (pos == 2 ? buf[2] : buf[3]));
+        pos++;
+        return pv_u32_to_float(v);
+    }
+};
+
+__device__ __forceinline__ v3 uniform_sample_sphere(float u1, float u2) {       // core/montecarlo.cpp:283-290
+    float z = 1.f - 2.f * u1;
+    float r = __fsqrt_rn(fmaxf(0.f, 1.f - z * z));
+    float phi = 2.f * PV_PI_F * u2;
+    return V3(r * cosf(phi), r * sinf(phi), z);
+}
+__device__ __forceinline__ v3 uniform_sample_cone(float u1, float u2, float costhetamax) {   // :405-410
+    float costheta = (1.f - u1) + u1 * costhetamax;
+    float sintheta = __fsqrt_rn(1.f - costheta * costheta);
+    float phi = u2 * 2.f * PV_PI_F;
+    return V3(cosf(phi) * sintheta, sinf(phi) * sintheta, costheta);
+}
+__device__ __forceinline__ void concentric_sample_disk(float u1, float u2, float *dx, float *dy) {   // :306-348
+    float r, theta;
+    float sx = 2 * u1 - 1, sy = 2 * u2 - 1;
+    if (sx == 0.f && sy == 0.f) { *dx = 0.f; *dy = 0.f; return; }
+    if (sx >= -sy) {
+        if (sx > sy) { r = sx; if (sy > 0.f) theta = __fdiv_rn(sy, r); else theta = 8.0f + __fdiv_rn(sy, r); }
+        else { r = sy; theta = 2.0f - __fdiv_rn(sx, r); }
+    } else {
+        if (sx <= sy) { r = -sx; theta = 4.0f - __fdiv_rn(sy, r); }
+        else { r = -sy; theta = 6.0f + __fdiv_rn(sx, r); }
+    }
+    theta *= PV_PI_F / 4.f;
+    *dx = r * cosf(theta);
+    *dy = r * sinf(theta);
+}
+__device__ __forceinline__ void coordinate_system(v3 v1, v3 *v2, v3 *v3o) {      // core/geometry.h:508-518
+    if (fabsf(v1.x) > fabsf(v1.y)) {
+        float invLen = __fdiv_rn(1.f, __fsqrt_rn(v1.x * v1.x + v1.z * v1.z));
+        *v2 = V3(-v1.z * invLen, 0.f, v1.x * invLen);
+    } else {
+        float invLen = __fdiv_rn(1.f, __fsqrt_rn(v1.y * v1.y + v1.z * v1.z));
+        *v2 = V3(0.f, v1.z * invLen, -v1.y * invLen);
+    }
+    *v3o = vcross(v1, *v2);
+}
+// FresnelDielectric::Evaluate + FrDiel (core/reflection.cpp:60-67,115-135), eta_i = 1, eta_t = ior
+__device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
+    cosi = fminf(fmaxf(cosi, -1.f), 1.f);
+    bool entering = cosi > 0.f;
+    float ei = 1.f, et = ior;
+    if (!entering) { float t = ei; ei = et; et = t; }
+    float sint = __fdiv_rn(ei, et) * __fsqrt_rn(fmaxf(0.f, 1.f - cosi * cosi));
+    if (sint >= 1.f) return 1.f;
+    float cost = __fsqrt_rn(fmaxf(0.f, 1.f - sint * sint));
+    float ac = fabsf(cosi);
+    float Rparl = __fdiv_rn((et * ac) - (ei * cost), (et * ac) + (ei * cost));
+    float Rperp = __fdiv_rn((ei * ac) - (et * cost), (ei * ac) + (et * cost));
+    return __fdiv_rn(Rparl * Rparl + Rperp * Rperp, 2.f);
+}
+
+__global__ void __launch_bounds__(SH_THREADS) shoot_kernel(ShootArgs a) {
+    __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
+    __shared__ uint32_t s_perm[41];
+    __shared__ float s_minmax[3];
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    if (threadIdx.x < PV_NSPEC) {
+        s_cie[threadIdx.x] = sc.cie_y[threadIdx.x]; s_sa[threadIdx.x] = med.sigma_a[threadIdx.x];
+        s_ss[threadIdx.x] = med.sigma_s[threadIdx.x]; s_st[threadIdx.x] = med.sigma_a[threadIdx.x] + med.sigma_s[threadIdx.x];
+    }
+    if (threadIdx.x < 41) s_perm[threadIdx.x] = a.perm[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mn = INFINITY, mx = 0.f, y1 = 0.f;
+        for (int b = 0; b < PV_NSPEC; ++b) { mn = fminf(mn, s_st[b]); mx = fmaxf(mx, s_st[b]); y1 += s_cie[b]; }
+        s_minmax[0] = mn; s_minmax[1] = mx; s_minmax[2] = __fdiv_rn(y1 * 300.f, 106.856895f * (float)PV_NSPEC);
+    }
+    __syncthreads();
+    const float st_min = s_minmax[0], st_max = s_minmax[1], y_one = s_minmax[2];
+    const uint64_t total = (uint64_t)a.n_local_blocks * SH_BLOCK;
+    const uint32_t halton_base[6] = {2, 3, 5, 7, 11, 13};
+
+    Frame cur;
+    Frame stack[SH_MAXDEPTH];
+    int sp = 0, state = ST_NEWPATH;
+    PathRng rng; rng.reset(0, a.k0, a.k1);
+    uint64_t path = 0, gblock = 0; uint32_t lblock = 0, dep_seq = 0;
+    uint32_t c_nodes = 0, c_tris = 0, c_dens = 0, c_seg = 0, c_ovf = 0, c_paths = 0;
+
+    for (;;) {
+        if (state == ST_NEWPATH) {
+            // ---- fetch a light path (warp-aggregated counter) and emit it: photonshooter.cpp:248-275
+            cg::coalesced_group g = cg::coalesced_threads();
+            unsigned long long w = 0;
+            if (g.thread_rank() == 0) w = atomicAdd(a.work, (unsigned long long)g.size());
+            w = g.shfl(w, 0) + g.thread_rank();
+            if (w >= total) break;
+            lblock = (uint32_t)(w / SH_BLOCK);
+            gblock = a.b_start + (uint64_t)lblock * a.world;
+            path = (gblock - 1) * SH_BLOCK + (w % SH_BLOCK) + 1;
+            rng.reset(path, a.k0, a.k1);
+            dep_seq = 0; sp = 0; c_paths++;
+            float u[6];
+            {
+                const uint32_t *p = s_perm;
+#pragma unroll
+                for (int dmn = 0; dmn < 6; ++dmn) {
+                    uint32_t base = halton_base[dmn], n = (uint32_t)path;
+                    double val = 0, invBase = 1. / base, invBi = invBase;
+                    while (n > 0) {
+                        uint32_t d_i = p[n % base];
+                        val += d_i * invBi;
+                        n = __double2uint_rz((double)n * invBase);
+                        invBi *= invBase;
+                    }
+                    u[dmn] = fminf((float)val, PV_ONE_MINUS_EPS);
+                    p += base;
+                }
+            }
+            // SampleDiscrete (montecarlo.h:99-107): upper_bound on the CDF
+            int nl = (int)sc.n_lights, lo = 0, hi = nl + 1;
+            while (lo < hi) { int mid = (lo + hi) / 2; if (u[0] < sc.light_cdf[mid]) hi = mid; else lo = mid + 1; }
+            int lightNum = max(lo - 1, 0);
+            float lightPdf = __fdiv_rn(sc.light_func[lightNum], sc.light_func_int * nl);
+            const pv_light &l = sc.lights[lightNum];
+            v3 ro, rd; float pdf, scale = 1.f;
+            if (l.type == PV_LIGHT_POINT) {                                // lights/point.cpp:80-88
+                ro = V3(l.pos[0], l.pos[1], l.pos[2]); rd = uniform_sample_sphere(u[1], u[2]);
+                pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
+            } else if (l.type == PV_LIGHT_SPOT) {                          // lights/spot.cpp:106-114
+                v3 v = uniform_sample_cone(u[1], u[2], l.cos_total_width);
+                ro = V3(l.pos[0], l.pos[1], l.pos[2]); rd = xf_vec(l.light_to_world, v);
+                pdf = __fdiv_rn(1.f, 2.f * PV_PI_F * (1.f - l.cos_total_width));
+                scale = spot_falloff(l, rd);
+            } else {                                                       // lights/distant.cpp:82-102
+                const float *wb = sc.world_bound;
+                v3 pmin = V3(wb[0], wb[1], wb[2]), pmax = V3(wb[3], wb[4], wb[5]);
+                v3 wc = pmin * .5f + pmax * .5f;
+                float wr = bbox_inside(wb, wb + 3, wc) ? vlen(wc - pmax) : 0.f;
+                v3 ld = V3(l.dir[0], l.dir[1], l.dir[2]), v1, v2;
+                coordinate_system(ld, &v1, &v2);
+                float d1, d2;
+                concentric_sample_disk(u[1], u[2], &d1, &d2);
+                v3 Pdisk = wc + (v1 * d1 + v2 * d2) * wr;
+                ro = Pdisk + ld * wr; rd = -ld;
+                pdf = __fdiv_rn(1.f, PV_PI_F * wr * wr);
+            }
+            float ad = fabsf(vdot(rd, rd));                                // AbsDot(Nl, photonRay.d) with Nl == ray.d
+            float den = pdf * lightPdf;
+            bool black = true;
+#pragma unroll
+            for (int b = 0; b < PV_NSPEC; ++b) {
+                float Le = l.type == PV_LIGHT_SPOT ? l.intensity[b] * scale : l.intensity[b];
+                cur.alpha[b] = __fdiv_rn(Le * ad, den);
+                black = black && (cur.alpha[b] == 0.f);
+            }
+            if (pdf == 0.f || black) continue;                             // stays in ST_NEWPATH
+            cur.o[0] = ro.x; cur.o[1] = ro.y; cur.o[2] = ro.z; cur.d[0] = rd.x; cur.d[1] = rd.y; cur.d[2] = rd.z;
+            cur.mint = 0.f; cur.maxt = INFINITY; cur.nI = 0; cur.spec = 1; cur.loop_i = -1; cur.prim = -1;
+            state = ST_TRACE;
+            continue;
+        }
+        const v3 o = V3(cur.o[0], cur.o[1], cur.o[2]), d = V3(cur.d[0], cur.d[1], cur.d[2]);
+        bool pop = false;
+        if (state == ST_TRACE) {
+            // ---- followPhoton head: intersect, march the medium (photonshooter.cpp:54-128)
+            c_seg++;
+            float thit = cur.maxt;
+            BvhCounters bc = {0, 0};
+            int prim = bvh_traverse<false>(sc, o, d, cur.mint, &thit, &bc);
+            c_nodes += bc.nodes; c_tris += bc.tris;
+            if (prim < 0) pop = true;
+            else {
+                // hit record: shapes/trianglemesh.cpp:160-205 with default uvs, core/diffgeom.cpp:40-55
+                const float *tv = sc.tri + 9 * (size_t)prim;
+                v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
+                v3 dp1 = p1 - p3, dp2 = p2 - p3;
+                v3 dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                  // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1
+                v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;                  // (-du2*dp1 + du1*dp2) * invdet, du2 = 0, du1 = -1
+                v3 nn = vnorm(vcross(dpdu, dpdv));
+                v3 hp = ray_at(o, d, thit);
+                cur.prim = prim; cur.ip[0] = hp.x; cur.ip[1] = hp.y; cur.ip[2] = hp.z;
+                cur.inn[0] = nn.x; cur.inn[1] = nn.y; cur.inn[2] = nn.z;
+                cur.idpdu[0] = dpdu.x; cur.idpdu[1] = dpdu.y; cur.idpdu[2] = dpdu.z;
+                cur.ieps = 1e-3f * thit;
+                cur.maxt = thit;                                            // GeometricPrimitive::Intersect: r.maxt = thit
+                cur.nI++;
+                float length = vlen(d);
+                if (length == 0.f) pop = true;
+                else {
+                    v3 rnd = vdiv(d, length);
+                    float t0, t1;
+                    if (!med_intersectp(med, o, rnd, cur.mint * length, cur.maxt * length, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
+                    t0 += rng.next() * a.stepsize;
+                    const float t_i = t0;
+                    const float xi = rng.next();
+                    bool interaction = false;
+                    while (t0 < t1) {
+                        float uo = rng.next();                               // Transmittance(sample == NULL): offset = RandomFloat()
+                        uint32_t ns = 0;
+                        float s = med_tau_scalar(med, o, rnd, t_i, t0, a.istep4, uo, &ns);
+                        c_dens += ns;
+                        // xi > Tr.y() ?  y(exp(-sig_t s)) lies between exp(-st_max s) y1 and exp(-st_min s) y1
+                        bool hitv;
+                        float elo = expf(-(st_max * s)) * y_one, ehi = expf(-(st_min * s)) * y_one;
+                        if (xi > ehi * 1.0001f) hitv = true;
+                        else if (xi < elo * 0.9999f) hitv = false;
+                        else {
+                            float yy = 0.f;
+                            for (int b = 0; b < PV_NSPEC; ++b) yy += s_cie[b] * expf(-(s_st[b] * s));
+                            hitv = xi > __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC);
+                        }
+                        if (hitv) { interaction = true; break; }
+                        t0 += a.stepsize;
+                    }
+                    if (interaction) {
+                        v3 pt = ray_at(o, rnd, t0);
+                        uint32_t ns = 0;
+                        float dens = med_density(med, pt, &ns);
+                        c_dens += 2 * ns;
+                        float ys = 0.f, ya = 0.f;
+                        for (int b = 0; b < PV_NSPEC; ++b) { ys += s_cie[b] * (s_ss[b] * dens); ya += s_cie[b] * (s_sa[b] * dens); }
+                        ys = __fdiv_rn(ys * 300.f, 106.856895f * (float)PV_NSPEC); ya = __fdiv_rn(ya * 300.f, 106.856895f * (float)PV_NSPEC);
+                        bool scatter = rng.next() > __fdiv_rn(ys, ya + ys);     // Q1 (photonshooter.cpp:88)
+                        if (!scatter) pop = true;
+                        else {
+                            if (cur.nI > 1) {
+                                // ---- deposit (photonshooter.cpp:98-102), normalised by nshot of its block (:333)
+                                cg::coalesced_group g = cg::coalesced_threads();
+                                unsigned long long slot = 0;
+                                if (g.thread_rank() == 0) slot = atomicAdd(a.n_out, (unsigned long long)g.size());
+                                slot = g.shfl(slot, 0) + g.thread_rank();
+                                atomicAdd(&a.block_counts[(uint32_t)(gblock - a.first_block)], 1u);
+                                if (slot < a.cap) {
+                                    const float fn = (float)(gblock * SH_BLOCK);
+                                    a.pos[3 * slot] = pt.x; a.pos[3 * slot + 1] = pt.y; a.pos[3 * slot + 2] = pt.z;
+                                    a.wi[3 * slot] = rnd.x; a.wi[3 * slot + 1] = rnd.y; a.wi[3 * slot + 2] = rnd.z;
+                                    float4 *dst = reinterpret_cast<float4 *>(a.alpha32 + 32 * slot);
+#pragma unroll
+                                    for (int q = 0; q < 7; ++q)
+                                        dst[q] = make_float4(__fdiv_rn(cur.alpha[4 * q], fn), __fdiv_rn(cur.alpha[4 * q + 1], fn),
+                                                             __fdiv_rn(cur.alpha[4 * q + 2], fn), __fdiv_rn(cur.alpha[4 * q + 3], fn));
+                                    dst[7] = make_float4(__fdiv_rn(cur.alpha[28], fn), __fdiv_rn(cur.alpha[29], fn), 0.f, 0.f);
+                                    a.ids[slot] = (path << 16) | (uint64_t)(dep_seq & 0xffffu);
+                                }
+                                dep_seq++;
+                            }
+                            float u1 = rng.next(), u2 = rng.next();
+                            v3 dir = uniform_sample_sphere(u1, u2);
+                            const float pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
+                            float ref = med_phase(med, pt, rnd, dir);
+                            if (ref == 0.f) pop = true;
+                            else {
+#pragma unroll
+                                for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(cur.alpha[b] * ref, pdf);
+                                cur.o[0] = pt.x; cur.o[1] = pt.y; cur.o[2] = pt.z; cur.d[0] = dir.x; cur.d[1] = dir.y; cur.d[2] = dir.z;
+                                cur.mint = 0.f; cur.maxt = INFINITY; cur.loop_i = -1;
+                                // Q2: after the scattered sub-path, the surface code runs with this ray and the hit above
+                                if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
+                                // the recursive call itself: same ray, state TRACE
+                                state = ST_TRACE;
+                                continue;
+                            }
+                        }
+                    } else {
+                        state = ST_SURFACE; cur.loop_i = -1;
+                        continue;
+                    }
+                }
+            }
+        } else {
+            // ---- surface part (photonshooter.cpp:131-227); caustic/indirect/direct maps are off on this path
+            if (cur.loop_i < 0) {
+                float uo = rng.next();
+                uint32_t ns = 0;
+                float s = med_tau_scalar(med, o, d, cur.mint, cur.maxt, a.istep4, uo, &ns);
+                c_dens += ns;
+#pragma unroll
+                for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] *= expf(-(s_st[b] * s));
+                cur.loop_i = 0;
+                if (cur.nI >= a.max_depth) pop = true;
+            }
+            if (!pop) {
+                const pv_material &mat = sc.mats[sc.prim_mat[cur.prim]];
+                const v3 wo = -d;
+                const v3 nn = V3(cur.inn[0], cur.inn[1], cur.inn[2]);
+                const v3 sn = vnorm(V3(cur.idpdu[0], cur.idpdu[1], cur.idpdu[2]));        // BSDF frame, reflection.cpp:619-627
+                const v3 tn = vcross(nn, sn);
+                if (mat.type == PV_MAT_MATTE) {
+                    // Lambertian bounce (reflection.cpp:323-330,534-598).  With the surface maps off the path always dies
+                    // here (Q6: indirectDone && !specularPath), but frames still on the stack keep drawing from this path's
+                    // stream, so the number of draws consumed must match the reference: 3 for BSDFSample, then the Russian
+                    // roulette draw only if the sample is valid.
+                    float u0 = rng.next(), u1 = rng.next(); rng.next();
+                    bool kd_black = true;
+                    for (int b = 0; b < PV_NSPEC; ++b) kd_black = kd_black && mat.kd[b] == 0.f;
+                    if (!kd_black) {
+                        v3 wol = V3(vdot(wo, sn), vdot(wo, tn), vdot(wo, nn));
+                        v3 wil;
+                        concentric_sample_disk(u0, u1, &wil.x, &wil.y);
+                        wil.z = __fsqrt_rn(fmaxf(0.f, 1.f - wil.x * wil.x - wil.y * wil.y));
+                        if (wol.z < 0.f) wil.z *= -1.f;
+                        float pdf = (wol.z * wil.z > 0.f) ? fabsf(wil.z) * PV_INV_PI_F : 0.f;
+                        if (pdf != 0.f) {
+                            v3 wiW = V3(sn.x * wil.x + tn.x * wil.y + nn.x * wil.z, sn.y * wil.x + tn.y * wil.y + nn.y * wil.z,
+                                        sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
+                            if (vdot(wiW, nn) * vdot(wo, nn) > 0.f) rng.next();       // continueProb draw
+                        }
+                    }
+                    pop = true;
+                } else {
+                    // glass: SpecularReflection + dispersive SpecularTransmission (materials/glass.cpp:42-59)
+                    bool hasR = false, hasT = false;
+                    for (int b = 0; b < PV_NSPEC; ++b) { hasR = hasR || mat.kr[b] != 0.f; hasT = hasT || mat.kt[b] != 0.f; }
+                    const int matching = (hasR ? 1 : 0) + (hasT ? 1 : 0);
+                    int nz = 0;
+                    for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) nz++;
+                    const bool do_split = hasT && nz != 1 && mat.vn > 0.f;       // alpha.lambda < 0 && dispersive()
+                    bool spawned = false;
+                    for (;;) {
+                        // next spectrum of the split (splitSpectrum core/spectrum.h:253-265): bins with c != 0, in order
+                        int bin = -1;
+                        if (do_split) {
+                            int seen = 0;
+                            for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] != 0.f) { if (seen == cur.loop_i) { bin = b; break; } seen++; }
+                            if (bin < 0) break;
+                        } else if (cur.loop_i > 0) break;
+                        cur.loop_i++;
+                        float u0 = rng.next(), u1 = rng.next(), uc = rng.next();
+                        (void)u0; (void)u1;
+                        if (matching == 0) continue;
+                        int which = min((int)floorf(uc * matching), matching - 1);
+                        bool pickT = hasR ? (which == 1) : true;
+                        v3 wol = V3(vdot(wo, sn), vdot(wo, tn), vdot(wo, nn));
+                        v3 wil; float F = fresnel_dielectric(wol.z, mat.index);
+                        float fpdf = 1.f;
+                        if (!pickT) wil = V3(-wol.x, -wol.y, wol.z);
+                        else {
+                            bool entering = wol.z > 0.f;
+                            float ei = 1.f, et = mat.index;
+                            int lam = -1;
+                            if (do_split) lam = 400 + bin * 10;                    // extractLambda: integer step (700-400)/29 == 10
+                            else if (nz == 1) { for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) lam = 400 + b * 10; }
+                            if (lam > 0 && mat.vn > 0.f) {                         // Cauchy, reflection.cpp:155-161
+                                float lmu = __fdiv_rn((float)lam, 1000.f);
+                                float B = (float)((double)__fdiv_rn(et - 1.f, mat.vn) * 0.52345);
+                                float A = (float)((double)et - ((double)B / 0.34522792));
+                                et = (float)((double)A + (double)B / ((double)lmu * (double)lmu));
+                            }
+                            if (!entering) { float t = ei; ei = et; et = t; }
+                            float sini2 = fmaxf(0.f, 1.f - wol.z * wol.z);
+                            float eta = __fdiv_rn(ei, et);
+                            float sint2 = eta * eta * sini2;
+                            if (sint2 >= 1.f) continue;                            // total internal reflection: pdf stays 0
+                            float cost = __fsqrt_rn(fmaxf(0.f, 1.f - sint2));
+                            if (entering) cost = -cost;
+                            wil = V3(eta * -wol.x, eta * -wol.y, cost);
+                        }
+                        if (matching > 1) fpdf = __fdiv_rn(fpdf, (float)matching);
+                        v3 wiW = V3(sn.x * wil.x + tn.x * wil.y + nn.x * wil.z, sn.y * wil.x + tn.y * wil.y + nn.y * wil.z,
+                                    sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
+                        float adn = fabsf(vdot(wiW, nn));
+                        float anew[PV_NSPEC], ynew = 0.f, yold = 0.f; bool fblack = true;
+#pragma unroll
+                        for (int b = 0; b < PV_NSPEC; ++b) {
+                            float ab = do_split ? (b == bin ? cur.alpha[b] : 0.f) : cur.alpha[b];
+                            float fb = pickT ? __fdiv_rn((1.f - F) * mat.kt[b], fabsf(wil.z)) : __fdiv_rn(F * mat.kr[b], fabsf(wil.z));
+                            fblack = fblack && fb == 0.f;
+                            anew[b] = __fdiv_rn((ab * fb) * adn, fpdf);
+                            ynew += s_cie[b] * anew[b]; yold += s_cie[b] * ab;
+                        }
+                        if (fblack) continue;
+                        ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
+                        float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
+                        if (rng.next() > continueProb) continue;
+                        if (!cur.spec) continue;                                // indirectDone && !specularPath
+                        // spawn the child; this frame resumes at loop_i afterwards
+                        if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
+#pragma unroll
+                        for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(anew[b], continueProb);
+                        cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
+                        cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
+                        cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
+                        spawned = true;
+                        break;
+                    }
+                    if (spawned) { state = ST_TRACE; continue; }
+                    pop = true;
+                }
+            }
+        }
+        if (pop) {
+            if (sp == 0) state = ST_NEWPATH;
+            else { cur = stack[--sp]; state = ST_SURFACE; }
+        }
+    }
+    // ---- counters
+    unsigned long long vals[6] = {c_nodes, c_tris, c_dens, c_seg, c_ovf, c_paths};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        unsigned long long v = vals[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(PV_FULL, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&a.stats[i], v);
+    }
+}
+
+// ---------------------------------------------------------------- host: MT19937 only to reproduce task 0's Halton tables
+static void halton_tables_task0(uint32_t perm[41]) {
+    // RNG rng(31 * taskNum) with taskNum == 0, then PermutedHalton(6, rng): core/rng.cpp:43-107, montecarlo.cpp:380-397
+    uint32_t mt[624]; int mti;
+    mt[0] = 0u;
+    for (mti = 1; mti < 624; mti++) mt[mti] = 1812433253u * (mt[mti - 1] ^ (mt[mti - 1] >> 30)) + (uint32_t)mti;
+    auto next = [&]() -> uint32_t {
+        static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+        uint32_t y;
+        if (mti >= 624) {
+            int kk;
+            for (kk = 0; kk < 624 - 397; kk++) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u]; }
+            for (; kk < 623; kk++) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u]; }
+            y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu); mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+            mti = 0;
+        }
+        y = mt[mti++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    };
+    const uint32_t bases[6] = {2, 3, 5, 7, 11, 13};
+    uint32_t *p = perm;
+    for (int d = 0; d < 6; ++d) {
+        uint32_t b = bases[d];
+        for (uint32_t i = 0; i < b; ++i) p[i] = i;
+        for (uint32_t i = 0; i < b; ++i) { uint32_t other = i + (next() % (b - i)); std::swap(p[i], p[other]); }
+        p += b;
+    }
+}
+
+int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats) {
+    if (!ctx->has_scene || ctx->hscene.med.type == PV_MEDIUM_NONE || ctx->hscene.n_lights == 0) {
+        ctx->err = "pv_shoot: scene needs a medium and at least one light"; return PV_ESTATE;
+    }
+    if (first_block < 1 || prm->world < 1 || prm->rank >= prm->world) { ctx->err = "pv_shoot: bad block / rank arguments"; return PV_EINVAL; }
+    if (!(prm->stepsize > 0.f) || !(prm->integrator_stepsize > 0.f)) { ctx->err = "pv_shoot: step sizes must be > 0"; return PV_EINVAL; }
+    if (first_block == 1) { ctx->n_photons = 0; ctx->built = false; }
+    if (n_blocks == 0) return PV_OK;
+    // blocks of this rank inside the wave: b with (b - 1) % world == rank
+    uint64_t b_start = first_block + ((prm->rank + prm->world - ((first_block - 1) % prm->world)) % prm->world);
+    uint64_t b_end = first_block + n_blocks;              // exclusive
+    uint32_t n_local = b_start < b_end ? (uint32_t)((b_end - b_start + prm->world - 1) / prm->world) : 0;
+    memset(counts, 0, sizeof(uint32_t) * n_blocks);
+    if (n_local == 0) return PV_OK;
+
+    int rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, sizeof(uint32_t) * (size_t)n_blocks + 64); if (rc) return rc;
+    uint32_t *d_counts = (uint32_t *)ctx->io2;
+    unsigned long long *d_nout = ctx->d_counters + 1, *d_work = ctx->d_counters + 2, *d_stats = ctx->d_counters + 8;
+    // first guess of the capacity: 8% deposit yield on top of what is already stored
+    uint64_t want_cap = ctx->n_photons + (uint64_t)((double)n_local * SH_BLOCK * 0.08) + 65536;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        rc = pvi_reserve_photons(ctx, want_cap); if (rc) return rc;
+        ShootArgs a;
+        a.sc = ctx->dscene; a.b_start = b_start; a.n_local_blocks = n_local; a.world = prm->world; a.first_block = first_block;
+        a.stepsize = prm->stepsize; a.istep4 = 4.f * prm->integrator_stepsize; a.max_depth = prm->max_photon_depth;
+        a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
+        halton_tables_task0(a.perm);
+        a.pos = ctx->d_pos; a.wi = ctx->d_wi; a.alpha32 = ctx->d_alpha; a.ids = ctx->d_ids;
+        a.n_out = d_nout; a.cap = ctx->cap_photons; a.block_counts = d_counts; a.work = d_work; a.stats = d_stats;
+        unsigned long long init_n = ctx->n_photons, zero = 0;
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_nout, &init_n, sizeof(init_n), cudaMemcpyHostToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_work, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks, ctx->stream));
+        int per_sm = 0;
+        PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel, SH_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        uint64_t total = (uint64_t)n_local * SH_BLOCK;
+        int blocks = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (total + SH_THREADS - 1) / SH_THREADS);
+        PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        shoot_kernel<<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
+        PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        unsigned long long h_nout = 0, h_stats[8];
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(&h_nout, d_nout, sizeof(h_nout), cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_nout > ctx->cap_photons) { want_cap = h_nout + 65536; continue; }      // too small: grow and replay the (deterministic) wave
+        float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->n_photons = h_nout;
+        if (stats) {
+            stats->nodes_visited += h_stats[0]; stats->tri_tests += h_stats[1]; stats->density_samples += h_stats[2];
+            stats->segments += h_stats[3]; stats->stack_overflows += h_stats[4]; stats->paths_local += h_stats[5];
+            stats->seconds += ms * 1e-3;
+        }
+        return PV_OK;
+    }
+    ctx->err = "pv_shoot: could not size the photon buffer";
+    return PV_ENOMEM;
+}
+
+__global__ void id_keys_kernel(const uint64_t *__restrict__ ids, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = ids[i]; vals[i] = (uint32_t)i; }
+}
+__global__ void permute_photons_kernel(const uint32_t *__restrict__ order, uint64_t n, const float *__restrict__ pos, const float *__restrict__ wi,
+                                       const float *__restrict__ alpha, const uint64_t *__restrict__ ids, float *__restrict__ pos_o,
+                                       float *__restrict__ wi_o, float *__restrict__ alpha_o, uint64_t *__restrict__ ids_o) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t j = t >> 3; uint32_t sub = (uint32_t)(t & 7);
+    if (j >= n) return;
+    uint32_t src = order[j];
+    *(reinterpret_cast<float4 *>(alpha_o + j * 32) + sub) = *(reinterpret_cast<const float4 *>(alpha + (uint64_t)src * 32) + sub);
+    if (sub < 3) { pos_o[3 * j + sub] = pos[3 * (uint64_t)src + sub]; wi_o[3 * j + sub] = wi[3 * (uint64_t)src + sub]; }
+    if (sub == 3) ids_o[j] = ids[src];
+}
+
+// Drop photons of blocks > last_block and order the rest by id = (path index << 16 | deposit ordinal): the photon
+// set and its order then depend only on (scene, seed, target), not on thread scheduling or the number of ranks.
+int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
+    uint64_t n = ctx->n_photons;
+    ctx->built = false;
+    if (n == 0) return PV_OK;
+    if (n > 0xFFFFFFF0ull) { ctx->err = "too many photons"; return PV_EINVAL; }
+    size_t need = n * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 256;
+    int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
+    uint64_t *keys = (uint64_t *)ctx->scratch, *keys_tmp = keys + n;
+    uint32_t *vals = (uint32_t *)(keys_tmp + n), *vals_tmp = vals + n;
+    id_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ids, n, keys, vals);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    // highest path index bounds the key width
+    uint64_t max_path = last_block ? last_block * SH_BLOCK : ~0ull >> 16;
+    int bits = 16; while (bits < 64 && (max_path >> (bits - 16)) != 0) ++bits;
+    bits = std::min(64, bits + 1);
+    // photons of later blocks may still be present: they sort to the end because their path index is larger
+    uint64_t *skeys; uint32_t *svals;
+    rc = pvi_sort_pairs_u64(ctx, keys, vals, keys_tmp, vals_tmp, n, 64, &skeys, &svals); if (rc) return rc;
+    (void)bits;
+    // count survivors: ids <= (last_block * 4096) << 16 | 0xffff
+    uint64_t keep = n;
+    if (last_block) {
+        uint64_t limit = ((last_block * SH_BLOCK) << 16) | 0xffffull;
+        std::vector<uint64_t> probe(1);
+        uint64_t lo = 0, hi = n;                                  // upper_bound over the sorted keys (few D2H probes)
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) / 2;
+            PV_CUDA_CHECK(ctx, cudaMemcpy(probe.data(), skeys + mid, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            if (probe[0] <= limit) lo = mid + 1; else hi = mid;
+        }
+        keep = lo;
+    }
+    float *np, *nw, *na; uint64_t *ni;
+    uint64_t cap = std::max<uint64_t>(keep, 1024);
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&np, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&nw, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&na, cap * 32 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ni, cap * sizeof(uint64_t)));
+    if (keep) {
+        permute_photons_kernel<<<(unsigned)((keep * 8 + 255) / 256), 256, 0, ctx->stream>>>(svals, keep, ctx->d_pos, ctx->d_wi, ctx->d_alpha, ctx->d_ids,
+                                                                                         np, nw, na, ni);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_pos); cudaFree(ctx->d_wi); cudaFree(ctx->d_alpha); cudaFree(ctx->d_ids);
+    ctx->d_pos = np; ctx->d_wi = nw; ctx->d_alpha = na; ctx->d_ids = ni; ctx->cap_photons = cap; ctx->n_photons = keep;
+    return PV_OK;
+}
+
+// Single-rank driver == PhotonShootingTask::Run's outer loop (photonshooter.cpp:245-356): waves of blocks until the
+// running photon count reaches the target at some block M; give-up rule of :285-299.
+int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm_in, pv_shoot_stats *stats) {
+    pv_shoot_params prm = *prm_in;
+    pv_shoot_stats st; memset(&st, 0, sizeof(st));
+    if (prm.world != 1 || prm.rank != 0) { ctx->err = "pv_shoot: use pv_shoot_blocks/pv_shoot_finish when world > 1"; return PV_EINVAL; }
+    uint64_t max_paths = prm.max_paths ? prm.max_paths : ((uint64_t)1 << 40);
+    uint64_t block = 0, total = 0, last = 0;
+    uint32_t wave = 64;
+    std::vector<uint32_t> counts;
+    bool done = false; int rc = PV_OK;
+    if (n_wanted == 0) { ctx->n_photons = 0; ctx->built = false; if (stats) *stats = st; return PV_OK; }
+    while (!done) {
+        counts.assign(wave, 0);
+        rc = pvi_shoot_blocks(ctx, block + 1, wave, &prm, counts.data(), &st); if (rc) return rc;
+        for (uint32_t i = 0; i < wave; ++i) {
+            uint64_t nshot_before = block * SH_BLOCK;
+            // "Unable to store enough photons.  Giving up." (photonshooter.cpp:285-299, unsuccessful() :37-39)
+            if (nshot_before > 500000 && total < n_wanted && (total == 0 || total < SH_BLOCK / 1024)) {
+                ctx->n_photons = 0; ctx->err = "Unable to store enough photons.  Giving up."; rc = PV_ENOPHOTONS; done = true; break;
+            }
+            block++; total += counts[i];
+            if (total >= n_wanted || block * SH_BLOCK >= max_paths) { last = block; done = true; break; }
+        }
+        if (!done) {
+            // size the next wave from the observed yield, aiming a little past the target
+            double per_block = std::max(1e-3, (double)total / (double)block);
+            double remaining = (double)(n_wanted - total) / per_block;
+            wave = (uint32_t)std::min<double>(std::max<double>(remaining * 1.03 + 8, 64), 262144);
+            uint64_t left = (max_paths / SH_BLOCK > block) ? (max_paths / SH_BLOCK - block) : 1;
+            wave = (uint32_t)std::min<uint64_t>(wave, left);
+        }
+    }
+    if (rc == PV_OK) rc = pvi_shoot_finish(ctx, last);
+    st.paths = last * SH_BLOCK; st.blocks = last; st.photons_local = ctx->n_photons;
+    if (stats) *stats = st;
+    return rc;
+}

@@ -1,0 +1,59 @@
+// pv_trace.cu -- batch forms of Scene::Intersect / IntersectP (accelerators/bvh.cpp:585-685 walking the
+// exported LinearBVHNode array, shapes/trianglemesh.cpp:127-281) and of
+// PhotonVolumeIntegrator::Transmittance (integrators/photonvolume.cpp:15-30).  One thread per ray.
+#include "pv_ctx.h"
+
+__global__ void intersect_kernel(const DevScene *__restrict__ sc, const pv_ray *__restrict__ rays, uint64_t n, uint32_t *__restrict__ prim,
+                                 float *__restrict__ t) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pv_ray r = rays[i];
+    float maxt = r.maxt;
+    int h = bvh_traverse<false>(*sc, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, &maxt, nullptr);
+    prim[i] = h < 0 ? 0xFFFFFFFFu : (uint32_t)h;
+    t[i] = h < 0 ? INFINITY : maxt;
+}
+__global__ void occluded_kernel(const DevScene *__restrict__ sc, const pv_ray *__restrict__ rays, uint64_t n, uint8_t *__restrict__ hit) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pv_ray r = rays[i];
+    float maxt = r.maxt;
+    hit[i] = bvh_traverse<true>(*sc, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, &maxt, nullptr) >= 0 ? 1 : 0;
+}
+// one warp per ray: lane 0..29 own a spectral bin; the optical-depth scalar is computed redundantly (uniform loads)
+__global__ void transmittance_kernel(const DevScene *__restrict__ sc, const pv_ray *__restrict__ rays, uint64_t n, float step,
+                                     const float *__restrict__ u, float *__restrict__ T) {
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const DevMedium &med = sc->med;
+    float tr = 1.f;
+    if (med.type != PV_MEDIUM_NONE) {
+        pv_ray r = rays[w];
+        float s = med_tau_scalar(med, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, step, u ? u[w] : 0.5f, nullptr);
+        if (lane < PV_NSPEC) tr = expf(-((med.sigma_a[lane] + med.sigma_s[lane]) * s));
+    }
+    if (lane < PV_NSPEC) T[w * PV_NSPEC + lane] = tr;
+}
+
+int pvi_intersect(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint32_t *d_prim, float *d_t) {
+    if (!ctx->has_scene) { ctx->err = "pv_intersect: no scene"; return PV_ESTATE; }
+    if (!n) return PV_OK;
+    intersect_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays, n, d_prim, d_t);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit) {
+    if (!ctx->has_scene) { ctx->err = "pv_occluded: no scene"; return PV_ESTATE; }
+    if (!n) return PV_OK;
+    occluded_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays, n, d_hit);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+int pvi_transmittance(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, const float *d_u, float *d_T) {
+    if (!ctx->has_scene) { ctx->err = "pv_transmittance: no scene"; return PV_ESTATE; }
+    if (!n) return PV_OK;
+    transmittance_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays, n, step, d_u, d_T);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}

@@ -170,9 +170,11 @@ int pv_get_photons(pv_ctx *ctx, float *pos, float *wi, float *alpha,
 int pv_get_photons_dev(pv_ctx *ctx, float *pos, float *wi, float *alpha,
                        uint64_t *ids, uint64_t capacity, uint64_t *n);
 int pv_photon_count(pv_ctx *ctx, uint64_t *n);
-/* Morton-sort the photons into the hashed uniform grid.  cell_size <= 0
- * picks one from the photon density.                                        */
-int pv_build(pv_ctx *ctx, float cell_size);
+/* Sort the photons into the uniform grid the gather walks.  maxdist / nused
+ * are the integrator's lookup parameters (integrators/photonvolume.h:17-20);
+ * they only size the cells: h = min(maxdist, radius expected to hold nused
+ * photons).  Lookups with other parameters stay exact, just slower.         */
+int pv_build(pv_ctx *ctx, float maxdist, uint32_t nused);
 
 /* ---- KdTree::Lookup + PhotonProcess (core/kdtree.h:150-183,
  *      core/photonshooter.h:186-203) --------------------------------------- */
@@ -210,6 +212,22 @@ int pv_last_kernel_ms(pv_ctx *ctx, float *ms);
 /* ---- PhotonShooter::Preprocess, volume branch (photonshooter.cpp:457-526) */
 int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted,
              const pv_shoot_params *params, pv_shoot_stats *stats);
+
+/* Multi-rank form of the same pass.  Light paths are grouped in the reference's
+ * blocks of 4096 (photonshooter.cpp:247); block b (1-based, global) holds Halton
+ * indices (b-1)*4096+1 .. b*4096 and its deposits are divided by nshot = 4096*b
+ * (:301,333), so the photon set does not depend on how blocks are dealt to ranks.
+ * pv_shoot_blocks traces the blocks of [first_block, first_block+n_blocks) that
+ * belong to params->rank and returns the number of photons each of them deposited
+ * (0 for blocks of other ranks) in counts[n_blocks]; the caller sums counts over
+ * ranks, finds the first block at which the running total reaches the target and
+ * calls pv_shoot_finish(last_block): photons of later blocks are dropped and the
+ * rest is ordered by (path index, deposit ordinal).  first_block == 1 starts a
+ * new pass (clears the photon set).                                             */
+int pv_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks,
+                    const pv_shoot_params *params, uint32_t *counts,
+                    pv_shoot_stats *stats);
+int pv_shoot_finish(pv_ctx *ctx, uint64_t last_block);
 
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);
