@@ -94,14 +94,14 @@ def test_knn_edge_cases(pv_factory):
     nf, idx, d2 = pv.Lookup(np.zeros((3, 3), np.float32), k=5, r2=0.01)
     assert (nf == 0).all() and (idx == 0xFFFFFFFF).all() and np.isinf(d2).all()
     # fewer photons than k, queries far outside the grid, a single photon
-    pos = np.array([[0.1, 0.2, 0.3]], np.float32)
+    pos = np.array([[0.25, 0.5, 0.75]], np.float32)
     pv.set_photons(pos, np.array([[0, 0, 1]], np.float32), np.ones((1, 30), np.float32))
-    pv.build(maxdist=0.1, nused=5)
-    pts = np.array([[0.1, 0.2, 0.3], [0.15, 0.2, 0.3], [5, 5, 5], [0.1, 0.2, 0.4]], np.float32)
-    nf, idx, d2 = pv.Lookup(pts, k=5, r2=0.01)
-    bnf, bidx, bd2 = O.knn_brute(pos, pts, 5, 0.01)
+    pv.build(maxdist=0.125, nused=5)
+    pts = np.array([[0.25, 0.5, 0.75], [0.3125, 0.5, 0.75], [5, 5, 5], [0.25, 0.5, 0.875]], np.float32)
+    nf, idx, d2 = pv.Lookup(pts, k=5, r2=0.015625)
+    bnf, bidx, bd2 = O.knn_brute(pos, pts, 5, 0.015625)
     assert np.array_equal(nf, bnf) and np.array_equal(idx, bidx)
-    assert nf.tolist() == [1, 1, 0, 0]          # d2 == r2 is excluded (strict <, kdtree.h:180)
+    assert nf.tolist() == [1, 1, 0, 0]          # d2 == r2 (0.125^2 exactly) is excluded: strict <, kdtree.h:180
     # zero queries
     nf, idx, d2 = pv.Lookup(np.zeros((0, 3), np.float32), k=5, r2=0.01)
     assert len(nf) == 0
