@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- volumetric photon-mapping hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] -- Cornell box + heterogeneous 256^3 density-grid medium,
+16M photons, 1920x1080 camera rays, fixed-radius gather (nused 512 >= photons in radius, maxdist 0.018,
+stepsize 2/64).  Metric: volume-gather rays/s (whole job, all GPUs); photons-traced/s of the shooter is
+reported in the same line under "shoot".  A step = one gather pass (PhotonVolumeIntegrator::Li for every camera
+ray of the frame) against the resident photon map.  N > 1: photons are produced sharded, the map is replicated
+with one NCCL all-gather over NVLink, image tiles are dealt round-robin to ranks (strong scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []; self.proc = None; self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_gather_baseline(W, cfg, scene, pos, wi, alpha, rays, nsample, threads, seed):
+    """The CPU port (oracle) timed on a bounded sample of the same rays; kd-tree build is untimed preprocess."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    t0 = time.perf_counter()
+    tree = O.KdTree(pos)
+    build_s = time.perf_counter() - t0
+    sel = np.linspace(0, len(rays) - 1, nsample).astype(np.int64)
+    sample = np.ascontiguousarray(rays[sel])
+    t0 = time.perf_counter()
+    L, T, st = O.gather(scene, tree, wi, alpha, sample, cfg["stepsize"], cfg["nused"], cfg["maxdist"], seed=seed, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": nsample / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d camera rays (every %d-th), full %d-photon map; kd-tree build %.1f s untimed; %.1f s timed"
+                      % (nsample, len(rays), max(1, len(rays) // nsample), len(pos), build_s, dt),
+            "lookups_per_s": st.lookups / dt}, (sel, L, T)
+
+
+def run_reference(args, cfg, W, scene):
+    """--impl reference: the reference's CPU implementation of the gather on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_ph = args.photons or cfg["photons"]
+    pos, wi, alpha = W.photons_from_density(scene, n_ph)
+    rays, _ = W.frame_rays(cfg)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    tree = O.KdTree(pos)
+    nsample = args.ref_rays
+    times = []
+    for it in range(args.warmup + args.steps):
+        sel = (np.linspace(0, len(rays) - 1, nsample).astype(np.int64) + it * 7) % len(rays)
+        sample = np.ascontiguousarray(rays[sel])
+        t0 = time.perf_counter()
+        O.gather(scene, tree, wi, alpha, sample, cfg["stepsize"], cfg["nused"], cfg["maxdist"], seed=args.seed, nthreads=threads)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    val = nsample * args.steps / dt
+    out = {"impl": "reference", "metric": "volume-gather rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": cfg["label"], "photons": n_ph, "xres": cfg["xres"], "yres": cfg["yres"], "stepsize": cfg["stepsize"],
+                      "nused": cfg["nused"], "maxdist": cfg["maxdist"]},
+           "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                            "sample": "%d camera rays per step out of the %d-ray frame, full %d-photon map" % (nsample, len(rays), n_ph)},
+           "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3")
+    ap.add_argument("--photons", type=int, default=0, help="override the photon count (debug only; invalidates the number)")
+    ap.add_argument("--shoot-photons", type=int, default=400_000, help="bounded photon-shooting sample for the shoot rates")
+    ap.add_argument("--cpu-rays", type=int, default=12_000, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-rays", type=int, default=6_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=348)
+    args = ap.parse_args()
+
+    pkg = load_package()
+    from cs348b_pbrt_b200 import workloads as W
+    cfg = W.CONFIGS[args.workload]
+    scene = W.load_scene(cfg)
+    if args.impl == "reference":
+        run_reference(args, cfg, W, scene)
+        return
+
+    import torch
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    A = pkg._abi
+    peak, peak_kind = read_peaks()
+    n_ph = args.photons or cfg["photons"]
+
+    pv = pkg.PhotonVolume(device=local, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=args.seed)
+    pv.set_scene(scene)
+    ext = torch.cuda.ExternalStream(pv.stream(), device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ photon shooting (bounded sample, sharded by block)
+    import ctypes as C
+    shoot = {}
+    if args.shoot_photons > 0:
+        prm = A.ShootParams(0.05, cfg["stepsize"], 5, args.seed, rank, world, 0, 0.0)
+        st = A.ShootStats()
+        block, total, wave, last = 0, 0, 64 * world, 0
+        t0 = time.perf_counter()
+        while not last:
+            counts = (C.c_uint32 * wave)()
+            pv._chk(pv.lib.pv_shoot_blocks(pv.ctx, C.c_uint64(block + 1), C.c_uint32(wave), C.byref(prm), counts, C.byref(st)))
+            cnt = torch.tensor(np.ctypeslib.as_array(counts).astype(np.int64), device=dev)
+            if dist is not None:
+                dist.all_reduce(cnt)
+            cnt = cnt.cpu().numpy()
+            for c in cnt:
+                block += 1; total += int(c)
+                if total >= args.shoot_photons:
+                    last = block
+                    break
+            if not last:
+                per = max(total / block, 1e-3)
+                wave = int(min(max((args.shoot_photons - total) / per * 1.03 + 8, 64 * world), 262144))
+        pv._chk(pv.lib.pv_shoot_finish(pv.ctx, C.c_uint64(last)))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        sec = torch.tensor([st.seconds, float(st.paths_local), float(pv.photon_count()), float(st.nodes_visited), float(st.tri_tests),
+                            float(st.density_samples), float(st.stack_overflows)], dtype=torch.float64, device=dev)
+        mx = sec.clone()
+        if dist is not None:
+            dist.all_reduce(sec); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sec = sec.cpu().numpy(); dsec = float(mx.cpu().numpy()[0])
+        paths = last * 4096
+        shoot_bytes = sec[3] * 32 + sec[4] * 36 + sec[5] * 32 + sec[2] * 144       # SURVEY 8d shoot formula
+        shoot = {"photons": int(sec[2]), "paths": int(paths), "paths_traced_incl_discarded": int(sec[1]), "device_s": dsec, "wall_s": wall,
+                 "paths_per_s": sec[1] / dsec, "photons_per_s": sec[2] / dsec,
+                 "stack_overflows": int(sec[6]), "hbm_frac_algorithmic": shoot_bytes / dsec / 1e9 / (peak * world),
+                 "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": args.shoot_photons}}
+
+    # ------------------------------------------------------------------ the photon map of the gather workload
+    lo, hi = W.photon_slice(n_ph, rank, world)
+    t0 = time.perf_counter()
+    pos, wi, alpha = W.photons_from_density(scene, n_ph, lo=lo, hi=hi)
+    gen_s = time.perf_counter() - t0
+    allgather = None
+    if world == 1:
+        pv.set_photons(pos, wi, alpha)
+    else:
+        counts_t = torch.tensor([hi - lo], device=dev, dtype=torch.int64)
+        all_counts = [torch.zeros_like(counts_t) for _ in range(world)]
+        dist.all_gather(all_counts, counts_t)
+        all_counts = [int(c.item()) for c in all_counts]
+        mxc = max(all_counts)
+        loc = [torch.zeros((mxc, k), device=dev, dtype=torch.float32) for k in (3, 3, 30)]
+        for t, a in zip(loc, (pos, wi, alpha)):
+            t[:len(a)].copy_(torch.from_numpy(a))
+        full = [torch.empty((world * mxc, k), device=dev, dtype=torch.float32) for k in (3, 3, 30)]
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t, f in zip(loc, full):
+            dist.all_gather_into_tensor(f, t)
+        e1.record(); torch.cuda.synchronize()
+        ag_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ag_ms, op=dist.ReduceOp.MAX)
+        # drop the padding of short slices
+        keep = torch.cat([torch.arange(r * mxc, r * mxc + all_counts[r], device=dev) for r in range(world)])
+        full = [f.index_select(0, keep).contiguous() for f in full]
+        pv.set_photons_dev(full[0], full[1], full[2], n_ph)
+        nbytes = (world - 1) / world * n_ph * 144
+        allgather = {"ms": float(ag_ms.item()), "bytes_in_per_gpu": nbytes, "gb_per_s_per_gpu": nbytes / (float(ag_ms.item()) * 1e-3) / 1e9,
+                     "nvlink_peer_gb_per_s": 770.0}
+        del full, loc
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pv.build()
+    build_s = time.perf_counter() - t0
+
+    # ------------------------------------------------------------------ rays of this rank (image tiles dealt round-robin)
+    rays, order = W.frame_rays(cfg, rank, world)
+    n_local = len(rays)
+    n_total = cfg["xres"] * cfg["yres"]
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)
+    d_L = torch.empty((n_local, 30), device=dev); d_T = torch.empty((n_local, 30), device=dev)
+
+    for _ in range(max(args.warmup, 3)):
+        pv.Li_dev(d_rays, n_local, d_L, d_T)
+    pv.gather_stats(reset=True)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record(ext)
+    for _ in range(args.steps):
+        pv.Li_dev(d_rays, n_local, d_L, d_T)
+        kernel_ms.append(pv.last_kernel_ms())
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    stats = pv.gather_stats(reset=True)
+    value = n_total * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (gather_kernel), this rank
+    bytes_per_launch = W.gather_bytes(stats, n_local * args.steps) / args.steps
+    avg_kernel_ms = float(np.mean(kernel_ms))
+    achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_kind": peak_kind, "kernel": "gather_kernel", "avg_launch_ms": avg_kernel_ms,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "b_ph": 144,
+                "lookups_per_launch": stats.lookups / args.steps, "photons_found_per_lookup": stats.photons_found / max(stats.lookups, 1),
+                "candidates_per_lookup": stats.candidates_tested / max(stats.lookups, 1)}
+    tr = os.path.join(ROOT, "profiles", "r01_gather_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ end to end through the host-pointer C ABI call
+    h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10).copy()).pin_memory()
+    h_L = torch.empty((n_local, 30)).pin_memory(); h_T = torch.empty((n_local, 30)).pin_memory()
+    pv.Li_into(h_rays, n_local, h_L, h_T)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pv.Li_into(h_rays, n_local, h_L, h_T)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": n_total * args.steps / float(e2e_s.item()), "unit": "rays/s", "h2d_bytes_per_step": int(n_local * 40),
+           "d2h_bytes_per_step": int(n_local * 240)}
+    check = float(h_L.sum().item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu, (sel, cL, cT) = cpu_gather_baseline(W, cfg, scene, pos, wi, alpha, rays, args.cpu_rays, threads, args.seed)
+        # same sample through the CUDA path with the same per-ray Philox indices (ray_index_base 0)
+        gL, gT = pv.Li(np.ascontiguousarray(rays[sel]))
+        m = cL > 0
+        cpu["max_rel_err_vs_gpu"] = float((np.abs(gL - cL)[m] / cL[m]).max()) if m.any() else 0.0
+
+    if rank == 0:
+        out = {"metric": "volume-gather rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic",
+               "config": {"workload": cfg["label"], "photons": n_ph, "grid": cfg["grid"], "xres": cfg["xres"], "yres": cfg["yres"],
+                          "stepsize": cfg["stepsize"], "nused": cfg["nused"], "maxdist": cfg["maxdist"], "photon_record_bytes": 144,
+                          "l2_policy": "inputs_exceed_l2 (photon map %.1f GB)" % (n_ph * 160 / 1e9), "ray_order": "8x8 tiles",
+                          "parallelism": "tiles/%d" % world},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+               "shoot": shoot, "build": {"seconds": build_s, "photons": n_ph, "photon_gen_host_s": gen_s}, "allgather": allgather,
+               "lookups_per_s": stats.lookups * world / (total_ms * 1e-3) if world == 1 else None, "checksum_L": check}
+        print(json.dumps(out), flush=True)
+    pv.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
