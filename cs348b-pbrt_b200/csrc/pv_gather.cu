@@ -20,13 +20,20 @@
 
 #define GW_WARPS 4                       // warps per CTA
 #define GW_THREADS (GW_WARPS * 32)
+#define GW_STAGE 512                     // candidates staged per TMA round (x 16 B)
+#define SLOT_FLAG 0x80000000u            // list entry still holds a batch slot, not a photon position
 
 struct MapView {
     const float4 *pos4; const float4 *wi4; const float *alpha32; const uint32_t *cell_start;
     GridParams g;
     uint64_t n;
 };
-struct WarpBuf { float *d2; uint32_t *pos; uint32_t *hist; uint32_t cap; };
+// per-warp shared memory: candidate list (d2, pos), select histogram, run tables of the current batch,
+// mbarrier, TMA staging buffer
+struct WarpBuf {
+    float *d2; uint32_t *pos; uint32_t *hist; uint32_t *run_e; uint32_t *run_s; float4 *stage;
+    uint32_t mbar; uint32_t stage_addr; uint32_t cap; uint32_t phase;
+};
 struct WarpStats { uint32_t lookups, found, cand, heap, shadow, dens; };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -39,11 +46,50 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(PV_FULL, v, o));
     return v;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(mbar), "r"(phase) : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// list entries appended during a batch hold (slot | SLOT_FLAG); turn them into sorted photon positions:
+// run = largest i with run_e[i] <= slot (run_e = exclusive prefix of the batch's run lengths)
+__device__ __forceinline__ void warp_convert_slots(WarpBuf &b, uint32_t count, uint32_t lane) {
+    for (uint32_t e = lane; e < count; e += 32) {
+        uint32_t v = b.pos[e];
+        if (v & SLOT_FLAG) {
+            uint32_t t = v & ~SLOT_FLAG, lo = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) if (b.run_e[lo + st] <= t) lo += st;
+            b.pos[e] = b.run_s[lo] + (t - b.run_e[lo]);
+        }
+    }
+    __syncwarp();
+}
 
 // Keep the k smallest (d2, original index) entries of buf[0..count); returns the new count (== k) and the
-// k-th distance.  count > k on entry.  MSB radix select over the fp32 bit pattern (non-negative floats order
-// like unsigned ints), 8-bit digits, histogram in shared memory.
-__device__ uint32_t warp_select_k(const MapView &m, WarpBuf b, uint32_t count, uint32_t k, uint32_t lane, float *kth) {
+// k-th distance.  count > k on entry, entries hold photon positions.  MSB radix select over the fp32 bit pattern
+// (non-negative floats order like unsigned ints), 8-bit digits, histogram in shared memory.
+__device__ uint32_t warp_select_k(const MapView &m, WarpBuf &b, uint32_t count, uint32_t k, uint32_t lane, float *kth) {
     uint32_t prefix = 0, need = k, m_in_bucket = 0;
     int shift = 24;
     for (int pass = 0; pass < 4; ++pass, shift -= 8) {
@@ -121,16 +167,63 @@ __device__ uint32_t warp_select_k(const MapView &m, WarpBuf b, uint32_t count, u
     return out;
 }
 
+// One batch of <= 32 photon runs (lane i holds run [rs, re) of the sorted photon array): the runs are staged
+// back to back into shared memory with TMA bulk copies, GW_STAGE candidates per round, and scanned with
+// lane == candidate.  Accepted candidates are appended to the list as (d2, slot | SLOT_FLAG).
+__device__ __forceinline__ void warp_scan_batch(const MapView &m, WarpBuf &b, uint32_t rs, uint32_t re, v3 q, float r2, uint32_t k,
+                                                uint32_t lane, uint32_t &count, float &boundk, bool &have_k, uint32_t &cand) {
+    const uint32_t len = re - rs;
+    uint32_t inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
+    const uint32_t T = __shfl_sync(PV_FULL, inc, 31);
+    if (T == 0) return;
+    const uint32_t E = inc - len;
+    cand += T;
+    __syncwarp();                                        // earlier readers of run tables / stage are done
+    b.run_e[lane] = E; b.run_s[lane] = rs;
+    for (uint32_t cb = 0; cb < T; cb += GW_STAGE) {
+        const uint32_t cend = min(T, cb + GW_STAGE);
+        // order the generic-proxy reads of the previous round before the async-proxy writes of this one
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(b.mbar, (cend - cb) * 16u);
+        const uint32_t lo = max(E, cb), hi = min(E + len, cend);
+        if (lo < hi) tma_bulk_g2s(b.stage_addr + (lo - cb) * 16u, m.pos4 + rs + (lo - E), (hi - lo) * 16u, b.mbar);
+        mbar_wait(b.mbar, b.phase);
+        b.phase ^= 1u;
+        for (uint32_t t0 = cb; t0 < cend; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            bool acc = false; float d2 = 0.f;
+            if (t < cend) {
+                const float4 pp = b.stage[t - cb];
+                const float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
+                d2 = dx * dx + dy * dy + dz * dz;             // (p1 - p2).LengthSquared(), geometry.h:116,526
+                acc = d2 < r2 && d2 <= boundk;
+            }
+            const uint32_t mask = __ballot_sync(PV_FULL, acc);
+            if (acc) { const uint32_t slot = count + __popc(mask & lanemask_lt()); b.d2[slot] = d2; b.pos[slot] = t | SLOT_FLAG; }
+            count += __popc(mask);
+            if (count + 32 > b.cap) {                         // list full: keep the k nearest so far
+                __syncwarp();
+                warp_convert_slots(b, count, lane);
+                count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true;
+            }
+        }
+    }
+    __syncwarp();
+    warp_convert_slots(b, count, lane);
+}
+
 // KdTree::Lookup + PhotonProcess semantics on the grid: leaves in buf the photons with d2 < r2, or, when more
 // than k of them exist, the k smallest by (d2, original index).  Returns their number.
-__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf b, uint32_t lane, WarpStats *st) {
+__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf &b, uint32_t lane, WarpStats *st) {
     const GridParams &g = m.g;
     if (m.n == 0 || k == 0) return 0;
     // no photon can be within r if the query is farther than r from the grid
-    float ext[3] = {g.origin[0] + g.dims[0] * g.h, g.origin[1] + g.dims[1] * g.h, g.origin[2] + g.dims[2] * g.h};
-    float slack = r + g.margin;
-    if (q.x < g.origin[0] - slack || q.x > ext[0] + slack || q.y < g.origin[1] - slack || q.y > ext[1] + slack ||
-        q.z < g.origin[2] - slack || q.z > ext[2] + slack)
+    const float slack = r + g.margin;
+    if (q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.h + slack || q.y < g.origin[1] - slack ||
+        q.y > g.origin[1] + g.dims[1] * g.h + slack || q.z < g.origin[2] - slack || q.z > g.origin[2] + g.dims[2] * g.h + slack)
         return 0;
     const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
     const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
@@ -139,52 +232,41 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
     bool have_k = false;
     float boundk = INFINITY;
     for (int s = 1;; ++s) {
-        const int side = 2 * s + 1, rows = side * side;
-        const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
-        for (int j0 = 0; j0 < rows; j0 += 32) {
-            int j = j0 + (int)lane;
-            uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
-            if (j < rows) {
-                int dy = j % side - s, dz = j / side - s;
-                int y = cy + dy, z = cz + dz;
+        if (s == 1) {
+            // the 3x3x3 block: nine rows, each ONE contiguous run of <= 3 cells
+            uint32_t rs = 0, re = 0;
+            if (lane < 9) {
+                const int y = cy + (int)(lane % 3u) - 1, z = cz + (int)(lane / 3u) - 1;
                 if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
-                    bool full = (s == 1) || max(abs(dy), abs(dz)) == s;
-                    uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-                    if (full) {
-                        sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
-                        ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
-                    } else {
-                        if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
-                        if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
-                    }
+                    const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                    rs = __ldg(m.cell_start + (rowkey | (uint32_t)max(cx - 1, 0)));
+                    re = __ldg(m.cell_start + (rowkey | (uint32_t)min(cx + 1, g.dims[0] - 1)) + 1);
                 }
             }
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                uint32_t rs = half ? sb : sa, re = half ? eb : ea;
-                uint32_t live = __ballot_sync(PV_FULL, re > rs);
-                while (live) {
-                    int src = __ffs(live) - 1; live &= live - 1;
-                    uint32_t start = __shfl_sync(PV_FULL, rs, src), end = __shfl_sync(PV_FULL, re, src);
-                    cand += end - start;
-                    for (uint32_t base = start; base < end; base += 32) {
-                        uint32_t p = base + lane;
-                        bool acc = false; float d2 = 0.f;
-                        if (p < end) {
-                            float4 pp = __ldg(m.pos4 + p);
-                            float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
-                            d2 = dx * dx + dy * dy + dz * dz;                 // (p1 - p2).LengthSquared(), geometry.h:116,526
-                            acc = d2 < r2 && d2 <= boundk;
-                        }
-                        uint32_t mask = __ballot_sync(PV_FULL, acc);
-                        if (mask) {
-                            if (acc) { uint32_t slot = count + __popc(mask & lanemask_lt()); b.d2[slot] = d2; b.pos[slot] = p; }
-                            count += __popc(mask);
-                            __syncwarp();
-                            if (count + 32 > b.cap) { count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true; }
+            warp_scan_batch(m, b, rs, re, q, r2, k, lane, count, boundk, have_k, cand);
+        } else {
+            // shell s: rows on the rim of the (2s+1)^2 square are full runs, inner rows contribute their two end cells
+            const int side = 2 * s + 1, rows = side * side;
+            const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
+            for (int j0 = 0; j0 < rows; j0 += 32) {
+                const int j = j0 + (int)lane;
+                uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
+                if (j < rows) {
+                    const int dy = j % side - s, dz = j / side - s;
+                    const int y = cy + dy, z = cz + dz;
+                    if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
+                        const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                        if (max(abs(dy), abs(dz)) == s) {
+                            sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
+                            ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
+                        } else {
+                            if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
+                            if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
                         }
                     }
                 }
+                warp_scan_batch(m, b, sa, ea, q, r2, k, lane, count, boundk, have_k, cand);
+                warp_scan_batch(m, b, sb, eb, q, r2, k, lane, count, boundk, have_k, cand);
             }
         }
         // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon
@@ -193,7 +275,7 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
             const float qq[3] = {q.x, q.y, q.z}; const int cc[3] = {cx, cy, cz};
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                int lo = cc[a] - s, hi = cc[a] + s;
+                const int lo = cc[a] - s, hi = cc[a] + s;
                 if (lo > 0) gr = fminf(gr, qq[a] - (g.origin[a] + lo * g.h));
                 if (hi < g.dims[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
             }
@@ -216,24 +298,35 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
 }
 
 // LPhoton tail (photonvolume.cpp:83-104): returns totalFlux[lane] / (4/3 pi r^3 sigma_s[lane]) in lane == bin layout.
-__device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf b, uint32_t count, v3 w, float dens_pt, float sig_s_bin,
+// The phase function is not part of any discrete decision, so it uses the fast reciprocal square root
+// (<= 2 ulp, far inside the 1e-4 radiance tolerance): PhaseHG = (1-g^2)/(4 pi) * x^-3/2.
+__device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf &b, uint32_t count, v3 w, float dens_pt, float sig_s_bin,
                                uint32_t lane) {
     if (count < 10) return 0.f;
     const uint32_t grp = lane >> 3, sub = lane & 7;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // pass 1 (lane == photon): radius of the estimate, and the per-photon phase written over d2[]
     float mx = 0.f;
     const bool iso = med.g == 0.f;
-    const float ph0 = phase_hg(V3(0.f, 0.f, 1.f), V3(0.f, 0.f, 1.f), 0.f);       // 1/(4 pi): PhaseHG with g == 0
-    const v3 nw = -w;
+    const float g = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - g * g), gg1 = 1.f + g * g, g2 = 2.f * g;
+    for (uint32_t e = lane; e < count; e += 32) {
+        mx = fmaxf(mx, b.d2[e]);
+        if (!iso) {
+            const float4 wv = __ldg(m.wi4 + b.pos[e]);
+            const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
+            const float rsq = rsqrtf(gg1 - g2 * costheta);
+            b.d2[e] = pc * rsq * rsq * rsq;
+        }
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    // pass 2: 8 lanes x float4 per 128-byte alpha line, four photons per iteration
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t e0 = 0; e0 < count; e0 += 4) {
-        uint32_t e = e0 + grp;
+        const uint32_t e = e0 + grp;
         if (e < count) {
-            uint32_t p = b.pos[e];
-            mx = fmaxf(mx, b.d2[e]);
-            float ph = ph0;
-            if (!iso) { float4 wv = __ldg(m.wi4 + p); ph = phase_hg(V3(wv.x, wv.y, wv.z), nw, med.g); }
-            float4 a = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)p * 32) + sub);
-            acc.x += a.x * ph; acc.y += a.y * ph; acc.z += a.z * ph; acc.w += a.w * ph;
+            const float ph = iso ? pc : b.d2[e];
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)b.pos[e] * 32) + sub);
+            acc.x = fmaf(a.x, ph, acc.x); acc.y = fmaf(a.y, ph, acc.y); acc.z = fmaf(a.z, ph, acc.z); acc.w = fmaf(a.w, ph, acc.w);
         }
     }
 #pragma unroll
@@ -241,28 +334,34 @@ __device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf b
         acc.x += __shfl_xor_sync(PV_FULL, acc.x, o); acc.y += __shfl_xor_sync(PV_FULL, acc.y, o);
         acc.z += __shfl_xor_sync(PV_FULL, acc.z, o); acc.w += __shfl_xor_sync(PV_FULL, acc.w, o);
     }
-    mx = warp_max(mx);
     // transpose {8 lanes x 4 bins} -> lane == bin
-    int srcl = (lane >> 2) & 7;
-    float f0 = __shfl_sync(PV_FULL, acc.x, srcl), f1 = __shfl_sync(PV_FULL, acc.y, srcl);
-    float f2 = __shfl_sync(PV_FULL, acc.z, srcl), f3 = __shfl_sync(PV_FULL, acc.w, srcl);
-    int c = lane & 3;
-    float flux = c == 0 ? f0 : (c == 1 ? f1 : (c == 2 ? f2 : f3));
-    float dV = mx * __fsqrt_rn(mx);
-    float scale = sig_s_bin * dens_pt;                                  // sigma_s(pt): density * sig_s (or inside ? sig_s : 0)
-    bool any_scale = __ballot_sync(PV_FULL, lane < PV_NSPEC && scale != 0.f) != 0;
+    const int srcl = (lane >> 2) & 7;
+    const float f0 = __shfl_sync(PV_FULL, acc.x, srcl), f1 = __shfl_sync(PV_FULL, acc.y, srcl);
+    const float f2 = __shfl_sync(PV_FULL, acc.z, srcl), f3 = __shfl_sync(PV_FULL, acc.w, srcl);
+    const int c = lane & 3;
+    const float flux = c == 0 ? f0 : (c == 1 ? f1 : (c == 2 ? f2 : f3));
+    const float dV = mx * __fsqrt_rn(mx);
+    const float scale = sig_s_bin * dens_pt;                            // sigma_s(pt): density * sig_s (or inside ? sig_s : 0)
+    const bool any_scale = __ballot_sync(PV_FULL, lane < PV_NSPEC && scale != 0.f) != 0;
     if (dV != 0.f && any_scale) {
-        float f = (float)(4.0 / 3.0 * (double)PV_PI_F * (double)dV);   // 4.0/3.0*M_PI*dV is a double expression
+        const float f = (float)(4.0 / 3.0 * (double)PV_PI_F * (double)dV);   // 4.0/3.0*M_PI*dV is a double expression
         return __fdiv_rn(flux, scale * f);
     }
     return 0.f;
 }
 
 // ------------------------------------------------------------------ kernels
-__device__ __forceinline__ WarpBuf carve(unsigned char *smem, uint32_t cap, uint32_t warp) {
-    size_t per = (size_t)cap * 8 + 1024;
-    unsigned char *base = smem + per * warp;
-    WarpBuf b; b.d2 = (float *)base; b.pos = (uint32_t *)(base + (size_t)cap * 4); b.hist = (uint32_t *)(base + (size_t)cap * 8); b.cap = cap;
+__host__ __device__ __forceinline__ size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * 8 + 1024 + 256 + 16 + (size_t)GW_STAGE * 16; }
+__device__ __forceinline__ WarpBuf carve(unsigned char *smem, uint32_t cap, uint32_t warp, uint32_t lane) {
+    unsigned char *base = smem + warp_smem_bytes(cap) * warp;
+    WarpBuf b;
+    b.d2 = (float *)base; b.pos = (uint32_t *)(base + (size_t)cap * 4); b.hist = (uint32_t *)(base + (size_t)cap * 8);
+    b.run_e = b.hist + 256; b.run_s = b.run_e + 32;
+    unsigned char *mb = (unsigned char *)(b.run_s + 32);
+    b.stage = (float4 *)(mb + 16);
+    b.mbar = smem_u32(mb); b.stage_addr = smem_u32(b.stage); b.cap = cap; b.phase = 0;
+    if (lane == 0) mbar_init(b.mbar, 1);
+    __syncwarp();
     return b;
 }
 __device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpStats &st, uint32_t rays, uint32_t lane) {
@@ -278,7 +377,7 @@ __device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpStats
 }
 
 // bitonic sort of buf[0..n2) by (d2, original index); n2 is a power of two >= count, padding = +inf
-__device__ void warp_sort_entries(const MapView &m, WarpBuf b, uint32_t count, uint32_t n2, uint32_t *oidx, uint32_t lane) {
+__device__ void warp_sort_entries(const MapView &m, WarpBuf &b, uint32_t count, uint32_t n2, uint32_t *oidx, uint32_t lane) {
     for (uint32_t e = lane; e < n2; e += 32) {
         if (e < count) oidx[e] = __float_as_uint(__ldg(&m.pos4[b.pos[e]].w));
         else { b.d2[e] = INFINITY; oidx[e] = 0xFFFFFFFFu; }
@@ -303,7 +402,7 @@ __global__ void __launch_bounds__(GW_THREADS) knn_kernel(MapView m, const float 
                                                         unsigned long long *counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpBuf b = carve(smem, cap, warp);
+    WarpBuf b = carve(smem, cap, warp, lane);
     const float r = __fsqrt_rn(r2);
     for (;;) {
         unsigned long long q = 0;
@@ -332,7 +431,7 @@ __global__ void __launch_bounds__(GW_THREADS) lphoton_kernel(MapView m, const De
                                                             float *__restrict__ L, unsigned long long *counter) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpBuf b = carve(smem, cap, warp);
+    WarpBuf b = carve(smem, cap, warp, lane);
     const DevMedium &med = sc->med;
     const float r2 = maxdist * maxdist;
     const float sig_s = lane < PV_NSPEC ? med.sigma_s[lane] : 0.f;
@@ -395,10 +494,10 @@ struct GatherArgs {
     unsigned long long *counter;
 };
 
-__global__ void __launch_bounds__(GW_THREADS) gather_kernel(GatherArgs a) {
+__global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpBuf b = carve(smem, a.cap, warp);
+    WarpBuf b = carve(smem, a.cap, warp, lane);
     const DevScene &sc = *a.sc;
     const DevMedium &med = sc.med;
     const bool bin = lane < PV_NSPEC;
@@ -546,7 +645,7 @@ __global__ void __launch_bounds__(GW_THREADS) gather_kernel(GatherArgs a) {
 
 // ------------------------------------------------------------------ host side
 static uint32_t lookup_cap(uint32_t k) {
-    uint32_t cap = k + std::max<uint32_t>(k, 128u);
+    uint32_t cap = k + 64u;                          // the list must hold k entries plus one more ballot of 32
     cap = (cap + 63u) & ~63u;
     return std::max<uint32_t>(cap, 256u);
 }
@@ -557,7 +656,7 @@ static MapView map_view(pv_ctx *ctx) {
 }
 template <typename Kern>
 static int launch_cfg(pv_ctx *ctx, Kern kern, uint32_t cap, int *blocks, size_t *smem) {
-    *smem = ((size_t)cap * 8 + 1024) * GW_WARPS;
+    *smem = warp_smem_bytes(cap) * GW_WARPS;
     if (*smem > 200 * 1024) { ctx->err = "nused too large for the shared-memory candidate list"; return PV_EINVAL; }
     PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     int per_sm = 0;
