@@ -167,29 +167,42 @@ __device__ uint32_t warp_select_k(const MapView &m, WarpBuf &b, uint32_t count, 
     return out;
 }
 
-// One batch of <= 32 photon runs (lane i holds run [rs, re) of the sorted photon array): the runs are staged
+// One batch of <= 32 photon runs (lane i holds run [rs, rs+len) of the sorted photon array).  The runs are staged
 // back to back into shared memory with TMA bulk copies, GW_STAGE candidates per round, and scanned with
-// lane == candidate.  Accepted candidates are appended to the list as (d2, slot | SLOT_FLAG).
-__device__ __forceinline__ void warp_scan_batch(const MapView &m, WarpBuf &b, uint32_t rs, uint32_t re, v3 q, float r2, uint32_t k,
-                                                uint32_t lane, uint32_t &count, float &boundk, bool &have_k, uint32_t &cand) {
-    const uint32_t len = re - rs;
-    uint32_t inc = len;
+// lane == candidate.  batch_begin() publishes the run tables and issues round 0; batch_finish() waits, scans and
+// runs the remaining rounds.  Splitting the two lets the gather issue the NEXT march step's copies before it sums
+// the current step's photons, so the copy latency hides behind the alpha loads.
+struct Batch { uint32_t rs, len, E, T; };
+
+__device__ __forceinline__ void batch_round_issue(const MapView &m, WarpBuf &b, const Batch &bt, uint32_t cb, uint32_t lane) {
+    const uint32_t cend = min(bt.T, cb + GW_STAGE);
+    // order the generic-proxy reads of the previous round before the async-proxy writes of this one
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_expect_tx(b.mbar, (cend - cb) * 16u);
+    const uint32_t lo = max(bt.E, cb), hi = min(bt.E + bt.len, cend);
+    if (lo < hi) tma_bulk_g2s(b.stage_addr + (lo - cb) * 16u, m.pos4 + bt.rs + (lo - bt.E), (hi - lo) * 16u, b.mbar);
+}
+__device__ __forceinline__ Batch batch_begin(const MapView &m, WarpBuf &b, uint32_t rs, uint32_t re, uint32_t lane) {
+    Batch bt; bt.rs = rs; bt.len = re - rs;
+    uint32_t inc = bt.len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
-    const uint32_t T = __shfl_sync(PV_FULL, inc, 31);
-    if (T == 0) return;
-    const uint32_t E = inc - len;
-    cand += T;
-    __syncwarp();                                        // earlier readers of run tables / stage are done
-    b.run_e[lane] = E; b.run_s[lane] = rs;
-    for (uint32_t cb = 0; cb < T; cb += GW_STAGE) {
-        const uint32_t cend = min(T, cb + GW_STAGE);
-        // order the generic-proxy reads of the previous round before the async-proxy writes of this one
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(b.mbar, (cend - cb) * 16u);
-        const uint32_t lo = max(E, cb), hi = min(E + len, cend);
-        if (lo < hi) tma_bulk_g2s(b.stage_addr + (lo - cb) * 16u, m.pos4 + rs + (lo - E), (hi - lo) * 16u, b.mbar);
+    bt.T = __shfl_sync(PV_FULL, inc, 31);
+    bt.E = inc - bt.len;
+    if (bt.T == 0) return bt;
+    __syncwarp();                                        // earlier readers of the run tables are done
+    b.run_e[lane] = bt.E; b.run_s[lane] = rs;
+    batch_round_issue(m, b, bt, 0, lane);
+    return bt;
+}
+__device__ __forceinline__ void batch_finish(const MapView &m, WarpBuf &b, const Batch &bt, v3 q, float r2, uint32_t k, uint32_t lane,
+                                             uint32_t &count, float &boundk, bool &have_k, uint32_t &cand) {
+    if (bt.T == 0) return;
+    cand += bt.T;
+    for (uint32_t cb = 0; cb < bt.T; cb += GW_STAGE) {
+        const uint32_t cend = min(bt.T, cb + GW_STAGE);
+        if (cb) batch_round_issue(m, b, bt, cb, lane);
         mbar_wait(b.mbar, b.phase);
         b.phase ^= 1u;
         for (uint32_t t0 = cb; t0 < cend; t0 += 32) {
@@ -215,16 +228,48 @@ __device__ __forceinline__ void warp_scan_batch(const MapView &m, WarpBuf &b, ui
     warp_convert_slots(b, count, lane);
 }
 
-// KdTree::Lookup + PhotonProcess semantics on the grid: leaves in buf the photons with d2 < r2, or, when more
-// than k of them exist, the k smallest by (d2, original index).  Returns their number.
-__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf &b, uint32_t lane, WarpStats *st) {
-    const GridParams &g = m.g;
-    if (m.n == 0 || k == 0) return 0;
-    // no photon can be within r if the query is farther than r from the grid
+// Prefetched first batch of a lookup (the 3x3x3 block of the query's cell)
+struct Prefetch { bool in_range, issued; uint32_t rs, re; Batch bt; };
+
+__device__ __forceinline__ bool lookup_in_range(const GridParams &g, v3 q, float r) {
     const float slack = r + g.margin;
-    if (q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.h + slack || q.y < g.origin[1] - slack ||
-        q.y > g.origin[1] + g.dims[1] * g.h + slack || q.z < g.origin[2] - slack || q.z > g.origin[2] + g.dims[2] * g.h + slack)
-        return 0;
+    return !(q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.h + slack || q.y < g.origin[1] - slack ||
+             q.y > g.origin[1] + g.dims[1] * g.h + slack || q.z < g.origin[2] - slack || q.z > g.origin[2] + g.dims[2] * g.h + slack);
+}
+// the nine rows of the 3x3x3 block, each ONE contiguous run of <= 3 cells: lanes 0..8 load [rs, re)
+__device__ __forceinline__ void lookup_ranges(const MapView &m, v3 q, float r, uint32_t k, uint32_t lane, Prefetch &pf) {
+    const GridParams &g = m.g;
+    pf.issued = false; pf.rs = 0; pf.re = 0;
+    pf.in_range = m.n != 0 && k != 0 && lookup_in_range(g, q, r);
+    if (!pf.in_range) return;
+    const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
+    const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
+    const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
+    if (lane < 9) {
+        const int y = cy + (int)(lane % 3u) - 1, z = cz + (int)(lane / 3u) - 1;
+        if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
+            const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+            pf.rs = __ldg(m.cell_start + (rowkey | (uint32_t)max(cx - 1, 0)));
+            pf.re = __ldg(m.cell_start + (rowkey | (uint32_t)min(cx + 1, g.dims[0] - 1)) + 1);
+        }
+    }
+}
+__device__ __forceinline__ void lookup_issue(const MapView &m, WarpBuf &b, uint32_t lane, Prefetch &pf) {
+    if (!pf.in_range) return;
+    pf.bt = batch_begin(m, b, pf.rs, pf.re, lane);
+    pf.issued = true;
+}
+
+// KdTree::Lookup + PhotonProcess semantics on the grid: leaves in buf the photons with d2 < r2, or, when more
+// than k of them exist, the k smallest by (d2, original index).  Returns their number.  `pf` may carry the first
+// batch already in flight (lookup_ranges + lookup_issue called earlier for the same q).
+__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf &b, uint32_t lane, WarpStats *st,
+                                Prefetch *pfp) {
+    const GridParams &g = m.g;
+    Prefetch pf;
+    if (pfp) pf = *pfp; else { lookup_ranges(m, q, r, k, lane, pf); }
+    if (!pf.in_range) return 0;
+    if (!pf.issued) lookup_issue(m, b, lane, pf);
     const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
     const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
     const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
@@ -233,17 +278,7 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
     float boundk = INFINITY;
     for (int s = 1;; ++s) {
         if (s == 1) {
-            // the 3x3x3 block: nine rows, each ONE contiguous run of <= 3 cells
-            uint32_t rs = 0, re = 0;
-            if (lane < 9) {
-                const int y = cy + (int)(lane % 3u) - 1, z = cz + (int)(lane / 3u) - 1;
-                if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
-                    const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-                    rs = __ldg(m.cell_start + (rowkey | (uint32_t)max(cx - 1, 0)));
-                    re = __ldg(m.cell_start + (rowkey | (uint32_t)min(cx + 1, g.dims[0] - 1)) + 1);
-                }
-            }
-            warp_scan_batch(m, b, rs, re, q, r2, k, lane, count, boundk, have_k, cand);
+            batch_finish(m, b, pf.bt, q, r2, k, lane, count, boundk, have_k, cand);
         } else {
             // shell s: rows on the rim of the (2s+1)^2 square are full runs, inner rows contribute their two end cells
             const int side = 2 * s + 1, rows = side * side;
@@ -265,8 +300,10 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
                         }
                     }
                 }
-                warp_scan_batch(m, b, sa, ea, q, r2, k, lane, count, boundk, have_k, cand);
-                warp_scan_batch(m, b, sb, eb, q, r2, k, lane, count, boundk, have_k, cand);
+                Batch ba = batch_begin(m, b, sa, ea, lane);
+                batch_finish(m, b, ba, q, r2, k, lane, count, boundk, have_k, cand);
+                Batch bb = batch_begin(m, b, sb, eb, lane);
+                batch_finish(m, b, bb, q, r2, k, lane, count, boundk, have_k, cand);
             }
         }
         // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon
@@ -319,16 +356,19 @@ __device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf &
     }
     mx = warp_max(mx);
     __syncwarp();
-    // pass 2: 8 lanes x float4 per 128-byte alpha line, four photons per iteration
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t e0 = 0; e0 < count; e0 += 4) {
-        const uint32_t e = e0 + grp;
-        if (e < count) {
-            const float ph = iso ? pc : b.d2[e];
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)b.pos[e] * 32) + sub);
-            acc.x = fmaf(a.x, ph, acc.x); acc.y = fmaf(a.y, ph, acc.y); acc.z = fmaf(a.z, ph, acc.z); acc.w = fmaf(a.w, ph, acc.w);
-        }
+    // pass 2: 8 lanes x float4 per 128-byte alpha line, eight photons (two independent loads per lane) per iteration
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t e0 = 0; e0 < count; e0 += 8) {
+        const uint32_t ea = e0 + grp, eb = e0 + 4 + grp;
+        const bool va = ea < count, vb = eb < count;
+        const uint32_t pa = va ? b.pos[ea] : 0u, pb = vb ? b.pos[eb] : 0u;
+        const float pha = va ? (iso ? pc : b.d2[ea]) : 0.f, phb = vb ? (iso ? pc : b.d2[eb]) : 0.f;
+        const float4 aa = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)pa * 32) + sub);
+        const float4 ab = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)pb * 32) + sub);
+        acc.x = fmaf(aa.x, pha, acc.x); acc.y = fmaf(aa.y, pha, acc.y); acc.z = fmaf(aa.z, pha, acc.z); acc.w = fmaf(aa.w, pha, acc.w);
+        acc2.x = fmaf(ab.x, phb, acc2.x); acc2.y = fmaf(ab.y, phb, acc2.y); acc2.z = fmaf(ab.z, phb, acc2.z); acc2.w = fmaf(ab.w, phb, acc2.w);
     }
+    acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
         acc.x += __shfl_xor_sync(PV_FULL, acc.x, o); acc.y += __shfl_xor_sync(PV_FULL, acc.y, o);
@@ -410,7 +450,7 @@ __global__ void __launch_bounds__(GW_THREADS) knn_kernel(MapView m, const float 
         q = __shfl_sync(PV_FULL, q, 0);
         if (q >= n) break;
         v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
-        uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, nullptr);
+        uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, nullptr, nullptr);
         __syncwarp();
         uint32_t n2 = 1; while (n2 < cnt) n2 <<= 1;
         if (n2 < 2) n2 = 2;
@@ -441,7 +481,7 @@ __global__ void __launch_bounds__(GW_THREADS) lphoton_kernel(MapView m, const De
         q = __shfl_sync(PV_FULL, q, 0);
         if (q >= n) break;
         v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), w = V3(ws[3 * q], ws[3 * q + 1], ws[3 * q + 2]);
-        uint32_t cnt = warp_lookup(m, p, r2, maxdist, k, b, lane, nullptr);
+        uint32_t cnt = warp_lookup(m, p, r2, maxdist, k, b, lane, nullptr, nullptr);
         __syncwarp();
         float dens = med_density(med, p, nullptr);
         float l = warp_estimate(m, med, b, cnt, w, dens, sig_s, lane);
@@ -510,6 +550,7 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
     for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
     const float r2 = a.maxdist * a.maxdist;
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
+    const bool do_lookup = !rainbow && !(a.flags & PV_GATHER_NO_INDIRECT);
     const int nLights = (int)sc.n_lights;
     WarpStats st = {0, 0, 0, 0, 0, 0};
     uint32_t nrays = 0;
@@ -586,13 +627,18 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
                 t_carry = __shfl_sync(PV_FULL, t, 31);
                 // ---------------- lane == bin: the recurrence, one step at a time
                 const int nthis = min(32, nSamples - c0);
+                Prefetch pf; pf.in_range = false; pf.issued = false;
                 for (int i = 0; i < nthis; ++i) {
                     const float s_tau = __shfl_sync(PV_FULL, tau_s, i);
                     const int s_rr = __shfl_sync(PV_FULL, rr, i);
                     Tr = expf(-(sig_t * s_tau));                          // Exp(-stepTau): per-step, not cumulative (:155)
                     if (s_rr) {
                         const float s_u = __shfl_sync(PV_FULL, u_rr, i);
-                        if (s_u > .5f) { Tr = 0.f; stop = true; break; }
+                        if (s_u > .5f) {
+                            // a prefetched batch must not stay in flight on this warp's mbarrier
+                            if (pf.issued && pf.bt.T) { mbar_wait(b.mbar, b.phase); b.phase ^= 1u; }
+                            Tr = 0.f; stop = true; break;
+                        }
                         Tr = __fdiv_rn(Tr, .5f);
                     }
                     const float s_dens = __shfl_sync(PV_FULL, dens, i);
@@ -622,9 +668,18 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
                             }
                         }
                     }
-                    if (!rainbow && !(a.flags & PV_GATHER_NO_INDIRECT)) {
-                        uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, &st);
+                    if (do_lookup) {
+                        // cell ranges of the NEXT step are requested now and consumed after this step's scan
+                        Prefetch nx; nx.in_range = false; nx.issued = false;
+                        const bool has_next = i + 1 < nthis;
+                        if (has_next) {
+                            const v3 np = V3(__shfl_sync(PV_FULL, p.x, i + 1), __shfl_sync(PV_FULL, p.y, i + 1), __shfl_sync(PV_FULL, p.z, i + 1));
+                            lookup_ranges(a.m, np, a.maxdist, a.nused, lane, nx);
+                        }
+                        uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, &st, pf.in_range || pf.issued ? &pf : nullptr);
                         __syncwarp();
+                        if (has_next) lookup_issue(a.m, b, lane, nx);       // next step's TMA copies fly during the flux sum below
+                        pf = nx;
                         L_ii = warp_estimate(a.m, med, b, cnt, w, s_dens, sig_s, lane);
                         __syncwarp();
                     }
