@@ -7,18 +7,25 @@
 //  * spectral math runs with lane == spectral bin (30 of 32 lanes busy, one register per spectrum);
 //  * the per-step scalar work of 32 consecutive march steps (positions, density taps, shadow rays through
 //    the LinearBVHNode array, shadow-ray optical depth, Philox draws) runs with lane == step;
-//  * a lookup scans the photons of the (2s+1)^3 cell block around the query with lane == candidate:
-//    128-bit loads of {x,y,z,index}, ballot/popc compaction of accepted candidates into a per-warp
-//    shared-memory list, radix-select (shared-memory histogram) when more than nused are in range;
-//  * the flux sum reads each accepted photon's 128-byte alpha line with 8 lanes x float4, four photons
-//    per warp iteration.
+//  * a lookup stages the photons {x,y,z,index} of the 3x3x3 cell block around the query into shared memory
+//    with TMA bulk copies (cp.async.bulk -> UBLKCP, one copy per contiguous cell row, completion on an
+//    mbarrier; the copies of the NEXT march step are issued before the current step's flux sum), then scans
+//    them with lane == candidate (two per lane per iteration): ballot/popc compaction of accepted candidates
+//    into a per-warp list, radix select (shared-memory histogram) when more than nused are in range;
+//  * the flux sum reads each accepted photon's 128-byte alpha line with 8 lanes x float4 (128-bit loads),
+//    eight photons per warp iteration.
 // Results: neighbour sets are bit-exact (distances use the reference's unfused (dx*dx+dy*dy)+dz*dz on
 // identical fp32 positions, ties by photon index); radiance is within 1e-4 relative of the reference
 // (summation order and libm differ), see tests/test_gpu_parity.py.
 #include <algorithm>
 #include "pv_grid.cuh"
 
+#ifndef GW_WARPS
 #define GW_WARPS 4                       // warps per CTA
+#endif
+#ifndef GW_MIN_CTAS
+#define GW_MIN_CTAS 4
+#endif
 #define GW_THREADS (GW_WARPS * 32)
 #define GW_STAGE 512                     // candidates staged per TMA round (x 16 B)
 #define SLOT_FLAG 0x80000000u            // list entry still holds a batch slot, not a photon position
@@ -28,13 +35,18 @@ struct MapView {
     GridParams g;
     uint64_t n;
 };
-// per-warp shared memory: candidate list (d2, pos), select histogram, run tables of the current batch,
-// mbarrier, TMA staging buffer
-struct WarpBuf {
-    float *d2; uint32_t *pos; uint32_t *hist; uint32_t *run_e; uint32_t *run_s; float4 *stage;
-    uint32_t mbar; uint32_t stage_addr; uint32_t cap; uint32_t phase;
-};
-struct WarpStats { uint32_t lookups, found, cand, heap, shadow, dens; };
+// per-warp shared memory: candidate list of (d2 bits, photon position) pairs, select histogram, run tables of the
+// current batch, mbarrier, TMA staging buffer
+// layout per warp: ent[cap] | hist[256] | run_e[32] | run_s[32] | stats[8] | mbarrier (16 B) | stage[GW_STAGE]
+// Only two pointers are kept in registers; everything after the list sits at constant offsets from hdr.
+struct WarpBuf { uint2 *ent; unsigned char *hdr; uint32_t cap; uint32_t phase; };
+#define WB_HDR_BYTES (1024 + 128 + 128 + 32 + 16)
+__device__ __forceinline__ uint32_t *wb_hist(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr); }
+__device__ __forceinline__ uint32_t *wb_run_e(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024); }
+__device__ __forceinline__ uint32_t *wb_run_s(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024 + 128); }
+__device__ __forceinline__ uint32_t *wb_stats(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024 + 256); }
+__device__ __forceinline__ float4 *wb_stage(const WarpBuf &b) { return reinterpret_cast<float4 *>(b.hdr + WB_HDR_BYTES); }
+enum { ST_LOOKUPS = 0, ST_FOUND, ST_CAND, ST_HEAP, ST_SHADOW, ST_DENS };
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -47,6 +59,8 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
     return v;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t wb_mbar(const WarpBuf &b) { return smem_u32(b.hdr + 1024 + 256 + 32); }
+__device__ __forceinline__ uint32_t wb_stage_addr(const WarpBuf &b) { return smem_u32(b.hdr + WB_HDR_BYTES); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -75,39 +89,41 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 // run = largest i with run_e[i] <= slot (run_e = exclusive prefix of the batch's run lengths)
 __device__ __forceinline__ void warp_convert_slots(WarpBuf &b, uint32_t count, uint32_t lane) {
     for (uint32_t e = lane; e < count; e += 32) {
-        uint32_t v = b.pos[e];
+        const uint32_t v = b.ent[e].y;
         if (v & SLOT_FLAG) {
-            uint32_t t = v & ~SLOT_FLAG, lo = 0;
+            const uint32_t t = v & ~SLOT_FLAG; uint32_t lo = 0;
 #pragma unroll
-            for (int st = 16; st > 0; st >>= 1) if (b.run_e[lo + st] <= t) lo += st;
-            b.pos[e] = b.run_s[lo] + (t - b.run_e[lo]);
+            for (int st = 16; st > 0; st >>= 1) if (wb_run_e(b)[lo + st] <= t) lo += st;
+            b.ent[e].y = wb_run_s(b)[lo] + (t - wb_run_e(b)[lo]);
         }
     }
     __syncwarp();
 }
 
-// Keep the k smallest (d2, original index) entries of buf[0..count); returns the new count (== k) and the
+// Keep the k smallest (d2, original index) entries of ent[0..count); returns the new count (== k) and the
 // k-th distance.  count > k on entry, entries hold photon positions.  MSB radix select over the fp32 bit pattern
-// (non-negative floats order like unsigned ints), 8-bit digits, histogram in shared memory.
-__device__ uint32_t warp_select_k(const MapView &m, WarpBuf &b, uint32_t count, uint32_t k, uint32_t lane, float *kth) {
+// (non-negative floats order like unsigned ints), 8-bit digits, histogram in shared memory.  Only reached when
+// more than nused photons lie within maxdist, so it is kept out of line (instruction-cache footprint).
+__device__ __noinline__ unsigned long long warp_select_k_impl(const float4 *__restrict__ pos4, uint2 *ent, uint32_t *hist, uint32_t count,
+                                                             uint32_t k, uint32_t lane) {
     uint32_t prefix = 0, need = k, m_in_bucket = 0;
     int shift = 24;
     for (int pass = 0; pass < 4; ++pass, shift -= 8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b.hist[lane * 8 + i] = 0;
+        for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
         __syncwarp();
         for (uint32_t e = lane; e < count; e += 32) {
-            uint32_t bits = __float_as_uint(b.d2[e]);
-            if (pass == 0 || (bits >> (shift + 8)) == prefix) atomicAdd(&b.hist[(bits >> shift) & 255u], 1u);
+            const uint32_t bits = ent[e].x;
+            if (pass == 0 || (bits >> (shift + 8)) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
         }
         __syncwarp();
         uint32_t loc[8], s = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { loc[i] = b.hist[lane * 8 + i]; s += loc[i]; }
+        for (int i = 0; i < 8; ++i) { loc[i] = hist[lane * 8 + i]; s += loc[i]; }
         uint32_t inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
-        uint32_t owner = __ffs(__ballot_sync(PV_FULL, inc >= need)) - 1;      // first lane whose inclusive sum reaches need
+        const uint32_t owner = __ffs(__ballot_sync(PV_FULL, inc >= need)) - 1;      // first lane whose inclusive sum reaches need
         uint32_t digit = 0, before = 0, mcount = 0;
         if (lane == owner) {
             uint32_t run = inc - s;
@@ -134,8 +150,8 @@ __device__ uint32_t warp_select_k(const MapView &m, WarpBuf &b, uint32_t count, 
         for (uint32_t t = 0; t < need; ++t) {
             uint32_t best = 0xFFFFFFFFu;
             for (uint32_t e = lane; e < count; e += 32) {
-                if (__float_as_uint(b.d2[e]) == prefix) {
-                    uint32_t oi = __float_as_uint(__ldg(&m.pos4[b.pos[e]].w));
+                if (ent[e].x == prefix) {
+                    const uint32_t oi = __float_as_uint(__ldg(&pos4[ent[e].y].w));
                     if ((first || oi > last) && oi < best) best = oi;
                 }
             }
@@ -144,27 +160,34 @@ __device__ uint32_t warp_select_k(const MapView &m, WarpBuf &b, uint32_t count, 
         tie_idx = last;
     }
     // stable in-place compaction
-    uint32_t out = 0; float mx = 0.f;
+    uint32_t out = 0, mx = 0;
     for (uint32_t e0 = 0; e0 < count; e0 += 32) {
-        uint32_t e = e0 + lane;
-        bool keep = false; float d = 0.f; uint32_t p = 0;
+        const uint32_t e = e0 + lane;
+        bool keep = false; uint2 v = make_uint2(0u, 0u);
         if (e < count) {
-            d = b.d2[e]; p = b.pos[e];
-            uint32_t v = __float_as_uint(d) >> shift;
-            if (v < prefix) keep = true;
-            else if (v == prefix) {
+            v = ent[e];
+            const uint32_t hi = v.x >> shift;
+            if (hi < prefix) keep = true;
+            else if (hi == prefix) {
                 if (m_in_bucket == need) keep = true;
-                else keep = __float_as_uint(__ldg(&m.pos4[p].w)) <= tie_idx;
+                else keep = __float_as_uint(__ldg(&pos4[v.y].w)) <= tie_idx;
             }
         }
-        uint32_t mask = __ballot_sync(PV_FULL, keep);
+        const uint32_t mask = __ballot_sync(PV_FULL, keep);
         __syncwarp();
-        if (keep) { uint32_t slot = out + __popc(mask & lanemask_lt()); b.d2[slot] = d; b.pos[slot] = p; mx = fmaxf(mx, d); }
+        if (keep) { ent[out + __popc(mask & lanemask_lt())] = v; mx = max(mx, v.x); }
         out += __popc(mask);
         __syncwarp();
     }
-    *kth = warp_max(mx);
-    return out;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PV_FULL, mx, o));
+    return ((unsigned long long)mx << 32) | out;          // (k-th distance bits, new count): no out-pointers, callers keep registers
+}
+__device__ __forceinline__ uint32_t warp_select_k(const float4 *pos4, uint2 *ent, uint32_t *hist, uint32_t count, uint32_t k, uint32_t lane,
+                                                  float &kth) {
+    const unsigned long long r = warp_select_k_impl(pos4, ent, hist, count, k, lane);
+    kth = __uint_as_float((uint32_t)(r >> 32));
+    return (uint32_t)r;
 }
 
 // One batch of <= 32 photon runs (lane i holds run [rs, rs+len) of the sorted photon array).  The runs are staged
@@ -179,9 +202,9 @@ __device__ __forceinline__ void batch_round_issue(const MapView &m, WarpBuf &b, 
     // order the generic-proxy reads of the previous round before the async-proxy writes of this one
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) mbar_expect_tx(b.mbar, (cend - cb) * 16u);
+    if (lane == 0) mbar_expect_tx(wb_mbar(b), (cend - cb) * 16u);
     const uint32_t lo = max(bt.E, cb), hi = min(bt.E + bt.len, cend);
-    if (lo < hi) tma_bulk_g2s(b.stage_addr + (lo - cb) * 16u, m.pos4 + bt.rs + (lo - bt.E), (hi - lo) * 16u, b.mbar);
+    if (lo < hi) tma_bulk_g2s(wb_stage_addr(b) + (lo - cb) * 16u, m.pos4 + bt.rs + (lo - bt.E), (hi - lo) * 16u, wb_mbar(b));
 }
 __device__ __forceinline__ Batch batch_begin(const MapView &m, WarpBuf &b, uint32_t rs, uint32_t re, uint32_t lane) {
     Batch bt; bt.rs = rs; bt.len = re - rs;
@@ -192,7 +215,7 @@ __device__ __forceinline__ Batch batch_begin(const MapView &m, WarpBuf &b, uint3
     bt.E = inc - bt.len;
     if (bt.T == 0) return bt;
     __syncwarp();                                        // earlier readers of the run tables are done
-    b.run_e[lane] = bt.E; b.run_s[lane] = rs;
+    wb_run_e(b)[lane] = bt.E; wb_run_s(b)[lane] = rs;
     batch_round_issue(m, b, bt, 0, lane);
     return bt;
 }
@@ -203,24 +226,31 @@ __device__ __forceinline__ void batch_finish(const MapView &m, WarpBuf &b, const
     for (uint32_t cb = 0; cb < bt.T; cb += GW_STAGE) {
         const uint32_t cend = min(bt.T, cb + GW_STAGE);
         if (cb) batch_round_issue(m, b, bt, cb, lane);
-        mbar_wait(b.mbar, b.phase);
+        mbar_wait(wb_mbar(b), b.phase);
         b.phase ^= 1u;
-        for (uint32_t t0 = cb; t0 < cend; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            bool acc = false; float d2 = 0.f;
-            if (t < cend) {
-                const float4 pp = b.stage[t - cb];
+        for (uint32_t t0 = cb; t0 < cend; t0 += 64) {         // two candidates per lane per iteration
+            const uint32_t ta = t0 + lane, tb = ta + 32;
+            float da = INFINITY, db = INFINITY;
+            if (ta < cend) {
+                const float4 pp = wb_stage(b)[ta - cb];
                 const float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
-                d2 = dx * dx + dy * dy + dz * dz;             // (p1 - p2).LengthSquared(), geometry.h:116,526
-                acc = d2 < r2 && d2 <= boundk;
+                da = dx * dx + dy * dy + dz * dz;             // (p1 - p2).LengthSquared(), geometry.h:116,526
             }
-            const uint32_t mask = __ballot_sync(PV_FULL, acc);
-            if (acc) { const uint32_t slot = count + __popc(mask & lanemask_lt()); b.d2[slot] = d2; b.pos[slot] = t | SLOT_FLAG; }
-            count += __popc(mask);
-            if (count + 32 > b.cap) {                         // list full: keep the k nearest so far
+            if (tb < cend) {
+                const float4 pp = wb_stage(b)[tb - cb];
+                const float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
+                db = dx * dx + dy * dy + dz * dz;
+            }
+            const bool acca = da < r2 && da <= boundk, accb = db < r2 && db <= boundk;
+            const uint32_t ma = __ballot_sync(PV_FULL, acca), mb = __ballot_sync(PV_FULL, accb);
+            const uint32_t na = __popc(ma);
+            if (acca) b.ent[count + __popc(ma & lanemask_lt())] = make_uint2(__float_as_uint(da), ta | SLOT_FLAG);
+            if (accb) b.ent[count + na + __popc(mb & lanemask_lt())] = make_uint2(__float_as_uint(db), tb | SLOT_FLAG);
+            count += na + __popc(mb);
+            if (count + 64 > b.cap) {                         // list full: keep the k nearest so far
                 __syncwarp();
                 warp_convert_slots(b, count, lane);
-                count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true;
+                count = warp_select_k(m.pos4, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true;
             }
         }
     }
@@ -236,7 +266,9 @@ __device__ __forceinline__ bool lookup_in_range(const GridParams &g, v3 q, float
     return !(q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.h + slack || q.y < g.origin[1] - slack ||
              q.y > g.origin[1] + g.dims[1] * g.h + slack || q.z < g.origin[2] - slack || q.z > g.origin[2] + g.dims[2] * g.h + slack);
 }
-// the nine rows of the 3x3x3 block, each ONE contiguous run of <= 3 cells: lanes 0..8 load [rs, re)
+// The nine rows of the 3x3x3 block, each ONE contiguous run of <= 3 cells: lanes 0..8 load [rs, re).
+// Rows (and end cells of a row) whose nearest point is at least r away cannot hold a photon with d2 < r2 and are
+// dropped; distances to cell faces are shrunk by the grid margin first, so the cull is conservative.
 __device__ __forceinline__ void lookup_ranges(const MapView &m, v3 q, float r, uint32_t k, uint32_t lane, Prefetch &pf) {
     const GridParams &g = m.g;
     pf.issued = false; pf.rs = 0; pf.re = 0;
@@ -246,11 +278,23 @@ __device__ __forceinline__ void lookup_ranges(const MapView &m, v3 q, float r, u
     const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
     const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
     if (lane < 9) {
-        const int y = cy + (int)(lane % 3u) - 1, z = cz + (int)(lane / 3u) - 1;
+        const int dy = (int)(lane % 3u) - 1, dz = (int)(lane / 3u) - 1;
+        const int y = cy + dy, z = cz + dz;
         if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
-            const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-            pf.rs = __ldg(m.cell_start + (rowkey | (uint32_t)max(cx - 1, 0)));
-            pf.re = __ldg(m.cell_start + (rowkey | (uint32_t)min(cx + 1, g.dims[0] - 1)) + 1);
+            // distance from q to the row's slab in y and z (0 for the query's own slab)
+            const float ylo = g.origin[1] + cy * g.h, zlo = g.origin[2] + cz * g.h, xlo = g.origin[0] + cx * g.h;
+            float gy = dy == 0 ? 0.f : (dy < 0 ? q.y - ylo : (ylo + g.h) - q.y);
+            float gz = dz == 0 ? 0.f : (dz < 0 ? q.z - zlo : (zlo + g.h) - q.z);
+            gy = fmaxf(gy - g.margin, 0.f); gz = fmaxf(gz - g.margin, 0.f);
+            const float w2 = r * r - (gy * gy + gz * gz);
+            if (w2 > 0.f) {
+                const float gl = fmaxf((q.x - xlo) - g.margin, 0.f), gh = fmaxf(((xlo + g.h) - q.x) - g.margin, 0.f);
+                const int xa = (cx > 0 && gl * gl < w2) ? cx - 1 : cx;
+                const int xb = (cx < g.dims[0] - 1 && gh * gh < w2) ? cx + 1 : cx;
+                const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                pf.rs = __ldg(m.cell_start + (rowkey | (uint32_t)xa));
+                pf.re = __ldg(m.cell_start + (rowkey | (uint32_t)xb) + 1);
+            }
         }
     }
 }
@@ -260,11 +304,50 @@ __device__ __forceinline__ void lookup_issue(const MapView &m, WarpBuf &b, uint3
     pf.issued = true;
 }
 
-// KdTree::Lookup + PhotonProcess semantics on the grid: leaves in buf the photons with d2 < r2, or, when more
-// than k of them exist, the k smallest by (d2, original index).  Returns their number.  `pf` may carry the first
+// shells s >= 2 of a lookup (k-nearest mode with a sparse neighbourhood): rows on the rim of the (2s+1)^2 square are
+// full runs, inner rows contribute their two end cells.  Out of line (the fixed-radius gather never gets here) and
+// with everything passed BY VALUE, so the caller's state stays in registers.
+struct ShellState { uint32_t count, cand, have_k, phase; float boundk; };
+__device__ __noinline__ ShellState lookup_shell(MapView m, WarpBuf b, int s, int cx, int cy, int cz, float qx, float qy, float qz, float r2,
+                                                uint32_t k, uint32_t lane, ShellState st) {
+    const GridParams &g = m.g;
+    const v3 q = V3(qx, qy, qz);
+    uint32_t count = st.count, cand = st.cand; float boundk = st.boundk; bool have_k = st.have_k != 0;
+    b.phase = st.phase;
+    const int side = 2 * s + 1, rows = side * side;
+    const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
+    for (int j0 = 0; j0 < rows; j0 += 32) {
+        const int j = j0 + (int)lane;
+        uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
+        if (j < rows) {
+            const int dy = j % side - s, dz = j / side - s;
+            const int y = cy + dy, z = cz + dz;
+            if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
+                const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                if (max(abs(dy), abs(dz)) == s) {
+                    sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
+                    ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
+                } else {
+                    if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
+                    if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            Batch bt = batch_begin(m, b, half ? sb : sa, half ? eb : ea, lane);
+            batch_finish(m, b, bt, q, r2, k, lane, count, boundk, have_k, cand);
+        }
+    }
+    ShellState o; o.count = count; o.cand = cand; o.have_k = have_k ? 1u : 0u; o.phase = b.phase; o.boundk = boundk;
+    return o;
+}
+
+// KdTree::Lookup + PhotonProcess semantics on the grid: leaves in ent[] the photons with d2 < r2, or, when more
+// than k of them exist, the k smallest by (d2, original index).  Returns their number.  `pfp` may carry the first
 // batch already in flight (lookup_ranges + lookup_issue called earlier for the same q).
-__device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf &b, uint32_t lane, WarpStats *st,
-                                Prefetch *pfp) {
+__device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint32_t k, WarpBuf &b, uint32_t lane,
+                                                bool stats, Prefetch *pfp) {
     const GridParams &g = m.g;
     Prefetch pf;
     if (pfp) pf = *pfp; else { lookup_ranges(m, q, r, k, lane, pf); }
@@ -277,36 +360,13 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
     bool have_k = false;
     float boundk = INFINITY;
     for (int s = 1;; ++s) {
-        if (s == 1) {
-            batch_finish(m, b, pf.bt, q, r2, k, lane, count, boundk, have_k, cand);
-        } else {
-            // shell s: rows on the rim of the (2s+1)^2 square are full runs, inner rows contribute their two end cells
-            const int side = 2 * s + 1, rows = side * side;
-            const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
-            for (int j0 = 0; j0 < rows; j0 += 32) {
-                const int j = j0 + (int)lane;
-                uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
-                if (j < rows) {
-                    const int dy = j % side - s, dz = j / side - s;
-                    const int y = cy + dy, z = cz + dz;
-                    if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
-                        const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-                        if (max(abs(dy), abs(dz)) == s) {
-                            sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
-                            ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
-                        } else {
-                            if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
-                            if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
-                        }
-                    }
-                }
-                Batch ba = batch_begin(m, b, sa, ea, lane);
-                batch_finish(m, b, ba, q, r2, k, lane, count, boundk, have_k, cand);
-                Batch bb = batch_begin(m, b, sb, eb, lane);
-                batch_finish(m, b, bb, q, r2, k, lane, count, boundk, have_k, cand);
-            }
+        if (s == 1) batch_finish(m, b, pf.bt, q, r2, k, lane, count, boundk, have_k, cand);
+        else {
+            ShellState ss; ss.count = count; ss.cand = cand; ss.have_k = have_k ? 1u : 0u; ss.phase = b.phase; ss.boundk = boundk;
+            ss = lookup_shell(m, b, s, cx, cy, cz, q.x, q.y, q.z, r2, k, lane, ss);
+            count = ss.count; cand = ss.cand; have_k = ss.have_k != 0; b.phase = ss.phase; boundk = ss.boundk;
         }
-        // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon
+        // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon with d2 < r2
         float gr = INFINITY;
         {
             const float qq[3] = {q.x, q.y, q.z}; const int cc[3] = {cx, cy, cz};
@@ -317,54 +377,64 @@ __device__ uint32_t warp_lookup(const MapView &m, v3 q, float r2, float r, uint3
                 if (hi < g.dims[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
             }
         }
-        if (count > k) { count = warp_select_k(m, b, count, k, lane, &boundk); have_k = true; }
+        if (count > k) { count = warp_select_k(m.pos4, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true; }
         if (gr == INFINITY) break;                       // the block covers the whole grid
         gr -= g.margin;
         if (gr >= r) break;                              // everything with d2 < r2 has been seen
         if (count == k) {
             if (!have_k) {                               // exactly k so far: the bound is their max distance
                 float mx = 0.f;
-                for (uint32_t e = lane; e < count; e += 32) mx = fmaxf(mx, b.d2[e]);
+                for (uint32_t e = lane; e < count; e += 32) mx = fmaxf(mx, __uint_as_float(b.ent[e].x));
                 boundk = warp_max(mx); have_k = true;
             }
             if (gr > 0.f && boundk < gr * gr) break;     // strict: an unseen photon cannot even tie
         }
     }
-    if (st) { st->lookups++; st->found += count; st->cand += cand; if (count == k) st->heap++; }
+    if (stats && lane == 0) {
+        uint32_t *st = wb_stats(b);
+        st[ST_LOOKUPS] += 1; st[ST_FOUND] += count; st[ST_CAND] += cand; if (count == k) st[ST_HEAP] += 1;
+    }
     return count;
 }
 
 // LPhoton tail (photonvolume.cpp:83-104): returns totalFlux[lane] / (4/3 pi r^3 sigma_s[lane]) in lane == bin layout.
 // The phase function is not part of any discrete decision, so it uses the fast reciprocal square root
 // (<= 2 ulp, far inside the 1e-4 radiance tolerance): PhaseHG = (1-g^2)/(4 pi) * x^-3/2.
-__device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf &b, uint32_t count, v3 w, float dens_pt, float sig_s_bin,
-                               uint32_t lane) {
+__device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf &b, uint32_t count, v3 w, float dens_pt,
+                                               float sig_s_bin, uint32_t lane) {
     if (count < 10) return 0.f;
     const uint32_t grp = lane >> 3, sub = lane & 7;
-    // pass 1 (lane == photon): radius of the estimate, and the per-photon phase written over d2[]
+    // pass 1 (lane == photon): radius of the estimate; the per-photon phase replaces d2 in the entry.
+    // The list is padded to a multiple of 8 with zero-weight entries so pass 2 needs no bounds checks
+    // (capacity: count <= k and cap >= k + 64).
     float mx = 0.f;
-    const bool iso = med.g == 0.f;
     const float g = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - g * g), gg1 = 1.f + g * g, g2 = 2.f * g;
-    for (uint32_t e = lane; e < count; e += 32) {
-        mx = fmaxf(mx, b.d2[e]);
-        if (!iso) {
-            const float4 wv = __ldg(m.wi4 + b.pos[e]);
-            const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
-            const float rsq = rsqrtf(gg1 - g2 * costheta);
-            b.d2[e] = pc * rsq * rsq * rsq;
-        }
+    const bool iso = g == 0.f;
+    const uint32_t padded = (count + 7u) & ~7u;
+    for (uint32_t e = lane; e < padded; e += 32) {
+        if (e < count) {
+            const uint2 v = b.ent[e];
+            mx = fmaxf(mx, __uint_as_float(v.x));
+            float ph = pc;
+            if (!iso) {
+                const float4 wv = __ldg(m.wi4 + v.y);
+                const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
+                const float rsq = rsqrtf(gg1 - g2 * costheta);
+                ph = pc * rsq * rsq * rsq;
+            }
+            b.ent[e].x = __float_as_uint(ph);
+        } else b.ent[e] = make_uint2(0u, 0u);
     }
     mx = warp_max(mx);
     __syncwarp();
     // pass 2: 8 lanes x float4 per 128-byte alpha line, eight photons (two independent loads per lane) per iteration
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t e0 = 0; e0 < count; e0 += 8) {
-        const uint32_t ea = e0 + grp, eb = e0 + 4 + grp;
-        const bool va = ea < count, vb = eb < count;
-        const uint32_t pa = va ? b.pos[ea] : 0u, pb = vb ? b.pos[eb] : 0u;
-        const float pha = va ? (iso ? pc : b.d2[ea]) : 0.f, phb = vb ? (iso ? pc : b.d2[eb]) : 0.f;
-        const float4 aa = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)pa * 32) + sub);
-        const float4 ab = __ldg(reinterpret_cast<const float4 *>(m.alpha32 + (size_t)pb * 32) + sub);
+    const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
+    for (uint32_t e0 = grp; e0 < padded; e0 += 8) {
+        const uint2 va = b.ent[e0], vb = b.ent[e0 + 4];
+        const float4 aa = __ldg(a4 + (size_t)va.y * 8);
+        const float4 ab = __ldg(a4 + (size_t)vb.y * 8);
+        const float pha = __uint_as_float(va.x), phb = __uint_as_float(vb.x);
         acc.x = fmaf(aa.x, pha, acc.x); acc.y = fmaf(aa.y, pha, acc.y); acc.z = fmaf(aa.z, pha, acc.z); acc.w = fmaf(aa.w, pha, acc.w);
         acc2.x = fmaf(ab.x, phb, acc2.x); acc2.y = fmaf(ab.y, phb, acc2.y); acc2.z = fmaf(ab.z, phb, acc2.z); acc2.w = fmaf(ab.w, phb, acc2.w);
     }
@@ -391,46 +461,46 @@ __device__ float warp_estimate(const MapView &m, const DevMedium &med, WarpBuf &
 }
 
 // ------------------------------------------------------------------ kernels
-__host__ __device__ __forceinline__ size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * 8 + 1024 + 256 + 16 + (size_t)GW_STAGE * 16; }
+__host__ __device__ __forceinline__ size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * 8 + WB_HDR_BYTES + (size_t)GW_STAGE * 16; }
 __device__ __forceinline__ WarpBuf carve(unsigned char *smem, uint32_t cap, uint32_t warp, uint32_t lane) {
     unsigned char *base = smem + warp_smem_bytes(cap) * warp;
     WarpBuf b;
-    b.d2 = (float *)base; b.pos = (uint32_t *)(base + (size_t)cap * 4); b.hist = (uint32_t *)(base + (size_t)cap * 8);
-    b.run_e = b.hist + 256; b.run_s = b.run_e + 32;
-    unsigned char *mb = (unsigned char *)(b.run_s + 32);
-    b.stage = (float4 *)(mb + 16);
-    b.mbar = smem_u32(mb); b.stage_addr = smem_u32(b.stage); b.cap = cap; b.phase = 0;
-    if (lane == 0) mbar_init(b.mbar, 1);
+    b.ent = (uint2 *)base; b.hdr = base + (size_t)cap * 8; b.cap = cap; b.phase = 0;
+    if (lane < 8) wb_stats(b)[lane] = 0;
+    if (lane == 0) mbar_init(wb_mbar(b), 1);
     __syncwarp();
     return b;
 }
-__device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpStats &st, uint32_t rays, uint32_t lane) {
+__device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpBuf &b, uint32_t rays, uint32_t lane) {
+    __syncwarp();
     if (lane == 0 && gs) {
+        const uint32_t *st = wb_stats(b);
         atomicAdd((unsigned long long *)&gs->rays, (unsigned long long)rays);
-        atomicAdd((unsigned long long *)&gs->lookups, (unsigned long long)st.lookups);
-        atomicAdd((unsigned long long *)&gs->photons_found, (unsigned long long)st.found);
-        atomicAdd((unsigned long long *)&gs->candidates_tested, (unsigned long long)st.cand);
-        atomicAdd((unsigned long long *)&gs->heap_lookups, (unsigned long long)st.heap);
-        atomicAdd((unsigned long long *)&gs->shadow_rays, (unsigned long long)st.shadow);
-        atomicAdd((unsigned long long *)&gs->density_samples, (unsigned long long)st.dens);
+        atomicAdd((unsigned long long *)&gs->lookups, (unsigned long long)st[ST_LOOKUPS]);
+        atomicAdd((unsigned long long *)&gs->photons_found, (unsigned long long)st[ST_FOUND]);
+        atomicAdd((unsigned long long *)&gs->candidates_tested, (unsigned long long)st[ST_CAND]);
+        atomicAdd((unsigned long long *)&gs->heap_lookups, (unsigned long long)st[ST_HEAP]);
+        atomicAdd((unsigned long long *)&gs->shadow_rays, (unsigned long long)st[ST_SHADOW]);
+        atomicAdd((unsigned long long *)&gs->density_samples, (unsigned long long)st[ST_DENS]);
     }
 }
 
-// bitonic sort of buf[0..n2) by (d2, original index); n2 is a power of two >= count, padding = +inf
+// bitonic sort of ent[0..n2) by (d2, original index); n2 is a power of two >= count, padding = +inf.
+// oidx[] (original photon indices) lives in the unused upper part of the list.
 __device__ void warp_sort_entries(const MapView &m, WarpBuf &b, uint32_t count, uint32_t n2, uint32_t *oidx, uint32_t lane) {
     for (uint32_t e = lane; e < n2; e += 32) {
-        if (e < count) oidx[e] = __float_as_uint(__ldg(&m.pos4[b.pos[e]].w));
-        else { b.d2[e] = INFINITY; oidx[e] = 0xFFFFFFFFu; }
+        if (e < count) oidx[e] = __float_as_uint(__ldg(&m.pos4[b.ent[e].y].w));
+        else { b.ent[e] = make_uint2(__float_as_uint(INFINITY), 0u); oidx[e] = 0xFFFFFFFFu; }
     }
     __syncwarp();
     for (uint32_t size = 2; size <= n2; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = lane; t < n2 / 2; t += 32) {
-                uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
-                bool up = (i & size) == 0;
-                float di = b.d2[i], dj = b.d2[j]; uint32_t oi = oidx[i], oj = oidx[j];
-                bool gt = di > dj || (di == dj && oi > oj);
-                if (gt == up) { b.d2[i] = dj; b.d2[j] = di; oidx[i] = oj; oidx[j] = oi; }
+                const uint32_t i = 2 * t - (t & (stride - 1)), j = i + stride;
+                const bool up = (i & size) == 0;
+                const uint32_t di = b.ent[i].x, dj = b.ent[j].x, oi = oidx[i], oj = oidx[j];
+                const bool gt = di > dj || (di == dj && oi > oj);
+                if (gt == up) { b.ent[i].x = dj; b.ent[j].x = di; oidx[i] = oj; oidx[j] = oi; }
             }
             __syncwarp();
         }
@@ -450,16 +520,14 @@ __global__ void __launch_bounds__(GW_THREADS) knn_kernel(MapView m, const float 
         q = __shfl_sync(PV_FULL, q, 0);
         if (q >= n) break;
         v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
-        uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, nullptr, nullptr);
+        uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, false, nullptr);
         __syncwarp();
-        uint32_t n2 = 1; while (n2 < cnt) n2 <<= 1;
-        if (n2 < 2) n2 = 2;
-        // original indices live after the entries: pos[] is reused as the index array via hist-free space
-        uint32_t *oidx = b.pos + (b.cap - n2);          // upper part of pos[]: the host sizes cap >= 2*n2 + 64
+        uint32_t n2 = 2; while (n2 < cnt) n2 <<= 1;
+        uint32_t *oidx = reinterpret_cast<uint32_t *>(b.ent + n2);      // the host sizes cap >= 2*n2 (8-byte entries, 4-byte indices)
         warp_sort_entries(m, b, cnt, n2, oidx, lane);
         for (uint32_t e = lane; e < k; e += 32) {
             idx[q * k + e] = e < cnt ? oidx[e] : 0xFFFFFFFFu;
-            d2out[q * k + e] = e < cnt ? b.d2[e] : INFINITY;
+            d2out[q * k + e] = e < cnt ? __uint_as_float(b.ent[e].x) : INFINITY;
         }
         if (lane == 0) nfound[q] = cnt;
         __syncwarp();
@@ -481,7 +549,7 @@ __global__ void __launch_bounds__(GW_THREADS) lphoton_kernel(MapView m, const De
         q = __shfl_sync(PV_FULL, q, 0);
         if (q >= n) break;
         v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), w = V3(ws[3 * q], ws[3 * q + 1], ws[3 * q + 2]);
-        uint32_t cnt = warp_lookup(m, p, r2, maxdist, k, b, lane, nullptr, nullptr);
+        uint32_t cnt = warp_lookup(m, p, r2, maxdist, k, b, lane, false, nullptr);
         __syncwarp();
         float dens = med_density(med, p, nullptr);
         float l = warp_estimate(m, med, b, cnt, w, dens, sig_s, lane);
@@ -495,7 +563,7 @@ __device__ __forceinline__ float lerp_or_zero(float x, float x0, float x1, float
     if (x < x0 || x1 < x) return 0.f;
     return y0 + __fdiv_rn((x - x0) * (y1 - y0), x1 - x0);
 }
-__device__ float rainbow_bin(float Ld, v3 w, v3 wi, uint32_t lane) {
+__device__ __noinline__ float rainbow_bin(float Ld, v3 w, v3 wi, uint32_t lane) {
     float cosTheta = vdot(wi, -w);
     float theta = 57.2957f * acosf(cosTheta);
     float I = __fdiv_rn(0.5f + 4.5f * powf((float)(0.5 * (double)(1.f + cosTheta)), 8.f), 4.f * PV_PI_F);
@@ -534,7 +602,13 @@ struct GatherArgs {
     unsigned long long *counter;
 };
 
-__global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
+// wo of Light::Sample_L(p, ...) recomputed in the spectral pass (rainbow media only)
+__device__ __forceinline__ v3 light_wo(const pv_light &l, v3 p) {
+    if (l.type == PV_LIGHT_DISTANT) return V3(l.dir[0], l.dir[1], l.dir[2]);
+    return vnorm(V3(l.pos[0], l.pos[1], l.pos[2]) - p);
+}
+
+__global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpBuf b = carve(smem, a.cap, warp, lane);
@@ -544,15 +618,16 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
     // spectra in lane == bin layout
     const float sig_a = bin ? med.sigma_a[lane] : 0.f, sig_s = bin ? med.sigma_s[lane] : 0.f, le = bin ? med.le[lane] : 0.f;
     const float sig_t = sig_a + sig_s;
-    const float cie = bin ? sc.cie_y[lane] : 0.f;
-    float sig_t_max = warp_max(sig_t);
+    const float sig_t_max = warp_max(sig_t);
     float y_sig_a = 0.f, y_sig_s = 0.f;
     for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
+    const bool y_any = y_sig_a != 0.f || y_sig_s != 0.f;                 // sa.y() != 0 || ss.y() != 0 wherever the density is non-zero
+    const bool any_sig_s = __ballot_sync(PV_FULL, sig_s != 0.f) != 0;    // !ss.IsBlack() wherever the density is non-zero
     const float r2 = a.maxdist * a.maxdist;
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
     const bool do_lookup = !rainbow && !(a.flags & PV_GATHER_NO_INDIRECT);
+    const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
     const int nLights = (int)sc.n_lights;
-    WarpStats st = {0, 0, 0, 0, 0, 0};
     uint32_t nrays = 0;
     for (;;) {
         unsigned long long ri = 0;
@@ -564,130 +639,109 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
         const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
         float Tr = 1.f, Lv = 0.f;
         float t0, t1;
-        bool hit = med.type != PV_MEDIUM_NONE && med_intersectp(med, ro, rd, ray.mint, ray.maxt, &t0, &t1) && (t1 - t0) != 0.f;
+        const bool hit = med.type != PV_MEDIUM_NONE && med_intersectp(med, ro, rd, ray.mint, ray.maxt, &t0, &t1) && (t1 - t0) != 0.f;
         if (hit) {
             const int nSamples = (int)ceilf(__fdiv_rn(t1 - t0, a.stepsize));
             const float step = __fdiv_rn(t1 - t0, (float)nSamples);
-            const v3 p_first = ray_at(ro, rd, t0);
-            const v3 w = -rd;
+            const float t_first = t0;                           // p = ray(t0) before the jitter (photonvolume.cpp:133)
             float tbase = t0 + ray.u_scatter * step;            // t0 += u * step
             float t_carry = tbase;
             const uint64_t gidx = a.ray_index_base + ri;
-            uint32_t rw[4];
-            pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
             bool stop = false;
             for (int c0 = 0; c0 < nSamples && !stop; c0 += 32) {
-                // ---------------- lane == step: everything that does not depend on the recurrence
+                // ---------------- lane == step: everything that does not depend on the recurrence.
+                // Per step only seven scalars survive into the spectral pass:
+                //   c_t     sample parameter (p = ray(c_t))
+                //   c_tau   optical-depth scalar of the step segment (tau[b] = sig_t[b] * c_tau)
+                //   c_rr    Russian-roulette draw if Tr.y() < 1e-3 at this step, else -1
+                //   c_dens  density at p (1/0 for homogeneous media)
+                //   c_ln    light chosen for the step
+                //   c_sh    optical-depth scalar of the shadow ray
+                //   c_dfac  falloff / dist^2 * phase * nLights (0: unlit / occluded): L_d[b] = I[b] * exp(-sig_t[b]*c_sh) * c_dfac
                 const int si = c0 + (int)lane;
-                const bool live = si < nSamples;
-                float t = tbase;
-                for (uint32_t j = 0; j < lane; ++j) t += step;     // the reference accumulates t0 += step (photonvolume.cpp:147)
-                float tprev = t_carry;                             // t of the previous step (lane 0: last step of the previous chunk)
-                if (lane > 0) { tprev = tbase; for (uint32_t j = 0; j + 1 < lane; ++j) tprev += step; }
-                const v3 p = ray_at(ro, rd, t);
-                const v3 pPrev = (si == 0) ? p_first : ray_at(ro, rd, tprev);
-                float tau_s = 0.f, dens = 0.f, u_rr = 0.f, sh_tau = 0.f, ph_d = 0.f, fall = 0.f, ld2 = 1.f;
-                int ln = 0, vis = 0, rr = 0;
-                v3 wo = V3(0.f, 0.f, 1.f);
-                uint32_t sw[4] = {0, 0, 0, 0};
-                if (live) {
+                float c_t = tbase;
+                for (uint32_t j = 0; j < lane; ++j) c_t += step;     // the reference accumulates t0 += step (photonvolume.cpp:147)
+                float c_tau = 0.f, c_rr = -1.f, c_dens = 0.f, c_sh = 0.f, c_dfac = 0.f;
+                int c_ln = 0;
+                uint32_t ns = 0, nshadow = 0;
+                if (si < nSamples) {
+                    float tprev = t_carry;                           // previous step (lane 0: last step of the previous chunk)
+                    if (lane > 0) { tprev = tbase; for (uint32_t j = 0; j + 1 < lane; ++j) tprev += step; }
+                    const v3 p = ray_at(ro, rd, c_t);
+                    const v3 pPrev = ray_at(ro, rd, si == 0 ? t_first : tprev);
+                    uint32_t sw[4];
                     pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_STEP, a.k0, a.k1, sw);
-                }
-                if (live) {
-                    uint32_t ns = 0;
-                    tau_s = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
-                    u_rr = pv_u32_to_float(sw[1]);
-                    // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau_s) bounds every bin from below; y(1) ~ 1
-                    if (sig_t_max * tau_s > 6.0f) {
+                    c_tau = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
+                    // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau) bounds every bin from below and y(1) ~ 1, so only large taus need the sum
+                    if (sig_t_max * c_tau > 6.0f) {
                         float yy = 0.f;
-                        for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * tau_s));
-                        rr = __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f;
+                        for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * c_tau));
+                        if (__fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f) c_rr = pv_u32_to_float(sw[1]);
                     }
-                    dens = med_density(med, p, &ns);
-                    if (dens != 0.f && nLights > 0 && !(a.flags & PV_GATHER_NO_DIRECT)) {
-                        float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
-                        ln = min((int)floorf(u_l * nLights), nLights - 1);
+                    c_dens = med_density(med, p, &ns);
+                    if (c_dens != 0.f && do_direct) {
+                        uint32_t rw[4];
+                        pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
+                        const float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
+                        c_ln = min((int)floorf(u_l * nLights), nLights - 1);
                         LightQuery lq;
-                        light_query(sc.lights[ln], p, &lq);
-                        wo = lq.wi; fall = lq.falloff; ld2 = lq.point_like ? lq.inv_mode_d2 : -1.f;
-                        // L.IsBlack() is decided per bin in the spectral pass; the shadow ray is traced whenever it could matter
-                        if (fall != 0.f) {
-                            st.shadow++;
+                        light_query(sc.lights[c_ln], p, &lq);
+                        if (lq.falloff != 0.f) {
+                            nshadow = 1;
                             float mt = lq.vis_maxt;
-                            vis = bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0;
-                            if (vis) {
-                                sh_tau = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize,
-                                                        pv_u32_to_float(sw[2]), &ns);
-                                ph_d = med_phase(med, p, w, -wo);
+                            if (bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
+                                c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize,
+                                                      pv_u32_to_float(sw[2]), &ns);
+                                const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
+                                c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
                             }
                         }
                     }
-                    st.dens += ns;
                 }
-                t_carry = __shfl_sync(PV_FULL, t, 31);
+                __syncwarp();
+                ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);
+                if (lane == 0) { wb_stats(b)[ST_DENS] += ns; wb_stats(b)[ST_SHADOW] += nshadow; }
+                t_carry = __shfl_sync(PV_FULL, c_t, 31);
                 // ---------------- lane == bin: the recurrence, one step at a time
                 const int nthis = min(32, nSamples - c0);
                 Prefetch pf; pf.in_range = false; pf.issued = false;
                 for (int i = 0; i < nthis; ++i) {
-                    const float s_tau = __shfl_sync(PV_FULL, tau_s, i);
-                    const int s_rr = __shfl_sync(PV_FULL, rr, i);
+                    const float s_tau = __shfl_sync(PV_FULL, c_tau, i);
+                    const float s_rr = __shfl_sync(PV_FULL, c_rr, i);
                     Tr = expf(-(sig_t * s_tau));                          // Exp(-stepTau): per-step, not cumulative (:155)
-                    if (s_rr) {
-                        const float s_u = __shfl_sync(PV_FULL, u_rr, i);
-                        if (s_u > .5f) {
+                    if (s_rr >= 0.f) {
+                        if (s_rr > .5f) {
                             // a prefetched batch must not stay in flight on this warp's mbarrier
-                            if (pf.issued && pf.bt.T) { mbar_wait(b.mbar, b.phase); b.phase ^= 1u; }
+                            if (pf.issued && pf.bt.T) { mbar_wait(wb_mbar(b), b.phase); b.phase ^= 1u; }
                             Tr = 0.f; stop = true; break;
                         }
-                        Tr = __fdiv_rn(Tr, .5f);
+                        Tr = Tr * 2.f;                                    // Tr /= continueProb (0.5): exact
                     }
-                    const float s_dens = __shfl_sync(PV_FULL, dens, i);
-                    const v3 sp = V3(__shfl_sync(PV_FULL, p.x, i), __shfl_sync(PV_FULL, p.y, i), __shfl_sync(PV_FULL, p.z, i));
+                    const float s_dens = __shfl_sync(PV_FULL, c_dens, i);
+                    const v3 sp = ray_at(ro, rd, __shfl_sync(PV_FULL, c_t, i));
                     const float ss = sig_s * s_dens, sa = sig_a * s_dens;
                     float L_d = 0.f, L_ii = 0.f;
-                    const int s_vis = __shfl_sync(PV_FULL, vis, i);
-                    if (s_vis) {
-                        const int s_ln = __shfl_sync(PV_FULL, ln, i);
-                        const float s_fall = __shfl_sync(PV_FULL, fall, i), s_ld2 = __shfl_sync(PV_FULL, ld2, i);
-                        const float s_sh = __shfl_sync(PV_FULL, sh_tau, i), s_ph = __shfl_sync(PV_FULL, ph_d, i);
-                        const pv_light &lt = sc.lights[s_ln];
+                    const float s_dfac = __shfl_sync(PV_FULL, c_dfac, i);
+                    if (s_dfac != 0.f) {
+                        const pv_light &lt = sc.lights[__shfl_sync(PV_FULL, c_ln, i)];
                         const float I = bin ? lt.intensity[lane] : 0.f;
-                        float Lb;
-                        if (s_ld2 < 0.f) Lb = I;
-                        else if (lt.type == PV_LIGHT_SPOT) Lb = __fdiv_rn(I * s_fall, s_ld2);
-                        else Lb = __fdiv_rn(I, s_ld2);
-                        const bool black = __ballot_sync(PV_FULL, bin && Lb != 0.f) == 0;
-                        const bool ss_black = __ballot_sync(PV_FULL, bin && ss != 0.f) == 0;
-                        if (!black && !ss_black) {
-                            const float Ld = Lb * expf(-(sig_t * s_sh));
-                            if (rainbow) {
-                                const v3 swo = V3(__shfl_sync(PV_FULL, wo.x, i), __shfl_sync(PV_FULL, wo.y, i), __shfl_sync(PV_FULL, wo.z, i));
-                                L_d = rainbow_bin(Ld, rd, swo, lane);
-                            } else {
-                                L_d = __fdiv_rn((Ld * s_ph) * (float)nLights, 1.f);
-                            }
-                        }
+                        const float Ld = (I * expf(-(sig_t * __shfl_sync(PV_FULL, c_sh, i)))) * s_dfac;
+                        L_d = rainbow ? rainbow_bin(Ld, rd, light_wo(lt, sp), lane) : Ld;
                     }
                     if (do_lookup) {
                         // cell ranges of the NEXT step are requested now and consumed after this step's scan
                         Prefetch nx; nx.in_range = false; nx.issued = false;
                         const bool has_next = i + 1 < nthis;
-                        if (has_next) {
-                            const v3 np = V3(__shfl_sync(PV_FULL, p.x, i + 1), __shfl_sync(PV_FULL, p.y, i + 1), __shfl_sync(PV_FULL, p.z, i + 1));
-                            lookup_ranges(a.m, np, a.maxdist, a.nused, lane, nx);
-                        }
-                        uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, &st, pf.in_range || pf.issued ? &pf : nullptr);
+                        if (has_next) lookup_ranges(a.m, ray_at(ro, rd, __shfl_sync(PV_FULL, c_t, i + 1)), a.maxdist, a.nused, lane, nx);
+                        const uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, true, pf.in_range ? &pf : nullptr);
                         __syncwarp();
                         if (has_next) lookup_issue(a.m, b, lane, nx);       // next step's TMA copies fly during the flux sum below
                         pf = nx;
-                        L_ii = warp_estimate(a.m, med, b, cnt, w, s_dens, sig_s, lane);
+                        L_ii = warp_estimate(a.m, med, b, cnt, -rd, s_dens, sig_s, lane);
                         __syncwarp();
                     }
-                    // sa.y() != 0 || ss.y() != 0  (photonvolume.cpp:210): y(sig * density) vanishes with the density or with y(sig)
-                    const bool y_a = s_dens != 0.f && y_sig_a != 0.f, y_s = s_dens != 0.f && y_sig_s != 0.f;
-                    float L_i;
-                    if (y_a || y_s) L_i = L_d + __fdiv_rn(ss, sa + ss) * L_ii;
-                    else L_i = L_d;
+                    // L_i = L_d + (ss/(sa+ss)) * L_ii unless sa.y() == 0 && ss.y() == 0 (photonvolume.cpp:210-213)
+                    const float L_i = (s_dens != 0.f && y_any) ? L_d + __fdiv_rn(ss, sa + ss) * L_ii : L_d;
                     Lv = ((sa * (le * s_dens)) * step) + ((ss * L_i) * step) + (Tr * Lv);
                 }
                 tbase = t_carry + step;
@@ -695,12 +749,12 @@ __global__ void __launch_bounds__(GW_THREADS, 4) gather_kernel(GatherArgs a) {
         }
         if (bin) { a.L[ri * PV_NSPEC + lane] = hit ? Lv : 0.f; a.T[ri * PV_NSPEC + lane] = hit ? Tr : 1.f; }
     }
-    flush_stats(a.stats, st, nrays, lane);
+    flush_stats(a.stats, b, nrays, lane);
 }
 
 // ------------------------------------------------------------------ host side
 static uint32_t lookup_cap(uint32_t k) {
-    uint32_t cap = k + 64u;                          // the list must hold k entries plus one more ballot of 32
+    uint32_t cap = k + 64u;                          // the list must hold k entries plus one more iteration of 64 candidates
     cap = (cap + 63u) & ~63u;
     return std::max<uint32_t>(cap, 256u);
 }
@@ -726,6 +780,7 @@ int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, u
     if (n == 0 || k == 0) return PV_OK;
     uint32_t n2 = 2; while (n2 < k) n2 <<= 1;
     uint32_t cap = std::max(lookup_cap(k), 2 * n2 + 64);
+    cap = (cap + 63u) & ~63u;
     int blocks; size_t smem;
     int rc = launch_cfg(ctx, knn_kernel, cap, &blocks, &smem); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
