@@ -218,7 +218,7 @@ __global__ void keys_kernel(const float *__restrict__ pos, uint64_t n, GridParam
 // the first lane of each group also moves pos/wi into the float4 planes.
 __global__ void gather_records_kernel(const uint32_t *__restrict__ order, uint64_t n, const float *__restrict__ pos,
                                       const float *__restrict__ wi, const float *__restrict__ alpha, float4 *__restrict__ pos4,
-                                      float4 *__restrict__ wi4, float *__restrict__ alpha32, const DevScene *__restrict__ sc) {
+                                      float4 *__restrict__ wi4, float *__restrict__ alpha32, uint32_t *__restrict__ orig, const DevScene *__restrict__ sc) {
     uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
     uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -234,7 +234,8 @@ __global__ void gather_records_kernel(const uint32_t *__restrict__ order, uint64
         if (gate && !bbox_inside(sc->med.p0, sc->med.p1, med_to_volume_p(sc->med, V3(px, py, pz)))) a = make_float4(0.f, 0.f, 0.f, 0.f);
         *(reinterpret_cast<float4 *>(alpha32 + j * 32) + sub) = a;
         if (sub == 0) {
-            pos4[j] = make_float4(px, py, pz, __uint_as_float(src));
+            pos4[j] = make_float4(px, py, pz, __uint_as_float((uint32_t)j));
+            orig[j] = src;
             wi4[j] = make_float4(wi[(uint64_t)src * 3], wi[(uint64_t)src * 3 + 1], wi[(uint64_t)src * 3 + 2], 0.f);
         }
     }
@@ -293,7 +294,9 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     }
     double rho = (double)n / vol;
     double hk = std::cbrt(3.0 * (double)std::max<uint32_t>(nused, 1) / (4.0 * M_PI * rho));
-    double h = std::min((double)maxdist, hk);
+    // a hair above maxdist, so that the 3x3x3 block provably holds every photon within maxdist (see one_shell_r)
+    const double margin_est = 1.01e-4 * (double)maxdist + 4e-6 * (maxabs + maxext);
+    double h = std::min((double)maxdist + 3.0 * margin_est, hk);
     const int max_dim = 256;                                  // key bits <= 24 -> cell table <= 64 MiB
     h = std::max(h, maxext / (max_dim - 1));
     h = std::max(h, 1e-6);
@@ -308,6 +311,7 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     g.yzbits = ceil_log2(std::max(g.dims[1], g.dims[2]));
     g.table_size = (uint32_t)1 << (g.xbits + 2 * g.yzbits);
     g.margin = (float)(1e-4 * h + 4e-6 * (maxabs + maxext));
+    g.one_shell_r = g.h - 2.f * g.margin;            // lookups with r <= this never need more than the 3x3x3 block
     int key_bits = std::max(1, g.xbits + 2 * g.yzbits);
 
     // 3. keys + sort
@@ -325,16 +329,18 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
         if (ctx->m_pos4) cudaFree(ctx->m_pos4);
         if (ctx->m_wi4) cudaFree(ctx->m_wi4);
         if (ctx->m_alpha32) cudaFree(ctx->m_alpha32);
-        ctx->m_pos4 = nullptr; ctx->m_wi4 = nullptr; ctx->m_alpha32 = nullptr; ctx->map_cap = 0;
+        if (ctx->m_orig) cudaFree(ctx->m_orig);
+        ctx->m_pos4 = nullptr; ctx->m_wi4 = nullptr; ctx->m_alpha32 = nullptr; ctx->m_orig = nullptr; ctx->map_cap = 0;
         PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->m_pos4, nn * sizeof(float4)));
         PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->m_wi4, nn * sizeof(float4)));
         PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->m_alpha32, nn * 32 * sizeof(float)));
+        PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->m_orig, nn * sizeof(uint32_t)));
         ctx->map_cap = n;
     }
     {
         int blocks = (int)std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * 16);
         gather_records_kernel<<<blocks, 256, 0, ctx->stream>>>(svals, n, ctx->d_pos, ctx->d_wi, ctx->d_alpha, ctx->m_pos4, ctx->m_wi4,
-                                                             ctx->m_alpha32, ctx->has_scene ? ctx->dscene : nullptr);
+                                                             ctx->m_alpha32, ctx->m_orig, ctx->has_scene ? ctx->dscene : nullptr);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     // 5. cell table

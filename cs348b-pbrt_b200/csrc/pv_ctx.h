@@ -16,6 +16,7 @@ struct GridParams {
     int xbits, yzbits;      // key bits: xbits + 2*yzbits
     uint32_t table_size;    // number of keys (cell_start has table_size + 1 entries)
     float margin;           // conservative slack subtracted from the guaranteed search radius
+    float one_shell_r;      // radius up to which the 3x3x3 block of an in-grid query is exhaustive
 };
 
 struct pv_ctx {
@@ -37,7 +38,8 @@ struct pv_ctx {
     uint64_t n_photons = 0, cap_photons = 0;
 
     // the map: photons sorted by cell key
-    float4 *m_pos4 = nullptr;      // x, y, z, original index (bits)
+    float4 *m_pos4 = nullptr;      // x, y, z, sorted position (bits)
+    uint32_t *m_orig = nullptr;    // sorted position -> original photon index
     float4 *m_wi4 = nullptr;       // wi.xyz, 0
     float *m_alpha32 = nullptr;    // 32 floats per photon: alpha[30], 0, 0  (one 128-byte line)
     uint32_t *cell_start = nullptr;

@@ -28,23 +28,22 @@
 #endif
 #define GW_THREADS (GW_WARPS * 32)
 #define GW_STAGE 512                     // candidates staged per TMA round (x 16 B)
-#define SLOT_FLAG 0x80000000u            // list entry still holds a batch slot, not a photon position
 
 struct MapView {
-    const float4 *pos4; const float4 *wi4; const float *alpha32; const uint32_t *cell_start;
+    const float4 *pos4;            // x, y, z, sorted position of the photon (bits): a staged candidate carries its own address
+    const float4 *wi4; const float *alpha32; const uint32_t *cell_start;
+    const uint32_t *orig;          // sorted position -> original photon index (tie-breaks and the k-NN output only)
     GridParams g;
     uint64_t n;
 };
 // per-warp shared memory: candidate list of (d2 bits, photon position) pairs, select histogram, run tables of the
 // current batch, mbarrier, TMA staging buffer
-// layout per warp: ent[cap] | hist[256] | run_e[32] | run_s[32] | stats[8] | mbarrier (16 B) | stage[GW_STAGE]
+// layout per warp: ent[cap] | hist[256] | stats[8] | mbarrier (16 B) | stage[GW_STAGE]
 // Only two pointers are kept in registers; everything after the list sits at constant offsets from hdr.
 struct WarpBuf { uint2 *ent; unsigned char *hdr; uint32_t cap; uint32_t phase; };
-#define WB_HDR_BYTES (1024 + 128 + 128 + 32 + 16)
+#define WB_HDR_BYTES (1024 + 32 + 16)
 __device__ __forceinline__ uint32_t *wb_hist(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr); }
-__device__ __forceinline__ uint32_t *wb_run_e(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024); }
-__device__ __forceinline__ uint32_t *wb_run_s(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024 + 128); }
-__device__ __forceinline__ uint32_t *wb_stats(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024 + 256); }
+__device__ __forceinline__ uint32_t *wb_stats(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024); }
 __device__ __forceinline__ float4 *wb_stage(const WarpBuf &b) { return reinterpret_cast<float4 *>(b.hdr + WB_HDR_BYTES); }
 enum { ST_LOOKUPS = 0, ST_FOUND, ST_CAND, ST_HEAP, ST_SHADOW, ST_DENS };
 
@@ -59,7 +58,7 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
     return v;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t wb_mbar(const WarpBuf &b) { return smem_u32(b.hdr + 1024 + 256 + 32); }
+__device__ __forceinline__ uint32_t wb_mbar(const WarpBuf &b) { return smem_u32(b.hdr + 1024 + 32); }
 __device__ __forceinline__ uint32_t wb_stage_addr(const WarpBuf &b) { return smem_u32(b.hdr + WB_HDR_BYTES); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
@@ -85,26 +84,11 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-// list entries appended during a batch hold (slot | SLOT_FLAG); turn them into sorted photon positions:
-// run = largest i with run_e[i] <= slot (run_e = exclusive prefix of the batch's run lengths)
-__device__ __forceinline__ void warp_convert_slots(WarpBuf &b, uint32_t count, uint32_t lane) {
-    for (uint32_t e = lane; e < count; e += 32) {
-        const uint32_t v = b.ent[e].y;
-        if (v & SLOT_FLAG) {
-            const uint32_t t = v & ~SLOT_FLAG; uint32_t lo = 0;
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1) if (wb_run_e(b)[lo + st] <= t) lo += st;
-            b.ent[e].y = wb_run_s(b)[lo] + (t - wb_run_e(b)[lo]);
-        }
-    }
-    __syncwarp();
-}
-
 // Keep the k smallest (d2, original index) entries of ent[0..count); returns the new count (== k) and the
 // k-th distance.  count > k on entry, entries hold photon positions.  MSB radix select over the fp32 bit pattern
 // (non-negative floats order like unsigned ints), 8-bit digits, histogram in shared memory.  Only reached when
 // more than nused photons lie within maxdist, so it is kept out of line (instruction-cache footprint).
-__device__ __noinline__ unsigned long long warp_select_k_impl(const float4 *__restrict__ pos4, uint2 *ent, uint32_t *hist, uint32_t count,
+__device__ __noinline__ unsigned long long warp_select_k_impl(const uint32_t *__restrict__ orig, uint2 *ent, uint32_t *hist, uint32_t count,
                                                              uint32_t k, uint32_t lane) {
     uint32_t prefix = 0, need = k, m_in_bucket = 0;
     int shift = 24;
@@ -151,7 +135,7 @@ __device__ __noinline__ unsigned long long warp_select_k_impl(const float4 *__re
             uint32_t best = 0xFFFFFFFFu;
             for (uint32_t e = lane; e < count; e += 32) {
                 if (ent[e].x == prefix) {
-                    const uint32_t oi = __float_as_uint(__ldg(&pos4[ent[e].y].w));
+                    const uint32_t oi = __ldg(&orig[ent[e].y]);
                     if ((first || oi > last) && oi < best) best = oi;
                 }
             }
@@ -170,7 +154,7 @@ __device__ __noinline__ unsigned long long warp_select_k_impl(const float4 *__re
             if (hi < prefix) keep = true;
             else if (hi == prefix) {
                 if (m_in_bucket == need) keep = true;
-                else keep = __float_as_uint(__ldg(&pos4[v.y].w)) <= tie_idx;
+                else keep = __ldg(&orig[v.y]) <= tie_idx;
             }
         }
         const uint32_t mask = __ballot_sync(PV_FULL, keep);
@@ -183,9 +167,9 @@ __device__ __noinline__ unsigned long long warp_select_k_impl(const float4 *__re
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PV_FULL, mx, o));
     return ((unsigned long long)mx << 32) | out;          // (k-th distance bits, new count): no out-pointers, callers keep registers
 }
-__device__ __forceinline__ uint32_t warp_select_k(const float4 *pos4, uint2 *ent, uint32_t *hist, uint32_t count, uint32_t k, uint32_t lane,
+__device__ __forceinline__ uint32_t warp_select_k(const uint32_t *orig, uint2 *ent, uint32_t *hist, uint32_t count, uint32_t k, uint32_t lane,
                                                   float &kth) {
-    const unsigned long long r = warp_select_k_impl(pos4, ent, hist, count, k, lane);
+    const unsigned long long r = warp_select_k_impl(orig, ent, hist, count, k, lane);
     kth = __uint_as_float((uint32_t)(r >> 32));
     return (uint32_t)r;
 }
@@ -214,8 +198,6 @@ __device__ __forceinline__ Batch batch_begin(const MapView &m, WarpBuf &b, uint3
     bt.T = __shfl_sync(PV_FULL, inc, 31);
     bt.E = inc - bt.len;
     if (bt.T == 0) return bt;
-    __syncwarp();                                        // earlier readers of the run tables are done
-    wb_run_e(b)[lane] = bt.E; wb_run_s(b)[lane] = rs;
     batch_round_issue(m, b, bt, 0, lane);
     return bt;
 }
@@ -230,36 +212,36 @@ __device__ __forceinline__ void batch_finish(const MapView &m, WarpBuf &b, const
         b.phase ^= 1u;
         for (uint32_t t0 = cb; t0 < cend; t0 += 64) {         // two candidates per lane per iteration
             const uint32_t ta = t0 + lane, tb = ta + 32;
-            float da = INFINITY, db = INFINITY;
+            float da = INFINITY, db = INFINITY; uint32_t pa = 0, pb = 0;
             if (ta < cend) {
                 const float4 pp = wb_stage(b)[ta - cb];
                 const float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
                 da = dx * dx + dy * dy + dz * dz;             // (p1 - p2).LengthSquared(), geometry.h:116,526
+                pa = __float_as_uint(pp.w);
             }
             if (tb < cend) {
                 const float4 pp = wb_stage(b)[tb - cb];
                 const float dx = pp.x - q.x, dy = pp.y - q.y, dz = pp.z - q.z;
                 db = dx * dx + dy * dy + dz * dz;
+                pb = __float_as_uint(pp.w);
             }
             const bool acca = da < r2 && da <= boundk, accb = db < r2 && db <= boundk;
             const uint32_t ma = __ballot_sync(PV_FULL, acca), mb = __ballot_sync(PV_FULL, accb);
             const uint32_t na = __popc(ma);
-            if (acca) b.ent[count + __popc(ma & lanemask_lt())] = make_uint2(__float_as_uint(da), ta | SLOT_FLAG);
-            if (accb) b.ent[count + na + __popc(mb & lanemask_lt())] = make_uint2(__float_as_uint(db), tb | SLOT_FLAG);
+            if (acca) b.ent[count + __popc(ma & lanemask_lt())] = make_uint2(__float_as_uint(da), pa);
+            if (accb) b.ent[count + na + __popc(mb & lanemask_lt())] = make_uint2(__float_as_uint(db), pb);
             count += na + __popc(mb);
             if (count + 64 > b.cap) {                         // list full: keep the k nearest so far
                 __syncwarp();
-                warp_convert_slots(b, count, lane);
-                count = warp_select_k(m.pos4, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true;
+                count = warp_select_k(m.orig, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true;
             }
         }
     }
     __syncwarp();
-    warp_convert_slots(b, count, lane);
 }
 
 // Prefetched first batch of a lookup (the 3x3x3 block of the query's cell)
-struct Prefetch { bool in_range, issued; uint32_t rs, re; Batch bt; };
+struct Prefetch { bool in_range, issued, fast; int cx, cy, cz; uint32_t rs, re; Batch bt; };
 
 __device__ __forceinline__ bool lookup_in_range(const GridParams &g, v3 q, float r) {
     const float slack = r + g.margin;
@@ -271,12 +253,16 @@ __device__ __forceinline__ bool lookup_in_range(const GridParams &g, v3 q, float
 // dropped; distances to cell faces are shrunk by the grid margin first, so the cull is conservative.
 __device__ __forceinline__ void lookup_ranges(const MapView &m, v3 q, float r, uint32_t k, uint32_t lane, Prefetch &pf) {
     const GridParams &g = m.g;
-    pf.issued = false; pf.rs = 0; pf.re = 0;
-    pf.in_range = m.n != 0 && k != 0 && lookup_in_range(g, q, r);
+    pf.issued = false; pf.fast = false; pf.rs = 0; pf.re = 0;
+    // unclamped cell of the query: inside the grid is the common case and needs no distance test
+    const int ux = (int)floorf((q.x - g.origin[0]) * g.inv_h), uy = (int)floorf((q.y - g.origin[1]) * g.inv_h),
+              uz = (int)floorf((q.z - g.origin[2]) * g.inv_h);
+    const bool inside = ux >= 0 && ux < g.dims[0] && uy >= 0 && uy < g.dims[1] && uz >= 0 && uz < g.dims[2];
+    pf.in_range = m.n != 0 && k != 0 && (inside || lookup_in_range(g, q, r));
     if (!pf.in_range) return;
-    const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
-    const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
-    const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
+    const int cx = min(max(ux, 0), g.dims[0] - 1), cy = min(max(uy, 0), g.dims[1] - 1), cz = min(max(uz, 0), g.dims[2] - 1);
+    pf.cx = cx; pf.cy = cy; pf.cz = cz;
+    pf.fast = inside && r <= g.one_shell_r;              // the 3x3x3 block is exhaustive: no shell loop, no radius bookkeeping
     if (lane < 9) {
         const int dy = (int)(lane % 3u) - 1, dz = (int)(lane / 3u) - 1;
         const int y = cy + dy, z = cz + dz;
@@ -353,9 +339,7 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
     if (pfp) pf = *pfp; else { lookup_ranges(m, q, r, k, lane, pf); }
     if (!pf.in_range) return 0;
     if (!pf.issued) lookup_issue(m, b, lane, pf);
-    const int cx = pv_cell_coord(q.x, g.origin[0], g.inv_h, g.dims[0]);
-    const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]);
-    const int cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
+    const int cx = pf.cx, cy = pf.cy, cz = pf.cz;
     uint32_t count = 0, cand = 0;
     bool have_k = false;
     float boundk = INFINITY;
@@ -366,6 +350,8 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
             ss = lookup_shell(m, b, s, cx, cy, cz, q.x, q.y, q.z, r2, k, lane, ss);
             count = ss.count; cand = ss.cand; have_k = ss.have_k != 0; b.phase = ss.phase; boundk = ss.boundk;
         }
+        if (count > k) { count = warp_select_k(m.orig, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true; }
+        if (s == 1 && pf.fast) break;
         // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon with d2 < r2
         float gr = INFINITY;
         {
@@ -377,7 +363,6 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
                 if (hi < g.dims[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
             }
         }
-        if (count > k) { count = warp_select_k(m.pos4, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true; }
         if (gr == INFINITY) break;                       // the block covers the whole grid
         gr -= g.margin;
         if (gr >= r) break;                              // everything with d2 < r2 has been seen
@@ -427,13 +412,24 @@ __device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium
     }
     mx = warp_max(mx);
     __syncwarp();
-    // pass 2: 8 lanes x float4 per 128-byte alpha line, eight photons (two independent loads per lane) per iteration
+    // pass 2: 8 lanes x float4 per 128-byte alpha line; sixteen photons (four independent 128-bit loads per lane) per
+    // iteration so the L2 latency of the alpha lines overlaps instead of adding up
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
-    for (uint32_t e0 = grp; e0 < padded; e0 += 8) {
+    uint32_t e0 = grp;
+    for (; e0 + 12 < padded; e0 += 16) {
+        const uint2 v0 = b.ent[e0], v1 = b.ent[e0 + 4], v2 = b.ent[e0 + 8], v3_ = b.ent[e0 + 12];
+        const float4 x0 = __ldg(a4 + (size_t)v0.y * 8), x1 = __ldg(a4 + (size_t)v1.y * 8);
+        const float4 x2 = __ldg(a4 + (size_t)v2.y * 8), x3 = __ldg(a4 + (size_t)v3_.y * 8);
+        const float p0 = __uint_as_float(v0.x), p1 = __uint_as_float(v1.x), p2 = __uint_as_float(v2.x), p3 = __uint_as_float(v3_.x);
+        acc.x = fmaf(x0.x, p0, acc.x); acc.y = fmaf(x0.y, p0, acc.y); acc.z = fmaf(x0.z, p0, acc.z); acc.w = fmaf(x0.w, p0, acc.w);
+        acc2.x = fmaf(x1.x, p1, acc2.x); acc2.y = fmaf(x1.y, p1, acc2.y); acc2.z = fmaf(x1.z, p1, acc2.z); acc2.w = fmaf(x1.w, p1, acc2.w);
+        acc.x = fmaf(x2.x, p2, acc.x); acc.y = fmaf(x2.y, p2, acc.y); acc.z = fmaf(x2.z, p2, acc.z); acc.w = fmaf(x2.w, p2, acc.w);
+        acc2.x = fmaf(x3.x, p3, acc2.x); acc2.y = fmaf(x3.y, p3, acc2.y); acc2.z = fmaf(x3.z, p3, acc2.z); acc2.w = fmaf(x3.w, p3, acc2.w);
+    }
+    for (; e0 < padded; e0 += 8) {                            // padded is a multiple of 8: e0 and e0 + 4 are valid
         const uint2 va = b.ent[e0], vb = b.ent[e0 + 4];
-        const float4 aa = __ldg(a4 + (size_t)va.y * 8);
-        const float4 ab = __ldg(a4 + (size_t)vb.y * 8);
+        const float4 aa = __ldg(a4 + (size_t)va.y * 8), ab = __ldg(a4 + (size_t)vb.y * 8);
         const float pha = __uint_as_float(va.x), phb = __uint_as_float(vb.x);
         acc.x = fmaf(aa.x, pha, acc.x); acc.y = fmaf(aa.y, pha, acc.y); acc.z = fmaf(aa.z, pha, acc.z); acc.w = fmaf(aa.w, pha, acc.w);
         acc2.x = fmaf(ab.x, phb, acc2.x); acc2.y = fmaf(ab.y, phb, acc2.y); acc2.z = fmaf(ab.z, phb, acc2.z); acc2.w = fmaf(ab.w, phb, acc2.w);
@@ -489,7 +485,7 @@ __device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpBuf &
 // oidx[] (original photon indices) lives in the unused upper part of the list.
 __device__ void warp_sort_entries(const MapView &m, WarpBuf &b, uint32_t count, uint32_t n2, uint32_t *oidx, uint32_t lane) {
     for (uint32_t e = lane; e < n2; e += 32) {
-        if (e < count) oidx[e] = __float_as_uint(__ldg(&m.pos4[b.ent[e].y].w));
+        if (e < count) oidx[e] = __ldg(&m.orig[b.ent[e].y]);
         else { b.ent[e] = make_uint2(__float_as_uint(INFINITY), 0u); oidx[e] = 0xFFFFFFFFu; }
     }
     __syncwarp();
@@ -759,7 +755,7 @@ static uint32_t lookup_cap(uint32_t k) {
     return std::max<uint32_t>(cap, 256u);
 }
 static MapView map_view(pv_ctx *ctx) {
-    MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.g = ctx->grid;
+    MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.orig = ctx->m_orig; m.g = ctx->grid;
     m.n = ctx->n_photons;
     return m;
 }
