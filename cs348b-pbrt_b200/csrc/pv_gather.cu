@@ -27,7 +27,9 @@
 #define GW_MIN_CTAS 4
 #endif
 #define GW_THREADS (GW_WARPS * 32)
+#ifndef GW_STAGE
 #define GW_STAGE 512                     // candidates staged per TMA round (x 16 B)
+#endif
 
 struct MapView {
     const float4 *pos4;            // x, y, z, sorted position of the photon (bits): a staged candidate carries its own address

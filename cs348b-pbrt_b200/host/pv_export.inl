@@ -1,0 +1,178 @@
+// pv_export.inl -- flatten the reference's host scene objects into the C-ABI scene description
+// (include/pv.h pv_scene_desc), SURVEY.md Appendix B.
+//
+// Included by a translation unit that has ALREADY included the reference headers with
+// `#define private public` / `#define protected public` in effect (core/scene.h, accelerators/bvh.h,
+// shapes/trianglemesh.h, lights/{point,spot,distant}.h, volumes/{homogeneous,volumegrid,rainbow}.h,
+// materials/{matte,glass}.h) and include/pv.h.  Users: host/pv_pbrt_adapter.cpp (the drop-in classes) and
+// oracle/ref_harness.cpp (fixture generation).  No reference source is modified.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include <stdio.h>
+#include <string.h>
+
+// Layout of accelerators/bvh.cpp:154-164 (the struct is private to that .cpp, so it is re-declared here).
+struct LinearBVHNode {
+    BBox bounds;
+    union { uint32_t primitivesOffset; uint32_t secondChildOffset; };
+    uint8_t nPrimitives, axis, pad[2];
+};
+
+struct PvHostScene {
+    std::vector<pv_bvh_node> nodes;
+    std::vector<float> tri;
+    std::vector<uint32_t> prim_material;
+    std::vector<pv_material> materials;
+    std::vector<pv_light> lights;
+    std::vector<float> density;
+    pv_medium medium;
+    bool has_medium;
+    pv_scene_desc desc;
+};
+
+static inline void pv_spec_out(const Spectrum &s, float *dst) { memcpy(dst, s.c, sizeof(float) * nSpectralSamples); }
+static inline void pv_mat_out(const Transform &t, float *dst) {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) dst[4 * i + j] = t.m.m[i][j];
+}
+
+static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err) {
+    BVHAccel *bvh = dynamic_cast<BVHAccel *>(scene->aggregate);
+    if (!bvh) { err = "pv: the scene aggregate is not the \"bvh\" accelerator"; return false; }
+    const uint32_t nPrims = (uint32_t)bvh->primitives.size();
+    const LinearBVHNode *nodes = (const LinearBVHNode *)bvh->nodes;
+    uint32_t nNodes = 0;
+    if (nodes) {   // depth-first layout (flattenBVHTree bvh.cpp:559-577): the node count is the largest index reached + 1
+        std::vector<uint32_t> todo; todo.push_back(0);
+        while (!todo.empty()) {
+            uint32_t i = todo.back(); todo.pop_back();
+            if (i + 1 > nNodes) nNodes = i + 1;
+            if (nodes[i].nPrimitives == 0) { todo.push_back(i + 1); todo.push_back(nodes[i].secondChildOffset); }
+        }
+    }
+    hs.nodes.resize(nNodes);
+    if (nNodes) memcpy(hs.nodes.data(), nodes, sizeof(pv_bvh_node) * nNodes);
+    hs.tri.assign(9 * (size_t)nPrims, 0.f);
+    hs.prim_material.assign(nPrims, 0u);
+    hs.materials.clear();
+    std::map<const Material *, uint32_t> matIndex;
+    DifferentialGeometry dummy;
+    for (uint32_t i = 0; i < nPrims; ++i) {
+        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
+        if (!gp) { err = "pv: a primitive is not a GeometricPrimitive (instancing is out of scope)"; return false; }
+        const Triangle *t = dynamic_cast<const Triangle *>(gp->shape.GetPtr());
+        if (!t) { err = "pv: a shape is not a Triangle (only triangle meshes are on this path)"; return false; }
+        for (int k = 0; k < 3; ++k) {
+            const Point &p = t->mesh->p[t->v[k]];          // already world space (shapes/trianglemesh.cpp:70-71)
+            hs.tri[9 * i + 3 * k + 0] = p.x; hs.tri[9 * i + 3 * k + 1] = p.y; hs.tri[9 * i + 3 * k + 2] = p.z;
+        }
+        const Material *m = gp->material.GetPtr();
+        if (!matIndex.count(m)) {
+            pv_material pm; memset(&pm, 0, sizeof(pm));
+            if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
+                pm.type = PV_MAT_MATTE;
+                pv_spec_out(mm->Kd->Evaluate(dummy).Clamp(), pm.kd);
+                if (mm->sigma->Evaluate(dummy) != 0.f) fprintf(stderr, "pv: warning: matte sigma != 0 (Oren-Nayar) is treated as Lambertian\n");
+            } else if (const GlassMaterial *gm = dynamic_cast<const GlassMaterial *>(m)) {
+                pm.type = PV_MAT_GLASS;
+                pv_spec_out(gm->Kr->Evaluate(dummy).Clamp(), pm.kr);
+                pv_spec_out(gm->Kt->Evaluate(dummy).Clamp(), pm.kt);
+                pm.index = gm->index->Evaluate(dummy);
+                pm.vn = gm->Vn;
+            } else {
+                fprintf(stderr, "pv: warning: unsupported material on primitive %u, photons treat it as black matte\n", i);
+                pm.type = PV_MAT_MATTE;
+            }
+            matIndex[m] = (uint32_t)hs.materials.size(); hs.materials.push_back(pm);
+        }
+        hs.prim_material[i] = matIndex[m];
+    }
+    hs.lights.clear();
+    for (size_t i = 0; i < scene->lights.size(); ++i) {
+        pv_light pl; memset(&pl, 0, sizeof(pl));
+        Light *l = scene->lights[i];
+        pv_mat_out(l->LightToWorld, pl.light_to_world);
+        pv_mat_out(l->WorldToLight, pl.world_to_light);
+        pl.power_y = l->Power(scene).y();
+        if (PointLight *p = dynamic_cast<PointLight *>(l)) {
+            pl.type = PV_LIGHT_POINT;
+            pl.pos[0] = p->lightPos.x; pl.pos[1] = p->lightPos.y; pl.pos[2] = p->lightPos.z;
+            pv_spec_out(p->Intensity, pl.intensity);
+        } else if (SpotLight *s = dynamic_cast<SpotLight *>(l)) {
+            pl.type = PV_LIGHT_SPOT;
+            pl.pos[0] = s->lightPos.x; pl.pos[1] = s->lightPos.y; pl.pos[2] = s->lightPos.z;
+            pv_spec_out(s->Intensity, pl.intensity);
+            pl.cos_total_width = s->cosTotalWidth; pl.cos_falloff_start = s->cosFalloffStart;
+        } else if (DistantLight *d = dynamic_cast<DistantLight *>(l)) {
+            pl.type = PV_LIGHT_DISTANT;
+            pl.dir[0] = d->lightDir.x; pl.dir[1] = d->lightDir.y; pl.dir[2] = d->lightDir.z;
+            pv_spec_out(d->L, pl.intensity);
+        } else { err = "pv: unsupported light type (point, spot and distant lights are on this path)"; return false; }
+        hs.lights.push_back(pl);
+    }
+    hs.has_medium = false;
+    memset(&hs.medium, 0, sizeof(hs.medium));
+    hs.density.clear();
+    if (VolumeRegion *vr = scene->volumeRegion) {
+        pv_medium &m = hs.medium;
+        // RainbowVolume derives from HomogeneousVolumeDensity: test it first
+        if (HomogeneousVolumeDensity *h = dynamic_cast<HomogeneousVolumeDensity *>(vr)) {
+            m.type = dynamic_cast<RainbowVolume *>(vr) ? PV_MEDIUM_RAINBOW : PV_MEDIUM_HOMOGENEOUS;
+            pv_mat_out(h->WorldToVolume, m.world_to_volume);
+            m.p0[0] = h->extent.pMin.x; m.p0[1] = h->extent.pMin.y; m.p0[2] = h->extent.pMin.z;
+            m.p1[0] = h->extent.pMax.x; m.p1[1] = h->extent.pMax.y; m.p1[2] = h->extent.pMax.z;
+            pv_spec_out(h->sig_a, m.sigma_a); pv_spec_out(h->sig_s, m.sigma_s); pv_spec_out(h->le, m.le); m.g = h->g;
+        } else if (VolumeGridDensity *gd = dynamic_cast<VolumeGridDensity *>(vr)) {
+            m.type = PV_MEDIUM_GRID;
+            pv_mat_out(gd->WorldToVolume, m.world_to_volume);
+            m.p0[0] = gd->extent.pMin.x; m.p0[1] = gd->extent.pMin.y; m.p0[2] = gd->extent.pMin.z;
+            m.p1[0] = gd->extent.pMax.x; m.p1[1] = gd->extent.pMax.y; m.p1[2] = gd->extent.pMax.z;
+            pv_spec_out(gd->sig_a, m.sigma_a); pv_spec_out(gd->sig_s, m.sigma_s); pv_spec_out(gd->le, m.le); m.g = gd->g;
+            m.nx = gd->nx; m.ny = gd->ny; m.nz = gd->nz;
+            hs.density.assign(gd->density, gd->density + (size_t)gd->nx * gd->ny * gd->nz);
+            m.density = hs.density.data();
+        } else { err = "pv: unsupported volume region (homogeneous, volumegrid and rainbow are on this path)"; return false; }
+        hs.has_medium = true;
+    }
+    pv_scene_desc &d = hs.desc;
+    memset(&d, 0, sizeof(d));
+    d.nodes = hs.nodes.data(); d.n_nodes = nNodes;
+    d.tri_verts = hs.tri.data(); d.prim_material = hs.prim_material.data(); d.n_prims = nPrims;
+    d.materials = hs.materials.data(); d.n_materials = (uint32_t)hs.materials.size();
+    d.lights = hs.lights.data(); d.n_lights = (uint32_t)hs.lights.size();
+    d.medium = hs.has_medium ? &hs.medium : NULL;
+    const BBox &wb = scene->WorldBound();
+    d.world_bound[0] = wb.pMin.x; d.world_bound[1] = wb.pMin.y; d.world_bound[2] = wb.pMin.z;
+    d.world_bound[3] = wb.pMax.x; d.world_bound[4] = wb.pMax.y; d.world_bound[5] = wb.pMax.z;
+    memcpy(d.cie_y, SampledSpectrum::Y.c, sizeof(d.cie_y));
+    return true;
+}
+
+// PVSCN001 interchange file (read by cs348b-pbrt_b200/sceneio.py)
+static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
+    FILE *f = fopen(fn.c_str(), "wb");
+    if (!f) { perror(fn.c_str()); return false; }
+    const pv_scene_desc &d = hs.desc;
+    uint32_t hdr[8] = {d.n_nodes, d.n_prims, d.n_materials, d.n_lights, hs.has_medium ? 1u : 0u, 0, 0, 0};
+    bool ok = fwrite("PVSCN001", 1, 8, f) == 8 && fwrite(hdr, 4, 8, f) == 8 && fwrite(d.world_bound, 4, 6, f) == 6 &&
+              fwrite(d.cie_y, 4, PV_NSPEC, f) == PV_NSPEC;
+    ok = ok && fwrite(hs.nodes.data(), sizeof(pv_bvh_node), hs.nodes.size(), f) == hs.nodes.size();
+    ok = ok && fwrite(hs.tri.data(), 4, hs.tri.size(), f) == hs.tri.size();
+    ok = ok && fwrite(hs.prim_material.data(), 4, hs.prim_material.size(), f) == hs.prim_material.size();
+    ok = ok && fwrite(hs.materials.data(), sizeof(pv_material), hs.materials.size(), f) == hs.materials.size();
+    ok = ok && fwrite(hs.lights.data(), sizeof(pv_light), hs.lights.size(), f) == hs.lights.size();
+    if (ok && hs.has_medium) {
+        const pv_medium &m = hs.medium;
+        int32_t dims[3] = {m.nx, m.ny, m.nz};
+        ok = fwrite(&m.type, 4, 1, f) == 1 && fwrite(m.world_to_volume, 4, 16, f) == 16 && fwrite(m.p0, 4, 3, f) == 3 &&
+             fwrite(m.p1, 4, 3, f) == 3 && fwrite(m.sigma_a, 4, 30, f) == 30 && fwrite(m.sigma_s, 4, 30, f) == 30 &&
+             fwrite(m.le, 4, 30, f) == 30 && fwrite(&m.g, 4, 1, f) == 1 && fwrite(dims, 4, 3, f) == 3;
+        if (ok && m.type == PV_MEDIUM_GRID) ok = fwrite(hs.density.data(), 4, hs.density.size(), f) == hs.density.size();
+    }
+    fclose(f);
+    if (!ok) fprintf(stderr, "pv: short write on %s\n", fn.c_str());
+    else fprintf(stderr, "[pv] exported scene: %u nodes, %u prims, %u materials, %u lights -> %s\n", d.n_nodes, d.n_prims, d.n_materials,
+                 d.n_lights, fn.c_str());
+    return ok;
+}

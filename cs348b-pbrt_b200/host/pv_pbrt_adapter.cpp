@@ -1,0 +1,327 @@
+// pv_pbrt_adapter.cpp -- the host side of the drop-in: the reference's own classes, re-implemented over the C ABI.
+//
+// Linked INTO the reference (piwell/CS348B-pbrt) in place of three of its translation units; every class keeps the
+// declaration of the reference's header, so core/api.cpp (the name-string "plugin registry", :572-586, :1221-1288),
+// the parser, cameras, samplers, surface integrators and the film are used unchanged:
+//
+//   replaced TU                          what this file provides instead
+//   core/photonshooter.cpp   (:457-526)  PhotonShooter::Preprocess -> pv_set_scene + pv_shoot + pv_build on the GPU.
+//                                        The rest of that TU is still the reference's: it is compiled from
+//                                        /root/reference with -DPreprocess=RefPreprocess, which keeps its CPU pass
+//                                        available (as PhotonShooter::RefPreprocess) for the SURFACE photon maps that
+//                                        the untouched PhotonIntegrator reads (integrators/photonmap.cpp:159-164).
+//   integrators/photonvolume.cpp         PhotonVolumeIntegrator::{RequestSamples, Transmittance, Li} and
+//                                        CreatePhotonVolumeIntegrator (same .pbrt parameters, :224-229).
+//   renderers/samplerrenderer.cpp        SamplerRenderer with a BATCHED Render: image tiles run the unchanged camera /
+//                                        sampler / surface-integrator code on the reference's pthread pool
+//                                        (core/parallel.cpp) and queue their camera rays; the volume term of the whole
+//                                        frame is ONE pv_gather call; samples are then added to the unchanged Film.
+//
+// Nothing here computes radiance on the CPU: Li without a CUDA device is an error (Severe), not a fallback.
+// PhotonVolumeIntegrator::Transmittance, which the surface integrators call one ray at a time, stays the reference's
+// three lines over VolumeRegion::tau (core/volume.cpp) -- it is not worth a device round trip per shadow ray; the GPU
+// uses its own batch form (pv_transmittance and the in-kernel marches).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <map>
+#include <algorithm>
+#include <sys/time.h>
+
+#define private public
+#define protected public
+#include "stdafx.h"
+#include "core/pbrt.h"
+#include "core/scene.h"
+#include "core/light.h"
+#include "core/sampler.h"
+#include "core/camera.h"
+#include "core/film.h"
+#include "core/intersection.h"
+#include "core/paramset.h"
+#include "core/montecarlo.h"
+#include "core/progressreporter.h"
+#include "core/photonshooter.h"
+#include "accelerators/bvh.h"
+#include "shapes/trianglemesh.h"
+#include "lights/point.h"
+#include "lights/spot.h"
+#include "lights/distant.h"
+#include "volumes/homogeneous.h"
+#include "volumes/volumegrid.h"
+#include "volumes/rainbow.h"
+#include "materials/matte.h"
+#include "materials/glass.h"
+#include "integrators/photonvolume.h"
+#include "renderers/samplerrenderer.h"
+#undef private
+#undef protected
+
+#include "../../include/pv.h"
+#include "pv_export.inl"
+
+// PhotonShooter::Preprocess of the reference's own TU, renamed at compile time (see host/Makefile); called through its
+// Itanium-ABI name because the class declaration cannot be extended.
+extern "C" void _ZN13PhotonShooter13RefPreprocessEPK5ScenePK6CameraPK8Renderer(PhotonShooter *, const Scene *, const Camera *,
+                                                                              const Renderer *);
+
+namespace {
+struct PvBridge {
+    pv_ctx *ctx;
+    PvHostScene scene;
+    float stepsize, maxdist;
+    uint32_t nused;
+    uint64_t seed;
+    bool ready;
+    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), ready(false) {}
+};
+PvBridge g_pv;
+
+double now_s() { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+
+void pv_fail(const char *what, int rc) {
+    Severe("%s failed (%d): %s", what, rc, pv_last_error(g_pv.ctx));
+}
+
+struct PvRecord {                 // one camera sample waiting for its volume term
+    float imageX, imageY, rayWeight;
+    Spectrum Ls;                  // surface radiance (before the volume transmittance)
+    pv_ray ray;
+};
+std::vector<std::vector<PvRecord> > *g_records = NULL;
+}  // namespace
+
+// ------------------------------------------------------------------ PhotonShooter::Preprocess (core/photonshooter.cpp:457-526)
+void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const Renderer *renderer) {
+    if (scene->lights.size() == 0) return;
+    const SamplerRenderer *sr = dynamic_cast<const SamplerRenderer *>(renderer);
+    PhotonVolumeIntegrator *vi = sr ? dynamic_cast<PhotonVolumeIntegrator *>(sr->volumeIntegrator) : NULL;
+    if (!vi || !scene->volumeRegion) {
+        // not the photon-volume path: the reference's CPU pass, untouched
+        _ZN13PhotonShooter13RefPreprocessEPK5ScenePK6CameraPK8Renderer(this, scene, camera, renderer);
+        return;
+    }
+    std::string err;
+    if (!pv_export_scene(scene, g_pv.scene, err)) Severe("%s", err.c_str());
+    if (!g_pv.ctx) {
+        const char *dev = getenv("PV_DEVICE");
+        int rc = pv_create(&g_pv.ctx, dev ? atoi(dev) : 0);
+        if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
+    }
+    int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
+    if (rc) pv_fail("pv_set_scene", rc);
+    g_pv.stepsize = vi->stepSize; g_pv.maxdist = vi->maxDist; g_pv.nused = (uint32_t)vi->nUsed;
+    const char *seed = getenv("PV_SEED");
+    g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
+    if (nVolumePhotonsWanted > 0) {
+        pv_shoot_params prm; memset(&prm, 0, sizeof(prm));
+        prm.stepsize = stepSize; prm.integrator_stepsize = vi->stepSize; prm.max_photon_depth = maxPhotonDepth;
+        prm.seed = g_pv.seed; prm.rank = 0; prm.world = 1; prm.time = camera ? camera->shutterOpen : 0.f;
+        pv_shoot_stats st;
+        double t0 = now_s();
+        rc = pv_shoot(g_pv.ctx, nVolumePhotonsWanted, &prm, &st);
+        if (rc == PV_ENOPHOTONS) Error("Unable to store enough photons.  Giving up.\n");      // photonshooter.cpp:292
+        else if (rc) pv_fail("pv_shoot", rc);
+        nVolumePaths = (int)st.paths;
+        rc = pv_build(g_pv.ctx, vi->maxDist, (uint32_t)vi->nUsed);
+        if (rc) pv_fail("pv_build", rc);
+        uint64_t n = 0; pv_photon_count(g_pv.ctx, &n);
+        fprintf(stderr, "[pv] shot %llu volume photons from %llu light paths in %.3f s (device %.3f s), map built\n",
+                (unsigned long long)n, (unsigned long long)st.paths, now_s() - t0, st.seconds);
+    } else {
+        rc = pv_set_photons(g_pv.ctx, NULL, NULL, NULL, 0);
+        if (!rc) rc = pv_build(g_pv.ctx, vi->maxDist, (uint32_t)vi->nUsed);
+        if (rc) pv_fail("pv_build", rc);
+    }
+    g_pv.ready = true;
+    // surface photon maps (caustic / indirect / radiance photons) stay on the reference's CPU pass
+    if (nCausticPhotonsWanted + nIndirectPhotonsWanted > 0) {
+        uint32_t keep = nVolumePhotonsWanted;
+        nVolumePhotonsWanted = 0;
+        _ZN13PhotonShooter13RefPreprocessEPK5ScenePK6CameraPK8Renderer(this, scene, camera, renderer);
+        nVolumePhotonsWanted = keep;
+    }
+}
+
+// ------------------------------------------------------------------ PhotonVolumeIntegrator (integrators/photonvolume.cpp)
+void PhotonVolumeIntegrator::RequestSamples(Sampler *sampler, Sample *sample, const Scene *scene) {
+    tauSampleOffset = sample->Add1D(1);
+    scatterSampleOffset = sample->Add1D(1);
+}
+
+Spectrum PhotonVolumeIntegrator::Transmittance(const Scene *scene, const Renderer *renderer, const RayDifferential &ray,
+                                               const Sample *sample, RNG &rng, MemoryArena &arena) const {
+    if (!scene->volumeRegion) return Spectrum(1.f);
+    float step = sample ? stepSize : 4.f * stepSize;
+    float offset = sample ? sample->oneD[tauSampleOffset][0] : rng.RandomFloat();
+    return Exp(-scene->volumeRegion->tau(ray, step, offset));
+}
+
+static void pv_fill_ray(const RayDifferential &ray, float u_scatter, pv_ray *r) {
+    r->o[0] = ray.o.x; r->o[1] = ray.o.y; r->o[2] = ray.o.z;
+    r->d[0] = ray.d.x; r->d[1] = ray.d.y; r->d[2] = ray.d.z;
+    r->mint = ray.mint; r->maxt = ray.maxt; r->time = ray.time; r->u_scatter = u_scatter;
+}
+
+// Single-ray form (kept so every caller of the VolumeIntegrator interface still works); the renderer below batches.
+Spectrum PhotonVolumeIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
+                                    RNG &rng, Spectrum *T, MemoryArena &arena) const {
+    if (!scene->volumeRegion) { *T = 1.f; return 0.f; }
+    if (!g_pv.ready) Severe("PhotonVolumeIntegrator::Li: the GPU photon-volume context was not set up (no CUDA device?)");
+    pv_ray r; pv_fill_ray(ray, sample->oneD[scatterSampleOffset][0], &r);
+    pv_gather_params prm; memset(&prm, 0, sizeof(prm));
+    prm.stepsize = stepSize; prm.nused = (uint32_t)nUsed; prm.maxdist = maxDist; prm.seed = g_pv.seed;
+    prm.ray_index_base = ((uint64_t)rng.RandomUInt() << 20) | 0x8000000000000000ull;     // a stream of its own per call
+    float L[PV_NSPEC], Tr[PV_NSPEC];
+    int rc = pv_gather(g_pv.ctx, &r, 1, &prm, L, Tr);
+    if (rc) pv_fail("pv_gather", rc);
+    Spectrum Lv(0.f);
+    memcpy(Lv.c, L, sizeof(L)); memcpy(T->c, Tr, sizeof(Tr));
+    return Lv;
+}
+
+PhotonVolumeIntegrator *CreatePhotonVolumeIntegrator(const ParamSet &params, PhotonShooter *phs) {
+    float stepSize = params.FindOneFloat("stepsize", 1.f);
+    int nUsed = params.FindOneInt("nused", 250);
+    float maxDist = params.FindOneFloat("maxdist", 0.1f);
+    return new PhotonVolumeIntegrator(stepSize, nUsed, maxDist, phs);
+}
+
+// ------------------------------------------------------------------ SamplerRenderer (renderers/samplerrenderer.cpp)
+SamplerRenderer::SamplerRenderer(Sampler *s, Camera *c, SurfaceIntegrator *si, VolumeIntegrator *vi, bool visIds, PhotonShooter *ps) {
+    sampler = s; camera = c; surfaceIntegrator = si; volumeIntegrator = vi; visualizeObjectIds = visIds; photonShooter = ps;
+}
+SamplerRenderer::~SamplerRenderer() {
+    delete sampler; delete camera; delete surfaceIntegrator; delete volumeIntegrator; delete photonShooter;
+}
+
+static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Sample *sample, RNG &rng,
+                                MemoryArena &arena, Intersection *isect) {
+    // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
+    if (scene->Intersect(ray, isect)) return r->surfaceIntegrator->Li(scene, r, ray, *isect, sample, rng, arena);
+    Spectrum Li = 0.f;
+    for (uint32_t i = 0; i < scene->lights.size(); ++i) Li += scene->lights[i]->Le(ray);
+    return Li;
+}
+
+Spectrum SamplerRenderer::Li(const Scene *scene, const RayDifferential &ray, const Sample *sample, RNG &rng, MemoryArena &arena,
+                             Intersection *isect, Spectrum *T) const {
+    Spectrum localT; if (!T) T = &localT;
+    Intersection localIsect; if (!isect) isect = &localIsect;
+    Spectrum Li = pv_surface_term(this, scene, ray, sample, rng, arena, isect);
+    Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
+    return *T * Li + Lvi;
+}
+Spectrum SamplerRenderer::Transmittance(const Scene *scene, const RayDifferential &ray, const Sample *sample, RNG &rng,
+                                        MemoryArena &arena) const {
+    return volumeIntegrator->Transmittance(scene, this, ray, sample, rng, arena);
+}
+
+// One image tile (the reference's task, :60-164) up to the volume term: camera ray + surface radiance per sample.
+// When the GPU path is active the samples are queued (in task order, so the frame is reproducible); otherwise the task
+// finishes the sample exactly like the reference.
+void SamplerRendererTask::Run() {
+    Sampler *sampler = mainSampler->GetSubSampler(taskNum, taskCount);
+    if (!sampler) { reporter.Update(); return; }
+    const SamplerRenderer *sr = static_cast<const SamplerRenderer *>(renderer);
+    PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(sr->volumeIntegrator);
+    const bool batch = g_records && vi && g_pv.ready && scene->volumeRegion && !visualizeObjectIds;
+    MemoryArena arena;
+    RNG rng(taskNum);
+    int maxSamples = sampler->MaximumSampleCount();
+    Sample *samples = origSample->Duplicate(maxSamples);
+    RayDifferential *rays = new RayDifferential[maxSamples];
+    Spectrum *Ls = new Spectrum[maxSamples];
+    Spectrum *Ts = new Spectrum[maxSamples];
+    Intersection *isects = new Intersection[maxSamples];
+    std::vector<PvRecord> *out = batch ? &(*g_records)[taskNum] : NULL;
+    int sampleCount;
+    while ((sampleCount = sampler->GetMoreSamples(samples, rng)) > 0) {
+        for (int i = 0; i < sampleCount; ++i) {
+            float rayWeight = camera->GenerateRayDifferential(samples[i], &rays[i]);
+            rays[i].ScaleDifferentials(1.f / sqrtf(sampler->samplesPerPixel));
+            if (batch) {
+                PvRecord rec;
+                rec.imageX = samples[i].imageX; rec.imageY = samples[i].imageY; rec.rayWeight = rayWeight;
+                rec.Ls = 0.f;
+                if (rayWeight > 0.f) rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i]);
+                pv_fill_ray(rays[i], samples[i].oneD[vi->scatterSampleOffset][0], &rec.ray);
+                out->push_back(rec);
+                continue;
+            }
+            if (rayWeight > 0.f) Ls[i] = rayWeight * renderer->Li(scene, rays[i], &samples[i], rng, arena, &isects[i], &Ts[i]);
+            else { Ls[i] = 0.f; Ts[i] = 1.f; }
+            if (Ls[i].HasNaNs() || Ls[i].y() < -1e-5 || isinf(Ls[i].y())) Ls[i] = Spectrum(0.f);
+        }
+        if (!batch && sampler->ReportResults(samples, rays, Ls, isects, sampleCount))
+            for (int i = 0; i < sampleCount; ++i) camera->film->AddSample(samples[i], Ls[i]);
+        arena.FreeAll();
+    }
+    camera->film->UpdateDisplay(sampler->xPixelStart, sampler->yPixelStart, sampler->xPixelEnd + 1, sampler->yPixelEnd + 1);
+    delete sampler;
+    delete[] samples; delete[] rays; delete[] Ls; delete[] Ts; delete[] isects;
+    reporter.Update();
+}
+
+void SamplerRenderer::Render(const Scene *scene) {
+    if (photonShooter != NULL) photonShooter->Preprocess(scene, camera, this);
+    surfaceIntegrator->Preprocess(scene, camera, this);
+    volumeIntegrator->Preprocess(scene, camera, this);
+    Sample *sample = new Sample(sampler, surfaceIntegrator, volumeIntegrator, scene);
+    camera->AutoFocus(this, scene, sample);
+    int nPixels = camera->film->xResolution * camera->film->yResolution;
+    int nTasks = max(32 * NumSystemCores(), nPixels / (16 * 16));
+    nTasks = RoundUpPow2(nTasks);
+    std::vector<std::vector<PvRecord> > records(nTasks);
+    g_records = &records;
+    double t0 = now_s();
+    {
+        ProgressReporter reporter(nTasks, "Rendering");
+        vector<Task *> renderTasks;
+        for (int i = 0; i < nTasks; ++i)
+            renderTasks.push_back(new SamplerRendererTask(scene, this, camera, reporter, sampler, sample, visualizeObjectIds,
+                                                          nTasks - 1 - i, nTasks));
+        EnqueueTasks(renderTasks);
+        WaitForAllTasks();
+        for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
+        reporter.Done();
+    }
+    g_records = NULL;
+    // ---- the volume term of the whole frame: one pv_gather
+    size_t total = 0;
+    for (int t = 0; t < nTasks; ++t) total += records[t].size();
+    if (total) {
+        PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(volumeIntegrator);
+        std::vector<pv_ray> rays(total);
+        size_t k = 0;
+        for (int t = 0; t < nTasks; ++t) for (size_t i = 0; i < records[t].size(); ++i) rays[k++] = records[t][i].ray;
+        std::vector<float> L(total * PV_NSPEC), T(total * PV_NSPEC);
+        pv_gather_params prm; memset(&prm, 0, sizeof(prm));
+        prm.stepsize = vi->stepSize; prm.nused = (uint32_t)vi->nUsed; prm.maxdist = vi->maxDist; prm.seed = g_pv.seed;
+        double t1 = now_s();
+        int rc = pv_gather(g_pv.ctx, rays.data(), total, &prm, L.data(), T.data());
+        if (rc) pv_fail("pv_gather", rc);
+        float ms = 0.f; pv_last_kernel_ms(g_pv.ctx, &ms);
+        fprintf(stderr, "[pv] surface pass %.3f s on %d cores; volume gather of %zu camera rays %.3f s (kernel %.3f ms)\n", t1 - t0,
+                NumSystemCores(), total, now_s() - t1, ms);
+        k = 0;
+        for (int t = 0; t < nTasks; ++t)
+            for (size_t i = 0; i < records[t].size(); ++i, ++k) {
+                const PvRecord &rec = records[t][i];
+                Spectrum Lv(0.f), Tr(1.f), Lo(0.f);
+                if (rec.rayWeight > 0.f) {
+                    memcpy(Lv.c, &L[k * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &T[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                    Lo = rec.rayWeight * (Tr * rec.Ls + Lv);                  // Ls[i] = rayWeight * (T * Li + Lvi), :111,:249
+                }
+                if (Lo.HasNaNs() || Lo.y() < -1e-5 || isinf(Lo.y())) Lo = Spectrum(0.f);      // :118-133
+                CameraSample cs; cs.imageX = rec.imageX; cs.imageY = rec.imageY; cs.lensU = cs.lensV = 0.f; cs.time = rec.ray.time;
+                camera->film->AddSample(cs, Lo);
+            }
+    }
+    delete sample;
+    camera->film->WriteImage();
+}

@@ -64,12 +64,7 @@
 
 #include "../include/pv.h"
 
-// Layout of accelerators/bvh.cpp:154-164 (defined in the .cpp, so re-declared).
-struct LinearBVHNode {
-    BBox bounds;
-    union { uint32_t primitivesOffset; uint32_t secondChildOffset; };
-    uint8_t nPrimitives, axis, pad[2];
-};
+#include "../cs348b-pbrt_b200/host/pv_export.inl"
 
 static std::vector<std::string> g_ops;
 static int g_rc = 0;
@@ -99,138 +94,6 @@ static uint64_t read_header(FILE *f, const char *magic) {
 static void write_header(FILE *f, const char *magic, uint64_t n) {
     wr(f, magic, 8); wr(f, &n, 1);
 }
-static void spec_out(const Spectrum &s, float *dst) {
-    memcpy(dst, s.c, sizeof(float) * nSpectralSamples);
-}
-static void mat_out(const Transform &t, float *dst, bool inverse) {
-    const Matrix4x4 &m = inverse ? t.mInv : t.m;
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) dst[4*i+j] = m.m[i][j];
-}
-
-// ---------------------------------------------------------------- scene export
-static void export_scene(const Scene *scene, const std::string &fn) {
-    BVHAccel *bvh = dynamic_cast<BVHAccel *>(scene->aggregate);
-    if (!bvh) { fprintf(stderr, "aggregate is not a BVHAccel\n"); exit(4); }
-    uint32_t nPrims = bvh->primitives.size();
-    // count nodes by walking the flattened array
-    const LinearBVHNode *nodes = (const LinearBVHNode *)bvh->nodes;
-    uint32_t nNodes = 0;
-    if (nodes) {
-        // depth-first layout: the last node reachable is the max index visited
-        std::vector<uint32_t> todo; todo.push_back(0);
-        while (!todo.empty()) {
-            uint32_t i = todo.back(); todo.pop_back();
-            nNodes = std::max(nNodes, i + 1);
-            if (nodes[i].nPrimitives == 0) { todo.push_back(i + 1); todo.push_back(nodes[i].secondChildOffset); }
-        }
-    }
-    std::vector<float> tri(9 * (size_t)nPrims);
-    std::vector<uint32_t> primMat(nPrims);
-    std::vector<pv_material> mats;
-    std::map<const Material *, uint32_t> matIndex;
-    DifferentialGeometry dummy;
-    for (uint32_t i = 0; i < nPrims; ++i) {
-        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
-        if (!gp) { fprintf(stderr, "primitive %u is not a GeometricPrimitive\n", i); exit(4); }
-        const Triangle *t = dynamic_cast<const Triangle *>(gp->shape.GetPtr());
-        if (!t) { fprintf(stderr, "primitive %u is not a Triangle\n", i); exit(4); }
-        for (int k = 0; k < 3; ++k) {
-            const Point &p = t->mesh->p[t->v[k]];
-            tri[9*i + 3*k + 0] = p.x; tri[9*i + 3*k + 1] = p.y; tri[9*i + 3*k + 2] = p.z;
-        }
-        const Material *m = gp->material.GetPtr();
-        if (!matIndex.count(m)) {
-            pv_material pm; memset(&pm, 0, sizeof(pm));
-            if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
-                pm.type = PV_MAT_MATTE;
-                spec_out(mm->Kd->Evaluate(dummy).Clamp(), pm.kd);
-                if (mm->sigma->Evaluate(dummy) != 0.f) fprintf(stderr, "warning: matte sigma != 0 (OrenNayar) not exported\n");
-            } else if (const GlassMaterial *gm = dynamic_cast<const GlassMaterial *>(m)) {
-                pm.type = PV_MAT_GLASS;
-                spec_out(gm->Kr->Evaluate(dummy).Clamp(), pm.kr);
-                spec_out(gm->Kt->Evaluate(dummy).Clamp(), pm.kt);
-                pm.index = gm->index->Evaluate(dummy);
-                pm.vn = gm->Vn;
-            } else {
-                fprintf(stderr, "warning: unsupported material on prim %u, exported as black matte\n", i);
-                pm.type = PV_MAT_MATTE;
-            }
-            matIndex[m] = mats.size(); mats.push_back(pm);
-        }
-        primMat[i] = matIndex[m];
-    }
-    std::vector<pv_light> lights;
-    for (size_t i = 0; i < scene->lights.size(); ++i) {
-        pv_light pl; memset(&pl, 0, sizeof(pl));
-        Light *l = scene->lights[i];
-        mat_out(l->LightToWorld, pl.light_to_world, false);
-        mat_out(l->WorldToLight, pl.world_to_light, false);
-        pl.power_y = l->Power(scene).y();
-        if (PointLight *p = dynamic_cast<PointLight *>(l)) {
-            pl.type = PV_LIGHT_POINT;
-            pl.pos[0] = p->lightPos.x; pl.pos[1] = p->lightPos.y; pl.pos[2] = p->lightPos.z;
-            spec_out(p->Intensity, pl.intensity);
-        } else if (SpotLight *s = dynamic_cast<SpotLight *>(l)) {
-            pl.type = PV_LIGHT_SPOT;
-            pl.pos[0] = s->lightPos.x; pl.pos[1] = s->lightPos.y; pl.pos[2] = s->lightPos.z;
-            spec_out(s->Intensity, pl.intensity);
-            pl.cos_total_width = s->cosTotalWidth; pl.cos_falloff_start = s->cosFalloffStart;
-        } else if (DistantLight *d = dynamic_cast<DistantLight *>(l)) {
-            pl.type = PV_LIGHT_DISTANT;
-            pl.dir[0] = d->lightDir.x; pl.dir[1] = d->lightDir.y; pl.dir[2] = d->lightDir.z;
-            spec_out(d->L, pl.intensity);
-        } else { fprintf(stderr, "unsupported light %zu\n", i); exit(4); }
-        lights.push_back(pl);
-    }
-    FILE *f = xopen(fn, "wb");
-    wr(f, "PVSCN001", 8);
-    VolumeRegion *vr = scene->volumeRegion;
-    uint32_t hdr[8] = { nNodes, nPrims, (uint32_t)mats.size(), (uint32_t)lights.size(), vr ? 1u : 0u, 0, 0, 0 };
-    wr(f, hdr, 8);
-    const BBox &wb = scene->WorldBound();
-    float wbf[6] = { wb.pMin.x, wb.pMin.y, wb.pMin.z, wb.pMax.x, wb.pMax.y, wb.pMax.z };
-    wr(f, wbf, 6);
-    wr(f, SampledSpectrum::Y.c, nSpectralSamples);
-    wr(f, (const char *)nodes, 32 * (size_t)nNodes);
-    wr(f, tri.data(), tri.size());
-    wr(f, primMat.data(), primMat.size());
-    wr(f, mats.data(), mats.size());
-    wr(f, lights.data(), lights.size());
-    if (vr) {
-        int32_t type = 0, dims[3] = {0, 0, 0};
-        float w2v[16], p0[3], p1[3], sa[30], ss[30], le[30], g = 0;
-        const float *density = NULL;
-        // RainbowVolume derives from HomogeneousVolumeDensity: test it first.
-        if (RainbowVolume *rv = dynamic_cast<RainbowVolume *>(vr)) {
-            type = PV_MEDIUM_RAINBOW;
-            HomogeneousVolumeDensity *h = rv;
-            mat_out(h->WorldToVolume, w2v, false);
-            p0[0]=h->extent.pMin.x; p0[1]=h->extent.pMin.y; p0[2]=h->extent.pMin.z;
-            p1[0]=h->extent.pMax.x; p1[1]=h->extent.pMax.y; p1[2]=h->extent.pMax.z;
-            spec_out(h->sig_a, sa); spec_out(h->sig_s, ss); spec_out(h->le, le); g = h->g;
-        } else if (HomogeneousVolumeDensity *h = dynamic_cast<HomogeneousVolumeDensity *>(vr)) {
-            type = PV_MEDIUM_HOMOGENEOUS;
-            mat_out(h->WorldToVolume, w2v, false);
-            p0[0]=h->extent.pMin.x; p0[1]=h->extent.pMin.y; p0[2]=h->extent.pMin.z;
-            p1[0]=h->extent.pMax.x; p1[1]=h->extent.pMax.y; p1[2]=h->extent.pMax.z;
-            spec_out(h->sig_a, sa); spec_out(h->sig_s, ss); spec_out(h->le, le); g = h->g;
-        } else if (VolumeGridDensity *gd = dynamic_cast<VolumeGridDensity *>(vr)) {
-            type = PV_MEDIUM_GRID;
-            mat_out(gd->WorldToVolume, w2v, false);
-            p0[0]=gd->extent.pMin.x; p0[1]=gd->extent.pMin.y; p0[2]=gd->extent.pMin.z;
-            p1[0]=gd->extent.pMax.x; p1[1]=gd->extent.pMax.y; p1[2]=gd->extent.pMax.z;
-            spec_out(gd->sig_a, sa); spec_out(gd->sig_s, ss); spec_out(gd->le, le); g = gd->g;
-            dims[0] = gd->nx; dims[1] = gd->ny; dims[2] = gd->nz; density = gd->density;
-        } else { fprintf(stderr, "unsupported volume region\n"); exit(4); }
-        wr(f, &type, 1); wr(f, w2v, 16); wr(f, p0, 3); wr(f, p1, 3);
-        wr(f, sa, 30); wr(f, ss, 30); wr(f, le, 30); wr(f, &g, 1); wr(f, dims, 3);
-        if (density) wr(f, density, (size_t)dims[0] * dims[1] * dims[2]);
-    }
-    fclose(f);
-    fprintf(stderr, "[harness] exported scene: %u nodes, %u prims, %zu materials, %zu lights -> %s\n",
-            nNodes, nPrims, mats.size(), lights.size(), fn.c_str());
-}
-
 // ---------------------------------------------------------------- photons
 static std::vector<Photon> g_photons;       // original (merge) order
 static uint32_t g_nshot = 0;
@@ -450,7 +313,7 @@ void pbrtWorldEnd() {
     for (size_t i = 0; i < g_ops.size(); ++i) {
         const std::string &op = g_ops[i];
         #define ARG(k) (i + (k) < g_ops.size() ? g_ops[i + (k)] : (fprintf(stderr, "missing arg for %s\n", op.c_str()), exit(2), g_ops[0]))
-        if (op == "--export-scene") { export_scene(scene, ARG(1)); i += 1; }
+        if (op == "--export-scene") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
         else if (op == "--shoot") { shoot(sh, scene, sr->camera, sr); }
         else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }
         else if (op == "--dump-photons") { dump_photons(ARG(1)); i += 1; }
