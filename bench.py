@@ -92,35 +92,74 @@ def cpu_gather_baseline(W, cfg, scene, pos, wi, alpha, rays, nsample, threads, s
 
 
 def run_reference(args, cfg, W, scene):
-    """--impl reference: the reference's CPU implementation of the gather on the host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the gather on the host cores (rank 0 only).
+    Preferred: oracle/_ref/ref_harness = the UNMODIFIED reference (KdTree<Photon>, PhotonVolumeIntegrator::Li, its pthread
+    task system) built from /root/reference by oracle/Makefile; it is fed the same scene, photon set and camera rays through
+    files.  Fallback when that binary is absent: the C port (oracle/pv_oracle.c)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import re
+    import tempfile
     threads = os.cpu_count() or 1
     n_ph = args.photons or cfg["photons"]
     pos, wi, alpha = W.photons_from_density(scene, n_ph)
     rays, _ = W.frame_rays(cfg)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    tree = O.KdTree(pos)
     nsample = args.ref_rays
-    times = []
-    for it in range(args.warmup + args.steps):
+    nit = args.warmup + args.steps
+    samples = []
+    for it in range(nit):
         sel = (np.linspace(0, len(rays) - 1, nsample).astype(np.int64) + it * 7) % len(rays)
-        sample = np.ascontiguousarray(rays[sel])
-        t0 = time.perf_counter()
-        O.gather(scene, tree, wi, alpha, sample, cfg["stepsize"], cfg["nused"], cfg["maxdist"], seed=args.seed, nthreads=threads)
-        if it >= args.warmup:
-            times.append(time.perf_counter() - t0)
+        samples.append(np.ascontiguousarray(rays[sel]))
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    kind = "reference" if os.path.exists(harness) and cfg["grid"] else "port"
+    times = []
+    if kind == "reference":
+        from cs348b_pbrt_b200 import sceneio, scenes
+        with tempfile.TemporaryDirectory() as tmp:
+            pho = os.path.join(tmp, "photons.pho")
+            with open(pho, "wb") as f:
+                f.write(b"PVPHOT01" + np.uint64(n_ph).tobytes())
+                for a in range(0, n_ph, 1 << 20):
+                    b = min(n_ph, a + (1 << 20))
+                    f.write(np.concatenate([pos[a:b], wi[a:b], alpha[a:b]], axis=1).astype(np.float32).tobytes())
+            dens = os.path.join(tmp, "density.raw")
+            scene.density.astype(np.float32).tofile(dens)
+            pbrt = os.path.join(tmp, "scene.pbrt")
+            open(pbrt, "w").write(scenes.cornell_pbrt(scenes.grid_volume_text(32, scenes.blob_density(32)), 0, stepsize=cfg["stepsize"],
+                                                      nused=cfg["nused"], maxdist=cfg["maxdist"]))
+            ops = ["--ncores", str(threads), "--grid-file", str(cfg["grid"]), dens, "--load-photons", pho]
+            for it in range(nit):
+                rf = os.path.join(tmp, "rays_%d.bin" % it)
+                sceneio.write_rays(rf, samples[it])
+                ops += ["--li-parallel", rf, str(1000 + it), "-"]
+            out = subprocess.run([harness, pbrt] + ops, capture_output=True, text=True)
+            if out.returncode != 0:
+                raise RuntimeError("ref_harness failed: " + out.stderr[-2000:])
+            found = re.findall(r"li-parallel: (\d+) rays in ([0-9.]+) s on (\d+) cores", out.stderr)
+            times = [float(t) for _, t, _ in found][args.warmup:]
+            if found:
+                threads = int(found[-1][2])
+    if not times:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        tree = O.KdTree(pos)
+        for it in range(nit):
+            t0 = time.perf_counter()
+            O.gather(scene, tree, wi, alpha, samples[it], cfg["stepsize"], cfg["nused"], cfg["maxdist"], seed=args.seed, nthreads=threads)
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
     dt = sum(times)
-    val = nsample * args.steps / dt
+    val = nsample * len(times) / dt
     out = {"impl": "reference", "metric": "volume-gather rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / len(times), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": cfg["label"], "photons": n_ph, "xres": cfg["xres"], "yres": cfg["yres"], "stepsize": cfg["stepsize"],
-                      "nused": cfg["nused"], "maxdist": cfg["maxdist"]},
-           "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                            "sample": "%d camera rays per step out of the %d-ray frame, full %d-photon map" % (nsample, len(rays), n_ph)},
+           "config": {"workload": cfg["label"], "photons": n_ph, "grid": cfg["grid"], "xres": cfg["xres"], "yres": cfg["yres"],
+                      "stepsize": cfg["stepsize"], "nused": cfg["nused"], "maxdist": cfg["maxdist"]},
+           "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
+                            "sample": "%d camera rays per step (every %d-th of the %d-ray frame), full %d-photon map in the reference's KdTree"
+                                      % (nsample, max(1, len(rays) // nsample), len(rays), n_ph)},
            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -141,7 +180,7 @@ def main():
     args = ap.parse_args()
 
     pkg = load_package()
-    from cs348b_pbrt_b200 import workloads as W
+    from cs348b_pbrt_b200 import workloads as W, multigpu as MG
     cfg = W.CONFIGS[args.workload]
     scene = W.load_scene(cfg)
     if args.impl == "reference":
@@ -183,16 +222,11 @@ def main():
             pv._chk(pv.lib.pv_shoot_blocks(pv.ctx, C.c_uint64(block + 1), C.c_uint32(wave), C.byref(prm), counts, C.byref(st)))
             cnt = torch.tensor(np.ctypeslib.as_array(counts).astype(np.int64), device=dev)
             if dist is not None:
-                dist.all_reduce(cnt)
-            cnt = cnt.cpu().numpy()
-            for c in cnt:
-                block += 1; total += int(c)
-                if total >= args.shoot_photons:
-                    last = block
-                    break
+                dist.all_reduce(cnt)                                   # deposits per block, summed over ranks
+            last, total, used = MG.last_block(cnt.cpu().numpy(), block + 1, total, args.shoot_photons)
+            block += used
             if not last:
-                per = max(total / block, 1e-3)
-                wave = int(min(max((args.shoot_photons - total) / per * 1.03 + 8, 64 * world), 262144))
+                wave = MG.next_wave(total, block, args.shoot_photons, world)
         pv._chk(pv.lib.pv_shoot_finish(pv.ctx, C.c_uint64(last)))
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -218,31 +252,16 @@ def main():
     if world == 1:
         pv.set_photons(pos, wi, alpha)
     else:
-        counts_t = torch.tensor([hi - lo], device=dev, dtype=torch.int64)
-        all_counts = [torch.zeros_like(counts_t) for _ in range(world)]
-        dist.all_gather(all_counts, counts_t)
-        all_counts = [int(c.item()) for c in all_counts]
-        mxc = max(all_counts)
-        loc = [torch.zeros((mxc, k), device=dev, dtype=torch.float32) for k in (3, 3, 30)]
-        for t, a in zip(loc, (pos, wi, alpha)):
-            t[:len(a)].copy_(torch.from_numpy(a))
-        full = [torch.empty((world * mxc, k), device=dev, dtype=torch.float32) for k in (3, 3, 30)]
         barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for t, f in zip(loc, full):
-            dist.all_gather_into_tensor(f, t)
-        e1.record(); torch.cuda.synchronize()
-        ag_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        f_pos, f_wi, f_alpha, n_all, ag_s = MG.allgather_photons(dist, torch, pos, wi, alpha, dev)
+        assert n_all == n_ph
+        ag_ms = torch.tensor([ag_s * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(ag_ms, op=dist.ReduceOp.MAX)
-        # drop the padding of short slices
-        keep = torch.cat([torch.arange(r * mxc, r * mxc + all_counts[r], device=dev) for r in range(world)])
-        full = [f.index_select(0, keep).contiguous() for f in full]
-        pv.set_photons_dev(full[0], full[1], full[2], n_ph)
+        pv.set_photons_dev(f_pos, f_wi, f_alpha, n_ph)
         nbytes = (world - 1) / world * n_ph * 144
         allgather = {"ms": float(ag_ms.item()), "bytes_in_per_gpu": nbytes, "gb_per_s_per_gpu": nbytes / (float(ag_ms.item()) * 1e-3) / 1e9,
                      "nvlink_peer_gb_per_s": 770.0}
-        del full, loc
+        del f_pos, f_wi, f_alpha
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     pv.build()

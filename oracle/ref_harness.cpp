@@ -301,6 +301,65 @@ static void transmittance(SamplerRenderer *ren, const Scene *scene, const std::s
     fclose(o);
 }
 
+
+// ---- the reference's own multithreaded path (core/parallel.cpp task system) over a ray file: what bench.py --impl reference times
+class LiTask : public Task {
+public:
+    LiTask(SamplerRenderer *r, const Scene *sc, const std::vector<pv_ray> *ry, size_t b, size_t e, uint32_t sd, float *o, Sample *orig)
+        : ren(r), scene(sc), rays(ry), begin(b), end(e), seed(sd), out(o), origSample(orig) {}
+    void Run() {
+        PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(ren->volumeIntegrator);
+        Sample *sample = origSample->Duplicate(1);
+        MemoryArena arena;
+        for (size_t i = begin; i < end; ++i) {
+            RayDifferential r(to_ray((*rays)[i]));
+            RNG rng(seed + (uint32_t)i);
+            sample->oneD[vi->scatterSampleOffset][0] = (*rays)[i].u_scatter;
+            sample->oneD[vi->tauSampleOffset][0] = 0.5f;
+            Spectrum T(1.f);
+            Spectrum L = vi->Li(scene, ren, r, sample, rng, &T, arena);
+            memcpy(out + 60 * i, L.c, 30 * sizeof(float)); memcpy(out + 60 * i + 30, T.c, 30 * sizeof(float));
+            arena.FreeAll();
+        }
+        delete[] sample;
+    }
+    SamplerRenderer *ren; const Scene *scene; const std::vector<pv_ray> *rays; size_t begin, end; uint32_t seed; float *out; Sample *origSample;
+};
+static void li_parallel(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
+    std::vector<pv_ray> rays = read_rays(rfn);
+    Sample *sample = new Sample(ren->sampler, ren->surfaceIntegrator, ren->volumeIntegrator, scene);
+    std::vector<float> out(60 * rays.size());
+    std::vector<Task *> tasks;
+    const size_t chunk = 64;
+    for (size_t b = 0; b < rays.size(); b += chunk)
+        tasks.push_back(new LiTask(ren, scene, &rays, b, std::min(rays.size(), b + chunk), seed, out.data(), sample));
+    double t0 = now_s();
+    EnqueueTasks(tasks);
+    WaitForAllTasks();
+    double dt = now_s() - t0;
+    for (size_t i = 0; i < tasks.size(); ++i) delete tasks[i];
+    fprintf(stderr, "[harness] li-parallel: %zu rays in %.6f s on %d cores\n", rays.size(), dt, NumSystemCores());
+    if (ofn != "-") {
+        FILE *o = xopen(ofn, "wb");
+        write_header(o, "PVLI0001", rays.size());
+        wr(o, out.data(), out.size());
+        fclose(o);
+    }
+}
+// replace the parsed (small) density grid by an n^3 grid read from a raw float file: the 256^3 grid of config 3 would be
+// a 120 MB text block in the .pbrt file
+static void swap_grid(Scene *scene, int n, const std::string &fn) {
+    VolumeGridDensity *gd = dynamic_cast<VolumeGridDensity *>(scene->volumeRegion);
+    if (!gd) { fprintf(stderr, "--grid-file needs a volumegrid scene\n"); exit(4); }
+    std::vector<float> d((size_t)n * n * n);
+    FILE *f = xopen(fn, "rb"); rd(f, d.data(), d.size()); fclose(f);
+    Transform v2w = Inverse(gd->WorldToVolume);
+    VolumeGridDensity *ng = new VolumeGridDensity(gd->sig_a, gd->sig_s, gd->g, gd->le, gd->extent, v2w, n, n, n, d.data());
+    scene->volumeRegion = ng;
+    scene->bound = Union(scene->aggregate->WorldBound(), ng->WorldBound());
+    fprintf(stderr, "[harness] density grid replaced by %d^3 from %s\n", n, fn.c_str());
+}
+
 // ---------------------------------------------------------------- WorldEnd hook
 void pbrtWorldEnd() {
     VERIFY_WORLD("WorldEnd");
@@ -321,6 +380,8 @@ void pbrtWorldEnd() {
         else if (op == "--lphoton") { lphoton(vi, scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--intersect") { intersect(scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--li") { li(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
+        else if (op == "--li-parallel") { li_parallel(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
+        else if (op == "--grid-file") { swap_grid(scene, atoi(ARG(1).c_str()), ARG(2)); i += 2; }
         else if (op == "--transmittance") { transmittance(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
         else if (op == "--stats") {
             FILE *f = xopen(ARG(1), "w");
