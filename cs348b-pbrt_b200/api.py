@@ -22,7 +22,8 @@ class PVError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "csrc", "libpv.so")
+    """csrc/libpv.so; PV_LIBPV names another build of the same library (kernel tuning variants, see csrc/variants.sh)."""
+    return os.environ.get("PV_LIBPV") or os.path.join(_HERE, "csrc", "libpv.so")
 
 
 def load_library():
@@ -202,6 +203,11 @@ class PhotonVolume:
     def last_kernel_ms(self):
         ms = C.c_float(0)
         self._chk(self.lib.pv_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def last_march_ms(self):
+        ms = C.c_float(0)
+        self._chk(self.lib.pv_last_march_ms(self.ctx, C.byref(ms)))
         return ms.value
 
     def stream(self):

@@ -44,6 +44,7 @@ int pv_create(pv_ctx **out, int device) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dscene, sizeof(DevScene)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_stats, sizeof(pv_gather_stats)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_counters, 64 * sizeof(unsigned long long)) == cudaSuccess &&
@@ -59,10 +60,12 @@ void pv_destroy(pv_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -329,7 +332,6 @@ int pv_gather_dev(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_p
     if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_gather_dev: null pointer"; return PV_EINVAL; }
     int rc = pvi_gather(ctx, rays, n, params, L, T); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n) cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return PV_OK;
 }
 int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
@@ -344,7 +346,6 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
     PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, d_L, sb, cudaMemcpyDeviceToHost, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, d_T, sb, cudaMemcpyDeviceToHost, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return PV_OK;
 }
 int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset) {
@@ -359,6 +360,12 @@ int pv_last_kernel_ms(pv_ctx *ctx, float *ms) {
     LOCK(ctx);
     if (!ms) { ctx->err = "pv_last_kernel_ms: null out"; return PV_EINVAL; }
     *ms = ctx->last_ms;
+    return PV_OK;
+}
+int pv_last_march_ms(pv_ctx *ctx, float *ms) {
+    LOCK(ctx);
+    if (!ms) { ctx->err = "pv_last_march_ms: null out"; return PV_EINVAL; }
+    *ms = ctx->last_march_ms;
     return PV_OK;
 }
 int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted, const pv_shoot_params *params, pv_shoot_stats *stats) {

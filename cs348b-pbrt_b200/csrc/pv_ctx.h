@@ -54,8 +54,12 @@ struct pv_ctx {
 
     pv_gather_stats *d_stats = nullptr;
     unsigned long long *d_counters = nullptr;      // work-distribution counters
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
+    // march records of the ray slice being gathered (pv_march.cu): RayHdr per ray, StepRec per march step
+    void *march_hdr = nullptr; size_t march_hdr_bytes = 0;
+    void *march_steps = nullptr; size_t march_steps_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // around gather_kernel
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels
+    float last_ms = 0.f, last_march_ms = 0.f;
     int sm_count = 148;
 };
 
@@ -76,6 +80,10 @@ int pvi_sort_pairs_u32(pv_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *ke
                        uint32_t **keys_out, uint32_t **vals_out);
 int pvi_sort_pairs_u64(pv_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int key_bits,
                        uint64_t **keys_out, uint32_t **vals_out);
+// pv_march.cu
+#define PV_MARCH_MAX_BYTES (16ull << 30)          // step records of one ray slice
+#define PV_GATHER_SLICE_RAYS (4ull << 20)
+int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, uint64_t *total_steps);
 // pv_gather.cu
 int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, uint32_t *d_idx, float *d_d2, uint32_t *d_nfound);
 int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L);

@@ -19,6 +19,7 @@
 // (summation order and libm differ), see tests/test_gpu_parity.py.
 #include <algorithm>
 #include "pv_grid.cuh"
+#include "pv_march.cuh"
 
 #ifndef GW_WARPS
 #define GW_WARPS 4                       // warps per CTA
@@ -47,7 +48,7 @@ struct WarpBuf { uint2 *ent; unsigned char *hdr; uint32_t cap; uint32_t phase; }
 __device__ __forceinline__ uint32_t *wb_hist(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr); }
 __device__ __forceinline__ uint32_t *wb_stats(const WarpBuf &b) { return reinterpret_cast<uint32_t *>(b.hdr + 1024); }
 __device__ __forceinline__ float4 *wb_stage(const WarpBuf &b) { return reinterpret_cast<float4 *>(b.hdr + WB_HDR_BYTES); }
-enum { ST_LOOKUPS = 0, ST_FOUND, ST_CAND, ST_HEAP, ST_SHADOW, ST_DENS };
+enum { ST_LOOKUPS = 0, ST_FOUND, ST_CAND, ST_HEAP };
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -478,8 +479,6 @@ __device__ __forceinline__ void flush_stats(pv_gather_stats *gs, const WarpBuf &
         atomicAdd((unsigned long long *)&gs->photons_found, (unsigned long long)st[ST_FOUND]);
         atomicAdd((unsigned long long *)&gs->candidates_tested, (unsigned long long)st[ST_CAND]);
         atomicAdd((unsigned long long *)&gs->heap_lookups, (unsigned long long)st[ST_HEAP]);
-        atomicAdd((unsigned long long *)&gs->shadow_rays, (unsigned long long)st[ST_SHADOW]);
-        atomicAdd((unsigned long long *)&gs->density_samples, (unsigned long long)st[ST_DENS]);
     }
 }
 
@@ -590,11 +589,11 @@ struct GatherArgs {
     MapView m;
     const DevScene *sc;
     const pv_ray *rays;
+    const RayHdr *hdr;             // per ray: where its march steps are (pv_march.cu)
+    const StepRec *steps;
     uint64_t n;
-    float stepsize, maxdist;
+    float maxdist;
     uint32_t nused, flags, cap;
-    uint32_t k0, k1;               // Philox key
-    uint64_t ray_index_base;
     float *L, *T;
     pv_gather_stats *stats;
     unsigned long long *counter;
@@ -616,16 +615,12 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
     // spectra in lane == bin layout
     const float sig_a = bin ? med.sigma_a[lane] : 0.f, sig_s = bin ? med.sigma_s[lane] : 0.f, le = bin ? med.le[lane] : 0.f;
     const float sig_t = sig_a + sig_s;
-    const float sig_t_max = warp_max(sig_t);
     float y_sig_a = 0.f, y_sig_s = 0.f;
     for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
     const bool y_any = y_sig_a != 0.f || y_sig_s != 0.f;                 // sa.y() != 0 || ss.y() != 0 wherever the density is non-zero
-    const bool any_sig_s = __ballot_sync(PV_FULL, sig_s != 0.f) != 0;    // !ss.IsBlack() wherever the density is non-zero
     const float r2 = a.maxdist * a.maxdist;
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
     const bool do_lookup = !rainbow && !(a.flags & PV_GATHER_NO_INDIRECT);
-    const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
-    const int nLights = (int)sc.n_lights;
     uint32_t nrays = 0;
     for (;;) {
         unsigned long long ri = 0;
@@ -633,73 +628,24 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
         ri = __shfl_sync(PV_FULL, ri, 0);
         if (ri >= a.n) break;
         nrays++;
-        const pv_ray ray = a.rays[ri];
-        const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
+        const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri));
+        const int nSamples = __float_as_int(h0.z);
+        const float step = h0.w;
+        const StepRec *recs = a.steps + (((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x));
         float Tr = 1.f, Lv = 0.f;
-        float t0, t1;
-        const bool hit = med.type != PV_MEDIUM_NONE && med_intersectp(med, ro, rd, ray.mint, ray.maxt, &t0, &t1) && (t1 - t0) != 0.f;
-        if (hit) {
-            const int nSamples = (int)ceilf(__fdiv_rn(t1 - t0, a.stepsize));
-            const float step = __fdiv_rn(t1 - t0, (float)nSamples);
-            const float t_first = t0;                           // p = ray(t0) before the jitter (photonvolume.cpp:133)
-            float tbase = t0 + ray.u_scatter * step;            // t0 += u * step
-            float t_carry = tbase;
-            const uint64_t gidx = a.ray_index_base + ri;
+        if (nSamples > 0) {
+            const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
+            const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
             bool stop = false;
             for (int c0 = 0; c0 < nSamples && !stop; c0 += 32) {
-                // ---------------- lane == step: everything that does not depend on the recurrence.
-                // Per step only seven scalars survive into the spectral pass:
-                //   c_t     sample parameter (p = ray(c_t))
-                //   c_tau   optical-depth scalar of the step segment (tau[b] = sig_t[b] * c_tau)
-                //   c_rr    Russian-roulette draw if Tr.y() < 1e-3 at this step, else -1
-                //   c_dens  density at p (1/0 for homogeneous media)
-                //   c_ln    light chosen for the step
-                //   c_sh    optical-depth scalar of the shadow ray
-                //   c_dfac  falloff / dist^2 * phase * nLights (0: unlit / occluded): L_d[b] = I[b] * exp(-sig_t[b]*c_sh) * c_dfac
-                const int si = c0 + (int)lane;
-                float c_t = tbase;
-                for (uint32_t j = 0; j < lane; ++j) c_t += step;     // the reference accumulates t0 += step (photonvolume.cpp:147)
-                float c_tau = 0.f, c_rr = -1.f, c_dens = 0.f, c_sh = 0.f, c_dfac = 0.f;
+                // ---------------- lane == step: the march records of the next 32 steps (written by march_steps_kernel)
+                float c_t = 0.f, c_tau = 0.f, c_rr = -1.f, c_dens = 0.f, c_sh = 0.f, c_dfac = 0.f;
                 int c_ln = 0;
-                uint32_t ns = 0, nshadow = 0;
-                if (si < nSamples) {
-                    float tprev = t_carry;                           // previous step (lane 0: last step of the previous chunk)
-                    if (lane > 0) { tprev = tbase; for (uint32_t j = 0; j + 1 < lane; ++j) tprev += step; }
-                    const v3 p = ray_at(ro, rd, c_t);
-                    const v3 pPrev = ray_at(ro, rd, si == 0 ? t_first : tprev);
-                    uint32_t sw[4];
-                    pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_STEP, a.k0, a.k1, sw);
-                    c_tau = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
-                    // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau) bounds every bin from below and y(1) ~ 1, so only large taus need the sum
-                    if (sig_t_max * c_tau > 6.0f) {
-                        float yy = 0.f;
-                        for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * c_tau));
-                        if (__fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f) c_rr = pv_u32_to_float(sw[1]);
-                    }
-                    c_dens = med_density(med, p, &ns);
-                    if (c_dens != 0.f && do_direct) {
-                        uint32_t rw[4];
-                        pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
-                        const float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
-                        c_ln = min((int)floorf(u_l * nLights), nLights - 1);
-                        LightQuery lq;
-                        light_query(sc.lights[c_ln], p, &lq);
-                        if (lq.falloff != 0.f) {
-                            nshadow = 1;
-                            float mt = lq.vis_maxt;
-                            if (bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
-                                c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize,
-                                                      pv_u32_to_float(sw[2]), &ns);
-                                const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
-                                c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
-                            }
-                        }
-                    }
+                if (c0 + (int)lane < nSamples) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(recs + c0 + lane);
+                    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                    c_t = ra.x; c_tau = ra.y; c_rr = ra.z; c_dens = ra.w; c_sh = rb.x; c_dfac = rb.y; c_ln = __float_as_int(rb.z);
                 }
-                __syncwarp();
-                ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);
-                if (lane == 0) { wb_stats(b)[ST_DENS] += ns; wb_stats(b)[ST_SHADOW] += nshadow; }
-                t_carry = __shfl_sync(PV_FULL, c_t, 31);
                 // ---------------- lane == bin: the recurrence, one step at a time
                 const int nthis = min(32, nSamples - c0);
                 Prefetch pf; pf.in_range = false; pf.issued = false;
@@ -742,10 +688,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
                     const float L_i = (s_dens != 0.f && y_any) ? L_d + __fdiv_rn(ss, sa + ss) * L_ii : L_d;
                     Lv = ((sa * (le * s_dens)) * step) + ((ss * L_i) * step) + (Tr * Lv);
                 }
-                tbase = t_carry + step;
             }
         }
-        if (bin) { a.L[ri * PV_NSPEC + lane] = hit ? Lv : 0.f; a.T[ri * PV_NSPEC + lane] = hit ? Tr : 1.f; }
+        if (bin) { a.L[ri * PV_NSPEC + lane] = Lv; a.T[ri * PV_NSPEC + lane] = Tr; }
     }
     flush_stats(a.stats, b, nrays, lane);
 }
@@ -798,23 +743,53 @@ int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, u
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }
-int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T) {
-    if (!ctx->has_scene) { ctx->err = "pv_gather: no scene"; return PV_ESTATE; }
-    bool need_map = !(prm->flags & PV_GATHER_NO_INDIRECT) && ctx->hscene.med.type != PV_MEDIUM_RAINBOW && ctx->hscene.med.type != PV_MEDIUM_NONE;
-    if (need_map && !ctx->built) { ctx->err = "pv_gather: photon map not built (call pv_build)"; return PV_ESTATE; }
-    if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
-    if (n == 0) return PV_OK;
+// Li for rays [0, n): march records first (pv_march.cu), then the gather kernel.  Rays are taken in slices so that the
+// step records of one slice stay within PV_MARCH_MAX_BYTES / the free device memory.
+static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, float *d_L, float *d_T) {
+    uint64_t total = 0;
+    pv_gather_params p = *prm;
+    int rc = pvi_march(ctx, d_rays, n, &p, flags, &total);
+    if (rc == PV_ENOMEM && n > 4096) {                      // step records do not fit: two half slices
+        const uint64_t h = n / 2;
+        rc = gather_slice(ctx, d_rays, h, prm, flags, d_L, d_T); if (rc) return rc;
+        p.ray_index_base = prm->ray_index_base + h;
+        return gather_slice(ctx, d_rays + h, n - h, &p, flags, d_L + h * PV_NSPEC, d_T + h * PV_NSPEC);
+    }
+    if (rc == PV_ENOMEM) ctx->err = "pv_gather: out of device memory for the march records";
+    if (rc) return rc;
     GatherArgs a;
-    a.m = map_view(ctx); a.sc = ctx->dscene; a.rays = d_rays; a.n = n; a.stepsize = prm->stepsize; a.maxdist = prm->maxdist;
-    a.nused = prm->nused; a.flags = prm->flags | (need_map ? 0u : PV_GATHER_NO_INDIRECT); a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
-    a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32); a.ray_index_base = prm->ray_index_base;
+    a.m = map_view(ctx); a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (const StepRec *)ctx->march_steps;
+    a.n = n; a.maxdist = prm->maxdist;
+    a.nused = prm->nused; a.flags = flags; a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
     a.L = d_L; a.T = d_T; a.stats = ctx->d_stats; a.counter = ctx->d_counters;
     int blocks; size_t smem;
-    int rc = launch_cfg(ctx, gather_kernel, a.cap, &blocks, &smem); if (rc) return rc;
+    rc = launch_cfg(ctx, gather_kernel, a.cap, &blocks, &smem); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     gather_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaGetLastError());
+    // device times of this slice (the next slice starts with a stream synchronisation anyway)
+    PV_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms += ms;
+    cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->last_march_ms += ms;
+    return PV_OK;
+}
+int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T) {
+    if (!ctx->has_scene) { ctx->err = "pv_gather: no scene"; return PV_ESTATE; }
+    bool need_map = !(prm->flags & PV_GATHER_NO_INDIRECT) && ctx->hscene.med.type != PV_MEDIUM_RAINBOW && ctx->hscene.med.type != PV_MEDIUM_NONE;
+    if (need_map && !ctx->built) { ctx->err = "pv_gather: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
+    ctx->last_ms = 0.f; ctx->last_march_ms = 0.f;
+    if (n == 0) return PV_OK;
+    const uint32_t flags = prm->flags | (need_map ? 0u : PV_GATHER_NO_INDIRECT);
+    const uint64_t slice = PV_GATHER_SLICE_RAYS;
+    for (uint64_t r0 = 0; r0 < n; r0 += slice) {
+        const uint64_t nr = std::min<uint64_t>(slice, n - r0);
+        pv_gather_params p = *prm; p.ray_index_base = prm->ray_index_base + r0;
+        int rc = gather_slice(ctx, d_rays + r0, nr, &p, flags, d_L + r0 * PV_NSPEC, d_T + r0 * PV_NSPEC);
+        if (rc) return rc;
+    }
     return PV_OK;
 }

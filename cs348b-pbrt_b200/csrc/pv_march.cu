@@ -1,0 +1,166 @@
+// pv_march.cu -- the map-independent half of PhotonVolumeIntegrator::Li (integrators/photonvolume.cpp:112-222).
+//
+//   march_setup_kernel  one thread per camera ray: medium interval (vr->IntersectP :119-124), nSamples / step
+//                       (:130-131), jittered start (:135); reserves the ray's StepRec run with one atomicAdd per warp.
+//   march_steps_kernel  one warp per ray, lane == march step (lanes stride over the ray's steps): sample position
+//                       with the reference's accumulated t0 += step (:147), step-segment optical depth (:153-155),
+//                       Russian-roulette draw (:158-165), density at the sample, light choice (:177-182), shadow ray
+//                       through the LinearBVHNode array and its optical depth (VisibilityTester::Transmittance,
+//                       core/light.cpp:51-56), phase function.
+// Both are streaming kernels: no shared memory, full occupancy.  The photon lookups and the Lv/Tr recurrence are in
+// pv_gather.cu; seven scalars per step cross over in a StepRec (pv_march.cuh).
+#include <algorithm>
+#include "pv_ctx.h"
+#include "pv_march.cuh"
+
+#define MS_THREADS 256
+
+__global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene *__restrict__ scp, const pv_ray *__restrict__ rays, uint64_t n,
+                                                                float stepsize, RayHdr *__restrict__ hdr, unsigned long long *total) {
+    const DevMedium &med = scp->med;
+    const uint64_t ri = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    int nSamples = 0; float step = 0.f, t_first = 0.f, tbase = 0.f;
+    if (ri < n) {
+        const pv_ray ray = rays[ri];
+        const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
+        float t0, t1;
+        if (med.type != PV_MEDIUM_NONE && med_intersectp(med, ro, rd, ray.mint, ray.maxt, &t0, &t1) && (t1 - t0) != 0.f) {
+            nSamples = (int)ceilf(__fdiv_rn(t1 - t0, stepsize));
+            if (nSamples < 0) nSamples = 0;
+            step = __fdiv_rn(t1 - t0, (float)nSamples);
+            t_first = t0;                                   // p = ray(t0) before the jitter (photonvolume.cpp:133)
+            tbase = t0 + ray.u_scatter * step;              // t0 += u * step
+        }
+    }
+    // reserve nSamples records: exclusive scan inside the warp, one atomic per warp
+    uint32_t inc = (uint32_t)nSamples;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
+    unsigned long long base = 0;
+    if (lane == 31 && inc) base = atomicAdd(total, (unsigned long long)inc);
+    base = __shfl_sync(PV_FULL, base, 31);
+    if (ri < n) {
+        RayHdr h;
+        h.offset = base + (inc - (uint32_t)nSamples); h.nSamples = nSamples; h.step = step;
+        h.pad[0] = t_first; h.pad[1] = tbase; h.pad[2] = 0.f; h.pad[3] = 0.f;
+        reinterpret_cast<float4 *>(hdr + ri)[0] = reinterpret_cast<const float4 *>(&h)[0];
+        reinterpret_cast<float4 *>(hdr + ri)[1] = reinterpret_cast<const float4 *>(&h)[1];
+    }
+}
+
+struct MarchArgs {
+    const DevScene *sc;
+    const pv_ray *rays;
+    const RayHdr *hdr;
+    StepRec *steps;
+    uint64_t n;
+    float stepsize;
+    uint32_t flags;
+    uint32_t k0, k1;               // Philox key
+    uint64_t ray_index_base;
+    pv_gather_stats *stats;
+};
+
+__global__ void __launch_bounds__(MS_THREADS) march_steps_kernel(MarchArgs a) {
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * MS_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * MS_THREADS) >> 5;
+    float sig_t_max = 0.f; bool any_sig_s = false;
+    for (int bb = 0; bb < PV_NSPEC; ++bb) { sig_t_max = fmaxf(sig_t_max, med.sigma_a[bb] + med.sigma_s[bb]); any_sig_s |= med.sigma_s[bb] != 0.f; }
+    const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
+    const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
+    const int nLights = (int)sc.n_lights;
+    uint32_t ns = 0, nshadow = 0;
+    for (uint64_t ri = warp0; ri < a.n; ri += nwarps) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri)), h1 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri) + 1);
+        const int nSamples = __float_as_int(h0.z);
+        if (nSamples <= 0) continue;
+        const unsigned long long off = ((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x);
+        const float step = h0.w, t_first = h1.x, tbase = h1.y;
+        const pv_ray ray = a.rays[ri];
+        const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
+        const uint64_t gidx = a.ray_index_base + ri;
+        uint32_t rw[4] = {0u, 0u, 0u, 0u};
+        if (do_direct) pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
+        // the reference accumulates t0 += step (photonvolume.cpp:147): step si sits at tbase + step + ... + step (si times)
+        float c_t = tbase, tprev = t_first;
+        for (uint32_t j = 0; j < lane; ++j) { tprev = c_t; c_t += step; }
+        for (int si = (int)lane; si < nSamples; si += 32) {
+            float c_tau, c_rr = -1.f, c_dens, c_sh = 0.f, c_dfac = 0.f;
+            int c_ln = 0;
+            const v3 p = ray_at(ro, rd, c_t);
+            const v3 pPrev = ray_at(ro, rd, si == 0 ? t_first : tprev);
+            uint32_t sw[4];
+            pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_STEP, a.k0, a.k1, sw);
+            c_tau = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
+            // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau) bounds every bin from below and y(1) ~ 1, so only large taus need the sum
+            if (sig_t_max * c_tau > 6.0f) {
+                float yy = 0.f;
+                for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * c_tau));
+                if (__fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f) c_rr = pv_u32_to_float(sw[1]);
+            }
+            c_dens = med_density(med, p, &ns);
+            if (c_dens != 0.f && do_direct) {
+                const float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
+                c_ln = min((int)floorf(u_l * nLights), nLights - 1);
+                LightQuery lq;
+                light_query(sc.lights[c_ln], p, &lq);
+                if (lq.falloff != 0.f) {
+                    nshadow++;
+                    float mt = lq.vis_maxt;
+                    if (bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
+                        c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize, pv_u32_to_float(sw[2]), &ns);
+                        const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
+                        c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
+                    }
+                }
+            }
+            float4 *out = reinterpret_cast<float4 *>(a.steps + off + (unsigned long long)si);
+            out[0] = make_float4(c_t, c_tau, c_rr, c_dens);
+            out[1] = make_float4(c_sh, c_dfac, __int_as_float(c_ln), 0.f);
+            for (int j = 0; j < 32; ++j) { tprev = c_t; c_t += step; }
+        }
+    }
+    ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);
+    if (lane == 0 && a.stats) {
+        atomicAdd((unsigned long long *)&a.stats->density_samples, (unsigned long long)ns);
+        atomicAdd((unsigned long long *)&a.stats->shadow_rays, (unsigned long long)nshadow);
+    }
+}
+
+// Fills ctx->march_hdr / ctx->march_steps for rays [0, n).  Returns PV_ENOMEM (without an error message change) when the
+// step records do not fit, so the caller can retry with fewer rays.
+int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, uint64_t *total_steps) {
+    int rc = pv_ensure(ctx, &ctx->march_hdr, &ctx->march_hdr_bytes, n * sizeof(RayHdr)); if (rc) return rc;
+    unsigned long long *d_total = ctx->d_counters + 8;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    const uint32_t blocks = (uint32_t)((n + MS_THREADS - 1) / MS_THREADS);
+    march_setup_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(ctx->dscene, d_rays, n, prm->stepsize, (RayHdr *)ctx->march_hdr, d_total);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    unsigned long long total = 0;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *total_steps = total;
+    size_t free_b = 0, total_b = 0;
+    const size_t need = (size_t)total * sizeof(StepRec);
+    if (need > ctx->march_steps_bytes) {
+        PV_CUDA_CHECK(ctx, cudaMemGetInfo(&free_b, &total_b));
+        if (need > free_b + ctx->march_steps_bytes || need > (size_t)PV_MARCH_MAX_BYTES) return PV_ENOMEM;
+    }
+    rc = pv_ensure(ctx, &ctx->march_steps, &ctx->march_steps_bytes, need); if (rc) return rc;
+    MarchArgs a;
+    a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (StepRec *)ctx->march_steps; a.n = n;
+    a.stepsize = prm->stepsize; a.flags = flags; a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
+    a.ray_index_base = prm->ray_index_base; a.stats = ctx->d_stats;
+    if (total) {
+        const uint64_t want = (n * 32 + MS_THREADS - 1) / MS_THREADS;
+        const uint32_t mblocks = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);      // 8 CTAs of 8 warps per SM
+        march_steps_kernel<<<mblocks, MS_THREADS, 0, ctx->stream>>>(a);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    return PV_OK;
+}

@@ -206,8 +206,11 @@ int pv_gather_dev(pv_ctx *ctx, const pv_ray *rays, uint64_t n,
 int pv_lphoton(pv_ctx *ctx, const float *pts, const float *w, uint64_t n,
                uint32_t nused, float maxdist, float *L);
 int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset);
-/* device time (ms) of the last gather kernel launch, CUDA events on its stream */
+/* Device times (ms) of the last pv_gather / pv_gather_dev call, CUDA events on its
+ * stream: the gather kernel (lookups + estimate + recurrence) and the march
+ * kernels that precede it (per-step medium / shadow-ray work).                */
 int pv_last_kernel_ms(pv_ctx *ctx, float *ms);
+int pv_last_march_ms(pv_ctx *ctx, float *ms);
 
 /* ---- PhotonShooter::Preprocess, volume branch (photonshooter.cpp:457-526) */
 int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted,
