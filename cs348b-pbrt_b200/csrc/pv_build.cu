@@ -9,6 +9,7 @@
 // Everything is HBM-bound streaming work; algorithmic bytes per photon are listed in DESIGN.md.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "pv_grid.cuh"
 
 // ------------------------------------------------------------------ exclusive scan (u32)
@@ -208,7 +209,7 @@ __global__ void bbox_kernel(const float *__restrict__ pos, uint64_t n, int *__re
 __global__ void keys_kernel(const float *__restrict__ pos, uint64_t n, GridParams g, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int cx = pv_cell_coord(pos[3 * i + 0], g.origin[0], g.inv_h, g.dims[0]);
+    int cx = pv_cell_coord(pos[3 * i + 0], g.origin[0], g.inv_hx, g.dims[0]);
     int cy = pv_cell_coord(pos[3 * i + 1], g.origin[1], g.inv_h, g.dims[1]);
     int cz = pv_cell_coord(pos[3 * i + 2], g.origin[2], g.inv_h, g.dims[2]);
     keys[i] = pv_cell_key(g.xbits, cx, cy, cz);
@@ -257,7 +258,7 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     if (!(maxdist > 0.f)) { ctx->err = "pv_build: maxdist must be > 0"; return PV_EINVAL; }
     GridParams g{};
     if (n == 0) {
-        g.origin[0] = g.origin[1] = g.origin[2] = 0.f; g.h = maxdist; g.inv_h = 1.f / maxdist;
+        g.origin[0] = g.origin[1] = g.origin[2] = 0.f; g.h = maxdist; g.inv_h = 1.f / maxdist; g.hx = g.h; g.inv_hx = g.inv_h; g.xshift = 0;
         g.dims[0] = g.dims[1] = g.dims[2] = 1; g.xbits = 0; g.yzbits = 0; g.table_size = 1; g.margin = 0.f;
         if (ctx->table_cap < 2) {
             if (ctx->cell_start) cudaFree(ctx->cell_start);
@@ -307,8 +308,24 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
         g.dims[a] = std::min(max_dim, std::max(1, (int)std::floor(ext[a] / h) + 1));
         maxd = std::max(maxd, g.dims[a]);
     }
-    g.xbits = ceil_log2(g.dims[0]);
     g.yzbits = ceil_log2(std::max(g.dims[1], g.dims[2]));
+    // finer cells along x (up to two halvings) while the key stays within 24 bits and cells are not much
+    // more numerous than photons
+    g.xshift = 0;
+    {
+        const int coarse = g.dims[0];
+        int xs_max = 2;
+        if (const char *e = getenv("PV_XSHIFT_MAX")) xs_max = std::max(0, std::min(4, atoi(e)));      // tuning knob
+        for (int xs = 1; xs <= xs_max; ++xs) {
+            const int fine = coarse << xs;
+            if (ceil_log2(fine) + 2 * g.yzbits > 24) break;
+            if ((double)fine * g.dims[1] * g.dims[2] > 8.0 * (double)n) break;
+            g.xshift = xs;
+        }
+    }
+    g.hx = g.h / (float)(1 << g.xshift); g.inv_hx = 1.f / g.hx;       // exact: a power of two
+    g.dims[0] = std::max(1, (int)std::floor(ext[0] / (double)g.hx) + 1);
+    g.xbits = ceil_log2(g.dims[0]);
     g.table_size = (uint32_t)1 << (g.xbits + 2 * g.yzbits);
     g.margin = (float)(1e-4 * h + 4e-6 * (maxabs + maxext));
     g.one_shell_r = g.h - 2.f * g.margin;            // lookups with r <= this never need more than the 3x3x3 block

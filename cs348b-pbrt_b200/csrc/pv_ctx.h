@@ -6,13 +6,18 @@
 #include <vector>
 #include "pv_device.cuh"
 
-// Uniform grid of photon cells.  Sort key of a cell = (morton2(cy, cz) << xbits) | cx:
-// rows of cells along x are contiguous in memory (a (2s+1)-cell run of a lookup block is ONE
-// contiguous photon range), rows themselves follow a Morton (Z-order) curve over (y, z).
+// Grid of photon cells.  Sort key of a cell = (morton2(cy, cz) << xbits) | cx:
+// rows of cells along x are contiguous in memory (the part of a row a lookup needs is ONE contiguous
+// photon range), rows themselves follow a Morton (Z-order) curve over (y, z).  Cells are h x h in (y, z) and
+// hx = h / 2^xshift along x: the finer x resolution lets a lookup clip each row to the chord of its search
+// sphere at no extra cost (still one range per row).  "Coarse" x cells (2^xshift fine cells, h wide) keep the
+// shell geometry of the k-nearest search cubic.
 struct GridParams {
     float origin[3];
     float h, inv_h;
-    int dims[3];
+    float hx, inv_hx;       // cell size along x
+    int xshift;             // h = hx * 2^xshift
+    int dims[3];            // dims[0] counts FINE x cells
     int xbits, yzbits;      // key bits: xbits + 2*yzbits
     uint32_t table_size;    // number of keys (cell_start has table_size + 1 entries)
     float margin;           // conservative slack subtracted from the guaranteed search radius

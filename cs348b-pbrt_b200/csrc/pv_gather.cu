@@ -29,8 +29,16 @@
 #endif
 #define GW_THREADS (GW_WARPS * 32)
 #ifndef GW_STAGE
-#define GW_STAGE 512                     // candidates staged per TMA round (x 16 B)
+#define GW_STAGE 256                     // candidates staged per TMA round (x 16 B)
 #endif
+#ifndef GW_ALPHA_NOALLOC
+#define GW_ALPHA_NOALLOC 1
+#endif
+#ifndef GW_P2_UNROLL
+#define GW_P2_UNROLL 4
+#endif
+#define GW_STR(x) #x
+#define GW_UNROLL(n) _Pragma(GW_STR(unroll n))
 
 struct MapView {
     const float4 *pos4;            // x, y, z, sorted position of the photon (bits): a staged candidate carries its own address
@@ -244,52 +252,65 @@ __device__ __forceinline__ void batch_finish(const MapView &m, WarpBuf &b, const
 }
 
 // Prefetched first batch of a lookup (the 3x3x3 block of the query's cell)
-struct Prefetch { bool in_range, issued, fast; int cx, cy, cz; uint32_t rs, re; Batch bt; };
+// Only what the common (fixed-radius, in-grid) lookup needs is carried from one march step to the next: the run
+// [bt.rs, bt.rs + bt.len) of this lane's row and the batch totals.  The query's cell is recomputed on the rare shell path.
+struct Prefetch { bool in_range, issued, fast; Batch bt; };
+// clamped cell of a query point: COARSE x cell (the cubic shell geometry of the k-nearest search is in coarse cells), y, z
+__device__ __forceinline__ void lookup_cell(const GridParams &g, v3 q, int &cx, int &cy, int &cz) {
+    const int ux = (int)floorf((q.x - g.origin[0]) * g.inv_hx), uy = (int)floorf((q.y - g.origin[1]) * g.inv_h),
+              uz = (int)floorf((q.z - g.origin[2]) * g.inv_h);
+    cx = min(max(ux, 0), g.dims[0] - 1) >> g.xshift; cy = min(max(uy, 0), g.dims[1] - 1); cz = min(max(uz, 0), g.dims[2] - 1);
+}
 
 __device__ __forceinline__ bool lookup_in_range(const GridParams &g, v3 q, float r) {
     const float slack = r + g.margin;
-    return !(q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.h + slack || q.y < g.origin[1] - slack ||
+    return !(q.x < g.origin[0] - slack || q.x > g.origin[0] + g.dims[0] * g.hx + slack || q.y < g.origin[1] - slack ||
              q.y > g.origin[1] + g.dims[1] * g.h + slack || q.z < g.origin[2] - slack || q.z > g.origin[2] + g.dims[2] * g.h + slack);
 }
-// The nine rows of the 3x3x3 block, each ONE contiguous run of <= 3 cells: lanes 0..8 load [rs, re).
-// Rows (and end cells of a row) whose nearest point is at least r away cannot hold a photon with d2 < r2 and are
-// dropped; distances to cell faces are shrunk by the grid margin first, so the cull is conservative.
+// The nine rows of the 3x3 (y, z) block around the query, each ONE contiguous photon run: lanes 0..8 load [rs, re).
+// A row whose (y, z) slab is at least r away cannot hold a photon with d2 < r2 and is dropped; the others are clipped
+// along x to the chord of the search sphere at that row, in fine x cells.  Distances to cell faces are shrunk and the
+// chord is widened by the grid margin first, and floor((p - o) * inv_hx) is monotone in p, so the clip is conservative.
 __device__ __forceinline__ void lookup_ranges(const MapView &m, v3 q, float r, uint32_t k, uint32_t lane, Prefetch &pf) {
     const GridParams &g = m.g;
-    pf.issued = false; pf.fast = false; pf.rs = 0; pf.re = 0;
+    pf.issued = false; pf.fast = false; pf.bt.rs = 0; pf.bt.len = 0; pf.bt.E = 0; pf.bt.T = 0;
     // unclamped cell of the query: inside the grid is the common case and needs no distance test
-    const int ux = (int)floorf((q.x - g.origin[0]) * g.inv_h), uy = (int)floorf((q.y - g.origin[1]) * g.inv_h),
+    const int ux = (int)floorf((q.x - g.origin[0]) * g.inv_hx), uy = (int)floorf((q.y - g.origin[1]) * g.inv_h),
               uz = (int)floorf((q.z - g.origin[2]) * g.inv_h);
     const bool inside = ux >= 0 && ux < g.dims[0] && uy >= 0 && uy < g.dims[1] && uz >= 0 && uz < g.dims[2];
     pf.in_range = m.n != 0 && k != 0 && (inside || lookup_in_range(g, q, r));
     if (!pf.in_range) return;
-    const int cx = min(max(ux, 0), g.dims[0] - 1), cy = min(max(uy, 0), g.dims[1] - 1), cz = min(max(uz, 0), g.dims[2] - 1);
-    pf.cx = cx; pf.cy = cy; pf.cz = cz;
-    pf.fast = inside && r <= g.one_shell_r;              // the 3x3x3 block is exhaustive: no shell loop, no radius bookkeeping
+    const int cx = min(max(ux, 0), g.dims[0] - 1) >> g.xshift, cy = min(max(uy, 0), g.dims[1] - 1), cz = min(max(uz, 0), g.dims[2] - 1);
+    pf.fast = inside && r <= g.one_shell_r;              // the 3x3 rows are exhaustive: no shell loop, no radius bookkeeping
     if (lane < 9) {
         const int dy = (int)(lane % 3u) - 1, dz = (int)(lane / 3u) - 1;
         const int y = cy + dy, z = cz + dz;
         if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
             // distance from q to the row's slab in y and z (0 for the query's own slab)
-            const float ylo = g.origin[1] + cy * g.h, zlo = g.origin[2] + cz * g.h, xlo = g.origin[0] + cx * g.h;
+            const float ylo = g.origin[1] + cy * g.h, zlo = g.origin[2] + cz * g.h;
             float gy = dy == 0 ? 0.f : (dy < 0 ? q.y - ylo : (ylo + g.h) - q.y);
             float gz = dz == 0 ? 0.f : (dz < 0 ? q.z - zlo : (zlo + g.h) - q.z);
             gy = fmaxf(gy - g.margin, 0.f); gz = fmaxf(gz - g.margin, 0.f);
             const float w2 = r * r - (gy * gy + gz * gz);
             if (w2 > 0.f) {
-                const float gl = fmaxf((q.x - xlo) - g.margin, 0.f), gh = fmaxf(((xlo + g.h) - q.x) - g.margin, 0.f);
-                const int xa = (cx > 0 && gl * gl < w2) ? cx - 1 : cx;
-                const int xb = (cx < g.dims[0] - 1 && gh * gh < w2) ? cx + 1 : cx;
-                const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-                pf.rs = __ldg(m.cell_start + (rowkey | (uint32_t)xa));
-                pf.re = __ldg(m.cell_start + (rowkey | (uint32_t)xb) + 1);
+                const float half = __fsqrt_ru(w2) + g.margin;
+                int xa = (int)floorf(((q.x - half) - g.origin[0]) * g.inv_hx), xb = (int)floorf(((q.x + half) - g.origin[0]) * g.inv_hx);
+                if (!pf.fast) {                           // shell 1 of the k-nearest search: the coarse cells cx-1 .. cx+1 only
+                    xa = max(xa, (cx - 1) << g.xshift); xb = min(xb, ((cx + 2) << g.xshift) - 1);
+                }
+                xa = max(xa, 0); xb = min(xb, g.dims[0] - 1);
+                if (xa <= xb) {
+                    const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                    pf.bt.rs = __ldg(m.cell_start + (rowkey | (uint32_t)xa));
+                    pf.bt.len = __ldg(m.cell_start + (rowkey | (uint32_t)xb) + 1);      // run END until lookup_issue turns it into a length
+                }
             }
         }
     }
 }
 __device__ __forceinline__ void lookup_issue(const MapView &m, WarpBuf &b, uint32_t lane, Prefetch &pf) {
     if (!pf.in_range) return;
-    pf.bt = batch_begin(m, b, pf.rs, pf.re, lane);
+    pf.bt = batch_begin(m, b, pf.bt.rs, pf.bt.len, lane);
     pf.issued = true;
 }
 
@@ -304,7 +325,9 @@ __device__ __noinline__ ShellState lookup_shell(MapView m, WarpBuf b, int s, int
     uint32_t count = st.count, cand = st.cand; float boundk = st.boundk; bool have_k = st.have_k != 0;
     b.phase = st.phase;
     const int side = 2 * s + 1, rows = side * side;
-    const int x0 = max(cx - s, 0), x1 = min(cx + s, g.dims[0] - 1);
+    // x extent of the shell in fine cells: coarse cells cx-s .. cx+s
+    const int xs = g.xshift, xlast = g.dims[0] - 1;
+    const int x0 = max((cx - s) << xs, 0), x1 = min(((cx + s + 1) << xs) - 1, xlast);
     for (int j0 = 0; j0 < rows; j0 += 32) {
         const int j = j0 + (int)lane;
         uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
@@ -314,11 +337,13 @@ __device__ __noinline__ ShellState lookup_shell(MapView m, WarpBuf b, int s, int
             if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
                 const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
                 if (max(abs(dy), abs(dz)) == s) {
-                    sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0));
-                    ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1);
+                    if (x0 <= x1) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1); }
                 } else {
-                    if (cx - s >= 0) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s))); ea = __ldg(m.cell_start + (rowkey | (uint32_t)(cx - s)) + 1); }
-                    if (cx + s < g.dims[0]) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s))); eb = __ldg(m.cell_start + (rowkey | (uint32_t)(cx + s)) + 1); }
+                    // inner rows: the two end (coarse) cells of the shell
+                    const int la = (cx - s) << xs, lb = min(((cx - s + 1) << xs) - 1, xlast);
+                    const int ra = (cx + s) << xs, rb = min(((cx + s + 1) << xs) - 1, xlast);
+                    if (cx - s >= 0 && la <= lb) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)la)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)lb) + 1); }
+                    if (ra <= xlast) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)ra)); eb = __ldg(m.cell_start + (rowkey | (uint32_t)rb) + 1); }
                 }
             }
         }
@@ -342,10 +367,10 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
     if (pfp) pf = *pfp; else { lookup_ranges(m, q, r, k, lane, pf); }
     if (!pf.in_range) return 0;
     if (!pf.issued) lookup_issue(m, b, lane, pf);
-    const int cx = pf.cx, cy = pf.cy, cz = pf.cz;
     uint32_t count = 0, cand = 0;
     bool have_k = false;
     float boundk = INFINITY;
+    int cx = 0, cy = 0, cz = 0;
     for (int s = 1;; ++s) {
         if (s == 1) batch_finish(m, b, pf.bt, q, r2, k, lane, count, boundk, have_k, cand);
         else {
@@ -355,15 +380,17 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
         }
         if (count > k) { count = warp_select_k(m.orig, b.ent, wb_hist(b), count, k, lane, boundk); have_k = true; }
         if (s == 1 && pf.fast) break;
+        if (s == 1) lookup_cell(g, q, cx, cy, cz);
         // radius up to which the block [c-s, c+s]^3 is guaranteed to contain every photon with d2 < r2
         float gr = INFINITY;
         {
             const float qq[3] = {q.x, q.y, q.z}; const int cc[3] = {cx, cy, cz};
+            const int ncoarse[3] = {((g.dims[0] - 1) >> g.xshift) + 1, g.dims[1], g.dims[2]};      // x in coarse cells of width h
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const int lo = cc[a] - s, hi = cc[a] + s;
                 if (lo > 0) gr = fminf(gr, qq[a] - (g.origin[a] + lo * g.h));
-                if (hi < g.dims[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
+                if (hi < ncoarse[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
             }
         }
         if (gr == INFINITY) break;                       // the block covers the whole grid
@@ -385,6 +412,16 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
     return count;
 }
 
+// 128-bit load of a photon's alpha quarter-line that does not allocate in L1: with ~220 KB of the SM's 256 KB carved
+// out as shared memory L1 is tiny, and the alpha lines (read once per lookup) would evict everything else.
+__device__ __forceinline__ float4 ld_alpha(const float4 *p) {
+#if !GW_ALPHA_NOALLOC
+    return __ldg(p);
+#endif
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 // LPhoton tail (photonvolume.cpp:83-104): returns totalFlux[lane] / (4/3 pi r^3 sigma_s[lane]) in lane == bin layout.
 // The phase function is not part of any discrete decision, so it uses the fast reciprocal square root
 // (<= 2 ulp, far inside the 1e-4 radiance tolerance): PhaseHG = (1-g^2)/(4 pi) * x^-3/2.
@@ -420,19 +457,21 @@ __device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
     uint32_t e0 = grp;
+GW_UNROLL(GW_P2_UNROLL)
     for (; e0 + 12 < padded; e0 += 16) {
         const uint2 v0 = b.ent[e0], v1 = b.ent[e0 + 4], v2 = b.ent[e0 + 8], v3_ = b.ent[e0 + 12];
-        const float4 x0 = __ldg(a4 + (size_t)v0.y * 8), x1 = __ldg(a4 + (size_t)v1.y * 8);
-        const float4 x2 = __ldg(a4 + (size_t)v2.y * 8), x3 = __ldg(a4 + (size_t)v3_.y * 8);
+        const float4 x0 = ld_alpha(a4 + (size_t)v0.y * 8), x1 = ld_alpha(a4 + (size_t)v1.y * 8);
+        const float4 x2 = ld_alpha(a4 + (size_t)v2.y * 8), x3 = ld_alpha(a4 + (size_t)v3_.y * 8);
         const float p0 = __uint_as_float(v0.x), p1 = __uint_as_float(v1.x), p2 = __uint_as_float(v2.x), p3 = __uint_as_float(v3_.x);
         acc.x = fmaf(x0.x, p0, acc.x); acc.y = fmaf(x0.y, p0, acc.y); acc.z = fmaf(x0.z, p0, acc.z); acc.w = fmaf(x0.w, p0, acc.w);
         acc2.x = fmaf(x1.x, p1, acc2.x); acc2.y = fmaf(x1.y, p1, acc2.y); acc2.z = fmaf(x1.z, p1, acc2.z); acc2.w = fmaf(x1.w, p1, acc2.w);
         acc.x = fmaf(x2.x, p2, acc.x); acc.y = fmaf(x2.y, p2, acc.y); acc.z = fmaf(x2.z, p2, acc.z); acc.w = fmaf(x2.w, p2, acc.w);
         acc2.x = fmaf(x3.x, p3, acc2.x); acc2.y = fmaf(x3.y, p3, acc2.y); acc2.z = fmaf(x3.z, p3, acc2.z); acc2.w = fmaf(x3.w, p3, acc2.w);
     }
+#pragma unroll 1
     for (; e0 < padded; e0 += 8) {                            // padded is a multiple of 8: e0 and e0 + 4 are valid
         const uint2 va = b.ent[e0], vb = b.ent[e0 + 4];
-        const float4 aa = __ldg(a4 + (size_t)va.y * 8), ab = __ldg(a4 + (size_t)vb.y * 8);
+        const float4 aa = ld_alpha(a4 + (size_t)va.y * 8), ab = ld_alpha(a4 + (size_t)vb.y * 8);
         const float pha = __uint_as_float(va.x), phb = __uint_as_float(vb.x);
         acc.x = fmaf(aa.x, pha, acc.x); acc.y = fmaf(aa.y, pha, acc.y); acc.z = fmaf(aa.z, pha, acc.z); acc.w = fmaf(aa.w, pha, acc.w);
         acc2.x = fmaf(ab.x, phb, acc2.x); acc2.y = fmaf(ab.y, phb, acc2.y); acc2.z = fmaf(ab.z, phb, acc2.z); acc2.w = fmaf(ab.w, phb, acc2.w);

@@ -2,7 +2,7 @@
 //
 //   march_setup_kernel  one thread per camera ray: medium interval (vr->IntersectP :119-124), nSamples / step
 //                       (:130-131), jittered start (:135); reserves the ray's StepRec run with one atomicAdd per warp.
-//   march_steps_kernel  one warp per ray, lane == march step (lanes stride over the ray's steps): sample position
+//   march_steps_kernel  one thread per ray (a warp = 32 neighbouring rays marching in lockstep): sample position
 //                       with the reference's accumulated t0 += step (:147), step-segment optical depth (:153-155),
 //                       Russian-roulette draw (:158-165), density at the sample, light choice (:177-182), shadow ray
 //                       through the LinearBVHNode array and its optical depth (VisibilityTester::Transmittance,
@@ -13,7 +13,10 @@
 #include "pv_ctx.h"
 #include "pv_march.cuh"
 
-#define MS_THREADS 256
+#define MS_THREADS 128
+#ifndef MS_MIN_CTAS
+#define MS_MIN_CTAS 8
+#endif
 
 __global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene *__restrict__ scp, const pv_ray *__restrict__ rays, uint64_t n,
                                                                 float stepsize, RayHdr *__restrict__ hdr, unsigned long long *total) {
@@ -62,39 +65,45 @@ struct MarchArgs {
     pv_gather_stats *stats;
 };
 
-__global__ void __launch_bounds__(MS_THREADS) march_steps_kernel(MarchArgs a) {
+// One THREAD per ray, steps in sequence: the 32 lanes of a warp are 32 neighbouring camera rays (callers pass rays
+// in image-tile order) at the same march depth, so their density taps fall into the same few voxels and the warp's
+// eight trilinear taps touch a handful of 32-byte sectors instead of 256.
+__global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(MarchArgs a) {
     const DevScene &sc = *a.sc;
     const DevMedium &med = sc.med;
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * MS_THREADS + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * MS_THREADS) >> 5;
     float sig_t_max = 0.f; bool any_sig_s = false;
     for (int bb = 0; bb < PV_NSPEC; ++bb) { sig_t_max = fmaxf(sig_t_max, med.sigma_a[bb] + med.sigma_s[bb]); any_sig_s |= med.sigma_s[bb] != 0.f; }
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
     const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
     const int nLights = (int)sc.n_lights;
     uint32_t ns = 0, nshadow = 0;
-    for (uint64_t ri = warp0; ri < a.n; ri += nwarps) {
-        const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri)), h1 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri) + 1);
-        const int nSamples = __float_as_int(h0.z);
-        if (nSamples <= 0) continue;
+    const uint64_t ri = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x;
+    int nSamples = 0;
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+    if (ri < a.n) {
+        h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri)); h1 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri) + 1);
+        nSamples = __float_as_int(h0.z);
+    }
+    if (nSamples > 0) {
         const unsigned long long off = ((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x);
-        const float step = h0.w, t_first = h1.x, tbase = h1.y;
+        const float step = h0.w, t_first = h1.x;
         const pv_ray ray = a.rays[ri];
         const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
         const uint64_t gidx = a.ray_index_base + ri;
         uint32_t rw[4] = {0u, 0u, 0u, 0u};
         if (do_direct) pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
-        // the reference accumulates t0 += step (photonvolume.cpp:147): step si sits at tbase + step + ... + step (si times)
-        float c_t = tbase, tprev = t_first;
-        for (uint32_t j = 0; j < lane; ++j) { tprev = c_t; c_t += step; }
-        for (int si = (int)lane; si < nSamples; si += 32) {
+        float c_t = h1.y;                                   // t0 + u * step; then t0 += step per sample (photonvolume.cpp:135,147)
+        v3 pPrev = ray_at(ro, rd, t_first);
+        float4 *out = reinterpret_cast<float4 *>(a.steps + off);
+        for (int si = 0; si < nSamples; ++si, c_t += step, out += 2) {
             float c_tau, c_rr = -1.f, c_dens, c_sh = 0.f, c_dfac = 0.f;
             int c_ln = 0;
             const v3 p = ray_at(ro, rd, c_t);
-            const v3 pPrev = ray_at(ro, rd, si == 0 ? t_first : tprev);
             uint32_t sw[4];
             pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_STEP, a.k0, a.k1, sw);
             c_tau = med_tau_scalar(med, pPrev, p - pPrev, 0.f, 1.f, .5f * a.stepsize, pv_u32_to_float(sw[0]), &ns);
+            pPrev = p;
             // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau) bounds every bin from below and y(1) ~ 1, so only large taus need the sum
             if (sig_t_max * c_tau > 6.0f) {
                 float yy = 0.f;
@@ -117,14 +126,12 @@ __global__ void __launch_bounds__(MS_THREADS) march_steps_kernel(MarchArgs a) {
                     }
                 }
             }
-            float4 *out = reinterpret_cast<float4 *>(a.steps + off + (unsigned long long)si);
             out[0] = make_float4(c_t, c_tau, c_rr, c_dens);
             out[1] = make_float4(c_sh, c_dfac, __int_as_float(c_ln), 0.f);
-            for (int j = 0; j < 32; ++j) { tprev = c_t; c_t += step; }
         }
     }
     ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);
-    if (lane == 0 && a.stats) {
+    if (lane == 0 && a.stats && (ns | nshadow)) {
         atomicAdd((unsigned long long *)&a.stats->density_samples, (unsigned long long)ns);
         atomicAdd((unsigned long long *)&a.stats->shadow_rays, (unsigned long long)nshadow);
     }
@@ -156,9 +163,7 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     a.stepsize = prm->stepsize; a.flags = flags; a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
     a.ray_index_base = prm->ray_index_base; a.stats = ctx->d_stats;
     if (total) {
-        const uint64_t want = (n * 32 + MS_THREADS - 1) / MS_THREADS;
-        const uint32_t mblocks = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);      // 8 CTAs of 8 warps per SM
-        march_steps_kernel<<<mblocks, MS_THREADS, 0, ctx->stream>>>(a);
+        march_steps_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
