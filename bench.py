@@ -173,8 +173,8 @@ def main():
     ap.add_argument("--workload", default="config3")
     ap.add_argument("--photons", type=int, default=0, help="override the photon count (debug only; invalidates the number)")
     ap.add_argument("--shoot-photons", type=int, default=400_000, help="bounded photon-shooting sample for the shoot rates")
-    ap.add_argument("--cpu-rays", type=int, default=40_000, help="rays of the bounded CPU-baseline sample")
-    ap.add_argument("--ref-rays", type=int, default=60_000)
+    ap.add_argument("--cpu-rays", type=int, default=600_000, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-rays", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=348)
     args = ap.parse_args()

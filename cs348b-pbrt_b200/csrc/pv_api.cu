@@ -2,6 +2,7 @@
 // context lifetime.  No arithmetic of the path lives here.
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include "pv_ctx.h"
 
@@ -66,6 +67,9 @@ void pv_destroy(pv_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -334,18 +338,61 @@ int pv_gather_dev(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_p
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PV_OK;
 }
+// Host-pointer Li: the frame is cut into slices; the host->device copy of slice s+1 and the device->host copy of
+// slice s-1 run on their own streams while slice s is gathered, so only the first upload and the last download are
+// exposed (the result is 240 B per ray, ~0.5 GB for a 1080p frame).  Asynchronous only if the caller's buffers are
+// pinned; with pageable memory CUDA serialises the copies and the result is the same.
 int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
     LOCK(ctx);
     if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_gather: null pointer"; return PV_EINVAL; }
     if (!n) return PV_OK;
-    int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, rays, n * sizeof(pv_ray)); if (rc) return rc;
-    size_t sb = n * PV_NSPEC * sizeof(float);
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * sizeof(pv_ray)); if (rc) return rc;
+    const size_t sb = n * PV_NSPEC * sizeof(float);
     rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 2 * sb); if (rc) return rc;
+    pv_ray *d_rays = (pv_ray *)ctx->io;
     float *d_L = (float *)ctx->io2, *d_T = d_L + n * PV_NSPEC;
-    rc = pvi_gather(ctx, (const pv_ray *)ctx->io, n, params, d_L, d_T); if (rc) return rc;
-    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, d_L, sb, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, d_T, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->copy_in) {
+        PV_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        PV_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    const uint64_t min_slice = 1ull << 18;
+    int nslices = (int)std::max<uint64_t>(1, std::min<uint64_t>(4, n / min_slice));
+    if (const char *e = getenv("PV_GATHER_SLICES")) nslices = std::max(1, std::min(PV_GATHER_MAX_SLICES, atoi(e)));     // tuning knob
+    cudaEvent_t in_done[PV_GATHER_MAX_SLICES], comp_done[PV_GATHER_MAX_SLICES];
+    for (int s = 0; s < nslices; ++s) {
+        PV_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in_done[s], cudaEventDisableTiming));
+        PV_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&comp_done[s], cudaEventDisableTiming));
+    }
+    auto lo = [&](int s) { return n * (uint64_t)s / (uint64_t)nslices; };
+    // the device buffers of an earlier call may still be read by work on ctx->stream
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < nslices; ++s) {
+        const uint64_t a = lo(s), b = lo(s + 1);
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays + a, rays + a, (b - a) * sizeof(pv_ray), cudaMemcpyHostToDevice, ctx->copy_in));
+        PV_CUDA_CHECK(ctx, cudaEventRecord(in_done[s], ctx->copy_in));
+    }
+    float ms = 0.f, march_ms = 0.f;
+    rc = PV_OK;
+    for (int s = 0; s < nslices && rc == PV_OK; ++s) {
+        const uint64_t a = lo(s), b = lo(s + 1);
+        pv_gather_params p = *params; p.ray_index_base = params->ray_index_base + a;
+        PV_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, in_done[s], 0));
+        rc = pvi_gather(ctx, d_rays + a, b - a, &p, d_L + a * PV_NSPEC, d_T + a * PV_NSPEC);
+        if (rc) break;
+        ms += ctx->last_ms; march_ms += ctx->last_march_ms;
+        PV_CUDA_CHECK(ctx, cudaEventRecord(comp_done[s], ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[s], 0));
+        const size_t ob = (b - a) * PV_NSPEC * sizeof(float);
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L + a * PV_NSPEC, d_L + a * PV_NSPEC, ob, cudaMemcpyDeviceToHost, ctx->copy_out));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T + a * PV_NSPEC, d_T + a * PV_NSPEC, ob, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_out);
+    for (int s = 0; s < nslices; ++s) { cudaEventDestroy(in_done[s]); cudaEventDestroy(comp_done[s]); }
+    if (rc) return rc;
+    if (e != cudaSuccess) { ctx->err = std::string("pv_gather: ") + cudaGetErrorString(e); return PV_ECUDA; }
+    ctx->last_ms = ms; ctx->last_march_ms = march_ms;
     return PV_OK;
 }
 int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset) {

@@ -27,6 +27,7 @@ struct GridParams {
 struct pv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // pv_gather overlaps its host copies with the kernels
     std::mutex mu;
     std::string err;
 
@@ -62,6 +63,7 @@ struct pv_ctx {
     // march records of the ray slice being gathered (pv_march.cu): RayHdr per ray, StepRec per march step
     void *march_hdr = nullptr; size_t march_hdr_bytes = 0;
     void *march_steps = nullptr; size_t march_steps_bytes = 0;
+    unsigned long long *h_total = nullptr;         // mapped pinned word: step count of the slice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // around gather_kernel
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels
     float last_ms = 0.f, last_march_ms = 0.f;
@@ -88,6 +90,7 @@ int pvi_sort_pairs_u64(pv_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *ke
 // pv_march.cu
 #define PV_MARCH_MAX_BYTES (16ull << 30)          // step records of one ray slice
 #define PV_GATHER_SLICE_RAYS (4ull << 20)
+#define PV_GATHER_MAX_SLICES 8                     // host-pointer pv_gather: copy/compute pipeline depth
 int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, uint64_t *total_steps);
 // pv_gather.cu
 int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, uint32_t *d_idx, float *d_d2, uint32_t *d_nfound);

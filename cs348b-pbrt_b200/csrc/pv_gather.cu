@@ -34,6 +34,15 @@
 #ifndef GW_ALPHA_NOALLOC
 #define GW_ALPHA_NOALLOC 1
 #endif
+#ifndef GW_PRELOAD
+#define GW_PRELOAD 1                     // alpha lines of the first 16 photons requested before the phase pass
+#endif
+#ifndef GW_PF_WI
+#define GW_PF_WI 0
+#endif
+#ifndef GW_STATS
+#define GW_STATS 1
+#endif
 #ifndef GW_P2_UNROLL
 #define GW_P2_UNROLL 4
 #endif
@@ -46,6 +55,7 @@ struct MapView {
     const uint32_t *orig;          // sorted position -> original photon index (tie-breaks and the k-NN output only)
     GridParams g;
     uint64_t n;
+    int need_wi;                   // the medium's phase function depends on wi (g != 0)
 };
 // per-warp shared memory: candidate list of (d2 bits, photon position) pairs, select histogram, run tables of the
 // current batch, mbarrier, TMA staging buffer
@@ -241,6 +251,13 @@ __device__ __forceinline__ void batch_finish(const MapView &m, WarpBuf &b, const
             const uint32_t na = __popc(ma);
             if (acca) b.ent[count + __popc(ma & lanemask_lt())] = make_uint2(__float_as_uint(da), pa);
             if (accb) b.ent[count + na + __popc(mb & lanemask_lt())] = make_uint2(__float_as_uint(db), pb);
+#if GW_PF_WI
+            // anisotropic phase: the accepted photons' wi will be read by the estimate; pull them towards L1 now
+            if (m.need_wi) {
+                if (acca) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.wi4 + pa));
+                if (accb) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.wi4 + pb));
+            }
+#endif
             count += na + __popc(mb);
             if (count + 64 > b.cap) {                         // list full: keep the k nearest so far
                 __syncwarp();
@@ -405,9 +422,11 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
             if (gr > 0.f && boundk < gr * gr) break;     // strict: an unseen photon cannot even tie
         }
     }
-    if (stats && lane == 0) {
-        uint32_t *st = wb_stats(b);
-        st[ST_LOOKUPS] += 1; st[ST_FOUND] += count; st[ST_CAND] += cand; if (count == k) st[ST_HEAP] += 1;
+    if (GW_STATS && stats && lane == 0) {
+        uint4 *st = reinterpret_cast<uint4 *>(wb_stats(b));           // one 128-bit read-modify-write: {lookups, found, candidates, heap}
+        uint4 v = *st;
+        v.x += 1; v.y += count; v.z += cand; v.w += count == k ? 1u : 0u;
+        *st = v;
     }
     return count;
 }
@@ -436,6 +455,18 @@ __device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium
     const float g = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - g * g), gg1 = 1.f + g * g, g2 = 2.f * g;
     const bool iso = g == 0.f;
     const uint32_t padded = (count + 7u) & ~7u;
+    const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
+#if GW_PRELOAD
+    // The alpha lines of the first 16 photons (count >= 10, so padded >= 16) are requested BEFORE pass 1: their L2
+    // latency overlaps the wi loads and the phase computation instead of following them.
+    float4 q0, q1, q2, q3;
+    {
+        const uint32_t j0 = grp, j1 = grp + 4, j2 = grp + 8, j3 = grp + 12;
+        const uint32_t i0 = b.ent[j0].y, i1 = b.ent[j1].y, i2 = j2 < count ? b.ent[j2].y : 0u, i3 = j3 < count ? b.ent[j3].y : 0u;
+        q0 = ld_alpha(a4 + (size_t)i0 * 8); q1 = ld_alpha(a4 + (size_t)i1 * 8);
+        q2 = ld_alpha(a4 + (size_t)i2 * 8); q3 = ld_alpha(a4 + (size_t)i3 * 8);
+    }
+#endif
     for (uint32_t e = lane; e < padded; e += 32) {
         if (e < count) {
             const uint2 v = b.ent[e];
@@ -455,8 +486,18 @@ __device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium
     // pass 2: 8 lanes x float4 per 128-byte alpha line; sixteen photons (four independent 128-bit loads per lane) per
     // iteration so the L2 latency of the alpha lines overlaps instead of adding up
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
     uint32_t e0 = grp;
+#if GW_PRELOAD
+    {
+        const float p0 = __uint_as_float(b.ent[e0].x), p1 = __uint_as_float(b.ent[e0 + 4].x), p2 = __uint_as_float(b.ent[e0 + 8].x),
+                    p3 = __uint_as_float(b.ent[e0 + 12].x);
+        acc.x = fmaf(q0.x, p0, acc.x); acc.y = fmaf(q0.y, p0, acc.y); acc.z = fmaf(q0.z, p0, acc.z); acc.w = fmaf(q0.w, p0, acc.w);
+        acc2.x = fmaf(q1.x, p1, acc2.x); acc2.y = fmaf(q1.y, p1, acc2.y); acc2.z = fmaf(q1.z, p1, acc2.z); acc2.w = fmaf(q1.w, p1, acc2.w);
+        acc.x = fmaf(q2.x, p2, acc.x); acc.y = fmaf(q2.y, p2, acc.y); acc.z = fmaf(q2.z, p2, acc.z); acc.w = fmaf(q2.w, p2, acc.w);
+        acc2.x = fmaf(q3.x, p3, acc2.x); acc2.y = fmaf(q3.y, p3, acc2.y); acc2.z = fmaf(q3.z, p3, acc2.z); acc2.w = fmaf(q3.w, p3, acc2.w);
+        e0 += 16;
+    }
+#endif
 GW_UNROLL(GW_P2_UNROLL)
     for (; e0 + 12 < padded; e0 += 16) {
         const uint2 v0 = b.ent[e0], v1 = b.ent[e0 + 4], v2 = b.ent[e0 + 8], v3_ = b.ent[e0 + 12];
@@ -743,6 +784,7 @@ static uint32_t lookup_cap(uint32_t k) {
 static MapView map_view(pv_ctx *ctx) {
     MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.orig = ctx->m_orig; m.g = ctx->grid;
     m.n = ctx->n_photons;
+    m.need_wi = ctx->has_scene && ctx->hscene.med.g != 0.f;
     return m;
 }
 template <typename Kern>

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene 
     }
 }
 
+__global__ void publish_total_kernel(const unsigned long long *total, unsigned long long *host_mapped) { *host_mapped = *total; }
+
 struct MarchArgs {
     const DevScene *sc;
     const pv_ray *rays;
@@ -147,9 +149,13 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     const uint32_t blocks = (uint32_t)((n + MS_THREADS - 1) / MS_THREADS);
     march_setup_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(ctx->dscene, d_rays, n, prm->stepsize, (RayHdr *)ctx->march_hdr, d_total);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
-    unsigned long long total = 0;
-    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    // The step count comes back through mapped pinned memory, not a memcpy: a copy would queue on the device->host copy
+    // engine behind the result download of the previous slice (pv_gather overlaps the two).
+    if (!ctx->h_total) PV_CUDA_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_total, sizeof(unsigned long long), cudaHostAllocMapped));
+    publish_total_kernel<<<1, 1, 0, ctx->stream>>>(d_total, ctx->h_total);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long total = *(volatile unsigned long long *)ctx->h_total;
     *total_steps = total;
     size_t free_b = 0, total_b = 0;
     const size_t need = (size_t)total * sizeof(StepRec);

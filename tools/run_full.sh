@@ -1,0 +1,12 @@
+# full default bench + reference arm + smoke + ncu evidence (launch list, full capture of gather_kernel and march_steps_kernel)
+cd /root/repo
+tag=${1:-r01_v2}
+( time python bench.py ) > gpurun_out/${tag}_bench.log 2>&1
+( time python bench.py --impl reference --steps 2 --warmup 1 ) > gpurun_out/${tag}_ref.log 2>&1
+( time python __graft_entry__.py smoke ) > gpurun_out/${tag}_smoke.log 2>&1
+export PV_BENCH_CACHE=/tmp/pvcache
+B="python bench.py --steps 2 --warmup 3 --shoot-photons 100000 --no-cpu-baseline"
+$B > gpurun_out/${tag}_plain.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${tag}_launches.csv $B > gpurun_out/${tag}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k gather_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_gather -f $B > gpurun_out/${tag}_ncu_gather.log 2>&1
+ncu --set full --clock-control none --import-source on -k march_steps_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_march -f $B > gpurun_out/${tag}_ncu_march.log 2>&1
