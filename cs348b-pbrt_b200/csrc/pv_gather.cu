@@ -382,7 +382,10 @@ __device__ __forceinline__ uint32_t warp_lookup(const MapView &m, v3 q, float r2
     const GridParams &g = m.g;
     Prefetch pf;
     if (pfp) pf = *pfp; else { lookup_ranges(m, q, r, k, lane, pf); }
-    if (!pf.in_range) return 0;
+    if (!pf.in_range) {                                  // no photon can be within r: still a lookup for the statistics
+        if (GW_STATS && stats && lane == 0) wb_stats(b)[ST_LOOKUPS] += 1;
+        return 0;
+    }
     if (!pf.issued) lookup_issue(m, b, lane, pf);
     uint32_t count = 0, cand = 0;
     bool have_k = false;

@@ -39,6 +39,73 @@ HOMOG_VOLUME = ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s"
                 '  "point p0" [-1 -1 -1] "point p1" [1 1 1]')
 
 
+# BASELINE config 1: the parameters of the reference's projectScene/volumescene_png.pbrt (rainbow medium, distant light,
+# three matte quads, photonmap surface integrator with final gathering), with the counts / resolution / output as knobs.
+VOLUMESCENE_TEMPLATE = """# BASELINE.json configs[0]: rainbow-volume scene of the reference project
+Film "image" "string filename" "{outfile}" "integer xresolution" [{xres}] "integer yresolution" [{yres}]
+Sampler "lowdiscrepancy" "integer pixelsamples" [{spp}]
+PixelFilter "{filt}"
+SurfaceIntegrator "photonmap" "integer nused" [300] "bool finalgather" ["{finalgather}"] "integer finalgathersamples" [64]
+  "float maxdist" [.15] "integer indirectphotons" [0] "integer causticphotons" [{caustic}]
+VolumeIntegrator "photonvolume" "float stepsize" [.15] "integer nused" [50] "float maxdist" [0.5]
+  "integer volumephotons" [{nphotons}]
+Rotate 0 1 0 0
+Camera "perspective" "float fov" [70]
+WorldBegin
+Translate 0 -0.5 3.5
+Volume "rainbow" "color sigma_a" [.05 .05 .05] "color sigma_s" [.1 .1 .1] "point p0" [-10 0 -5] "point p1" [5 5 5]
+AttributeBegin
+LightSource "distant" "point from" [0 3 0] "point to" [0 2 5] "color L" [150 150 150]
+AttributeEnd
+Material "matte" "color Kd" [.01 .01 .01]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-5 0 -5  5 0 -5  5 0 5  -5 0 5]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-5 0 3  5 0 3  5 10 3  -5 10 3]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [5 0 3  5 0 -3  5 10 -3  5 10 3]
+WorldEnd
+"""
+
+# BASELINE config 4: the parameters of projectScene/pinkfloyd.pbrt (homogeneous medium, narrow spot + point light, a
+# dispersive glass wedge -- 8 triangles -- and a matte wall), wedge mesh written out inline.
+PRISM_TEMPLATE = """# BASELINE.json configs[3]: prism-dispersion scene of the reference project
+Film "image" "integer xresolution" [{xres}] "integer yresolution" [{yres}] "string filename" "{outfile}"
+Sampler "lowdiscrepancy" "integer pixelsamples" [{spp}]
+PixelFilter "{filt}"
+SurfaceIntegrator "photonmap" "integer nused" [50] "bool finalgather" ["false"] "float maxdist" [.15]
+  "integer indirectphotons" [0] "integer causticphotons" [{caustic}]
+VolumeIntegrator "photonvolume" "float stepsize" [.05] "integer nused" [{nused}] "float maxdist" [0.4]
+  "integer volumephotons" [{nphotons}]
+Rotate 5 1 0 0
+Camera "perspective" "float fov" [70]
+WorldBegin
+Translate 0 -0.5 3.5
+Volume "homogeneous" "color sigma_a" [.05 .05 .05] "color sigma_s" [.1 .1 .1] "point p0" [-10 -10 -10] "point p1" [5 5 5]
+AttributeBegin
+LightSource "spot" "point from" [-3 0.72 0] "point to" [0 1.55 0] "color I" [15000 15000 15000] "float coneangle" [0.8]
+LightSource "point" "point from" [0.1 1.35 -4] "color I" [4 4 4]
+AttributeEnd
+AttributeBegin
+Material "glass" "float index" [1.3] "float Vn" [2.75] "color Kr" [0 0 0] "color Kt" [1 1 1]
+Translate 0.1 1.35 0
+Rotate 90 0 1 0
+Scale 0.05 0.7 0.85
+Shape "trianglemesh" "point P" [1 -1 -1  1 -1 1  -1 -1 1  -1 -1 -1  1 1 0  -1 1 0]
+  "integer indices" [0 1 2  0 2 3  1 4 5  1 5 2  0 4 1  2 5 3  4 0 3  4 3 5]
+AttributeEnd
+Material "matte" "color Kd" [.001 .001 .001]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [5 -20 3  5 -20 -3  5 20 -3  5 20 3]
+WorldEnd
+"""
+
+
+def volumescene_pbrt(nphotons=5000, caustic=5000, finalgather=True, xres=300, yres=300, spp=1, filt="gaussian", outfile="volume.pfm"):
+    return VOLUMESCENE_TEMPLATE.format(nphotons=nphotons, caustic=caustic, finalgather="true" if finalgather else "false", xres=xres,
+                                       yres=yres, spp=spp, filt=filt, outfile=outfile)
+
+
+def prism_pbrt(nphotons=5000000, caustic=1, nused=500, xres=512, yres=512, spp=32, filt="gaussian", outfile="pinkfloyd.pfm"):
+    return PRISM_TEMPLATE.format(nphotons=nphotons, caustic=caustic, nused=nused, xres=xres, yres=yres, spp=spp, filt=filt, outfile=outfile)
+
+
 def blob_density(n, seed=348, nblobs=8, floor=0.05):
     """Config-3 density: 8 seeded Gaussian blobs + floor, float32, index z*n*n + y*n + x
     (volumes/volumegrid.h:64).  Evaluated at voxel centres of [-1,1]^3."""

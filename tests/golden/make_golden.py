@@ -35,6 +35,7 @@ def run(scene_file, *ops):
 def query_points(rays, stepsize, n_per_ray, lo=-1.0, hi=1.0):
     """March points of camera rays inside the medium box (like Li's sample points)."""
     pts, ws = [], []
+    lo = np.broadcast_to(np.asarray(lo, np.float64), (3,)); hi = np.broadcast_to(np.asarray(hi, np.float64), (3,))
     for r in rays:
         o, d = r["o"].astype(np.float64), r["d"].astype(np.float64)
         with np.errstate(divide="ignore"):
@@ -48,7 +49,7 @@ def query_points(rays, stepsize, n_per_ray, lo=-1.0, hi=1.0):
     return np.asarray(pts, np.float32), np.asarray(ws, np.float32)
 
 
-def aggregate_test_rays(n, seed, bound=(-1.2, 1.2)):
+def aggregate_test_rays(n, seed, bound=(-1.2, 1.2), target=None):
     """Ray set in the spirit of renderers/aggregatetest.cpp:61-119: random origins, sphere-uniform and
     axis-aligned directions, finite and infinite extents."""
     rng = np.random.default_rng(seed)
@@ -58,6 +59,11 @@ def aggregate_test_rays(n, seed, bound=(-1.2, 1.2)):
     axis = rng.integers(0, 3, size=n); sign = rng.choice([-1.0, 1.0], size=n)
     ax = rng.random(n) < 0.15
     d[ax] = 0; d[ax, axis[ax]] = sign[ax]
+    if target is not None:                                               # small object in a big scene: aim 40% of the rays at it
+        aim = rng.random(n) < 0.4
+        tgt = np.asarray(target[0], np.float32) + rng.uniform(-1, 1, size=(n, 3)).astype(np.float32) * np.asarray(target[1], np.float32)
+        dd = tgt - o; dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+        d[aim] = dd[aim]
     d *= rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)          # non-unit directions too
     rays = sceneio.make_rays(o, d, 0.0, np.inf)
     fin = rng.random(n) < 0.3
@@ -69,8 +75,10 @@ def aggregate_test_rays(n, seed, bound=(-1.2, 1.2)):
     return rays
 
 
-def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays, li_res, knn_k_list):
+def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays, li_res, knn_k_list, camera=None, box=(-1.0, 1.0),
+                     wanted=0, shoot_step=0.05, hit_bound=(-1.2, 1.2), hit_target=None, q_near_photons=False):
     out = {}
+    camera = camera or {}
     scn = os.path.join(HERE, name + ".scn")
     pho = os.path.join(tmp, name + ".pho")
     stats = os.path.join(tmp, name + ".json")
@@ -82,14 +90,17 @@ def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays,
     print("  %s: %d photons from %d paths" % (name, len(pos), st["nshot"]))
 
     # camera rays (+ jittered scatter sample) and query points along them
-    rays = scenes.camera_rays(li_res, li_res)
+    rays = scenes.camera_rays(li_res, li_res, **camera)
     rng = np.random.default_rng(7)
     sel = rng.choice(len(rays), size=n_li_rays, replace=False)
     rays = rays[np.sort(sel)]
     rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
     rays["u_scatter"][:8] = np.float32(0.5)
     out["li_rays"] = rays
-    pts, ws = query_points(rays[::4], stepsize, 6)
+    pts, ws = query_points(rays[::4], stepsize, 6, box[0], box[1])
+    if q_near_photons:          # photons fill a tiny part of the medium (a light beam): put the queries where the photons are
+        pick = rng.choice(len(pos), size=len(pts), replace=False)
+        pts = (pos[pick] + rng.uniform(-0.08, 0.08, size=(len(pts), 3))).astype(np.float32)
     out["q_pts"], out["q_w"] = pts, ws
 
     rf = os.path.join(tmp, "rays.bin"); qf = os.path.join(tmp, "q.bin")
@@ -112,10 +123,10 @@ def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays,
     n = len(rays)
     tr = np.frombuffer(buf, np.float32, count=n * 31, offset=16).reshape(n, 31)
     out["tr_u"], out["tr_T"] = tr[:, 0].copy(), tr[:, 1:].copy()
-    out["params"] = np.array([nused, maxdist, stepsize], np.float64)
+    out["params"] = np.array([nused, maxdist, stepsize, wanted, shoot_step], np.float64)
 
     # BVH hit ids
-    arays = aggregate_test_rays(3000, 11)
+    arays = aggregate_test_rays(3000, 11, hit_bound, hit_target)
     af = os.path.join(tmp, "arays.bin"); sceneio.write_rays(af, arays)
     run(scene_file, "--intersect", af, os.path.join(tmp, "hits.bin"))
     prim, t, occ = sceneio.read_hits(os.path.join(tmp, "hits.bin"))
@@ -152,7 +163,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         homog = os.path.join(tmp, "cornell_homog.pbrt")
         open(homog, "w").write(scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 6000))
-        golden_for_scene(tmp, "cornell_homog", homog, 50, 0.25, 0.05, 96, 64, [(50, 0.25 ** 2), (16, 0.1 ** 2)])
+        golden_for_scene(tmp, "cornell_homog", homog, 50, 0.25, 0.05, 96, 64, [(50, 0.25 ** 2), (16, 0.1 ** 2)], wanted=6000)
         golden_synthetic_knn(tmp, homog)
 
         n = 32
@@ -160,10 +171,51 @@ def main():
         grid = os.path.join(tmp, "cornell_grid.pbrt")
         open(grid, "w").write(scenes.cornell_pbrt(scenes.grid_volume_text(n, dens), 2500, stepsize=0.0625, nused=50,
                                                   maxdist=0.25, shoot_step=0.05))
-        golden_for_scene(tmp, "cornell_grid32", grid, 50, 0.25, 0.0625, 64, 64, [(50, 0.25 ** 2)])
+        golden_for_scene(tmp, "cornell_grid32", grid, 50, 0.25, 0.0625, 64, 64, [(50, 0.25 ** 2)], wanted=2500)
         g = sceneio.read_scene(os.path.join(HERE, "cornell_grid32.scn"))
         assert np.array_equal(g.density, dens), "density grid did not survive the text round trip"
+        project_goldens(tmp)
+
+
+def project_goldens(tmp):
+    """BASELINE configs 1 and 4 (the reference project's own scenes, parameters in scenes.py).
+    Kernel-level goldens use the scenes with final gathering off and no caustic map, so that the reference's single MT19937
+    stream is consumed by the volume path alone and the oracle can replay it; the end-to-end images use the shipped settings
+    (config 1) / reduced counts (config 4) and are rendered by the unmodified reference binary."""
+    # config 1: rainbow medium [-10,0,-5]-[5,5,5] under Translate(0,-.5,3.5), distant light, camera at the origin looking +z
+    vol = os.path.join(tmp, "rainbow_vol.pbrt")
+    open(vol, "w").write(scenes.volumescene_pbrt(nphotons=3000, caustic=0, finalgather=False, xres=64, yres=64))
+    golden_for_scene(tmp, "rainbow_vol", vol, 50, 0.5, 0.15, 64, 48, [(50, 0.5 ** 2)], camera=dict(fov_deg=70.0, eye=(0, 0, 0), look=(0, 0, 1)),
+                     box=((-10, -0.5, -1.5), (5, 4.5, 8.5)), wanted=3000, shoot_step=0.1, hit_bound=(-6.0, 9.0))
+    # config 4 (reduced): glass wedge with dispersion (Vn 2.75), spot + point light, homogeneous medium
+    prism = os.path.join(tmp, "prism_small.pbrt")
+    open(prism, "w").write(scenes.prism_pbrt(nphotons=4000, caustic=0, nused=100, xres=64, yres=64, spp=1))
+    golden_for_scene(tmp, "prism_small", prism, 100, 0.4, 0.05, 48, 48, [(100, 0.4 ** 2)],
+                     camera=dict(fov_deg=70.0, eye=(0, 0, 0), look=(0, 0.0872, 0.9962)), box=((-10, -10.5, -6.5), (5, 4.5, 8.5)),
+                     wanted=4000, shoot_step=0.1, hit_bound=(-6.0, 9.0), hit_target=((0.1, 0.85, 3.5), (0.9, 0.8, 0.1)), q_near_photons=True)
+    # end-to-end reference images
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "pbrt_ref")
+    for name, text in (("config1_volumescene", scenes.volumescene_pbrt(outfile="config1_volumescene.pfm", xres=150, yres=150)),
+                       ("config4_prism", scenes.prism_pbrt(nphotons=20000, nused=200, xres=96, yres=96, spp=8, outfile="config4_prism.pfm"))):
+        f = os.path.join(tmp, name + ".pbrt"); open(f, "w").write(text)
+        open(os.path.join(ROOT, "tests", "scenes", name + ".pbrt"), "w").write(text)
+        subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)
+        np.save(os.path.join(HERE, name + "_ref.npy"), read_pfm(os.path.join(tmp, name + ".pfm")).astype(np.float16))
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        kind = f.readline().strip()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        data = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, 3 if kind == b"PF" else 1)
+    return data[::-1].copy()
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "project":          # only the config-1 / config-4 goldens
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            project_goldens(tmp_)
+    else:
+        main()

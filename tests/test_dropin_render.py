@@ -24,6 +24,39 @@ def read_pfm(path):
     return data[::-1].copy()
 
 
+def luminance(a):
+    return 0.2126 * a[..., 0] + 0.7152 * a[..., 1] + 0.0722 * a[..., 2]
+
+
+def block_mean(a, b):
+    h, w = a.shape[0] // b * b, a.shape[1] // b * b
+    return a[:h, :w].reshape(h // b, b, w // b, b).mean(axis=(1, 3))
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
+@pytest.mark.parametrize("name,tol_mean,tol_mre", [("config1_volumescene", 0.03, 0.10), ("config4_prism", 0.05, 0.15)])
+def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name, tol_mean, tol_mre):
+    """BASELINE configs[0] (rainbow-volume scene with the shipped settings, 150x150) and configs[3] (glass-prism dispersion
+    scene, reduced to 20k photons / 96x96 / 8 spp) rendered by the drop-in and compared with the unmodified reference's
+    render of the same file (tests/golden/<name>_ref.npy, float16).  Random streams differ (MT19937 vs keyed Philox; the
+    surface photon maps still come from the reference's CPU pass), so the tolerance is statistical: mean luminance within
+    tol_mean, mean relative error of 6x6-pixel block means over lit blocks within tol_mre."""
+    scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
+    out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[pv] shot" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
+    img = read_pfm(os.path.join(tmp_path, name + ".pfm"))
+    ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_ref.npy")).astype(np.float32)
+    assert img.shape == ref.shape
+    li, lr = luminance(img), luminance(ref)
+    assert np.isfinite(li).all()
+    assert abs(li.mean() - lr.mean()) / lr.mean() < tol_mean, (li.mean(), lr.mean())
+    bi, br = block_mean(li, 6), block_mean(lr, 6)
+    lit = br > 0.05 * br.mean()
+    mre = (np.abs(bi - br)[lit] / br[lit]).mean()
+    assert mre < tol_mre, mre
+
+
 @pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
 def test_dropin_renders_the_config2_scene_like_the_reference(tmp_path):
     scene = os.path.join(ROOT, "tests", "scenes", "cornell_e2e.pbrt")

@@ -9,6 +9,8 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 RTOL_RADIANCE = 1e-4
+# rainbow_vol / prism_small = BASELINE configs 1 and 4 (the reference project's own scenes, reduced counts; tests/golden/make_golden.py)
+ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small"]
 
 
 def relerr(a, b, floor=1e-30):
@@ -37,14 +39,14 @@ def test_library_is_the_cuda_one(pkg):
     pv.close()
 
 
-@pytest.mark.parametrize("name", ["cornell_homog", "cornell_grid32"])
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_knn_bit_exact_vs_reference(golden, pv_factory, name):
     g, scene = golden(name)
-    pv = pv_factory(nused=50, maxdist=0.25)
+    pv = pv_factory(nused=int(g["params"][0]), maxdist=float(g["params"][1]))
     pv.set_scene(scene)
     pv.set_photons(g["shot_pos"], g["shot_wi"], g["shot_alpha"])
     pv.build()
-    for k in (50, 16):
+    for k in (50, 16, 100):
         if "knn%d_idx" % k not in g:
             continue
         nf, idx, d2 = pv.Lookup(g["q_pts"], k=k, r2=float(g["knn%d_r2" % k][0]))
@@ -115,7 +117,7 @@ def test_lookup_before_build_fails_loudly(pkg, pv_factory):
     assert "not built" in str(e.value)
 
 
-@pytest.mark.parametrize("name", ["cornell_homog", "cornell_grid32"])
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_bvh_hits_bit_exact_vs_reference(golden, pv_factory, name):
     g, scene = golden(name)
     pv = pv_factory()
@@ -127,7 +129,7 @@ def test_bvh_hits_bit_exact_vs_reference(golden, pv_factory, name):
     assert np.array_equal(occ.astype(np.uint32), g["hit_occluded"])
 
 
-@pytest.mark.parametrize("name", ["cornell_homog", "cornell_grid32"])
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_transmittance_vs_reference(golden, pv_factory, name):
     g, scene = golden(name)
     pv = pv_factory(stepsize=float(g["params"][2]))
@@ -136,7 +138,7 @@ def test_transmittance_vs_reference(golden, pv_factory, name):
     assert relerr(T, g["tr_T"]).max() < 1e-5                # libm expf differs in the last ulps
 
 
-@pytest.mark.parametrize("name", ["cornell_homog", "cornell_grid32"])
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_lphoton_vs_reference(golden, pv_factory, name):
     g, scene = golden(name)
     pv = pv_factory(nused=int(g["params"][0]), maxdist=float(g["params"][1]))
@@ -149,10 +151,11 @@ def test_lphoton_vs_reference(golden, pv_factory, name):
     assert relerr(L, ref)[ref > 0].max() < RTOL_RADIANCE
 
 
-def test_li_homogeneous_vs_reference(golden, pv_factory):
-    """Homogeneous medium + one delta light: Li does not depend on any random draw, so the CUDA result is
+@pytest.mark.parametrize("name", ["cornell_homog", "rainbow_vol"])
+def test_li_homogeneous_vs_reference(golden, pv_factory, name):
+    """Homogeneous (or rainbow) medium + one delta light: Li does not depend on any random draw, so the CUDA result is
     compared directly with what the reference binary returned."""
-    g, scene = golden("cornell_homog")
+    g, scene = golden(name)
     pv = pv_factory(stepsize=float(g["params"][2]), nused=int(g["params"][0]), maxdist=float(g["params"][1]))
     pv.set_scene(scene)
     pv.set_photons(g["shot_pos"], g["shot_wi"], g["shot_alpha"])
@@ -165,7 +168,8 @@ def test_li_homogeneous_vs_reference(golden, pv_factory):
     assert np.array_equal(L == 0, g["li_L"] == 0)
 
 
-@pytest.mark.parametrize("name,flags", [("cornell_homog", 0), ("cornell_grid32", 0), ("cornell_grid32", 1), ("cornell_grid32", 2)])
+@pytest.mark.parametrize("name,flags", [("cornell_homog", 0), ("cornell_grid32", 0), ("cornell_grid32", 1), ("cornell_grid32", 2),
+                                        ("rainbow_vol", 0), ("prism_small", 0)])
 def test_li_vs_oracle_same_philox_stream(golden, pv_factory, name, flags):
     g, scene = golden(name)
     stepsize, nused, maxdist = float(g["params"][2]), int(g["params"][0]), float(g["params"][1])
@@ -206,16 +210,18 @@ def pkg_rays(o, d):
     return load_package().sceneio.make_rays(o, d)
 
 
-@pytest.mark.parametrize("name,wanted", [("cornell_homog", 3000), ("cornell_grid32", 1200)])
-def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted):
-    """Same per-path Philox streams on both sides: photons are matched one to one by (path, deposit ordinal)."""
+@pytest.mark.parametrize("name,wanted,sstep", [("cornell_homog", 3000, 0.05), ("cornell_grid32", 1200, 0.05), ("rainbow_vol", 1500, 0.1),
+                                               ("prism_small", 4000, 0.1)])
+def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, sstep):
+    """Same per-path Philox streams on both sides: photons are matched one to one by (path, deposit ordinal).
+    prism_small: every path goes through the dispersive glass wedge (splitSpectrum into 30 monochromatic photons, Cauchy refraction)."""
     g, scene = golden(name)
     istep = float(g["params"][2])
     pv = pv_factory(stepsize=istep, seed=77)
     pv.set_scene(scene)
-    st = pv.Preprocess(wanted, stepsize=0.05, max_photon_depth=5, build=False)
+    st = pv.Preprocess(wanted, stepsize=sstep, max_photon_depth=5, build=False)
     pos, wi, alpha, ids = pv.get_photons()
-    ref = O.shoot(scene, wanted, 0.05, istep, seed=77, rng_mode=O.PHILOX, nthreads=8)
+    ref = O.shoot(scene, wanted, sstep, istep, seed=77, rng_mode=O.PHILOX, nthreads=8)
     assert ref["rc"] == 0
     assert st.paths == ref["nshot"]
     assert st.stack_overflows == 0

@@ -4,7 +4,9 @@ import numpy as np
 import pytest
 import oracle_lib as O
 
-SCENES = ["cornell_homog", "cornell_grid32"]
+SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small"]
+# rainbow_vol / prism_small: BASELINE configs 1 and 4 (the reference project's rainbow-volume and glass-prism scenes, reduced counts)
+WANTED = {"cornell_homog": (6000, 0.05), "cornell_grid32": (2500, 0.05), "rainbow_vol": (3000, 0.1), "prism_small": (4000, 0.1)}
 
 
 def relerr(a, b):
@@ -34,7 +36,7 @@ def test_philox_known_answer():
 def test_knn_index_sets_match_reference(golden, name):
     g, _ = golden(name)
     tree = O.KdTree(g["shot_pos"])
-    for k in (50, 16):
+    for k in (50, 16, 100):
         if "knn%d_idx" % k not in g:
             continue
         nf, idx, d2, ties = tree.knn(g["q_pts"], k, float(g["knn%d_r2" % k][0]))
@@ -102,7 +104,8 @@ def test_li_matches_reference_with_mt_stream(golden, name):
     assert relerr(T, refT).max() < 1e-6
     m = refL > 0
     assert relerr(L, refL)[m].max() < 1e-5
-    assert st.lookups > 0
+    # rainbow media skip the photon gather (integrators/photonvolume.cpp:205-207)
+    assert (st.lookups == 0) if name == "rainbow_vol" else (st.lookups > 0)
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -110,9 +113,9 @@ def test_shooter_reproduces_reference_photons(golden, name):
     """followPhoton/Run restated: with the reference's MT stream (--ncores 1) the photon list is identical."""
     g, scene = golden(name)
     n = len(g["shot_pos"])
-    wanted = 6000 if name == "cornell_homog" else 2500
+    wanted, shoot_step = WANTED[name]
     stepsize = float(g["params"][2])
-    res = O.shoot(scene, wanted, 0.05, stepsize, rng_mode=O.MT)
+    res = O.shoot(scene, wanted, shoot_step, stepsize, rng_mode=O.MT)
     assert res["rc"] == 0
     assert res["nshot"] == int(g["nshot"][0])
     assert res["n"] == n
