@@ -43,6 +43,9 @@
 #ifndef GW_STATS
 #define GW_STATS 1
 #endif
+#ifndef GW_LIGHT_REG
+#define GW_LIGHT_REG 1
+#endif
 #ifndef GW_P2_UNROLL
 #define GW_P2_UNROLL 4
 #endif
@@ -688,7 +691,11 @@ __device__ __forceinline__ v3 light_wo(const pv_light &l, v3 p) {
     return vnorm(V3(l.pos[0], l.pos[1], l.pos[2]) - p);
 }
 
+#ifdef GW_MAXNREG
+__global__ void __maxnreg__(GW_MAXNREG) gather_kernel(GatherArgs a) {
+#else
 __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherArgs a) {
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpBuf b = carve(smem, a.cap, warp, lane);
@@ -704,6 +711,8 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
     const float r2 = a.maxdist * a.maxdist;
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
     const bool do_lookup = !rainbow && !(a.flags & PV_GATHER_NO_INDIRECT);
+    const bool one_light = GW_LIGHT_REG && sc.n_lights == 1;                              // the common case keeps the light's spectrum in a register
+    const float I_light0 = (bin && sc.n_lights > 0) ? sc.lights[0].intensity[lane] : 0.f;
     uint32_t nrays = 0;
     for (;;) {
         unsigned long long ri = 0;
@@ -750,8 +759,8 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
                     float L_d = 0.f, L_ii = 0.f;
                     const float s_dfac = __shfl_sync(PV_FULL, c_dfac, i);
                     if (s_dfac != 0.f) {
-                        const pv_light &lt = sc.lights[__shfl_sync(PV_FULL, c_ln, i)];
-                        const float I = bin ? lt.intensity[lane] : 0.f;
+                        const pv_light &lt = sc.lights[one_light ? 0 : __shfl_sync(PV_FULL, c_ln, i)];
+                        const float I = one_light ? I_light0 : (bin ? lt.intensity[lane] : 0.f);
                         const float Ld = (I * expf(-(sig_t * __shfl_sync(PV_FULL, c_sh, i)))) * s_dfac;
                         L_d = rainbow ? rainbow_bin(Ld, rd, light_wo(lt, sp), lane) : Ld;
                     }
