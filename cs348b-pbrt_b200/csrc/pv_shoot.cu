@@ -110,7 +110,10 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
     return __fdiv_rn(Rparl * Rparl + Rperp * Rperp, 2.f);
 }
 
-__global__ void __launch_bounds__(SH_THREADS) shoot_kernel(ShootArgs a) {
+#ifndef SH_MIN_CTAS
+#define SH_MIN_CTAS 4                // 16 warps/SM at 128 registers: the spills cost less than the occupancy gains
+#endif
+__global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
     __shared__ uint32_t s_perm[41];
     __shared__ float s_minmax[3];
