@@ -309,16 +309,17 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
         maxd = std::max(maxd, g.dims[a]);
     }
     g.yzbits = ceil_log2(std::max(g.dims[1], g.dims[2]));
-    // finer cells along x (up to two halvings) while the key stays within 24 bits and cells are not much
+    // finer cells along x (up to two halvings) while the key stays within 24 (26) bits and cells are not much
     // more numerous than photons
     g.xshift = 0;
     {
         const int coarse = g.dims[0];
+        const int max_key_bits = n >= (1ull << 25) ? 26 : 24;      // cell table <= 64 MiB, 256 MiB for very large maps
         int xs_max = 2;
         if (const char *e = getenv("PV_XSHIFT_MAX")) xs_max = std::max(0, std::min(4, atoi(e)));      // tuning knob
         for (int xs = 1; xs <= xs_max; ++xs) {
             const int fine = coarse << xs;
-            if (ceil_log2(fine) + 2 * g.yzbits > 24) break;
+            if (ceil_log2(fine) + 2 * g.yzbits > max_key_bits) break;
             if ((double)fine * g.dims[1] * g.dims[2] > 8.0 * (double)n) break;
             g.xshift = xs;
         }

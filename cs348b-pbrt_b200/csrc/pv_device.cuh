@@ -42,6 +42,27 @@ struct DevScene {
     float light_func[PV_MAX_LIGHTS], light_cdf[PV_MAX_LIGHTS + 1], light_func_int;
 };
 
+// The geometric part of a DevMedium copied into registers at kernel start.  The scene lives in global memory behind a
+// pointer the compiler must assume the kernel's own stores may alias, so every density tap would otherwise re-load the
+// extent, the grid dimensions and the grid pointer.  Same field names as DevMedium: the medium functions below are
+// templates over either.
+struct MedView {
+    int type, identity, nx, ny, nz;
+    float g;
+    float p0[3], p1[3];
+    const float *density;
+    float w2v[16];
+};
+__device__ __forceinline__ MedView make_medview(const DevMedium &m) {
+    MedView v;
+    v.type = m.type; v.identity = m.identity; v.nx = m.nx; v.ny = m.ny; v.nz = m.nz; v.g = m.g; v.density = m.density;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { v.p0[i] = m.p0[i]; v.p1[i] = m.p1[i]; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v.w2v[i] = m.w2v[i];
+    return v;
+}
+
 struct v3 { float x, y, z; };
 __device__ __forceinline__ v3 V3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ v3 operator+(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -78,8 +99,10 @@ __device__ __forceinline__ v3 xf_vec(const float *m, v3 v) {            // core/
     float x = v.x, y = v.y, z = v.z;
     return V3(m[0] * x + m[1] * y + m[2] * z, m[4] * x + m[5] * y + m[6] * z, m[8] * x + m[9] * y + m[10] * z);
 }
-__device__ __forceinline__ v3 med_to_volume_p(const DevMedium &m, v3 p) { return m.identity ? p : xf_point(m.w2v, p); }
-__device__ __forceinline__ v3 med_to_volume_v(const DevMedium &m, v3 v) { return m.identity ? v : xf_vec(m.w2v, v); }
+template <class Med>
+__device__ __forceinline__ v3 med_to_volume_p(const Med &m, v3 p) { return m.identity ? p : xf_point(m.w2v, p); }
+template <class Med>
+__device__ __forceinline__ v3 med_to_volume_v(const Med &m, v3 v) { return m.identity ? v : xf_vec(m.w2v, v); }
 
 // core/geometry.cpp:68-86
 __device__ __forceinline__ bool bbox_intersectp(const float *p0, const float *p1, v3 o, v3 d, float mint, float maxt,
@@ -102,17 +125,21 @@ __device__ __forceinline__ bool bbox_inside(const float *p0, const float *p1, v3
     return p.x >= p0[0] && p.x <= p1[0] && p.y >= p0[1] && p.y <= p1[1] && p.z >= p0[2] && p.z <= p1[2];
 }
 
-__device__ __forceinline__ bool med_is_homog(const DevMedium &m) { return m.type == PV_MEDIUM_HOMOGENEOUS || m.type == PV_MEDIUM_RAINBOW; }
-__device__ __forceinline__ bool med_intersectp(const DevMedium &m, v3 o, v3 d, float mint, float maxt, float *t0, float *t1) {
+template <class Med>
+__device__ __forceinline__ bool med_is_homog(const Med &m) { return m.type == PV_MEDIUM_HOMOGENEOUS || m.type == PV_MEDIUM_RAINBOW; }
+template <class Med>
+__device__ __forceinline__ bool med_intersectp(const Med &m, v3 o, v3 d, float mint, float maxt, float *t0, float *t1) {
     return bbox_intersectp(m.p0, m.p1, med_to_volume_p(m, o), med_to_volume_v(m, d), mint, maxt, t0, t1);
 }
 __device__ __forceinline__ float lerpf(float t, float a, float b) { return (1.f - t) * a + t * b; }   // core/pbrt.h:218
-__device__ __forceinline__ float grid_D(const DevMedium &m, int x, int y, int z) {                    // volumes/volumegrid.h:60-65
+template <class Med>
+__device__ __forceinline__ float grid_D(const Med &m, int x, int y, int z) {                    // volumes/volumegrid.h:60-65
     x = min(max(x, 0), m.nx - 1); y = min(max(y, 0), m.ny - 1); z = min(max(z, 0), m.nz - 1);
     return __ldg(m.density + ((size_t)z * m.nx * m.ny + (size_t)y * m.nx + x));
 }
 // volumes/volumegrid.cpp:39-57
-__device__ __forceinline__ float grid_density(const DevMedium &m, v3 Pobj) {
+template <class Med>
+__device__ __forceinline__ float grid_density(const Med &m, v3 Pobj) {
     if (!bbox_inside(m.p0, m.p1, Pobj)) return 0.f;
     float vx_ = __fdiv_rn(Pobj.x - m.p0[0], m.p1[0] - m.p0[0]);
     float vy_ = __fdiv_rn(Pobj.y - m.p0[1], m.p1[1] - m.p0[1]);
@@ -130,7 +157,8 @@ __device__ __forceinline__ float grid_density(const DevMedium &m, v3 Pobj) {
 }
 // scalar "density" multiplying the constant spectra: 1/0 inside/outside for homogeneous media
 // (volumes/homogeneous.h:62-70), the trilinear density for grids (core/volume.h:80-88)
-__device__ __forceinline__ float med_density(const DevMedium &m, v3 p, uint32_t *nsamples) {
+template <class Med>
+__device__ __forceinline__ float med_density(const Med &m, v3 p, uint32_t *nsamples) {
     v3 po = med_to_volume_p(m, p);
     if (med_is_homog(m)) return bbox_inside(m.p0, m.p1, po) ? 1.f : 0.f;
     if (nsamples) (*nsamples)++;
@@ -142,7 +170,8 @@ __device__ __forceinline__ float phase_hg(v3 w, v3 wp, float g) {
     float x = 1.f + g * g - 2.f * g * costheta;
     return __fdiv_rn(1.f / (4.f * PV_PI_F) * (1.f - g * g), x * __fsqrt_rn(x));
 }
-__device__ __forceinline__ float med_phase(const DevMedium &m, v3 p, v3 w, v3 wp) {     // homogeneous.h:74-77, volume.h:92-94
+template <class Med>
+__device__ __forceinline__ float med_phase(const Med &m, v3 p, v3 w, v3 wp) {     // homogeneous.h:74-77, volume.h:92-94
     if (med_is_homog(m) && !bbox_inside(m.p0, m.p1, med_to_volume_p(m, p))) return 0.f;
     return phase_hg(w, wp, m.g);
 }
@@ -150,7 +179,8 @@ __device__ __forceinline__ float med_phase(const DevMedium &m, v3 p, v3 w, v3 wp
 // homogeneous.h:78-82: s = Distance(ray(t0), ray(t1)); core/volume.cpp:296-310: s = (sum of densities) * stepSize.
 // (The reference accumulates sigma_t*density per bin before multiplying by stepSize; factoring the constant
 // spectrum out changes rounding by O(1e-7) relative -- inside the 1e-4 per-ray tolerance, see DESIGN.md.)
-__device__ __forceinline__ float med_tau_scalar(const DevMedium &m, v3 o, v3 d, float mint, float maxt, float stepSize,
+template <class Med>
+__device__ __forceinline__ float med_tau_scalar(const Med &m, v3 o, v3 d, float mint, float maxt, float stepSize,
                                                 float u, uint32_t *nsamples) {
     float t0, t1;
     if (med_is_homog(m)) {

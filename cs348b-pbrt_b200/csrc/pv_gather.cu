@@ -44,7 +44,7 @@
 #define GW_STATS 1
 #endif
 #ifndef GW_LIGHT_REG
-#define GW_LIGHT_REG 1
+#define GW_LIGHT_REG 0                  // measured: the extra live register costs more than the per-step load it saves
 #endif
 #ifndef GW_P2_UNROLL
 #define GW_P2_UNROLL 4

@@ -72,10 +72,11 @@ struct MarchArgs {
 // eight trilinear taps touch a handful of 32-byte sectors instead of 256.
 __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(MarchArgs a) {
     const DevScene &sc = *a.sc;
-    const DevMedium &med = sc.med;
+    const DevMedium &gmed = sc.med;
+    const MedView med = make_medview(gmed);             // extent / grid dimensions / grid pointer in registers
     const uint32_t lane = threadIdx.x & 31;
     float sig_t_max = 0.f; bool any_sig_s = false;
-    for (int bb = 0; bb < PV_NSPEC; ++bb) { sig_t_max = fmaxf(sig_t_max, med.sigma_a[bb] + med.sigma_s[bb]); any_sig_s |= med.sigma_s[bb] != 0.f; }
+    for (int bb = 0; bb < PV_NSPEC; ++bb) { sig_t_max = fmaxf(sig_t_max, gmed.sigma_a[bb] + gmed.sigma_s[bb]); any_sig_s |= gmed.sigma_s[bb] != 0.f; }
     const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
     const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
     const int nLights = (int)sc.n_lights;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
             // Tr.y() < 1e-3 ?  exp(-sig_t_max * tau) bounds every bin from below and y(1) ~ 1, so only large taus need the sum
             if (sig_t_max * c_tau > 6.0f) {
                 float yy = 0.f;
-                for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((med.sigma_a[bb] + med.sigma_s[bb]) * c_tau));
+                for (int bb = 0; bb < PV_NSPEC; ++bb) yy += sc.cie_y[bb] * expf(-((gmed.sigma_a[bb] + gmed.sigma_s[bb]) * c_tau));
                 if (__fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f) c_rr = pv_u32_to_float(sw[1]);
             }
             c_dens = med_density(med, p, &ns);

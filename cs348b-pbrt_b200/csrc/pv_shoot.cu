@@ -118,10 +118,11 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
     __shared__ uint32_t s_perm[41];
     __shared__ float s_minmax[3];
     const DevScene &sc = *a.sc;
-    const DevMedium &med = sc.med;
+    const DevMedium &gmed = sc.med;
+    const MedView med = make_medview(gmed);             // extent / grid dimensions / grid pointer in registers
     if (threadIdx.x < PV_NSPEC) {
-        s_cie[threadIdx.x] = sc.cie_y[threadIdx.x]; s_sa[threadIdx.x] = med.sigma_a[threadIdx.x];
-        s_ss[threadIdx.x] = med.sigma_s[threadIdx.x]; s_st[threadIdx.x] = med.sigma_a[threadIdx.x] + med.sigma_s[threadIdx.x];
+        s_cie[threadIdx.x] = sc.cie_y[threadIdx.x]; s_sa[threadIdx.x] = gmed.sigma_a[threadIdx.x];
+        s_ss[threadIdx.x] = gmed.sigma_s[threadIdx.x]; s_st[threadIdx.x] = gmed.sigma_a[threadIdx.x] + gmed.sigma_s[threadIdx.x];
     }
     if (threadIdx.x < 41) s_perm[threadIdx.x] = a.perm[threadIdx.x];
     __syncthreads();
