@@ -45,13 +45,29 @@ struct ShootArgs {
     unsigned long long *work, *stats;     // stats: nodes, tris, density samples, segments, overflows, paths
 };
 
+__device__ __noinline__ uint4 path_philox_block(uint32_t c0, uint32_t c1, uint32_t j, uint32_t k0, uint32_t k1) {
+    uint32_t out[4];
+    pv_philox4x32_10(c0, c1, j, PV_RNG_PATH, k0, k1, out);
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+#ifndef SH_TAU_MED
+#define SH_TAU_MED const MedView
+#endif
+// One copy of DensityRegion::tau for the shooter's two call sites (free-flight march, surface transmittance)
+__device__ __noinline__ float shoot_tau(SH_TAU_MED m, float ox, float oy, float oz, float dx, float dy, float dz, float mint, float maxt,
+                                        float stepSize, float u, uint32_t *nsamples) {
+    return med_tau_scalar(m, V3(ox, oy, oz), V3(dx, dy, dz), mint, maxt, stepSize, u, nsamples);
+}
 struct PathRng {
     uint32_t c0, c1, j, pos, k0, k1, buf[4];
     __device__ __forceinline__ void reset(uint64_t path, uint32_t key0, uint32_t key1) {
         c0 = (uint32_t)path; c1 = (uint32_t)(path >> 32); j = 0; pos = 4; k0 = key0; k1 = key1;
     }
     __device__ __forceinline__ float next() {
-        if (pos == 4) { pv_philox4x32_10(c0, c1, j++, PV_RNG_PATH, k0, k1, buf); pos = 0; }
+        if (pos == 4) {                  // one out-of-line Philox block per four draws: ~25 call sites would otherwise inline 10 rounds each
+            const uint4 r = path_philox_block(c0, c1, j++, k0, k1);
+            buf[0] = r.x; buf[1] = r.y; buf[2] = r.z; buf[3] = r.w; pos = 0;
+        }
         uint32_t v = pos == 0 ? buf[0] : (pos == 1 ? buf[1] : (pos == 2 ? buf[2] : buf[3]));
         pos++;
         return pv_u32_to_float(v);
@@ -61,14 +77,16 @@ struct PathRng {
 __device__ __forceinline__ v3 uniform_sample_sphere(float u1, float u2) {       // core/montecarlo.cpp:283-290
     float z = 1.f - 2.f * u1;
     float r = __fsqrt_rn(fmaxf(0.f, 1.f - z * z));
-    float phi = 2.f * PV_PI_F * u2;
-    return V3(r * cosf(phi), r * sinf(phi), z);
+    float phi = 2.f * PV_PI_F * u2, sp, cp;
+    sincosf(phi, &sp, &cp);                       // one argument reduction for both
+    return V3(r * cp, r * sp, z);
 }
 __device__ __forceinline__ v3 uniform_sample_cone(float u1, float u2, float costhetamax) {   // :405-410
     float costheta = (1.f - u1) + u1 * costhetamax;
     float sintheta = __fsqrt_rn(1.f - costheta * costheta);
-    float phi = u2 * 2.f * PV_PI_F;
-    return V3(cosf(phi) * sintheta, sinf(phi) * sintheta, costheta);
+    float phi = u2 * 2.f * PV_PI_F, sp, cp;
+    sincosf(phi, &sp, &cp);
+    return V3(cp * sintheta, sp * sintheta, costheta);
 }
 __device__ __forceinline__ void concentric_sample_disk(float u1, float u2, float *dx, float *dy) {   // :306-348
     float r, theta;
@@ -82,8 +100,10 @@ __device__ __forceinline__ void concentric_sample_disk(float u1, float u2, float
         else { r = -sy; theta = 6.0f + __fdiv_rn(sx, r); }
     }
     theta *= PV_PI_F / 4.f;
-    *dx = r * cosf(theta);
-    *dy = r * sinf(theta);
+    float st, ct;
+    sincosf(theta, &st, &ct);
+    *dx = r * ct;
+    *dy = r * st;
 }
 __device__ __forceinline__ void coordinate_system(v3 v1, v3 *v2, v3 *v3o) {      // core/geometry.h:508-518
     if (fabsf(v1.x) > fabsf(v1.y)) {
@@ -110,6 +130,15 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
     return __fdiv_rn(Rparl * Rparl + Rperp * Rperp, 2.f);
 }
 
+// The 30-bin spectrum loops stay ROLLED: unrolled (with an IEEE division or an expf per bin) they made the kernel 12 k
+// instructions (197 KB) and the instruction cache missed on a third of the fetches; rolled, alpha[] is indexed dynamically
+// and lives in local memory, which the free-flight march -- where the time goes -- never touches.
+#ifndef SH_BIN_UNROLL
+#define SH_BIN_UNROLL 1
+#endif
+#define SH_STR(x) #x
+#define SH_PRAGMA_UNROLL(n) _Pragma(SH_STR(unroll n))
+#define SH_UNROLL_BINS SH_PRAGMA_UNROLL(SH_BIN_UNROLL)
 #ifndef SH_MIN_CTAS
 #define SH_MIN_CTAS 4                // 16 warps/SM at 128 registers: the spills cost less than the occupancy gains
 #endif
@@ -128,6 +157,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
     __syncthreads();
     if (threadIdx.x == 0) {
         float mn = INFINITY, mx = 0.f, y1 = 0.f;
+SH_UNROLL_BINS
         for (int b = 0; b < PV_NSPEC; ++b) { mn = fminf(mn, s_st[b]); mx = fmaxf(mx, s_st[b]); y1 += s_cie[b]; }
         s_minmax[0] = mn; s_minmax[1] = mx; s_minmax[2] = __fdiv_rn(y1 * 300.f, 106.856895f * (float)PV_NSPEC);
     }
@@ -212,7 +242,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
             float ad = fabsf(vdot(rd, rd));                                // AbsDot(Nl, photonRay.d) with Nl == ray.d
             float den = pdf * lightPdf;
             bool black = true;
-#pragma unroll
+SH_UNROLL_BINS
             for (int b = 0; b < PV_NSPEC; ++b) {
                 float Le = l.type == PV_LIGHT_SPOT ? l.intensity[b] * scale : l.intensity[b];
                 cur.alpha[b] = __fdiv_rn(Le * ad, den);
@@ -262,7 +292,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                     while (t0 < t1) {
                         float uo = rng.next();                               // Transmittance(sample == NULL): offset = RandomFloat()
                         uint32_t ns = 0;
-                        float s = med_tau_scalar(med, o, rnd, t_i, t0, a.istep4, uo, &ns);
+                        float s = shoot_tau(med, o.x, o.y, o.z, rnd.x, rnd.y, rnd.z, t_i, t0, a.istep4, uo, &ns);
                         c_dens += ns;
                         // xi > Tr.y() ?  y(exp(-sig_t s)) lies between exp(-st_max s) y1 and exp(-st_min s) y1
                         bool hitv;
@@ -271,6 +301,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                         else if (xi < elo * 0.9999f) hitv = false;
                         else {
                             float yy = 0.f;
+SH_UNROLL_BINS
                             for (int b = 0; b < PV_NSPEC; ++b) yy += s_cie[b] * expf(-(s_st[b] * s));
                             hitv = xi > __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC);
                         }
@@ -283,6 +314,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                         float dens = med_density(med, pt, &ns);
                         c_dens += 2 * ns;
                         float ys = 0.f, ya = 0.f;
+SH_UNROLL_BINS
                         for (int b = 0; b < PV_NSPEC; ++b) { ys += s_cie[b] * (s_ss[b] * dens); ya += s_cie[b] * (s_sa[b] * dens); }
                         ys = __fdiv_rn(ys * 300.f, 106.856895f * (float)PV_NSPEC); ya = __fdiv_rn(ya * 300.f, 106.856895f * (float)PV_NSPEC);
                         bool scatter = rng.next() > __fdiv_rn(ys, ya + ys);     // Q1 (photonshooter.cpp:88)
@@ -300,7 +332,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                                     a.pos[3 * slot] = pt.x; a.pos[3 * slot + 1] = pt.y; a.pos[3 * slot + 2] = pt.z;
                                     a.wi[3 * slot] = rnd.x; a.wi[3 * slot + 1] = rnd.y; a.wi[3 * slot + 2] = rnd.z;
                                     float4 *dst = reinterpret_cast<float4 *>(a.alpha32 + 32 * slot);
-#pragma unroll
+SH_UNROLL_BINS
                                     for (int q = 0; q < 7; ++q)
                                         dst[q] = make_float4(__fdiv_rn(cur.alpha[4 * q], fn), __fdiv_rn(cur.alpha[4 * q + 1], fn),
                                                              __fdiv_rn(cur.alpha[4 * q + 2], fn), __fdiv_rn(cur.alpha[4 * q + 3], fn));
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                             float ref = med_phase(med, pt, rnd, dir);
                             if (ref == 0.f) pop = true;
                             else {
-#pragma unroll
+SH_UNROLL_BINS
                                 for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(cur.alpha[b] * ref, pdf);
                                 cur.o[0] = pt.x; cur.o[1] = pt.y; cur.o[2] = pt.z; cur.d[0] = dir.x; cur.d[1] = dir.y; cur.d[2] = dir.z;
                                 cur.mint = 0.f; cur.maxt = INFINITY; cur.loop_i = -1;
@@ -337,9 +369,9 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
             if (cur.loop_i < 0) {
                 float uo = rng.next();
                 uint32_t ns = 0;
-                float s = med_tau_scalar(med, o, d, cur.mint, cur.maxt, a.istep4, uo, &ns);
+                float s = shoot_tau(med, o.x, o.y, o.z, d.x, d.y, d.z, cur.mint, cur.maxt, a.istep4, uo, &ns);
                 c_dens += ns;
-#pragma unroll
+SH_UNROLL_BINS
                 for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] *= expf(-(s_st[b] * s));
                 cur.loop_i = 0;
                 if (cur.nI >= a.max_depth) pop = true;
@@ -357,6 +389,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                     // roulette draw only if the sample is valid.
                     float u0 = rng.next(), u1 = rng.next(); rng.next();
                     bool kd_black = true;
+SH_UNROLL_BINS
                     for (int b = 0; b < PV_NSPEC; ++b) kd_black = kd_black && mat.kd[b] == 0.f;
                     if (!kd_black) {
                         v3 wol = V3(vdot(wo, sn), vdot(wo, tn), vdot(wo, nn));
@@ -375,9 +408,11 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                 } else {
                     // glass: SpecularReflection + dispersive SpecularTransmission (materials/glass.cpp:42-59)
                     bool hasR = false, hasT = false;
+SH_UNROLL_BINS
                     for (int b = 0; b < PV_NSPEC; ++b) { hasR = hasR || mat.kr[b] != 0.f; hasT = hasT || mat.kt[b] != 0.f; }
                     const int matching = (hasR ? 1 : 0) + (hasT ? 1 : 0);
                     int nz = 0;
+SH_UNROLL_BINS
                     for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) nz++;
                     const bool do_split = hasT && nz != 1 && mat.vn > 0.f;       // alpha.lambda < 0 && dispersive()
                     bool spawned = false;
@@ -386,6 +421,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                         int bin = -1;
                         if (do_split) {
                             int seen = 0;
+SH_UNROLL_BINS
                             for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] != 0.f) { if (seen == cur.loop_i) { bin = b; break; } seen++; }
                             if (bin < 0) break;
                         } else if (cur.loop_i > 0) break;
@@ -404,7 +440,9 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                             float ei = 1.f, et = mat.index;
                             int lam = -1;
                             if (do_split) lam = 400 + bin * 10;                    // extractLambda: integer step (700-400)/29 == 10
-                            else if (nz == 1) { for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) lam = 400 + b * 10; }
+                            else if (nz == 1) {
+SH_UNROLL_BINS
+                                for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) lam = 400 + b * 10; }
                             if (lam > 0 && mat.vn > 0.f) {                         // Cauchy, reflection.cpp:155-161
                                 float lmu = __fdiv_rn((float)lam, 1000.f);
                                 float B = (float)((double)__fdiv_rn(et - 1.f, mat.vn) * 0.52345);
@@ -425,7 +463,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                                     sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
                         float adn = fabsf(vdot(wiW, nn));
                         float anew[PV_NSPEC], ynew = 0.f, yold = 0.f; bool fblack = true;
-#pragma unroll
+SH_UNROLL_BINS
                         for (int b = 0; b < PV_NSPEC; ++b) {
                             float ab = do_split ? (b == bin ? cur.alpha[b] : 0.f) : cur.alpha[b];
                             float fb = pickT ? __fdiv_rn((1.f - F) * mat.kt[b], fabsf(wil.z)) : __fdiv_rn(F * mat.kr[b], fabsf(wil.z));
@@ -440,7 +478,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
                         if (!cur.spec) continue;                                // indirectDone && !specularPath
                         // spawn the child; this frame resumes at loop_i afterwards
                         if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
-#pragma unroll
+SH_UNROLL_BINS
                         for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(anew[b], continueProb);
                         cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
                         cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
