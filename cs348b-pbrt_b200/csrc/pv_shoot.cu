@@ -140,7 +140,7 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
 #define SH_PRAGMA_UNROLL(n) _Pragma(SH_STR(unroll n))
 #define SH_UNROLL_BINS SH_PRAGMA_UNROLL(SH_BIN_UNROLL)
 #ifndef SH_MIN_CTAS
-#define SH_MIN_CTAS 4                // 16 warps/SM at 128 registers: the spills cost less than the occupancy gains
+#define SH_MIN_CTAS 8                // 32 warps/SM at 64 registers: latency-bound on density taps, the spills cost less than the occupancy gains (measured 4: 40.9 ms, 6: 36.1 ms, 8: 35.2 ms)
 #endif
 __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
