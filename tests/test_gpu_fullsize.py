@@ -1,0 +1,137 @@
+"""GPU (-m gpu): BASELINE config 3 at FULL size (256^3 density grid, 16 M photons, 1920x1080 = 54.8 M lookups).
+
+The oracle cannot finish this size in seconds, so parity is checked through properties that do not depend on size:
+  * determinism: the persistent kernel claims rays with an atomic counter; the result must not depend on who got which ray;
+  * sharding invariance: gathering two halves of the frame (with their ray_index_base) equals gathering the frame -- bit exact;
+  * grid invariance: the neighbour SETS must not depend on the cell size the map was built for -> the exact neighbour
+    counters (lookups, photons found) agree and the radiance agrees to summation-order accuracy;
+  * linearity: doubling every photon's alpha doubles the in-scattered estimate bit for bit (power-of-two scaling is exact);
+  * brute force: at a sample of query points the k-NN index sets over all 16 M photons equal a numpy brute-force search;
+  * a bounded sample of rays against the CPU oracle (the same check bench.py's cpu_baseline leg reports).
+"""
+import numpy as np
+import pytest
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frame(pkg):
+    import importlib
+    W = importlib.import_module("cs348b_pbrt_b200.workloads")
+    cfg = W.CONFIGS["config3"]
+    scene = W.load_scene(cfg)
+    pos, wi, alpha = W.photons_from_density(scene, cfg["photons"])
+    rays, _ = W.frame_rays(cfg)
+    pv = pkg.PhotonVolume(device=0, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=348)
+    pv.set_scene(scene)
+    pv.set_photons(pos, wi, alpha)
+    pv.build()
+    import torch
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).cuda()
+    yield dict(cfg=cfg, scene=scene, pos=pos, wi=wi, alpha=alpha, rays=rays, pv=pv, d_rays=d_rays, torch=torch)
+    pv.close()
+
+
+def gather_dev(f, pv=None, lo=0, hi=None, base=0, flags=0):
+    torch = f["torch"]
+    pv = pv or f["pv"]
+    hi = len(f["rays"]) if hi is None else hi
+    n = hi - lo
+    L = torch.empty((n, 30), device="cuda"); T = torch.empty((n, 30), device="cuda")
+    pv.gather_stats(reset=True)
+    pv.Li_dev(f["d_rays"][lo:hi].contiguous(), n, L, T, ray_index_base=base, flags=flags)
+    return L, T, pv.gather_stats(reset=True)
+
+
+def test_full_frame_is_deterministic_and_shards_exactly(frame):
+    torch = frame["torch"]
+    n = len(frame["rays"])
+    L1, T1, s1 = gather_dev(frame)
+    L2, T2, s2 = gather_dev(frame)
+    assert torch.equal(L1, L2) and torch.equal(T1, T2)
+    assert (s1.lookups, s1.photons_found, s1.candidates_tested) == (s2.lookups, s2.photons_found, s2.candidates_tested)
+    assert s1.rays == n and s1.lookups > 50_000_000
+    assert bool(torch.isfinite(L1).all()) and float(L1.max()) > 0
+    h = n // 2 + 7                                          # not tile aligned
+    La, Ta, sa = gather_dev(frame, lo=0, hi=h, base=0)
+    Lb, Tb, sb = gather_dev(frame, lo=h, hi=n, base=h)
+    assert torch.equal(torch.cat([La, Lb]), L1) and torch.equal(torch.cat([Ta, Tb]), T1)
+    assert sa.lookups + sb.lookups == s1.lookups and sa.photons_found + sb.photons_found == s1.photons_found
+
+
+@pytest.mark.parametrize("cell_scale", [2.3, 0.45])
+def test_neighbour_sets_do_not_depend_on_the_grid(frame, pkg, cell_scale):
+    """Same photons in a map built for another radius: 2.3x (bigger cells, other x refinement) and 0.45x (cells smaller than
+    the search radius: the multi-shell search path of the k-nearest code)."""
+    cfg = frame["cfg"]
+    n = 200_000
+    L1, T1, s1 = gather_dev(frame, hi=n)
+    pv2 = pkg.PhotonVolume(device=0, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=348)
+    try:
+        pv2.set_scene(frame["scene"])
+        pv2.set_photons(frame["pos"], frame["wi"], frame["alpha"])
+        pv2.build(maxdist=cell_scale * cfg["maxdist"], nused=cfg["nused"])
+        L2, T2, s2 = gather_dev(frame, pv=pv2, hi=n)
+    finally:
+        pv2.close()
+    assert (s1.lookups, s1.photons_found) == (s2.lookups, s2.photons_found)          # exact neighbour counts
+    assert s2.candidates_tested != s1.candidates_tested
+    torch = frame["torch"]
+    assert torch.equal(T1, T2)
+    rel = ((L1 - L2).abs() / L1.abs().clamp_min(1e-30))[L1 > 0]
+    assert float(rel.max()) < 1e-5                                                   # summation order only
+
+
+def test_in_scattered_radiance_is_linear_in_alpha(frame, pkg):
+    cfg = frame["cfg"]
+    n = 200_000
+    NO_DIRECT = pkg._abi.GATHER_NO_DIRECT
+    L1, _, _ = gather_dev(frame, hi=n, flags=NO_DIRECT)
+    pv2 = pkg.PhotonVolume(device=0, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=348)
+    try:
+        pv2.set_scene(frame["scene"])
+        pv2.set_photons(frame["pos"], frame["wi"], frame["alpha"] * np.float32(2))
+        pv2.build()
+        L2, _, _ = gather_dev(frame, pv=pv2, hi=n, flags=NO_DIRECT)
+    finally:
+        pv2.close()
+    assert float(L1.max()) > 0
+    assert frame["torch"].equal(L2, 2 * L1)
+
+
+def test_knn_over_16m_photons_matches_brute_force(frame):
+    pos = frame["pos"]
+    rng = np.random.default_rng(11)
+    pts = (pos[rng.choice(len(pos), 24, replace=False)] + rng.uniform(-0.01, 0.01, size=(24, 3))).astype(np.float32)
+    px = np.ascontiguousarray(pos[:, 0])
+    for k, r in ((512, frame["cfg"]["maxdist"]), (20, 0.05)):
+        r2 = float(np.float32(r) * np.float32(r))
+        nf, idx, d2 = frame["pv"].Lookup(pts, k=k, r2=r2)
+        for q in range(len(pts)):
+            slab = np.nonzero(np.abs(px - pts[q, 0]) <= np.float32(r * 1.001))[0]     # exact superset of the ball
+            d = pos[slab] - pts[q]
+            dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]          # float32, the reference's operation order
+            inside = dd < np.float32(r2)
+            cand, dd = slab[inside], dd[inside]
+            o = np.lexsort((cand, dd))[:k]
+            order, dd = cand[o], dd[o]
+            assert nf[q] == len(order)
+            assert np.array_equal(idx[q, :nf[q]], order.astype(np.uint32))
+            assert np.array_equal(d2[q, :nf[q]].view(np.uint32), dd.view(np.uint32))
+
+
+def test_sample_of_the_frame_against_the_oracle(frame):
+    cfg = frame["cfg"]
+    rays = frame["rays"]
+    sel = np.linspace(0, len(rays) - 1, 1500).astype(np.int64)
+    sample = np.ascontiguousarray(rays[sel])
+    L, T = frame["pv"].Li(sample)
+    tree = O.KdTree(frame["pos"])
+    oL, oT, st = O.gather(frame["scene"], tree, frame["wi"], frame["alpha"], sample, cfg["stepsize"], cfg["nused"], cfg["maxdist"],
+                          seed=348, nthreads=16)
+    m = oL > 0
+    assert m.any() and st.lookups > 10_000
+    assert (np.abs(L - oL)[m] / oL[m]).max() < 1e-4
+    assert np.abs(T - oT).max() < 1e-5
