@@ -138,12 +138,19 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         if (rc) pv_fail("pv_build", rc);
     }
     g_pv.ready = true;
-    // surface photon maps (caustic / indirect / radiance photons) stay on the reference's CPU pass
+    // Surface photon maps (caustic / indirect / radiance photons) stay on the reference's CPU pass.  That pass keeps
+    // scattering photons in the medium only while its own volume map is not full (`scatter && !volumeDone`,
+    // photonshooter.cpp:96), and in scenes without specular surfaces the "caustic" photons are exactly those scattered
+    // paths (Q6: volume scattering does not clear specularPath).  So the CPU pass is asked for as many volume photons as
+    // surface photons -- what the shipped scenes do anyway (volumescene_png.pbrt: 5000 / 5000) -- never for the full
+    // volume count; its volume photons are dropped, the volume map is the GPU's.
     if (nCausticPhotonsWanted + nIndirectPhotonsWanted > 0) {
         uint32_t keep = nVolumePhotonsWanted;
-        nVolumePhotonsWanted = 0;
+        nVolumePhotonsWanted = std::min(keep, std::max(nCausticPhotonsWanted, nIndirectPhotonsWanted));
+        int keepPaths = nVolumePaths;
         _ZN13PhotonShooter13RefPreprocessEPK5ScenePK6CameraPK8Renderer(this, scene, camera, renderer);
-        nVolumePhotonsWanted = keep;
+        nVolumePhotonsWanted = keep; nVolumePaths = keepPaths;
+        delete volumeMap; volumeMap = NULL;
     }
 }
 
