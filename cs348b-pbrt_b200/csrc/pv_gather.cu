@@ -348,22 +348,36 @@ __device__ __noinline__ ShellState lookup_shell(MapView m, WarpBuf b, int s, int
     // x extent of the shell in fine cells: coarse cells cx-s .. cx+s
     const int xs = g.xshift, xlast = g.dims[0] - 1;
     const int x0 = max((cx - s) << xs, 0), x1 = min(((cx + s + 1) << xs) - 1, xlast);
+    const float ylo = g.origin[1] + cy * g.h, zlo = g.origin[2] + cz * g.h;
     for (int j0 = 0; j0 < rows; j0 += 32) {
         const int j = j0 + (int)lane;
         uint32_t sa = 0, ea = 0, sb = 0, eb = 0;
+        // Nothing farther than the current k-th distance (or r) can enter the result any more: rows of the shell outside
+        // that sphere are skipped, the others clipped to its chord -- same conservative margins as lookup_ranges (a tie
+        // at exactly the k-th distance lies on the sphere and stays inside the widened chord).
+        const float bound2 = fminf(r2, boundk);
         if (j < rows) {
             const int dy = j % side - s, dz = j / side - s;
             const int y = cy + dy, z = cz + dz;
             if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
-                const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
-                if (max(abs(dy), abs(dz)) == s) {
-                    if (x0 <= x1) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)x0)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)x1) + 1); }
-                } else {
-                    // inner rows: the two end (coarse) cells of the shell
-                    const int la = (cx - s) << xs, lb = min(((cx - s + 1) << xs) - 1, xlast);
-                    const int ra = (cx + s) << xs, rb = min(((cx + s + 1) << xs) - 1, xlast);
-                    if (cx - s >= 0 && la <= lb) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)la)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)lb) + 1); }
-                    if (ra <= xlast) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)ra)); eb = __ldg(m.cell_start + (rowkey | (uint32_t)rb) + 1); }
+                float gy = dy == 0 ? 0.f : (dy < 0 ? q.y - (ylo + (dy + 1) * g.h) : (ylo + dy * g.h) - q.y);
+                float gz = dz == 0 ? 0.f : (dz < 0 ? q.z - (zlo + (dz + 1) * g.h) : (zlo + dz * g.h) - q.z);
+                gy = fmaxf(gy - g.margin, 0.f); gz = fmaxf(gz - g.margin, 0.f);
+                const float w2 = bound2 - (gy * gy + gz * gz);
+                if (w2 > 0.f) {
+                    const float half = __fsqrt_ru(w2) + g.margin;
+                    const int xa = (int)floorf(((q.x - half) - g.origin[0]) * g.inv_hx), xb = (int)floorf(((q.x + half) - g.origin[0]) * g.inv_hx);
+                    const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                    if (max(abs(dy), abs(dz)) == s) {
+                        const int a0 = max(x0, xa), a1 = min(x1, xb);
+                        if (a0 <= a1) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)a0)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)a1) + 1); }
+                    } else {
+                        // inner rows: the two end (coarse) cells of the shell
+                        const int la = max((cx - s) << xs, xa), lb = min(min(((cx - s + 1) << xs) - 1, xlast), xb);
+                        const int ra = max((cx + s) << xs, xa), rb = min(min(((cx + s + 1) << xs) - 1, xlast), xb);
+                        if (cx - s >= 0 && la <= lb) { sa = __ldg(m.cell_start + (rowkey | (uint32_t)la)); ea = __ldg(m.cell_start + (rowkey | (uint32_t)lb) + 1); }
+                        if (ra <= rb) { sb = __ldg(m.cell_start + (rowkey | (uint32_t)ra)); eb = __ldg(m.cell_start + (rowkey | (uint32_t)rb) + 1); }
+                    }
                 }
             }
         }
