@@ -46,6 +46,9 @@
 #ifndef GW_LIGHT_REG
 #define GW_LIGHT_REG 0                  // measured: the extra live register costs more than the per-step load it saves
 #endif
+#ifndef GW_PAD16
+#define GW_PAD16 0
+#endif
 #ifndef GW_P2_UNROLL
 #define GW_P2_UNROLL 4
 #endif
@@ -474,7 +477,11 @@ __device__ __forceinline__ float warp_estimate(const MapView &m, const DevMedium
     float mx = 0.f;
     const float g = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - g * g), gg1 = 1.f + g * g, g2 = 2.f * g;
     const bool iso = g == 0.f;
+#if GW_PAD16
+    const uint32_t padded = (count + 15u) & ~15u;        // whole 16-photon iterations only: the 8-photon tail (one more exposed L2 round trip) never runs
+#else
     const uint32_t padded = (count + 7u) & ~7u;
+#endif
     const float4 *a4 = reinterpret_cast<const float4 *>(m.alpha32) + sub;
 #if GW_PRELOAD
     // The alpha lines of the first 16 photons (count >= 10, so padded >= 16) are requested BEFORE pass 1: their L2
