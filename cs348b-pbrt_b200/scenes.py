@@ -35,6 +35,43 @@ Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -4  1 -1 -
 WorldEnd
 """
 
+# The same box with every photon map of the reference's shooter switched on (SURVEY 8(f)-2): a dispersive glass wedge under
+# the light makes real caustics, the matte walls indirect / direct / radiance photons, the medium volume photons.
+CORNELL_SURF_TEMPLATE = """# synthetic Cornell box, all photon maps on (surface maps: core/photonshooter.cpp:147-189)
+Film "image" "string filename" "{outfile}"
+ "integer xresolution" [{xres}] "integer yresolution" [{yres}]
+Sampler "lowdiscrepancy" "integer pixelsamples" [1]
+PixelFilter "box"
+SurfaceIntegrator "photonmap" "integer nused" [{surf_nused}] "bool finalgather" ["{finalgather}"] "integer finalgathersamples" [{fgsamples}]
+  "float maxdist" [{surf_maxdist}] "integer indirectphotons" [{indirect}] "integer causticphotons" [{caustic}]
+  "float stepsize" [{shoot_step}] "integer maxphotondepth" [5]
+VolumeIntegrator "photonvolume" "float stepsize" [{stepsize}] "integer nused" [{nused}] "float maxdist" [{maxdist}]
+  "integer volumephotons" [{nphotons}]
+LookAt 0 0 -3.4  0 0 0  0 1 0
+Camera "perspective" "float fov" [40]
+WorldBegin
+{volume}
+LightSource "point" "point from" [0 0.8 0] "color I" [20 20 20]
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -1  1 -1 -1  1 -1 1  -1 -1 1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 1 -1  1 1 -1  1 1 1  -1 1 1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 1  1 -1 1  1 1 1  -1 1 1]
+Material "matte" "color Kd" [.6 .1 .1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -1  -1 -1 1  -1 1 1  -1 1 -1]
+Material "matte" "color Kd" [.1 .6 .1]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [1 -1 -1  1 -1 1  1 1 1  1 1 -1]
+Material "matte" "color Kd" [.6 .6 .6]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 -1 -4  1 -1 -4  1 1 -4  -1 1 -4]
+AttributeBegin
+Material "glass" "float index" [1.5] "float Vn" [{vn}] "color Kr" [1 1 1] "color Kt" [1 1 1]
+Translate 0 -0.3 0.1
+Scale 0.45 0.25 0.45
+Shape "trianglemesh" "point P" [1 -1 -1  1 -1 1  -1 -1 1  -1 -1 -1  1 1 0  -1 1 0]
+  "integer indices" [0 1 2  0 2 3  1 4 5  1 5 2  0 4 1  2 5 3  4 0 3  4 3 5]
+AttributeEnd
+WorldEnd
+"""
+
 HOMOG_VOLUME = ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s" [.15 .15 .15] "float g" [0]\n'
                 '  "point p0" [-1 -1 -1] "point p1" [1 1 1]')
 
@@ -133,6 +170,15 @@ def cornell_pbrt(volume_text, nphotons, xres=64, yres=64, stepsize=0.05, nused=5
                  outfile="cornell_vol.pfm", title="synthetic Cornell box (SURVEY.md Appendix C)"):
     return CORNELL_TEMPLATE.format(title=title, outfile=outfile, xres=xres, yres=yres, shoot_step=shoot_step,
                                    stepsize=stepsize, nused=nused, maxdist=maxdist, nphotons=nphotons, volume=volume_text)
+
+
+def cornell_surf_pbrt(nphotons=3000, caustic=1500, indirect=4000, finalgather=True, fgsamples=8, surf_nused=50, surf_maxdist=0.25,
+                      xres=64, yres=64, stepsize=0.05, nused=50, maxdist=0.25, shoot_step=0.05, vn=0.0, volume_text=None,
+                      outfile="cornell_surf.pfm"):
+    return CORNELL_SURF_TEMPLATE.format(outfile=outfile, xres=xres, yres=yres, surf_nused=surf_nused, surf_maxdist=surf_maxdist,
+                                        finalgather="true" if finalgather else "false", fgsamples=fgsamples, indirect=indirect,
+                                        caustic=caustic, shoot_step=shoot_step, stepsize=stepsize, nused=nused, maxdist=maxdist,
+                                        nphotons=nphotons, vn=vn, volume=volume_text or HOMOG_VOLUME)
 
 
 def camera_rays(xres, yres, fov_deg=40.0, eye=(0.0, 0.0, -3.4), look=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0),

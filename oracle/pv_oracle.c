@@ -946,7 +946,21 @@ typedef struct {
     phvec *local;
     uint64_t path_index; uint32_t deposit_seq;
     bvh_counters bc; med_counters mc; uint64_t segments;
+    /* surface maps (photonshooter.cpp:147-189).  All zero == the volume-only pass: causticDone and indirectDone true,
+       volumeDone false -- no surface deposit, no radiance photon, diffuse bounces end the path (Q6). */
+    phvec *surf[4];                 /* caustic, indirect, direct, radiance sites (wi := n, alpha := rho_r) */
+    int want_caustic, want_indirect, volume_done, final_gather;
+    uint64_t first_hit_scatters;    /* shooter->nVolumePaths++ (:104) */
 } shoot_ctx;
+#define PVO_ID(cls, path, seq) (((uint64_t)(cls) << 60) | ((uint64_t)(path) << 16) | ((uint64_t)(seq) & 0xffffu))
+/* skip n draws of the path stream (BSDF::rho's stratified samples are drawn and, for a Lambertian BRDF, never used) */
+static void st_skip(stream *s, uint32_t n) {
+    if (s->mode == PVO_RNG_MT) { for (uint32_t i = 0; i < n; ++i) (void)mt_next(s->mt); return; }
+    uint64_t consumed = (uint64_t)s->j * 4 - (4 - s->pos) + n;
+    uint32_t q = (uint32_t)(consumed / 4), r = (uint32_t)(consumed % 4);
+    if (r == 0) { s->j = q; s->pos = 4; }
+    else { pv_philox4x32_10(s->c0, s->c1, q, PV_RNG_PATH, s->k0, s->k1, s->buf); s->j = q + 1; s->pos = r; }
+}
 
 typedef struct { int prim; v3 p; v3 nn, dpdu; float rayEpsilon; } isect_t;
 typedef struct { v3 o, d; float mint, maxt; } ray_t;
@@ -1010,11 +1024,12 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         float ys = s_y(sc, &sig_s), ya = s_y(sc, &sig_a);
         int scatter = (st_float(c->rng) > (ys) / (ya + ys));     /* Q1: inverted test, photonshooter.cpp:88 */
         if (!scatter) return;
+        if (!c->volume_done) {                                   /* `if (scatter && !volumeDone)` :96 */
         if (nIntersections > 1) {
-            uint64_t id = (c->path_index << 16) | (c->deposit_seq & 0xffffu);
+            uint64_t id = PVO_ID(0, c->path_index, c->deposit_seq);
             c->deposit_seq++;
             phvec_push(c->local, interactPt, &alpha, rnd, id);
-        }
+        } else c->first_hit_scatters++;
         float u1 = st_float(c->rng);
         float u2 = st_float(c->rng);
         v3 direction = uniform_sample_sphere(u1, u2);
@@ -1026,6 +1041,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         photonRay.o = interactPt; photonRay.d = direction; photonRay.mint = 0.f; photonRay.maxt = INFINITY;
         follow_photon(c, photonRay, photonIsect, alpha, nIntersections, specularPath);
         /* Q2: falls through into the surface code with the scattered ray and the ORIGINAL isect */
+        }
     }
     {
         spec tr = shoot_transmittance(c, &photonRay);
@@ -1033,7 +1049,30 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
     }
     const pv_material *mat = &sc->materials[sc->prim_material[photonIsect.prim]];
     v3 wo = vneg(photonRay.d);
-    /* caustic/indirect/direct maps are off in this path: no surface deposits, no radiance photons */
+    /* surface deposits (photonshooter.cpp:147-189); hasNonSpecular == a matte surface with a non-black Kd (materials/matte.cpp:55) */
+    {
+        spec Kd = s_load(mat->kd);
+        int hasNonSpecular = mat->type == PV_MAT_MATTE && !s_black(&Kd);
+        if (hasNonSpecular) {
+            int cls = -1;
+            if (specularPath && nIntersections > 1) { if (c->want_caustic) cls = 0; }
+            else if (nIntersections == 1 && c->want_indirect && c->final_gather) cls = 2;
+            else if (nIntersections > 1 && c->want_indirect) cls = 1;
+            if (cls >= 0) {
+                phvec_push(c->surf[cls], photonIsect.p, &alpha, wo, PVO_ID(cls + 1, c->path_index, c->deposit_seq));
+                c->deposit_seq++;
+                if (c->final_gather && st_float(c->rng) < .125f) {
+                    v3 n = photonIsect.nn;
+                    if (vdot(n, vneg(photonRay.d)) < 0.f) n = vneg(n);          /* Faceforward(n, -photonRay.d) */
+                    /* rho_r = BSDF::rho(rng, BSDF_ALL_REFLECTION) == Kd for a Lambertian (reflection.cpp:647-659, :326);
+                       rho_t == 0; each rho draws 2 x StratifiedSample2D(6x6) = 144 floats */
+                    phvec_push(c->surf[3], photonIsect.p, &Kd, n, PVO_ID(4, c->path_index, c->deposit_seq));
+                    c->deposit_seq++;
+                    st_skip(c->rng, 288);
+                }
+            }
+        }
+    }
     if (nIntersections >= c->prm->max_photon_depth) return;
     /* BSDF frame core/reflection.cpp:619-627 */
     v3 nn = photonIsect.nn, ng = photonIsect.nn;
@@ -1061,6 +1100,10 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         float continueProb = fminf(1.f, s_y(sc, &anew) / s_y(sc, &alpha));
         if (st_float(c->rng) > continueProb) return;
         /* specularPath &= false; indirectDone && !specularPath -> continue (Q6) */
+        if (!c->want_indirect) return;
+        spec an2; for (int b = 0; b < NS; ++b) an2.c[b] = anew.c[b] / continueProb;
+        ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
+        follow_photon(c, nr, photonIsect, an2, nIntersections, 0);
         return;
     }
     /* glass: specular reflection + dispersive transmission (materials/glass.cpp:42-59,
@@ -1153,8 +1196,8 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
             float continueProb = fminf(1.f, s_y(sc, &anew) / s_y(sc, &a));
             if (st_float(c->rng) > continueProb) continue;
             spec an2; for (int b = 0; b < NS; ++b) an2.c[b] = anew.c[b] / continueProb;
-            /* specular: specularPath stays as it was */
-            if (!specularPath) continue;
+            /* specular: specularPath stays as it was; `indirectDone && !specularPath` -> continue */
+            if (!c->want_indirect && !specularPath) continue;
             ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
             follow_photon(c, nr, photonIsect, an2, nIntersections, specularPath);
         }
@@ -1343,6 +1386,113 @@ int pvo_shoot(const pv_scene_desc *sc, uint64_t n_wanted, const pv_shoot_params 
     out->segments = segments;
     return rc;
 }
+/* PhotonShootingTask::Run with all maps (photonshooter.cpp:232-357), ONE task: per-class done flags that change at block
+ * ends (:303-341), per-class path counts, the give-up rule over the three wanted counts (:285-299). */
+int pvo_shoot_maps(const pv_scene_desc *sc, uint64_t n_volume, uint64_t n_caustic, uint64_t n_indirect, int final_gather,
+                   const pv_shoot_params *prm, int rng_mode, pvo_maps *out) {
+    memset(out, 0, sizeof(*out));
+    if (!sc->n_lights || !sc->medium) return PV_EINVAL;
+    mt_rng mt; mt_seed(&mt, 0u);
+    halton6 h; halton6_init(&h, &mt);
+    distrib1d ld; distrib_init(&ld, sc);
+    phvec acc[5], local[5]; memset(acc, 0, sizeof(acc)); memset(local, 0, sizeof(local));
+    stream st; memset(&st, 0, sizeof(st)); st.mode = rng_mode; st.mt = &mt;
+    st.k0 = (uint32_t)prm->seed; st.k1 = (uint32_t)(prm->seed >> 32);
+    shoot_ctx c; memset(&c, 0, sizeof(c));
+    c.sc = sc; c.prm = prm; c.rng = &st; c.local = &local[0];
+    for (int k = 0; k < 4; ++k) c.surf[k] = &local[k + 1];
+    c.final_gather = final_gather;
+    int causticDone = n_caustic == 0, indirectDone = n_indirect == 0, volumeDone = n_volume == 0;
+    uint64_t nshot = 0, path = 0;
+    uint64_t max_paths = prm->max_paths ? prm->max_paths : ((uint64_t)1 << 40);
+    int rc = 0;
+    for (;;) {
+        c.want_caustic = !causticDone; c.want_indirect = !indirectDone; c.volume_done = volumeDone;
+        for (uint32_t i = 0; i < 4096; ++i) {
+            ++path;
+            if (rng_mode != PVO_RNG_MT) { st.c0 = (uint32_t)path; st.c1 = (uint32_t)(path >> 32); st.j = 0; st.pos = 4; }
+            shoot_path(&c, &h, &ld, path);
+        }
+        out->blocks++;
+#define UNSUCC(needed, found) ((found) < (needed) && ((found) == 0 || (found) < 4096 / 1024))
+        if (nshot > 500000 && (UNSUCC(n_caustic, acc[1].n) || UNSUCC(n_indirect, acc[2].n) || UNSUCC(n_volume, acc[0].n))) {
+            rc = PV_ENOPHOTONS; acc[0].n = acc[1].n = acc[2].n = acc[4].n = 0; break;       /* :292-296 (direct photons are kept) */
+        }
+#undef UNSUCC
+        nshot += 4096;
+        if (!indirectDone) {
+            out->n_indirect_paths += 4096;
+            for (uint64_t i = 0; i < local[2].n; ++i) { spec a = s_load(local[2].alpha + NS * i);
+                phvec_push(&acc[2], V(local[2].pos[3*i], local[2].pos[3*i+1], local[2].pos[3*i+2]), &a, V(local[2].wi[3*i], local[2].wi[3*i+1], local[2].wi[3*i+2]), local[2].ids[i]); }
+            if (acc[2].n >= n_indirect) indirectDone = 1;
+            out->n_direct_paths += 4096;
+            for (uint64_t i = 0; i < local[3].n; ++i) { spec a = s_load(local[3].alpha + NS * i);
+                phvec_push(&acc[3], V(local[3].pos[3*i], local[3].pos[3*i+1], local[3].pos[3*i+2]), &a, V(local[3].wi[3*i], local[3].wi[3*i+1], local[3].wi[3*i+2]), local[3].ids[i]); }
+        }
+        local[2].n = local[3].n = 0;
+        if (!causticDone) {
+            out->n_caustic_paths += 4096;
+            for (uint64_t i = 0; i < local[1].n; ++i) { spec a = s_load(local[1].alpha + NS * i);
+                phvec_push(&acc[1], V(local[1].pos[3*i], local[1].pos[3*i+1], local[1].pos[3*i+2]), &a, V(local[1].wi[3*i], local[1].wi[3*i+1], local[1].wi[3*i+2]), local[1].ids[i]); }
+            if (acc[1].n >= n_caustic) causticDone = 1;
+        }
+        local[1].n = 0;
+        if (!volumeDone) {
+            out->n_volume_paths += 4096;
+            merge_block(NULL, &acc[0], &local[0], nshot);
+            if (acc[0].n >= n_volume) volumeDone = 1;
+        }
+        local[0].n = 0;
+        for (uint64_t i = 0; i < local[4].n; ++i) { spec a = s_load(local[4].alpha + NS * i);
+            phvec_push(&acc[4], V(local[4].pos[3*i], local[4].pos[3*i+1], local[4].pos[3*i+2]), &a, V(local[4].wi[3*i], local[4].wi[3*i+1], local[4].wi[3*i+2]), local[4].ids[i]); }
+        local[4].n = 0;
+        if (indirectDone && causticDone && volumeDone) break;
+        if (nshot >= max_paths) break;
+    }
+    out->n_volume_paths += c.first_hit_scatters;
+    for (int k = 0; k < 5; ++k) {
+        phvec_free(&local[k]);
+        out->cls[k].n = acc[k].n; out->cls[k].pos = acc[k].pos; out->cls[k].wi = acc[k].wi; out->cls[k].alpha = acc[k].alpha; out->cls[k].ids = acc[k].ids;
+        out->cls[k].nshot = nshot; out->cls[k].blocks = out->blocks;
+    }
+    out->nshot = nshot;
+    free(ld.func); free(ld.cdf);
+    return rc;
+}
+void pvo_maps_free(pvo_maps *m) { for (int k = 0; k < 5; ++k) pvo_photons_free(&m->cls[k]); }
+
+/* EPhoton + ComputeRadianceTask::Run (photonshooter.cpp:17-35,359-395) for radiance photons with rho_t == 0:
+ * Lo = INV_PI * rho_r * (E_direct + E_indirect + E_caustic), E = sum of alpha over the found photons with n.wi > 0,
+ * divided by count * md2 * pi, md2 = the search radius^2 as the lookup left it. */
+static void ephoton_acc(const pvo_kdtree *t, const float *wi, const float *alpha, uint64_t count, uint32_t nLookup, float maxDist2,
+                        v3 p, v3 n, closeph *buf, spec *E) {
+    if (!t || t->nNodes == 0) return;
+    photon_proc proc = {buf, nLookup, 0, 0};
+    float md2 = maxDist2;
+    kd_lookup(t, 0, p, &proc, &md2);
+    if (proc.nFound == 0) return;
+    spec e = s_const(0.f);
+    for (uint32_t i = 0; i < proc.nFound; ++i) {
+        uint32_t o = t->nodeOrig[buf[i].node];
+        if (vdot(n, V(wi[3 * o], wi[3 * o + 1], wi[3 * o + 2])) > 0.f)
+            for (int b = 0; b < NS; ++b) e.c[b] += alpha[NS * (size_t)o + b];
+    }
+    float den = (float)((double)((float)(int)count * md2) * 3.14159265358979323846);     /* count * md2 * M_PI: float * double */
+    for (int b = 0; b < NS; ++b) E->c[b] += e.c[b] / den;
+}
+int pvo_radiance(const pvo_kdtree *maps[3], const float *wis[3], const float *alphas[3], const uint64_t counts[3],
+                 const float *rp_pos, const float *rp_n, const float *rho_r, uint64_t n, uint32_t nLookup, float maxDist2, float *Lo) {
+    closeph *buf = (closeph *)malloc(sizeof(closeph) * (nLookup ? nLookup : 1));
+    for (uint64_t i = 0; i < n; ++i) {
+        v3 p = V(rp_pos[3 * i], rp_pos[3 * i + 1], rp_pos[3 * i + 2]), nn = V(rp_n[3 * i], rp_n[3 * i + 1], rp_n[3 * i + 2]);
+        spec r = s_load(rho_r + NS * i), E = s_const(0.f);
+        if (!s_black(&r)) for (int k = 0; k < 3; ++k) ephoton_acc(maps[k], wis[k], alphas[k], counts[k], nLookup, maxDist2, p, nn, buf, &E);
+        for (int b = 0; b < NS; ++b) Lo[NS * i + b] = (INV_PI_F * r.c[b]) * E.c[b];
+    }
+    free(buf);
+    return 0;
+}
+
 void pvo_photons_free(pvo_photons *p) {
     free(p->pos); free(p->wi); free(p->alpha); free(p->ids);
     memset(p, 0, sizeof(*p));

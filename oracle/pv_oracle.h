@@ -78,6 +78,23 @@ int  pvo_shoot(const pv_scene_desc *sc, uint64_t n_wanted, const pv_shoot_params
                int rng_mode, int nthreads, pvo_photons *out);
 void pvo_photons_free(pvo_photons *p);
 
+/* The same pass with the surface maps on (photonshooter.cpp:147-189,303-341), ONE task.
+ * cls[0] volume (alpha / nshot), cls[1] caustic, cls[2] indirect, cls[3] direct, cls[4] radiance-photon sites
+ * (wi plane = faceforwarded normal, alpha plane = rho_r; rho_t == 0 for the matte surfaces that can hold one).
+ * ids = class << 60 | path index << 16 | deposit ordinal along the path. */
+typedef struct pvo_maps {
+    pvo_photons cls[5];
+    uint64_t nshot, blocks;
+    uint64_t n_caustic_paths, n_indirect_paths, n_direct_paths, n_volume_paths;
+} pvo_maps;
+int  pvo_shoot_maps(const pv_scene_desc *sc, uint64_t n_volume, uint64_t n_caustic, uint64_t n_indirect, int final_gather,
+                    const pv_shoot_params *prm, int rng_mode, pvo_maps *out);
+void pvo_maps_free(pvo_maps *m);
+/* ComputeRadianceTask::Run + EPhoton (photonshooter.cpp:17-35,359-395), rho_t == 0: maps in the order direct, indirect,
+ * caustic (NULL = absent), counts = nDirectPaths, nIndirectPaths, nCausticPaths. Lo[30n]. */
+int  pvo_radiance(const pvo_kdtree *maps[3], const float *wis[3], const float *alphas[3], const uint64_t counts[3],
+                  const float *rp_pos, const float *rp_n, const float *rho_r, uint64_t n, uint32_t nLookup, float maxDist2, float *Lo);
+
 /* small known-answer helpers exposed for unit tests */
 uint32_t pvo_mt_first(uint32_t seed, uint32_t *out, uint32_t n);
 void     pvo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

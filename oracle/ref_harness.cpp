@@ -96,6 +96,10 @@ static void write_header(FILE *f, const char *magic, uint64_t n) {
 }
 // ---------------------------------------------------------------- photons
 static std::vector<Photon> g_photons;       // original (merge) order
+static std::vector<Photon> g_surf[3];       // caustic, indirect, direct photons of the last --shoot, merge order
+static std::vector<RadiancePhoton> g_rad;   // radiance photons with Lo (ComputeRadianceTask)
+static std::vector<Spectrum> g_rho_r, g_rho_t;
+static int g_paths[4] = {0, 0, 0, 0};       // nCausticPaths, nIndirectPaths, nDirectPaths, nVolumePaths
 static uint32_t g_nshot = 0;
 static double g_shoot_seconds = 0;
 
@@ -142,6 +146,25 @@ static void shoot(PhotonShooter *sh, const Scene *scene, const Camera *camera, c
     progress.Done();
     if (causticPhotons.size()) sh->causticMap = new KdTree<Photon>(causticPhotons);
     if (indirectPhotons.size()) sh->indirectMap = new KdTree<Photon>(indirectPhotons);
+    // radiance photons exactly as PhotonShooter::Preprocess computes them (core/photonshooter.cpp:494-524)
+    KdTree<Photon> *directMap = directPhotons.size() ? new KdTree<Photon>(directPhotons) : NULL;
+    if (sh->finalGather && radiancePhotons.size()) {
+        vector<Task *> radianceTasks;
+        uint32_t numTasks = 64;
+        ProgressReporter progRadiance(numTasks, "Computing photon radiances");
+        for (uint32_t i = 0; i < numTasks; ++i)
+            radianceTasks.push_back(new ComputeRadianceTask(progRadiance, i, numTasks, radiancePhotons, rpReflectances, rpTransmittances,
+                sh->nLookup, sh->maxDistSquared, nDirectPaths, directMap, sh->nIndirectPaths, sh->indirectMap,
+                sh->nCausticPaths, sh->causticMap, sh->nVolumePaths, sh->volumeMap));
+        EnqueueTasks(radianceTasks);
+        WaitForAllTasks();
+        for (uint32_t i = 0; i < radianceTasks.size(); ++i) delete radianceTasks[i];
+        progRadiance.Done();
+    }
+    delete directMap;
+    g_surf[0] = causticPhotons; g_surf[1] = indirectPhotons; g_surf[2] = directPhotons;
+    g_rad = radiancePhotons; g_rho_r = rpReflectances; g_rho_t = rpTransmittances;
+    g_paths[0] = sh->nCausticPaths; g_paths[1] = sh->nIndirectPaths; g_paths[2] = nDirectPaths; g_paths[3] = sh->nVolumePaths;
     g_photons.swap(volumePhotons);
     g_nshot = nshot;
     install_volume_map(sh);
@@ -165,7 +188,25 @@ static void load_photons(const std::string &fn) {
     }
     fclose(f);
 }
-static void dump_photons(const std::string &fn) {
+static void dump_photon_vec(const std::string &fn, const std::vector<Photon> &v);
+static void dump_photons(const std::string &fn) { dump_photon_vec(fn, g_photons); }
+// surface maps of the last --shoot: <prefix>.caustic / .indirect / .direct (PVPHOT01) and <prefix>.radiance
+// (PVRADP01: p[3] n[3] Lo[30] rho_r[30] rho_t[30] per radiance photon)
+static void dump_maps(const std::string &prefix) {
+    static const char *names[3] = {".caustic", ".indirect", ".direct"};
+    for (int k = 0; k < 3; ++k) dump_photon_vec(prefix + names[k], g_surf[k]);
+    FILE *f = xopen(prefix + ".radiance", "wb");
+    write_header(f, "PVRADP01", g_rad.size());
+    for (size_t i = 0; i < g_rad.size(); ++i) {
+        float rec[96];
+        const RadiancePhoton &r = g_rad[i];
+        rec[0] = r.p.x; rec[1] = r.p.y; rec[2] = r.p.z; rec[3] = r.n.x; rec[4] = r.n.y; rec[5] = r.n.z;
+        memcpy(&rec[6], r.Lo.c, 30 * sizeof(float)); memcpy(&rec[36], g_rho_r[i].c, 30 * sizeof(float)); memcpy(&rec[66], g_rho_t[i].c, 30 * sizeof(float));
+        wr(f, rec, 96);
+    }
+    fclose(f);
+}
+static void dump_photon_vec(const std::string &fn, const std::vector<Photon> &g_photons) {
     FILE *f = xopen(fn, "wb");
     write_header(f, "PVPHOT01", g_photons.size());
     for (size_t i = 0; i < g_photons.size(); ++i) {
@@ -376,6 +417,7 @@ void pbrtWorldEnd() {
         else if (op == "--shoot") { shoot(sh, scene, sr->camera, sr); }
         else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }
         else if (op == "--dump-photons") { dump_photons(ARG(1)); i += 1; }
+        else if (op == "--dump-maps") { dump_maps(ARG(1)); i += 1; }
         else if (op == "--knn") { knn(sh, ARG(1), atoi(ARG(2).c_str()), (float)atof(ARG(3).c_str()), ARG(4)); i += 4; }
         else if (op == "--lphoton") { lphoton(vi, scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--intersect") { intersect(scene, ARG(1), ARG(2)); i += 2; }
@@ -385,8 +427,10 @@ void pbrtWorldEnd() {
         else if (op == "--transmittance") { transmittance(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
         else if (op == "--stats") {
             FILE *f = xopen(ARG(1), "w");
-            fprintf(f, "{\"nshot\": %u, \"volume_photons\": %zu, \"shoot_seconds\": %.6f, \"cores\": %d}\n",
-                    g_nshot, g_photons.size(), g_shoot_seconds, NumSystemCores());
+            fprintf(f, "{\"nshot\": %u, \"volume_photons\": %zu, \"shoot_seconds\": %.6f, \"cores\": %d, \"caustic_paths\": %d, "
+                    "\"indirect_paths\": %d, \"direct_paths\": %d, \"volume_paths\": %d, \"nlookup\": %u, \"maxdist2\": %.9g, \"final_gather\": %d}\n",
+                    g_nshot, g_photons.size(), g_shoot_seconds, NumSystemCores(), g_paths[0], g_paths[1], g_paths[2], g_paths[3],
+                    sh->nLookup, sh->maxDistSquared, (int)sh->finalGather);
             fclose(f); i += 1;
         }
         else if (op == "--render") { renderer->Render(scene); }

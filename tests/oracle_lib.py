@@ -134,3 +134,52 @@ def shoot(scene, n_wanted, stepsize, integrator_stepsize, max_photon_depth=5, se
         res["alpha"] = np.zeros((0, A.NSPEC), np.float32); res["ids"] = np.zeros(0, np.uint64)
     lib().pvo_photons_free(C.byref(out))
     return res
+
+
+class Maps(C.Structure):
+    _fields_ = [("cls", Photons * 5), ("nshot", C.c_uint64), ("blocks", C.c_uint64), ("n_caustic_paths", C.c_uint64),
+                ("n_indirect_paths", C.c_uint64), ("n_direct_paths", C.c_uint64), ("n_volume_paths", C.c_uint64)]
+
+
+MAP_NAMES = ("volume", "caustic", "indirect", "direct", "radiance")
+
+
+def shoot_maps(scene, n_volume, n_caustic, n_indirect, final_gather, stepsize, integrator_stepsize, max_photon_depth=5, seed=0,
+               rng_mode=PHILOX, max_paths=0):
+    """pvo_shoot_maps: all photon maps of one PhotonShootingTask (core/photonshooter.cpp:232-357)."""
+    prm = A.ShootParams(stepsize, integrator_stepsize, max_photon_depth, seed, 0, 1, max_paths, 0.0)
+    out = Maps()
+    d = scene.desc()
+    rc = lib().pvo_shoot_maps(C.byref(d), C.c_uint64(n_volume), C.c_uint64(n_caustic), C.c_uint64(n_indirect), C.c_int(int(final_gather)),
+                              C.byref(prm), C.c_int(rng_mode), C.byref(out))
+    res = dict(rc=rc, nshot=out.nshot, blocks=out.blocks, caustic_paths=out.n_caustic_paths, indirect_paths=out.n_indirect_paths,
+               direct_paths=out.n_direct_paths, volume_paths=out.n_volume_paths)
+    for k, name in enumerate(MAP_NAMES):
+        c = out.cls[k]; n = c.n
+        if n:
+            res[name] = dict(pos=np.ctypeslib.as_array(c.pos, shape=(n, 3)).copy(), wi=np.ctypeslib.as_array(c.wi, shape=(n, 3)).copy(),
+                             alpha=np.ctypeslib.as_array(c.alpha, shape=(n, A.NSPEC)).copy(), ids=np.ctypeslib.as_array(c.ids, shape=(n,)).copy())
+        else:
+            res[name] = dict(pos=np.zeros((0, 3), np.float32), wi=np.zeros((0, 3), np.float32), alpha=np.zeros((0, A.NSPEC), np.float32),
+                             ids=np.zeros(0, np.uint64))
+    lib().pvo_maps_free(C.byref(out))
+    return res
+
+
+def radiance(maps, counts, rp_pos, rp_n, rho_r, n_lookup, max_dist2):
+    """pvo_radiance: maps = [(pos, wi, alpha) or None] in the order direct, indirect, caustic; counts = path counts."""
+    trees, handles, wis, alphas = [], (C.c_void_p * 3)(), (C.c_void_p * 3)(), (C.c_void_p * 3)()
+    keep = []
+    for k, m in enumerate(maps):
+        if m is None or len(m[0]) == 0:
+            handles[k] = None; wis[k] = None; alphas[k] = None
+            continue
+        t = KdTree(m[0]); w = f32(m[1]); a = f32(m[2])
+        trees.append(t); keep += [w, a]
+        handles[k] = t.h; wis[k] = w.ctypes.data; alphas[k] = a.ctypes.data
+    cnt = (C.c_uint64 * 3)(*[int(c) for c in counts])
+    rp_pos = f32(rp_pos).reshape(-1, 3); rp_n = f32(rp_n).reshape(-1, 3); rho_r = f32(rho_r).reshape(-1, A.NSPEC)
+    n = len(rp_pos)
+    Lo = np.zeros((n, A.NSPEC), np.float32)
+    lib().pvo_radiance(handles, wis, alphas, cnt, _p(rp_pos), _p(rp_n), _p(rho_r), C.c_uint64(n), C.c_uint32(n_lookup), C.c_float(max_dist2), _p(Lo))
+    return Lo
