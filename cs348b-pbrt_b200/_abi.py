@@ -74,10 +74,25 @@ class GatherStats(C.Structure):
                 ("density_samples", C.c_uint64)]
 
 
+MAP_VOLUME, MAP_CAUSTIC, MAP_INDIRECT, MAP_DIRECT, MAP_RADIANCE = 0, 1, 2, 3, 4
+
+
+class MapsParams(C.Structure):
+    _fields_ = [("n_volume_wanted", C.c_uint64), ("n_caustic_wanted", C.c_uint64), ("n_indirect_wanted", C.c_uint64),
+                ("final_gather", C.c_int32)]
+
+
+class MapsStats(C.Structure):
+    _fields_ = [("nshot", C.c_uint64), ("blocks", C.c_uint64), ("n_caustic_paths", C.c_uint64), ("n_indirect_paths", C.c_uint64),
+                ("n_direct_paths", C.c_uint64), ("n_volume_paths", C.c_uint64), ("n", C.c_uint64 * 5),
+                ("replayed_blocks", C.c_uint64), ("shoot", ShootStats)]
+
+
 # every symbol include/pv.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_set_scene", "pv_set_photons",
     "pv_set_photons_dev", "pv_get_photons", "pv_get_photons_dev", "pv_photon_count", "pv_build", "pv_knn",
     "pv_intersect", "pv_occluded", "pv_transmittance", "pv_gather", "pv_gather_dev", "pv_lphoton",
     "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
+    "pv_shoot_maps", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons",
 ]

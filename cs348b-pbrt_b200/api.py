@@ -137,6 +137,41 @@ class PhotonVolume:
             self.build()
         return st
 
+    # ---- PhotonShooter::Preprocess with the surface maps on (core/photonshooter.cpp:147-189, 457-526) ----
+    def PreprocessMaps(self, n_volume_wanted, n_caustic_wanted, n_indirect_wanted, final_gather, stepsize=0.1, max_photon_depth=5,
+                       max_paths=0, integrator_stepsize=None):
+        prm = A.ShootParams(float(stepsize), float(self.stepsize if integrator_stepsize is None else integrator_stepsize),
+                            int(max_photon_depth), self.seed, 0, 1, max_paths, 0.0)
+        mp = A.MapsParams(int(n_volume_wanted), int(n_caustic_wanted), int(n_indirect_wanted), 1 if final_gather else 0)
+        st = A.MapsStats()
+        self._chk(self.lib.pv_shoot_maps(self.ctx, C.byref(mp), C.byref(prm), C.byref(st)))
+        return st
+
+    def get_map_photons(self, which, capacity=None):
+        n = C.c_uint64(0)
+        self._chk(self.lib.pv_get_map_photons(self.ctx, C.c_int(which), None, None, None, None, C.c_uint64(1 << 62), C.byref(n)))
+        n = n.value if capacity is None else min(n.value, capacity)
+        pos = np.zeros((n, 3), np.float32); wi = np.zeros((n, 3), np.float32)
+        alpha = np.zeros((n, A.NSPEC), np.float32); ids = np.zeros(n, np.uint64)
+        got = C.c_uint64(0)
+        self._chk(self.lib.pv_get_map_photons(self.ctx, C.c_int(which), _vp(pos), _vp(wi), _vp(alpha), _vp(ids), C.c_uint64(n), C.byref(got)))
+        return pos, wi, alpha, ids
+
+    def set_map_photons(self, which, pos, wi, alpha):
+        pos, wi, alpha = _f32(pos), _f32(wi), _f32(alpha)
+        self._chk(self.lib.pv_set_map_photons(self.ctx, C.c_int(which), _vp(pos), _vp(wi), _vp(alpha), C.c_uint64(pos.size // 3)))
+
+    def RadiancePhotons(self, n_lookup, max_dist2, path_counts=None):
+        """ComputeRadianceTask (core/photonshooter.cpp:359-395): Lo of every radiance photon.  path_counts = (nDirectPaths,
+        nIndirectPaths, nCausticPaths) or None for those of the last PreprocessMaps."""
+        n = C.c_uint64(0)
+        self._chk(self.lib.pv_get_map_photons(self.ctx, C.c_int(A.MAP_RADIANCE), None, None, None, None, C.c_uint64(1 << 62), C.byref(n)))
+        Lo = np.zeros((n.value, A.NSPEC), np.float32)
+        pc = (C.c_uint64 * 3)(*[int(c) for c in path_counts]) if path_counts is not None else None
+        got = C.c_uint64(0)
+        self._chk(self.lib.pv_radiance_photons(self.ctx, C.c_uint32(n_lookup), C.c_float(max_dist2), pc, _vp(Lo), C.c_uint64(n.value), C.byref(got)))
+        return Lo
+
     # ---- KdTree::Lookup --------------------------------------------------
     def Lookup(self, pts, k=None, r2=None):
         pts = _f32(pts).reshape(-1, 3); n = len(pts)

@@ -63,6 +63,8 @@ void pv_destroy(pv_ctx *ctx) {
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
                     ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
+    if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -429,6 +431,64 @@ int pv_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const 
 int pv_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
     LOCK(ctx);
     return pvi_shoot_finish(ctx, last_block);
+}
+
+// ---- surface photon maps
+int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params, pv_maps_stats *stats) {
+    LOCK(ctx);
+    if (!maps || !params) { ctx->err = "pv_shoot_maps: null params"; return PV_EINVAL; }
+    return pvi_shoot_maps(ctx, maps, params, stats);
+}
+int pv_get_map_photons(pv_ctx *ctx, int map, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t capacity, uint64_t *n) {
+    LOCK(ctx);
+    if (map == PV_MAP_VOLUME) return get_photons_impl(ctx, pos, wi, alpha, ids, capacity, n, cudaMemcpyDeviceToHost);
+    if (map < PV_MAP_CAUSTIC || map > PV_MAP_RADIANCE) { ctx->err = "pv_get_map_photons: bad map"; return PV_EINVAL; }
+    const PhotonSet &s = ctx->surf[map - 1];
+    uint64_t m = std::min<uint64_t>(capacity, s.n);
+    if (n) *n = m;
+    if (!m) return PV_OK;
+    if (pos) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(pos, s.pos, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (wi) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(wi, s.wi, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (alpha) {
+        int rc2 = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, m * PV_NSPEC * sizeof(float)); if (rc2) return rc2;
+        alpha_32_to_30_kernel<<<(unsigned)((m * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(s.alpha, (float *)ctx->io, m);
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(alpha, ctx->io, m * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (ids) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ids, s.ids, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi, const float *alpha, uint64_t n) {
+    LOCK(ctx);
+    if (map < PV_MAP_CAUSTIC || map > PV_MAP_RADIANCE) { ctx->err = "pv_set_map_photons: map must be PV_MAP_CAUSTIC..PV_MAP_RADIANCE"; return PV_EINVAL; }
+    if (n && (!pos || !wi || !alpha)) { ctx->err = "pv_set_map_photons: null plane"; return PV_EINVAL; }
+    PhotonSet &s = ctx->surf[map - 1];
+    s.n = 0; ctx->rad_valid = false;
+    int rc = pvi_reserve_set(ctx, &s, n); if (rc) return rc;
+    if (n) {
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(s.pos, pos, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(s.wi, wi, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io, alpha, n * PV_NSPEC * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        alpha_30_to_32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->io, s.alpha, n);
+        iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.ids, n);
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    s.n = n;
+    return PV_OK;
+}
+int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n) {
+    LOCK(ctx);
+    const uint64_t own[3] = {ctx->map_paths[2], ctx->map_paths[1], ctx->map_paths[0]};      // direct, indirect, caustic
+    int rc = pvi_radiance(ctx, n_lookup, max_dist2, path_counts ? path_counts : own); if (rc) return rc;
+    uint64_t m = std::min<uint64_t>(capacity, ctx->surf[3].n);
+    if (n) *n = m;
+    if (!m || !Lo) return PV_OK;
+    rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, m * PV_NSPEC * sizeof(float)); if (rc) return rc;
+    alpha_32_to_30_kernel<<<(unsigned)((m * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(ctx->rad_Lo, (float *)ctx->io, m);
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(Lo, ctx->io, m * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
 }
 
 }  // extern "C"

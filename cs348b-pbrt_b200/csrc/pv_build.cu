@@ -363,7 +363,7 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     {
         int blocks = (int)std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * 16);
         gather_records_kernel<<<blocks, 256, 0, ctx->stream>>>(svals, n, ctx->d_pos, ctx->d_wi, ctx->d_alpha, ctx->m_pos4, ctx->m_wi4,
-                                                             ctx->m_alpha32, ctx->m_orig, ctx->has_scene ? ctx->dscene : nullptr);
+                                                             ctx->m_alpha32, ctx->m_orig, ctx->has_scene && ctx->build_gate ? ctx->dscene : nullptr);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     // 5. cell table

@@ -24,6 +24,13 @@ struct GridParams {
     float one_shell_r;      // radius up to which the 3x3x3 block of an in-grid query is exhaustive
 };
 
+// a photon set in deposit order (same SoA planes as the context's main set)
+struct PhotonSet {
+    float *pos = nullptr, *wi = nullptr, *alpha = nullptr;   // pos[3n], wi[3n], alpha[32n]
+    uint64_t *ids = nullptr;
+    uint64_t n = 0, cap = 0;
+};
+
 struct pv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -42,6 +49,13 @@ struct pv_ctx {
     float *d_pos = nullptr, *d_wi = nullptr, *d_alpha = nullptr;
     uint64_t *d_ids = nullptr;
     uint64_t n_photons = 0, cap_photons = 0;
+
+    // surface maps of the shooter (core/photonshooter.cpp:147-189): caustic, indirect, direct photons and radiance-photon
+    // sites (wi plane = faceforwarded normal, alpha plane = rho_r), indexed by PV_MAP_* - 1; Lo of the radiance photons
+    PhotonSet surf[4];
+    float *rad_Lo = nullptr; uint64_t rad_Lo_cap = 0; bool rad_valid = false;
+    uint64_t map_paths[4] = {0, 0, 0, 0};          // nCausticPaths, nIndirectPaths, nDirectPaths, nVolumePaths
+    bool build_gate = true;                        // pv_build folds the medium's extent gate into alpha (volume photons only)
 
     // the map: photons sorted by cell key
     float4 *m_pos4 = nullptr;      // x, y, z, sorted position (bits)
@@ -106,3 +120,8 @@ int pvi_reserve_photons(pv_ctx *ctx, uint64_t n);
 int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats);
 int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block);
 int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm, pv_shoot_stats *stats);
+int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm, pv_maps_stats *out);
+int pvi_reserve_set(pv_ctx *ctx, PhotonSet *s, uint64_t n);
+void pvi_free_set(PhotonSet *s);
+// pv_gather.cu
+int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t counts[3]);

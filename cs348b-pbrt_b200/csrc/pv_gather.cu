@@ -662,6 +662,50 @@ __global__ void __launch_bounds__(GW_THREADS) lphoton_kernel(MapView m, const De
     }
 }
 
+// EPhoton (core/photonshooter.cpp:17-35) for every radiance-photon site against ONE surface map: the n_lookup nearest
+// photons within max_dist2 (the same lookup as the volume estimate), alpha summed over those arriving on the normal's
+// side, divided by path count * md2 * pi where md2 is the search radius^2 as KdTree::Lookup leaves it (the heap's
+// largest distance once n_lookup photons were found, else max_dist2).  Accumulates into E32 (32 floats per site).
+__global__ void __launch_bounds__(GW_THREADS) ephoton_kernel(MapView m, const float *__restrict__ rp_pos, const float *__restrict__ rp_n,
+                                                            const float *__restrict__ rho32, uint64_t n, uint32_t k, float r2, float count,
+                                                            uint32_t cap, float *__restrict__ E32, unsigned long long *counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, cap, warp, lane);
+    const float r = __fsqrt_rn(r2);
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1ull);
+        q = __shfl_sync(PV_FULL, q, 0);
+        if (q >= n) break;
+        // `if (!rho_r.IsBlack())` (:371)
+        if (__ballot_sync(PV_FULL, lane < PV_NSPEC && rho32[q * 32 + lane] != 0.f) == 0) continue;
+        const v3 p = V3(rp_pos[3 * q], rp_pos[3 * q + 1], rp_pos[3 * q + 2]), nn = V3(rp_n[3 * q], rp_n[3 * q + 1], rp_n[3 * q + 2]);
+        const uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, false, nullptr);
+        __syncwarp();
+        if (cnt) {
+            float mx = 0.f;
+            for (uint32_t e = lane; e < cnt; e += 32) mx = fmaxf(mx, __uint_as_float(b.ent[e].x));
+            mx = warp_max(mx);
+            const float md2 = cnt == k ? mx : r2;
+            float acc = 0.f;
+            for (uint32_t e = 0; e < cnt; ++e) {
+                const uint32_t sp = b.ent[e].y;
+                const float4 wv = __ldg(m.wi4 + sp);
+                if (nn.x * wv.x + nn.y * wv.y + nn.z * wv.z > 0.f) acc += __ldg(m.alpha32 + (size_t)sp * 32 + lane);
+            }
+            const float den = (float)((double)(count * md2) * 3.14159265358979323846);          // count * md2 * M_PI
+            E32[q * 32 + lane] += __fdiv_rn(acc, den);
+        }
+        __syncwarp();
+    }
+}
+// rp.Lo += INV_PI * rho_r * E (:379)
+__global__ void radiance_lo_kernel(const float *__restrict__ rho32, const float *__restrict__ E32, uint64_t n, float *__restrict__ Lo32) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * 32) Lo32[i] = (PV_INV_PI_F * rho32[i]) * E32[i];
+}
+
 // RainbowVolume::rainbowReflection (volumes/rainbow.cpp:41-78) for bin `lane`
 __device__ __forceinline__ float lerp_or_zero(float x, float x0, float x1, float y0, float y1) {
     if (x < x0 || x1 < x) return 0.f;
@@ -855,6 +899,59 @@ int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, u
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
     lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(map_view(ctx), ctx->dscene, d_pts, d_w, n, nused, maxdist, cap, d_L, ctx->d_counters);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+// ComputeRadianceTask::Run (core/photonshooter.cpp:359-395) for all radiance-photon sites of the context: one grid build and
+// one ephoton_kernel launch per surface map, in the reference's summation order direct, indirect, caustic.
+int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t counts[3]) {
+    PhotonSet &rp = ctx->surf[3];
+    ctx->rad_valid = false;
+    const uint64_t n = rp.n;
+    if (!(max_dist2 > 0.f) || n_lookup == 0) { ctx->err = "pv_radiance_photons: n_lookup and max_dist2 must be > 0"; return PV_EINVAL; }
+    if (n == 0) { ctx->rad_valid = true; return PV_OK; }
+    if (ctx->rad_Lo_cap < n) {
+        if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
+        ctx->rad_Lo = nullptr; ctx->rad_Lo_cap = 0;
+        PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->rad_Lo, n * 32 * sizeof(float)));
+        ctx->rad_Lo_cap = n;
+    }
+    int rc = PV_OK;
+    float *E32 = ctx->rad_Lo;                             // E accumulates in place (pv_build uses the io buffers), Lo = INV_PI * rho_r * E at the end
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(E32, 0, n * 32 * sizeof(float), ctx->stream));
+    const int order[3] = {2, 1, 0};                       // ctx->surf index of direct, indirect, caustic
+    const float maxdist = sqrtf(max_dist2);
+    auto swap_main = [&](PhotonSet &s) {
+        std::swap(ctx->d_pos, s.pos); std::swap(ctx->d_wi, s.wi); std::swap(ctx->d_alpha, s.alpha); std::swap(ctx->d_ids, s.ids);
+        std::swap(ctx->n_photons, s.n); std::swap(ctx->cap_photons, s.cap);
+    };
+    for (int k = 0; k < 3 && rc == PV_OK; ++k) {
+        PhotonSet &s = ctx->surf[order[k]];
+        if (s.n == 0 || counts[k] == 0) continue;
+        swap_main(s);
+        ctx->build_gate = false;                          // surface photons are not gated by the medium's extent
+        rc = pvi_build(ctx, maxdist, n_lookup);
+        ctx->build_gate = true;
+        if (rc == PV_OK) {
+            uint32_t cap = lookup_cap(n_lookup);
+            int blocks; size_t smem;
+            rc = launch_cfg(ctx, ephoton_kernel, cap, &blocks, &smem);
+            if (rc == PV_OK) {
+                cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream);
+                MapView m = map_view(ctx); m.need_wi = 1;
+                ephoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(m, rp.pos, rp.wi, rp.alpha, n, n_lookup, max_dist2, (float)(int)counts[k], cap, E32,
+                                                                        ctx->d_counters);
+                if (cudaGetLastError() != cudaSuccess) { ctx->err = "ephoton_kernel launch failed"; rc = PV_ECUDA; }
+                cudaStreamSynchronize(ctx->stream);
+            }
+        }
+        swap_main(s);
+        ctx->built = false;
+    }
+    if (rc) return rc;
+    radiance_lo_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(rp.alpha, E32, n, ctx->rad_Lo);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->rad_valid = true;
     return PV_OK;
 }
 // Li for rays [0, n): march records first (pv_march.cu), then the gather kernel.  Rays are taken in slices so that the

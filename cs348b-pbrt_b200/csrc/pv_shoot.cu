@@ -1,5 +1,7 @@
 // pv_shoot.cu -- photon shooting (K1-K3): PhotonShootingTask::Run / followPhoton
-// (core/photonshooter.cpp:47-357), volume-photon branch, as one persistent-thread sm_100a kernel.
+// (core/photonshooter.cpp:47-357) as one persistent-thread sm_100a kernel.  Two instantiations: the volume-photon
+// branch alone (surface maps off: diffuse bounces end the path, nothing but volume photons is stored) and the
+// pass with the surface maps on (caustic / indirect / direct deposits, radiance-photon sites, :147-189).
 //
 // Each thread is a small state machine {NEWPATH, TRACE, SURFACE}; all lanes of a warp meet at the head of the
 // same loop every iteration (path regeneration happens in-loop), so divergence is confined to one iteration.
@@ -41,9 +43,15 @@ struct ShootArgs {
     uint32_t perm[41];              // PermutedHalton tables of task 0 (RNG(31*0)), montecarlo.cpp:380-397
     float *pos, *wi, *alpha32; uint64_t *ids;
     unsigned long long *n_out; uint64_t cap;
-    uint32_t *block_counts;
-    unsigned long long *work, *stats;     // stats: nodes, tris, density samples, segments, overflows, paths
+    uint32_t *block_counts;               // [class][block of the wave]
+    uint32_t wave_blocks;                 // row length of block_counts
+    uint32_t flags;                       // SF_*: the reference's per-task done flags, constant over a wave
+    unsigned long long *work, *stats;     // stats: nodes, tris, density samples, segments, overflows, paths, first-hit scatters
 };
+// !causticDone, !indirectDone, volumeDone, finalGather (photonshooter.cpp:239-241, :411)
+enum { SF_WANT_CAUSTIC = 1, SF_WANT_INDIRECT = 2, SF_VOLUME_DONE = 4, SF_FINAL_GATHER = 8 };
+// photon classes: the top 4 bits of a photon id
+enum { PC_VOLUME = 0, PC_CAUSTIC = 1, PC_INDIRECT = 2, PC_DIRECT = 3, PC_RADIANCE = 4, PC_COUNT = 5 };
 
 __device__ __noinline__ uint4 path_philox_block(uint32_t c0, uint32_t c1, uint32_t j, uint32_t k0, uint32_t k1) {
     uint32_t out[4];
@@ -72,7 +80,36 @@ struct PathRng {
         pos++;
         return pv_u32_to_float(v);
     }
+    // discard n draws (BSDF::rho's stratified samples, which a Lambertian BRDF never reads)
+    __device__ __forceinline__ void skip(uint32_t n) {
+        const uint32_t consumed = j * 4 - (4 - pos) + n;
+        const uint32_t q = consumed >> 2, r = consumed & 3;
+        if (r == 0) { j = q; pos = 4; }
+        else { const uint4 b = path_philox_block(c0, c1, q, k0, k1); buf[0] = b.x; buf[1] = b.y; buf[2] = b.z; buf[3] = b.w; j = q + 1; pos = r; }
+    }
 };
+
+// Append one photon of class `cls`: one atomicAdd per coalesced group (warp-aggregated), alpha as one 128-byte line.
+// Volume photons are divided by nshot of their block at deposit time (photonshooter.cpp:333); surface photons are not.
+__device__ __forceinline__ void deposit_photon(const ShootArgs &a, uint32_t cls, uint64_t gblock, uint64_t path, uint32_t dep_seq, v3 p, v3 w,
+                                               const float *alpha, float fn) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long slot = 0;
+    if (g.thread_rank() == 0) slot = atomicAdd(a.n_out, (unsigned long long)g.size());
+    slot = g.shfl(slot, 0) + g.thread_rank();
+    atomicAdd(&a.block_counts[cls * a.wave_blocks + (uint32_t)(gblock - a.first_block)], 1u);
+    if (slot < a.cap) {
+        a.pos[3 * slot] = p.x; a.pos[3 * slot + 1] = p.y; a.pos[3 * slot + 2] = p.z;
+        a.wi[3 * slot] = w.x; a.wi[3 * slot + 1] = w.y; a.wi[3 * slot + 2] = w.z;
+        float4 *dst = reinterpret_cast<float4 *>(a.alpha32 + 32 * slot);
+#pragma unroll 1
+        for (int q = 0; q < 7; ++q)
+            dst[q] = make_float4(__fdiv_rn(alpha[4 * q], fn), __fdiv_rn(alpha[4 * q + 1], fn),
+                                 __fdiv_rn(alpha[4 * q + 2], fn), __fdiv_rn(alpha[4 * q + 3], fn));
+        dst[7] = make_float4(__fdiv_rn(alpha[28], fn), __fdiv_rn(alpha[29], fn), 0.f, 0.f);
+        a.ids[slot] = ((uint64_t)cls << 60) | (path << 16) | (uint64_t)(dep_seq & 0xffffu);
+    }
+}
 
 __device__ __forceinline__ v3 uniform_sample_sphere(float u1, float u2) {       // core/montecarlo.cpp:283-290
     float z = 1.f - 2.f * u1;
@@ -142,6 +179,7 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
 #ifndef SH_MIN_CTAS
 #define SH_MIN_CTAS 8                // 32 warps/SM at 64 registers: latency-bound on density taps, the spills cost less than the occupancy gains (measured 4: 40.9 ms, 6: 36.1 ms, 8: 35.2 ms)
 #endif
+template <bool SURF>
 __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
     __shared__ uint32_t s_perm[41];
@@ -319,28 +357,17 @@ SH_UNROLL_BINS
                         ys = __fdiv_rn(ys * 300.f, 106.856895f * (float)PV_NSPEC); ya = __fdiv_rn(ya * 300.f, 106.856895f * (float)PV_NSPEC);
                         bool scatter = rng.next() > __fdiv_rn(ys, ya + ys);     // Q1 (photonshooter.cpp:88)
                         if (!scatter) pop = true;
-                        else {
+                        else if (SURF && (a.flags & SF_VOLUME_DONE)) {
+                            // `if (scatter && !volumeDone)` (:96): with the volume map full the event is ignored and the
+                            // surface code runs with the unscattered ray
+                            state = ST_SURFACE; cur.loop_i = -1;
+                            continue;
+                        } else {
                             if (cur.nI > 1) {
                                 // ---- deposit (photonshooter.cpp:98-102), normalised by nshot of its block (:333)
-                                cg::coalesced_group g = cg::coalesced_threads();
-                                unsigned long long slot = 0;
-                                if (g.thread_rank() == 0) slot = atomicAdd(a.n_out, (unsigned long long)g.size());
-                                slot = g.shfl(slot, 0) + g.thread_rank();
-                                atomicAdd(&a.block_counts[(uint32_t)(gblock - a.first_block)], 1u);
-                                if (slot < a.cap) {
-                                    const float fn = (float)(gblock * SH_BLOCK);
-                                    a.pos[3 * slot] = pt.x; a.pos[3 * slot + 1] = pt.y; a.pos[3 * slot + 2] = pt.z;
-                                    a.wi[3 * slot] = rnd.x; a.wi[3 * slot + 1] = rnd.y; a.wi[3 * slot + 2] = rnd.z;
-                                    float4 *dst = reinterpret_cast<float4 *>(a.alpha32 + 32 * slot);
-SH_UNROLL_BINS
-                                    for (int q = 0; q < 7; ++q)
-                                        dst[q] = make_float4(__fdiv_rn(cur.alpha[4 * q], fn), __fdiv_rn(cur.alpha[4 * q + 1], fn),
-                                                             __fdiv_rn(cur.alpha[4 * q + 2], fn), __fdiv_rn(cur.alpha[4 * q + 3], fn));
-                                    dst[7] = make_float4(__fdiv_rn(cur.alpha[28], fn), __fdiv_rn(cur.alpha[29], fn), 0.f, 0.f);
-                                    a.ids[slot] = (path << 16) | (uint64_t)(dep_seq & 0xffffu);
-                                }
+                                deposit_photon(a, PC_VOLUME, gblock, path, dep_seq, pt, rnd, cur.alpha, (float)(gblock * SH_BLOCK));
                                 dep_seq++;
-                            }
+                            } else if (SURF) atomicAdd(&a.block_counts[PC_COUNT * a.wave_blocks + (uint32_t)(gblock - a.first_block)], 1u);   // shooter->nVolumePaths++ (:104)
                             float u1 = rng.next(), u2 = rng.next();
                             v3 dir = uniform_sample_sphere(u1, u2);
                             const float pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
@@ -374,6 +401,36 @@ SH_UNROLL_BINS
 SH_UNROLL_BINS
                 for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] *= expf(-(s_st[b] * s));
                 cur.loop_i = 0;
+                if (SURF) {
+                    // ---- surface deposits (photonshooter.cpp:147-189).  hasNonSpecular == matte with a non-black Kd
+                    // (materials/matte.cpp:55); glass has only specular components.
+                    const pv_material &dm = sc.mats[sc.prim_mat[cur.prim]];
+                    bool nonspec = false;
+                    if (dm.type == PV_MAT_MATTE) {
+SH_UNROLL_BINS
+                        for (int b = 0; b < PV_NSPEC; ++b) nonspec = nonspec || dm.kd[b] != 0.f;
+                    }
+                    if (nonspec) {
+                        int cls = -1;
+                        if (cur.spec && cur.nI > 1) { if (a.flags & SF_WANT_CAUSTIC) cls = PC_CAUSTIC; }
+                        else if (cur.nI == 1 && (a.flags & SF_WANT_INDIRECT) && (a.flags & SF_FINAL_GATHER)) cls = PC_DIRECT;
+                        else if (cur.nI > 1 && (a.flags & SF_WANT_INDIRECT)) cls = PC_INDIRECT;
+                        if (cls >= 0) {
+                            const v3 hp = V3(cur.ip[0], cur.ip[1], cur.ip[2]);
+                            deposit_photon(a, (uint32_t)cls, gblock, path, dep_seq, hp, -d, cur.alpha, 1.f);
+                            dep_seq++;
+                            // radiance-photon site (:178-188): p, Faceforward(n, -d), rho_r = Kd (Lambertian::rho), rho_t = 0;
+                            // the two BSDF::rho calls draw 2 x 2 x StratifiedSample2D(6 x 6) = 288 floats
+                            if ((a.flags & SF_FINAL_GATHER) && rng.next() < .125f) {
+                                v3 rn = V3(cur.inn[0], cur.inn[1], cur.inn[2]);
+                                if (vdot(rn, -d) < 0.f) rn = -rn;
+                                deposit_photon(a, PC_RADIANCE, gblock, path, dep_seq, hp, rn, dm.kd, 1.f);
+                                dep_seq++;
+                                rng.skip(288);
+                            }
+                        }
+                    }
+                }
                 if (cur.nI >= a.max_depth) pop = true;
             }
             if (!pop) {
@@ -401,7 +458,34 @@ SH_UNROLL_BINS
                         if (pdf != 0.f) {
                             v3 wiW = V3(sn.x * wil.x + tn.x * wil.y + nn.x * wil.z, sn.y * wil.x + tn.y * wil.y + nn.y * wil.z,
                                         sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
-                            if (vdot(wiW, nn) * vdot(wo, nn) > 0.f) rng.next();       // continueProb draw
+                            if (vdot(wiW, nn) * vdot(wo, nn) > 0.f) {
+                                if (!SURF) rng.next();                              // continueProb draw
+                                else {
+                                    // anew = alpha * f * |wi.n| / pdf, f = Kd / pi; Russian roulette on y(anew) / y(alpha) (:204-213)
+                                    const float adn = fabsf(vdot(wiW, nn));
+                                    float ynew = 0.f, yold = 0.f;
+SH_UNROLL_BINS
+                                    for (int b = 0; b < PV_NSPEC; ++b) {
+                                        const float an = __fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf);
+                                        ynew += s_cie[b] * an; yold += s_cie[b] * cur.alpha[b];
+                                    }
+                                    ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
+                                    const float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
+                                    // specularPath &= false, then `indirectDone && !specularPath` ends the path (:216-219)
+                                    if (!(rng.next() > continueProb) && (a.flags & SF_WANT_INDIRECT)) {
+SH_UNROLL_BINS
+                                        for (int b = 0; b < PV_NSPEC; ++b)
+                                            cur.alpha[b] = __fdiv_rn(__fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf), continueProb);
+                                        cur.spec = 0;
+                                        cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
+                                        cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
+                                        cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
+                                        // the loop over `spectrums` has one entry here (no transmission, no split): a tail call
+                                        state = ST_TRACE;
+                                        continue;
+                                    }
+                                }
+                            }
                         }
                     }
                     pop = true;
@@ -475,7 +559,7 @@ SH_UNROLL_BINS
                         ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
                         float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
                         if (rng.next() > continueProb) continue;
-                        if (!cur.spec) continue;                                // indirectDone && !specularPath
+                        if (!cur.spec && !(SURF && (a.flags & SF_WANT_INDIRECT))) continue;   // indirectDone && !specularPath
                         // spawn the child; this frame resumes at loop_i afterwards
                         if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
 SH_UNROLL_BINS
@@ -536,26 +620,31 @@ static void halton_tables_task0(uint32_t perm[41]) {
     }
 }
 
-int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats) {
+// One wave of blocks.  surf_flags < 0: the volume-only kernel, counts[n_blocks].  Otherwise the all-maps kernel with the
+// done flags SF_* held constant over the wave, counts[PC_COUNT + 1][n_blocks] (last row: first-hit scatter events, :104).
+static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, int surf_flags, uint32_t *counts,
+                      pv_shoot_stats *stats) {
+    const bool surf = surf_flags >= 0;
+    const uint32_t n_cls = surf ? PC_COUNT + 1 : 1;
     if (!ctx->has_scene || ctx->hscene.med.type == PV_MEDIUM_NONE || ctx->hscene.n_lights == 0) {
         ctx->err = "pv_shoot: scene needs a medium and at least one light"; return PV_ESTATE;
     }
     if (first_block < 1 || prm->world < 1 || prm->rank >= prm->world) { ctx->err = "pv_shoot: bad block / rank arguments"; return PV_EINVAL; }
     if (!(prm->stepsize > 0.f) || !(prm->integrator_stepsize > 0.f)) { ctx->err = "pv_shoot: step sizes must be > 0"; return PV_EINVAL; }
-    if (first_block == 1) { ctx->n_photons = 0; ctx->built = false; }
+    if (first_block == 1 && !surf) { ctx->n_photons = 0; ctx->built = false; }
     if (n_blocks == 0) return PV_OK;
     // blocks of this rank inside the wave: b with (b - 1) % world == rank
     uint64_t b_start = first_block + ((prm->rank + prm->world - ((first_block - 1) % prm->world)) % prm->world);
     uint64_t b_end = first_block + n_blocks;              // exclusive
     uint32_t n_local = b_start < b_end ? (uint32_t)((b_end - b_start + prm->world - 1) / prm->world) : 0;
-    memset(counts, 0, sizeof(uint32_t) * n_blocks);
+    memset(counts, 0, sizeof(uint32_t) * n_blocks * n_cls);
     if (n_local == 0) return PV_OK;
 
-    int rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, sizeof(uint32_t) * (size_t)n_blocks + 64); if (rc) return rc;
+    int rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, sizeof(uint32_t) * (size_t)n_blocks * n_cls + 64); if (rc) return rc;
     uint32_t *d_counts = (uint32_t *)ctx->io2;
     unsigned long long *d_nout = ctx->d_counters + 1, *d_work = ctx->d_counters + 2, *d_stats = ctx->d_counters + 8;
     // first guess of the capacity: 8% deposit yield on top of what is already stored
-    uint64_t want_cap = ctx->n_photons + (uint64_t)((double)n_local * SH_BLOCK * 0.08) + 65536;
+    uint64_t want_cap = ctx->n_photons + (uint64_t)((double)n_local * SH_BLOCK * (surf ? 1.5 : 0.08)) + 65536;
     for (int attempt = 0; attempt < 3; ++attempt) {
         rc = pvi_reserve_photons(ctx, want_cap); if (rc) return rc;
         ShootArgs a;
@@ -565,24 +654,27 @@ int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const
         halton_tables_task0(a.perm);
         a.pos = ctx->d_pos; a.wi = ctx->d_wi; a.alpha32 = ctx->d_alpha; a.ids = ctx->d_ids;
         a.n_out = d_nout; a.cap = ctx->cap_photons; a.block_counts = d_counts; a.work = d_work; a.stats = d_stats;
+        a.wave_blocks = n_blocks; a.flags = surf ? (uint32_t)surf_flags : 0u;
         unsigned long long init_n = ctx->n_photons, zero = 0;
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_nout, &init_n, sizeof(init_n), cudaMemcpyHostToDevice, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_work, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks * n_cls, ctx->stream));
         int per_sm = 0;
-        PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel, SH_THREADS, 0));
+        if (surf) PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel<true>, SH_THREADS, 0));
+        else PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel<false>, SH_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         uint64_t total = (uint64_t)n_local * SH_BLOCK;
         int blocks = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (total + SH_THREADS - 1) / SH_THREADS);
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        shoot_kernel<<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
+        if (surf) shoot_kernel<true><<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
+        else shoot_kernel<false><<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         unsigned long long h_nout = 0, h_stats[8];
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(&h_nout, d_nout, sizeof(h_nout), cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
-        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * n_blocks * n_cls, cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
         if (h_nout > ctx->cap_photons) { want_cap = h_nout + 65536; continue; }      // too small: grow and replay the (deterministic) wave
         float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -597,10 +689,31 @@ int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const
     ctx->err = "pv_shoot: could not size the photon buffer";
     return PV_ENOMEM;
 }
+int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats) {
+    return shoot_wave(ctx, first_block, n_blocks, prm, -1, counts, stats);
+}
 
 __global__ void id_keys_kernel(const uint64_t *__restrict__ ids, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { keys[i] = ids[i]; vals[i] = (uint32_t)i; }
+}
+int pvi_reserve_set(pv_ctx *ctx, PhotonSet *s, uint64_t n) {
+    if (n <= s->cap) return PV_OK;
+    pvi_free_set(s);
+    uint64_t cap = std::max<uint64_t>(n, 1024);
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&s->pos, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&s->wi, cap * 3 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&s->alpha, cap * 32 * sizeof(float)));
+    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&s->ids, cap * sizeof(uint64_t)));
+    s->cap = cap;
+    return PV_OK;
+}
+void pvi_free_set(PhotonSet *s) {
+    if (s->pos) cudaFree(s->pos);
+    if (s->wi) cudaFree(s->wi);
+    if (s->alpha) cudaFree(s->alpha);
+    if (s->ids) cudaFree(s->ids);
+    *s = PhotonSet();
 }
 __global__ void permute_photons_kernel(const uint32_t *__restrict__ order, uint64_t n, const float *__restrict__ pos, const float *__restrict__ wi,
                                        const float *__restrict__ alpha, const uint64_t *__restrict__ ids, float *__restrict__ pos_o,
@@ -616,9 +729,12 @@ __global__ void permute_photons_kernel(const uint32_t *__restrict__ order, uint6
 
 // Drop photons of blocks > last_block and order the rest by id = (path index << 16 | deposit ordinal): the photon
 // set and its order then depend only on (scene, seed, target), not on thread scheduling or the number of ranks.
-int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
+// split: the ids carry a class in their top bits (pv_shoot_maps); class 0 stays the context's photon set, the others
+// move to ctx->surf[class - 1].
+static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split) {
     uint64_t n = ctx->n_photons;
     ctx->built = false;
+    if (split) for (int c = 0; c < 4; ++c) ctx->surf[c].n = 0;
     if (n == 0) return PV_OK;
     if (n > 0xFFFFFFF0ull) { ctx->err = "too many photons"; return PV_EINVAL; }
     size_t need = n * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 256;
@@ -636,17 +752,33 @@ int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
     rc = pvi_sort_pairs_u64(ctx, keys, vals, keys_tmp, vals_tmp, n, 64, &skeys, &svals); if (rc) return rc;
     (void)bits;
     // count survivors: ids <= (last_block * 4096) << 16 | 0xffff
-    uint64_t keep = n;
-    if (last_block) {
-        uint64_t limit = ((last_block * SH_BLOCK) << 16) | 0xffffull;
-        std::vector<uint64_t> probe(1);
-        uint64_t lo = 0, hi = n;                                  // upper_bound over the sorted keys (few D2H probes)
+    auto upper_bound = [&](uint64_t limit, uint64_t *out) -> int {  // first position with key > limit (few D2H probes)
+        uint64_t probe = 0, lo = 0, hi = n;
         while (lo < hi) {
             uint64_t mid = (lo + hi) / 2;
-            PV_CUDA_CHECK(ctx, cudaMemcpy(probe.data(), skeys + mid, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-            if (probe[0] <= limit) lo = mid + 1; else hi = mid;
+            PV_CUDA_CHECK(ctx, cudaMemcpy(&probe, skeys + mid, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            if (probe <= limit) lo = mid + 1; else hi = mid;
         }
-        keep = lo;
+        *out = lo;
+        return PV_OK;
+    };
+    const uint64_t path_limit = last_block ? (((last_block * SH_BLOCK) << 16) | 0xffffull) : ((1ull << 60) - 1);
+    uint64_t keep = n;
+    if (last_block || split) { rc = upper_bound(path_limit, &keep); if (rc) return rc; }
+    if (split) {
+        for (uint32_t c = 1; c < PC_COUNT; ++c) {
+            uint64_t lo = 0, hi = 0;
+            rc = upper_bound(((uint64_t)c << 60) - 1, &lo); if (rc) return rc;
+            rc = upper_bound(((uint64_t)c << 60) | path_limit, &hi); if (rc) return rc;
+            PhotonSet &ps = ctx->surf[c - 1];
+            rc = pvi_reserve_set(ctx, &ps, hi - lo); if (rc) return rc;
+            ps.n = hi - lo;
+            if (ps.n) {
+                permute_photons_kernel<<<(unsigned)((ps.n * 8 + 255) / 256), 256, 0, ctx->stream>>>(svals + lo, ps.n, ctx->d_pos, ctx->d_wi, ctx->d_alpha,
+                                                                                                  ctx->d_ids, ps.pos, ps.wi, ps.alpha, ps.ids);
+                PV_CUDA_CHECK(ctx, cudaGetLastError());
+            }
+        }
     }
     float *np, *nw, *na; uint64_t *ni;
     uint64_t cap = std::max<uint64_t>(keep, 1024);
@@ -664,6 +796,7 @@ int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
     ctx->d_pos = np; ctx->d_wi = nw; ctx->d_alpha = na; ctx->d_ids = ni; ctx->cap_photons = cap; ctx->n_photons = keep;
     return PV_OK;
 }
+int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) { return shoot_finish(ctx, last_block, false); }
 
 // Single-rank driver == PhotonShootingTask::Run's outer loop (photonshooter.cpp:245-356): waves of blocks until the
 // running photon count reaches the target at some block M; give-up rule of :285-299.
@@ -701,5 +834,96 @@ int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm_in, pv_
     if (rc == PV_OK) rc = pvi_shoot_finish(ctx, last);
     st.paths = last * SH_BLOCK; st.blocks = last; st.photons_local = ctx->n_photons;
     if (stats) *stats = st;
+    return rc;
+}
+
+// All photon maps in one pass == PhotonShootingTask::Run's outer loop for ONE task (photonshooter.cpp:245-356).  The
+// reference's done flags change how later paths behave (no more scattering in the medium once the volume map is full,
+// :96; diffuse bounces end the path once the indirect map is full, :218), and they change at block ends.  A wave of
+// blocks is traced with the flags held constant; the host then replays the reference's per-block bookkeeping over the
+// per-class counts, and if a flag flips at block M inside the wave, the wave is rolled back and traced again up to M
+// (it is deterministic), so that every later block sees the new flags.  Waves aim just short of the next expected flip.
+int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm_in, pv_maps_stats *out) {
+    pv_shoot_params prm = *prm_in;
+    pv_maps_stats ms; memset(&ms, 0, sizeof(ms));
+    if (prm.world != 1 || prm.rank != 0) { ctx->err = "pv_shoot_maps: single rank only"; return PV_EINVAL; }
+    const uint64_t wanted[3] = {mp->n_volume_wanted, mp->n_caustic_wanted, mp->n_indirect_wanted};     // by class id
+    bool done[3] = {wanted[0] == 0, wanted[1] == 0, wanted[2] == 0};
+    ctx->n_photons = 0; ctx->built = false; ctx->rad_valid = false;
+    for (int c = 0; c < 4; ++c) { ctx->surf[c].n = 0; ctx->map_paths[c] = 0; }
+    if (done[0] && done[1] && done[2]) { if (out) *out = ms; return PV_OK; }
+    const uint64_t max_paths = prm.max_paths ? prm.max_paths : ((uint64_t)1 << 40);
+    uint64_t block = 0, tot[PC_COUNT] = {0, 0, 0, 0, 0}, first_hits = 0;
+    uint64_t paths[4] = {0, 0, 0, 0};                       // caustic, indirect, direct, volume
+    uint32_t wave = 64;
+    std::vector<uint32_t> counts;
+    bool finished = false, aborted = false;
+    int rc = PV_OK;
+    auto unsuccessful = [](uint64_t needed, uint64_t found) { return found < needed && (found == 0 || found < SH_BLOCK / 1024); };
+    while (!finished) {
+        const int flags = (done[1] ? 0 : SF_WANT_CAUSTIC) | (done[2] ? 0 : SF_WANT_INDIRECT) | (done[0] ? SF_VOLUME_DONE : 0) |
+                          (mp->final_gather ? SF_FINAL_GATHER : 0);
+        const uint64_t n_before = ctx->n_photons, first = block + 1;
+        counts.assign((size_t)wave * (PC_COUNT + 1), 0);
+        rc = shoot_wave(ctx, first, wave, &prm, flags, counts.data(), &ms.shoot); if (rc) return rc;
+        bool flip = false;
+        uint32_t used = 0;
+        for (uint32_t i = 0; i < wave; ++i) {
+            // "Unable to store enough photons.  Giving up." over all three wanted counts (:285-299)
+            if (block * SH_BLOCK > 500000 && (unsuccessful(wanted[1], tot[1]) || unsuccessful(wanted[2], tot[2]) || unsuccessful(wanted[0], tot[0]))) {
+                aborted = true; finished = true; break;
+            }
+            block++; used++;
+            if (!done[2]) {                                  // :303-318
+                paths[1] += SH_BLOCK; tot[2] += counts[(size_t)PC_INDIRECT * wave + i];
+                paths[2] += SH_BLOCK; tot[3] += counts[(size_t)PC_DIRECT * wave + i];
+                if (tot[2] >= wanted[2]) { done[2] = true; flip = true; }
+            }
+            if (!done[1]) {                                  // :320-328
+                paths[0] += SH_BLOCK; tot[1] += counts[(size_t)PC_CAUSTIC * wave + i];
+                if (tot[1] >= wanted[1]) { done[1] = true; flip = true; }
+            }
+            if (!done[0]) {                                  // :330-341
+                paths[3] += SH_BLOCK; tot[0] += counts[(size_t)PC_VOLUME * wave + i];
+                if (tot[0] >= wanted[0]) { done[0] = true; flip = true; }
+            }
+            tot[4] += counts[(size_t)PC_RADIANCE * wave + i];
+            first_hits += counts[(size_t)PC_COUNT * wave + i];
+            if ((done[0] && done[1] && done[2]) || block * SH_BLOCK >= max_paths) { finished = true; break; }
+            if (flip) break;
+        }
+        if (aborted) break;
+        if (flip && !finished && used < wave) {
+            // roll the wave back and trace it again up to the block of the flip, with the flags it started with
+            ctx->n_photons = n_before;
+            counts.assign((size_t)used * (PC_COUNT + 1), 0);
+            rc = shoot_wave(ctx, first, used, &prm, flags, counts.data(), &ms.shoot); if (rc) return rc;
+            ms.replayed_blocks += used;
+        }
+        if (!finished) {
+            // next wave: 97% of the way to the nearest expected flip, from the yields seen so far
+            double nearest = 1e30;
+            for (int c = 0; c < 3; ++c)
+                if (!done[c]) {
+                    const double per_block = (double)tot[c] / (double)block;
+                    nearest = std::min(nearest, per_block > 0 ? (double)(wanted[c] - tot[c]) / per_block : 4.0 * (double)block);
+                }
+            wave = (uint32_t)std::min<double>(std::max<double>(nearest * 0.97, 16), 65536);
+            const uint64_t left = max_paths / SH_BLOCK > block ? max_paths / SH_BLOCK - block : 1;
+            wave = (uint32_t)std::min<uint64_t>(wave, left);
+        }
+    }
+    if (aborted) {
+        ctx->n_photons = 0;
+        for (int c = 0; c < 4; ++c) ctx->surf[c].n = 0;
+        ctx->err = "Unable to store enough photons.  Giving up.";
+        rc = PV_ENOPHOTONS;
+    } else rc = shoot_finish(ctx, block, true);
+    ms.nshot = block * SH_BLOCK; ms.blocks = block;
+    ms.n_caustic_paths = paths[0]; ms.n_indirect_paths = paths[1]; ms.n_direct_paths = paths[2]; ms.n_volume_paths = paths[3] + first_hits;
+    ms.shoot.paths = ms.nshot; ms.shoot.blocks = block; ms.shoot.photons_local = ctx->n_photons;
+    ms.n[0] = ctx->n_photons;
+    for (int c = 0; c < 4; ++c) { ms.n[c + 1] = ctx->surf[c].n; ctx->map_paths[c] = c == 3 ? ms.n_volume_paths : paths[c]; }
+    if (out) *out = ms;
     return rc;
 }

@@ -232,6 +232,48 @@ int pv_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks,
                     pv_shoot_stats *stats);
 int pv_shoot_finish(pv_ctx *ctx, uint64_t last_block);
 
+/* ---- PhotonShooter::Preprocess with the SURFACE photon maps on ----------
+ * followPhoton's surface branch (core/photonshooter.cpp:147-189): caustic / indirect / direct
+ * deposits and radiance-photon sites, the per-task done flags that change path behaviour at
+ * block ends (:239-241, :303-341), the give-up rule over all wanted counts (:285-299), then
+ * ComputeRadianceTask + EPhoton (:17-35, :359-395).  The reference's PhotonIntegrator keeps
+ * reading these maps as KdTree<Photon> / KdTree<RadiancePhoton> (integrators/photonmap.cpp:
+ * 159-164); the adapter fills them from pv_get_map_photons / pv_radiance_photons.            */
+enum { PV_MAP_VOLUME = 0, PV_MAP_CAUSTIC = 1, PV_MAP_INDIRECT = 2, PV_MAP_DIRECT = 3,
+       PV_MAP_RADIANCE = 4 };
+typedef struct pv_maps_params {
+    uint64_t n_volume_wanted, n_caustic_wanted, n_indirect_wanted;   /* photonshooter.cpp:529-533 */
+    int32_t  final_gather;       /* direct photons and radiance photons only with final gathering */
+} pv_maps_params;
+typedef struct pv_maps_stats {
+    uint64_t nshot, blocks;      /* light paths / 4096-path blocks of the whole pass               */
+    uint64_t n_caustic_paths, n_indirect_paths, n_direct_paths, n_volume_paths;  /* the divisors the
+                                    estimates use (:305,:313,:321,:331; n_volume_paths includes :104) */
+    uint64_t n[5];               /* photons kept per PV_MAP_* class                                */
+    uint64_t replayed_blocks;    /* blocks traced twice because a done flag flipped inside a wave   */
+    pv_shoot_stats shoot;
+} pv_maps_stats;
+/* One pass, single rank.  Afterwards the context's photon set (pv_get_photons, pv_build) is the
+ * volume map; the other classes are read with pv_get_map_photons.  Photons of every class are
+ * ordered by (light path, deposit ordinal): the order one reference task stores them in.
+ * ids = class << 60 | path index << 16 | deposit ordinal along the path.                         */
+int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params,
+                  pv_maps_stats *stats);
+/* SoA planes like pv_get_photons.  PV_MAP_RADIANCE: wi = faceforwarded normal, alpha = rho_r
+ * (rho_t == 0: only matte surfaces hold radiance photons on this path).                          */
+int pv_get_map_photons(pv_ctx *ctx, int map, float *pos, float *wi, float *alpha,
+                       uint64_t *ids, uint64_t capacity, uint64_t *n);
+/* Inject a class (golden sets): map in PV_MAP_CAUSTIC..PV_MAP_RADIANCE.                          */
+int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi,
+                       const float *alpha, uint64_t n);
+/* ComputeRadianceTask::Run for every radiance photon: Lo = INV_PI * rho_r * (E_direct +
+ * E_indirect + E_caustic), EPhoton = n_lookup nearest photons within max_dist2 facing the
+ * normal, over path count * final search radius^2 * pi.  path_counts = nDirectPaths,
+ * nIndirectPaths, nCausticPaths (NULL: the counts of the last pv_shoot_maps).  Builds a grid per
+ * class, so the volume map must be (re)built with pv_build afterwards.  Lo[30 * capacity].       */
+int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2,
+                        const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n);
+
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);
 

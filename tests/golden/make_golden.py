@@ -175,6 +175,7 @@ def main():
         g = sceneio.read_scene(os.path.join(HERE, "cornell_grid32.scn"))
         assert np.array_equal(g.density, dens), "density grid did not survive the text round trip"
         project_goldens(tmp)
+        surface_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -203,6 +204,48 @@ def project_goldens(tmp):
         np.save(os.path.join(HERE, name + "_ref.npy"), read_pfm(os.path.join(tmp, name + ".pfm")).astype(np.float16))
 
 
+def read_radiance(fn):
+    """PVRADP01 (oracle/ref_harness.cpp --dump-maps): p[3] n[3] Lo[30] rho_r[30] rho_t[30] per radiance photon."""
+    buf = open(fn, "rb").read()
+    assert buf[:8] == b"PVRADP01"
+    n = int(np.frombuffer(buf, np.uint64, 1, 8)[0])
+    r = np.frombuffer(buf, np.float32, 96 * n, 16).reshape(n, 96)
+    return dict(pos=r[:, 0:3].copy(), n=r[:, 3:6].copy(), Lo=r[:, 6:36].copy(), rho_r=r[:, 36:66].copy(), rho_t=r[:, 66:96].copy())
+
+
+# name -> (scene text, (volume, caustic, indirect) wanted, final gather, shooter step, integrator step)
+SURFACE_CASES = {
+    # every map on: glass wedge (no dispersion) under the light, matte walls, homogeneous medium
+    "cornell_surf": (lambda: scenes.cornell_surf_pbrt(nphotons=1500, caustic=800, indirect=2000), (1500, 800, 2000), True, 0.05, 0.05),
+    # dispersive wedge (Vn 2), caustic map finishes last, indirect first
+    "cornell_surf_disp": (lambda: scenes.cornell_surf_pbrt(vn=2.0, nphotons=2500, caustic=1500, indirect=600), (2500, 1500, 600), True, 0.05, 0.05),
+    # BASELINE config 1 with its shipped surface-integrator settings (caustic map + final gathering), reduced counts
+    "rainbow_surf": (lambda: scenes.volumescene_pbrt(nphotons=1500, caustic=1000, finalgather=True, xres=64, yres=64), (1500, 1000, 0), True, 0.1, 0.15),
+}
+
+
+def surface_goldens(tmp):
+    """the reference's own photon lists of ALL maps (one task => deterministic) and its radiance photons."""
+    for name, (text, wanted, fg, shoot_step, istep) in SURFACE_CASES.items():
+        f = os.path.join(tmp, name + ".pbrt"); open(f, "w").write(text())
+        prefix = os.path.join(tmp, name)
+        run(f, "--export-scene", os.path.join(HERE, name + ".scn"), "--shoot", "--dump-photons", prefix + ".volume", "--dump-maps", prefix,
+            "--stats", prefix + ".json")
+        st = json.load(open(prefix + ".json"))
+        out = {}
+        for k in ("volume", "caustic", "indirect", "direct"):
+            pos, wi, alpha = sceneio.read_photons(prefix + "." + k)
+            out[k + "_pos"], out[k + "_wi"], out[k + "_alpha"] = pos, wi, alpha
+        rad = read_radiance(prefix + ".radiance")
+        assert not rad["rho_t"].any()
+        out["rad_pos"], out["rad_n"], out["rad_Lo"], out["rad_rho_r"] = rad["pos"], rad["n"], rad["Lo"], rad["rho_r"]
+        out["counts"] = np.array([st["nshot"], st["caustic_paths"], st["indirect_paths"], st["direct_paths"], st["volume_paths"]], np.uint64)
+        out["params"] = np.array([wanted[0], wanted[1], wanted[2], int(fg), shoot_step, istep, st["nlookup"], st["maxdist2"]], np.float64)
+        print("  %s: nshot %d, volume %d caustic %d indirect %d direct %d radiance %d" % (
+            name, st["nshot"], len(out["volume_pos"]), len(out["caustic_pos"]), len(out["indirect_pos"]), len(out["direct_pos"]), len(rad["pos"])))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def read_pfm(path):
     with open(path, "rb") as f:
         kind = f.readline().strip()
@@ -213,7 +256,11 @@ def read_pfm(path):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "project":          # only the config-1 / config-4 goldens
+    if len(sys.argv) > 1 and sys.argv[1] == "surface":          # only the surface-map goldens
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            surface_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "project":          # only the config-1 / config-4 goldens
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             project_goldens(tmp_)

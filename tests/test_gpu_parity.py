@@ -260,3 +260,143 @@ def test_shooter_sharded_blocks_reproduce_single_rank(golden, pv_factory, pkg):
     assert np.array_equal(ids[order], i1)
     assert np.array_equal(np.concatenate([p[0] for p in parts])[order], p1)
     assert np.array_equal(np.concatenate([p[2] for p in parts])[order], a1)
+
+
+# ---- surface photon maps
+SURF_SCENES = ["cornell_surf", "cornell_surf_disp", "rainbow_surf"]
+MAP_KEYS = ("volume", "caustic", "indirect", "direct", "radiance")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_all_maps_vs_oracle_same_philox_stream(golden, pv_factory, pkg, name):
+    """pv_shoot_maps against the pinned oracle on the same per-path Philox streams: every class matched one to one on
+    (class, path, deposit ordinal), same nshot and per-map path counts (i.e. the done flags flipped at the same blocks)."""
+    g, scene = golden(name)
+    nv, nc, ni, fg, sstep, istep = g["params"][:6]
+    pv = pv_factory(stepsize=float(istep), seed=91)
+    pv.set_scene(scene)
+    st = pv.PreprocessMaps(int(nv), int(nc), int(ni), bool(fg), stepsize=float(sstep), max_photon_depth=5)
+    ref = O.shoot_maps(scene, int(nv), int(nc), int(ni), bool(fg), float(sstep), float(istep), seed=91, rng_mode=O.PHILOX)
+    assert ref["rc"] == 0
+    assert st.shoot.stack_overflows == 0
+    assert (st.nshot, st.n_caustic_paths, st.n_indirect_paths, st.n_direct_paths) == (ref["nshot"], ref["caustic_paths"], ref["indirect_paths"],
+                                                                                    ref["direct_paths"])
+    assert abs(int(st.n_volume_paths) - int(ref["volume_paths"])) <= 0.005 * ref["volume_paths"] + 2
+    for which, key in enumerate(MAP_KEYS):
+        pos, wi, alpha, ids = pv.get_map_photons(which)
+        r = ref[key]
+        assert len(ids) == int(st.n[which])
+        if len(r["ids"]) == 0:
+            assert len(ids) == 0, key
+            continue
+        assert np.all((ids >> np.uint64(60)) == which), key
+        assert np.all(np.diff(ids.astype(np.int64)) > 0), key              # ordered by (path, deposit ordinal)
+        common, ia, ib = np.intersect1d(ids, r["ids"], return_indices=True)
+        assert len(common) >= 0.995 * max(len(ids), len(r["ids"])), key
+        assert abs(len(ids) - len(r["ids"])) <= 0.005 * len(r["ids"]) + 2, key
+        dpos = np.abs(pos[ia] - r["pos"][ib]).max(axis=1)
+        assert np.quantile(dpos, 0.99) < 1e-4, key
+        ok = dpos < 1e-4
+        assert np.abs(wi[ia][ok] - r["wi"][ib][ok]).max() < 1e-4, key
+        assert relerr(alpha[ia][ok], r["alpha"][ib][ok]).max() < 1e-3, key
+
+
+def ephoton_rule(maps, counts, sites, normals, rho_r, k, r2):
+    """Brute-force EPhoton / ComputeRadianceTask with the rule the CUDA path states: the k smallest by (d2, photon index) among
+    d2 < r2, d2 in the reference's unfused fp32 ((dx*dx + dy*dy) + dz*dz).  Also returns the sites where some map has a TIE at
+    the k-th distance: there the reference's own result depends on its kd-tree traversal order (strict `<` in
+    KdTree::Lookup, heap ties by node address), so it is not a parity target."""
+    sites = np.asarray(sites, np.float32); n = len(sites)
+    E = np.zeros((n, 30), np.float64); tie = np.zeros(n, bool)
+    r2 = np.float32(r2)
+    for (pos, wi, alpha), count in zip(maps, counts):
+        if len(pos) == 0 or count == 0:
+            continue
+        pos = np.asarray(pos, np.float32)
+        d = sites[:, None, :] - pos[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]          # float32, same association
+        for i in range(n):
+            cand = np.nonzero(d2[i] < r2)[0]
+            if len(cand) == 0:
+                continue
+            order = cand[np.lexsort((cand, d2[i][cand]))]
+            md2 = r2
+            if len(order) >= k:
+                if len(order) > k and d2[i][order[k]] == d2[i][order[k - 1]]:
+                    tie[i] = True
+                order = order[:k]
+                md2 = d2[i][order].max()
+            facing = (np.asarray(wi, np.float32)[order] * normals[i]).sum(axis=1) > 0
+            den = np.float32(np.float64(np.float32(np.float32(count) * md2)) * np.pi)
+            E[i] += np.asarray(alpha, np.float64)[order][facing].sum(axis=0) / np.float64(den)
+    black = ~(np.asarray(rho_r) != 0).any(axis=1)
+    Lo = (np.float32(1.0 / np.pi) * np.asarray(rho_r, np.float64)) * E
+    Lo[black] = 0
+    return Lo, tie
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_radiance_photons_vs_reference(golden, pv_factory, pkg, name):
+    """pv_radiance_photons on the REFERENCE's own direct / indirect / caustic lists and radiance-photon sites (three grid builds +
+    EPhoton lookups on the GPU): Lo within 1e-4 of the reference's ComputeRadianceTask at every site whose n_lookup-nearest sets are
+    unique, and within 1e-4 of the brute-force rule (ties by photon index) everywhere.  Exact ties are real here: the 30
+    monochromatic children of a photon that a dispersive glass face REFLECTS all land on the same point."""
+    A = pkg._abi
+    g, scene = golden(name)
+    nlookup, md2 = int(g["params"][6]), float(g["params"][7])
+    nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+    pv = pv_factory()
+    pv.set_scene(scene)
+    for which, key in ((A.MAP_CAUSTIC, "caustic"), (A.MAP_INDIRECT, "indirect"), (A.MAP_DIRECT, "direct")):
+        pv.set_map_photons(which, g[key + "_pos"], g[key + "_wi"], g[key + "_alpha"])
+    pv.set_map_photons(A.MAP_RADIANCE, g["rad_pos"], g["rad_n"], g["rad_rho_r"])
+    maps = [(g[k + "_pos"], g[k + "_wi"], g[k + "_alpha"]) for k in ("direct", "indirect", "caustic")]
+    ref = g["rad_Lo"]
+    assert (ref > 0).any()
+    # (k = 8 would put md2 == 0 at sites where >= 8 reflected monochromatic photons coincide: the reference divides by zero there)
+    for k, r2 in ((nlookup, md2), (40, md2), (20, 0.25 * md2)):
+        got = pv.RadiancePhotons(k, r2, path_counts=(dp, ip, cp))
+        rule, tie = ephoton_rule(maps, (dp, ip, cp), g["rad_pos"], g["rad_n"], g["rad_rho_r"], k, r2)
+        # the reference itself for its own parameters, the pinned oracle (the reference's kd-tree order) for the others
+        want = ref if k == nlookup else O.radiance(maps, [dp, ip, cp], g["rad_pos"], g["rad_n"], g["rad_rho_r"], k, r2)
+        assert tie.mean() < 0.2, (k, tie.mean())
+        u = ~tie
+        assert relerr(got[u], want[u])[want[u] > 0].max() < 1e-4, k
+        assert np.array_equal(got[u] == 0, want[u] == 0), k
+        assert relerr(got, rule)[rule > 0].max() < 1e-4, k
+        assert np.array_equal(got == 0, rule == 0), k
+
+
+@pytest.mark.gpu
+def test_all_maps_with_surface_maps_off_is_the_volume_pass(golden, pv_factory):
+    g, scene = golden("cornell_homog")
+    pv = pv_factory(stepsize=0.05, seed=5); pv.set_scene(scene)
+    st = pv.Preprocess(1500, stepsize=0.05, build=False)
+    a = pv.get_photons()
+    pv2 = pv_factory(stepsize=0.05, seed=5); pv2.set_scene(scene)
+    st2 = pv2.PreprocessMaps(1500, 0, 0, True, stepsize=0.05)
+    b = pv2.get_photons()
+    assert st2.nshot == st.paths
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert list(st2.n)[1:] == [0, 0, 0, 0]
+
+
+@pytest.mark.gpu
+def test_radiance_then_volume_gather_still_works(golden, pv_factory):
+    """pv_radiance_photons rebuilds the grid per surface map; a pv_build afterwards restores the volume map."""
+    g, scene = golden("cornell_surf")
+    pv = pv_factory(stepsize=0.05, nused=50, maxdist=0.25, seed=3); pv.set_scene(scene)
+    pv.PreprocessMaps(1500, 800, 2000, True, stepsize=0.05)
+    pv.build()
+    pts = pv.get_photons()[0][:64]
+    nf0, idx0, d0 = pv.Lookup(pts)
+    Lo = pv.RadiancePhotons(50, 0.0625)
+    assert np.isfinite(Lo).all() and (Lo > 0).any()
+    with pytest.raises(Exception):
+        pv.Lookup(pts)                                                     # map not built any more: loud, not stale
+    pv.build()
+    nf1, idx1, d1 = pv.Lookup(pts)
+    assert np.array_equal(nf0, nf1) and np.array_equal(idx0, idx1)

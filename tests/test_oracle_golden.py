@@ -122,3 +122,52 @@ def test_shooter_reproduces_reference_photons(golden, name):
     assert np.abs(res["pos"] - g["shot_pos"]).max() < 1e-5
     assert np.abs(res["wi"] - g["shot_wi"]).max() < 1e-5
     assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-5
+
+
+# ---- surface photon maps: core/photonshooter.cpp:147-189, 303-341, 359-395
+SURF_SCENES = ["cornell_surf", "cornell_surf_disp", "rainbow_surf"]
+
+
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_all_maps_reproduce_reference_photon_lists(golden, name):
+    """One task, the reference's MT stream: the caustic / indirect / direct / volume lists, the radiance-photon sites, nshot and the
+    per-map path counts are the reference's, photon for photon (so the done flags flip at the same blocks)."""
+    g, scene = golden(name)
+    nv, nc, ni, fg, sstep, istep = g["params"][:6]
+    res = O.shoot_maps(scene, int(nv), int(nc), int(ni), bool(fg), float(sstep), float(istep), rng_mode=O.MT)
+    assert res["rc"] == 0
+    nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+    assert (res["nshot"], res["caustic_paths"], res["indirect_paths"], res["direct_paths"], res["volume_paths"]) == (nshot, cp, ip, dp, vp)
+    for k in ("volume", "caustic", "indirect", "direct"):
+        assert len(res[k]["pos"]) == len(g[k + "_pos"]), k
+        if len(g[k + "_pos"]):
+            assert np.abs(res[k]["pos"] - g[k + "_pos"]).max() < 1e-5, k
+            assert np.abs(res[k]["wi"] - g[k + "_wi"]).max() < 1e-5, k
+            assert relerr(res[k]["alpha"], g[k + "_alpha"]).max() < 1e-5, k
+    assert len(res["radiance"]["pos"]) == len(g["rad_pos"]) > 0
+    assert np.abs(res["radiance"]["pos"] - g["rad_pos"]).max() < 1e-5
+    assert np.array_equal(res["radiance"]["wi"], g["rad_n"])            # faceforwarded normals
+    assert np.array_equal(res["radiance"]["alpha"], g["rad_rho_r"])     # rho_r == Kd of the matte surface
+
+
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_radiance_photons_match_reference(golden, name):
+    """EPhoton + ComputeRadianceTask on the reference's own maps."""
+    g, scene = golden(name)
+    nlookup, md2 = int(g["params"][6]), float(g["params"][7])
+    nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+    maps = [(g[k + "_pos"], g[k + "_wi"], g[k + "_alpha"]) for k in ("direct", "indirect", "caustic")]
+    Lo = O.radiance(maps, [dp, ip, cp], g["rad_pos"], g["rad_n"], g["rad_rho_r"], nlookup, md2)
+    ref = g["rad_Lo"]
+    assert (ref > 0).any()
+    assert relerr(Lo, ref)[ref > 0].max() < 2e-6                        # summation order inside the heap: a few ulp
+    assert np.array_equal(Lo == 0, ref == 0)
+
+
+def test_all_maps_with_surface_maps_off_is_the_volume_pass(golden):
+    """caustic = indirect = 0 must reduce to the volume-only pass the other tests pin."""
+    g, scene = golden("cornell_homog")
+    a = O.shoot(scene, 1500, 0.05, 0.05, rng_mode=O.MT)
+    b = O.shoot_maps(scene, 1500, 0, 0, True, 0.05, 0.05, rng_mode=O.MT)
+    assert b["nshot"] == a["nshot"] and np.array_equal(b["volume"]["pos"], a["pos"]) and np.array_equal(b["volume"]["alpha"], a["alpha"])
+    assert len(b["caustic"]["pos"]) == len(b["indirect"]["pos"]) == len(b["direct"]["pos"]) == len(b["radiance"]["pos"]) == 0
