@@ -5,11 +5,12 @@
 // the parser, cameras, samplers, surface integrators and the film are used unchanged:
 //
 //   replaced TU                          what this file provides instead
-//   core/photonshooter.cpp   (:457-526)  PhotonShooter::Preprocess -> pv_set_scene + pv_shoot + pv_build on the GPU.
-//                                        The rest of that TU is still the reference's: it is compiled from
-//                                        /root/reference with -DPreprocess=RefPreprocess, which keeps its CPU pass
-//                                        available (as PhotonShooter::RefPreprocess) for the SURFACE photon maps that
-//                                        the untouched PhotonIntegrator reads (integrators/photonmap.cpp:159-164).
+//   core/photonshooter.cpp   (:457-526)  PhotonShooter::Preprocess -> pv_set_scene + pv_shoot_maps (all photon maps in one
+//                                        GPU pass) + pv_radiance_photons + pv_build.  The caustic / indirect / radiance maps the
+//                                        untouched PhotonIntegrator reads (integrators/photonmap.cpp:159-164) are rebuilt as
+//                                        the reference's KdTree<> objects from the device's photon lists.  The rest of that TU
+//                                        is still the reference's, compiled with -DPreprocess=RefPreprocess: its CPU pass stays
+//                                        reachable for scenes off this path and under PV_SURFACE_MAPS=cpu.
 //   integrators/photonvolume.cpp         PhotonVolumeIntegrator::{RequestSamples, Transmittance, Li} and
 //                                        CreatePhotonVolumeIntegrator (same .pbrt parameters, :224-229).
 //   renderers/samplerrenderer.cpp        SamplerRenderer with a BATCHED Render: image tiles run the unchanged camera /
@@ -117,10 +118,66 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
     g_pv.stepsize = vi->stepSize; g_pv.maxdist = vi->maxDist; g_pv.nused = (uint32_t)vi->nUsed;
     const char *seed = getenv("PV_SEED");
     g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
-    if (nVolumePhotonsWanted > 0) {
-        pv_shoot_params prm; memset(&prm, 0, sizeof(prm));
-        prm.stepsize = stepSize; prm.integrator_stepsize = vi->stepSize; prm.max_photon_depth = maxPhotonDepth;
-        prm.seed = g_pv.seed; prm.rank = 0; prm.world = 1; prm.time = camera ? camera->shutterOpen : 0.f;
+    pv_shoot_params prm; memset(&prm, 0, sizeof(prm));
+    prm.stepsize = stepSize; prm.integrator_stepsize = vi->stepSize; prm.max_photon_depth = maxPhotonDepth;
+    prm.seed = g_pv.seed; prm.rank = 0; prm.world = 1; prm.time = camera ? camera->shutterOpen : 0.f;
+    const char *surf_mode = getenv("PV_SURFACE_MAPS");                 // "cpu": keep the reference's CPU pass for the surface maps
+    const bool surface_wanted = nCausticPhotonsWanted + nIndirectPhotonsWanted > 0;
+    const bool surface_gpu = surface_wanted && !(surf_mode && !strcmp(surf_mode, "cpu"));
+    if (surface_gpu) {
+        // ---- every map in ONE GPU pass (photonshooter.cpp:147-189, 232-357); the untouched PhotonIntegrator keeps reading
+        // causticMap / indirectMap / radianceMap / nCausticPaths / nIndirectPaths (integrators/photonmap.cpp:159-164), so they
+        // are rebuilt here as the reference's own KdTree<> objects from what the device returns.
+        pv_maps_params mp; memset(&mp, 0, sizeof(mp));
+        mp.n_volume_wanted = nVolumePhotonsWanted; mp.n_caustic_wanted = nCausticPhotonsWanted; mp.n_indirect_wanted = nIndirectPhotonsWanted;
+        mp.final_gather = finalGather ? 1 : 0;
+        pv_maps_stats ms;
+        double t0 = now_s();
+        rc = pv_shoot_maps(g_pv.ctx, &mp, &prm, &ms);
+        if (rc == PV_ENOPHOTONS) Error("Unable to store enough photons.  Giving up.\n");      // photonshooter.cpp:292
+        else if (rc) pv_fail("pv_shoot_maps", rc);
+        nCausticPaths = (int)ms.n_caustic_paths; nIndirectPaths = (int)ms.n_indirect_paths; nVolumePaths = (int)ms.n_volume_paths;
+        KdTree<Photon> **maps[2] = {&causticMap, &indirectMap};
+        const int which[2] = {PV_MAP_CAUSTIC, PV_MAP_INDIRECT};
+        for (int k = 0; k < 2; ++k) {
+            uint64_t n = ms.n[which[k]], got = 0;
+            delete *maps[k]; *maps[k] = NULL;
+            if (!n) continue;
+            std::vector<float> pos(3 * n), wi(3 * n), alpha((size_t)PV_NSPEC * n);
+            rc = pv_get_map_photons(g_pv.ctx, which[k], pos.data(), wi.data(), alpha.data(), NULL, n, &got);
+            if (rc) pv_fail("pv_get_map_photons", rc);
+            vector<Photon> photons(got);
+            for (uint64_t i = 0; i < got; ++i) {
+                Photon &p = photons[i];
+                p.p = Point(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]); p.wi = Vector(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+                p.alpha = Spectrum(0.f); memcpy(p.alpha.c, &alpha[(size_t)PV_NSPEC * i], sizeof(float) * PV_NSPEC);
+            }
+            *maps[k] = new KdTree<Photon>(photons);
+        }
+        delete radianceMap; radianceMap = NULL;
+        uint64_t nrad = ms.n[PV_MAP_RADIANCE];
+        if (finalGather && nrad) {
+            // ComputeRadianceTask on the device (photonshooter.cpp:359-395, 494-524)
+            std::vector<float> pos(3 * nrad), nrm(3 * nrad), Lo((size_t)PV_NSPEC * nrad);
+            uint64_t got = 0;
+            rc = pv_radiance_photons(g_pv.ctx, nLookup, maxDistSquared, NULL, Lo.data(), nrad, &got);
+            if (rc) pv_fail("pv_radiance_photons", rc);
+            rc = pv_get_map_photons(g_pv.ctx, PV_MAP_RADIANCE, pos.data(), nrm.data(), NULL, NULL, nrad, &got);
+            if (rc) pv_fail("pv_get_map_photons", rc);
+            vector<RadiancePhoton> rps(got);
+            for (uint64_t i = 0; i < got; ++i) {
+                rps[i] = RadiancePhoton(Point(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), Normal(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+                memcpy(rps[i].Lo.c, &Lo[(size_t)PV_NSPEC * i], sizeof(float) * PV_NSPEC);
+            }
+            radianceMap = new KdTree<RadiancePhoton>(rps);
+        }
+        rc = pv_build(g_pv.ctx, vi->maxDist, (uint32_t)vi->nUsed);
+        if (rc) pv_fail("pv_build", rc);
+        fprintf(stderr, "[pv] all maps on the GPU: %llu volume, %llu caustic, %llu indirect, %llu direct photons, %llu radiance photons from %llu light "
+                        "paths in %.3f s (device %.3f s, %llu blocks replayed)\n",
+                (unsigned long long)ms.n[0], (unsigned long long)ms.n[1], (unsigned long long)ms.n[2], (unsigned long long)ms.n[3],
+                (unsigned long long)ms.n[4], (unsigned long long)ms.nshot, now_s() - t0, ms.shoot.seconds, (unsigned long long)ms.replayed_blocks);
+    } else if (nVolumePhotonsWanted > 0) {
         pv_shoot_stats st;
         double t0 = now_s();
         rc = pv_shoot(g_pv.ctx, nVolumePhotonsWanted, &prm, &st);
@@ -138,13 +195,10 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         if (rc) pv_fail("pv_build", rc);
     }
     g_pv.ready = true;
-    // Surface photon maps (caustic / indirect / radiance photons) stay on the reference's CPU pass.  That pass keeps
-    // scattering photons in the medium only while its own volume map is not full (`scatter && !volumeDone`,
-    // photonshooter.cpp:96), and in scenes without specular surfaces the "caustic" photons are exactly those scattered
-    // paths (Q6: volume scattering does not clear specularPath).  So the CPU pass is asked for as many volume photons as
-    // surface photons -- what the shipped scenes do anyway (volumescene_png.pbrt: 5000 / 5000) -- never for the full
-    // volume count; its volume photons are dropped, the volume map is the GPU's.
-    if (nCausticPhotonsWanted + nIndirectPhotonsWanted > 0) {
+    // PV_SURFACE_MAPS=cpu: the surface maps from the reference's own CPU pass instead.  That pass keeps scattering photons in
+    // the medium only while its own volume map is not full (`scatter && !volumeDone`, photonshooter.cpp:96), so it is asked for
+    // as many volume photons as surface photons, never for the full volume count; its volume photons are dropped.
+    if (surface_wanted && !surface_gpu) {
         uint32_t keep = nVolumePhotonsWanted;
         nVolumePhotonsWanted = std::min(keep, std::max(nCausticPhotonsWanted, nIndirectPhotonsWanted));
         int keepPaths = nVolumePaths;

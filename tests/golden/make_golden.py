@@ -196,8 +196,11 @@ def project_goldens(tmp):
                      wanted=4000, shoot_step=0.1, hit_bound=(-6.0, 9.0), hit_target=((0.1, 0.85, 3.5), (0.9, 0.8, 0.1)), q_near_photons=True)
     # end-to-end reference images
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "pbrt_ref")
+    surf = scenes.cornell_surf_pbrt(nphotons=20000, caustic=5000, indirect=10000, finalgather=True, fgsamples=16, xres=72, yres=72,
+                                    outfile="cornell_surf_e2e.pfm").replace('"integer pixelsamples" [1]', '"integer pixelsamples" [4]')
     for name, text in (("config1_volumescene", scenes.volumescene_pbrt(outfile="config1_volumescene.pfm", xres=150, yres=150)),
-                       ("config4_prism", scenes.prism_pbrt(nphotons=20000, nused=200, xres=96, yres=96, spp=8, outfile="config4_prism.pfm"))):
+                       ("config4_prism", scenes.prism_pbrt(nphotons=20000, nused=200, xres=96, yres=96, spp=8, outfile="config4_prism.pfm")),
+                       ("cornell_surf_e2e", surf)):
         f = os.path.join(tmp, name + ".pbrt"); open(f, "w").write(text)
         open(os.path.join(ROOT, "tests", "scenes", name + ".pbrt"), "w").write(text)
         subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)

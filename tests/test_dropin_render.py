@@ -34,17 +34,22 @@ def block_mean(a, b):
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
-@pytest.mark.parametrize("name,tol_mean,tol_mre", [("config1_volumescene", 0.03, 0.10), ("config4_prism", 0.05, 0.15)])
+@pytest.mark.parametrize("name,tol_mean,tol_mre", [("config1_volumescene", 0.03, 0.10), ("config4_prism", 0.05, 0.15),
+                                                   ("cornell_surf_e2e", 0.04, 0.10)])
 def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name, tol_mean, tol_mre):
     """BASELINE configs[0] (rainbow-volume scene with the shipped settings, 150x150) and configs[3] (glass-prism dispersion
     scene, reduced to 20k photons / 96x96 / 8 spp) rendered by the drop-in and compared with the unmodified reference's
-    render of the same file (tests/golden/<name>_ref.npy, float16).  Random streams differ (MT19937 vs keyed Philox; the
-    surface photon maps still come from the reference's CPU pass), so the tolerance is statistical: mean luminance within
-    tol_mean, mean relative error of 6x6-pixel block means over lit blocks within tol_mre."""
+    render of the same file (tests/golden/<name>_ref.npy, float16).  cornell_surf_e2e: every photon map on (glass wedge
+    caustics, indirect + direct photons, radiance photons, final gathering with 16 samples, 4 spp, 72x72).  ALL photon maps come
+    from the GPU pass (pv_shoot_maps / pv_radiance_photons); the unmodified PhotonIntegrator reads them through its own
+    KdTree<> objects.  Random streams differ (MT19937 vs keyed Philox), so the tolerance is statistical: mean luminance within
+    tol_mean, mean relative error of 6x6-pixel block means over lit blocks within tol_mre (two reference runs with different
+    task counts differ by 1 % / 4 % on cornell_surf_e2e)."""
     scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "[pv] shot" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
+    assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
+    assert "Shooting photons" not in out.stderr                               # ... and the reference's CPU shooting pass did not
     img = read_pfm(os.path.join(tmp_path, name + ".pfm"))
     ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_ref.npy")).astype(np.float32)
     assert img.shape == ref.shape
