@@ -42,12 +42,21 @@ class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", Spec), ("kr", Spec), ("kt", Spec), ("index", C.c_float), ("vn", C.c_float)]
 
 
+class Sphere(C.Structure):
+    _fields_ = [("object_to_world", Mat16), ("world_to_object", Mat16), ("radius", C.c_float), ("zmin", C.c_float), ("zmax", C.c_float),
+                ("theta_min", C.c_float), ("theta_max", C.c_float), ("phi_max", C.c_float), ("flip_normal", C.c_int32)]
+
+
+SHAPE_TRIANGLE = 0xFFFFFFFF
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("nodes", C.POINTER(BvhNode)), ("n_nodes", C.c_uint32),
                 ("tri_verts", C.POINTER(C.c_float)), ("prim_material", C.POINTER(C.c_uint32)), ("n_prims", C.c_uint32),
                 ("materials", C.POINTER(Material)), ("n_materials", C.c_uint32),
                 ("lights", C.POINTER(Light)), ("n_lights", C.c_uint32),
-                ("medium", C.POINTER(Medium)), ("world_bound", C.c_float * 6), ("cie_y", Spec)]
+                ("medium", C.POINTER(Medium)), ("world_bound", C.c_float * 6), ("cie_y", Spec),
+                ("prim_shape", C.POINTER(C.c_uint32)), ("spheres", C.POINTER(Sphere)), ("n_spheres", C.c_uint32)]
 
 
 class GatherParams(C.Structure):

@@ -59,7 +59,7 @@ void pv_destroy(pv_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_pos, ctx->d_wi,
+    void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_prim_shape, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
                     ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -93,6 +93,9 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     if (s->n_prims && (!s->tri_verts || !s->prim_material || !s->materials)) { ctx->err = "pv_set_scene: null geometry arrays"; return PV_EINVAL; }
     for (uint32_t i = 0; i < s->n_prims; ++i)
         if (s->prim_material[i] >= s->n_materials) { ctx->err = "pv_set_scene: material index out of range"; return PV_EINVAL; }
+    if (s->n_spheres && (!s->spheres || !s->prim_shape)) { ctx->err = "pv_set_scene: spheres without a prim_shape table"; return PV_EINVAL; }
+    for (uint32_t i = 0; s->n_spheres && i < s->n_prims; ++i)
+        if (s->prim_shape[i] != PV_SHAPE_TRIANGLE && s->prim_shape[i] >= s->n_spheres) { ctx->err = "pv_set_scene: sphere index out of range"; return PV_EINVAL; }
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_scene = false; ctx->built = false;
     int rc;
@@ -101,12 +104,15 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     if ((rc = upload(ctx, &ctx->d_prim_mat, s->prim_material, sizeof(uint32_t) * (size_t)s->n_prims))) return rc;
     if ((rc = upload(ctx, &ctx->d_mats, s->materials, sizeof(pv_material) * (size_t)s->n_materials))) return rc;
     if ((rc = upload(ctx, &ctx->d_lights, s->lights, sizeof(pv_light) * (size_t)s->n_lights))) return rc;
+    if ((rc = upload(ctx, &ctx->d_prim_shape, s->prim_shape, s->n_spheres ? sizeof(uint32_t) * (size_t)s->n_prims : 0))) return rc;
+    if ((rc = upload(ctx, &ctx->d_spheres, s->spheres, sizeof(pv_sphere) * (size_t)s->n_spheres))) return rc;
     DevScene &h = ctx->hscene;
     memset(&h, 0, sizeof(h));
     h.nodes = (const pv_bvh_node *)ctx->d_nodes; h.n_nodes = s->n_nodes;
     h.tri = (const float *)ctx->d_tri; h.prim_mat = (const uint32_t *)ctx->d_prim_mat; h.n_prims = s->n_prims;
     h.mats = (const pv_material *)ctx->d_mats; h.n_mats = s->n_materials;
     h.lights = (const pv_light *)ctx->d_lights; h.n_lights = s->n_lights;
+    h.prim_shape = (const uint32_t *)ctx->d_prim_shape; h.spheres = (const pv_sphere *)ctx->d_spheres; h.n_spheres = s->n_spheres;
     memcpy(h.world_bound, s->world_bound, sizeof(h.world_bound));
     memcpy(h.cie_y, s->cie_y, sizeof(h.cie_y));
     if (s->medium && s->medium->type != PV_MEDIUM_NONE) {

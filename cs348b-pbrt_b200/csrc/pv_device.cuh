@@ -40,6 +40,8 @@ struct DevScene {
     float world_bound[6];
     float cie_y[PV_NSPEC];
     float light_func[PV_MAX_LIGHTS], light_cdf[PV_MAX_LIGHTS + 1], light_func_int;
+    // primitives that are spheres (shapes/sphere.cpp); n_spheres == 0: every primitive is a triangle
+    const uint32_t *prim_shape; const pv_sphere *spheres; uint32_t n_spheres;
 };
 
 // The geometric part of a DevMedium copied into registers at kernel start.  The scene lives in global memory behind a
@@ -240,6 +242,62 @@ __device__ __forceinline__ bool tri_hit(const float *tv, v3 o, v3 d, float mint,
     *tHit = t;
     return true;
 }
+// shapes/sphere.cpp:58-110 (Intersect) == :167-214 (IntersectP): the hit parameter.  Quadratic: core/pbrt.h:309-323.
+__device__ __forceinline__ void sphere_phit(const pv_sphere &s, v3 ro, v3 rd, float thit, v3 *phit, float *phi) {
+    v3 p = ray_at(ro, rd, thit);
+    if (p.x == 0.f && p.y == 0.f) p.x = 1e-5f * s.radius;
+    float ph = atan2f(p.y, p.x);
+    if (ph < 0.f) ph = (float)((double)ph + 2.0 * 3.14159265358979323846);
+    *phit = p; *phi = ph;
+}
+__device__ __forceinline__ bool sphere_clipped(const pv_sphere &s, v3 phit, float phi) {
+    return (s.zmin > -s.radius && phit.z < s.zmin) || (s.zmax < s.radius && phit.z > s.zmax) || phi > s.phi_max;
+}
+static __device__ __noinline__ bool sphere_hit(const pv_sphere *sp, float ox, float oy, float oz, float dx, float dy, float dz, float mint, float maxt,
+                                        float *tHit) {
+    const pv_sphere &s = *sp;
+    const v3 ro = xf_point(s.world_to_object, V3(ox, oy, oz)), rd = xf_vec(s.world_to_object, V3(dx, dy, dz));
+    const float A = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+    const float B = 2.f * (rd.x * ro.x + rd.y * ro.y + rd.z * ro.z);
+    const float C = ro.x * ro.x + ro.y * ro.y + ro.z * ro.z - s.radius * s.radius;
+    const float discrim = B * B - 4.f * A * C;
+    if (discrim < 0.f) return false;
+    const float rootDiscrim = __fsqrt_rn(discrim);
+    const float q = B < 0.f ? -.5f * (B - rootDiscrim) : -.5f * (B + rootDiscrim);
+    float t0 = __fdiv_rn(q, A), t1 = __fdiv_rn(C, q);
+    if (t0 > t1) { const float t = t0; t0 = t1; t1 = t; }
+    if (t0 > maxt || t1 < mint) return false;
+    float thit = t0;
+    if (t0 < mint) { thit = t1; if (thit > maxt) return false; }
+    v3 phit; float phi;
+    sphere_phit(s, ro, rd, thit, &phit, &phi);
+    if (sphere_clipped(s, phit, phi)) {
+        if (thit == t1) return false;
+        if (t1 > maxt) return false;
+        thit = t1;
+        sphere_phit(s, ro, rd, thit, &phit, &phi);
+        if (sphere_clipped(s, phit, phi)) return false;
+    }
+    *tHit = thit;
+    return true;
+}
+// shapes/sphere.cpp:112-163 + core/diffgeom.cpp:40-55: hit point, normal and dpdu (world space), rayEpsilon
+static __device__ __noinline__ void sphere_dg(const pv_sphere *sp, v3 o, v3 d, float t, v3 *hp, v3 *nn, v3 *dpdu_w, float *eps) {
+    const pv_sphere &s = *sp;
+    const v3 ro = xf_point(s.world_to_object, o), rd = xf_vec(s.world_to_object, d);
+    v3 phit; float phi;
+    sphere_phit(s, ro, rd, t, &phit, &phi);
+    const float theta = acosf(fminf(fmaxf(__fdiv_rn(phit.z, s.radius), -1.f), 1.f));
+    const float zradius = __fsqrt_rn(phit.x * phit.x + phit.y * phit.y);
+    const float invzradius = __fdiv_rn(1.f, zradius);
+    const float cosphi = phit.x * invzradius, sinphi = phit.y * invzradius;
+    const v3 dpdu = V3(-s.phi_max * phit.y, s.phi_max * phit.x, 0.f);
+    const v3 dpdv = V3(phit.z * cosphi, phit.z * sinphi, -s.radius * sinf(theta)) * (s.theta_max - s.theta_min);
+    const v3 wu = xf_vec(s.object_to_world, dpdu), wv = xf_vec(s.object_to_world, dpdv);
+    v3 n = vnorm(vcross(wu, wv));
+    if (s.flip_normal) n = n * -1.f;
+    *hp = xf_point(s.object_to_world, phit); *nn = n; *dpdu_w = wu; *eps = 5e-4f * t;
+}
 struct BvhCounters { uint32_t nodes, tris; };
 // accelerators/bvh.cpp:585-636 (ANY = false) and :639-685 (ANY = true)
 template <bool ANY>
@@ -262,7 +320,11 @@ __device__ __forceinline__ int bvh_traverse(const DevScene &sc, v3 o, v3 d, floa
                 for (uint32_t i = 0; i < nPrims; ++i) {
                     float t;
                     if (bc) bc->tris++;
-                    if (tri_hit(sc.tri + 9 * (size_t)(offset + i), o, d, mint, *maxt, &t)) {
+                    uint32_t shape = PV_SHAPE_TRIANGLE;
+                    if (sc.n_spheres) shape = __ldg(sc.prim_shape + offset + i);
+                    const bool ph = shape == PV_SHAPE_TRIANGLE ? tri_hit(sc.tri + 9 * (size_t)(offset + i), o, d, mint, *maxt, &t)
+                                                               : sphere_hit(sc.spheres + shape, o.x, o.y, o.z, d.x, d.y, d.z, mint, *maxt, &t);
+                    if (ph) {
                         if (ANY) return (int)(offset + i);
                         hit = (int)(offset + i);
                         *maxt = t;

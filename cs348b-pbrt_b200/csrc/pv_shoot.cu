@@ -304,17 +304,23 @@ SH_UNROLL_BINS
             if (prim < 0) pop = true;
             else {
                 // hit record: shapes/trianglemesh.cpp:160-205 with default uvs, core/diffgeom.cpp:40-55
-                const float *tv = sc.tri + 9 * (size_t)prim;
-                v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
-                v3 dp1 = p1 - p3, dp2 = p2 - p3;
-                v3 dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                  // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1
-                v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;                  // (-du2*dp1 + du1*dp2) * invdet, du2 = 0, du1 = -1
-                v3 nn = vnorm(vcross(dpdu, dpdv));
-                v3 hp = ray_at(o, d, thit);
+                v3 dpdu, nn, hp; float eps;
+                uint32_t shape = PV_SHAPE_TRIANGLE;
+                if (sc.n_spheres) shape = sc.prim_shape[prim];
+                if (shape == PV_SHAPE_TRIANGLE) {
+                    const float *tv = sc.tri + 9 * (size_t)prim;
+                    v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
+                    v3 dp1 = p1 - p3, dp2 = p2 - p3;
+                    dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                     // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1
+                    v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;                  // (-du2*dp1 + du1*dp2) * invdet, du2 = 0, du1 = -1
+                    nn = vnorm(vcross(dpdu, dpdv));
+                    hp = ray_at(o, d, thit);
+                    eps = 1e-3f * thit;
+                } else sphere_dg(sc.spheres + shape, o, d, thit, &hp, &nn, &dpdu, &eps);   // shapes/sphere.cpp:112-163
                 cur.prim = prim; cur.ip[0] = hp.x; cur.ip[1] = hp.y; cur.ip[2] = hp.z;
                 cur.inn[0] = nn.x; cur.inn[1] = nn.y; cur.inn[2] = nn.z;
                 cur.idpdu[0] = dpdu.x; cur.idpdu[1] = dpdu.y; cur.idpdu[2] = dpdu.z;
-                cur.ieps = 1e-3f * thit;
+                cur.ieps = eps;
                 cur.maxt = thit;                                            // GeometricPrimitive::Intersect: r.maxt = thit
                 cur.nI++;
                 float length = vlen(d);

@@ -27,6 +27,8 @@ struct PvHostScene {
     std::vector<pv_material> materials;
     std::vector<pv_light> lights;
     std::vector<float> density;
+    std::vector<uint32_t> prim_shape;          // PV_SHAPE_TRIANGLE or an index into spheres
+    std::vector<pv_sphere> spheres;
     pv_medium medium;
     bool has_medium;
     pv_scene_desc desc;
@@ -56,14 +58,25 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     hs.tri.assign(9 * (size_t)nPrims, 0.f);
     hs.prim_material.assign(nPrims, 0u);
     hs.materials.clear();
+    hs.prim_shape.assign(nPrims, PV_SHAPE_TRIANGLE);
+    hs.spheres.clear();
     std::map<const Material *, uint32_t> matIndex;
     DifferentialGeometry dummy;
     for (uint32_t i = 0; i < nPrims; ++i) {
         const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
         if (!gp) { err = "pv: a primitive is not a GeometricPrimitive (instancing is out of scope)"; return false; }
         const Triangle *t = dynamic_cast<const Triangle *>(gp->shape.GetPtr());
-        if (!t) { err = "pv: a shape is not a Triangle (only triangle meshes are on this path)"; return false; }
-        for (int k = 0; k < 3; ++k) {
+        const Sphere *sph = t ? NULL : dynamic_cast<const Sphere *>(gp->shape.GetPtr());
+        if (!t && !sph) { err = "pv: a shape is neither a Triangle nor a Sphere (triangle meshes and spheres are on this path)"; return false; }
+        if (sph) {                                          // shapes/sphere.cpp:40-50
+            pv_sphere ps; memset(&ps, 0, sizeof(ps));
+            pv_mat_out(*sph->ObjectToWorld, ps.object_to_world); pv_mat_out(*sph->WorldToObject, ps.world_to_object);
+            ps.radius = sph->radius; ps.zmin = sph->zmin; ps.zmax = sph->zmax;
+            ps.theta_min = sph->thetaMin; ps.theta_max = sph->thetaMax; ps.phi_max = sph->phiMax;
+            ps.flip_normal = (sph->ReverseOrientation ^ sph->TransformSwapsHandedness) ? 1 : 0;
+            hs.prim_shape[i] = (uint32_t)hs.spheres.size(); hs.spheres.push_back(ps);
+        }
+        for (int k = 0; t && k < 3; ++k) {
             const Point &p = t->mesh->p[t->v[k]];          // already world space (shapes/trianglemesh.cpp:70-71)
             hs.tri[9 * i + 3 * k + 0] = p.x; hs.tri[9 * i + 3 * k + 1] = p.y; hs.tri[9 * i + 3 * k + 2] = p.z;
         }
@@ -146,6 +159,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     d.world_bound[0] = wb.pMin.x; d.world_bound[1] = wb.pMin.y; d.world_bound[2] = wb.pMin.z;
     d.world_bound[3] = wb.pMax.x; d.world_bound[4] = wb.pMax.y; d.world_bound[5] = wb.pMax.z;
     memcpy(d.cie_y, SampledSpectrum::Y.c, sizeof(d.cie_y));
+    if (!hs.spheres.empty()) { d.prim_shape = hs.prim_shape.data(); d.spheres = hs.spheres.data(); d.n_spheres = (uint32_t)hs.spheres.size(); }
     return true;
 }
 
@@ -154,7 +168,7 @@ static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
     FILE *f = fopen(fn.c_str(), "wb");
     if (!f) { perror(fn.c_str()); return false; }
     const pv_scene_desc &d = hs.desc;
-    uint32_t hdr[8] = {d.n_nodes, d.n_prims, d.n_materials, d.n_lights, hs.has_medium ? 1u : 0u, 0, 0, 0};
+    uint32_t hdr[8] = {d.n_nodes, d.n_prims, d.n_materials, d.n_lights, hs.has_medium ? 1u : 0u, d.n_spheres, 0, 0};
     bool ok = fwrite("PVSCN001", 1, 8, f) == 8 && fwrite(hdr, 4, 8, f) == 8 && fwrite(d.world_bound, 4, 6, f) == 6 &&
               fwrite(d.cie_y, 4, PV_NSPEC, f) == PV_NSPEC;
     ok = ok && fwrite(hs.nodes.data(), sizeof(pv_bvh_node), hs.nodes.size(), f) == hs.nodes.size();
@@ -170,6 +184,9 @@ static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
              fwrite(m.le, 4, 30, f) == 30 && fwrite(&m.g, 4, 1, f) == 1 && fwrite(dims, 4, 3, f) == 3;
         if (ok && m.type == PV_MEDIUM_GRID) ok = fwrite(hs.density.data(), 4, hs.density.size(), f) == hs.density.size();
     }
+    if (ok && d.n_spheres)
+        ok = fwrite(hs.prim_shape.data(), 4, hs.prim_shape.size(), f) == hs.prim_shape.size() &&
+             fwrite(hs.spheres.data(), sizeof(pv_sphere), hs.spheres.size(), f) == hs.spheres.size();
     fclose(f);
     if (!ok) fprintf(stderr, "pv: short write on %s\n", fn.c_str());
     else fprintf(stderr, "[pv] exported scene: %u nodes, %u prims, %u materials, %u lights -> %s\n", d.n_nodes, d.n_prims, d.n_materials,

@@ -49,6 +49,7 @@
 #include "core/photonshooter.h"
 #include "accelerators/bvh.h"
 #include "shapes/trianglemesh.h"
+#include "shapes/sphere.h"
 #include "lights/point.h"
 #include "lights/spot.h"
 #include "lights/distant.h"

@@ -1,7 +1,9 @@
 """Binary interchange files either side of the hot path.
 
 PVSCN001  flattened scene exported from the reference's host objects
-          (LinearBVHNode[], triangle table, materials, lights, medium [+ grid])
+          (LinearBVHNode[], triangle table, materials, lights, medium [+ grid],
+          optional sphere table: header word 5 = sphere count, prim_shape[] and
+          pv_sphere[] appended at the end of the file)
 PVPHOT01  photon set: n x {p.xyz, wi.xyz, alpha[30]}  (core/photonshooter.h:20-27
           minus the fork's unused lambda/intensity)
 PVRAY001  rays: n x pv_ray (40 B)
@@ -27,6 +29,8 @@ class Scene:
         self.density = None
         self.world_bound = np.zeros(6, dtype=np.float32)
         self.cie_y = np.zeros(A.NSPEC, dtype=np.float32)
+        self.prim_shape = None              # uint32 per primitive: SHAPE_TRIANGLE or an index into spheres
+        self.spheres = (A.Sphere * 0)()
 
     @property
     def n_prims(self):
@@ -51,6 +55,11 @@ class Scene:
                 self.density = np.ascontiguousarray(self.density, dtype=np.float32)
                 self.medium.density = self.density.ctypes.data_as(C.POINTER(C.c_float))
             d.medium = C.pointer(self.medium)
+        if len(self.spheres):
+            self.prim_shape = np.ascontiguousarray(self.prim_shape, dtype=np.uint32)
+            d.prim_shape = self.prim_shape.ctypes.data_as(C.POINTER(C.c_uint32))
+            d.spheres = C.cast(self.spheres, C.POINTER(A.Sphere))
+            d.n_spheres = len(self.spheres)
         for i in range(6):
             d.world_bound[i] = float(self.world_bound[i])
         for i in range(A.NSPEC):
@@ -66,7 +75,7 @@ def read_scene(path):
         raise ValueError("not a PVSCN001 file: %s" % path)
     off = 8
     hdr = struct.unpack_from("<8I", buf, off); off += 32
-    n_nodes, n_prims, n_mat, n_lights, has_medium = hdr[:5]
+    n_nodes, n_prims, n_mat, n_lights, has_medium, n_spheres = hdr[:6]
     s = Scene()
     s.world_bound = np.frombuffer(buf, dtype=np.float32, count=6, offset=off).copy(); off += 24
     s.cie_y = np.frombuffer(buf, dtype=np.float32, count=A.NSPEC, offset=off).copy(); off += 4 * A.NSPEC
@@ -92,13 +101,16 @@ def read_scene(path):
             cnt = m.nx * m.ny * m.nz
             s.density = np.frombuffer(buf, dtype=np.float32, count=cnt, offset=off).copy(); off += 4 * cnt
         s.medium = m
+    if n_spheres:
+        s.prim_shape = np.frombuffer(buf, dtype=np.uint32, count=n_prims, offset=off).copy(); off += 4 * n_prims
+        s.spheres = (A.Sphere * n_spheres).from_buffer_copy(buf, off); off += C.sizeof(A.Sphere) * n_spheres
     return s
 
 
 def write_scene(path, s):
     with open(path, "wb") as f:
         f.write(b"PVSCN001")
-        f.write(struct.pack("<8I", s.n_nodes, s.n_prims, len(s.materials), len(s.lights), 1 if s.medium is not None else 0, 0, 0, 0))
+        f.write(struct.pack("<8I", s.n_nodes, s.n_prims, len(s.materials), len(s.lights), 1 if s.medium is not None else 0, len(s.spheres), 0, 0))
         f.write(np.asarray(s.world_bound, dtype=np.float32).tobytes())
         f.write(np.asarray(s.cie_y, dtype=np.float32).tobytes())
         f.write(np.asarray(s.nodes, dtype=np.uint8).tobytes())
@@ -113,6 +125,8 @@ def write_scene(path, s):
             f.write(struct.pack("<3i", m.nx, m.ny, m.nz))
             if m.type == A.MEDIUM_GRID:
                 f.write(np.asarray(s.density, dtype=np.float32).tobytes())
+        if len(s.spheres):
+            f.write(np.asarray(s.prim_shape, dtype=np.uint32).tobytes()); f.write(bytes(s.spheres))
 
 
 def _hdr(magic, n):

@@ -134,6 +134,45 @@ WorldEnd
 """
 
 
+# The parameters of projectScene/scene.pbrt (the "crystal ball": a glass SPHERE in a homogeneous medium under a narrow spot
+# light plus a point light, three matte quads, photonmap surface integrator with a caustic map and final gathering).
+SPHERE_TEMPLATE = """# projectScene/scene.pbrt of the reference project: glass sphere (shapes/sphere.cpp) in a homogeneous medium
+Film "image" "integer xresolution" [{xres}] "integer yresolution" [{yres}] "string filename" "{outfile}"
+Sampler "lowdiscrepancy" "integer pixelsamples" [{spp}]
+PixelFilter "{filt}"
+SurfaceIntegrator "photonmap" "integer nused" [{surf_nused}] "bool finalgather" ["{finalgather}"] "integer finalgathersamples" [{fgsamples}]
+  "float maxdist" [.25] "integer indirectphotons" [0] "integer causticphotons" [{caustic}]
+VolumeIntegrator "photonvolume" "float stepsize" [.05] "integer nused" [{nused}] "float maxdist" [0.5]
+  "integer volumephotons" [{nphotons}]
+Rotate 5 1 0 0
+Camera "perspective" "float fov" [70]
+WorldBegin
+Translate -1 -1 3.5
+Volume "homogeneous" "color sigma_a" [.05 .05 .05] "color sigma_s" [.1 .1 .1] "point p0" [-10 0 -5] "point p1" [5 5 5]
+AttributeBegin
+LightSource "spot" "point from" [-3 5 0] "point to" [0 2 0] "color I" [2500 2500 2500] "float coneangle" [6]
+LightSource "point" "point from" [0 2 -4] "color I" [8 8 8]
+AttributeEnd
+AttributeBegin
+Material "glass" "color Kr" [{kr} {kr} {kr}] "color Kt" [1 1 1] "float index" [1.5] "float Vn" [{vn}]
+Translate 0 2 0
+{sphere_xform}Shape "sphere" "float radius" [.6]{sphere_params}
+AttributeEnd
+Material "matte" "color Kd" [.6 .6 .9]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-5 0 -5  5 0 -5  5 0 5  -5 0 5]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-5 0 3  5 0 3  5 10 3  -5 10 3]
+Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [5 0 3  5 0 -3  5 10 -3  5 10 3]
+WorldEnd
+"""
+
+
+def sphere_pbrt(nphotons=1000000, caustic=50000, finalgather=True, fgsamples=64, surf_nused=300, nused=300, xres=300, yres=300, spp=8,
+                filt="gaussian", vn=0.0, kr=0.0, sphere_xform="", sphere_params="", outfile="scene.pfm"):
+    return SPHERE_TEMPLATE.format(nphotons=nphotons, caustic=caustic, finalgather="true" if finalgather else "false", fgsamples=fgsamples,
+                                  surf_nused=surf_nused, nused=nused, xres=xres, yres=yres, spp=spp, filt=filt, vn=vn, kr=kr,
+                                  sphere_xform=sphere_xform, sphere_params=sphere_params, outfile=outfile)
+
+
 def volumescene_pbrt(nphotons=5000, caustic=5000, finalgather=True, xres=300, yres=300, spp=1, filt="gaussian", outfile="volume.pfm"):
     return VOLUMESCENE_TEMPLATE.format(nphotons=nphotons, caustic=caustic, finalgather="true" if finalgather else "false", xres=xres,
                                        yres=yres, spp=spp, filt=filt, outfile=outfile)

@@ -93,6 +93,17 @@ typedef struct pv_material {
     float   index, vn;              /* glass (materials/glass.cpp:42-70)          */
 } pv_material;
 
+/* shapes/sphere.cpp:40-164 Sphere: a BVH primitive that is not a triangle.
+ * Matrices row-major like pv_light's. */
+typedef struct pv_sphere {
+    float   object_to_world[16], world_to_object[16];
+    float   radius, zmin, zmax;             /* clamped as the ctor leaves them (:44-46)  */
+    float   theta_min, theta_max, phi_max;  /* radians (:47-49)                         */
+    int32_t flip_normal;                    /* ReverseOrientation ^ TransformSwapsHandedness
+                                               (core/diffgeom.cpp:52-53)                 */
+} pv_sphere;
+#define PV_SHAPE_TRIANGLE 0xFFFFFFFFu
+
 /* Flattened scene, exported from the unchanged host objects. */
 typedef struct pv_scene_desc {
     const pv_bvh_node *nodes;       uint32_t n_nodes;
@@ -106,6 +117,11 @@ typedef struct pv_scene_desc {
     float              world_bound[6];
     float              cie_y[PV_NSPEC];  /* SampledSpectrum::Y bin averages
                                             (core/spectrum.h:368-381)             */
+    /* optional: primitives that are spheres.  prim_shape[i] = PV_SHAPE_TRIANGLE or an index
+     * into spheres[]; NULL / n_spheres == 0 -> every primitive is a triangle (the
+     * tri_verts slot of a sphere primitive is ignored).                           */
+    const uint32_t    *prim_shape;
+    const pv_sphere   *spheres;     uint32_t n_spheres;
 } pv_scene_desc;
 
 /* PhotonVolumeIntegrator ctor params (integrators/photonvolume.h:17-20) +

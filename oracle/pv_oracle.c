@@ -360,6 +360,47 @@ static inline int tri_hit(const float *tv, v3 o, v3 d, float mint, float maxt, f
     *tHit = t;
     return 1;
 }
+/* shapes/sphere.cpp:58-110 (Intersect) == :167-214 (IntersectP): the hit parameter only.  Quadratic: core/pbrt.h:309-323 */
+static inline void sphere_phit(const pv_sphere *s, v3 ro, v3 rd, float thit, v3 *phit, float *phi) {
+    *phit = ray_at(ro, rd, thit);
+    if (phit->x == 0.f && phit->y == 0.f) phit->x = 1e-5f * s->radius;
+    float ph = atan2f(phit->y, phit->x);
+    if (ph < 0.) ph = (float)((double)ph + (double)2.f * 3.14159265358979323846);
+    *phi = ph;
+}
+static inline int sphere_clipped(const pv_sphere *s, v3 phit, float phi) {
+    return (s->zmin > -s->radius && phit.z < s->zmin) || (s->zmax < s->radius && phit.z > s->zmax) || phi > s->phi_max;
+}
+static int sphere_hit(const pv_sphere *s, v3 o, v3 d, float mint, float maxt, float *tHit) {
+    v3 ro = xf_point(s->world_to_object, o), rd = xf_vec(s->world_to_object, d);
+    float A = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+    float B = 2 * (rd.x * ro.x + rd.y * ro.y + rd.z * ro.z);
+    float C = ro.x * ro.x + ro.y * ro.y + ro.z * ro.z - s->radius * s->radius;
+    float discrim = B * B - 4.f * A * C;
+    if (discrim < 0.) return 0;
+    float rootDiscrim = sqrtf(discrim);
+    float q = B < 0 ? -.5f * (B - rootDiscrim) : -.5f * (B + rootDiscrim);
+    float t0 = q / A, t1 = C / q;
+    if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+    if (t0 > maxt || t1 < mint) return 0;
+    float thit = t0;
+    if (t0 < mint) { thit = t1; if (thit > maxt) return 0; }
+    v3 phit; float phi;
+    sphere_phit(s, ro, rd, thit, &phit, &phi);
+    if (sphere_clipped(s, phit, phi)) {
+        if (thit == t1) return 0;
+        if (t1 > maxt) return 0;
+        thit = t1;
+        sphere_phit(s, ro, rd, thit, &phit, &phi);
+        if (sphere_clipped(s, phit, phi)) return 0;
+    }
+    *tHit = thit;
+    return 1;
+}
+static inline int prim_hit(const pv_scene_desc *sc, uint32_t prim, v3 o, v3 d, float mint, float maxt, float *tHit) {
+    if (sc->n_spheres && sc->prim_shape[prim] != PV_SHAPE_TRIANGLE) return sphere_hit(&sc->spheres[sc->prim_shape[prim]], o, d, mint, maxt, tHit);
+    return tri_hit(sc->tri_verts + 9 * (size_t)prim, o, d, mint, maxt, tHit);
+}
 /* accelerators/bvh.cpp:585-636; returns primitive index (reordered array) or -1; *maxt shrinks */
 static int bvh_intersect(const pv_scene_desc *sc, v3 o, v3 d, float mint, float *maxt, bvh_counters *bc) {
     if (!sc->n_nodes) return -1;
@@ -375,7 +416,7 @@ static int bvh_intersect(const pv_scene_desc *sc, v3 o, v3 d, float mint, float 
                 for (uint32_t i = 0; i < node->n_primitives; ++i) {
                     float t;
                     if (bc) bc->tri_tests++;
-                    if (tri_hit(sc->tri_verts + 9 * (size_t)(node->offset + i), o, d, mint, *maxt, &t)) {
+                    if (prim_hit(sc, node->offset + i, o, d, mint, *maxt, &t)) {
                         hit = (int)(node->offset + i);
                         *maxt = t;
                     }
@@ -407,7 +448,7 @@ static int bvh_intersectp(const pv_scene_desc *sc, v3 o, v3 d, float mint, float
                 for (uint32_t i = 0; i < node->n_primitives; ++i) {
                     float t;
                     if (bc) bc->tri_tests++;
-                    if (tri_hit(sc->tri_verts + 9 * (size_t)(node->offset + i), o, d, mint, maxt, &t)) return 1;
+                    if (prim_hit(sc, node->offset + i, o, d, mint, maxt, &t)) return 1;
                 }
                 if (todoOffset == 0) break;
                 nodeNum = todo[--todoOffset];
@@ -975,6 +1016,28 @@ static spec shoot_transmittance(shoot_ctx *c, const ray_t *r) {
 
 /* dg + shading frame for a triangle hit: shapes/trianglemesh.cpp:160-205, core/diffgeom.cpp:40-55 */
 static void make_isect(const pv_scene_desc *sc, int prim, v3 o, v3 d, float t, isect_t *is) {
+    if (sc->n_spheres && sc->prim_shape[prim] != PV_SHAPE_TRIANGLE) {
+        /* shapes/sphere.cpp:112-163 + core/diffgeom.cpp:40-55 */
+        const pv_sphere *s = &sc->spheres[sc->prim_shape[prim]];
+        v3 ro = xf_point(s->world_to_object, o), rd = xf_vec(s->world_to_object, d);
+        v3 phit; float phi;
+        sphere_phit(s, ro, rd, t, &phit, &phi);
+        float cz = phit.z / s->radius; cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
+        float theta = acosf(cz);
+        float zradius = sqrtf(phit.x * phit.x + phit.y * phit.y);
+        float invzradius = 1.f / zradius;
+        float cosphi = phit.x * invzradius, sinphi = phit.y * invzradius;
+        v3 dpdu = V(-s->phi_max * phit.y, s->phi_max * phit.x, 0);
+        v3 dpdv = vmul(V(phit.z * cosphi, phit.z * sinphi, -s->radius * sinf(theta)), s->theta_max - s->theta_min);
+        v3 wdpdu = xf_vec(s->object_to_world, dpdu), wdpdv = xf_vec(s->object_to_world, dpdv);
+        is->prim = prim;
+        is->p = xf_point(s->object_to_world, phit);
+        is->dpdu = wdpdu;
+        is->nn = vnorm(vcross(wdpdu, wdpdv));
+        if (s->flip_normal) is->nn = vmul(is->nn, -1.f);
+        is->rayEpsilon = 5e-4f * t;
+        return;
+    }
     const float *tv = sc->tri_verts + 9 * (size_t)prim;
     v3 p1 = V(tv[0], tv[1], tv[2]), p2 = V(tv[3], tv[4], tv[5]), p3 = V(tv[6], tv[7], tv[8]);
     /* default uvs (0,0),(1,0),(1,1): du1=-1 du2=0 dv1=-1 dv2=-1, determinant 1 */

@@ -176,6 +176,7 @@ def main():
         assert np.array_equal(g.density, dens), "density grid did not survive the text round trip"
         project_goldens(tmp)
         surface_goldens(tmp)
+        sphere_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -200,11 +201,32 @@ def project_goldens(tmp):
                                     outfile="cornell_surf_e2e.pfm").replace('"integer pixelsamples" [1]', '"integer pixelsamples" [4]')
     for name, text in (("config1_volumescene", scenes.volumescene_pbrt(outfile="config1_volumescene.pfm", xres=150, yres=150)),
                        ("config4_prism", scenes.prism_pbrt(nphotons=20000, nused=200, xres=96, yres=96, spp=8, outfile="config4_prism.pfm")),
-                       ("cornell_surf_e2e", surf)):
+                       ("cornell_surf_e2e", surf),
+                       ("sphere_e2e", scenes.sphere_pbrt(nphotons=100000, caustic=5000, finalgather=True, fgsamples=16, surf_nused=100, nused=100,
+                                                         xres=96, yres=96, spp=4, outfile="sphere_e2e.pfm"))):
         f = os.path.join(tmp, name + ".pbrt"); open(f, "w").write(text)
         open(os.path.join(ROOT, "tests", "scenes", name + ".pbrt"), "w").write(text)
         subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)
         np.save(os.path.join(HERE, name + "_ref.npy"), read_pfm(os.path.join(tmp, name + ".pfm")).astype(np.float16))
+
+
+def sphere_goldens(tmp):
+    """Sphere primitives (shapes/sphere.cpp).  sphere_glass = the parameters of the reference project's
+    projectScene/scene.pbrt (glass ball in a homogeneous medium, spot + point light) at reduced counts; sphere_disp = the same with a
+    rotated, non-uniformly scaled, PARTIAL sphere (zmin/zmax/phimax) of dispersive, reflecting glass."""
+    cam = dict(fov_deg=70.0, eye=(0, 0, 0), look=(0, 0.0872, 0.9962))
+    box = ((-11, -1, -1.5), (4, 4, 8.5))
+    target = ((-1.0, 1.0, 3.5), (0.7, 0.7, 0.7))
+    f = os.path.join(tmp, "sphere_glass.pbrt")
+    open(f, "w").write(scenes.sphere_pbrt(nphotons=4000, caustic=0, finalgather=False, nused=100, xres=64, yres=64, spp=1))
+    golden_for_scene(tmp, "sphere_glass", f, 100, 0.5, 0.05, 48, 48, [(100, 0.5 ** 2)], camera=cam, box=box, wanted=4000, shoot_step=0.1,
+                     hit_bound=(-6.0, 9.0), hit_target=target, q_near_photons=True)
+    f = os.path.join(tmp, "sphere_disp.pbrt")
+    open(f, "w").write(scenes.sphere_pbrt(nphotons=4000, caustic=0, finalgather=False, nused=100, xres=64, yres=64, spp=1, vn=4.0, kr=0.5,
+                                          sphere_xform="Rotate 30 1 0 0\nScale 1 0.8 1.2\n",
+                                          sphere_params=' "float zmin" [-0.4] "float zmax" [0.5] "float phimax" [300]'))
+    golden_for_scene(tmp, "sphere_disp", f, 100, 0.5, 0.05, 48, 48, [(100, 0.5 ** 2)], camera=cam, box=box, wanted=4000, shoot_step=0.1,
+                     hit_bound=(-6.0, 9.0), hit_target=target, q_near_photons=True)
 
 
 def read_radiance(fn):
@@ -259,7 +281,11 @@ def read_pfm(path):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "surface":          # only the surface-map goldens
+    if len(sys.argv) > 1 and sys.argv[1] == "sphere":           # only the sphere-scene goldens
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            sphere_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "surface":          # only the surface-map goldens
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             surface_goldens(tmp_)

@@ -10,7 +10,8 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 RTOL_RADIANCE = 1e-4
 # rainbow_vol / prism_small = BASELINE configs 1 and 4 (the reference project's own scenes, reduced counts; tests/golden/make_golden.py)
-ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small"]
+# sphere_glass / sphere_disp: Sphere primitives (the project's glass-ball scene, and a rotated / scaled / partial / dispersive variant)
+ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp"]
 
 
 def relerr(a, b, floor=1e-30):
@@ -169,7 +170,7 @@ def test_li_homogeneous_vs_reference(golden, pv_factory, name):
 
 
 @pytest.mark.parametrize("name,flags", [("cornell_homog", 0), ("cornell_grid32", 0), ("cornell_grid32", 1), ("cornell_grid32", 2),
-                                        ("rainbow_vol", 0), ("prism_small", 0)])
+                                        ("rainbow_vol", 0), ("prism_small", 0), ("sphere_glass", 0), ("sphere_disp", 0)])
 def test_li_vs_oracle_same_philox_stream(golden, pv_factory, name, flags):
     g, scene = golden(name)
     stepsize, nused, maxdist = float(g["params"][2]), int(g["params"][0]), float(g["params"][1])
@@ -211,7 +212,7 @@ def pkg_rays(o, d):
 
 
 @pytest.mark.parametrize("name,wanted,sstep", [("cornell_homog", 3000, 0.05), ("cornell_grid32", 1200, 0.05), ("rainbow_vol", 1500, 0.1),
-                                               ("prism_small", 4000, 0.1)])
+                                               ("prism_small", 4000, 0.1), ("sphere_glass", 4000, 0.1), ("sphere_disp", 4000, 0.1)])
 def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, sstep):
     """Same per-path Philox streams on both sides: photons are matched one to one by (path, deposit ordinal).
     prism_small: every path goes through the dispersive glass wedge (splitSpectrum into 30 monochromatic photons, Cauchy refraction)."""
@@ -232,7 +233,14 @@ def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, 
     dpos = np.abs(pos[ia] - ref["pos"][ib]).max(axis=1)
     assert np.quantile(dpos, 0.99) < 1e-4
     ok = dpos < 1e-4
-    assert relerr(alpha[ia][ok], ref["alpha"][ib][ok]).max() < 1e-3
+    e = relerr(alpha[ia][ok], ref["alpha"][ib][ok]).max(axis=1)
+    if name.startswith("sphere"):
+        # curved glass: the normal comes out of acosf / sinf / atan2f (libm vs CUDA, last-ulp differences), and the Fresnel term
+        # has a square-root singularity at the critical angle that internal reflections in the ball do reach -- a 1e-7 change
+        # of the normal moves F by ~sqrt(1e-7) there.  Nearly all photons agree to 1e-3, the rest to a few per cent.
+        assert np.quantile(e, 0.99) < 1e-3 and e.max() < 5e-2, (np.quantile(e, 0.99), e.max())
+    else:
+        assert e.max() < 1e-3
     assert np.all(np.diff(ids.astype(np.int64)) > 0)        # deterministic order: sorted by (path, ordinal)
 
 
