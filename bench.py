@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--workload", default="config3")
     ap.add_argument("--photons", type=int, default=0, help="override the photon count (debug only; invalidates the number)")
     ap.add_argument("--shoot-photons", type=int, default=400_000, help="bounded photon-shooting sample for the shoot rates")
+    ap.add_argument("--maps-photons", type=int, default=200_000, help="volume-photon target of the all-maps shooting sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=600_000, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--ref-rays", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -242,6 +243,25 @@ def main():
                  "paths_per_s": sec[1] / dsec, "photons_per_s": sec[2] / dsec,
                  "stack_overflows": int(sec[6]), "hbm_frac_algorithmic": shoot_bytes / dsec / 1e9 / (peak * world),
                  "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": args.shoot_photons}}
+
+        # the same pass with the SURFACE maps on (pv_shoot_maps + pv_radiance_photons): every photon class of
+        # the reference's shooter in the config-3 scene, bounded sample, single rank (rank 0 reports)
+        if world == 1 and args.maps_photons > 0:
+            pvm = pkg.PhotonVolume(device=local, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=args.seed)
+            pvm.set_scene(scene)
+            n = args.maps_photons
+            t0 = time.perf_counter()
+            ms = pvm.PreprocessMaps(n, n // 4, n // 2, True, stepsize=0.05, max_photon_depth=5)
+            t1 = time.perf_counter()
+            Lo = pvm.RadiancePhotons(50, 0.05 ** 2)
+            t2 = time.perf_counter()
+            shoot["all_maps"] = {"photons": {k: int(ms.n[i]) for i, k in enumerate(("volume", "caustic", "indirect", "direct", "radiance"))},
+                                 "paths": int(ms.nshot), "replayed_blocks": int(ms.replayed_blocks), "device_s": float(ms.shoot.seconds),
+                                 "paths_per_s": float(ms.shoot.paths_local) / float(ms.shoot.seconds),
+                                 "photons_per_s": float(sum(ms.n)) / float(ms.shoot.seconds), "wall_s": t1 - t0,
+                                 "radiance_photons_wall_s": t2 - t1, "radiance_finite": bool(np.isfinite(Lo).all()),
+                                 "params": {"volume": n, "caustic": n // 4, "indirect": n // 2, "finalgather": True, "nlookup": 50, "maxdist": 0.05}}
+            pvm.close()
 
     # ------------------------------------------------------------------ the photon map of the gather workload
     lo, hi = W.photon_slice(n_ph, rank, world)

@@ -59,7 +59,7 @@ void pv_destroy(pv_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_prim_shape, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
+    void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
                     ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -100,11 +100,23 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     ctx->has_scene = false; ctx->built = false;
     int rc;
     if ((rc = upload(ctx, &ctx->d_nodes, s->nodes, sizeof(pv_bvh_node) * (size_t)s->n_nodes))) return rc;
-    if ((rc = upload(ctx, &ctx->d_tri, s->tri_verts, sizeof(float) * 9 * (size_t)s->n_prims))) return rc;
+    if (s->n_spheres) {
+        // sphere primitives are tagged in the device copy of the triangle table (see DevScene)
+        if (s->n_spheres > PV_SPHERE_INDEX_MASK) { ctx->err = "pv_set_scene: too many spheres"; return PV_EINVAL; }
+        std::vector<float> tri(s->tri_verts, s->tri_verts + 9 * (size_t)s->n_prims);
+        for (uint32_t i = 0; i < s->n_prims; ++i) {
+            if (s->prim_shape[i] == PV_SHAPE_TRIANGLE) {
+                if (tri[9 * (size_t)i] != tri[9 * (size_t)i]) { ctx->err = "pv_set_scene: NaN triangle vertex"; return PV_EINVAL; }
+                continue;
+            }
+            const uint32_t bits = PV_SPHERE_TAG | s->prim_shape[i];
+            memcpy(&tri[9 * (size_t)i], &bits, sizeof(bits));
+        }
+        if ((rc = upload(ctx, &ctx->d_tri, tri.data(), sizeof(float) * tri.size()))) return rc;
+    } else if ((rc = upload(ctx, &ctx->d_tri, s->tri_verts, sizeof(float) * 9 * (size_t)s->n_prims))) return rc;
     if ((rc = upload(ctx, &ctx->d_prim_mat, s->prim_material, sizeof(uint32_t) * (size_t)s->n_prims))) return rc;
     if ((rc = upload(ctx, &ctx->d_mats, s->materials, sizeof(pv_material) * (size_t)s->n_materials))) return rc;
     if ((rc = upload(ctx, &ctx->d_lights, s->lights, sizeof(pv_light) * (size_t)s->n_lights))) return rc;
-    if ((rc = upload(ctx, &ctx->d_prim_shape, s->prim_shape, s->n_spheres ? sizeof(uint32_t) * (size_t)s->n_prims : 0))) return rc;
     if ((rc = upload(ctx, &ctx->d_spheres, s->spheres, sizeof(pv_sphere) * (size_t)s->n_spheres))) return rc;
     DevScene &h = ctx->hscene;
     memset(&h, 0, sizeof(h));
@@ -112,7 +124,7 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     h.tri = (const float *)ctx->d_tri; h.prim_mat = (const uint32_t *)ctx->d_prim_mat; h.n_prims = s->n_prims;
     h.mats = (const pv_material *)ctx->d_mats; h.n_mats = s->n_materials;
     h.lights = (const pv_light *)ctx->d_lights; h.n_lights = s->n_lights;
-    h.prim_shape = (const uint32_t *)ctx->d_prim_shape; h.spheres = (const pv_sphere *)ctx->d_spheres; h.n_spheres = s->n_spheres;
+    h.spheres = (const pv_sphere *)ctx->d_spheres; h.n_spheres = s->n_spheres;
     memcpy(h.world_bound, s->world_bound, sizeof(h.world_bound));
     memcpy(h.cie_y, s->cie_y, sizeof(h.cie_y));
     if (s->medium && s->medium->type != PV_MEDIUM_NONE) {

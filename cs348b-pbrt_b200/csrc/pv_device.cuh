@@ -40,9 +40,13 @@ struct DevScene {
     float world_bound[6];
     float cie_y[PV_NSPEC];
     float light_func[PV_MAX_LIGHTS], light_cdf[PV_MAX_LIGHTS + 1], light_func_int;
-    // primitives that are spheres (shapes/sphere.cpp); n_spheres == 0: every primitive is a triangle
-    const uint32_t *prim_shape; const pv_sphere *spheres; uint32_t n_spheres;
+    // primitives that are spheres (shapes/sphere.cpp).  On the device a sphere primitive is TAGGED IN THE TRIANGLE TABLE:
+    // the first float of its 9-float slot is a NaN whose low 22 bits are the index into spheres[] (pv_set_scene writes it),
+    // so the leaf loop pays one compare on a value it loads anyway and triangle-only scenes load nothing extra.
+    const pv_sphere *spheres; uint32_t n_spheres;
 };
+#define PV_SPHERE_TAG 0x7FC00000u
+#define PV_SPHERE_INDEX_MASK 0x003FFFFFu
 
 // The geometric part of a DevMedium copied into registers at kernel start.  The scene lives in global memory behind a
 // pointer the compiler must assume the kernel's own stores may alias, so every density tap would otherwise re-load the
@@ -300,7 +304,9 @@ static __device__ __noinline__ void sphere_dg(const pv_sphere *sp, v3 o, v3 d, f
 }
 struct BvhCounters { uint32_t nodes, tris; };
 // accelerators/bvh.cpp:585-636 (ANY = false) and :639-685 (ANY = true)
-template <bool ANY>
+// SPH: the scene holds sphere primitives (the NaN tag is only looked for then; kernels are instantiated for both cases so
+// that triangle-only scenes run exactly the triangle-only code)
+template <bool ANY, bool SPH>
 __device__ __forceinline__ int bvh_traverse(const DevScene &sc, v3 o, v3 d, float mint, float *maxt, BvhCounters *bc) {
     if (!sc.n_nodes) return -1;
     int hit = -1;
@@ -320,10 +326,13 @@ __device__ __forceinline__ int bvh_traverse(const DevScene &sc, v3 o, v3 d, floa
                 for (uint32_t i = 0; i < nPrims; ++i) {
                     float t;
                     if (bc) bc->tris++;
-                    uint32_t shape = PV_SHAPE_TRIANGLE;
-                    if (sc.n_spheres) shape = __ldg(sc.prim_shape + offset + i);
-                    const bool ph = shape == PV_SHAPE_TRIANGLE ? tri_hit(sc.tri + 9 * (size_t)(offset + i), o, d, mint, *maxt, &t)
-                                                               : sphere_hit(sc.spheres + shape, o.x, o.y, o.z, d.x, d.y, d.z, mint, *maxt, &t);
+                    const float *tv = sc.tri + 9 * (size_t)(offset + i);
+                    bool ph;
+                    if (SPH) {
+                        const float tag = __ldg(tv);
+                        ph = tag == tag ? tri_hit(tv, o, d, mint, *maxt, &t)
+                                        : sphere_hit(sc.spheres + (__float_as_uint(tag) & PV_SPHERE_INDEX_MASK), o.x, o.y, o.z, d.x, d.y, d.z, mint, *maxt, &t);
+                    } else ph = tri_hit(tv, o, d, mint, *maxt, &t);
                     if (ph) {
                         if (ANY) return (int)(offset + i);
                         hit = (int)(offset + i);

@@ -70,6 +70,7 @@ struct MarchArgs {
 // One THREAD per ray, steps in sequence: the 32 lanes of a warp are 32 neighbouring camera rays (callers pass rays
 // in image-tile order) at the same march depth, so their density taps fall into the same few voxels and the warp's
 // eight trilinear taps touch a handful of 32-byte sectors instead of 256.
+template <bool SPH>
 __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(MarchArgs a) {
     const DevScene &sc = *a.sc;
     const DevMedium &gmed = sc.med;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
                 if (lq.falloff != 0.f) {
                     nshadow++;
                     float mt = lq.vis_maxt;
-                    if (bvh_traverse<true>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
+                    if (bvh_traverse<true, SPH>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
                         c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize, pv_u32_to_float(sw[2]), &ns);
                         const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
                         c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
@@ -170,7 +171,8 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     a.stepsize = prm->stepsize; a.flags = flags; a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
     a.ray_index_base = prm->ray_index_base; a.stats = ctx->d_stats;
     if (total) {
-        march_steps_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
+        if (ctx->hscene.n_spheres) march_steps_kernel<true><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
+        else march_steps_kernel<false><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev3, ctx->stream));

@@ -179,7 +179,7 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
 #ifndef SH_MIN_CTAS
 #define SH_MIN_CTAS 8                // 32 warps/SM at 64 registers: latency-bound on density taps, the spills cost less than the occupancy gains (measured 4: 40.9 ms, 6: 36.1 ms, 8: 35.2 ms)
 #endif
-template <bool SURF>
+template <bool SURF, bool SPH>
 __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
     __shared__ uint32_t s_perm[41];
@@ -299,16 +299,14 @@ SH_UNROLL_BINS
             c_seg++;
             float thit = cur.maxt;
             BvhCounters bc = {0, 0};
-            int prim = bvh_traverse<false>(sc, o, d, cur.mint, &thit, &bc);
+            int prim = bvh_traverse<false, SPH>(sc, o, d, cur.mint, &thit, &bc);
             c_nodes += bc.nodes; c_tris += bc.tris;
             if (prim < 0) pop = true;
             else {
                 // hit record: shapes/trianglemesh.cpp:160-205 with default uvs, core/diffgeom.cpp:40-55
                 v3 dpdu, nn, hp; float eps;
-                uint32_t shape = PV_SHAPE_TRIANGLE;
-                if (sc.n_spheres) shape = sc.prim_shape[prim];
-                if (shape == PV_SHAPE_TRIANGLE) {
-                    const float *tv = sc.tri + 9 * (size_t)prim;
+                const float *tv = sc.tri + 9 * (size_t)prim;
+                if (!SPH || tv[0] == tv[0]) {
                     v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
                     v3 dp1 = p1 - p3, dp2 = p2 - p3;
                     dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                     // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1
@@ -316,7 +314,7 @@ SH_UNROLL_BINS
                     nn = vnorm(vcross(dpdu, dpdv));
                     hp = ray_at(o, d, thit);
                     eps = 1e-3f * thit;
-                } else sphere_dg(sc.spheres + shape, o, d, thit, &hp, &nn, &dpdu, &eps);   // shapes/sphere.cpp:112-163
+                } else sphere_dg(sc.spheres + (__float_as_uint(tv[0]) & PV_SPHERE_INDEX_MASK), o, d, thit, &hp, &nn, &dpdu, &eps);   // NaN-tagged slot: shapes/sphere.cpp:112-163
                 cur.prim = prim; cur.ip[0] = hp.x; cur.ip[1] = hp.y; cur.ip[2] = hp.z;
                 cur.inn[0] = nn.x; cur.inn[1] = nn.y; cur.inn[2] = nn.z;
                 cur.idpdu[0] = dpdu.x; cur.idpdu[1] = dpdu.y; cur.idpdu[2] = dpdu.z;
@@ -667,14 +665,15 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks * n_cls, ctx->stream));
         int per_sm = 0;
-        if (surf) PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel<true>, SH_THREADS, 0));
-        else PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shoot_kernel<false>, SH_THREADS, 0));
+        const bool sph = ctx->hscene.n_spheres != 0;
+        void (*kern)(ShootArgs) = surf ? (sph ? shoot_kernel<true, true> : shoot_kernel<true, false>)
+                                       : (sph ? shoot_kernel<false, true> : shoot_kernel<false, false>);
+        PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SH_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         uint64_t total = (uint64_t)n_local * SH_BLOCK;
         int blocks = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (total + SH_THREADS - 1) / SH_THREADS);
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        if (surf) shoot_kernel<true><<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
-        else shoot_kernel<false><<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
+        kern<<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         unsigned long long h_nout = 0, h_stats[8];

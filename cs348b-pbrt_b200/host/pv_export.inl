@@ -62,6 +62,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     hs.spheres.clear();
     std::map<const Material *, uint32_t> matIndex;
     DifferentialGeometry dummy;
+    bool warned_uv = false;
     for (uint32_t i = 0; i < nPrims; ++i) {
         const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
         if (!gp) { err = "pv: a primitive is not a GeometricPrimitive (instancing is out of scope)"; return false; }
@@ -76,6 +77,11 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             ps.flip_normal = (sph->ReverseOrientation ^ sph->TransformSwapsHandedness) ? 1 : 0;
             hs.prim_shape[i] = (uint32_t)hs.spheres.size(); hs.spheres.push_back(ps);
         }
+        if (t && t->mesh->uvs && !warned_uv) {
+            warned_uv = true;
+            fprintf(stderr, "pv: warning: explicit triangle uvs are ignored by the photon shooter (default-uv shading frame, shapes/trianglemesh.cpp:166-175); "
+                            "diffuse bounce directions are distributed identically but drawn in another tangent frame\n");
+        }
         for (int k = 0; t && k < 3; ++k) {
             const Point &p = t->mesh->p[t->v[k]];          // already world space (shapes/trianglemesh.cpp:70-71)
             hs.tri[9 * i + 3 * k + 0] = p.x; hs.tri[9 * i + 3 * k + 1] = p.y; hs.tri[9 * i + 3 * k + 2] = p.z;
@@ -86,6 +92,10 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
                 pm.type = PV_MAT_MATTE;
                 pv_spec_out(mm->Kd->Evaluate(dummy).Clamp(), pm.kd);
+                // the device material is ONE reflectance: a spatially varying Kd texture is flattened to its value at (u, v) = (0, 0)
+                DifferentialGeometry probe; probe.u = 0.37f; probe.v = 0.61f; probe.p = Point(0.37f, 0.61f, 0.13f);
+                if (mm->Kd->Evaluate(probe).Clamp() != mm->Kd->Evaluate(dummy).Clamp())
+                    fprintf(stderr, "pv: warning: textured matte Kd on primitive %u is flattened to its value at uv = (0, 0) for photon shooting\n", i);
                 if (mm->sigma->Evaluate(dummy) != 0.f) fprintf(stderr, "pv: warning: matte sigma != 0 (Oren-Nayar) is treated as Lambertian\n");
             } else if (const GlassMaterial *gm = dynamic_cast<const GlassMaterial *>(m)) {
                 pm.type = PV_MAT_GLASS;

@@ -62,6 +62,25 @@ for kern in ("gather", "march"):
     for a in sorted(agg, key=lambda a: -a[3])[:25]:
         md.append("| %s:%d | %.2f | %.2f | `%s` |" % (a[0], a[1], 100 * a[3] / ts, 100 * a[4] / ti, a[2].replace("|", "\\|")))
     md.append("")
+# the shooter: one row per captured launch (volume-only waves first, then the all-maps waves of pv_shoot_maps)
+rep = os.path.join(G, "%s_shoot.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(P, "%s_shoot_raw.csv" % tag), "w").write(raw)
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    cols = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
+            "l1tex__t_sector_hit_rate.pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__icc_request_hit_rate.pct",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+    md.append("## shoot_kernel launches (`%s_shoot_raw.csv`; `<false>` = volume photons only, `<true>` = all photon maps)\n" % tag)
+    md.append("| kernel | " + " | ".join(c.split(".")[0].replace("smsp__", "").replace("sm__", "") for c in cols) + " |\n|---|" + "---|" * len(cols))
+    ik = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        if len(r) != len(hdr):
+            continue
+        md.append("| %s | " % r[ik][:40] + " | ".join(r[hdr.index(c)] if c in hdr else "-" for c in cols) + " |")
+    md.append("")
 lc = os.path.join(G, "%s_launches.csv" % tag)
 if os.path.exists(lc):
     rows = [r for r in csv.reader(l for l in open(lc) if l.startswith('"'))]

@@ -10,3 +10,5 @@ $B > gpurun_out/${tag}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${tag}_launches.csv $B > gpurun_out/${tag}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k gather_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_gather -f $B > gpurun_out/${tag}_ncu_gather.log 2>&1
 ncu --set full --clock-control none --import-source on -k march_steps_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_march -f $B > gpurun_out/${tag}_ncu_march.log 2>&1
+# the shooter: volume-only and all-maps instantiations (the first launches of a run are the volume-only waves, then pv_shoot_maps)
+ncu --set full --clock-control none --import-source on -k regex:shoot_kernel -c 10 -o gpurun_out/${tag}_shoot -f $B > gpurun_out/${tag}_ncu_shoot.log 2>&1
