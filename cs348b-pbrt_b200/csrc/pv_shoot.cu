@@ -66,6 +66,66 @@ __device__ __noinline__ float shoot_tau(SH_TAU_MED m, float ox, float oy, float 
                                         float stepSize, float u, uint32_t *nsamples) {
     return med_tau_scalar(m, V3(ox, oy, oz), V3(dx, dy, dz), mint, maxt, stepSize, u, nsamples);
 }
+// EXPERIMENT (SH_COOP_TAU=1, off by default; see DESIGN.md "Shooter experiments"): warp-cooperative DensityRegion::tau
+// (core/volume.cpp:296-310) for a density-grid medium.  The lanes of a full warp pool the samples of all their pending tau
+// evaluations: each owner lane enumerates its sample parameters t_j exactly as the scalar loop does (SH_SLOTS at a time) into
+// its row of `vals`; the rows are flattened with a prefix sum and the lanes take the samples round-robin (owner by binary
+// search over the prefix table, the owner's ray by shuffle, result written over t_j); each owner adds its row up IN ORDER.
+// Same sample points, same summation order: bit-identical to med_tau_scalar.  Every lane of the warp must call.
+#ifndef SH_SLOTS
+#define SH_SLOTS 16
+#endif
+#ifndef SH_COOP_TAU
+#define SH_COOP_TAU 0
+#endif
+template <class Med>
+__device__ __forceinline__ float coop_tau(const Med &m, uint32_t lane, bool want, v3 o, v3 d, float mint, float maxt,
+                                          float stepSize, float u, float *vals, uint32_t *pref, uint32_t *nsamples) {
+    float tcur = 0.f, tend = 0.f, sum = 0.f;
+    v3 dn = V3(0.f, 0.f, 0.f);
+    bool has = false;
+    if (want) {
+        const float length = vlen(d);
+        if (length != 0.f) {
+            dn = vdiv(d, length);
+            float t0, t1;
+            if (med_intersectp(m, o, dn, mint * length, maxt * length, &t0, &t1)) { has = true; tcur = t0 + u * stepSize; tend = t1; }
+        }
+    }
+    for (;;) {
+        uint32_t n = 0;
+        if (has) while (n < SH_SLOTS && tcur < tend) { vals[lane * SH_SLOTS + n] = tcur; tcur += stepSize; ++n; }
+        uint32_t inc = n;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(PV_FULL, inc, off); if (lane >= (uint32_t)off) inc += t; }
+        const uint32_t total = __shfl_sync(PV_FULL, inc, 31);
+        if (total == 0) break;
+        pref[lane] = inc - n;
+        if (lane == 0) pref[32] = total;
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < total;
+            uint32_t owner = 0;
+            if (valid) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) if (pref[owner + sft] <= i) owner += sft;
+            }
+            const float ox = __shfl_sync(PV_FULL, o.x, owner), oy = __shfl_sync(PV_FULL, o.y, owner), oz = __shfl_sync(PV_FULL, o.z, owner);
+            const float dx = __shfl_sync(PV_FULL, dn.x, owner), dy = __shfl_sync(PV_FULL, dn.y, owner), dz = __shfl_sync(PV_FULL, dn.z, owner);
+            if (valid) {
+                float *slot = vals + owner * SH_SLOTS + (i - pref[owner]);
+                *slot = grid_density(m, med_to_volume_p(m, ray_at(V3(ox, oy, oz), V3(dx, dy, dz), *slot)));
+            }
+        }
+        __syncwarp();
+        for (uint32_t k = 0; k < n; ++k) sum += vals[lane * SH_SLOTS + k];
+        if (nsamples) *nsamples += n;
+        __syncwarp();
+    }
+    return sum * stepSize;
+}
+
 struct PathRng {
     uint32_t c0, c1, j, pos, k0, k1, buf[4];
     __device__ __forceinline__ void reset(uint64_t path, uint32_t key0, uint32_t key1) {
@@ -184,6 +244,10 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
     __shared__ uint32_t s_perm[41];
     __shared__ float s_minmax[3];
+#if SH_COOP_TAU
+    __shared__ float s_tau_vals[SH_THREADS / 32][32 * SH_SLOTS];
+    __shared__ uint32_t s_tau_pref[SH_THREADS / 32][33];
+#endif
     const DevScene &sc = *a.sc;
     const DevMedium &gmed = sc.med;
     const MedView med = make_medview(gmed);             // extent / grid dimensions / grid pointer in registers
@@ -219,6 +283,9 @@ SH_UNROLL_BINS
         // TRACE they all trace together -- the segment march, where nearly all the time goes, runs with full warps.
         if (__all_sync(PV_FULL, state == ST_DONE)) break;
         const bool short_round = __any_sync(PV_FULL, state == ST_NEWPATH || state == ST_SURFACE);
+#if SH_COOP_TAU
+        const uint32_t part = __ballot_sync(PV_FULL, state == ST_TRACE);      // the lanes of a TRACE round (all of them, except at the very end)
+#endif
         if (state == ST_DONE || (short_round && state == ST_TRACE)) continue;
         if (state == ST_NEWPATH) {
             // ---- fetch a light path (warp-aggregated counter) and emit it: photonshooter.cpp:248-275
@@ -301,6 +368,11 @@ SH_UNROLL_BINS
             BvhCounters bc = {0, 0};
             int prim = bvh_traverse<false, SPH>(sc, o, d, cur.mint, &thit, &bc);
             c_nodes += bc.nodes; c_tris += bc.tris;
+#if SH_COOP_TAU
+            bool marching = false, interaction = false;
+            v3 rnd = V3(0.f, 0.f, 0.f);
+            float t0 = 1.0f, t1 = 0.0f, t_i = 0.f, xi = 0.f;
+#endif
             if (prim < 0) pop = true;
             else {
                 // hit record: shapes/trianglemesh.cpp:160-205 with default uvs, core/diffgeom.cpp:40-55
@@ -324,6 +396,31 @@ SH_UNROLL_BINS
                 float length = vlen(d);
                 if (length == 0.f) pop = true;
                 else {
+#if SH_COOP_TAU
+                    rnd = vdiv(d, length);
+                    if (!med_intersectp(med, o, rnd, cur.mint * length, cur.maxt * length, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
+                    t0 += rng.next() * a.stepsize;
+                    t_i = t0;
+                    xi = rng.next();
+                    marching = true;
+                }
+            }
+            {
+                {
+                    const bool coop = med.type == PV_MEDIUM_GRID && part == PV_FULL;
+                    for (;;) {
+                        const bool step = marching && !interaction && t0 < t1;
+                        if (coop ? !__any_sync(PV_FULL, step) : !step) break;
+                        float uo = 0.f;
+                        if (step) uo = rng.next();
+                        uint32_t ns = 0;
+                        float s;
+                        if (coop) s = coop_tau(med, threadIdx.x & 31, step, o, rnd, t_i, t0, a.istep4, uo, s_tau_vals[threadIdx.x >> 5],
+                                               s_tau_pref[threadIdx.x >> 5], &ns);
+                        else s = shoot_tau(med, o.x, o.y, o.z, rnd.x, rnd.y, rnd.z, t_i, t0, a.istep4, uo, &ns);
+                        c_dens += ns;
+                        if (!step) continue;
+#else
                     v3 rnd = vdiv(d, length);
                     float t0, t1;
                     if (!med_intersectp(med, o, rnd, cur.mint * length, cur.maxt * length, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
@@ -336,6 +433,7 @@ SH_UNROLL_BINS
                         uint32_t ns = 0;
                         float s = shoot_tau(med, o.x, o.y, o.z, rnd.x, rnd.y, rnd.z, t_i, t0, a.istep4, uo, &ns);
                         c_dens += ns;
+#endif
                         // xi > Tr.y() ?  y(exp(-sig_t s)) lies between exp(-st_max s) y1 and exp(-st_min s) y1
                         bool hitv;
                         float elo = expf(-(st_max * s)) * y_one, ehi = expf(-(st_min * s)) * y_one;
@@ -347,9 +445,16 @@ SH_UNROLL_BINS
                             for (int b = 0; b < PV_NSPEC; ++b) yy += s_cie[b] * expf(-(s_st[b] * s));
                             hitv = xi > __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC);
                         }
+#if SH_COOP_TAU
+                        if (hitv) { interaction = true; continue; }
+#else
                         if (hitv) { interaction = true; break; }
+#endif
                         t0 += a.stepsize;
                     }
+#if SH_COOP_TAU
+                    if (!marching) { /* no segment to march: pop is set */ } else
+#endif
                     if (interaction) {
                         v3 pt = ray_at(o, rnd, t0);
                         uint32_t ns = 0;
