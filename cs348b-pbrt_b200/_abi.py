@@ -97,11 +97,14 @@ class MapsStats(C.Structure):
                 ("replayed_blocks", C.c_uint64), ("shoot", ShootStats)]
 
 
+ALLREDUCE_U32_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_void_p)
+
+
 # every symbol include/pv.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_set_scene", "pv_set_photons",
     "pv_set_photons_dev", "pv_get_photons", "pv_get_photons_dev", "pv_photon_count", "pv_build", "pv_knn",
     "pv_intersect", "pv_occluded", "pv_transmittance", "pv_gather", "pv_gather_dev", "pv_lphoton",
     "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
-    "pv_shoot_maps", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons",
+    "pv_shoot_maps", "pv_shoot_maps_ranks", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons",
 ]

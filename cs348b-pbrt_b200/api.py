@@ -147,6 +147,26 @@ class PhotonVolume:
         self._chk(self.lib.pv_shoot_maps(self.ctx, C.byref(mp), C.byref(prm), C.byref(st)))
         return st
 
+    def PreprocessMapsRanks(self, n_volume_wanted, n_caustic_wanted, n_indirect_wanted, final_gather, rank, world, allreduce, stepsize=0.1,
+                            max_photon_depth=5, max_paths=0, integrator_stepsize=None):
+        """pv_shoot_maps_ranks: the all-maps pass sharded by 4096-path blocks.  `allreduce(np.ndarray[uint32])` sums the array in
+        place over all ranks (see multigpu.allreduce_counts)."""
+        prm = A.ShootParams(float(stepsize), float(self.stepsize if integrator_stepsize is None else integrator_stepsize),
+                            int(max_photon_depth), self.seed, int(rank), int(world), max_paths, 0.0)
+        mp = A.MapsParams(int(n_volume_wanted), int(n_caustic_wanted), int(n_indirect_wanted), 1 if final_gather else 0)
+        st = A.MapsStats()
+
+        def _cb(data, n, user):
+            try:
+                allreduce(np.ctypeslib.as_array(data, shape=(int(n),)))
+                return 0
+            except Exception:                      # never unwind through the C frames
+                import traceback; traceback.print_exc()
+                return 1
+        cb = A.ALLREDUCE_U32_FN(_cb)
+        self._chk(self.lib.pv_shoot_maps_ranks(self.ctx, C.byref(mp), C.byref(prm), cb, None, C.byref(st)))
+        return st
+
     def get_map_photons(self, which, capacity=None):
         n = C.c_uint64(0)
         self._chk(self.lib.pv_get_map_photons(self.ctx, C.c_int(which), None, None, None, None, C.c_uint64(1 << 62), C.byref(n)))

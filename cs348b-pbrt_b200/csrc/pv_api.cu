@@ -455,7 +455,13 @@ int pv_shoot_finish(pv_ctx *ctx, uint64_t last_block) {
 int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params, pv_maps_stats *stats) {
     LOCK(ctx);
     if (!maps || !params) { ctx->err = "pv_shoot_maps: null params"; return PV_EINVAL; }
-    return pvi_shoot_maps(ctx, maps, params, stats);
+    return pvi_shoot_maps(ctx, maps, params, nullptr, nullptr, stats);
+}
+int pv_shoot_maps_ranks(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params, pv_allreduce_u32_fn allreduce, void *user,
+                        pv_maps_stats *stats) {
+    LOCK(ctx);
+    if (!maps || !params) { ctx->err = "pv_shoot_maps_ranks: null params"; return PV_EINVAL; }
+    return pvi_shoot_maps(ctx, maps, params, allreduce, user, stats);
 }
 int pv_get_map_photons(pv_ctx *ctx, int map, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t capacity, uint64_t *n) {
     LOCK(ctx);

@@ -121,7 +121,8 @@ int pvi_reserve_photons(pv_ctx *ctx, uint64_t n);
 int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats);
 int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block);
 int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm, pv_shoot_stats *stats);
-int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm, pv_maps_stats *out);
+int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm, pv_allreduce_u32_fn allreduce, void *user,
+                   pv_maps_stats *out);
 int pvi_reserve_set(pv_ctx *ctx, PhotonSet *s, uint64_t n);
 void pvi_free_set(PhotonSet *s);
 // pv_gather.cu

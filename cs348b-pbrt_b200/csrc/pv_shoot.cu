@@ -953,10 +953,15 @@ int pvi_shoot(pv_ctx *ctx, uint64_t n_wanted, const pv_shoot_params *prm_in, pv_
 // blocks is traced with the flags held constant; the host then replays the reference's per-block bookkeeping over the
 // per-class counts, and if a flag flips at block M inside the wave, the wave is rolled back and traced again up to M
 // (it is deterministic), so that every later block sees the new flags.  Waves aim just short of the next expected flip.
-int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm_in, pv_maps_stats *out) {
+// Several ranks: every rank traces the blocks b with (b - 1) % world == rank of each wave, the per-class, per-block counts are
+// summed over ranks through `allreduce`, and every rank then replays the SAME bookkeeping on the same numbers -- flags, flips,
+// roll-backs and the last block come out identical everywhere without any other communication.
+int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *prm_in, pv_allreduce_u32_fn allreduce, void *user,
+                   pv_maps_stats *out) {
     pv_shoot_params prm = *prm_in;
     pv_maps_stats ms; memset(&ms, 0, sizeof(ms));
-    if (prm.world != 1 || prm.rank != 0) { ctx->err = "pv_shoot_maps: single rank only"; return PV_EINVAL; }
+    if (prm.world < 1 || prm.rank >= prm.world) { ctx->err = "pv_shoot_maps: bad rank / world"; return PV_EINVAL; }
+    if (prm.world > 1 && !allreduce) { ctx->err = "pv_shoot_maps: world > 1 needs pv_shoot_maps_ranks with an all-reduce callback"; return PV_EINVAL; }
     const uint64_t wanted[3] = {mp->n_volume_wanted, mp->n_caustic_wanted, mp->n_indirect_wanted};     // by class id
     bool done[3] = {wanted[0] == 0, wanted[1] == 0, wanted[2] == 0};
     ctx->n_photons = 0; ctx->built = false; ctx->rad_valid = false;
@@ -976,6 +981,7 @@ int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params 
         const uint64_t n_before = ctx->n_photons, first = block + 1;
         counts.assign((size_t)wave * (PC_COUNT + 1), 0);
         rc = shoot_wave(ctx, first, wave, &prm, flags, counts.data(), &ms.shoot); if (rc) return rc;
+        if (prm.world > 1 && allreduce(counts.data(), counts.size(), user) != 0) { ctx->err = "pv_shoot_maps: the all-reduce callback failed"; return PV_EINVAL; }
         bool flip = false;
         uint32_t used = 0;
         for (uint32_t i = 0; i < wave; ++i) {
@@ -1008,7 +1014,7 @@ int pvi_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params 
             ctx->n_photons = n_before;
             counts.assign((size_t)used * (PC_COUNT + 1), 0);
             rc = shoot_wave(ctx, first, used, &prm, flags, counts.data(), &ms.shoot); if (rc) return rc;
-            ms.replayed_blocks += used;
+            ms.replayed_blocks += used;                      // (the counts of the replay are the ones already booked: no second all-reduce)
         }
         if (!finished) {
             // next wave: 97% of the way to the nearest expected flip, from the yields seen so far

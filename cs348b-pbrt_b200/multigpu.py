@@ -21,6 +21,23 @@ def next_wave(total, blocks_done, target, world, cap=262144):
     return int(min(max((target - total) / per_block * 1.03 + 8, 64 * world), cap))
 
 
+def allreduce_counts(dist, torch, device):
+    """The callback PhotonVolume.PreprocessMapsRanks wants: sums a uint32 numpy array in place over all ranks (per-class,
+    per-block deposit counts of one wave of the sharded all-maps pass)."""
+    def fn(arr):
+        t = torch.from_numpy(arr.astype(np.int64)).to(device)
+        dist.all_reduce(t)
+        arr[:] = t.cpu().numpy().astype(np.uint32)
+    return fn
+
+
+def merge_by_id(parts):
+    """Per-rank photon lists (pos, wi, alpha, ids), each ordered by id -> the global list ordered by id (= the single-rank order)."""
+    ids = np.concatenate([p[3] for p in parts])
+    order = np.argsort(ids, kind="stable")
+    return tuple(np.concatenate([p[k] for p in parts])[order] for k in range(4))
+
+
 def allgather_photons(dist, torch, pos, wi, alpha, device):
     """Replicate the photon planes of all ranks (rank order, i.e. global photon order).  Slices may differ in length:
     planes are padded to the longest slice for all_gather_into_tensor and the padding is dropped afterwards.

@@ -275,6 +275,16 @@ typedef struct pv_maps_stats {
  * ids = class << 60 | path index << 16 | deposit ordinal along the path.                         */
 int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params,
                   pv_maps_stats *stats);
+/* The same pass sharded over params->world ranks (one process per GPU): rank r traces the 4096-path
+ * blocks b with (b-1) % world == r.  `allreduce` must sum data[0..n) in place over all ranks
+ * (ncclAllReduce / torch.distributed.all_reduce on a staging tensor) and return 0; it is called once
+ * per wave with the per-class, per-block deposit counts, after which every rank replays the same
+ * bookkeeping, so flags, roll-backs and the last block agree everywhere.  Afterwards each rank
+ * holds ITS photons of every class (ordered by id); the union over ranks, ordered by id, is exactly
+ * the single-rank result.  stats->n[] are local counts, the path counts and nshot are global.      */
+typedef int (*pv_allreduce_u32_fn)(uint32_t *data, uint64_t n, void *user);
+int pv_shoot_maps_ranks(pv_ctx *ctx, const pv_maps_params *maps, const pv_shoot_params *params,
+                        pv_allreduce_u32_fn allreduce, void *user, pv_maps_stats *stats);
 /* SoA planes like pv_get_photons.  PV_MAP_RADIANCE: wi = faceforwarded normal, alpha = rho_r
  * (rho_t == 0: only matte surfaces hold radiance photons on this path).                          */
 int pv_get_map_photons(pv_ctx *ctx, int map, float *pos, float *wi, float *alpha,

@@ -408,3 +408,52 @@ def test_radiance_then_volume_gather_still_works(golden, pv_factory):
     pv.build()
     nf1, idx1, d1 = pv.Lookup(pts)
     assert np.array_equal(nf0, nf1) and np.array_equal(idx0, idx1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell_surf", "rainbow_surf"])
+def test_all_maps_sharded_over_two_ranks_reproduce_single_rank(golden, pv_factory, pkg, name):
+    """pv_shoot_maps_ranks: emission dealt to 2 ranks by 4096-path blocks (two contexts on one GPU, driven by two threads whose
+    all-reduce callback meets at a barrier).  Both ranks must take the same decisions (flag flips, roll-backs, last block) and the
+    union of their photons, ordered by id, must be the single-rank result bit for bit -- for every photon class."""
+    import threading
+    from cs348b_pbrt_b200 import multigpu as MG
+    g, scene = golden(name)
+    nv, nc, ni, fg, sstep, istep = g["params"][:6]
+    args = (int(nv), int(nc), int(ni), bool(fg))
+    pv1 = pv_factory(stepsize=float(istep), seed=17); pv1.set_scene(scene)
+    st1 = pv1.PreprocessMaps(*args, stepsize=float(sstep), max_photon_depth=5)
+    world = 2
+    pvs = []
+    for r in range(world):
+        p = pv_factory(stepsize=float(istep), seed=17); p.set_scene(scene); pvs.append(p)
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    stats = [None] * world; errs = []
+
+    def run(r):
+        def allreduce(arr):
+            slots[r] = arr.copy()
+            barrier.wait(timeout=120)
+            total = sum(s.astype(np.uint64) for s in slots).astype(np.uint32)
+            barrier.wait(timeout=120)
+            arr[:] = total
+        try:
+            stats[r] = pvs[r].PreprocessMapsRanks(*args, rank=r, world=world, allreduce=allreduce, stepsize=float(sstep), max_photon_depth=5)
+        except Exception as e:          # pragma: no cover
+            errs.append(e); barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th: t.start()
+    for t in th: t.join(timeout=300)
+    assert not errs, errs
+    for r in range(world):
+        s = stats[r]
+        assert (s.nshot, s.blocks, s.n_caustic_paths, s.n_indirect_paths, s.n_direct_paths, s.n_volume_paths) == (
+            st1.nshot, st1.blocks, st1.n_caustic_paths, st1.n_indirect_paths, st1.n_direct_paths, st1.n_volume_paths)
+    for which in range(5):
+        want = pv1.get_map_photons(which)
+        got = MG.merge_by_id([p.get_map_photons(which) for p in pvs])
+        assert sum(int(stats[r].n[which]) for r in range(world)) == int(st1.n[which]) == len(want[3])
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), which
+    assert min(int(stats[r].n[0]) for r in range(world)) > 0          # both ranks really traced photons

@@ -20,6 +20,16 @@ def test_last_block_rule():
     assert MG.next_wave(100, 10, 1000, 2) >= 90
 
 
+def test_merge_by_id_restores_the_single_rank_order():
+    rng = np.random.default_rng(1)
+    ids = np.sort(rng.choice(10_000, size=500, replace=False)).astype(np.uint64)
+    pos = rng.random((500, 3)).astype(np.float32); wi = rng.random((500, 3)).astype(np.float32); alpha = rng.random((500, 30)).astype(np.float32)
+    pick = rng.random(500) < 0.4                                   # photons of "rank 0"; both parts stay ordered by id
+    parts = [(pos[m], wi[m], alpha[m], ids[m]) for m in (pick, ~pick)]
+    got = MG.merge_by_id(parts)
+    assert np.array_equal(got[3], ids) and np.array_equal(got[0], pos) and np.array_equal(got[2], alpha)
+
+
 def test_photon_slices_partition_the_set():
     n = 7_300_000
     for world in (1, 2, 3, 8):
@@ -56,6 +66,10 @@ def _worker(rank, world, port, q):
             counts[i] = 10 + i
     t = torch.from_numpy(counts.copy()); dist.all_reduce(t)
     last, total, used = MG.last_block(t.numpy(), 1, 0, 100)
+    # the all-reduce callback of the sharded all-maps pass (uint32 counts in place) and the id merge of per-rank photon lists
+    cnt = np.arange(12, dtype=np.uint32) * (rank + 1)
+    MG.allreduce_counts(dist, torch, dev)(cnt)
+    ok = ok and np.array_equal(cnt, np.arange(12, dtype=np.uint32) * 3)
     q.put((rank, ok, last, total, used))
     dist.destroy_process_group()
 
