@@ -8,7 +8,7 @@ import ctypes as C
 NSPEC = 30
 PV_OK, PV_EINVAL, PV_ECUDA, PV_ENOMEM, PV_ESTATE, PV_ENOPHOTONS = 0, -1, -2, -3, -4, -5
 LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2
-MEDIUM_NONE, MEDIUM_HOMOGENEOUS, MEDIUM_GRID, MEDIUM_RAINBOW = 0, 1, 2, 3
+MEDIUM_NONE, MEDIUM_HOMOGENEOUS, MEDIUM_GRID, MEDIUM_RAINBOW, MEDIUM_EXPONENTIAL = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_GLASS = 0, 1
 GATHER_NO_DIRECT, GATHER_NO_INDIRECT = 1, 2
 

@@ -137,7 +137,10 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
         d.g = m->g; d.nx = m->nx; d.ny = m->ny; d.nz = m->nz;
         static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
         d.identity = memcmp(d.w2v, ident, sizeof(ident)) == 0;
-        if (m->type == PV_MEDIUM_GRID) {
+        if (m->type == PV_MEDIUM_EXPONENTIAL && (!m->density || m->nx != 5 || m->ny != 1 || m->nz != 1)) {
+            ctx->err = "pv_set_scene: exponential medium wants density = {a, b, updir.xyz}, nx = 5, ny = nz = 1"; return PV_EINVAL;
+        }
+        if (m->type == PV_MEDIUM_GRID || m->type == PV_MEDIUM_EXPONENTIAL) {
             if (!m->density || m->nx < 1 || m->ny < 1 || m->nz < 1) { ctx->err = "pv_set_scene: grid medium without density"; return PV_EINVAL; }
             if ((rc = upload(ctx, &ctx->d_density, m->density, sizeof(float) * (size_t)m->nx * m->ny * m->nz))) return rc;
             d.density = (const float *)ctx->d_density;

@@ -21,6 +21,7 @@
 #define PV_FULL 0xffffffffu
 
 struct DevMedium {
+    static constexpr bool kExp = true;      // may be an exponential medium (see MedViewPlain)
     int type;
     float w2v[16];
     float p0[3], p1[3];
@@ -53,14 +54,19 @@ struct DevScene {
 // extent, the grid dimensions and the grid pointer.  Same field names as DevMedium: the medium functions below are
 // templates over either.
 struct MedView {
+    static constexpr bool kExp = true;
     int type, identity, nx, ny, nz;
     float g;
     float p0[3], p1[3];
     const float *density;
     float w2v[16];
 };
-__device__ __forceinline__ MedView make_medview(const DevMedium &m) {
-    MedView v;
+// the same view for kernels instantiated for scenes WITHOUT an exponential medium: the density sampler then carries no
+// trace of that case (the shooter is sensitive to every instruction in it)
+struct MedViewPlain : MedView { static constexpr bool kExp = false; };
+template <class MV>
+__device__ __forceinline__ MV make_medview(const DevMedium &m) {
+    MV v;
     v.type = m.type; v.identity = m.identity; v.nx = m.nx; v.ny = m.ny; v.nz = m.nz; v.g = m.g; v.density = m.density;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { v.p0[i] = m.p0[i]; v.p1[i] = m.p1[i]; }
@@ -143,10 +149,17 @@ __device__ __forceinline__ float grid_D(const Med &m, int x, int y, int z) {    
     x = min(max(x, 0), m.nx - 1); y = min(max(y, 0), m.ny - 1); z = min(max(z, 0), m.nz - 1);
     return __ldg(m.density + ((size_t)z * m.nx * m.ny + (size_t)y * m.nx + x));
 }
-// volumes/volumegrid.cpp:39-57
+// ExponentialDensity::Density (volumes/exponential.h:57-61) for a point inside the extent, given Pobj - extent.pMin;
+// e = {a, b, updir.xyz}.  Out of line: the trilinear sampler below is inlined in several hot loops and must stay small.
+static __device__ __noinline__ float exp_density(const float *e, float dx, float dy, float dz) {
+    const float height = dx * __ldg(e + 2) + dy * __ldg(e + 3) + dz * __ldg(e + 4);
+    return __ldg(e) * expf(-__ldg(e + 1) * height);
+}
+// volumes/volumegrid.cpp:39-57 (and the exponential medium, which shares the DensityRegion code paths)
 template <class Med>
 __device__ __forceinline__ float grid_density(const Med &m, v3 Pobj) {
     if (!bbox_inside(m.p0, m.p1, Pobj)) return 0.f;
+    if (Med::kExp && m.type == PV_MEDIUM_EXPONENTIAL) return exp_density(m.density, Pobj.x - m.p0[0], Pobj.y - m.p0[1], Pobj.z - m.p0[2]);
     float vx_ = __fdiv_rn(Pobj.x - m.p0[0], m.p1[0] - m.p0[0]);
     float vy_ = __fdiv_rn(Pobj.y - m.p0[1], m.p1[1] - m.p0[1]);
     float vz_ = __fdiv_rn(Pobj.z - m.p0[2], m.p1[2] - m.p0[2]);

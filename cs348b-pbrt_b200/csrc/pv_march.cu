@@ -74,7 +74,7 @@ template <bool SPH>
 __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(MarchArgs a) {
     const DevScene &sc = *a.sc;
     const DevMedium &gmed = sc.med;
-    const MedView med = make_medview(gmed);             // extent / grid dimensions / grid pointer in registers
+    const MedView med = make_medview<MedView>(gmed);             // extent / grid dimensions / grid pointer in registers
     const uint32_t lane = threadIdx.x & 31;
     float sig_t_max = 0.f; bool any_sig_s = false;
     for (int bb = 0; bb < PV_NSPEC; ++bb) { sig_t_max = fmaxf(sig_t_max, gmed.sigma_a[bb] + gmed.sigma_s[bb]); any_sig_s |= gmed.sigma_s[bb] != 0.f; }

@@ -14,6 +14,7 @@
 // nshot = 4096*b (Q4), independent of the number of ranks.  Deposits are appended with warp-aggregated atomics
 // (one atomicAdd per coalesced group) into SoA planes; the 30-bin alpha goes out as one 128-byte line (8 x float4).
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include <cooperative_groups.h>
 #include "pv_ctx.h"
@@ -59,9 +60,10 @@ __device__ __noinline__ uint4 path_philox_block(uint32_t c0, uint32_t c1, uint32
     return make_uint4(out[0], out[1], out[2], out[3]);
 }
 #ifndef SH_TAU_MED
-#define SH_TAU_MED const MedView
+#define SH_TAU_MED const MV
 #endif
 // One copy of DensityRegion::tau for the shooter's two call sites (free-flight march, surface transmittance)
+template <class MV>
 __device__ __noinline__ float shoot_tau(SH_TAU_MED m, float ox, float oy, float oz, float dx, float dy, float dz, float mint, float maxt,
                                         float stepSize, float u, uint32_t *nsamples) {
     return med_tau_scalar(m, V3(ox, oy, oz), V3(dx, dy, dz), mint, maxt, stepSize, u, nsamples);
@@ -239,8 +241,12 @@ __device__ __forceinline__ float fresnel_dielectric(float cosi, float ior) {
 #ifndef SH_MIN_CTAS
 #define SH_MIN_CTAS 8                // 32 warps/SM at 64 registers: latency-bound on density taps, the spills cost less than the occupancy gains (measured 4: 40.9 ms, 6: 36.1 ms, 8: 35.2 ms)
 #endif
-template <bool SURF, bool SPH>
+// KIND: bit 0 = the scene holds sphere primitives, bit 1 = the medium is exponential.  Plain scenes (triangles; homogeneous,
+// rainbow or grid medium) run an instantiation that carries no trace of the other cases.
+template <bool SURF, int KIND>
 __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
+    constexpr bool SPH = (KIND & 1) != 0;
+    typedef typename std::conditional<(KIND & 2) != 0, MedView, MedViewPlain>::type MV;
     __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
     __shared__ uint32_t s_perm[41];
     __shared__ float s_minmax[3];
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArg
 #endif
     const DevScene &sc = *a.sc;
     const DevMedium &gmed = sc.med;
-    const MedView med = make_medview(gmed);             // extent / grid dimensions / grid pointer in registers
+    const MV med = make_medview<MV>(gmed);             // extent / grid dimensions / grid pointer in registers
     if (threadIdx.x < PV_NSPEC) {
         s_cie[threadIdx.x] = sc.cie_y[threadIdx.x]; s_sa[threadIdx.x] = gmed.sigma_a[threadIdx.x];
         s_ss[threadIdx.x] = gmed.sigma_s[threadIdx.x]; s_st[threadIdx.x] = gmed.sigma_a[threadIdx.x] + gmed.sigma_s[threadIdx.x];
@@ -770,9 +776,11 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks * n_cls, ctx->stream));
         int per_sm = 0;
-        const bool sph = ctx->hscene.n_spheres != 0;
-        void (*kern)(ShootArgs) = surf ? (sph ? shoot_kernel<true, true> : shoot_kernel<true, false>)
-                                       : (sph ? shoot_kernel<false, true> : shoot_kernel<false, false>);
+        const int kind = (ctx->hscene.n_spheres != 0 ? 1 : 0) | (ctx->hscene.med.type == PV_MEDIUM_EXPONENTIAL ? 2 : 0);
+        static void (*const kerns[2][4])(ShootArgs) = {
+            {shoot_kernel<false, 0>, shoot_kernel<false, 1>, shoot_kernel<false, 2>, shoot_kernel<false, 3>},
+            {shoot_kernel<true, 0>, shoot_kernel<true, 1>, shoot_kernel<true, 2>, shoot_kernel<true, 3>}};
+        void (*kern)(ShootArgs) = kerns[surf ? 1 : 0][kind];
         PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SH_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         uint64_t total = (uint64_t)n_local * SH_BLOCK;

@@ -155,7 +155,17 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             m.nx = gd->nx; m.ny = gd->ny; m.nz = gd->nz;
             hs.density.assign(gd->density, gd->density + (size_t)gd->nx * gd->ny * gd->nz);
             m.density = hs.density.data();
-        } else { err = "pv: unsupported volume region (homogeneous, volumegrid and rainbow are on this path)"; return false; }
+        } else if (ExponentialDensity *ed = dynamic_cast<ExponentialDensity *>(vr)) {
+            m.type = PV_MEDIUM_EXPONENTIAL;                     // volumes/exponential.h:43-68: {a, b, updir} travel in the density slot
+            pv_mat_out(ed->WorldToVolume, m.world_to_volume);
+            m.p0[0] = ed->extent.pMin.x; m.p0[1] = ed->extent.pMin.y; m.p0[2] = ed->extent.pMin.z;
+            m.p1[0] = ed->extent.pMax.x; m.p1[1] = ed->extent.pMax.y; m.p1[2] = ed->extent.pMax.z;
+            pv_spec_out(ed->sig_a, m.sigma_a); pv_spec_out(ed->sig_s, m.sigma_s); pv_spec_out(ed->le, m.le); m.g = ed->g;
+            m.nx = 5; m.ny = 1; m.nz = 1;
+            const float prm[5] = {ed->a, ed->b, ed->upDir.x, ed->upDir.y, ed->upDir.z};
+            hs.density.assign(prm, prm + 5);
+            m.density = hs.density.data();
+        } else { err = "pv: unsupported volume region (homogeneous, volumegrid, exponential and rainbow are on this path)"; return false; }
         hs.has_medium = true;
     }
     pv_scene_desc &d = hs.desc;
@@ -192,7 +202,7 @@ static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
         ok = fwrite(&m.type, 4, 1, f) == 1 && fwrite(m.world_to_volume, 4, 16, f) == 16 && fwrite(m.p0, 4, 3, f) == 3 &&
              fwrite(m.p1, 4, 3, f) == 3 && fwrite(m.sigma_a, 4, 30, f) == 30 && fwrite(m.sigma_s, 4, 30, f) == 30 &&
              fwrite(m.le, 4, 30, f) == 30 && fwrite(&m.g, 4, 1, f) == 1 && fwrite(dims, 4, 3, f) == 3;
-        if (ok && m.type == PV_MEDIUM_GRID) ok = fwrite(hs.density.data(), 4, hs.density.size(), f) == hs.density.size();
+        if (ok && (m.type == PV_MEDIUM_GRID || m.type == PV_MEDIUM_EXPONENTIAL)) ok = fwrite(hs.density.data(), 4, hs.density.size(), f) == hs.density.size();
     }
     if (ok && d.n_spheres)
         ok = fwrite(hs.prim_shape.data(), 4, hs.prim_shape.size(), f) == hs.prim_shape.size() &&

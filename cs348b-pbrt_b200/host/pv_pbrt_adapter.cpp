@@ -55,6 +55,7 @@
 #include "lights/distant.h"
 #include "volumes/homogeneous.h"
 #include "volumes/volumegrid.h"
+#include "volumes/exponential.h"
 #include "volumes/rainbow.h"
 #include "materials/matte.h"
 #include "materials/glass.h"

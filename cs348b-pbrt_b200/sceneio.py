@@ -97,7 +97,7 @@ def read_scene(path):
             m.sigma_a[i] = float(vals[22 + i]); m.sigma_s[i] = float(vals[52 + i]); m.le[i] = float(vals[82 + i])
         m.g = float(vals[112])
         m.nx, m.ny, m.nz = struct.unpack_from("<3i", buf, off); off += 12
-        if m.type == A.MEDIUM_GRID:
+        if m.type in (A.MEDIUM_GRID, A.MEDIUM_EXPONENTIAL):          # exponential: {a, b, updir.xyz} in the density slot
             cnt = m.nx * m.ny * m.nz
             s.density = np.frombuffer(buf, dtype=np.float32, count=cnt, offset=off).copy(); off += 4 * cnt
         s.medium = m
@@ -123,7 +123,7 @@ def write_scene(path, s):
             f.write(np.array(list(m.world_to_volume) + list(m.p0) + list(m.p1) + list(m.sigma_a) + list(m.sigma_s)
                              + list(m.le) + [m.g], dtype=np.float32).tobytes())
             f.write(struct.pack("<3i", m.nx, m.ny, m.nz))
-            if m.type == A.MEDIUM_GRID:
+            if m.type in (A.MEDIUM_GRID, A.MEDIUM_EXPONENTIAL):
                 f.write(np.asarray(s.density, dtype=np.float32).tobytes())
         if len(s.spheres):
             f.write(np.asarray(s.prim_shape, dtype=np.uint32).tobytes()); f.write(bytes(s.spheres))

@@ -76,6 +76,11 @@ HOMOG_VOLUME = ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s"
                 '  "point p0" [-1 -1 -1] "point p1" [1 1 1]')
 
 
+# ExponentialDensity (volumes/exponential.h): density a * exp(-b * height above the extent's floor)
+EXP_VOLUME = ('Volume "exponential" "color sigma_a" [.3 .3 .3] "color sigma_s" [.6 .6 .6] "float g" [0.2]\n'
+              '  "point p0" [-1 -1 -1] "point p1" [1 1 1] "float a" [2] "float b" [1.5] "vector updir" [0.2 1 0.1]')
+
+
 # BASELINE config 1: the parameters of the reference's projectScene/volumescene_png.pbrt (rainbow medium, distant light,
 # three matte quads, photonmap surface integrator with final gathering), with the counts / resolution / output as knobs.
 VOLUMESCENE_TEMPLATE = """# BASELINE.json configs[0]: rainbow-volume scene of the reference project

@@ -74,7 +74,7 @@ typedef struct pv_light {
 } pv_light;
 
 enum { PV_MEDIUM_NONE = 0, PV_MEDIUM_HOMOGENEOUS = 1, PV_MEDIUM_GRID = 2,
-       PV_MEDIUM_RAINBOW = 3 };
+       PV_MEDIUM_RAINBOW = 3, PV_MEDIUM_EXPONENTIAL = 4 };
 typedef struct pv_medium {
     int32_t type;
     float   world_to_volume[16];    /* row-major                                  */
@@ -82,7 +82,10 @@ typedef struct pv_medium {
     float   sigma_a[PV_NSPEC], sigma_s[PV_NSPEC], le[PV_NSPEC];
     float   g;
     int32_t nx, ny, nz;             /* grid only (volumes/volumegrid.h:66-70)     */
-    const float *density;           /* host, nx*ny*nz, index z*nx*ny + y*nx + x   */
+    const float *density;           /* host, nx*ny*nz, index z*nx*ny + y*nx + x.
+                                       PV_MEDIUM_EXPONENTIAL (volumes/exponential.h:43-68):
+                                       nx = 5, ny = nz = 1, density = {a, b, updir.xyz}
+                                       (updir normalised as the ctor leaves it)       */
 } pv_medium;
 
 enum { PV_MAT_MATTE = 0, PV_MAT_GLASS = 1 };

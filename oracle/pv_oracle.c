@@ -238,6 +238,10 @@ static inline float grid_D(const pv_medium *m, int x, int y, int z) {           
 static float grid_density(const pv_medium *m, v3 Pobj, med_counters *mc) {
     if (mc) mc->density_samples++;
     if (!bbox_inside(m->p0, m->p1, Pobj)) return 0;
+    if (m->type == PV_MEDIUM_EXPONENTIAL) {           /* volumes/exponential.h:57-61; density = {a, b, updir.xyz} */
+        float height = vdot(vsub(Pobj, V(m->p0[0], m->p0[1], m->p0[2])), V(m->density[2], m->density[3], m->density[4]));
+        return m->density[0] * expf(-m->density[1] * height);
+    }
     v3 vox = V((Pobj.x - m->p0[0]) / (m->p1[0] - m->p0[0]), (Pobj.y - m->p0[1]) / (m->p1[1] - m->p0[1]),
                (Pobj.z - m->p0[2]) / (m->p1[2] - m->p0[2]));
     vox.x = vox.x * m->nx - .5f; vox.y = vox.y * m->ny - .5f; vox.z = vox.z * m->nz - .5f;

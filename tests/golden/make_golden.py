@@ -177,6 +177,7 @@ def main():
         project_goldens(tmp)
         surface_goldens(tmp)
         sphere_goldens(tmp)
+        exponential_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -227,6 +228,13 @@ def sphere_goldens(tmp):
                                           sphere_params=' "float zmin" [-0.4] "float zmax" [0.5] "float phimax" [300]'))
     golden_for_scene(tmp, "sphere_disp", f, 100, 0.5, 0.05, 48, 48, [(100, 0.5 ** 2)], camera=cam, box=box, wanted=4000, shoot_step=0.1,
                      hit_bound=(-6.0, 9.0), hit_target=target, q_near_photons=True)
+
+
+def exponential_goldens(tmp):
+    """ExponentialDensity medium (volumes/exponential.h) in the Cornell box."""
+    f = os.path.join(tmp, "cornell_exp.pbrt")
+    open(f, "w").write(scenes.cornell_pbrt(scenes.EXP_VOLUME, 3000, stepsize=0.05, nused=50, maxdist=0.25, shoot_step=0.05))
+    golden_for_scene(tmp, "cornell_exp", f, 50, 0.25, 0.05, 64, 64, [(50, 0.25 ** 2)], wanted=3000)
 
 
 def read_radiance(fn):
@@ -281,7 +289,11 @@ def read_pfm(path):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "sphere":           # only the sphere-scene goldens
+    if len(sys.argv) > 1 and sys.argv[1] == "exponential":
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            exponential_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "sphere":           # only the sphere-scene goldens
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             sphere_goldens(tmp_)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 RTOL_RADIANCE = 1e-4
 # rainbow_vol / prism_small = BASELINE configs 1 and 4 (the reference project's own scenes, reduced counts; tests/golden/make_golden.py)
 # sphere_glass / sphere_disp: Sphere primitives (the project's glass-ball scene, and a rotated / scaled / partial / dispersive variant)
-ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp"]
+ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp", "cornell_exp"]
 
 
 def relerr(a, b, floor=1e-30):
@@ -170,7 +170,7 @@ def test_li_homogeneous_vs_reference(golden, pv_factory, name):
 
 
 @pytest.mark.parametrize("name,flags", [("cornell_homog", 0), ("cornell_grid32", 0), ("cornell_grid32", 1), ("cornell_grid32", 2),
-                                        ("rainbow_vol", 0), ("prism_small", 0), ("sphere_glass", 0), ("sphere_disp", 0)])
+                                        ("rainbow_vol", 0), ("prism_small", 0), ("sphere_glass", 0), ("sphere_disp", 0), ("cornell_exp", 0)])
 def test_li_vs_oracle_same_philox_stream(golden, pv_factory, name, flags):
     g, scene = golden(name)
     stepsize, nused, maxdist = float(g["params"][2]), int(g["params"][0]), float(g["params"][1])
@@ -212,7 +212,8 @@ def pkg_rays(o, d):
 
 
 @pytest.mark.parametrize("name,wanted,sstep", [("cornell_homog", 3000, 0.05), ("cornell_grid32", 1200, 0.05), ("rainbow_vol", 1500, 0.1),
-                                               ("prism_small", 4000, 0.1), ("sphere_glass", 4000, 0.1), ("sphere_disp", 4000, 0.1)])
+                                               ("prism_small", 4000, 0.1), ("sphere_glass", 4000, 0.1), ("sphere_disp", 4000, 0.1),
+                                               ("cornell_exp", 1000, 0.05)])
 def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, sstep):
     """Same per-path Philox streams on both sides: photons are matched one to one by (path, deposit ordinal).
     prism_small: every path goes through the dispersive glass wedge (splitSpectrum into 30 monochromatic photons, Cauchy refraction)."""

@@ -4,12 +4,13 @@ import numpy as np
 import pytest
 import oracle_lib as O
 
-SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp"]
+SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp", "cornell_exp"]
+# cornell_exp: ExponentialDensity medium (volumes/exponential.h)
 # sphere_glass / sphere_disp: Sphere primitives (shapes/sphere.cpp) -- the reference project's glass-ball scene (projectScene/scene.pbrt,
 # reduced counts) and a rotated, scaled, partial, dispersive + reflecting variant of it
 # rainbow_vol / prism_small: BASELINE configs 1 and 4 (the reference project's rainbow-volume and glass-prism scenes, reduced counts)
 WANTED = {"cornell_homog": (6000, 0.05), "cornell_grid32": (2500, 0.05), "rainbow_vol": (3000, 0.1), "prism_small": (4000, 0.1),
-          "sphere_glass": (4000, 0.1), "sphere_disp": (4000, 0.1)}
+          "sphere_glass": (4000, 0.1), "sphere_disp": (4000, 0.1), "cornell_exp": (3000, 0.05)}
 
 
 def relerr(a, b):
