@@ -142,6 +142,7 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
         }
         if (m->type == PV_MEDIUM_GRID || m->type == PV_MEDIUM_EXPONENTIAL) {
             if (!m->density || m->nx < 1 || m->ny < 1 || m->nz < 1) { ctx->err = "pv_set_scene: grid medium without density"; return PV_EINVAL; }
+            if ((uint64_t)m->nx * (uint64_t)m->ny * (uint64_t)m->nz >= (1ull << 31)) { ctx->err = "pv_set_scene: density grid of 2^31 voxels or more"; return PV_EINVAL; }
             if ((rc = upload(ctx, &ctx->d_density, m->density, sizeof(float) * (size_t)m->nx * m->ny * m->nz))) return rc;
             d.density = (const float *)ctx->d_density;
         }

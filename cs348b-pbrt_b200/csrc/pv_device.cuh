@@ -166,10 +166,26 @@ __device__ __forceinline__ float grid_density(const Med &m, v3 Pobj) {
     vx_ = vx_ * m.nx - .5f; vy_ = vy_ * m.ny - .5f; vz_ = vz_ * m.nz - .5f;
     int vx = (int)floorf(vx_), vy = (int)floorf(vy_), vz = (int)floorf(vz_);
     float dx = vx_ - vx, dy = vy_ - vy, dz = vz_ - vz;
+#ifndef PV_TAPS_SHARED_CLAMP
+#define PV_TAPS_SHARED_CLAMP 1
+#endif
+#if PV_TAPS_SHARED_CLAMP
+    // the eight D(x, y, z) taps (volumegrid.h:60-65) with each coordinate clamped ONCE and 32-bit offsets (the API rejects grids
+    // of 2^31 voxels or more): the same eight values as eight grid_D calls for a third of the integer work
+    const int x0 = min(max(vx, 0), m.nx - 1), x1 = min(max(vx + 1, 0), m.nx - 1);
+    const int y0 = min(max(vy, 0), m.ny - 1) * m.nx, y1 = min(max(vy + 1, 0), m.ny - 1) * m.nx;
+    const int sl = m.nx * m.ny;
+    const float *z0 = m.density + (size_t)(min(max(vz, 0), m.nz - 1) * sl), *z1 = m.density + (size_t)(min(max(vz + 1, 0), m.nz - 1) * sl);
+    float d00 = lerpf(dx, __ldg(z0 + (y0 + x0)), __ldg(z0 + (y0 + x1)));
+    float d10 = lerpf(dx, __ldg(z0 + (y1 + x0)), __ldg(z0 + (y1 + x1)));
+    float d01 = lerpf(dx, __ldg(z1 + (y0 + x0)), __ldg(z1 + (y0 + x1)));
+    float d11 = lerpf(dx, __ldg(z1 + (y1 + x0)), __ldg(z1 + (y1 + x1)));
+#else
     float d00 = lerpf(dx, grid_D(m, vx, vy, vz), grid_D(m, vx + 1, vy, vz));
     float d10 = lerpf(dx, grid_D(m, vx, vy + 1, vz), grid_D(m, vx + 1, vy + 1, vz));
     float d01 = lerpf(dx, grid_D(m, vx, vy, vz + 1), grid_D(m, vx + 1, vy, vz + 1));
     float d11 = lerpf(dx, grid_D(m, vx, vy + 1, vz + 1), grid_D(m, vx + 1, vy + 1, vz + 1));
+#endif
     float d0 = lerpf(dy, d00, d10);
     float d1 = lerpf(dy, d01, d11);
     return lerpf(dz, d0, d1);
