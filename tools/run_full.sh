@@ -12,3 +12,5 @@ ncu --set full --clock-control none --import-source on -k gather_kernel --launch
 ncu --set full --clock-control none --import-source on -k march_steps_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_march -f $B > gpurun_out/${tag}_ncu_march.log 2>&1
 # the shooter: volume-only and all-maps instantiations (the first launches of a run are the volume-only waves, then pv_shoot_maps)
 ncu --set full --clock-control none --import-source on -k regex:shoot_kernel -c 10 -o gpurun_out/${tag}_shoot -f $B > gpurun_out/${tag}_ncu_shoot.log 2>&1
+# BASELINE config 2 (k-nearest gather, 1 M photons, 512x512, k = 50) as a second bench line
+python bench.py --workload config2 --steps 5 --warmup 3 --shoot-photons 0 --maps-photons 0 --no-cpu-baseline > gpurun_out/${tag}_config2.log 2>&1
