@@ -192,6 +192,25 @@ class PhotonVolume:
         self._chk(self.lib.pv_radiance_photons(self.ctx, C.c_uint32(n_lookup), C.c_float(max_dist2), pc, _vp(Lo), C.c_uint64(n.value), C.byref(got)))
         return Lo
 
+    def select_map(self, which, maxdist, nused):
+        """Build the lookup grid over a photon class (A.MAP_*); build() puts the volume map back."""
+        self._chk(self.lib.pv_select_map(self.ctx, C.c_int(which), C.c_float(maxdist), C.c_uint32(nused)))
+
+    def SurfaceLPhoton(self, pts, nf, n_lookup, max_dist2, n_paths):
+        """PhotonIntegrator's LPhoton, diffuse branch (integrators/photonmap.cpp:62-108) on the selected surface map -> (Lr, Lt)."""
+        pts = _f32(pts).reshape(-1, 3); nf = _f32(nf).reshape(-1, 3); n = len(pts)
+        Lr = np.zeros((n, A.NSPEC), np.float32); Lt = np.zeros((n, A.NSPEC), np.float32)
+        self._chk(self.lib.pv_surface_lphoton(self.ctx, _vp(pts), _vp(nf), C.c_uint64(n), C.c_uint32(n_lookup), C.c_float(max_dist2),
+                                              C.c_uint64(int(n_paths)), _vp(Lr), _vp(Lt)))
+        return Lr, Lt
+
+    def RadianceNearest(self, pts, normals, want_Lo=True):
+        """RadiancePhotonProcess lookup of final gathering (integrators/photonmap.cpp:238-243) -> (index, Lo)."""
+        pts = _f32(pts).reshape(-1, 3); normals = _f32(normals).reshape(-1, 3); n = len(pts)
+        idx = np.zeros(n, np.uint32); Lo = np.zeros((n, A.NSPEC), np.float32) if want_Lo else None
+        self._chk(self.lib.pv_radiance_nearest(self.ctx, _vp(pts), _vp(normals), C.c_uint64(n), _vp(idx), _vp(Lo)))
+        return idx, Lo
+
     # ---- KdTree::Lookup --------------------------------------------------
     def Lookup(self, pts, k=None, r2=None):
         pts = _f32(pts).reshape(-1, 3); n = len(pts)

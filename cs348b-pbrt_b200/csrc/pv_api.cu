@@ -492,6 +492,7 @@ int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi, 
     if (n && (!pos || !wi || !alpha)) { ctx->err = "pv_set_map_photons: null plane"; return PV_EINVAL; }
     PhotonSet &s = ctx->surf[map - 1];
     s.n = 0; ctx->rad_valid = false;
+    if (ctx->map_which == map) ctx->built = false;
     int rc = pvi_reserve_set(ctx, &s, n); if (rc) return rc;
     if (n) {
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(s.pos, pos, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -503,6 +504,43 @@ int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi, 
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     s.n = n;
+    return PV_OK;
+}
+int pv_select_map(pv_ctx *ctx, int map, float maxdist, uint32_t nused) {
+    LOCK(ctx);
+    return pvi_build_map(ctx, map, maxdist, nused);
+}
+int pv_surface_lphoton(pv_ctx *ctx, const float *pts, const float *nf, uint64_t n, uint32_t n_lookup, float max_dist2, uint64_t n_paths,
+                       float *Lr, float *Lt) {
+    LOCK(ctx);
+    if (n && (!pts || !nf || !Lr || !Lt)) { ctx->err = "pv_surface_lphoton: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * 6 * sizeof(float)); if (rc) return rc;
+    float *d_pts = (float *)ctx->io, *d_nf = d_pts + n * 3;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pts, pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_nf, nf, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 2 * n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+    float *d_Lr = (float *)ctx->io2, *d_Lt = d_Lr + n * PV_NSPEC;
+    rc = pvi_surface_lphoton(ctx, d_pts, d_nf, n, n_lookup, max_dist2, n_paths, d_Lr, d_Lt); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(Lr, d_Lr, n * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(Lt, d_Lt, n * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_radiance_nearest(pv_ctx *ctx, const float *pts, const float *normals, uint64_t n, uint32_t *idx, float *Lo) {
+    LOCK(ctx);
+    if (n && (!pts || !normals || !idx)) { ctx->err = "pv_radiance_nearest: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * 6 * sizeof(float)); if (rc) return rc;
+    float *d_pts = (float *)ctx->io, *d_n = d_pts + n * 3;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pts, pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_n, normals, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, n * sizeof(uint32_t) + n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+    float *d_Lo = (float *)ctx->io2; uint32_t *d_idx = (uint32_t *)(d_Lo + n * PV_NSPEC);
+    rc = pvi_radiance_nearest(ctx, d_pts, d_n, n, d_idx, Lo ? d_Lo : nullptr); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(idx, d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Lo) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(Lo, d_Lo, n * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PV_OK;
 }
 int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n) {

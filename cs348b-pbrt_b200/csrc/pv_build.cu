@@ -251,9 +251,18 @@ __global__ void cell_start_kernel(const uint32_t *__restrict__ sorted_keys, uint
 
 static int ceil_log2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
 
-int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
+int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) { return pvi_build_map(ctx, PV_MAP_VOLUME, maxdist, nused); }
+
+// Build the lookup grid over one photon class: the volume photons (the context's main set; the medium's extent gate is folded
+// into alpha) or one of the surface classes of pv_shoot_maps / pv_set_map_photons (no gate).  There is ONE grid per context.
+int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
     ctx->built = false;
-    uint64_t n = ctx->n_photons;
+    if (which < PV_MAP_VOLUME || which > PV_MAP_RADIANCE) { ctx->err = "pv_select_map: bad map"; return PV_EINVAL; }
+    const bool is_volume = which == PV_MAP_VOLUME;
+    const float *src_pos = is_volume ? ctx->d_pos : ctx->surf[which - 1].pos, *src_wi = is_volume ? ctx->d_wi : ctx->surf[which - 1].wi;
+    const float *src_alpha = is_volume ? ctx->d_alpha : ctx->surf[which - 1].alpha;
+    uint64_t n = is_volume ? ctx->n_photons : ctx->surf[which - 1].n;
+    ctx->map_which = which; ctx->map_n = n;
     if (n > 0xFFFFFFF0ull) { ctx->err = "too many photons for 32-bit indices"; return PV_EINVAL; }
     if (!(maxdist > 0.f)) { ctx->err = "pv_build: maxdist must be > 0"; return PV_EINVAL; }
     GridParams g{};
@@ -278,7 +287,7 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
         int rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 64); if (rc) return rc;
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io2, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
         int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
-        bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_pos, n, (int *)ctx->io2);
+        bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(src_pos, n, (int *)ctx->io2);
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_bounds, ctx->io2, sizeof(h_bounds), cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -342,7 +351,7 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     size_t need = nn * 4 * sizeof(uint32_t) + 256;
     int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
     uint32_t *keys = (uint32_t *)ctx->scratch, *vals = keys + nn, *keys_tmp = vals + nn, *vals_tmp = keys_tmp + nn;
-    keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, n, g, keys, vals);
+    keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src_pos, n, g, keys, vals);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     uint32_t *skeys, *svals;
     rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, n, key_bits, &skeys, &svals); if (rc) return rc;
@@ -362,8 +371,8 @@ int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) {
     }
     {
         int blocks = (int)std::min<uint64_t>((n + 31) / 32, (uint64_t)ctx->sm_count * 16);
-        gather_records_kernel<<<blocks, 256, 0, ctx->stream>>>(svals, n, ctx->d_pos, ctx->d_wi, ctx->d_alpha, ctx->m_pos4, ctx->m_wi4,
-                                                             ctx->m_alpha32, ctx->m_orig, ctx->has_scene && ctx->build_gate ? ctx->dscene : nullptr);
+        gather_records_kernel<<<blocks, 256, 0, ctx->stream>>>(svals, n, src_pos, src_wi, src_alpha, ctx->m_pos4, ctx->m_wi4,
+                                                             ctx->m_alpha32, ctx->m_orig, ctx->has_scene && is_volume ? ctx->dscene : nullptr);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     // 5. cell table

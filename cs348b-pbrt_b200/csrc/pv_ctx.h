@@ -56,7 +56,7 @@ struct pv_ctx {
     PhotonSet surf[4];
     float *rad_Lo = nullptr; uint64_t rad_Lo_cap = 0; bool rad_valid = false;
     uint64_t map_paths[4] = {0, 0, 0, 0};          // nCausticPaths, nIndirectPaths, nDirectPaths, nVolumePaths
-    bool build_gate = true;                        // pv_build folds the medium's extent gate into alpha (volume photons only)
+    int map_which = 0; uint64_t map_n = 0;         // photon class (PV_MAP_*) and size of the set the grid was last built over
 
     // the map: photons sorted by cell key
     float4 *m_pos4 = nullptr;      // x, y, z, sorted position (bits)
@@ -98,6 +98,7 @@ int pv_ensure(pv_ctx *ctx, void **p, size_t *cap, size_t bytes);
 
 // pv_build.cu
 int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused);
+int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused);
 int pvi_sort_pairs_u32(pv_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int key_bits,
                        uint32_t **keys_out, uint32_t **vals_out);
 int pvi_sort_pairs_u64(pv_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int key_bits,
@@ -127,3 +128,6 @@ int pvi_reserve_set(pv_ctx *ctx, PhotonSet *s, uint64_t n);
 void pvi_free_set(PhotonSet *s);
 // pv_gather.cu
 int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t counts[3]);
+int pvi_surface_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_nf, uint64_t n, uint32_t n_lookup, float max_dist2, uint64_t n_paths,
+                        float *d_Lr, float *d_Lt);
+int pvi_radiance_nearest(pv_ctx *ctx, const float *d_pts, const float *d_n, uint64_t n, uint32_t *d_idx, float *d_Lo30);

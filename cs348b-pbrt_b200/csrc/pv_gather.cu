@@ -700,6 +700,120 @@ __global__ void __launch_bounds__(GW_THREADS) ephoton_kernel(MapView m, const fl
         __syncwarp();
     }
 }
+// PhotonIntegrator's LPhoton, diffuse branch (integrators/photonmap.cpp:62-108, kernel() :57-60): the n_lookup nearest photons of
+// the selected surface map within max_dist2, each weighted by the Simpson kernel 3/pi (1 - d2/md2)^2 over nPaths * md2 (md2 = the
+// search radius as the lookup leaves it), summed separately for photons arriving on the side of Nf (Lr) and on the other (Lt).
+// The caller finishes with L = Lr * rho_r / pi + Lt * rho_t / pi.
+__global__ void __launch_bounds__(GW_THREADS) surface_lphoton_kernel(MapView m, const float *__restrict__ pts, const float *__restrict__ nf,
+                                                                    uint64_t n, uint32_t k, float r2, float npaths, uint32_t cap,
+                                                                    float *__restrict__ Lr, float *__restrict__ Lt, unsigned long long *counter) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, cap, warp, lane);
+    const float r = __fsqrt_rn(r2);
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(counter, 1ull);
+        q = __shfl_sync(PV_FULL, q, 0);
+        if (q >= n) break;
+        const v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), nn = V3(nf[3 * q], nf[3 * q + 1], nf[3 * q + 2]);
+        const uint32_t cnt = warp_lookup(m, p, r2, r, k, b, lane, false, nullptr);
+        __syncwarp();
+        float accr = 0.f, acct = 0.f;
+        if (cnt) {
+            float mx = 0.f;
+            for (uint32_t e = lane; e < cnt; e += 32) mx = fmaxf(mx, __uint_as_float(b.ent[e].x));
+            mx = warp_max(mx);
+            const float md2 = cnt == k ? mx : r2;
+            const float den = npaths * md2;
+            for (uint32_t e = 0; e < cnt; ++e) {
+                const uint2 v = b.ent[e];
+                const float s = 1.f - __fdiv_rn(__uint_as_float(v.x), md2);
+                const float w = __fdiv_rn(((3.f * PV_INV_PI_F) * s) * s, den);
+                const float4 wv = __ldg(m.wi4 + v.y);
+                const float a = w * __ldg(m.alpha32 + (size_t)v.y * 32 + lane);
+                if (nn.x * wv.x + nn.y * wv.y + nn.z * wv.z > 0.f) accr += a; else acct += a;
+            }
+        }
+        if (lane < PV_NSPEC) { Lr[q * PV_NSPEC + lane] = accr; Lt[q * PV_NSPEC + lane] = acct; }
+        __syncwarp();
+    }
+}
+
+// RadiancePhotonProcess + KdTree::Lookup(p, proc, INFINITY) (core/photonshooter.h:54-70, core/kdtree.h:150-183; final gathering,
+// integrators/photonmap.cpp:238-243): the NEAREST radiance photon whose normal faces the query normal, no radius limit.  One
+// thread per query walks growing shells of grid cells until the best distance found is inside the radius the visited cube
+// guarantees.  The grid is the one built over the radiance-photon class: wi4 holds the photon normals.  Ties by photon index.
+__global__ void radiance_nearest_kernel(MapView m, const float *__restrict__ pts, const float *__restrict__ nrm, uint64_t n,
+                                        uint32_t *__restrict__ idx_out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const GridParams &g = m.g;
+    const v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), nn = V3(nrm[3 * q], nrm[3 * q + 1], nrm[3 * q + 2]);
+    float best = INFINITY; uint32_t best_i = 0xFFFFFFFFu;
+    if (m.n) {
+        int cx, cy, cz;
+        lookup_cell(g, p, cx, cy, cz);
+        const int xs = g.xshift, xlast = g.dims[0] - 1;
+        const int ncoarse[3] = {((g.dims[0] - 1) >> xs) + 1, g.dims[1], g.dims[2]};
+        const int cc[3] = {cx, cy, cz};
+        const float qq[3] = {p.x, p.y, p.z};
+        for (int s = 0;; ++s) {
+            for (int dz = -s; dz <= s; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= g.dims[2]) continue;
+                for (int dy = -s; dy <= s; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= g.dims[1]) continue;
+                    const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                    const bool rim = max(abs(dy), abs(dz)) == s;
+                    // rim rows: the coarse cells cx-s .. cx+s; inner rows: the two end cells of the shell
+                    const int nruns = rim || s == 0 ? 1 : 2;
+                    for (int h = 0; h < nruns; ++h) {
+                        int c0, c1;
+                        if (rim) { c0 = cx - s; c1 = cx + s; } else { c0 = c1 = h == 0 ? cx - s : cx + s; }
+                        if (c1 < 0 || c0 >= ncoarse[0]) continue;
+                        const int a0 = max(c0, 0) << xs, a1 = min(((min(c1, ncoarse[0] - 1) + 1) << xs) - 1, xlast);
+                        if (a0 > a1) continue;
+                        const uint32_t ps = __ldg(m.cell_start + (rowkey | (uint32_t)a0)), pe = __ldg(m.cell_start + (rowkey | (uint32_t)a1) + 1);
+                        for (uint32_t j = ps; j < pe; ++j) {
+                            const float4 w = __ldg(m.wi4 + j);
+                            if (w.x * nn.x + w.y * nn.y + w.z * nn.z > 0.f) {
+                                const float4 pp = __ldg(m.pos4 + j);
+                                const float dx = pp.x - p.x, dy2 = pp.y - p.y, dz2 = pp.z - p.z;
+                                const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                                if (d2 <= best) {
+                                    const uint32_t oi = __ldg(m.orig + j);
+                                    if (d2 < best || oi < best_i) { best = d2; best_i = oi; }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // radius up to which the cube [c-s, c+s]^3 holds every photon (same rule as warp_lookup)
+            float gr = INFINITY;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int lo = cc[a] - s, hi = cc[a] + s;
+                if (lo > 0) gr = fminf(gr, qq[a] - (g.origin[a] + lo * g.h));
+                if (hi < ncoarse[a] - 1) gr = fminf(gr, (g.origin[a] + (hi + 1) * g.h) - qq[a]);
+            }
+            if (gr == INFINITY) break;                       // the cube covers the whole grid
+            gr -= g.margin;
+            if (gr > 0.f && best < gr * gr) break;           // strict: an unseen photon cannot even tie
+        }
+    }
+    idx_out[q] = best_i;
+}
+__global__ void gather_lo_kernel(const uint32_t *__restrict__ idx, const float *__restrict__ Lo32, uint64_t n, float *__restrict__ out30) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * PV_NSPEC) return;
+    const uint64_t q = i / PV_NSPEC; const uint32_t b = (uint32_t)(i % PV_NSPEC);
+    const uint32_t j = idx[q];
+    out30[i] = j == 0xFFFFFFFFu ? 0.f : Lo32[(size_t)j * 32 + b];
+}
+
 // rp.Lo += INV_PI * rho_r * E (:379)
 __global__ void radiance_lo_kernel(const float *__restrict__ rho32, const float *__restrict__ E32, uint64_t n, float *__restrict__ Lo32) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -860,7 +974,7 @@ static uint32_t lookup_cap(uint32_t k) {
 }
 static MapView map_view(pv_ctx *ctx) {
     MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.orig = ctx->m_orig; m.g = ctx->grid;
-    m.n = ctx->n_photons;
+    m.n = ctx->map_n;
     m.need_wi = ctx->has_scene && ctx->hscene.med.g != 0.f;
     return m;
 }
@@ -889,8 +1003,41 @@ int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, u
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }
+int pvi_surface_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_nf, uint64_t n, uint32_t n_lookup, float max_dist2, uint64_t n_paths,
+                        float *d_Lr, float *d_Lt) {
+    if (!ctx->built || ctx->map_which == PV_MAP_VOLUME || ctx->map_which == PV_MAP_RADIANCE) {
+        ctx->err = "pv_surface_lphoton: select a surface photon map first (pv_select_map with PV_MAP_CAUSTIC / INDIRECT / DIRECT)"; return PV_ESTATE;
+    }
+    if (!(max_dist2 > 0.f) || n_lookup == 0 || n_paths == 0) { ctx->err = "pv_surface_lphoton: n_lookup, max_dist2 and n_paths must be > 0"; return PV_EINVAL; }
+    if (n == 0) return PV_OK;
+    uint32_t cap = lookup_cap(n_lookup);
+    int blocks; size_t smem;
+    int rc = launch_cfg(ctx, surface_lphoton_kernel, cap, &blocks, &smem); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    MapView m = map_view(ctx); m.need_wi = 1;
+    surface_lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(m, d_pts, d_nf, n, n_lookup, max_dist2, (float)(int)n_paths, cap, d_Lr, d_Lt,
+                                                                    ctx->d_counters);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    return PV_OK;
+}
+int pvi_radiance_nearest(pv_ctx *ctx, const float *d_pts, const float *d_n, uint64_t n, uint32_t *d_idx, float *d_Lo30) {
+    if (!ctx->built || ctx->map_which != PV_MAP_RADIANCE) {
+        ctx->err = "pv_radiance_nearest: select the radiance-photon map first (pv_select_map with PV_MAP_RADIANCE)"; return PV_ESTATE;
+    }
+    if (d_Lo30 && !ctx->rad_valid) { ctx->err = "pv_radiance_nearest: radiance not computed (call pv_radiance_photons)"; return PV_ESTATE; }
+    if (n == 0) return PV_OK;
+    MapView m = map_view(ctx);
+    radiance_nearest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(m, d_pts, d_n, n, d_idx);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    if (d_Lo30) {
+        gather_lo_kernel<<<(unsigned)((n * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(d_idx, ctx->rad_Lo, n, d_Lo30);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+    return PV_OK;
+}
 int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L) {
     if (!ctx->built) { ctx->err = "pv_lphoton: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (ctx->map_which != PV_MAP_VOLUME) { ctx->err = "pv_lphoton: the grid is built over a surface photon map (call pv_build)"; return PV_ESTATE; }
     if (!ctx->has_scene || ctx->hscene.med.type == PV_MEDIUM_NONE) { ctx->err = "pv_lphoton: scene has no medium"; return PV_ESTATE; }
     if (n == 0) return PV_OK;
     uint32_t cap = lookup_cap(nused);
@@ -920,17 +1067,10 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(E32, 0, n * 32 * sizeof(float), ctx->stream));
     const int order[3] = {2, 1, 0};                       // ctx->surf index of direct, indirect, caustic
     const float maxdist = sqrtf(max_dist2);
-    auto swap_main = [&](PhotonSet &s) {
-        std::swap(ctx->d_pos, s.pos); std::swap(ctx->d_wi, s.wi); std::swap(ctx->d_alpha, s.alpha); std::swap(ctx->d_ids, s.ids);
-        std::swap(ctx->n_photons, s.n); std::swap(ctx->cap_photons, s.cap);
-    };
     for (int k = 0; k < 3 && rc == PV_OK; ++k) {
         PhotonSet &s = ctx->surf[order[k]];
         if (s.n == 0 || counts[k] == 0) continue;
-        swap_main(s);
-        ctx->build_gate = false;                          // surface photons are not gated by the medium's extent
-        rc = pvi_build(ctx, maxdist, n_lookup);
-        ctx->build_gate = true;
+        rc = pvi_build_map(ctx, order[k] + 1, maxdist, n_lookup);      // surface photons are not gated by the medium's extent
         if (rc == PV_OK) {
             uint32_t cap = lookup_cap(n_lookup);
             int blocks; size_t smem;
@@ -944,7 +1084,6 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
                 cudaStreamSynchronize(ctx->stream);
             }
         }
-        swap_main(s);
         ctx->built = false;
     }
     if (rc) return rc;
@@ -991,6 +1130,7 @@ int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_pa
     if (!ctx->has_scene) { ctx->err = "pv_gather: no scene"; return PV_ESTATE; }
     bool need_map = !(prm->flags & PV_GATHER_NO_INDIRECT) && ctx->hscene.med.type != PV_MEDIUM_RAINBOW && ctx->hscene.med.type != PV_MEDIUM_NONE;
     if (need_map && !ctx->built) { ctx->err = "pv_gather: photon map not built (call pv_build)"; return PV_ESTATE; }
+    if (need_map && ctx->map_which != PV_MAP_VOLUME) { ctx->err = "pv_gather: the grid is built over a surface photon map (call pv_build)"; return PV_ESTATE; }
     if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
     ctx->last_ms = 0.f; ctx->last_march_ms = 0.f;
     if (n == 0) return PV_OK;

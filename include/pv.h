@@ -303,6 +303,23 @@ int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi,
 int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2,
                         const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n);
 
+/* ---- building blocks of the SURFACE integrator's lookups (PhotonIntegrator, integrators/photonmap.cpp) -------
+ * There is one lookup grid per context.  pv_build builds it over the volume photons; pv_select_map builds it over any
+ * photon class (PV_MAP_*), after which pv_knn and the two calls below query that class.  pv_gather / pv_lphoton refuse to
+ * run until pv_build has put the volume map back.                                                                  */
+int pv_select_map(pv_ctx *ctx, int map, float maxdist, uint32_t nused);
+/* LPhoton, diffuse branch (integrators/photonmap.cpp:62-108 with kernel() :57-60) on the selected caustic / indirect /
+ * direct map: pts[3n], nf[3n] = Faceforward(shading normal, wo).  Lr[30n] / Lt[30n] = kernel-weighted flux of the
+ * n_lookup nearest photons within max_dist2 arriving on the side of nf / on the other side, over n_paths * md2; the
+ * caller finishes with L = Lr * rho_r / pi + Lt * rho_t / pi.                                                      */
+int pv_surface_lphoton(pv_ctx *ctx, const float *pts, const float *nf, uint64_t n, uint32_t n_lookup,
+                       float max_dist2, uint64_t n_paths, float *Lr, float *Lt);
+/* RadiancePhotonProcess + KdTree::Lookup with an unbounded radius (core/photonshooter.h:54-70, final gathering
+ * integrators/photonmap.cpp:238-243) on the selected radiance-photon map: for each (point, normal) the nearest
+ * radiance photon whose normal has a positive dot product with it.  idx[n] = its index in the PV_MAP_RADIANCE list
+ * or 0xFFFFFFFF; Lo[30n] (may be NULL) = its radiance from the last pv_radiance_photons.                           */
+int pv_radiance_nearest(pv_ctx *ctx, const float *pts, const float *normals, uint64_t n, uint32_t *idx, float *Lo);
+
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);
 

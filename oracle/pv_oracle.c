@@ -1560,6 +1560,50 @@ int pvo_radiance(const pvo_kdtree *maps[3], const float *wis[3], const float *al
     return 0;
 }
 
+/* PhotonIntegrator's LPhoton, diffuse branch (integrators/photonmap.cpp:62-108; kernel() :57-60): Lr / Lt before the
+ * rho * INV_PI factors. */
+int pvo_surface_lphoton(const pvo_kdtree *t, const float *wi, const float *alpha, const float *pts, const float *nf, uint64_t n,
+                        uint32_t nLookup, float maxDist2, uint64_t nPaths, float *Lr, float *Lt) {
+    closeph *buf = (closeph *)malloc(sizeof(closeph) * (nLookup ? nLookup : 1));
+    for (uint64_t i = 0; i < n; ++i) {
+        spec lr = s_const(0.f), lt = s_const(0.f);
+        if (t && t->nNodes) {
+            v3 p = V(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Nf = V(nf[3 * i], nf[3 * i + 1], nf[3 * i + 2]);
+            photon_proc proc = {buf, nLookup, 0, 0};
+            float md2 = maxDist2;
+            kd_lookup(t, 0, p, &proc, &md2);
+            for (uint32_t k = 0; k < proc.nFound; ++k) {
+                uint32_t o = t->nodeOrig[buf[k].node];
+                float s = (1.f - dist2(t->nodePos[buf[k].node], p) / md2);
+                float kern = 3.f * INV_PI_F * s * s;
+                float w = kern / ((int)nPaths * md2);
+                spec *dst = vdot(Nf, V(wi[3 * o], wi[3 * o + 1], wi[3 * o + 2])) > 0.f ? &lr : &lt;
+                for (int b = 0; b < NS; ++b) dst->c[b] += w * alpha[NS * (size_t)o + b];
+            }
+        }
+        memcpy(Lr + NS * i, lr.c, sizeof(lr.c)); memcpy(Lt + NS * i, lt.c, sizeof(lt.c));
+    }
+    free(buf);
+    return 0;
+}
+/* RadiancePhotonProcess + KdTree::Lookup(p, proc, INFINITY) (core/photonshooter.h:54-70): the nearest radiance photon whose
+ * normal faces the query normal.  Stated as the rule the CUDA path implements: smallest (d2, index) among the facing photons
+ * (the reference's kd-tree keeps the first one it visits among exact ties). */
+int pvo_radiance_nearest(const float *rp_pos, const float *rp_n, uint64_t n_rp, const float *pts, const float *nrm, uint64_t n,
+                         uint32_t *idx, float *d2out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        v3 p = V(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), nn = V(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+        float best = INFINITY; uint32_t bi = 0xFFFFFFFFu;
+        for (uint64_t j = 0; j < n_rp; ++j) {
+            if (!(vdot(V(rp_n[3 * j], rp_n[3 * j + 1], rp_n[3 * j + 2]), nn) > 0.f)) continue;
+            float d2 = dist2(V(rp_pos[3 * j], rp_pos[3 * j + 1], rp_pos[3 * j + 2]), p);
+            if (d2 < best) { best = d2; bi = (uint32_t)j; }
+        }
+        idx[i] = bi; if (d2out) d2out[i] = best;
+    }
+    return 0;
+}
+
 void pvo_photons_free(pvo_photons *p) {
     free(p->pos); free(p->wi); free(p->alpha); free(p->ids);
     memset(p, 0, sizeof(*p));

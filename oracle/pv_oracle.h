@@ -95,6 +95,12 @@ void pvo_maps_free(pvo_maps *m);
 int  pvo_radiance(const pvo_kdtree *maps[3], const float *wis[3], const float *alphas[3], const uint64_t counts[3],
                   const float *rp_pos, const float *rp_n, const float *rho_r, uint64_t n, uint32_t nLookup, float maxDist2, float *Lo);
 
+/* the surface integrator's two photon lookups (integrators/photonmap.cpp:62-108 diffuse branch; :238-243) */
+int  pvo_surface_lphoton(const pvo_kdtree *t, const float *wi, const float *alpha, const float *pts, const float *nf, uint64_t n,
+                         uint32_t nLookup, float maxDist2, uint64_t nPaths, float *Lr, float *Lt);
+int  pvo_radiance_nearest(const float *rp_pos, const float *rp_n, uint64_t n_rp, const float *pts, const float *nrm, uint64_t n,
+                          uint32_t *idx, float *d2out);
+
 /* small known-answer helpers exposed for unit tests */
 uint32_t pvo_mt_first(uint32_t seed, uint32_t *out, uint32_t n);
 void     pvo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -39,6 +39,7 @@
 #define pbrtWorldEnd pbrtWorldEnd_reference
 #include "core/api.cpp"
 #undef pbrtWorldEnd
+#include "integrators/photonmap.cpp"
 #include "core/photonshooter.h"
 #include "core/kdtree.h"
 #include "core/parser.h"
@@ -102,6 +103,10 @@ static std::vector<Photon> g_surf[3];       // caustic, indirect, direct photons
 static std::vector<RadiancePhoton> g_rad;   // radiance photons with Lo (ComputeRadianceTask)
 static std::vector<Spectrum> g_rho_r, g_rho_t;
 static int g_paths[4] = {0, 0, 0, 0};       // nCausticPaths, nIndirectPaths, nDirectPaths, nVolumePaths
+static KdTree<RadiancePhoton> *g_radMap = NULL;   // the reference's radiance map, photons tagged with their list index
+// PhotonIntegrator's LPhoton (integrators/photonmap.cpp:62) is file-static: the reference's photonmap.cpp is compiled as part of
+// this translation unit (see the #include next to core/api.cpp), which makes it callable here; the archive's copy of that
+// object is then never pulled in by the linker.
 static uint32_t g_nshot = 0;
 static double g_shoot_seconds = 0;
 
@@ -166,6 +171,12 @@ static void shoot(PhotonShooter *sh, const Scene *scene, const Camera *camera, c
     delete directMap;
     g_surf[0] = causticPhotons; g_surf[1] = indirectPhotons; g_surf[2] = directPhotons;
     g_rad = radiancePhotons; g_rho_r = rpReflectances; g_rho_t = rpTransmittances;
+    delete g_radMap; g_radMap = NULL;
+    if (radiancePhotons.size()) {
+        vector<RadiancePhoton> tagged = radiancePhotons;
+        for (uint32_t i = 0; i < tagged.size(); ++i) memcpy(&tagged[i].Lo.intensity, &i, 4);     // unused member of the fork's Spectrum
+        g_radMap = new KdTree<RadiancePhoton>(tagged);
+    }
     g_paths[0] = sh->nCausticPaths; g_paths[1] = sh->nIndirectPaths; g_paths[2] = nDirectPaths; g_paths[3] = sh->nVolumePaths;
     g_photons.swap(volumePhotons);
     g_nshot = nshot;
@@ -271,6 +282,58 @@ static void lphoton(PhotonVolumeIntegrator *vi, const Scene *scene, const std::s
                                  Vector(q[6*i+3], q[6*i+4], q[6*i+5]), Point(q[6*i], q[6*i+1], q[6*i+2]),
                                  scene->volumeRegion, vi->maxDistSquared, 0.f);
         wr(o, L.c, 30);
+    }
+    fclose(o);
+}
+
+// The surface integrator's two photon lookups, driven through the reference's own code on the maps of the last --shoot.
+// (1) LPhoton (integrators/photonmap.cpp:62-108) at (p, n) with a purely diffuse-reflective and a purely diffuse-transmissive BSDF
+//     of unit albedo: the two calls return Lr / pi and Lt / pi of its diffuse branch.
+static void surface_lphoton(PhotonShooter *sh, const std::string &which, const std::string &qfn, const std::string &ofn) {
+    FILE *f = xopen(qfn, "rb");
+    uint64_t n = read_header(f, "PVQRY001");
+    std::vector<float> q(6 * n); rd(f, q.data(), q.size()); fclose(f);
+    KdTree<Photon> *map = which == "caustic" ? sh->causticMap : sh->indirectMap;
+    int nPaths = which == "caustic" ? sh->nCausticPaths : sh->nIndirectPaths;
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVSLPH01", n);
+    std::vector<ClosePhoton> buf(sh->nLookup);
+    MemoryArena arena;
+    RNG rng(7);
+    for (uint64_t i = 0; i < n; ++i) {
+        Point p(q[6*i], q[6*i+1], q[6*i+2]); Normal nn(q[6*i+3], q[6*i+4], q[6*i+5]);
+        Vector v2, v3; CoordinateSystem(Vector(nn), &v2, &v3);
+        DifferentialGeometry dg(p, v2, v3, Normal(0, 0, 0), Normal(0, 0, 0), 0.f, 0.f, NULL);
+        dg.nn = nn;                                              // exactly the query normal
+        Intersection isect; isect.dg = dg;
+        Spectrum out[2];
+        for (int t = 0; t < 2; ++t) {
+            BSDF *bsdf = BSDF_ALLOC(arena, BSDF)(dg, dg.nn);
+            BxDF *lam = BSDF_ALLOC(arena, Lambertian)(Spectrum(1.f));
+            bsdf->Add(t == 0 ? lam : (BxDF *)BSDF_ALLOC(arena, BRDFToBTDF)(lam));
+            out[t] = map ? LPhoton(map, nPaths, sh->nLookup, buf.data(), bsdf, rng, isect, Vector(nn), sh->maxDistSquared) : Spectrum(0.f);
+        }
+        wr(o, out[0].c, 30); wr(o, out[1].c, 30);
+        arena.FreeAll();
+    }
+    fclose(o);
+}
+// (2) the radiance-photon lookup of final gathering (integrators/photonmap.cpp:238-243): RadiancePhotonProcess, unbounded radius
+static void radiance_nearest(const std::string &qfn, const std::string &ofn) {
+    FILE *f = xopen(qfn, "rb");
+    uint64_t n = read_header(f, "PVQRY001");
+    std::vector<float> q(6 * n); rd(f, q.data(), q.size()); fclose(f);
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVRADN01", n);
+    for (uint64_t i = 0; i < n; ++i) {
+        Normal nn(q[6*i+3], q[6*i+4], q[6*i+5]);
+        RadiancePhotonProcess proc(nn);
+        float md2 = INFINITY;
+        if (g_radMap) g_radMap->Lookup(Point(q[6*i], q[6*i+1], q[6*i+2]), proc, md2);
+        uint32_t idx = 0xFFFFFFFFu;
+        Spectrum Lo(0.f);
+        if (proc.photon) { memcpy(&idx, &proc.photon->Lo.intensity, 4); Lo = proc.photon->Lo; }
+        wr(o, &idx, 1); wr(o, &md2, 1); wr(o, Lo.c, 30);
     }
     fclose(o);
 }
@@ -420,6 +483,8 @@ void pbrtWorldEnd() {
         else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }
         else if (op == "--dump-photons") { dump_photons(ARG(1)); i += 1; }
         else if (op == "--dump-maps") { dump_maps(ARG(1)); i += 1; }
+        else if (op == "--surface-lphoton") { surface_lphoton(sh, ARG(1), ARG(2), ARG(3)); i += 3; }
+        else if (op == "--radiance-nearest") { radiance_nearest(ARG(1), ARG(2)); i += 2; }
         else if (op == "--knn") { knn(sh, ARG(1), atoi(ARG(2).c_str()), (float)atof(ARG(3).c_str()), ARG(4)); i += 4; }
         else if (op == "--lphoton") { lphoton(vi, scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--intersect") { intersect(scene, ARG(1), ARG(2)); i += 2; }

@@ -273,6 +273,22 @@ def surface_goldens(tmp):
         assert not rad["rho_t"].any()
         out["rad_pos"], out["rad_n"], out["rad_Lo"], out["rad_rho_r"] = rad["pos"], rad["n"], rad["Lo"], rad["rho_r"]
         out["counts"] = np.array([st["nshot"], st["caustic_paths"], st["indirect_paths"], st["direct_paths"], st["volume_paths"]], np.uint64)
+        # the surface integrator's photon lookups through the reference's own code: LPhoton (caustic / indirect map) and the
+        # radiance-photon lookup of final gathering, at radiance-photon sites and at points jittered off them
+        rng = np.random.default_rng(23)
+        pick = rng.choice(len(rad["pos"]), size=min(200, len(rad["pos"])), replace=False)
+        qp = np.concatenate([rad["pos"][pick], rad["pos"][pick] + rng.uniform(-0.06, 0.06, size=(len(pick), 3))]).astype(np.float32)
+        qn = np.concatenate([rad["n"][pick], rad["n"][pick] * np.where(rng.random(len(pick)) < 0.3, -1.0, 1.0)[:, None]]).astype(np.float32)
+        qf = os.path.join(tmp, name + "_sq.bin"); sceneio.write_queries(qf, qp, qn)
+        run(f, "--shoot", "--surface-lphoton", "caustic", qf, prefix + ".slc", "--surface-lphoton", "indirect", qf, prefix + ".sli",
+            "--radiance-nearest", qf, prefix + ".rn")
+        out["sq_pts"], out["sq_n"] = qp, qn
+        for key, ext in (("caustic", ".slc"), ("indirect", ".sli")):
+            v = sceneio.read_spectra(prefix + ext, b"PVSLPH01", per=2)
+            out["slp_%s_Lr_pi" % key], out["slp_%s_Lt_pi" % key] = v[:, 0], v[:, 1]
+        buf = open(prefix + ".rn", "rb").read(); assert buf[:8] == b"PVRADN01"
+        rec = np.frombuffer(buf, np.uint32, count=len(qp) * 32, offset=16).reshape(len(qp), 32)
+        out["radn_idx"] = rec[:, 0].copy(); out["radn_d2"] = rec[:, 1].copy().view(np.float32); out["radn_Lo"] = rec[:, 2:].copy().view(np.float32)
         out["params"] = np.array([wanted[0], wanted[1], wanted[2], int(fg), shoot_step, istep, st["nlookup"], st["maxdist2"]], np.float64)
         print("  %s: nshot %d, volume %d caustic %d indirect %d direct %d radiance %d" % (
             name, st["nshot"], len(out["volume_pos"]), len(out["caustic_pos"]), len(out["indirect_pos"]), len(out["direct_pos"]), len(rad["pos"])))

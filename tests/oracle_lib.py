@@ -183,3 +183,21 @@ def radiance(maps, counts, rp_pos, rp_n, rho_r, n_lookup, max_dist2):
     Lo = np.zeros((n, A.NSPEC), np.float32)
     lib().pvo_radiance(handles, wis, alphas, cnt, _p(rp_pos), _p(rp_n), _p(rho_r), C.c_uint64(n), C.c_uint32(n_lookup), C.c_float(max_dist2), _p(Lo))
     return Lo
+
+
+def surface_lphoton(pos, wi, alpha, pts, nf, n_lookup, max_dist2, n_paths):
+    """pvo_surface_lphoton: PhotonIntegrator's LPhoton, diffuse branch -> (Lr, Lt)."""
+    pts = f32(pts).reshape(-1, 3); nf = f32(nf).reshape(-1, 3); n = len(pts)
+    t = KdTree(pos); wi = f32(wi); alpha = f32(alpha)
+    Lr = np.zeros((n, A.NSPEC), np.float32); Lt = np.zeros((n, A.NSPEC), np.float32)
+    lib().pvo_surface_lphoton(C.c_void_p(t.h), _p(wi), _p(alpha), _p(pts), _p(nf), C.c_uint64(n), C.c_uint32(n_lookup), C.c_float(max_dist2),
+                              C.c_uint64(int(n_paths)), _p(Lr), _p(Lt))
+    return Lr, Lt
+
+
+def radiance_nearest(rp_pos, rp_n, pts, nrm):
+    rp_pos = f32(rp_pos).reshape(-1, 3); rp_n = f32(rp_n).reshape(-1, 3); pts = f32(pts).reshape(-1, 3); nrm = f32(nrm).reshape(-1, 3)
+    n = len(pts)
+    idx = np.zeros(n, np.uint32); d2 = np.zeros(n, np.float32)
+    lib().pvo_radiance_nearest(_p(rp_pos), _p(rp_n), C.c_uint64(len(rp_pos)), _p(pts), _p(nrm), C.c_uint64(n), _p(idx), _p(d2))
+    return idx, d2

@@ -458,3 +458,59 @@ def test_all_maps_sharded_over_two_ranks_reproduce_single_rank(golden, pv_factor
         for a, b in zip(got, want):
             assert np.array_equal(a, b), which
     assert min(int(stats[r].n[0]) for r in range(world)) > 0          # both ranks really traced photons
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_surface_integrator_lookups_vs_reference(golden, pv_factory, pkg, name):
+    """pv_select_map + pv_surface_lphoton / pv_radiance_nearest against the reference's own LPhoton (integrators/photonmap.cpp:62-108)
+    and RadiancePhotonProcess lookup (:238-243) on the reference's photon lists: Lr, Lt within 1e-4; nearest distance bit-exact, index
+    equal wherever the nearest facing radiance photon is unique."""
+    A = pkg._abi
+    g, scene = golden(name)
+    nlookup, md2 = int(g["params"][6]), float(g["params"][7])
+    nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+    pv = pv_factory(); pv.set_scene(scene)
+    for which, key in ((A.MAP_CAUSTIC, "caustic"), (A.MAP_INDIRECT, "indirect"), (A.MAP_DIRECT, "direct")):
+        pv.set_map_photons(which, g[key + "_pos"], g[key + "_wi"], g[key + "_alpha"])
+    pv.set_map_photons(A.MAP_RADIANCE, g["rad_pos"], g["rad_n"], g["rad_rho_r"])
+    inv_pi = np.float32(1.0 / np.pi)
+    for which, key, npaths in ((A.MAP_CAUSTIC, "caustic", cp), (A.MAP_INDIRECT, "indirect", ip)):
+        if len(g[key + "_pos"]) == 0:
+            continue
+        pv.select_map(which, float(np.sqrt(md2)), nlookup)
+        Lr, Lt = pv.SurfaceLPhoton(g["sq_pts"], g["sq_n"], nlookup, md2, npaths)
+        oLr, oLt = O.surface_lphoton(g[key + "_pos"], g[key + "_wi"], g[key + "_alpha"], g["sq_pts"], g["sq_n"], nlookup, md2, npaths)
+        # exact ties at the n_lookup-th distance (coincident monochromatic photons) make the reference's own result order dependent
+        tie = np.zeros(len(g["sq_pts"]), bool)
+        t = O.KdTree(g[key + "_pos"])
+        nf, idx, d2, _ = t.knn(g["sq_pts"], nlookup + 1, md2)
+        full = nf > nlookup
+        tie[full] = d2[full, nlookup] == d2[full, nlookup - 1]
+        u = ~tie
+        assert tie.mean() < 0.2
+        for got, ref in ((Lr * inv_pi, g["slp_%s_Lr_pi" % key]), (Lt * inv_pi, g["slp_%s_Lt_pi" % key])):
+            m = ref[u] > 0
+            assert m.any()
+            assert relerr(got[u], ref[u])[m].max() < 1e-4, key
+            assert np.array_equal(got[u] == 0, ref[u] == 0), key
+        with pytest.raises(Exception):
+            pv.LPhoton(g["sq_pts"], g["sq_n"])                     # the volume estimate refuses to run on a surface map
+    all_Lo = pv.RadiancePhotons(nlookup, md2, path_counts=(dp, ip, cp))
+    pv.select_map(A.MAP_RADIANCE, float(np.sqrt(md2)), nlookup)
+    idx, Lo = pv.RadianceNearest(g["sq_pts"], g["sq_n"])
+    ref_idx = g["radn_idx"]
+    oidx, od2 = O.radiance_nearest(g["rad_pos"], g["rad_n"], g["sq_pts"], g["sq_n"])
+    assert np.array_equal(idx, oidx)                               # the stated rule: nearest facing photon, ties by index
+    d2 = ((g["rad_pos"][idx] - g["sq_pts"]).astype(np.float32) ** 2)
+    same = idx == ref_idx
+    assert same.mean() > 0.95
+    assert np.array_equal(od2.view(np.uint32), g["radn_d2"].view(np.uint32))   # ... at the reference's nearest distance, bit for bit
+    assert np.array_equal(Lo, all_Lo[idx])                         # its radiance: the Lo pv_radiance_photons computed for that photon
+    ref_Lo = g["radn_Lo"]                                          # (vs the reference: 1e-4 except at EPhoton tie sites, see the test above)
+    assert np.quantile(relerr(Lo[same], ref_Lo[same])[ref_Lo[same] > 0], 0.9) < 1e-4
+    # far-away and degenerate queries: still the global nearest facing photon
+    far = np.array([[50, 50, 50], [-30, 0, 0], [0, 0, 0]], np.float32); fn = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    fi, _ = pv.RadianceNearest(far, fn, want_Lo=False)
+    oi, _ = O.radiance_nearest(g["rad_pos"], g["rad_n"], far, fn)
+    assert np.array_equal(fi, oi)

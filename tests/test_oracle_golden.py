@@ -175,3 +175,31 @@ def test_all_maps_with_surface_maps_off_is_the_volume_pass(golden):
     b = O.shoot_maps(scene, 1500, 0, 0, True, 0.05, 0.05, rng_mode=O.MT)
     assert b["nshot"] == a["nshot"] and np.array_equal(b["volume"]["pos"], a["pos"]) and np.array_equal(b["volume"]["alpha"], a["alpha"])
     assert len(b["caustic"]["pos"]) == len(b["indirect"]["pos"]) == len(b["direct"]["pos"]) == len(b["radiance"]["pos"]) == 0
+
+
+@pytest.mark.parametrize("name", SURF_SCENES)
+def test_surface_integrator_lookups_match_reference(golden, name):
+    """PhotonIntegrator's LPhoton (diffuse branch) on the caustic / indirect map and the radiance-photon lookup of final gathering,
+    against what the reference's own functions return (oracle/ref_harness.cpp --surface-lphoton / --radiance-nearest)."""
+    g, scene = golden(name)
+    nlookup, md2 = int(g["params"][6]), float(g["params"][7])
+    nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+    inv_pi = np.float32(1.0 / np.pi)
+    for key, npaths in (("caustic", cp), ("indirect", ip)):
+        if len(g[key + "_pos"]) == 0:
+            assert not g["slp_%s_Lr_pi" % key].any()
+            continue
+        Lr, Lt = O.surface_lphoton(g[key + "_pos"], g[key + "_wi"], g[key + "_alpha"], g["sq_pts"], g["sq_n"], nlookup, md2, npaths)
+        for got, ref in ((Lr * inv_pi, g["slp_%s_Lr_pi" % key]), (Lt * inv_pi, g["slp_%s_Lt_pi" % key])):
+            assert (ref > 0).any()
+            assert relerr(got, ref)[ref > 0].max() < 2e-6
+            assert np.array_equal(got == 0, ref == 0)
+    idx, d2 = O.radiance_nearest(g["rad_pos"], g["rad_n"], g["sq_pts"], g["sq_n"])
+    found = g["radn_idx"] != 0xFFFFFFFF
+    assert np.array_equal(idx != 0xFFFFFFFF, found) and found.any()
+    assert np.array_equal(d2[found].view(np.uint32), g["radn_d2"][found].view(np.uint32))     # the same nearest distance, bit for bit
+    # the index differs only where several radiance photons sit at that exact distance (monochromatic children on one point)
+    diff = np.nonzero(idx != g["radn_idx"])[0]
+    for q in diff:
+        assert np.array_equal(g["rad_pos"][idx[q]], g["rad_pos"][g["radn_idx"][q]])            # coincident radiance photons
+    assert len(diff) <= 0.05 * len(idx)
