@@ -211,6 +211,16 @@ class PhotonVolume:
         self._chk(self.lib.pv_radiance_nearest(self.ctx, _vp(pts), _vp(normals), C.c_uint64(n), _vp(idx), _vp(Lo)))
         return idx, Lo
 
+    def FinalGather(self, rays, step=None, index_base=0):
+        """One batch of final-gather rays (integrators/photonmap.cpp:231-243): trace, nearest facing radiance photon at the hit, its
+        Lo times the transmittance along the ray -> (Lindir, radiance photon index)."""
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        L = np.zeros((n, A.NSPEC), np.float32); idx = np.zeros(n, np.uint32)
+        step = 4.0 * self.stepsize if step is None else float(step)
+        self._chk(self.lib.pv_final_gather(self.ctx, _vp(rays), C.c_uint64(n), C.c_float(step), C.c_uint64(self.seed), C.c_uint64(index_base),
+                                           _vp(L), _vp(idx)))
+        return L, idx
+
     # ---- KdTree::Lookup --------------------------------------------------
     def Lookup(self, pts, k=None, r2=None):
         pts = _f32(pts).reshape(-1, 3); n = len(pts)

@@ -543,6 +543,24 @@ int pv_radiance_nearest(pv_ctx *ctx, const float *pts, const float *normals, uin
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PV_OK;
 }
+int pv_final_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step, uint64_t seed, uint64_t index_base, float *Lindir, uint32_t *idx) {
+    LOCK(ctx);
+    if (n && (!rays || !Lindir)) { ctx->err = "pv_final_gather: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    // slices bound the device staging (30 floats out per ray)
+    const uint64_t slice = 4ull << 20;
+    for (uint64_t a = 0; a < n; a += slice) {
+        const uint64_t m = std::min<uint64_t>(slice, n - a);
+        int rc = stage_in(ctx, &ctx->io, &ctx->io_bytes, rays + a, m * sizeof(pv_ray)); if (rc) return rc;
+        rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, m * PV_NSPEC * sizeof(float) + m * sizeof(uint32_t)); if (rc) return rc;
+        float *d_L = (float *)ctx->io2; uint32_t *d_idx = (uint32_t *)(d_L + m * PV_NSPEC);
+        rc = pvi_final_gather(ctx, (const pv_ray *)ctx->io, m, step, seed, index_base + a, d_L, d_idx); if (rc) return rc;
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(Lindir + a * PV_NSPEC, d_L, m * PV_NSPEC * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (idx) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(idx + a, d_idx, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PV_OK;
+}
 int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n) {
     LOCK(ctx);
     const uint64_t own[3] = {ctx->map_paths[2], ctx->map_paths[1], ctx->map_paths[0]};      // direct, indirect, caustic

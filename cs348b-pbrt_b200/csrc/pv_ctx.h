@@ -131,3 +131,4 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
 int pvi_surface_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_nf, uint64_t n, uint32_t n_lookup, float max_dist2, uint64_t n_paths,
                         float *d_Lr, float *d_Lt);
 int pvi_radiance_nearest(pv_ctx *ctx, const float *d_pts, const float *d_n, uint64_t n, uint32_t *d_idx, float *d_Lo30);
+int pvi_final_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, uint64_t seed, uint64_t index_base, float *d_Lindir, uint32_t *d_idx);

@@ -744,12 +744,9 @@ __global__ void __launch_bounds__(GW_THREADS) surface_lphoton_kernel(MapView m, 
 // integrators/photonmap.cpp:238-243): the NEAREST radiance photon whose normal faces the query normal, no radius limit.  One
 // thread per query walks growing shells of grid cells until the best distance found is inside the radius the visited cube
 // guarantees.  The grid is the one built over the radiance-photon class: wi4 holds the photon normals.  Ties by photon index.
-__global__ void radiance_nearest_kernel(MapView m, const float *__restrict__ pts, const float *__restrict__ nrm, uint64_t n,
-                                        uint32_t *__restrict__ idx_out) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+__device__ __noinline__ uint32_t radiance_nearest(const MapView &m, float px, float py, float pz, float nx, float ny, float nz) {
     const GridParams &g = m.g;
-    const v3 p = V3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), nn = V3(nrm[3 * q], nrm[3 * q + 1], nrm[3 * q + 2]);
+    const v3 p = V3(px, py, pz), nn = V3(nx, ny, nz);
     float best = INFINITY; uint32_t best_i = 0xFFFFFFFFu;
     if (m.n) {
         int cx, cy, cz;
@@ -804,8 +801,55 @@ __global__ void radiance_nearest_kernel(MapView m, const float *__restrict__ pts
             if (gr > 0.f && best < gr * gr) break;           // strict: an unseen photon cannot even tie
         }
     }
-    idx_out[q] = best_i;
+    return best_i;
 }
+__global__ void radiance_nearest_kernel(MapView m, const float *__restrict__ pts, const float *__restrict__ nrm, uint64_t n,
+                                        uint32_t *__restrict__ idx_out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    idx_out[q] = radiance_nearest(m, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2], nrm[3 * q], nrm[3 * q + 1], nrm[3 * q + 2]);
+}
+// One final-gather ray (integrators/photonmap.cpp:231-243 and :278-289): trace it, look the nearest facing radiance photon up at
+// the hit (normal = the hit's geometric normal turned towards the ray origin), attenuate its radiance by the transmittance of
+// the medium along the ray (renderer->Transmittance with sample == NULL: step 4 * stepSize, one random offset -- here a keyed
+// Philox draw per ray).  Lindir = 0 when the ray leaves the scene or no radiance photon faces the hit.
+template <bool SPH>
+__global__ void final_gather_kernel(MapView m, const DevScene *__restrict__ scp, const pv_ray *__restrict__ rays, uint64_t n, float step,
+                                    uint32_t k0, uint32_t k1, uint64_t index_base, const float *__restrict__ Lo32, float *__restrict__ Lindir,
+                                    uint32_t *__restrict__ hit_idx) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const DevScene &sc = *scp;
+    const pv_ray r = rays[q];
+    const v3 o = V3(r.o[0], r.o[1], r.o[2]), d = V3(r.d[0], r.d[1], r.d[2]);
+    float thit = r.maxt;
+    const int prim = bvh_traverse<false, SPH>(sc, o, d, r.mint, &thit, nullptr);
+    uint32_t idx = 0xFFFFFFFFu;
+    float s = 0.f;
+    if (prim >= 0) {
+        v3 hp, nn, dpdu; float eps;
+        const float *tv = sc.tri + 9 * (size_t)prim;
+        if (!SPH || tv[0] == tv[0]) {                       // shapes/trianglemesh.cpp:160-205 (default uvs), core/diffgeom.cpp:40-55
+            const v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
+            const v3 dp1 = p1 - p3, dp2 = p2 - p3;
+            dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;
+            const v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;
+            nn = vnorm(vcross(dpdu, dpdv));
+            hp = ray_at(o, d, thit);
+        } else sphere_dg(sc.spheres + (__float_as_uint(tv[0]) & PV_SPHERE_INDEX_MASK), o, d, thit, &hp, &nn, &dpdu, &eps);
+        if (vdot(nn, -d) < 0.f) nn = -nn;                   // Faceforward(nGather, -bounceRay.d)
+        idx = radiance_nearest(m, hp.x, hp.y, hp.z, nn.x, nn.y, nn.z);
+        if (idx != 0xFFFFFFFFu && sc.med.type != PV_MEDIUM_NONE) {
+            uint32_t w[4];
+            pv_philox4x32_10((uint32_t)(index_base + q), (uint32_t)((index_base + q) >> 32), 0u, PV_RNG_FINAL_GATHER, k0, k1, w);
+            s = med_tau_scalar(sc.med, o, d, r.mint, thit, step, pv_u32_to_float(w[0]), nullptr);
+        }
+    }
+    if (hit_idx) hit_idx[q] = idx;
+    for (int b = 0; b < PV_NSPEC; ++b)
+        Lindir[q * PV_NSPEC + b] = idx == 0xFFFFFFFFu ? 0.f : Lo32[(size_t)idx * 32 + b] * expf(-((sc.med.sigma_a[b] + sc.med.sigma_s[b]) * s));
+}
+
 __global__ void gather_lo_kernel(const uint32_t *__restrict__ idx, const float *__restrict__ Lo32, uint64_t n, float *__restrict__ out30) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * PV_NSPEC) return;
@@ -1033,6 +1077,23 @@ int pvi_radiance_nearest(pv_ctx *ctx, const float *d_pts, const float *d_n, uint
         gather_lo_kernel<<<(unsigned)((n * PV_NSPEC + 255) / 256), 256, 0, ctx->stream>>>(d_idx, ctx->rad_Lo, n, d_Lo30);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
+    return PV_OK;
+}
+int pvi_final_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, uint64_t seed, uint64_t index_base, float *d_Lindir, uint32_t *d_idx) {
+    if (!ctx->has_scene) { ctx->err = "pv_final_gather: no scene"; return PV_ESTATE; }
+    if (!ctx->built || ctx->map_which != PV_MAP_RADIANCE) {
+        ctx->err = "pv_final_gather: select the radiance-photon map first (pv_select_map with PV_MAP_RADIANCE)"; return PV_ESTATE;
+    }
+    if (!ctx->rad_valid) { ctx->err = "pv_final_gather: radiance not computed (call pv_radiance_photons)"; return PV_ESTATE; }
+    if (!(step > 0.f)) { ctx->err = "pv_final_gather: step must be > 0"; return PV_EINVAL; }
+    if (n == 0) return PV_OK;
+    MapView m = map_view(ctx);
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (ctx->hscene.n_spheres) final_gather_kernel<true><<<blocks, 128, 0, ctx->stream>>>(m, ctx->dscene, d_rays, n, step, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                                       index_base, ctx->rad_Lo, d_Lindir, d_idx);
+    else final_gather_kernel<false><<<blocks, 128, 0, ctx->stream>>>(m, ctx->dscene, d_rays, n, step, (uint32_t)seed, (uint32_t)(seed >> 32), index_base,
+                                                                   ctx->rad_Lo, d_Lindir, d_idx);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }
 int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L) {

@@ -319,6 +319,13 @@ int pv_surface_lphoton(pv_ctx *ctx, const float *pts, const float *nf, uint64_t 
  * radiance photon whose normal has a positive dot product with it.  idx[n] = its index in the PV_MAP_RADIANCE list
  * or 0xFFFFFFFF; Lo[30n] (may be NULL) = its radiance from the last pv_radiance_photons.                           */
 int pv_radiance_nearest(pv_ctx *ctx, const float *pts, const float *normals, uint64_t n, uint32_t *idx, float *Lo);
+/* One batch of final-gather rays (integrators/photonmap.cpp:231-243, :278-289), the radiance-photon map selected: each ray is
+ * traced (Scene::Intersect), the nearest radiance photon facing Faceforward(hit normal, -d) is looked up at the hit, and its
+ * Lo is attenuated by renderer->Transmittance(ray, sample == NULL) = exp(-tau(ray up to the hit, step, u)) with
+ * step = 4 * the volume integrator's stepsize and u a Philox draw keyed by (seed, index_base + i).  Lindir[30n]; 0 for rays
+ * that hit nothing or find no facing photon.  idx[n] (may be NULL) = the radiance photon used or 0xFFFFFFFF.                */
+int pv_final_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step, uint64_t seed, uint64_t index_base,
+                    float *Lindir, uint32_t *idx);
 
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);

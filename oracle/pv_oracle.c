@@ -1604,6 +1604,40 @@ int pvo_radiance_nearest(const float *rp_pos, const float *rp_n, uint64_t n_rp, 
     return 0;
 }
 
+/* One batch of final-gather rays (integrators/photonmap.cpp:231-243): Scene::Intersect, Faceforward(hit normal, -d), nearest
+ * facing radiance photon, Lo * renderer->Transmittance(ray, NULL) with the offset drawn from the keyed Philox stream. */
+int pvo_final_gather(const pv_scene_desc *sc, const float *rp_pos, const float *rp_n, const float *rp_Lo, uint64_t n_rp, const pv_ray *rays,
+                     uint64_t n, float step, uint64_t seed, uint64_t index_base, float *Lindir, uint32_t *idx) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const pv_ray *r = &rays[i];
+        v3 o = V(r->o[0], r->o[1], r->o[2]), d = V(r->d[0], r->d[1], r->d[2]);
+        float thit = r->maxt;
+        int prim = bvh_intersect(sc, o, d, r->mint, &thit, NULL);
+        uint32_t bi = 0xFFFFFFFFu;
+        spec L = s_const(0.f);
+        if (prim >= 0) {
+            isect_t is; make_isect(sc, prim, o, d, thit, &is);
+            v3 nn = is.nn;
+            if (vdot(nn, vneg(d)) < 0.f) nn = vneg(nn);
+            float q[3] = {is.p.x, is.p.y, is.p.z}, qn[3] = {nn.x, nn.y, nn.z};
+            pvo_radiance_nearest(rp_pos, rp_n, n_rp, q, qn, 1, &bi, NULL);
+            if (bi != 0xFFFFFFFFu) {
+                spec T = s_const(1.f);
+                if (sc->medium && sc->medium->type != PV_MEDIUM_NONE) {
+                    uint32_t w[4]; uint64_t ri = index_base + i;
+                    pv_philox4x32_10((uint32_t)ri, (uint32_t)(ri >> 32), 0u, PV_RNG_FINAL_GATHER, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+                    spec tau = med_tau(sc->medium, o, d, r->mint, thit, step, pv_u32_to_float(w[0]), NULL);
+                    T = s_exp_neg(&tau);
+                }
+                for (int b = 0; b < NS; ++b) L.c[b] = rp_Lo[NS * (size_t)bi + b] * T.c[b];
+            }
+        }
+        memcpy(Lindir + NS * i, L.c, sizeof(L.c));
+        if (idx) idx[i] = bi;
+    }
+    return 0;
+}
+
 void pvo_photons_free(pvo_photons *p) {
     free(p->pos); free(p->wi); free(p->alpha); free(p->ids);
     memset(p, 0, sizeof(*p));

@@ -101,6 +101,9 @@ int  pvo_surface_lphoton(const pvo_kdtree *t, const float *wi, const float *alph
 int  pvo_radiance_nearest(const float *rp_pos, const float *rp_n, uint64_t n_rp, const float *pts, const float *nrm, uint64_t n,
                           uint32_t *idx, float *d2out);
 
+int  pvo_final_gather(const pv_scene_desc *sc, const float *rp_pos, const float *rp_n, const float *rp_Lo, uint64_t n_rp, const pv_ray *rays,
+                      uint64_t n, float step, uint64_t seed, uint64_t index_base, float *Lindir, uint32_t *idx);
+
 /* small known-answer helpers exposed for unit tests */
 uint32_t pvo_mt_first(uint32_t seed, uint32_t *out, uint32_t n);
 void     pvo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -201,3 +201,13 @@ def radiance_nearest(rp_pos, rp_n, pts, nrm):
     idx = np.zeros(n, np.uint32); d2 = np.zeros(n, np.float32)
     lib().pvo_radiance_nearest(_p(rp_pos), _p(rp_n), C.c_uint64(len(rp_pos)), _p(pts), _p(nrm), C.c_uint64(n), _p(idx), _p(d2))
     return idx, d2
+
+
+def final_gather(scene, rp_pos, rp_n, rp_Lo, rays, step, seed=0, index_base=0):
+    rp_pos = f32(rp_pos).reshape(-1, 3); rp_n = f32(rp_n).reshape(-1, 3); rp_Lo = f32(rp_Lo).reshape(-1, A.NSPEC)
+    rays = np.ascontiguousarray(rays); n = len(rays)
+    L = np.zeros((n, A.NSPEC), np.float32); idx = np.zeros(n, np.uint32)
+    d = scene.desc()
+    lib().pvo_final_gather(C.byref(d), _p(rp_pos), _p(rp_n), _p(rp_Lo), C.c_uint64(len(rp_pos)), _p(rays), C.c_uint64(n), C.c_float(step),
+                           C.c_uint64(seed), C.c_uint64(index_base), _p(L), _p(idx))
+    return L, idx

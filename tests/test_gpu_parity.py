@@ -514,3 +514,57 @@ def test_surface_integrator_lookups_vs_reference(golden, pv_factory, pkg, name):
     fi, _ = pv.RadianceNearest(far, fn, want_Lo=False)
     oi, _ = O.radiance_nearest(g["rad_pos"], g["rad_n"], far, fn)
     assert np.array_equal(fi, oi)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SURF_SCENES + ["sphere_glass"])
+def test_final_gather_rays_vs_oracle(golden, pv_factory, pkg, name):
+    """pv_final_gather (trace + nearest facing radiance photon at the hit + transmittance along the ray) against the composition of
+    the pinned oracle's pieces (bvh_intersect / make_isect are bit-exact vs the reference, pvo_radiance_nearest and the
+    transmittance march are pinned above) on the same Philox offsets: same radiance photon per ray, Lindir within 1e-4."""
+    A = pkg._abi
+    g, scene = golden(name)
+    rng = np.random.default_rng(3)
+    if name in SURF_SCENES:
+        rp_pos, rp_n, rp_rho = g["rad_pos"], g["rad_n"], g["rad_rho_r"]
+        Lo = g["rad_Lo"]
+        origins = g["sq_pts"][:200] + 1e-3 * g["sq_n"][:200]
+    else:                                              # a scene with a sphere: radiance photons scattered over its surfaces
+        hit = g["hit_prim"] != 0xFFFFFFFF
+        hr = g["hit_rays"][hit][:300]
+        rp_pos = (hr["o"] + hr["d"] * g["hit_t"][hit][:300, None]).astype(np.float32)
+        rp_n = -hr["d"] / np.linalg.norm(hr["d"], axis=1, keepdims=True); rp_n = rp_n.astype(np.float32)
+        rp_rho = np.ones((len(rp_pos), 30), np.float32); Lo = rng.random((len(rp_pos), 30)).astype(np.float32)
+        origins = g["q_pts"][:200]
+    n = 1500
+    o = origins[rng.integers(0, len(origins), size=n)].astype(np.float32)
+    z = rng.uniform(-1, 1, size=n); phi = rng.uniform(0, 2 * np.pi, size=n); rr = np.sqrt(1 - z * z)
+    d = np.stack([rr * np.cos(phi), rr * np.sin(phi), z], axis=1).astype(np.float32)
+    rays = pkg.sceneio.make_rays(o, d, 1e-3, np.inf)
+    istep = 0.05
+    pv = pv_factory(stepsize=istep, seed=29); pv.set_scene(scene)
+    pv.set_map_photons(A.MAP_RADIANCE, rp_pos, rp_n, rp_rho)
+    # Lo of the radiance photons: computed by pv_radiance_photons from injected maps where the golden has them, else zero maps + a fake Lo
+    if name in SURF_SCENES:
+        nshot, cp, ip, dp, vp = [int(x) for x in g["counts"]]
+        for which, key in ((A.MAP_CAUSTIC, "caustic"), (A.MAP_INDIRECT, "indirect"), (A.MAP_DIRECT, "direct")):
+            pv.set_map_photons(which, g[key + "_pos"], g[key + "_wi"], g[key + "_alpha"])
+        Lo = pv.RadiancePhotons(int(g["params"][6]), float(g["params"][7]), path_counts=(dp, ip, cp))
+    else:
+        # direct map = the radiance sites themselves with alpha chosen so that E is finite; only the plumbing matters here
+        pv.set_map_photons(A.MAP_DIRECT, rp_pos, rp_n, Lo)
+        Lo = pv.RadiancePhotons(20, 0.5, path_counts=(1000, 0, 0))
+    assert (Lo > 0).any()
+    pv.select_map(A.MAP_RADIANCE, 0.25, 50)
+    L, idx = pv.FinalGather(rays, index_base=1000)
+    oL, oidx = O.final_gather(scene, rp_pos, rp_n, Lo, rays, 4.0 * istep, seed=29, index_base=1000)
+    assert (oidx != 0xFFFFFFFF).sum() > 0.5 * n
+    same = idx == oidx
+    # different radiance photon only for coincident photons (exact ties)
+    for q in np.nonzero(~same)[0]:
+        assert idx[q] != 0xFFFFFFFF and oidx[q] != 0xFFFFFFFF and np.array_equal(rp_pos[idx[q]], rp_pos[oidx[q]]), q
+    assert same.mean() > 0.97
+    m = (oL > 0) & same[:, None]
+    assert m.any()
+    assert relerr(L, oL)[m].max() < 1e-4
+    assert np.array_equal((L == 0)[same], (oL == 0)[same])
