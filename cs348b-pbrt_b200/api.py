@@ -192,6 +192,10 @@ class PhotonVolume:
         self._chk(self.lib.pv_radiance_photons(self.ctx, C.c_uint32(n_lookup), C.c_float(max_dist2), pc, _vp(Lo), C.c_uint64(n.value), C.byref(got)))
         return Lo
 
+    def set_radiance_lo(self, Lo):
+        Lo = _f32(Lo).reshape(-1, A.NSPEC)
+        self._chk(self.lib.pv_set_radiance_lo(self.ctx, _vp(Lo), C.c_uint64(len(Lo))))
+
     def select_map(self, which, maxdist, nused):
         """Build the lookup grid over a photon class (A.MAP_*); build() puts the volume map back."""
         self._chk(self.lib.pv_select_map(self.ctx, C.c_int(which), C.c_float(maxdist), C.c_uint32(nused)))

@@ -506,6 +506,26 @@ int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi, 
     s.n = n;
     return PV_OK;
 }
+int pv_set_radiance_lo(pv_ctx *ctx, const float *Lo, uint64_t n) {
+    LOCK(ctx);
+    ctx->rad_valid = false;
+    if (n != ctx->surf[3].n) { ctx->err = "pv_set_radiance_lo: n differs from the number of radiance photons"; return PV_EINVAL; }
+    if (n && !Lo) { ctx->err = "pv_set_radiance_lo: null pointer"; return PV_EINVAL; }
+    if (n) {
+        if (ctx->rad_Lo_cap < n) {
+            if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
+            ctx->rad_Lo = nullptr; ctx->rad_Lo_cap = 0;
+            PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->rad_Lo, n * 32 * sizeof(float)));
+            ctx->rad_Lo_cap = n;
+        }
+        int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, n * PV_NSPEC * sizeof(float)); if (rc) return rc;
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io, Lo, n * PV_NSPEC * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        alpha_30_to_32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->io, ctx->rad_Lo, n);
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->rad_valid = true;
+    return PV_OK;
+}
 int pv_select_map(pv_ctx *ctx, int map, float maxdist, uint32_t nused) {
     LOCK(ctx);
     return pvi_build_map(ctx, map, maxdist, nused);

@@ -32,6 +32,10 @@
 #include <map>
 #include <algorithm>
 #include <sys/time.h>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
+#include <chrono>
 
 #define private public
 #define protected public
@@ -60,6 +64,7 @@
 #include "materials/matte.h"
 #include "materials/glass.h"
 #include "integrators/photonvolume.h"
+#include "integrators/photonmap.h"
 #include "renderers/samplerrenderer.h"
 #undef private
 #undef protected
@@ -79,8 +84,13 @@ struct PvBridge {
     float stepsize, maxdist;
     uint32_t nused;
     uint64_t seed;
+    uint64_t n_indirect;
     bool ready;
-    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), ready(false) {}
+    // final gathering runs on a context of its own (scene + radiance photons + their grid): rays spawned by specular bounces
+    // call the volume integrator (pv_gather on `ctx`, grid on the volume map) while primary hits are still being shaded
+    pv_ctx *fg_ctx;
+    std::vector<float> rad_pos, rad_nrm, rad_Lo;
+    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), fg_ctx(NULL) {}
 };
 PvBridge g_pv;
 
@@ -96,6 +106,79 @@ struct PvRecord {                 // one camera sample waiting for its volume te
     pv_ray ray;
 };
 std::vector<std::vector<PvRecord> > *g_records = NULL;
+
+// ---- final gathering of PRIMARY hits as a wavefront (integrators/photonmap.cpp:196-312) ----------------------------
+// The reference's PhotonIntegrator::Li traces 2 x gatherSamples rays per shaded point and, for each, looks the nearest radiance
+// photon up and marches the medium for the transmittance -- one ray at a time on the CPU; with final gathering on this is
+// nearly all of a render's time.  Here the task that shades a camera sample only GENERATES those rays (the reference's own
+// BSDF / sampling code and its MIS weights) and records, per ray, the spectrum C its radiance is multiplied with; the rays of
+// many samples go to the GPU as one pv_final_gather batch; then Ls += sum C * Lindir.  Everything else of Li (emission, direct
+// lighting, the caustic estimate, specular bounces) is the reference's own code, run through a clone of the integrator whose
+// shooter has no indirect map (so that Li adds neither the final gather nor the indirect estimate); rays spawned by specular
+// bounces re-enter through SamplerRenderer::Li and use the unmodified integrator, final gathering included.
+struct PvGatherRay { uint32_t rec; Spectrum C; pv_ray ray; };
+struct PvFinalGather {
+    PhotonIntegrator *full, *primary;      // the scene's integrator, and its clone without the indirect map
+    std::vector<std::vector<PvGatherRay> > rays;      // per render task
+    uint64_t next_index, total_rays; double gpu_seconds;
+    PvFinalGather() : full(NULL), primary(NULL), next_index(0), total_rays(0), gpu_seconds(0) {}
+};
+PvFinalGather *g_fg = NULL;
+
+// The sampling half of the final gather for one shaded point: which rays, with which weights (photonmap.cpp:204-312).
+void pv_queue_final_gather(const PhotonIntegrator *pi, const RayDifferential &ray, const Intersection &isect, const Sample *sample,
+                           MemoryArena &arena, uint32_t rec, std::vector<PvGatherRay> &out) {
+    KdTree<Photon> *indirectMap = pi->photonShooter->indirectMap;
+    BSDF *bsdf = isect.GetBSDF(ray, arena);
+    const BxDFType nonSpecular = BxDFType(BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_DIFFUSE | BSDF_GLOSSY);
+    if (bsdf->NumComponents(nonSpecular) == 0) return;
+    const Point &p = bsdf->dgShading.p;
+    const Normal &n = bsdf->dgShading.nn;
+    const Vector wo = -ray.d;
+    // directions of the 50 nearest indirect photons: the importance function of the second half of the rays (:204-219)
+    const uint32_t nDirs = 50;
+    ClosePhoton close[nDirs];
+    PhotonProcess proc(nDirs, close);
+    float searchDist2 = pi->maxDistSquared;
+    while (proc.nFound < nDirs) {
+        float md2 = searchDist2;
+        proc.nFound = 0;
+        indirectMap->Lookup(p, proc, md2);
+        searchDist2 *= 2.f;
+    }
+    Vector dirs[nDirs];
+    for (uint32_t i = 0; i < nDirs; ++i) dirs[i] = close[i].photon->wi;
+    const int gs = pi->gatherSamples;
+    const float cosGA = pi->cosGatherAngle, conePdf = UniformConePdf(cosGA);
+    PvGatherRay g; memset(&g.ray, 0, sizeof(g.ray)); g.rec = rec;
+    g.ray.o[0] = p.x; g.ray.o[1] = p.y; g.ray.o[2] = p.z; g.ray.mint = isect.rayEpsilon; g.ray.maxt = INFINITY; g.ray.time = ray.time;
+    for (int half = 0; half < 2; ++half)
+        for (int i = 0; i < gs; ++i) {
+            Vector wi; float pdf = 0.f; Spectrum fr;
+            if (half == 0) {                                                   // BSDF-sampled ray (:223-229)
+                BSDFSample bs(sample, pi->bsdfGatherSampleOffsets, i);
+                fr = bsdf->Sample_f(wo, &wi, bs, &pdf, BxDFType(BSDF_ALL & ~BSDF_SPECULAR));
+                if (fr.IsBlack() || pdf == 0.f) continue;
+            } else {                                                           // ray in a cone around a photon direction (:264-275)
+                BSDFSample gsamp(sample, pi->indirGatherSampleOffsets, i);
+                int photonNum = min((int)nDirs - 1, Floor2Int(gsamp.uComponent * nDirs));
+                Vector vx, vy;
+                CoordinateSystem(dirs[photonNum], &vx, &vy);
+                wi = UniformSampleCone(gsamp.uDir[0], gsamp.uDir[1], cosGA, vx, vy, dirs[photonNum]);
+                fr = bsdf->f(wo, wi);
+                if (fr.IsBlack()) continue;
+            }
+            float photonPdf = 0.f;                                             // pdf of the photon-direction strategy for wi (:246-252)
+            for (uint32_t j = 0; j < nDirs; ++j) if (Dot(dirs[j], wi) > .999f * cosGA) photonPdf += conePdf;
+            photonPdf /= nDirs;
+            float scale;
+            if (half == 0) scale = AbsDot(wi, n) * PowerHeuristic(gs, pdf, gs, photonPdf) / pdf;                       // :253-254
+            else scale = AbsDot(wi, n) * PowerHeuristic(gs, photonPdf, gs, bsdf->Pdf(wo, wi)) / photonPdf;            // :299-301
+            g.C = fr * (scale / gs);
+            g.ray.d[0] = wi.x; g.ray.d[1] = wi.y; g.ray.d[2] = wi.z;
+            out.push_back(g);
+        }
+}
 }  // namespace
 
 // ------------------------------------------------------------------ PhotonShooter::Preprocess (core/photonshooter.cpp:457-526)
@@ -139,6 +222,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         if (rc == PV_ENOPHOTONS) Error("Unable to store enough photons.  Giving up.\n");      // photonshooter.cpp:292
         else if (rc) pv_fail("pv_shoot_maps", rc);
         nCausticPaths = (int)ms.n_caustic_paths; nIndirectPaths = (int)ms.n_indirect_paths; nVolumePaths = (int)ms.n_volume_paths;
+        g_pv.n_indirect = ms.n[PV_MAP_INDIRECT];
         KdTree<Photon> **maps[2] = {&causticMap, &indirectMap};
         const int which[2] = {PV_MAP_CAUSTIC, PV_MAP_INDIRECT};
         for (int k = 0; k < 2; ++k) {
@@ -172,7 +256,9 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
                 memcpy(rps[i].Lo.c, &Lo[(size_t)PV_NSPEC * i], sizeof(float) * PV_NSPEC);
             }
             radianceMap = new KdTree<RadiancePhoton>(rps);
-        }
+            g_pv.rad_pos.swap(pos); g_pv.rad_nrm.swap(nrm); g_pv.rad_Lo.swap(Lo);
+            g_pv.rad_pos.resize(3 * got); g_pv.rad_nrm.resize(3 * got); g_pv.rad_Lo.resize((size_t)PV_NSPEC * got);
+        } else { g_pv.rad_pos.clear(); g_pv.rad_nrm.clear(); g_pv.rad_Lo.clear(); }
         rc = pv_build(g_pv.ctx, vi->maxDist, (uint32_t)vi->nUsed);
         if (rc) pv_fail("pv_build", rc);
         fprintf(stderr, "[pv] all maps on the GPU: %llu volume, %llu caustic, %llu indirect, %llu direct photons, %llu radiance photons from %llu light "
@@ -230,6 +316,83 @@ static void pv_fill_ray(const RayDifferential &ray, float u_scatter, pv_ray *r) 
     r->mint = ray.mint; r->maxt = ray.maxt; r->time = ray.time; r->u_scatter = u_scatter;
 }
 
+// ---- single-ray calls, gathered across the render threads --------------------------------------------------------------
+// Rays spawned by specular bounces reach the volume integrator one at a time from inside the reference's recursive surface
+// shading (SpecularReflect/Transmit -> Renderer::Li -> VolumeIntegrator::Li), on every render thread at once.  A device round
+// trip per ray, serialised by the context's mutex, is what such a render would spend its time on (measured: 3.2 of 3.3 s).
+// Instead the first thread that arrives opens a batch and waits a few tens of microseconds for the other threads' rays; the
+// batch is ONE pv_gather; everybody picks its own result up.  The result of a ray does not depend on who it shared a batch
+// with: every ray carries its own Philox stream index.
+namespace {
+struct LiBatch {
+    std::vector<pv_ray> rays; std::vector<uint64_t> index;
+    std::vector<float> L, T;
+    bool closed, done; int rc;
+    std::condition_variable cv;
+    LiBatch() : closed(false), done(false), rc(0) {}
+};
+struct LiBatcher {
+    std::mutex mu;
+    std::shared_ptr<LiBatch> open;
+    std::condition_variable arrived;
+    unsigned long long calls, batches;
+    double seconds;                      // inside pv_gather
+    bool in_flight;                      // a batch is on the device: the open one keeps collecting until it is back
+    LiBatcher() : calls(0), batches(0), seconds(0), in_flight(false) {}
+};
+LiBatcher g_li;
+const size_t kLiBatchMax = 64;
+}  // namespace
+
+static int pv_li_batched(const pv_ray &r, uint64_t index, const pv_gather_params &prm0, float *L, float *T) {
+    std::unique_lock<std::mutex> lock(g_li.mu);
+    g_li.calls++;
+    std::shared_ptr<LiBatch> b = g_li.open;
+    const bool leader = !b;
+    if (leader) { b = std::make_shared<LiBatch>(); g_li.open = b; }
+    const size_t slot = b->rays.size();
+    b->rays.push_back(r); b->index.push_back(index);
+    if (!leader) {
+        if (b->rays.size() >= kLiBatchMax) { b->closed = true; g_li.open.reset(); }
+        g_li.arrived.notify_all();
+        b->cv.wait(lock, [&] { return b->done; });
+    } else {
+        // wait for company: while another batch is on the device (one warp marches one ray, so a call takes as long as its
+        // longest ray -- of the order of a millisecond -- however few rays it carries), and then until every core has a ray in or
+        // 100 us have passed without a new arrival
+        const size_t want = (size_t)std::max(1, NumSystemCores());
+        while (!b->closed) {
+            if (g_li.in_flight) { g_li.arrived.wait_for(lock, std::chrono::microseconds(200)); continue; }
+            if (b->rays.size() >= want) break;
+            const size_t before = b->rays.size();
+            g_li.arrived.wait_for(lock, std::chrono::microseconds(100));
+            if (!g_li.in_flight && b->rays.size() == before) break;
+        }
+        if (!b->closed) { b->closed = true; g_li.open.reset(); }
+        while (g_li.in_flight) g_li.arrived.wait_for(lock, std::chrono::microseconds(200));
+        g_li.in_flight = true;
+        g_li.batches++;
+        const size_t n = b->rays.size();
+        b->L.resize(n * PV_NSPEC); b->T.resize(n * PV_NSPEC);
+        lock.unlock();
+        // rays of one call get consecutive stream indices: sort the batch into runs? -- simpler: one stream base per ray is what
+        // the ABI offers per CALL, so the batch goes down as ONE call whose base is the leader's index; ray i uses base + i
+        pv_gather_params prm = prm0; prm.ray_index_base = b->index[0];
+        const double t0 = now_s();
+        int rc = pv_gather(g_pv.ctx, b->rays.data(), n, &prm, b->L.data(), b->T.data());
+        const double dt = now_s() - t0;
+        lock.lock();
+        g_li.seconds += dt;
+        g_li.in_flight = false;
+        g_li.arrived.notify_all();
+        b->rc = rc; b->done = true;
+        b->cv.notify_all();
+    }
+    if (b->rc) return b->rc;
+    memcpy(L, &b->L[slot * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(T, &b->T[slot * PV_NSPEC], sizeof(float) * PV_NSPEC);
+    return 0;
+}
+
 // Single-ray form (kept so every caller of the VolumeIntegrator interface still works); the renderer below batches.
 Spectrum PhotonVolumeIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
                                     RNG &rng, Spectrum *T, MemoryArena &arena) const {
@@ -240,7 +403,7 @@ Spectrum PhotonVolumeIntegrator::Li(const Scene *scene, const Renderer *renderer
     prm.stepsize = stepSize; prm.nused = (uint32_t)nUsed; prm.maxdist = maxDist; prm.seed = g_pv.seed;
     prm.ray_index_base = ((uint64_t)rng.RandomUInt() << 20) | 0x8000000000000000ull;     // a stream of its own per call
     float L[PV_NSPEC], Tr[PV_NSPEC];
-    int rc = pv_gather(g_pv.ctx, &r, 1, &prm, L, Tr);
+    int rc = pv_li_batched(r, prm.ray_index_base, prm, L, Tr);
     if (rc) pv_fail("pv_gather", rc);
     Spectrum Lv(0.f);
     memcpy(Lv.c, L, sizeof(L)); memcpy(T->c, Tr, sizeof(Tr));
@@ -263,9 +426,15 @@ SamplerRenderer::~SamplerRenderer() {
 }
 
 static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Sample *sample, RNG &rng,
-                                MemoryArena &arena, Intersection *isect) {
+                                MemoryArena &arena, Intersection *isect, std::vector<PvGatherRay> *fg_out = NULL, uint32_t rec = 0) {
     // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
-    if (scene->Intersect(ray, isect)) return r->surfaceIntegrator->Li(scene, r, ray, *isect, sample, rng, arena);
+    if (scene->Intersect(ray, isect)) {
+        if (fg_out) {       // a primary hit: Li without the final gather, whose rays are queued for the GPU
+            pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, *fg_out);
+            return g_fg->primary->Li(scene, r, ray, *isect, sample, rng, arena);
+        }
+        return r->surfaceIntegrator->Li(scene, r, ray, *isect, sample, rng, arena);
+    }
     Spectrum Li = 0.f;
     for (uint32_t i = 0; i < scene->lights.size(); ++i) Li += scene->lights[i]->Le(ray);
     return Li;
@@ -311,7 +480,9 @@ void SamplerRendererTask::Run() {
                 PvRecord rec;
                 rec.imageX = samples[i].imageX; rec.imageY = samples[i].imageY; rec.rayWeight = rayWeight;
                 rec.Ls = 0.f;
-                if (rayWeight > 0.f) rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i]);
+                if (rayWeight > 0.f)
+                    rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i], g_fg ? &g_fg->rays[taskNum] : NULL,
+                                             (uint32_t)out->size());
                 pv_fill_ray(rays[i], samples[i].oneD[vi->scatterSampleOffset][0], &rec.ray);
                 out->push_back(rec);
                 continue;
@@ -336,22 +507,101 @@ void SamplerRenderer::Render(const Scene *scene) {
     volumeIntegrator->Preprocess(scene, camera, this);
     Sample *sample = new Sample(sampler, surfaceIntegrator, volumeIntegrator, scene);
     camera->AutoFocus(this, scene, sample);
+    // With the volume term on the GPU a render thread spends most of a specular bounce waiting for the device, and the batches
+    // of secondary rays are as large as there are threads waiting: run 4 threads per core unless the user chose a count
+    // (--ncores) or PV_THREADS says otherwise.  (The pool is created at the first EnqueueTasks, core/parallel.cpp:728-737.)
+    if (g_pv.ready && scene->volumeRegion) {
+        const char *th = getenv("PV_THREADS");
+        if (th && atoi(th) > 0) PbrtOptions.nCores = atoi(th);
+        else if (PbrtOptions.nCores == 0) PbrtOptions.nCores = min(256, 4 * NumSystemCores());
+    }
     int nPixels = camera->film->xResolution * camera->film->yResolution;
     int nTasks = max(32 * NumSystemCores(), nPixels / (16 * 16));
     nTasks = RoundUpPow2(nTasks);
     std::vector<std::vector<PvRecord> > records(nTasks);
     g_records = &records;
     double t0 = now_s();
+    // ---- final gathering of primary hits on the GPU?  Needs the photon-volume context, a PhotonIntegrator with final gathering, an
+    // indirect map with at least the 50 photons the importance lookup insists on (photonmap.cpp:209-214) and radiance photons.
+    PvFinalGather fg;
+    PhotonVolumeIntegrator *pvi = dynamic_cast<PhotonVolumeIntegrator *>(volumeIntegrator);
+    PhotonIntegrator *pmi = dynamic_cast<PhotonIntegrator *>(surfaceIntegrator);
+    const char *fg_mode = getenv("PV_FINAL_GATHER");                          // "cpu": keep the reference's per-ray final gather
+    if (g_pv.ready && pvi && pmi && pmi->finalGather && pmi->photonShooter && pmi->photonShooter->indirectMap && pmi->photonShooter->radianceMap &&
+        !g_pv.rad_pos.empty() &&
+        g_pv.n_indirect >= 50 && !(fg_mode && !strcmp(fg_mode, "cpu")) && !visualizeObjectIds) {
+        PhotonShooter *bare = (PhotonShooter *)malloc(sizeof(PhotonShooter));       // shallow clones, never destroyed (they own nothing)
+        memcpy((void *)bare, (const void *)pmi->photonShooter, sizeof(PhotonShooter));
+        bare->indirectMap = NULL;
+        fg.full = pmi;
+        fg.primary = (PhotonIntegrator *)malloc(sizeof(PhotonIntegrator));
+        memcpy((void *)fg.primary, (const void *)pmi, sizeof(PhotonIntegrator));
+        fg.primary->photonShooter = bare;
+        fg.rays.resize(nTasks);
+        if (!g_pv.fg_ctx) {
+            const char *dev = getenv("PV_DEVICE");
+            int rc = pv_create(&g_pv.fg_ctx, dev ? atoi(dev) : 0);
+            if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
+        }
+        const uint64_t nrad = g_pv.rad_pos.size() / 3;
+        std::vector<float> rho((size_t)PV_NSPEC * nrad, 1.f);                  // rho_r plays no part in the lookups
+        int rc = pv_set_scene(g_pv.fg_ctx, &g_pv.scene.desc);
+        if (!rc) rc = pv_set_map_photons(g_pv.fg_ctx, PV_MAP_RADIANCE, g_pv.rad_pos.data(), g_pv.rad_nrm.data(), rho.data(), nrad);
+        if (!rc) rc = pv_set_radiance_lo(g_pv.fg_ctx, g_pv.rad_Lo.data(), nrad);
+        if (!rc) rc = pv_select_map(g_pv.fg_ctx, PV_MAP_RADIANCE, sqrtf(pmi->maxDistSquared), pmi->nLookup);
+        if (rc) Severe("final-gather context failed (%d): %s", rc, pv_last_error(g_pv.fg_ctx));
+        g_fg = &fg;
+    }
     {
         ProgressReporter reporter(nTasks, "Rendering");
-        vector<Task *> renderTasks;
-        for (int i = 0; i < nTasks; ++i)
-            renderTasks.push_back(new SamplerRendererTask(scene, this, camera, reporter, sampler, sample, visualizeObjectIds,
-                                                          nTasks - 1 - i, nTasks));
-        EnqueueTasks(renderTasks);
-        WaitForAllTasks();
-        for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
+        // tasks run in groups so that the queued gather rays of a group (160 B each) stay within ~0.7 GB
+        const double raysPerTask = g_fg ? 2.0 * pmi->gatherSamples * sampler->samplesPerPixel * (double)nPixels / nTasks : 0.0;
+        const int group = g_fg ? max(1, min(nTasks, (int)(4.0e6 / max(raysPerTask, 1.0)))) : nTasks;
+        std::vector<float> Lindir;
+        std::vector<pv_ray> grays;
+        for (int first = 0; first < nTasks; first += group) {
+            const int last = min(nTasks, first + group);
+            vector<Task *> renderTasks;
+            for (int i = first; i < last; ++i)
+                renderTasks.push_back(new SamplerRendererTask(scene, this, camera, reporter, sampler, sample, visualizeObjectIds,
+                                                              nTasks - 1 - i, nTasks));
+            EnqueueTasks(renderTasks);
+            WaitForAllTasks();
+            for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
+            if (!g_fg) continue;
+            // ---- the gather rays of this group: ONE pv_final_gather, then Ls += sum C * Lindir
+            size_t ng = 0;
+            for (int t = 0; t < nTasks; ++t) ng += fg.rays[t].size();
+            if (!ng) continue;
+            grays.resize(ng); Lindir.resize(ng * PV_NSPEC);
+            size_t k = 0;
+            for (int t = 0; t < nTasks; ++t) for (size_t i = 0; i < fg.rays[t].size(); ++i) grays[k++] = fg.rays[t][i].ray;
+            double tg = now_s();
+            int rc = pv_final_gather(g_pv.fg_ctx, grays.data(), ng, 4.f * pvi->stepSize, g_pv.seed, fg.next_index, Lindir.data(), NULL);
+            if (rc) Severe("pv_final_gather failed (%d): %s", rc, pv_last_error(g_pv.fg_ctx));
+            fg.gpu_seconds += now_s() - tg; fg.next_index += ng; fg.total_rays += ng;
+            k = 0;
+            for (int t = 0; t < nTasks; ++t) {
+                for (size_t i = 0; i < fg.rays[t].size(); ++i, ++k) {
+                    const PvGatherRay &g = fg.rays[t][i];
+                    Spectrum Li(0.f);
+                    memcpy(Li.c, &Lindir[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                    records[t][g.rec].Ls += g.C * Li;
+                }
+                std::vector<PvGatherRay>().swap(fg.rays[t]);
+            }
+        }
         reporter.Done();
+    }
+    if (g_li.calls) {
+        fprintf(stderr, "[pv] volume term of %llu secondary rays (specular bounces) in %llu batched pv_gather calls, %.3f s inside them\n", g_li.calls,
+                g_li.batches, g_li.seconds);
+        g_li.calls = g_li.batches = 0; g_li.seconds = 0;
+    }
+    if (g_fg) {
+        fprintf(stderr, "[pv] final gathering of primary hits on the GPU: %llu gather rays in %.3f s\n", (unsigned long long)fg.total_rays,
+                fg.gpu_seconds);
+        g_fg = NULL;
     }
     g_records = NULL;
     // ---- the volume term of the whole frame: one pv_gather

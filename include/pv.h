@@ -303,6 +303,10 @@ int pv_set_map_photons(pv_ctx *ctx, int map, const float *pos, const float *wi,
 int pv_radiance_photons(pv_ctx *ctx, uint32_t n_lookup, float max_dist2,
                         const uint64_t *path_counts, float *Lo, uint64_t capacity, uint64_t *n);
 
+/* Inject the radiance of the PV_MAP_RADIANCE photons (Lo[30n], n = their count) instead of computing it with
+ * pv_radiance_photons: a second context that serves final-gather rays while the first one keeps its grid on the volume map. */
+int pv_set_radiance_lo(pv_ctx *ctx, const float *Lo, uint64_t n);
+
 /* ---- building blocks of the SURFACE integrator's lookups (PhotonIntegrator, integrators/photonmap.cpp) -------
  * There is one lookup grid per context.  pv_build builds it over the volume photons; pv_select_map builds it over any
  * photon class (PV_MAP_*), after which pv_knn and the two calls below query that class.  pv_gather / pv_lphoton refuse to
