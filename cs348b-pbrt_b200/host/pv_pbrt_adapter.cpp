@@ -341,7 +341,7 @@ struct LiBatcher {
     LiBatcher() : calls(0), batches(0), seconds(0), in_flight(false) {}
 };
 LiBatcher g_li;
-const size_t kLiBatchMax = 64;
+const size_t kLiBatchMax = 4096;
 }  // namespace
 
 static int pv_li_batched(const pv_ray &r, uint64_t index, const pv_gather_params &prm0, float *L, float *T) {
@@ -508,12 +508,13 @@ void SamplerRenderer::Render(const Scene *scene) {
     Sample *sample = new Sample(sampler, surfaceIntegrator, volumeIntegrator, scene);
     camera->AutoFocus(this, scene, sample);
     // With the volume term on the GPU a render thread spends most of a specular bounce waiting for the device, and the batches
-    // of secondary rays are as large as there are threads waiting: run 4 threads per core unless the user chose a count
+    // of secondary rays are as large as there are threads waiting (one warp marches one ray, so the device wants thousands of
+    // rays at once and a call lasts as long as its longest ray): run 16 threads per core unless the user chose a count
     // (--ncores) or PV_THREADS says otherwise.  (The pool is created at the first EnqueueTasks, core/parallel.cpp:728-737.)
     if (g_pv.ready && scene->volumeRegion) {
         const char *th = getenv("PV_THREADS");
         if (th && atoi(th) > 0) PbrtOptions.nCores = atoi(th);
-        else if (PbrtOptions.nCores == 0) PbrtOptions.nCores = min(256, 4 * NumSystemCores());
+        else if (PbrtOptions.nCores == 0) PbrtOptions.nCores = min(1024, 16 * NumSystemCores());
     }
     int nPixels = camera->film->xResolution * camera->film->yResolution;
     int nTasks = max(32 * NumSystemCores(), nPixels / (16 * 16));
