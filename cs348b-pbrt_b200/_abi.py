@@ -10,7 +10,7 @@ PV_OK, PV_EINVAL, PV_ECUDA, PV_ENOMEM, PV_ESTATE, PV_ENOPHOTONS = 0, -1, -2, -3,
 LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2
 MEDIUM_NONE, MEDIUM_HOMOGENEOUS, MEDIUM_GRID, MEDIUM_RAINBOW, MEDIUM_EXPONENTIAL = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_GLASS = 0, 1
-GATHER_NO_DIRECT, GATHER_NO_INDIRECT = 1, 2
+GATHER_NO_DIRECT, GATHER_NO_INDIRECT, GATHER_RAY_PARALLEL, GATHER_STEP_PARALLEL = 1, 2, 4, 8
 
 Spec = C.c_float * NSPEC
 Mat16 = C.c_float * 16

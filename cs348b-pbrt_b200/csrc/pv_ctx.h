@@ -78,6 +78,7 @@ struct pv_ctx {
     // march records of the ray slice being gathered (pv_march.cu): RayHdr per ray, StepRec per march step
     void *march_hdr = nullptr; size_t march_hdr_bytes = 0;
     void *march_steps = nullptr; size_t march_steps_bytes = 0;
+    void *lii = nullptr; size_t lii_bytes = 0;     // per-step in-scattered radiance of the step-parallel gather (32 floats per step)
     unsigned long long *h_total = nullptr;         // mapped pinned word: step count of the slice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // around gather_kernel
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels

@@ -906,6 +906,9 @@ struct GatherArgs {
     float *L, *T;
     pv_gather_stats *stats;
     unsigned long long *counter;
+    // step-parallel ("latency") form: in-scattered radiance of every march step, 32 floats per StepRec, filled by
+    // gather_lii_kernel and consumed by gather_kernel<true>
+    float *lii; unsigned long long total_steps;
 };
 
 // wo of Light::Sample_L(p, ...) recomputed in the spectral pass (rainbow media only)
@@ -914,6 +917,12 @@ __device__ __forceinline__ v3 light_wo(const pv_light &l, v3 p) {
     return vnorm(V3(l.pos[0], l.pos[1], l.pos[2]) - p);
 }
 
+// PRE: the photon estimates L_ii of all steps were computed beforehand by gather_lii_kernel (one warp per STEP); this kernel
+// then only runs the recurrence.  The throughput form (PRE == false, one warp does everything for its ray) is what a frame
+// of camera rays uses; with a few hundred rays it leaves the GPU idle for as long as one warp needs for its longest ray, so
+// small batches (secondary rays of the drop-in) take the step-parallel form.  Same functions on the same inputs: the results
+// are bit-identical.
+template <bool PRE>
 #ifdef GW_MAXNREG
 __global__ void __maxnreg__(GW_MAXNREG) gather_kernel(GatherArgs a) {
 #else
@@ -987,7 +996,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
                         const float Ld = (I * expf(-(sig_t * __shfl_sync(PV_FULL, c_sh, i)))) * s_dfac;
                         L_d = rainbow ? rainbow_bin(Ld, rd, light_wo(lt, sp), lane) : Ld;
                     }
-                    if (do_lookup) {
+                    if (PRE) {
+                        if (do_lookup) L_ii = __ldg(a.lii + ((size_t)(recs - a.steps) + (size_t)(c0 + i)) * 32 + lane);
+                    } else if (do_lookup) {
                         // cell ranges of the NEXT step are requested now and consumed after this step's scan
                         Prefetch nx; nx.in_range = false; nx.issued = false;
                         const bool has_next = i + 1 < nthis;
@@ -1008,6 +1019,35 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
         if (bin) { a.L[ri * PV_NSPEC + lane] = Lv; a.T[ri * PV_NSPEC + lane] = Tr; }
     }
     flush_stats(a.stats, b, nrays, lane);
+}
+
+// One warp per march STEP of the slice: the photon lookup and the radiance estimate of that step (the part of gather_kernel's
+// loop body that does not depend on the other steps of the ray).
+__global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_lii_kernel(GatherArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBuf b = carve(smem, a.cap, warp, lane);
+    const DevMedium &med = a.sc->med;
+    const float sig_s = lane < PV_NSPEC ? med.sigma_s[lane] : 0.f;
+    const float r2 = a.maxdist * a.maxdist;
+    for (;;) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(a.counter + 3, 1ull);
+        g = __shfl_sync(PV_FULL, g, 0);
+        if (g >= a.total_steps) break;
+        const float4 *rp = reinterpret_cast<const float4 *>(a.steps + g);
+        const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+        const uint32_t ri = __float_as_uint(rb.w);
+        const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
+        const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
+        const v3 sp = ray_at(ro, rd, ra.x);
+        const uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, true, nullptr);
+        __syncwarp();
+        const float L_ii = warp_estimate(a.m, med, b, cnt, -rd, ra.w, sig_s, lane);
+        __syncwarp();
+        a.lii[g * 32 + lane] = L_ii;
+    }
+    flush_stats(a.stats, b, 0, lane);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1173,11 +1213,30 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     a.n = n; a.maxdist = prm->maxdist;
     a.nused = prm->nused; a.flags = flags; a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
     a.L = d_L; a.T = d_T; a.stats = ctx->d_stats; a.counter = ctx->d_counters;
+    a.lii = nullptr; a.total_steps = total;
     int blocks; size_t smem;
-    rc = launch_cfg(ctx, gather_kernel, a.cap, &blocks, &smem); if (rc) return rc;
-    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
+    // Which form?  Step-parallel when the rays are too few to fill the persistent grid (one warp per ray) and the per-step
+    // results fit comfortably; PV_GATHER_STEP_PARALLEL / PV_GATHER_RAY_PARALLEL in params->flags force one or the other.
+    const bool lookups = !(flags & PV_GATHER_NO_INDIRECT);
+    bool step_parallel = lookups && total > 0 && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
+    if (flags & PV_GATHER_STEP_PARALLEL) step_parallel = lookups && total > 0;
+    if (flags & PV_GATHER_RAY_PARALLEL) step_parallel = false;
+    if (step_parallel) {
+        rc = pv_ensure(ctx, &ctx->lii, &ctx->lii_bytes, (size_t)total * 32 * sizeof(float)); if (rc) return rc;
+        a.lii = (float *)ctx->lii;
+    }
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    gather_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+    if (step_parallel) {
+        rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
+        gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        rc = launch_cfg(ctx, gather_kernel<true>, a.cap, &blocks, &smem); if (rc) return rc;
+        gather_kernel<true><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+    } else {
+        rc = launch_cfg(ctx, gather_kernel<false>, a.cap, &blocks, &smem); if (rc) return rc;
+        gather_kernel<false><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+    }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     // device times of this slice (the next slice starts with a stream synchronisation anyway)

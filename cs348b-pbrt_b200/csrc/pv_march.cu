@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
                 }
             }
             out[0] = make_float4(c_t, c_tau, c_rr, c_dens);
-            out[1] = make_float4(c_sh, c_dfac, __int_as_float(c_ln), 0.f);
+            out[1] = make_float4(c_sh, c_dfac, __int_as_float(c_ln), __uint_as_float((uint32_t)ri));    // pad = the ray of the step (slice-relative)
         }
     }
     ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);

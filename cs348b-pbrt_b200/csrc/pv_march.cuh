@@ -24,6 +24,6 @@ struct StepRec {
     float sh;     // optical-depth scalar of the shadow ray
     float dfac;   // falloff / dist^2 * phase * nLights (0: unlit or occluded): L_d[b] = I[b] * exp(-sigma_t[b]*sh) * dfac
     int ln;       // light chosen for the step
-    uint32_t pad;
+    uint32_t pad; // index of the step's ray within the slice (the step-parallel gather finds its ray through it)
 };
 static_assert(sizeof(RayHdr) == 32 && sizeof(StepRec) == 32, "march records are two 128-bit words");

@@ -140,6 +140,11 @@ typedef struct pv_gather_params {
 } pv_gather_params;
 #define PV_GATHER_NO_DIRECT   1u   /* skip the single-scattering term           */
 #define PV_GATHER_NO_INDIRECT 2u   /* skip LPhoton                               */
+/* Scheduling of the lookups (results are bit-identical either way; default: chosen from the number of rays): one warp per
+ * RAY (throughput form, frames of camera rays) or one warp per march STEP followed by a recurrence pass (latency form, the
+ * small batches of secondary rays: a call then no longer lasts as long as one warp needs for the longest ray).             */
+#define PV_GATHER_RAY_PARALLEL  4u
+#define PV_GATHER_STEP_PARALLEL 8u
 
 /* PhotonShooter params (core/photonshooter.cpp:529-548), volume branch. */
 typedef struct pv_shoot_params {

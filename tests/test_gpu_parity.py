@@ -568,3 +568,25 @@ def test_final_gather_rays_vs_oracle(golden, pv_factory, pkg, name):
     assert m.any()
     assert relerr(L, oL)[m].max() < 1e-4
     assert np.array_equal((L == 0)[same], (oL == 0)[same])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell_homog", "cornell_grid32", "prism_small"])
+def test_gather_step_parallel_equals_ray_parallel(golden, pv_factory, pkg, name):
+    """The two schedules of the gather -- one warp per ray (frames) and one warp per march step + recurrence pass (small batches
+    of secondary rays) -- run the same functions on the same inputs: L and T must agree bit for bit."""
+    A = pkg._abi
+    g, scene = golden(name)
+    nused, maxdist, stepsize = int(g["params"][0]), float(g["params"][1]), float(g["params"][2])
+    pv = pv_factory(stepsize=stepsize, nused=nused, maxdist=maxdist, seed=11)
+    pv.set_scene(scene)
+    pv.set_photons(g["shot_pos"], g["shot_wi"], g["shot_alpha"]); pv.build()
+    rays = g["li_rays"]
+    L0, T0 = pv.Li(rays, ray_index_base=5, flags=A.GATHER_RAY_PARALLEL)
+    L1, T1 = pv.Li(rays, ray_index_base=5, flags=A.GATHER_STEP_PARALLEL)
+    assert (L0 > 0).any()
+    assert np.array_equal(L0.view(np.uint32), L1.view(np.uint32)) and np.array_equal(T0.view(np.uint32), T1.view(np.uint32))
+    L2, T2 = pv.Li(rays, ray_index_base=5)                    # the default picks a schedule from the ray count
+    assert np.array_equal(L0.view(np.uint32), L2.view(np.uint32)) and np.array_equal(T0.view(np.uint32), T2.view(np.uint32))
+    L3, T3 = pv.Li(rays[:1], ray_index_base=5, flags=A.GATHER_STEP_PARALLEL)          # one ray
+    assert np.array_equal(L0[:1].view(np.uint32), L3.view(np.uint32))
