@@ -30,15 +30,15 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_sizes_match_the_c_compiler(pkg, tmp_path):
     A = pkg._abi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "pv.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "pv.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(pv_bvh_node),sizeof(pv_ray),sizeof(pv_light),sizeof(pv_medium),sizeof(pv_material),'
                    'sizeof(pv_scene_desc),sizeof(pv_gather_params),sizeof(pv_shoot_params),sizeof(pv_shoot_stats),'
-                   'sizeof(pv_gather_stats),sizeof(pv_maps_params),sizeof(pv_maps_stats));return 0;}\n')
+                   'sizeof(pv_gather_stats),sizeof(pv_maps_params),sizeof(pv_maps_stats),sizeof(pv_sphere));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mine = [C.sizeof(t) for t in (A.BvhNode, A.Ray, A.Light, A.Medium, A.Material, A.SceneDesc, A.GatherParams,
-                                  A.ShootParams, A.ShootStats, A.GatherStats, A.MapsParams, A.MapsStats)]
+                                  A.ShootParams, A.ShootStats, A.GatherStats, A.MapsParams, A.MapsStats, A.Sphere)]
     assert sizes == mine
     assert sizes[0] == 32 and sizes[1] == 40
 
