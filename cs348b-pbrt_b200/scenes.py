@@ -216,6 +216,36 @@ def cornell_pbrt(volume_text, nphotons, xres=64, yres=64, stepsize=0.05, nused=5
                                    stepsize=stepsize, nused=nused, maxdist=maxdist, nphotons=nphotons, volume=volume_text)
 
 
+# the Cornell box under the reference's other two volume integrators ("single": integrators/single.cpp,
+# "emission": integrators/emission.cpp).  No photon maps: the surface integrator is the plain direct-lighting one.
+VOLINT_MEDIA = {
+    # emitting homogeneous medium, point + spot light (the light choice of single.cpp:117-119 matters)
+    "volint_homog": ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s" [.15 .2 .25] "color Le" [.4 .2 .1] "float g" [0.4]\n'
+                     '  "point p0" [-1 -1 -1] "point p1" [1 1 1]', True, 0.05),
+    # optically thick homogeneous medium: the cumulative transmittance drops below 1e-3 and the Russian roulette runs
+    "volint_dense": ('Volume "homogeneous" "color sigma_a" [2 2 2] "color sigma_s" [3 2.5 2] "color Le" [.05 .1 .2] "float g" [0]\n'
+                     '  "point p0" [-1 -1 -1] "point p1" [1 1 1]', False, 0.05),
+}
+VOLINT_SPOT = 'LightSource "spot" "point from" [0.6 0.7 -0.6] "point to" [-0.2 -0.5 0.2] "color I" [30 25 20] "float coneangle" [40] "float conedeltaangle" [10]'
+
+
+def volint_pbrt(kind, volume_text, stepsize=0.05, second_light=False, xres=64, yres=64, outfile="volint.pfm"):
+    """Cornell box rendered with VolumeIntegrator `kind` ("single" | "emission")."""
+    text = cornell_pbrt(volume_text, 0, xres=xres, yres=yres, stepsize=stepsize, outfile=outfile,
+                        title="synthetic Cornell box, VolumeIntegrator \"%s\"" % kind)
+    head, rest = text.split('SurfaceIntegrator "photonmap"', 1)
+    rest = rest.split("LookAt", 1)[1]
+    text = (head + 'SurfaceIntegrator "directlighting"\nVolumeIntegrator "%s" "float stepsize" [%g]\nLookAt' % (kind, stepsize) + rest)
+    if second_light:
+        text = text.replace('Material "matte" "color Kd" [.6 .6 .6]', VOLINT_SPOT + '\nMaterial "matte" "color Kd" [.6 .6 .6]', 1)
+    return text
+
+
+def volint_grid_volume(n=32):
+    """Emitting, forward-scattering density grid (the config-3 blobs at n^3)."""
+    return grid_volume_text(n, blob_density(n)).replace('"float g"', '"color Le" [.3 .3 .1] "float g"')
+
+
 def cornell_surf_pbrt(nphotons=3000, caustic=1500, indirect=4000, finalgather=True, fgsamples=8, surf_nused=50, surf_maxdist=0.25,
                       xres=64, yres=64, stepsize=0.05, nused=50, maxdist=0.25, shoot_step=0.05, vn=0.0, volume_text=None,
                       outfile="cornell_surf.pfm"):

@@ -964,6 +964,120 @@ int pvo_gather(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi, co
     return 0;
 }
 
+/* ---------------------------------------------------------------- the other two volume integrators
+ * SingleScatteringIntegrator::Li  integrators/single.cpp:66-138
+ * EmissionIntegrator::Li          integrators/emission.cpp:63-106
+ * Both march like PhotonVolumeIntegrator::Li but keep a CUMULATIVE transmittance (Tr *= Exp(-stepTau), single.cpp:100,
+ * emission.cpp:89), test the Russian roulette on it, add Tr * Lve(p) per step and -- single only -- the light's
+ * single-scattered radiance Tr * ss * p(p, w, -wo) * Ld * nLights / pdf (single.cpp:128-129); the sum is scaled by the
+ * step length at the end.  MT mode replays the reference's draw order (three LDShuffleScrambled tables first for
+ * "single", none for "emission"; then per step: tau offset, roulette if taken, shadow-ray tau offset), Philox mode uses
+ * the streams of the CUDA path (the same counters as pvo_gather). */
+static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_index, const pv_gather_params *prm, int kind,
+                    int rng_mode, uint32_t mt_seed_v, float *Lout, float *Tout, pv_gather_stats *st) {
+    const pv_medium *vr = sc->medium;
+    spec Tr = s_const(1.f), Lv = s_const(0.f);
+    v3 ro = V(ray->o[0], ray->o[1], ray->o[2]), rd = V(ray->d[0], ray->d[1], ray->d[2]);
+    float t0, t1;
+    if (st) st->rays++;
+    if (!vr || vr->type == PV_MEDIUM_NONE || !med_intersectp(vr, ro, rd, ray->mint, ray->maxt, &t0, &t1) || (t1 - t0) == 0.f) {
+        memcpy(Tout, Tr.c, sizeof(Tr.c)); memcpy(Lout, Lv.c, sizeof(Lv.c));
+        return;
+    }
+    const int single = kind == PVO_VLI_SINGLE;
+    float stepSize = prm->stepsize;
+    int nSamples = (int)ceilf((t1 - t0) / stepSize);
+    float step = (t1 - t0) / nSamples;
+    v3 p = ray_at(ro, rd, t0), pPrev;
+    v3 w = vneg(rd);
+    t0 += ray->u_scatter * step;
+    int nLights = (int)sc->n_lights;
+
+    li_rng rg; rg.mode = rng_mode;
+    float *lightNum = NULL;
+    uint32_t scramble = 0, permkey = 0;
+    if (rng_mode == PVO_RNG_MT) {
+        mt_seed(&rg.mt, mt_seed_v);
+        if (single) {                                           /* single.cpp:85-90, montecarlo.h:304-323 */
+            lightNum = (float *)malloc(sizeof(float) * (size_t)nSamples * 4);
+            float *lightComp = lightNum + nSamples, *lightPos = lightNum + 2 * (size_t)nSamples;
+            uint32_t s1 = mt_next(&rg.mt);
+            for (int i = 0; i < nSamples; ++i) lightNum[i] = pv_van_der_corput((uint32_t)i, s1);
+            for (int i = 0; i < nSamples; ++i) mt_shuffle_f(lightNum + i, 1, 1, &rg.mt);
+            mt_shuffle_f(lightNum, (uint32_t)nSamples, 1, &rg.mt);
+            uint32_t s2 = mt_next(&rg.mt);
+            for (int i = 0; i < nSamples; ++i) lightComp[i] = pv_van_der_corput((uint32_t)i, s2);
+            for (int i = 0; i < nSamples; ++i) mt_shuffle_f(lightComp + i, 1, 1, &rg.mt);
+            mt_shuffle_f(lightComp, (uint32_t)nSamples, 1, &rg.mt);
+            uint32_t s3a = mt_next(&rg.mt), s3b = mt_next(&rg.mt);
+            for (int i = 0; i < nSamples; ++i) { lightPos[2 * i] = pv_van_der_corput((uint32_t)i, s3a); lightPos[2 * i + 1] = sobol2((uint32_t)i, s3b); }
+            for (int i = 0; i < nSamples; ++i) mt_shuffle_f(lightPos + 2 * i, 1, 2, &rg.mt);
+            mt_shuffle_f(lightPos, (uint32_t)nSamples, 2, &rg.mt);
+        }
+    } else {
+        uint32_t wds[4];
+        rg.k0 = (uint32_t)prm->seed; rg.k1 = (uint32_t)(prm->seed >> 32);
+        rg.r0 = (uint32_t)ray_index; rg.r1 = (uint32_t)(ray_index >> 32);
+        pv_philox4x32_10(rg.r0, rg.r1, 0, PV_RNG_RAY, rg.k0, rg.k1, wds);
+        scramble = wds[0]; permkey = wds[1];
+    }
+    med_counters mc = {0};
+    for (int i = 0; i < nSamples; ++i, t0 += step) {
+        uint32_t wds[4] = {0, 0, 0, 0};
+        if (rng_mode == PVO_RNG_PHILOX) pv_philox4x32_10(rg.r0, rg.r1, (uint32_t)i, PV_RNG_STEP, rg.k0, rg.k1, wds);
+        pPrev = p;
+        p = ray_at(ro, rd, t0);
+        float u_tau = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[0]);
+        spec stepTau = med_tau(vr, pPrev, vsub(p, pPrev), 0.f, 1.f, .5f * stepSize, u_tau, &mc);
+        for (int b = 0; b < NS; ++b) Tr.c[b] *= expf(-stepTau.c[b]);
+        if (s_y(sc, &Tr) < 1e-3) {
+            const float continueProb = .5f;
+            float u_rr = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[1]);
+            if (u_rr > continueProb) { Tr = s_const(0.f); break; }
+            for (int b = 0; b < NS; ++b) Tr.c[b] /= continueProb;
+        }
+        spec lve = med_sigma(vr, vr->le, p, &mc);
+        for (int b = 0; b < NS; ++b) Lv.c[b] += Tr.c[b] * lve.c[b];
+        if (!single) continue;
+        spec ss = med_sigma(vr, vr->sigma_s, p, &mc);
+        if (!s_black(&ss) && nLights > 0) {
+            float u_l = rng_mode == PVO_RNG_MT ? lightNum[i]
+                        : pv_van_der_corput(pv_permute((uint32_t)i, (uint32_t)nSamples, permkey), scramble);
+            int ln = (int)floorf(u_l * nLights);
+            if (ln > nLights - 1) ln = nLights - 1;
+            const pv_light *light = &sc->lights[ln];
+            float pdf; visray vis; v3 wo;
+            spec L = light_sample_L_point(light, p, &wo, &pdf, &vis);
+            if (!s_black(&L) && pdf > 0.f) {
+                if (st) st->shadow_rays++;
+                if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
+                    /* vis.Transmittance -> SingleScatteringIntegrator::Transmittance(sample = NULL): step 4 * stepSize (single.cpp:55-58) */
+                    float u_sh = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[2]);
+                    spec tau = med_tau(vr, vis.o, vis.d, vis.mint, vis.maxt, 4.f * stepSize, u_sh, &mc);
+                    float ph = med_p(vr, p, w, vneg(wo));
+                    for (int b = 0; b < NS; ++b) {
+                        float Ld = L.c[b] * expf(-tau.c[b]);
+                        Lv.c[b] += ((((Tr.c[b] * ss.c[b]) * ph) * Ld) * (float)nLights) / pdf;
+                    }
+                }
+            }
+        }
+    }
+    if (st) st->density_samples += mc.density_samples;
+    free(lightNum);
+    for (int b = 0; b < NS; ++b) Lv.c[b] *= step;
+    memcpy(Tout, Tr.c, sizeof(Tr.c)); memcpy(Lout, Lv.c, sizeof(Lv.c));
+}
+int pvo_volume_li(const pv_scene_desc *sc, const pv_ray *rays, uint64_t n, const pv_gather_params *prm, int kind, int rng_mode,
+                  uint32_t mt_seed_v, float *L, float *T, pv_gather_stats *stats) {
+    if (kind != PVO_VLI_SINGLE && kind != PVO_VLI_EMISSION) return -1;
+    pv_gather_stats st; memset(&st, 0, sizeof(st));
+    for (uint64_t i = 0; i < n; ++i)
+        vli_one(sc, &rays[i], prm->ray_index_base + i, prm, kind, rng_mode, mt_seed_v + (uint32_t)i, L + NS * i, T + NS * i, &st);
+    if (stats) *stats = st;
+    return 0;
+}
+
 /* ---------------------------------------------------------------- photon shooting (core/photonshooter.cpp:47-357) */
 typedef struct {
     uint64_t n, cap;

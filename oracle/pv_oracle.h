@@ -64,6 +64,15 @@ int pvo_gather(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi,
                const pv_gather_params *prm, int rng_mode, uint32_t mt_seed,
                int nthreads, float *L, float *T, pv_gather_stats *stats);
 
+/* The reference's other two volume integrators: SingleScatteringIntegrator::Li
+ * (integrators/single.cpp:66-138) and EmissionIntegrator::Li (integrators/emission.cpp:63-106).  Only
+ * prm->stepsize / seed / ray_index_base are read.  PVO_RNG_MT seeds RNG(mt_seed + i) for ray i like
+ * oracle/ref_harness.cpp --vli. */
+#define PVO_VLI_SINGLE   0
+#define PVO_VLI_EMISSION 1
+int pvo_volume_li(const pv_scene_desc *sc, const pv_ray *rays, uint64_t n, const pv_gather_params *prm, int kind,
+                  int rng_mode, uint32_t mt_seed, float *L, float *T, pv_gather_stats *stats);
+
 /* core/photonshooter.cpp:47-357, volume branch (caustic/indirect maps off).
  * PVO_RNG_MT: one task (taskNum 0), the reference's sequential stream.
  * PVO_RNG_PHILOX: per-path streams; blocks may be spread over nthreads. */

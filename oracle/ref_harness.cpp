@@ -9,6 +9,8 @@
 //                                                 (integrators/photonvolume.cpp)
 //   * Scene::Intersect / IntersectP               (accelerators/bvh.cpp:585-685)
 //   * PhotonShootingTask::Run                     (core/photonshooter.cpp:232-357)
+//   * SingleScatteringIntegrator::Li / EmissionIntegrator::Li
+//                                                 (integrators/single.cpp:66-138, emission.cpp:63-106)
 //   * the flattened scene the C ABI consumes      
 //
 // It reaches private members with `#define private public` and reaches the
@@ -390,6 +392,32 @@ static void li(SamplerRenderer *ren, const Scene *scene, const std::string &rfn,
     fclose(o);
 }
 
+// Li of whichever volume integrator the scene file names ("single", "emission" or "photonvolume"), one RNG(seed + i) per ray,
+// the scatter sample taken from the ray record: the golden of SURVEY.md 8(f)-4's SingleScatteringIntegrator / EmissionIntegrator
+static void vli(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
+    std::vector<pv_ray> rays = read_rays(rfn);
+    int scat = -1, tau = -1;
+    Sample *sample = new Sample(ren->sampler, ren->surfaceIntegrator, ren->volumeIntegrator, scene);
+    if (SingleScatteringIntegrator *s = dynamic_cast<SingleScatteringIntegrator *>(ren->volumeIntegrator)) { scat = s->scatterSampleOffset; tau = s->tauSampleOffset; }
+    else if (EmissionIntegrator *e = dynamic_cast<EmissionIntegrator *>(ren->volumeIntegrator)) { scat = e->scatterSampleOffset; tau = e->tauSampleOffset; }
+    else if (PhotonVolumeIntegrator *v = dynamic_cast<PhotonVolumeIntegrator *>(ren->volumeIntegrator)) { scat = v->scatterSampleOffset; tau = v->tauSampleOffset; }
+    else { fprintf(stderr, "--vli: unknown volume integrator\n"); exit(4); }
+    FILE *o = xopen(ofn, "wb");
+    write_header(o, "PVLI0001", rays.size());
+    MemoryArena arena;
+    for (size_t i = 0; i < rays.size(); ++i) {
+        RayDifferential r(to_ray(rays[i]));
+        RNG rng(seed + (uint32_t)i);
+        sample->oneD[scat][0] = rays[i].u_scatter;
+        sample->oneD[tau][0] = 0.5f;
+        Spectrum T(1.f);
+        Spectrum L = ren->volumeIntegrator->Li(scene, ren, r, sample, rng, &T, arena);
+        wr(o, L.c, 30); wr(o, T.c, 30);
+        arena.FreeAll();
+    }
+    fclose(o);
+}
+
 static void transmittance(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
     // sample == NULL branch of photonvolume.cpp:24-27: step = 4*stepSize, offset = rng.RandomFloat().
     // The offset used is written next to T so the caller can replay it.
@@ -489,6 +517,7 @@ void pbrtWorldEnd() {
         else if (op == "--lphoton") { lphoton(vi, scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--intersect") { intersect(scene, ARG(1), ARG(2)); i += 2; }
         else if (op == "--li") { li(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
+        else if (op == "--vli") { vli(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
         else if (op == "--li-parallel") { li_parallel(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }
         else if (op == "--grid-file") { swap_grid(scene, atoi(ARG(1).c_str()), ARG(2)); i += 2; }
         else if (op == "--transmittance") { transmittance(sr, scene, ARG(1), (uint32_t)strtoul(ARG(2).c_str(), NULL, 0), ARG(3)); i += 3; }

@@ -178,6 +178,7 @@ def main():
         surface_goldens(tmp)
         sphere_goldens(tmp)
         exponential_goldens(tmp)
+        volint_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -235,6 +236,36 @@ def exponential_goldens(tmp):
     f = os.path.join(tmp, "cornell_exp.pbrt")
     open(f, "w").write(scenes.cornell_pbrt(scenes.EXP_VOLUME, 3000, stepsize=0.05, nused=50, maxdist=0.25, shoot_step=0.05))
     golden_for_scene(tmp, "cornell_exp", f, 50, 0.25, 0.05, 64, 64, [(50, 0.25 ** 2)], wanted=3000)
+
+
+def volint_goldens(tmp):
+    """SURVEY 8(f)-4: SingleScatteringIntegrator::Li and EmissionIntegrator::Li of the unmodified reference (ref_harness --vli)
+    on three media; one RNG(seed + i) per ray so the oracle's MT mode can replay every draw."""
+    out = {}
+    cases = dict(scenes.VOLINT_MEDIA)
+    cases["volint_grid"] = (scenes.volint_grid_volume(32), False, 0.0625)
+    rays = scenes.camera_rays(64, 64)
+    rng = np.random.default_rng(19)
+    rays = rays[np.sort(rng.choice(len(rays), size=160, replace=False))]
+    rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
+    rays["u_scatter"][:8] = np.float32(0.5)
+    rays["maxt"][8:24] = rng.uniform(2.6, 4.2, size=16).astype(np.float32)     # rays that end inside the medium
+    out["rays"] = rays
+    rf = os.path.join(tmp, "volint_rays.bin"); sceneio.write_rays(rf, rays)
+    for name, (vol, second_light, stepsize) in cases.items():
+        for kind in ("single", "emission"):
+            f = os.path.join(tmp, "%s_%s.pbrt" % (name, kind))
+            open(f, "w").write(scenes.volint_pbrt(kind, vol, stepsize=stepsize, second_light=second_light))
+            ops = ["--vli", rf, 4000, os.path.join(tmp, "vli.bin")]
+            if kind == "single":
+                ops = ["--export-scene", os.path.join(HERE, name + ".scn")] + ops
+            run(f, *ops)
+            li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
+            out["%s_%s_L" % (name, kind)], out["%s_%s_T" % (name, kind)] = li[:, 0], li[:, 1]
+            print("  %s/%s: mean L %.4g, min T.y %.3g" % (name, kind, li[:, 0].mean(), li[:, 1].mean(axis=1).min()))
+        out[name + "_stepsize"] = np.array([stepsize], np.float32)
+    out["mt_seed"] = np.array([4000], np.uint32)
+    np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
 
 
 def read_radiance(fn):
@@ -309,6 +340,10 @@ if __name__ == "__main__":
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             exponential_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "volint":           # only the single / emission integrator goldens
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            volint_goldens(tmp_)
     elif len(sys.argv) > 1 and sys.argv[1] == "sphere":           # only the sphere-scene goldens
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:

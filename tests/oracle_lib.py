@@ -115,6 +115,22 @@ def gather(scene, tree, wi, alpha, rays, stepsize, nused, maxdist, seed=0, ray_i
     return L, T, st
 
 
+SINGLE, EMISSION = 0, 1
+
+
+def volume_li(scene, rays, stepsize, kind, seed=0, ray_index_base=0, rng_mode=PHILOX, mt_seed=0):
+    """SingleScatteringIntegrator::Li / EmissionIntegrator::Li (integrators/single.cpp:66-138, emission.cpp:63-106)."""
+    n = len(rays); rays = np.ascontiguousarray(rays)
+    L = np.zeros((n, A.NSPEC), np.float32); T = np.zeros((n, A.NSPEC), np.float32)
+    prm = A.GatherParams(stepsize, 0, 0.0, seed, ray_index_base, 0)
+    st = A.GatherStats()
+    d = scene.desc()
+    rc = lib().pvo_volume_li(C.byref(d), _p(rays), C.c_uint64(n), C.byref(prm), C.c_int(kind), C.c_int(rng_mode), C.c_uint32(mt_seed),
+                             _p(L), _p(T), C.byref(st))
+    assert rc == 0
+    return L, T, st
+
+
 def shoot(scene, n_wanted, stepsize, integrator_stepsize, max_photon_depth=5, seed=0, rng_mode=PHILOX, nthreads=1,
           max_paths=0):
     prm = A.ShootParams(stepsize, integrator_stepsize, max_photon_depth, seed, 0, 1, max_paths, 0.0)

@@ -203,3 +203,29 @@ def test_surface_integrator_lookups_match_reference(golden, name):
     for q in diff:
         assert np.array_equal(g["rad_pos"][idx[q]], g["rad_pos"][g["radn_idx"][q]])            # coincident radiance photons
     assert len(diff) <= 0.05 * len(idx)
+
+
+VOLINT = ["volint_homog", "volint_dense", "volint_grid"]
+
+
+@pytest.mark.parametrize("kind", ["single", "emission"])
+@pytest.mark.parametrize("name", VOLINT)
+def test_single_and_emission_li_match_reference_with_mt_stream(golden, pkg, name, kind):
+    """SURVEY 8(f)-4: SingleScatteringIntegrator::Li / EmissionIntegrator::Li replayed with the reference's own MT19937 draw
+    order (RNG(4000 + i) per ray, as ref_harness --vli): emitting media, two lights (light choice through the shuffled
+    low-discrepancy table), rays that end inside the medium, and a medium thick enough for the Russian roulette to run."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    scene = pkg.sceneio.read_scene(os.path.join(GOLDEN, name + ".scn"))
+    L, T, st = O.volume_li(scene, g["rays"], float(g[name + "_stepsize"][0]), O.SINGLE if kind == "single" else O.EMISSION,
+                           rng_mode=O.MT, mt_seed=int(g["mt_seed"][0]))
+    refL, refT = g["%s_%s_L" % (name, kind)], g["%s_%s_T" % (name, kind)]
+    assert (refL > 0).any() and np.array_equal(T == 0, refT == 0)
+    if name == "volint_dense":
+        assert (refT == 0).all(axis=1).any()              # some march was ended by the roulette ...
+        assert ((refT > 0) & (refT < 1e-2)).any()         # ... and some survived it
+    assert relerr(T, refT)[refT > 0].max() < 1e-5
+    m = refL > 0
+    assert np.array_equal(L > 0, m) and relerr(L, refL)[m].max() < 1e-5
+    assert (st.shadow_rays > 0) == (kind == "single")
