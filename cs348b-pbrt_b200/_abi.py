@@ -100,6 +100,8 @@ class MapsStats(C.Structure):
 ALLREDUCE_U32_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_void_p)
 
 
+VOLINT_SINGLE, VOLINT_EMISSION = 0, 1        # PV_VOLINT_*
+
 # every symbol include/pv.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_set_scene", "pv_set_photons",
@@ -107,4 +109,5 @@ EXPORTS = [
     "pv_intersect", "pv_occluded", "pv_transmittance", "pv_gather", "pv_gather_dev", "pv_lphoton",
     "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
     "pv_shoot_maps", "pv_shoot_maps_ranks", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons", "pv_select_map", "pv_surface_lphoton", "pv_radiance_nearest", "pv_final_gather", "pv_set_radiance_lo",
+    "pv_volume_li", "pv_volume_li_dev",
 ]

@@ -419,6 +419,30 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
     ctx->last_ms = ms; ctx->last_march_ms = march_ms;
     return PV_OK;
 }
+int pv_volume_li_dev(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
+    LOCK(ctx);
+    if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_volume_li_dev: null pointer"; return PV_EINVAL; }
+    int rc = pvi_volume_li(ctx, integrator, rays, n, params, L, T); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
+    LOCK(ctx);
+    if (!params || (n && (!rays || !L || !T))) { ctx->err = "pv_volume_li: null pointer"; return PV_EINVAL; }
+    const size_t rb = n * sizeof(pv_ray), sb = n * PV_NSPEC * sizeof(float);
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, rb); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 2 * sb); if (rc) return rc;
+    pv_ray *d_rays = (pv_ray *)ctx->io;
+    float *d_L = (float *)ctx->io2, *d_T = d_L + n * PV_NSPEC;
+    if (n) PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pvi_volume_li(ctx, integrator, d_rays, n, params, d_L, d_T); if (rc) return rc;
+    if (n) {
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, d_L, sb, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, d_T, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
 int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset) {
     LOCK(ctx);
     if (!out) { ctx->err = "pv_gather_stats_get: null out"; return PV_EINVAL; }

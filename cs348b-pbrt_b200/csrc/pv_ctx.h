@@ -113,6 +113,8 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
 int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, uint32_t *d_idx, float *d_d2, uint32_t *d_nfound);
 int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, uint32_t nused, float maxdist, float *d_L);
 int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T);
+// pv_volint.cu
+int pvi_volume_li(pv_ctx *ctx, int integrator, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T);
 // pv_trace.cu
 int pvi_intersect(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint32_t *d_prim, float *d_t);
 int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit);

@@ -236,6 +236,20 @@ int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset);
 int pv_last_kernel_ms(pv_ctx *ctx, float *ms);
 int pv_last_march_ms(pv_ctx *ctx, float *ms);
 
+/* ---- SingleScatteringIntegrator::Li (integrators/single.cpp:66-138) and
+ *      EmissionIntegrator::Li (integrators/emission.cpp:63-106) -------------
+ * The reference's other two VolumeIntegrator plugins: the
+ * same ray march with a cumulative transmittance, emission, and -- "single"
+ * -- one light's single-scattered radiance per step.  No photon map is read.
+ * Of params only stepsize, seed and ray_index_base are used.  L[30n], T[30n],
+ * host pointers (pv_volume_li) or device pointers (pv_volume_li_dev).         */
+#define PV_VOLINT_SINGLE   0
+#define PV_VOLINT_EMISSION 1
+int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n,
+                 const pv_gather_params *params, float *L, float *T);
+int pv_volume_li_dev(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n,
+                     const pv_gather_params *params, float *L, float *T);
+
 /* ---- PhotonShooter::Preprocess, volume branch (photonshooter.cpp:457-526) */
 int pv_shoot(pv_ctx *ctx, uint64_t n_volume_wanted,
              const pv_shoot_params *params, pv_shoot_stats *stats);
