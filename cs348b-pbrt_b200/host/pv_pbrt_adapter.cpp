@@ -64,6 +64,8 @@
 #include "materials/matte.h"
 #include "materials/glass.h"
 #include "integrators/photonvolume.h"
+#include "integrators/single.h"
+#include "integrators/emission.h"
 #include "integrators/photonmap.h"
 #include "renderers/samplerrenderer.h"
 #undef private
@@ -86,11 +88,12 @@ struct PvBridge {
     uint64_t seed;
     uint64_t n_indirect;
     bool ready;
+    int volint;                   // which Li the device runs: -1 photonvolume (pv_gather), else PV_VOLINT_* (pv_volume_li)
     // final gathering runs on a context of its own (scene + radiance photons + their grid): rays spawned by specular bounces
     // call the volume integrator (pv_gather on `ctx`, grid on the volume map) while primary hits are still being shaded
     pv_ctx *fg_ctx;
     std::vector<float> rad_pos, rad_nrm, rad_Lo;
-    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), fg_ctx(NULL) {}
+    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), volint(-1), fg_ctx(NULL) {}
 };
 PvBridge g_pv;
 
@@ -98,6 +101,24 @@ double now_s() { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 
 
 void pv_fail(const char *what, int rc) {
     Severe("%s failed (%d): %s", what, rc, pv_last_error(g_pv.ctx));
+}
+
+// The three VolumeIntegrator plugins whose Li runs on the device, seen through one pair of glasses.
+struct PvVolInt { int kind; float stepSize; int nUsed; float maxDist; int scatterSampleOffset; };
+bool pv_volint_of(const VolumeIntegrator *v, PvVolInt *o) {
+    if (const PhotonVolumeIntegrator *p = dynamic_cast<const PhotonVolumeIntegrator *>(v)) {
+        o->kind = -1; o->stepSize = p->stepSize; o->nUsed = p->nUsed; o->maxDist = p->maxDist; o->scatterSampleOffset = p->scatterSampleOffset;
+    } else if (const SingleScatteringIntegrator *s1 = dynamic_cast<const SingleScatteringIntegrator *>(v)) {
+        o->kind = PV_VOLINT_SINGLE; o->stepSize = s1->stepSize; o->nUsed = 0; o->maxDist = 0.f; o->scatterSampleOffset = s1->scatterSampleOffset;
+    } else if (const EmissionIntegrator *e = dynamic_cast<const EmissionIntegrator *>(v)) {
+        o->kind = PV_VOLINT_EMISSION; o->stepSize = e->stepSize; o->nUsed = 0; o->maxDist = 0.f; o->scatterSampleOffset = e->scatterSampleOffset;
+    } else return false;
+    return true;
+}
+// Li of a batch of rays with whichever of the three the scene file chose
+int pv_volume_term(const pv_ray *rays, size_t n, const pv_gather_params *prm, float *L, float *T) {
+    if (g_pv.volint < 0) return pv_gather(g_pv.ctx, rays, n, prm, L, T);
+    return pv_volume_li(g_pv.ctx, g_pv.volint, rays, n, prm, L, T);
 }
 
 struct PvRecord {                 // one camera sample waiting for its volume term
@@ -200,7 +221,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
     }
     int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
     if (rc) pv_fail("pv_set_scene", rc);
-    g_pv.stepsize = vi->stepSize; g_pv.maxdist = vi->maxDist; g_pv.nused = (uint32_t)vi->nUsed;
+    g_pv.stepsize = vi->stepSize; g_pv.maxdist = vi->maxDist; g_pv.nused = (uint32_t)vi->nUsed; g_pv.volint = -1;
     const char *seed = getenv("PV_SEED");
     g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
     pv_shoot_params prm; memset(&prm, 0, sizeof(prm));
@@ -379,7 +400,7 @@ static int pv_li_batched(const pv_ray &r, uint64_t index, const pv_gather_params
         // the ABI offers per CALL, so the batch goes down as ONE call whose base is the leader's index; ray i uses base + i
         pv_gather_params prm = prm0; prm.ray_index_base = b->index[0];
         const double t0 = now_s();
-        int rc = pv_gather(g_pv.ctx, b->rays.data(), n, &prm, b->L.data(), b->T.data());
+        int rc = pv_volume_term(b->rays.data(), n, &prm, b->L.data(), b->T.data());
         const double dt = now_s() - t0;
         lock.lock();
         g_li.seconds += dt;
@@ -394,20 +415,24 @@ static int pv_li_batched(const pv_ray &r, uint64_t index, const pv_gather_params
 }
 
 // Single-ray form (kept so every caller of the VolumeIntegrator interface still works); the renderer below batches.
-Spectrum PhotonVolumeIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
-                                    RNG &rng, Spectrum *T, MemoryArena &arena) const {
+static Spectrum pv_li_one(const char *who, const Scene *scene, const RayDifferential &ray, float u_scatter, float stepSize, int nUsed,
+                          float maxDist, RNG &rng, Spectrum *T) {
     if (!scene->volumeRegion) { *T = 1.f; return 0.f; }
-    if (!g_pv.ready) Severe("PhotonVolumeIntegrator::Li: the GPU photon-volume context was not set up (no CUDA device?)");
-    pv_ray r; pv_fill_ray(ray, sample->oneD[scatterSampleOffset][0], &r);
+    if (!g_pv.ready) Severe("%s::Li: the GPU context was not set up (no CUDA device?)", who);
+    pv_ray r; pv_fill_ray(ray, u_scatter, &r);
     pv_gather_params prm; memset(&prm, 0, sizeof(prm));
     prm.stepsize = stepSize; prm.nused = (uint32_t)nUsed; prm.maxdist = maxDist; prm.seed = g_pv.seed;
     prm.ray_index_base = ((uint64_t)rng.RandomUInt() << 20) | 0x8000000000000000ull;     // a stream of its own per call
     float L[PV_NSPEC], Tr[PV_NSPEC];
     int rc = pv_li_batched(r, prm.ray_index_base, prm, L, Tr);
-    if (rc) pv_fail("pv_gather", rc);
+    if (rc) pv_fail(g_pv.volint < 0 ? "pv_gather" : "pv_volume_li", rc);
     Spectrum Lv(0.f);
     memcpy(Lv.c, L, sizeof(L)); memcpy(T->c, Tr, sizeof(Tr));
     return Lv;
+}
+Spectrum PhotonVolumeIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
+                                    RNG &rng, Spectrum *T, MemoryArena &arena) const {
+    return pv_li_one("PhotonVolumeIntegrator", scene, ray, sample->oneD[scatterSampleOffset][0], stepSize, nUsed, maxDist, rng, T);
 }
 
 PhotonVolumeIntegrator *CreatePhotonVolumeIntegrator(const ParamSet &params, PhotonShooter *phs) {
@@ -415,6 +440,65 @@ PhotonVolumeIntegrator *CreatePhotonVolumeIntegrator(const ParamSet &params, Pho
     int nUsed = params.FindOneInt("nused", 250);
     float maxDist = params.FindOneFloat("maxdist", 0.1f);
     return new PhotonVolumeIntegrator(stepSize, nUsed, maxDist, phs);
+}
+
+// ------------------------------------------------------------------ SingleScatteringIntegrator (integrators/single.cpp),
+//                                                                    EmissionIntegrator (integrators/emission.cpp)
+// the reference's other two VolumeIntegrator plugins, same declarations (integrators/single.h:44-60,
+// emission.h), same .pbrt parameter ("stepsize", single.cpp:141-144, emission.cpp:109-112); Li runs on the device
+// (pv_volume_li), Transmittance stays the reference's three lines like PhotonVolumeIntegrator's above.
+void SingleScatteringIntegrator::RequestSamples(Sampler *sampler, Sample *sample, const Scene *scene) {
+    tauSampleOffset = sample->Add1D(1);
+    scatterSampleOffset = sample->Add1D(1);
+}
+Spectrum SingleScatteringIntegrator::Transmittance(const Scene *scene, const Renderer *renderer, const RayDifferential &ray,
+                                                   const Sample *sample, RNG &rng, MemoryArena &arena) const {
+    if (!scene->volumeRegion) return Spectrum(1.f);
+    float step = sample ? stepSize : 4.f * stepSize;
+    float offset = sample ? sample->oneD[tauSampleOffset][0] : rng.RandomFloat();
+    return Exp(-scene->volumeRegion->tau(ray, step, offset));
+}
+Spectrum SingleScatteringIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
+                                        RNG &rng, Spectrum *T, MemoryArena &arena) const {
+    return pv_li_one("SingleScatteringIntegrator", scene, ray, sample->oneD[scatterSampleOffset][0], stepSize, 0, 0.f, rng, T);
+}
+SingleScatteringIntegrator *CreateSingleScatteringIntegrator(const ParamSet &params) {
+    return new SingleScatteringIntegrator(params.FindOneFloat("stepsize", 1.f));
+}
+void EmissionIntegrator::RequestSamples(Sampler *sampler, Sample *sample, const Scene *scene) {
+    tauSampleOffset = sample->Add1D(1);
+    scatterSampleOffset = sample->Add1D(1);
+}
+Spectrum EmissionIntegrator::Transmittance(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample,
+                                           RNG &rng, MemoryArena &arena) const {
+    if (!scene->volumeRegion) return Spectrum(1.f);
+    float step = sample ? stepSize : 4.f * stepSize;
+    float offset = sample ? sample->oneD[tauSampleOffset][0] : rng.RandomFloat();
+    return Exp(-scene->volumeRegion->tau(ray, step, offset));
+}
+Spectrum EmissionIntegrator::Li(const Scene *scene, const Renderer *renderer, const RayDifferential &ray, const Sample *sample, RNG &rng,
+                                Spectrum *T, MemoryArena &arena) const {
+    return pv_li_one("EmissionIntegrator", scene, ray, sample->oneD[scatterSampleOffset][0], stepSize, 0, 0.f, rng, T);
+}
+EmissionIntegrator *CreateEmissionVolumeIntegrator(const ParamSet &params) {
+    return new EmissionIntegrator(params.FindOneFloat("stepsize", 1.f));
+}
+
+// The device context of a render whose volume integrator is "single" / "emission": the scene alone (no shooter exists for such
+// a scene file unless the surface integrator is a photon map, whose CPU pass is then the reference's own).
+static void pv_setup_volint(const Scene *scene, const PvVolInt &vi) {
+    std::string err;
+    if (!pv_export_scene(scene, g_pv.scene, err)) Severe("%s", err.c_str());
+    if (!g_pv.ctx) {
+        const char *dev = getenv("PV_DEVICE");
+        int rc = pv_create(&g_pv.ctx, dev ? atoi(dev) : 0);
+        if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
+    }
+    int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
+    if (rc) pv_fail("pv_set_scene", rc);
+    const char *seed = getenv("PV_SEED");
+    g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
+    g_pv.stepsize = vi.stepSize; g_pv.volint = vi.kind; g_pv.ready = true;
 }
 
 // ------------------------------------------------------------------ SamplerRenderer (renderers/samplerrenderer.cpp)
@@ -460,8 +544,8 @@ void SamplerRendererTask::Run() {
     Sampler *sampler = mainSampler->GetSubSampler(taskNum, taskCount);
     if (!sampler) { reporter.Update(); return; }
     const SamplerRenderer *sr = static_cast<const SamplerRenderer *>(renderer);
-    PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(sr->volumeIntegrator);
-    const bool batch = g_records && vi && g_pv.ready && scene->volumeRegion && !visualizeObjectIds;
+    PvVolInt vi;
+    const bool batch = g_records && pv_volint_of(sr->volumeIntegrator, &vi) && g_pv.ready && scene->volumeRegion && !visualizeObjectIds;
     MemoryArena arena;
     RNG rng(taskNum);
     int maxSamples = sampler->MaximumSampleCount();
@@ -483,7 +567,7 @@ void SamplerRendererTask::Run() {
                 if (rayWeight > 0.f)
                     rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i], g_fg ? &g_fg->rays[taskNum] : NULL,
                                              (uint32_t)out->size());
-                pv_fill_ray(rays[i], samples[i].oneD[vi->scatterSampleOffset][0], &rec.ray);
+                pv_fill_ray(rays[i], samples[i].oneD[vi.scatterSampleOffset][0], &rec.ray);
                 out->push_back(rec);
                 continue;
             }
@@ -505,6 +589,9 @@ void SamplerRenderer::Render(const Scene *scene) {
     if (photonShooter != NULL) photonShooter->Preprocess(scene, camera, this);
     surfaceIntegrator->Preprocess(scene, camera, this);
     volumeIntegrator->Preprocess(scene, camera, this);
+    PvVolInt vint;
+    const bool have_vint = pv_volint_of(volumeIntegrator, &vint);
+    if (have_vint && vint.kind >= 0 && scene->volumeRegion && !visualizeObjectIds) pv_setup_volint(scene, vint);
     Sample *sample = new Sample(sampler, surfaceIntegrator, volumeIntegrator, scene);
     camera->AutoFocus(this, scene, sample);
     // With the volume term on the GPU a render thread spends most of a specular bounce waiting for the device, and the batches
@@ -595,7 +682,7 @@ void SamplerRenderer::Render(const Scene *scene) {
         reporter.Done();
     }
     if (g_li.calls) {
-        fprintf(stderr, "[pv] volume term of %llu secondary rays (specular bounces) in %llu batched pv_gather calls, %.3f s inside them\n", g_li.calls,
+        fprintf(stderr, "[pv] volume term of %llu secondary rays (specular bounces) in %llu batched device calls, %.3f s inside them\n", g_li.calls,
                 g_li.batches, g_li.seconds);
         g_li.calls = g_li.batches = 0; g_li.seconds = 0;
     }
@@ -609,19 +696,19 @@ void SamplerRenderer::Render(const Scene *scene) {
     size_t total = 0;
     for (int t = 0; t < nTasks; ++t) total += records[t].size();
     if (total) {
-        PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(volumeIntegrator);
         std::vector<pv_ray> rays(total);
         size_t k = 0;
         for (int t = 0; t < nTasks; ++t) for (size_t i = 0; i < records[t].size(); ++i) rays[k++] = records[t][i].ray;
         std::vector<float> L(total * PV_NSPEC), T(total * PV_NSPEC);
         pv_gather_params prm; memset(&prm, 0, sizeof(prm));
-        prm.stepsize = vi->stepSize; prm.nused = (uint32_t)vi->nUsed; prm.maxdist = vi->maxDist; prm.seed = g_pv.seed;
+        prm.stepsize = vint.stepSize; prm.nused = (uint32_t)vint.nUsed; prm.maxdist = vint.maxDist; prm.seed = g_pv.seed;
         double t1 = now_s();
-        int rc = pv_gather(g_pv.ctx, rays.data(), total, &prm, L.data(), T.data());
-        if (rc) pv_fail("pv_gather", rc);
+        int rc = pv_volume_term(rays.data(), total, &prm, L.data(), T.data());
+        if (rc) pv_fail(g_pv.volint < 0 ? "pv_gather" : "pv_volume_li", rc);
         float ms = 0.f; pv_last_kernel_ms(g_pv.ctx, &ms);
-        fprintf(stderr, "[pv] surface pass %.3f s on %d cores; volume gather of %zu camera rays %.3f s (kernel %.3f ms)\n", t1 - t0,
-                NumSystemCores(), total, now_s() - t1, ms);
+        fprintf(stderr, "[pv] surface pass %.3f s on %d cores; %s of %zu camera rays %.3f s (kernel %.3f ms)\n", t1 - t0, NumSystemCores(),
+                g_pv.volint < 0 ? "volume gather" : (g_pv.volint == PV_VOLINT_SINGLE ? "single-scattering volume term" : "emission volume term"),
+                total, now_s() - t1, ms);
         k = 0;
         for (int t = 0; t < nTasks; ++t)
             for (size_t i = 0; i < records[t].size(); ++i, ++k) {

@@ -241,6 +241,17 @@ def volint_pbrt(kind, volume_text, stepsize=0.05, second_light=False, xres=64, y
     return text
 
 
+def volint_e2e_pbrt(kind, volume_text, stepsize=0.05, xres=72, yres=72, spp=4, outfile="volint_e2e.pfm"):
+    """End-to-end scene for the "single" / "emission" drop-in: the all-maps Cornell box (glass wedge => specular bounces whose
+    rays reach the volume integrator one at a time) under the direct-lighting surface integrator, two lights."""
+    text = cornell_surf_pbrt(xres=xres, yres=yres, stepsize=stepsize, volume_text=volume_text, outfile=outfile)
+    head, rest = text.split('SurfaceIntegrator "photonmap"', 1)
+    rest = rest.split("LookAt", 1)[1]
+    text = head + 'SurfaceIntegrator "directlighting"\nVolumeIntegrator "%s" "float stepsize" [%g]\nLookAt' % (kind, stepsize) + rest
+    text = text.replace('"integer pixelsamples" [1]', '"integer pixelsamples" [%d]' % spp)
+    return text.replace('Material "matte" "color Kd" [.6 .6 .6]', VOLINT_SPOT + '\nMaterial "matte" "color Kd" [.6 .6 .6]', 1)
+
+
 def volint_grid_volume(n=32):
     """Emitting, forward-scattering density grid (the config-3 blobs at n^3)."""
     return grid_volume_text(n, blob_density(n)).replace('"float g"', '"color Le" [.3 .3 .1] "float g"')

@@ -266,6 +266,24 @@ def volint_goldens(tmp):
         out[name + "_stepsize"] = np.array([stepsize], np.float32)
     out["mt_seed"] = np.array([4000], np.uint32)
     np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
+    # end-to-end images of the unmodified reference binary (glass wedge: specular bounces call the volume integrator per ray)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "pbrt_ref")
+    for name, kind, vol, stepsize in (("volint_single_e2e", "single", scenes.VOLINT_MEDIA["volint_homog"][0], 0.05),
+                                      ("volint_emission_e2e", "emission", scenes.volint_grid_volume(32), 0.0625)):
+        text = scenes.volint_e2e_pbrt(kind, vol, stepsize=stepsize, outfile=name + ".pfm")
+        f = os.path.join(tmp, name + ".pbrt"); open(f, "w").write(text)
+        open(os.path.join(ROOT, "tests", "scenes", name + ".pbrt"), "w").write(text)
+        subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)
+        img = read_pfm(os.path.join(tmp, name + ".pfm"))
+        np.save(os.path.join(HERE, name + "_ref.npy"), img.astype(np.float16))
+        subprocess.check_call([ref_bin, "--ncores", "3", "--quiet", f], cwd=tmp)          # another task count = other RNG seeds: the noise floor
+        img2 = read_pfm(os.path.join(tmp, name + ".pfm"))
+        lum = lambda a: 0.2126 * a[..., 0] + 0.7152 * a[..., 1] + 0.0722 * a[..., 2]
+        h = img.shape[0] // 6 * 6
+        bm = lambda a: lum(a)[:h, :h].reshape(h // 6, 6, h // 6, 6).mean(axis=(1, 3))
+        b1, b2 = bm(img), bm(img2); lit = b1 > 0.05 * b1.mean()
+        print("  %s: mean lum %.4g; two reference runs differ by %.3f%% (mean), %.3f%% (block MRE)" % (
+            name, lum(img).mean(), 100 * abs(lum(img).mean() - lum(img2).mean()) / lum(img).mean(), 100 * (np.abs(b1 - b2)[lit] / b1[lit]).mean()))
 
 
 def read_radiance(fn):
