@@ -101,6 +101,7 @@ ALLREDUCE_U32_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_v
 
 
 VOLINT_SINGLE, VOLINT_EMISSION = 0, 1        # PV_VOLINT_*
+VOLINT_WARP_PER_RAY, VOLINT_THREAD_PER_RAY = 4, 8
 
 # every symbol include/pv.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [

@@ -273,13 +273,13 @@ class PhotonVolume:
         self._chk(self.lib.pv_gather(self.ctx, _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
         return L, T
 
-    def VolumeLi(self, integrator, rays, ray_index_base=0):
+    def VolumeLi(self, integrator, rays, ray_index_base=0, flags=0):
         """SingleScatteringIntegrator::Li / EmissionIntegrator::Li (integrators/single.cpp:66-138, emission.cpp:63-106):
         integrator = "single" | "emission"; uses this object's stepsize and seed, no photon map."""
         kind = {"single": A.VOLINT_SINGLE, "emission": A.VOLINT_EMISSION}[integrator]
         rays = np.ascontiguousarray(rays); n = len(rays)
         L = np.zeros((n, A.NSPEC), np.float32); T = np.zeros((n, A.NSPEC), np.float32)
-        prm = self.gather_params(ray_index_base, 0)
+        prm = self.gather_params(ray_index_base, flags)          # flags: A.VOLINT_WARP_PER_RAY / A.VOLINT_THREAD_PER_RAY
         self._chk(self.lib.pv_volume_li(self.ctx, C.c_int(kind), _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
         return L, T
 

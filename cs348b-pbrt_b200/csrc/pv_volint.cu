@@ -12,7 +12,13 @@
 //     kernel: it is re-derived here from the same keyed Philox word (PV_RNG_STEP, word 1) when the test fires;
 //   * per step Lv += Tr * Lve(p) and, "single" only, Lv += Tr * ss * p(p, w, -wo) * Ld * nLights / pdf (single.cpp:113-130);
 //     the result is Lv * step, *T = Tr.
-// Streaming kernel: 64 B of records in and nothing out per step, 240 B out per ray.
+// Two schedules of the same arithmetic (bit-identical results, tests/test_gpu_volint.py):
+//   volint_kernel         one WARP per ray, lane == bin.  Lowest latency per ray; but the per-step bookkeeping (five shuffles,
+//                         loop control) is paid by all 32 lanes, and ncu shows the kernel issue-bound (76 % issue slots busy,
+//                         72 warp instructions per step, 4.5 ms for a 1080p frame of "single").  Used for small batches.
+//   volint_thread_kernel  one THREAD per ray, the 30 bins of Tr and Lv in registers, medium / light spectra in shared
+//                         memory.  The bookkeeping is paid once per ray-step instead of once per 32 lanes.  Used for frames.
+// Streaming kernels: 32 B of records in per step, 240 B out per ray.
 #include <algorithm>
 #include "pv_ctx.h"
 #include "pv_march.cuh"
@@ -114,6 +120,91 @@ __global__ void __launch_bounds__(VI_THREADS) volint_kernel(VolIntArgs a) {
     if (bin) { a.L[ri * PV_NSPEC + lane] = Lv * step; a.T[ri * PV_NSPEC + lane] = Tr; }
 }
 
+#define VT_THREADS 128
+// One thread per ray (frames of camera rays): same operations on the same values as volint_kernel, bin loops unrolled over
+// register arrays.  Spectra of the medium and of the lights are staged in shared memory (every lane reads the same word).
+template <bool SINGLE>
+__global__ void __launch_bounds__(VT_THREADS) volint_thread_kernel(VolIntArgs a) {
+    __shared__ float s_sig_t[PV_NSPEC], s_sig_s[PV_NSPEC], s_le[PV_NSPEC], s_cy[PV_NSPEC];
+    __shared__ float s_I[PV_MAX_LIGHTS][PV_NSPEC];
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    const int nLights = (int)sc.n_lights;
+    for (int i = threadIdx.x; i < PV_NSPEC; i += VT_THREADS) {
+        s_sig_t[i] = med.sigma_a[i] + med.sigma_s[i]; s_sig_s[i] = med.sigma_s[i]; s_le[i] = med.le[i]; s_cy[i] = sc.cie_y[i];
+    }
+    if (SINGLE)
+        for (int i = threadIdx.x; i < nLights * PV_NSPEC; i += VT_THREADS) s_I[i / PV_NSPEC][i % PV_NSPEC] = sc.lights[i / PV_NSPEC].intensity[i % PV_NSPEC];
+    __syncthreads();
+    const uint64_t ri = (uint64_t)blockIdx.x * VT_THREADS + threadIdx.x;
+    if (ri >= a.n) return;
+    float sig_t_max = 0.f;
+#pragma unroll
+    for (int b = 0; b < PV_NSPEC; ++b) sig_t_max = fmaxf(sig_t_max, s_sig_t[b]);
+    const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
+
+    const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri));
+    const int nSamples = __float_as_int(h0.z);
+    const float step = h0.w;
+    const float4 *rp = reinterpret_cast<const float4 *>(a.steps + (((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x)));
+    float Tr[PV_NSPEC], Lv[PV_NSPEC];
+#pragma unroll
+    for (int b = 0; b < PV_NSPEC; ++b) { Tr[b] = 1.f; Lv[b] = 0.f; }
+    if (nSamples > 0) {
+        const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
+        const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
+        const uint64_t gidx = a.ray_index_base + ri;
+        float S = 0.f;
+        float4 na = __ldg(rp), nb = __ldg(rp + 1);                        // t, tau, rr, dens | sh, dfac, ln, ray
+        for (int i = 0; i < nSamples; ++i, rp += 2) {
+            const float4 ra = na, rb = nb;
+            if (i + 1 < nSamples) { na = __ldg(rp + 2); nb = __ldg(rp + 3); }   // the next record is in flight during this step's bins
+            const float s_tau = ra.y, s_dens = ra.w;
+#pragma unroll
+            for (int b = 0; b < PV_NSPEC; ++b) Tr[b] = Tr[b] * expf(-(s_sig_t[b] * s_tau));
+            S += s_tau;
+            if (sig_t_max * S > 6.0f) {
+                float yy = 0.f;
+#pragma unroll
+                for (int b = 0; b < PV_NSPEC; ++b) yy += s_cy[b] * Tr[b];
+                if (__fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC) < 1e-3f) {
+                    uint32_t sw[4];
+                    pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)i, PV_RNG_STEP, a.k0, a.k1, sw);
+                    if (pv_u32_to_float(sw[1]) > .5f) {
+#pragma unroll
+                        for (int b = 0; b < PV_NSPEC; ++b) Tr[b] = 0.f;
+                        break;
+                    }
+#pragma unroll
+                    for (int b = 0; b < PV_NSPEC; ++b) Tr[b] = Tr[b] * 2.f;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < PV_NSPEC; ++b) Lv[b] = Lv[b] + Tr[b] * (s_le[b] * s_dens);
+            if (SINGLE) {
+                float s_dfac = rb.y;
+                if (s_dfac != 0.f) {
+                    const int ln = __float_as_int(rb.z);
+                    if (rainbow) {
+                        const v3 sp = ray_at(ro, rd, ra.x);
+                        s_dfac = (s_dfac * phase_hg(-rd, -vi_light_wo(sc.lights[ln], sp), med.g)) * (float)nLights;
+                    }
+                    const float s_sh = rb.x;
+                    const float *I = s_I[ln];
+#pragma unroll
+                    for (int b = 0; b < PV_NSPEC; ++b) {
+                        const float Ld = (I[b] * expf(-(s_sig_t[b] * s_sh))) * s_dfac;
+                        Lv[b] = Lv[b] + (Tr[b] * (s_sig_s[b] * s_dens)) * Ld;
+                    }
+                }
+            }
+        }
+    }
+    float *Lo = a.L + ri * PV_NSPEC, *To = a.T + ri * PV_NSPEC;
+#pragma unroll
+    for (int b = 0; b < PV_NSPEC; ++b) { Lo[b] = Lv[b] * step; To[b] = Tr[b]; }
+}
+
 static int volint_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, int integrator, float *d_L, float *d_T) {
     uint64_t total = 0;
     pv_gather_params p = *prm;
@@ -131,10 +222,21 @@ static int volint_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (const StepRec *)ctx->march_steps; a.n = n;
     a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32); a.ray_index_base = prm->ray_index_base;
     a.L = d_L; a.T = d_T;
-    const uint32_t blocks = (uint32_t)((n * 32 + VI_THREADS - 1) / VI_THREADS);
+    // Which schedule?  One thread per ray once the rays alone fill the machine (a few resident warps on every SM), one warp per
+    // ray below that; PV_VOLINT_THREAD_PER_RAY / PV_VOLINT_WARP_PER_RAY in params->flags force one or the other.
+    bool per_thread = n >= (uint64_t)ctx->sm_count * 512;
+    if (prm->flags & PV_VOLINT_THREAD_PER_RAY) per_thread = true;
+    if (prm->flags & PV_VOLINT_WARP_PER_RAY) per_thread = false;
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (integrator == PV_VOLINT_EMISSION) volint_kernel<false><<<blocks, VI_THREADS, 0, ctx->stream>>>(a);
-    else volint_kernel<true><<<blocks, VI_THREADS, 0, ctx->stream>>>(a);
+    if (per_thread) {
+        const uint32_t blocks = (uint32_t)((n + VT_THREADS - 1) / VT_THREADS);
+        if (integrator == PV_VOLINT_EMISSION) volint_thread_kernel<false><<<blocks, VT_THREADS, 0, ctx->stream>>>(a);
+        else volint_thread_kernel<true><<<blocks, VT_THREADS, 0, ctx->stream>>>(a);
+    } else {
+        const uint32_t blocks = (uint32_t)((n * 32 + VI_THREADS - 1) / VI_THREADS);
+        if (integrator == PV_VOLINT_EMISSION) volint_kernel<false><<<blocks, VI_THREADS, 0, ctx->stream>>>(a);
+        else volint_kernel<true><<<blocks, VI_THREADS, 0, ctx->stream>>>(a);
+    }
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev1));     // the next slice overwrites the march records

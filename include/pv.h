@@ -245,6 +245,10 @@ int pv_last_march_ms(pv_ctx *ctx, float *ms);
  * host pointers (pv_volume_li) or device pointers (pv_volume_li_dev).         */
 #define PV_VOLINT_SINGLE   0
 #define PV_VOLINT_EMISSION 1
+/* Scheduling (params->flags; results are bit-identical either way; default: chosen from the number of rays): one warp per
+ * ray with lane == spectral bin (small batches) or one thread per ray with the spectrum in registers (frames).            */
+#define PV_VOLINT_WARP_PER_RAY   4u
+#define PV_VOLINT_THREAD_PER_RAY 8u
 int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n,
                  const pv_gather_params *params, float *L, float *T);
 int pv_volume_li_dev(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n,

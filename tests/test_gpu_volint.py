@@ -82,6 +82,12 @@ def test_volume_li_vs_oracle_same_philox_stream(golden, pkg, pv_factory, name, k
     check(L, T, oL, oT)
     if name == "volint_dense":
         assert (oT == 0).all(axis=1).any() and ((oT > 0) & (oT < 1e-2)).any()     # roulette both ended and spared marches
+    # the two schedules (one warp per ray / one thread per ray) run the same arithmetic: bit-identical
+    A = pkg._abi
+    Lw, Tw = pv.VolumeLi(kind, rays, ray_index_base=700, flags=A.VOLINT_WARP_PER_RAY)
+    Lt, Tt = pv.VolumeLi(kind, rays, ray_index_base=700, flags=A.VOLINT_THREAD_PER_RAY)
+    assert np.array_equal(L, Lw) and np.array_equal(T, Tw)            # the default for 160 rays
+    assert np.array_equal(Lt.view(np.uint32), Lw.view(np.uint32)) and np.array_equal(Tt.view(np.uint32), Tw.view(np.uint32))
     # sharding by ray_index_base reproduces the one-call result bit for bit
     L2, T2 = pv.VolumeLi(kind, rays[50:120], ray_index_base=750)
     assert np.array_equal(L2, L[50:120]) and np.array_equal(T2, T[50:120])
@@ -100,6 +106,8 @@ def test_single_li_on_the_path_scenes_vs_oracle(golden, pv_factory, name):
     oL, oT, ost = O.volume_li(scene, rays, stepsize, O.SINGLE, seed=31337, ray_index_base=5)
     assert ost.shadow_rays > 0
     check(L, T, oL, oT)
+    Lt, Tt = pv.VolumeLi("single", rays, ray_index_base=5, flags=8)          # PV_VOLINT_THREAD_PER_RAY
+    assert np.array_equal(Lt.view(np.uint32), L.view(np.uint32)) and np.array_equal(Tt.view(np.uint32), T.view(np.uint32))
     Le, Te = pv.VolumeLi("emission", rays, ray_index_base=5)
     oLe, oTe, _ = O.volume_li(scene, rays, stepsize, O.EMISSION, seed=31337, ray_index_base=5)
     check(Le, Te, oLe, oTe, need_light=False)
