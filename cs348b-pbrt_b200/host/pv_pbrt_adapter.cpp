@@ -1,6 +1,6 @@
 // pv_pbrt_adapter.cpp -- the host side of the drop-in: the reference's own classes, re-implemented over the C ABI.
 //
-// Linked INTO the reference (piwell/CS348B-pbrt) in place of three of its translation units; every class keeps the
+// Linked INTO the reference (piwell/CS348B-pbrt) in place of five of its translation units; every class keeps the
 // declaration of the reference's header, so core/api.cpp (the name-string "plugin registry", :572-586, :1221-1288),
 // the parser, cameras, samplers, surface integrators and the film are used unchanged:
 //
@@ -13,6 +13,7 @@
 //                                        reachable for scenes off this path and under PV_SURFACE_MAPS=cpu.
 //   integrators/photonvolume.cpp         PhotonVolumeIntegrator::{RequestSamples, Transmittance, Li} and
 //                                        CreatePhotonVolumeIntegrator (same .pbrt parameters, :224-229).
+//   integrators/single.cpp, emission.cpp SingleScatteringIntegrator / EmissionIntegrator: Li over pv_volume_li.
 //   renderers/samplerrenderer.cpp        SamplerRenderer with a BATCHED Render: image tiles run the unchanged camera /
 //                                        sampler / surface-integrator code on the reference's pthread pool
 //                                        (core/parallel.cpp) and queue their camera rays; the volume term of the whole
