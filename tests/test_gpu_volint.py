@@ -134,3 +134,60 @@ def test_volume_li_edge_cases(golden, pkg, pv_factory):
     assert rc == -1 and b"unknown integrator" in pv.lib.pv_last_error(pv.ctx)          # PV_EINVAL
     # the photon-volume path of the same context is untouched by the call
     assert pv.photon_count() == 0
+
+
+@pytest.fixture(scope="module")
+def full_frame(pkg):
+    """BASELINE config 3's scene shape at full size: 256^3 density grid (made emitting), 1920x1080 camera rays, stepsize 2/64."""
+    import importlib
+    W = importlib.import_module("cs348b_pbrt_b200.workloads")
+    cfg = W.CONFIGS["config3"]
+    scene = W.load_scene(cfg)
+    for b in range(pkg._abi.NSPEC):
+        scene.medium.le[b] = 0.05 + 0.01 * b
+    rays, _ = W.frame_rays(cfg)
+    pv = pkg.PhotonVolume(device=0, stepsize=cfg["stepsize"], seed=348)
+    pv.set_scene(scene)
+    yield dict(cfg=cfg, scene=scene, rays=rays, pv=pv)
+    pv.close()
+
+
+@pytest.mark.parametrize("kind", ["single", "emission"])
+def test_full_frame_volume_li_properties(full_frame, pkg, kind):
+    """The oracle cannot march 2 M rays in seconds, so at full size parity rests on properties that do not depend on size:
+    determinism; the two kernel schedules agree bit for bit (frames take the thread-per-ray one by default); sharding the frame
+    by ray_index_base reproduces it bit for bit; the radiance is exactly linear in the emission and the light intensity (a
+    power-of-two scale is exact in fp32) while the transmittance does not move; and a sample of the frame against the oracle."""
+    A = pkg._abi
+    pv, rays, scene, cfg = full_frame["pv"], full_frame["rays"], full_frame["scene"], full_frame["cfg"]
+    n = len(rays)
+    L1, T1 = pv.VolumeLi(kind, rays)
+    L2, T2 = pv.VolumeLi(kind, rays)
+    assert np.array_equal(L1, L2) and np.array_equal(T1, T2)
+    assert np.isfinite(L1).all() and L1.max() > 0 and (T1 >= 0).all() and (T1 <= 1).all()
+    Lw, Tw = pv.VolumeLi(kind, rays, flags=A.VOLINT_WARP_PER_RAY)
+    assert np.array_equal(L1.view(np.uint32), Lw.view(np.uint32)) and np.array_equal(T1.view(np.uint32), Tw.view(np.uint32))
+    h = n // 2 + 7                                          # not tile aligned
+    La, Ta = pv.VolumeLi(kind, rays[:h], ray_index_base=0)
+    Lb, Tb = pv.VolumeLi(kind, rays[h:], ray_index_base=h)
+    assert np.array_equal(np.concatenate([La, Lb]), L1) and np.array_equal(np.concatenate([Ta, Tb]), T1)
+    # linearity: emission and every light twice as bright
+    try:
+        for b in range(A.NSPEC):
+            scene.medium.le[b] *= 2.0
+            for l in scene.lights:
+                l.intensity[b] *= 2.0
+        pv.set_scene(scene)
+        L3, T3 = pv.VolumeLi(kind, rays)
+    finally:
+        for b in range(A.NSPEC):
+            scene.medium.le[b] *= 0.5
+            for l in scene.lights:
+                l.intensity[b] *= 0.5
+        pv.set_scene(scene)
+    assert np.array_equal(L3, 2.0 * L1) and np.array_equal(T3, T1)
+    # a sample of the frame against the pinned oracle (same Philox stream: the sample is its own call on both sides)
+    sub = np.ascontiguousarray(rays[::400])
+    gL, gT = pv.VolumeLi(kind, sub, flags=A.VOLINT_THREAD_PER_RAY)
+    oL, oT, _ = O.volume_li(scene, sub, cfg["stepsize"], KINDS[kind], seed=348)
+    check(gL, gT, oL, oT)
