@@ -50,7 +50,7 @@ int pv_create(pv_ctx **out, int device) {
               cudaMalloc((void **)&ctx->d_stats, sizeof(pv_gather_stats)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_counters, 64 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(ctx->d_stats, 0, sizeof(pv_gather_stats)) == cudaSuccess;
-    if (!ok) { g_err = std::string("pv_create: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return PV_ECUDA; }
+    if (!ok) { g_err = std::string("pv_create: ") + cudaGetErrorString(cudaGetLastError()); pv_destroy(ctx); return PV_ECUDA; }   // frees what was made
     *out = ctx;
     return PV_OK;
 }
@@ -382,7 +382,17 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
     const uint64_t min_slice = 1ull << 18;
     int nslices = (int)std::max<uint64_t>(1, std::min<uint64_t>(4, n / min_slice));
     if (const char *e = getenv("PV_GATHER_SLICES")) nslices = std::max(1, std::min(PV_GATHER_MAX_SLICES, atoi(e)));     // tuning knob
-    cudaEvent_t in_done[PV_GATHER_MAX_SLICES], comp_done[PV_GATHER_MAX_SLICES];
+    // Every path out of this function (the CUDA checks below return early on an error) first waits for the copies that read or
+    // write the CALLER's buffers, then releases the per-slice events.
+    struct SliceEvents {
+        cudaStream_t in, out;
+        cudaEvent_t in_done[PV_GATHER_MAX_SLICES] = {}, comp_done[PV_GATHER_MAX_SLICES] = {};
+        ~SliceEvents() {
+            cudaStreamSynchronize(in); cudaStreamSynchronize(out);
+            for (int s = 0; s < PV_GATHER_MAX_SLICES; ++s) { if (in_done[s]) cudaEventDestroy(in_done[s]); if (comp_done[s]) cudaEventDestroy(comp_done[s]); }
+        }
+    } evs{ctx->copy_in, ctx->copy_out};
+    cudaEvent_t *in_done = evs.in_done, *comp_done = evs.comp_done;
     for (int s = 0; s < nslices; ++s) {
         PV_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in_done[s], cudaEventDisableTiming));
         PV_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&comp_done[s], cudaEventDisableTiming));
@@ -413,7 +423,6 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
     cudaStreamSynchronize(ctx->copy_in);
     cudaStreamSynchronize(ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->copy_out);
-    for (int s = 0; s < nslices; ++s) { cudaEventDestroy(in_done[s]); cudaEventDestroy(comp_done[s]); }
     if (rc) return rc;
     if (e != cudaSuccess) { ctx->err = std::string("pv_gather: ") + cudaGetErrorString(e); return PV_ECUDA; }
     ctx->last_ms = ms; ctx->last_march_ms = march_ms;
