@@ -39,11 +39,14 @@ static inline void pv_mat_out(const Transform &t, float *dst) {
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) dst[4 * i + j] = t.m.m[i][j];
 }
 
-static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err) {
-    BVHAccel *bvh = dynamic_cast<BVHAccel *>(scene->aggregate);
-    if (!bvh) { err = "pv: the scene aggregate is not the \"bvh\" accelerator"; return false; }
-    const uint32_t nPrims = (uint32_t)bvh->primitives.size();
-    const LinearBVHNode *nodes = (const LinearBVHNode *)bvh->nodes;
+// medium_only: export the volume region and nothing else (no geometry, no lights) -- all that EmissionIntegrator::Li reads
+// (integrators/emission.cpp:63-106); lets "emission", pbrt's DEFAULT volume integrator (core/api.cpp:211), run on the device in
+// scenes whose surfaces or lights are off this path (area lights, other shapes, other accelerators).
+static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err, bool medium_only = false) {
+    BVHAccel *bvh = medium_only ? NULL : dynamic_cast<BVHAccel *>(scene->aggregate);
+    if (!bvh && !medium_only) { err = "pv: the scene aggregate is not the \"bvh\" accelerator"; return false; }
+    const uint32_t nPrims = bvh ? (uint32_t)bvh->primitives.size() : 0u;
+    const LinearBVHNode *nodes = bvh ? (const LinearBVHNode *)bvh->nodes : NULL;
     uint32_t nNodes = 0;
     if (nodes) {   // depth-first layout (flattenBVHTree bvh.cpp:559-577): the node count is the largest index reached + 1
         std::vector<uint32_t> todo; todo.push_back(0);
@@ -112,7 +115,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
         hs.prim_material[i] = matIndex[m];
     }
     hs.lights.clear();
-    for (size_t i = 0; i < scene->lights.size(); ++i) {
+    for (size_t i = 0; !medium_only && i < scene->lights.size(); ++i) {
         pv_light pl; memset(&pl, 0, sizeof(pl));
         Light *l = scene->lights[i];
         pv_mat_out(l->LightToWorld, pl.light_to_world);

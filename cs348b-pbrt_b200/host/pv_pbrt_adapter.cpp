@@ -489,7 +489,13 @@ EmissionIntegrator *CreateEmissionVolumeIntegrator(const ParamSet &params) {
 // a scene file unless the surface integrator is a photon map, whose CPU pass is then the reference's own).
 static void pv_setup_volint(const Scene *scene, const PvVolInt &vi) {
     std::string err;
-    if (!pv_export_scene(scene, g_pv.scene, err)) Severe("%s", err.c_str());
+    if (!pv_export_scene(scene, g_pv.scene, err)) {
+        // "emission" is pbrt's default volume integrator and reads only the medium: a scene whose surfaces or lights are off
+        // this path (area lights, other shapes ...) still runs on the device, with the medium alone exported
+        std::string err2;
+        if (vi.kind != PV_VOLINT_EMISSION || !pv_export_scene(scene, g_pv.scene, err2, true)) Severe("%s", err.c_str());
+        Warning("%s -- the emission integrator needs the medium only, exporting that", err.c_str());
+    }
     if (!g_pv.ctx) {
         const char *dev = getenv("PV_DEVICE");
         int rc = pv_create(&g_pv.ctx, dev ? atoi(dev) : 0);

@@ -252,6 +252,14 @@ def volint_e2e_pbrt(kind, volume_text, stepsize=0.05, xres=72, yres=72, spp=4, o
     return text.replace('Material "matte" "color Kd" [.6 .6 .6]', VOLINT_SPOT + '\nMaterial "matte" "color Kd" [.6 .6 .6]', 1)
 
 
+def volint_offpath_pbrt(stepsize=0.05):
+    """An "emission" scene whose surfaces and lights are OFF the device path (a disk shape that is an area light): the drop-in
+    exports the medium alone for it (host/pv_export.inl, medium_only)."""
+    text = volint_pbrt("emission", VOLINT_MEDIA["volint_homog"][0], stepsize=stepsize)
+    return text.replace("WorldEnd", 'AttributeBegin\nAreaLightSource "diffuse" "color L" [5 5 5]\nTranslate 0 0.9 0\nRotate 90 1 0 0\n'
+                                    'Shape "disk" "float radius" [0.3]\nAttributeEnd\nWorldEnd')
+
+
 def volint_grid_volume(n=32):
     """Emitting, forward-scattering density grid (the config-3 blobs at n^3)."""
     return grid_volume_text(n, blob_density(n)).replace('"float g"', '"color Le" [.3 .3 .1] "float g"')

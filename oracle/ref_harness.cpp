@@ -506,7 +506,8 @@ void pbrtWorldEnd() {
     for (size_t i = 0; i < g_ops.size(); ++i) {
         const std::string &op = g_ops[i];
         #define ARG(k) (i + (k) < g_ops.size() ? g_ops[i + (k)] : (fprintf(stderr, "missing arg for %s\n", op.c_str()), exit(2), g_ops[0]))
-        if (op == "--export-scene") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
+        if (op == "--export-medium") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err, true)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
+        else if (op == "--export-scene") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
         else if (op == "--shoot") { shoot(sh, scene, sr->camera, sr); }
         else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }
         else if (op == "--dump-photons") { dump_photons(ARG(1)); i += 1; }

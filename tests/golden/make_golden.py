@@ -264,6 +264,13 @@ def volint_goldens(tmp):
             out["%s_%s_L" % (name, kind)], out["%s_%s_T" % (name, kind)] = li[:, 0], li[:, 1]
             print("  %s/%s: mean L %.4g, min T.y %.3g" % (name, kind, li[:, 0].mean(), li[:, 1].mean(axis=1).min()))
         out[name + "_stepsize"] = np.array([stepsize], np.float32)
+    # a scene off the device path except for its medium (disk-shaped area light): the full export must refuse it, the
+    # medium-only export (what the drop-in falls back to for "emission") carries all that EmissionIntegrator::Li reads
+    f = os.path.join(tmp, "volint_offpath.pbrt"); open(f, "w").write(scenes.volint_offpath_pbrt())
+    assert subprocess.run([HARNESS, f, "--export-scene", os.path.join(tmp, "refused.scn")], capture_output=True).returncode == 4
+    run(f, "--export-medium", os.path.join(HERE, "volint_offpath_medium.scn"), "--vli", rf, 4000, os.path.join(tmp, "vli.bin"))
+    li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
+    out["volint_offpath_emission_L"], out["volint_offpath_emission_T"] = li[:, 0], li[:, 1]
     out["mt_seed"] = np.array([4000], np.uint32)
     np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
     # end-to-end images of the unmodified reference binary (glass wedge: specular bounces call the volume integrator per ray)

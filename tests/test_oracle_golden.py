@@ -229,3 +229,18 @@ def test_single_and_emission_li_match_reference_with_mt_stream(golden, pkg, name
     m = refL > 0
     assert np.array_equal(L > 0, m) and relerr(L, refL)[m].max() < 1e-5
     assert (st.shadow_rays > 0) == (kind == "single")
+
+
+def test_emission_li_on_a_medium_only_export_matches_reference(golden, pkg):
+    """A scene whose surfaces and lights are off the device path (a disk-shaped area light): the exporter refuses it as a whole
+    but exports its medium alone (host/pv_export.inl `medium_only`, the drop-in's route for pbrt's default "emission"
+    integrator).  EmissionIntegrator::Li reads nothing else: the oracle on that geometry-less scene reproduces the reference's
+    values on the full scene bit for bit."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    scene = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_offpath_medium.scn"))
+    assert scene.n_nodes == 0 and scene.n_prims == 0 and len(scene.lights) == 0
+    L, T, _ = O.volume_li(scene, g["rays"], 0.05, O.EMISSION, rng_mode=O.MT, mt_seed=int(g["mt_seed"][0]))
+    assert (g["volint_offpath_emission_L"] > 0).any()
+    assert np.array_equal(L, g["volint_offpath_emission_L"]) and np.array_equal(T, g["volint_offpath_emission_T"])
