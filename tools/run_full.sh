@@ -14,3 +14,7 @@ ncu --set full --clock-control none --import-source on -k march_steps_kernel --l
 ncu --set full --clock-control none --import-source on -k regex:shoot_kernel -c 10 -o gpurun_out/${tag}_shoot -f $B > gpurun_out/${tag}_ncu_shoot.log 2>&1
 # BASELINE config 2 (k-nearest gather, 1 M photons, 512x512, k = 50) as a second bench line
 python bench.py --workload config2 --steps 5 --warmup 3 --shoot-photons 0 --maps-photons 0 --no-cpu-baseline > gpurun_out/${tag}_config2.log 2>&1
+# VolumeIntegrator "single" / "emission" (pv_volume_li) on the config-3 scene shape: plain run, then one full capture of the
+# thread-per-ray recurrence kernel (the first timed "single" launch)
+python tools/volint_bench.py > gpurun_out/${tag}_volint_bench.jsonl 2> gpurun_out/${tag}_volint_bench.err
+ncu --set full --clock-control none --import-source on -k regex:volint_thread_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_volint -f python tools/volint_bench.py --no-cpu --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_volint.log 2>&1
