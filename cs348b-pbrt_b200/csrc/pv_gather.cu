@@ -52,6 +52,13 @@
 #ifndef GW_P2_UNROLL
 #define GW_P2_UNROLL 4
 #endif
+#ifndef GW_RANGES_PRE
+// EXPERIMENT, off by default, not yet measured (profiles/r01_v5_gather_regions.md): the nine photon runs of a march step's 3x3
+// rows are computed by lanes 0..8 of the ray's warp while 23 lanes idle -- 183 of the kernel's 1112 warp instructions per
+// lookup.  With 1 a thread-per-STEP kernel (ranges_kernel) computes them for the whole slice beforehand, all lanes busy, and
+// gather_kernel<false> only loads them (80 B per step through ctx->lii, which the ray-parallel form does not use otherwise).
+#define GW_RANGES_PRE 0
+#endif
 #define GW_STR(x) #x
 #define GW_UNROLL(n) _Pragma(GW_STR(unroll n))
 
@@ -336,6 +343,67 @@ __device__ __forceinline__ void lookup_issue(const MapView &m, WarpBuf &b, uint3
     pf.bt = batch_begin(m, b, pf.bt.rs, pf.bt.len, lane);
     pf.issued = true;
 }
+#if GW_RANGES_PRE
+// What lookup_ranges leaves in the Prefetch of lanes 0..8, for one march step: nine [start, end) runs + the two flags.
+struct StepRanges { uint2 row[9]; uint32_t flags, pad; };            // 80 bytes; flags: 1 = in_range, 2 = fast
+static_assert(sizeof(StepRanges) == 80, "StepRanges");
+__device__ __forceinline__ void ranges_load(const StepRanges *sr, uint32_t lane, Prefetch &pf) {
+    const uint32_t fl = __ldg(&sr->flags);
+    pf.issued = false; pf.in_range = (fl & 1u) != 0; pf.fast = (fl & 2u) != 0; pf.bt.rs = 0; pf.bt.len = 0; pf.bt.E = 0; pf.bt.T = 0;
+    if (pf.in_range && lane < 9) { const uint2 v = __ldg(&sr->row[lane]); pf.bt.rs = v.x; pf.bt.len = v.y; }
+}
+// One THREAD per march step of the slice: the same arithmetic as lookup_ranges, the nine rows in a loop.
+__global__ void __launch_bounds__(256) ranges_kernel(MapView m, const pv_ray *__restrict__ rays, const StepRec *__restrict__ steps,
+                                                     unsigned long long total, float r, uint32_t k, StepRanges *__restrict__ out) {
+    const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const GridParams &g = m.g;
+    const float4 ra = __ldg(reinterpret_cast<const float4 *>(steps + s)), rb = __ldg(reinterpret_cast<const float4 *>(steps + s) + 1);
+    const uint32_t ri = __float_as_uint(rb.w);
+    const v3 ro = V3(__ldg(&rays[ri].o[0]), __ldg(&rays[ri].o[1]), __ldg(&rays[ri].o[2]));
+    const v3 rd = V3(__ldg(&rays[ri].d[0]), __ldg(&rays[ri].d[1]), __ldg(&rays[ri].d[2]));
+    const v3 q = ray_at(ro, rd, ra.x);
+    StepRanges sr;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sr.row[i] = make_uint2(0u, 0u);
+    sr.pad = 0u;
+    const int ux = (int)floorf((q.x - g.origin[0]) * g.inv_hx), uy = (int)floorf((q.y - g.origin[1]) * g.inv_h),
+              uz = (int)floorf((q.z - g.origin[2]) * g.inv_h);
+    const bool inside = ux >= 0 && ux < g.dims[0] && uy >= 0 && uy < g.dims[1] && uz >= 0 && uz < g.dims[2];
+    const bool in_range = m.n != 0 && k != 0 && (inside || lookup_in_range(g, q, r));
+    const bool fast = inside && r <= g.one_shell_r;
+    sr.flags = (in_range ? 1u : 0u) | (in_range && fast ? 2u : 0u);
+    if (in_range) {
+        const int cx = min(max(ux, 0), g.dims[0] - 1) >> g.xshift, cy = min(max(uy, 0), g.dims[1] - 1), cz = min(max(uz, 0), g.dims[2] - 1);
+#pragma unroll
+        for (int row = 0; row < 9; ++row) {
+            const int dy = row % 3 - 1, dz = row / 3 - 1;
+            const int y = cy + dy, z = cz + dz;
+            if (y >= 0 && y < g.dims[1] && z >= 0 && z < g.dims[2]) {
+                const float ylo = g.origin[1] + cy * g.h, zlo = g.origin[2] + cz * g.h;
+                float gy = dy == 0 ? 0.f : (dy < 0 ? q.y - ylo : (ylo + g.h) - q.y);
+                float gz = dz == 0 ? 0.f : (dz < 0 ? q.z - zlo : (zlo + g.h) - q.z);
+                gy = fmaxf(gy - g.margin, 0.f); gz = fmaxf(gz - g.margin, 0.f);
+                const float w2 = r * r - (gy * gy + gz * gz);
+                if (w2 > 0.f) {
+                    const float half = __fsqrt_ru(w2) + g.margin;
+                    int xa = (int)floorf(((q.x - half) - g.origin[0]) * g.inv_hx), xb = (int)floorf(((q.x + half) - g.origin[0]) * g.inv_hx);
+                    if (!fast) { xa = max(xa, (cx - 1) << g.xshift); xb = min(xb, ((cx + 2) << g.xshift) - 1); }
+                    xa = max(xa, 0); xb = min(xb, g.dims[0] - 1);
+                    if (xa <= xb) {
+                        const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                        sr.row[row] = make_uint2(__ldg(m.cell_start + (rowkey | (uint32_t)xa)), __ldg(m.cell_start + (rowkey | (uint32_t)xb) + 1));
+                    }
+                }
+            }
+        }
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(out + s);                       // 80 B = five 128-bit stores
+    o[0] = make_uint4(sr.row[0].x, sr.row[0].y, sr.row[1].x, sr.row[1].y); o[1] = make_uint4(sr.row[2].x, sr.row[2].y, sr.row[3].x, sr.row[3].y);
+    o[2] = make_uint4(sr.row[4].x, sr.row[4].y, sr.row[5].x, sr.row[5].y); o[3] = make_uint4(sr.row[6].x, sr.row[6].y, sr.row[7].x, sr.row[7].y);
+    o[4] = make_uint4(sr.row[8].x, sr.row[8].y, sr.flags, 0u);
+}
+#endif
 
 // shells s >= 2 of a lookup (k-nearest mode with a sparse neighbourhood): rows on the rim of the (2s+1)^2 square are
 // full runs, inner rows contribute their two end cells.  Out of line (the fixed-radius gather never gets here) and
@@ -1002,8 +1070,15 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
                         // cell ranges of the NEXT step are requested now and consumed after this step's scan
                         Prefetch nx; nx.in_range = false; nx.issued = false;
                         const bool has_next = i + 1 < nthis;
+#if GW_RANGES_PRE
+                        const StepRanges *srp = reinterpret_cast<const StepRanges *>(a.lii) + ((size_t)(recs - a.steps) + (size_t)(c0 + i));
+                        if (has_next) ranges_load(srp + 1, lane, nx);
+                        if (i == 0) ranges_load(srp, lane, pf);             // first step of a chunk: nothing was prefetched for it
+                        const uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, true, &pf);
+#else
                         if (has_next) lookup_ranges(a.m, ray_at(ro, rd, __shfl_sync(PV_FULL, c_t, i + 1)), a.maxdist, a.nused, lane, nx);
                         const uint32_t cnt = warp_lookup(a.m, sp, r2, a.maxdist, a.nused, b, lane, true, pf.in_range ? &pf : nullptr);
+#endif
                         __syncwarp();
                         if (has_next) lookup_issue(a.m, b, lane, nx);       // next step's TMA copies fly during the flux sum below
                         pf = nx;
@@ -1227,6 +1302,15 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     }
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+#if GW_RANGES_PRE
+    if (!step_parallel && lookups && total > 0) {           // inside the ev0..ev1 bracket: the kernel time reported stays comparable
+        rc = pv_ensure(ctx, &ctx->lii, &ctx->lii_bytes, (size_t)total * sizeof(StepRanges)); if (rc) return rc;
+        a.lii = (float *)ctx->lii;
+        ranges_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a.m, d_rays, a.steps, total, prm->maxdist, a.nused,
+                                                                                 (StepRanges *)ctx->lii);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+    }
+#endif
     if (step_parallel) {
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
