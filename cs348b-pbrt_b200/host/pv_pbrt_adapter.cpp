@@ -37,6 +37,7 @@
 #include <condition_variable>
 #include <memory>
 #include <chrono>
+#include <thread>
 
 #define private public
 #define protected public
@@ -93,6 +94,9 @@ struct PvBridge {
     // final gathering runs on a context of its own (scene + radiance photons + their grid): rays spawned by specular bounces
     // call the volume integrator (pv_gather on `ctx`, grid on the volume map) while primary hits are still being shaded
     pv_ctx *fg_ctx;
+    // PV_DEVICES="0,1,2,3": contexts on the other GPUs of the box, each holding the scene and a replica of the volume photon map
+    // (replicate the map, shard the camera rays).  Empty unless PV_DEVICES names more than one device.
+    std::vector<pv_ctx *> replicas;
     std::vector<float> rad_pos, rad_nrm, rad_Lo;
     PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), volint(-1), fg_ctx(NULL) {}
 };
@@ -117,9 +121,67 @@ bool pv_volint_of(const VolumeIntegrator *v, PvVolInt *o) {
     return true;
 }
 // Li of a batch of rays with whichever of the three the scene file chose
+int pv_volume_term_on(pv_ctx *ctx, const pv_ray *rays, size_t n, const pv_gather_params *prm, float *L, float *T) {
+    if (g_pv.volint < 0) return pv_gather(ctx, rays, n, prm, L, T);
+    return pv_volume_li(ctx, g_pv.volint, rays, n, prm, L, T);
+}
 int pv_volume_term(const pv_ray *rays, size_t n, const pv_gather_params *prm, float *L, float *T) {
-    if (g_pv.volint < 0) return pv_gather(g_pv.ctx, rays, n, prm, L, T);
-    return pv_volume_li(g_pv.ctx, g_pv.volint, rays, n, prm, L, T);
+    return pv_volume_term_on(g_pv.ctx, rays, n, prm, L, T);
+}
+
+// ---- several GPUs inside the drop-in (off unless PV_DEVICES lists more than one device; NOT yet run on a multi-GPU box) -----
+// The scene and the volume photon map are replicated (the whole map is a few GB at most); the camera rays of
+// the frame are cut into one contiguous run per device, each with its global ray index as Philox stream base, so the image does
+// not depend on the number of devices.  Shooting, final gathering and the secondary rays of specular bounces stay on the first.
+std::vector<int> pv_device_list() {
+    std::vector<int> d;
+    if (const char *e = getenv("PV_DEVICES"))
+        for (const char *p = e; *p;) { char *q; long v = strtol(p, &q, 10); if (q == p) break; d.push_back((int)v); p = *q == ',' ? q + 1 : q; }
+    if (d.empty()) { const char *e = getenv("PV_DEVICE"); d.push_back(e ? atoi(e) : 0); }
+    return d;
+}
+void pv_replicate(bool with_map, float maxdist, uint32_t nused) {
+    const std::vector<int> dev = pv_device_list();
+    for (size_t i = 0; i < g_pv.replicas.size(); ++i) pv_destroy(g_pv.replicas[i]);
+    g_pv.replicas.clear();
+    if (dev.size() < 2) return;
+    uint64_t n = 0;
+    std::vector<float> pos, wi, alpha;
+    if (with_map) {
+        int rc = pv_photon_count(g_pv.ctx, &n);
+        pos.resize(3 * n); wi.resize(3 * n); alpha.resize((size_t)PV_NSPEC * n);
+        if (!rc && n) rc = pv_get_photons(g_pv.ctx, pos.data(), wi.data(), alpha.data(), NULL, n, &n);
+        if (rc) pv_fail("pv_get_photons", rc);
+    }
+    for (size_t i = 1; i < dev.size(); ++i) {
+        pv_ctx *c = NULL;
+        int rc = pv_create(&c, dev[i]);
+        if (rc) Severe("pv_create on device %d failed (%d): %s", dev[i], rc, pv_last_error(NULL));
+        rc = pv_set_scene(c, &g_pv.scene.desc);
+        if (!rc && with_map) rc = pv_set_photons(c, pos.data(), wi.data(), alpha.data(), n);
+        if (!rc && with_map) rc = pv_build(c, maxdist, nused);
+        if (rc) Severe("replica on device %d failed (%d): %s", dev[i], rc, pv_last_error(c));
+        g_pv.replicas.push_back(c);
+    }
+    fprintf(stderr, "[pv] scene%s replicated on %zu more device(s)\n", with_map ? " and volume photon map" : "", g_pv.replicas.size());
+}
+// the volume term of a whole frame: one call per device, concurrently
+int pv_volume_term_frame(const pv_ray *rays, size_t n, const pv_gather_params *prm, float *L, float *T) {
+    const size_t G = 1 + g_pv.replicas.size();
+    if (G == 1 || n < 4096 * G) return pv_volume_term(rays, n, prm, L, T);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < G; ++d) {
+        const size_t a = n * d / G, b = n * (d + 1) / G;
+        pv_ctx *c = d == 0 ? g_pv.ctx : g_pv.replicas[d - 1];
+        th.push_back(std::thread([=, &rcs]() {
+            pv_gather_params p = *prm; p.ray_index_base = prm->ray_index_base + a;
+            rcs[d] = pv_volume_term_on(c, rays + a, b - a, &p, L + a * PV_NSPEC, T + a * PV_NSPEC);
+        }));
+    }
+    for (size_t d = 0; d < G; ++d) th[d].join();
+    for (size_t d = 0; d < G; ++d) if (rcs[d]) { if (d) Error("device call on replica %zu failed: %s", d, pv_last_error(g_pv.replicas[d - 1])); return rcs[d]; }
+    return 0;
 }
 
 struct PvRecord {                 // one camera sample waiting for its volume term
@@ -216,8 +278,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
     std::string err;
     if (!pv_export_scene(scene, g_pv.scene, err)) Severe("%s", err.c_str());
     if (!g_pv.ctx) {
-        const char *dev = getenv("PV_DEVICE");
-        int rc = pv_create(&g_pv.ctx, dev ? atoi(dev) : 0);
+        int rc = pv_create(&g_pv.ctx, pv_device_list()[0]);
         if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
     }
     int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
@@ -305,6 +366,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         if (rc) pv_fail("pv_build", rc);
     }
     g_pv.ready = true;
+    pv_replicate(true, vi->maxDist, (uint32_t)vi->nUsed);
     // PV_SURFACE_MAPS=cpu: the surface maps from the reference's own CPU pass instead.  That pass keeps scattering photons in
     // the medium only while its own volume map is not full (`scatter && !volumeDone`, photonshooter.cpp:96), so it is asked for
     // as many volume photons as surface photons, never for the full volume count; its volume photons are dropped.
@@ -497,8 +559,7 @@ static void pv_setup_volint(const Scene *scene, const PvVolInt &vi) {
         Warning("%s -- the emission integrator needs the medium only, exporting that", err.c_str());
     }
     if (!g_pv.ctx) {
-        const char *dev = getenv("PV_DEVICE");
-        int rc = pv_create(&g_pv.ctx, dev ? atoi(dev) : 0);
+        int rc = pv_create(&g_pv.ctx, pv_device_list()[0]);
         if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
     }
     int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
@@ -506,6 +567,7 @@ static void pv_setup_volint(const Scene *scene, const PvVolInt &vi) {
     const char *seed = getenv("PV_SEED");
     g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
     g_pv.stepsize = vi.stepSize; g_pv.volint = vi.kind; g_pv.ready = true;
+    pv_replicate(false, 0.f, 0);
 }
 
 // ------------------------------------------------------------------ SamplerRenderer (renderers/samplerrenderer.cpp)
@@ -634,8 +696,7 @@ void SamplerRenderer::Render(const Scene *scene) {
         fg.primary->photonShooter = bare;
         fg.rays.resize(nTasks);
         if (!g_pv.fg_ctx) {
-            const char *dev = getenv("PV_DEVICE");
-            int rc = pv_create(&g_pv.fg_ctx, dev ? atoi(dev) : 0);
+            int rc = pv_create(&g_pv.fg_ctx, pv_device_list()[0]);
             if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
         }
         const uint64_t nrad = g_pv.rad_pos.size() / 3;
@@ -710,7 +771,7 @@ void SamplerRenderer::Render(const Scene *scene) {
         pv_gather_params prm; memset(&prm, 0, sizeof(prm));
         prm.stepsize = vint.stepSize; prm.nused = (uint32_t)vint.nUsed; prm.maxdist = vint.maxDist; prm.seed = g_pv.seed;
         double t1 = now_s();
-        int rc = pv_volume_term(rays.data(), total, &prm, L.data(), T.data());
+        int rc = pv_volume_term_frame(rays.data(), total, &prm, L.data(), T.data());
         if (rc) pv_fail(g_pv.volint < 0 ? "pv_gather" : "pv_volume_li", rc);
         float ms = 0.f; pv_last_kernel_ms(g_pv.ctx, &ms);
         fprintf(stderr, "[pv] surface pass %.3f s on %d cores; %s of %zu camera rays %.3f s (kernel %.3f ms)\n", t1 - t0, NumSystemCores(),

@@ -1,0 +1,95 @@
+/* mock_libpv.c -- TEST DOUBLE of csrc/libpv.so for CPU tests of the drop-in's HOST logic (tests/test_adapter_host.py).
+ *
+ * Not a CPU implementation of anything: the "radiance" it returns is a hash of the ray's global stream index, which is exactly
+ * what makes it useful -- an image rendered through it changes if the adapter hands a ray to the device under another index,
+ * drops a ray, or stitches device results back in the wrong place.  Every call is appended to $MOCK_PV_LOG.
+ * Exports the entry points host/pv_pbrt_adapter.cpp binds (include/pv.h). */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include "pv.h"
+
+struct pv_ctx { int device; uint64_t n_photons; double photon_sum; };
+
+static void logf_(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+#include <stdarg.h>
+static void logf_(const char *fmt, ...) {
+    const char *fn = getenv("MOCK_PV_LOG");
+    if (!fn) return;
+    char buf[512];
+    va_list ap; va_start(ap, fmt); int n = vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    int fd = open(fn, O_WRONLY | O_APPEND | O_CREAT, 0644);
+    if (fd >= 0) { if (write(fd, buf, (size_t)n) < 0) {} close(fd); }          /* one O_APPEND write per line: atomic across threads */
+}
+
+int pv_version(void) { return 100; }
+const char *pv_last_error(pv_ctx *ctx) { (void)ctx; return "mock"; }
+int pv_create(pv_ctx **out, int device) {
+    *out = (pv_ctx *)calloc(1, sizeof(pv_ctx)); (*out)->device = device;
+    logf_("create dev=%d\n", device);
+    return PV_OK;
+}
+void pv_destroy(pv_ctx *ctx) { if (ctx) logf_("destroy dev=%d\n", ctx->device); free(ctx); }
+int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) { logf_("set_scene dev=%d prims=%u lights=%u\n", ctx->device, s->n_prims, s->n_lights); return PV_OK; }
+int pv_shoot(pv_ctx *ctx, uint64_t wanted, const pv_shoot_params *p, pv_shoot_stats *st) {
+    (void)p; ctx->n_photons = wanted; if (st) { memset(st, 0, sizeof(*st)); st->paths = 4096; }
+    logf_("shoot dev=%d n=%llu\n", ctx->device, (unsigned long long)wanted);
+    return PV_OK;
+}
+int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *p, pv_maps_stats *st) {
+    (void)p; ctx->n_photons = mp->n_volume_wanted; if (st) { memset(st, 0, sizeof(*st)); st->n[0] = mp->n_volume_wanted; }
+    logf_("shoot_maps dev=%d n=%llu\n", ctx->device, (unsigned long long)mp->n_volume_wanted);
+    return PV_OK;
+}
+int pv_build(pv_ctx *ctx, float maxdist, uint32_t nused) { logf_("build dev=%d n=%llu maxdist=%g nused=%u\n", ctx->device, (unsigned long long)ctx->n_photons, maxdist, nused); return PV_OK; }
+int pv_photon_count(pv_ctx *ctx, uint64_t *n) { *n = ctx->n_photons; return PV_OK; }
+int pv_get_photons(pv_ctx *ctx, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t cap, uint64_t *n) {
+    uint64_t m = cap < ctx->n_photons ? cap : ctx->n_photons;
+    double sum = 0;
+    for (uint64_t i = 0; i < m; ++i) {
+        for (int k = 0; k < 3; ++k) { if (pos) { pos[3 * i + k] = (float)(i % 977) * 0.001f + k; sum += pos[3 * i + k]; } if (wi) wi[3 * i + k] = k == 2; }
+        for (int b = 0; b < PV_NSPEC && alpha; ++b) { alpha[PV_NSPEC * i + b] = 1e-3f * (float)(b + 1); sum += alpha[PV_NSPEC * i + b]; }
+        if (ids) ids[i] = i;
+    }
+    if (n) *n = m;
+    logf_("get_photons dev=%d n=%llu sum=%.6f\n", ctx->device, (unsigned long long)m, sum);
+    return PV_OK;
+}
+int pv_set_photons(pv_ctx *ctx, const float *pos, const float *wi, const float *alpha, uint64_t n) {
+    (void)wi; double sum = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3 && pos; ++k) sum += pos[3 * i + k];
+        for (int b = 0; b < PV_NSPEC && alpha; ++b) sum += alpha[PV_NSPEC * i + b];
+    }
+    ctx->n_photons = n; ctx->photon_sum = sum;
+    logf_("set_photons dev=%d n=%llu sum=%.6f\n", ctx->device, (unsigned long long)n, sum);
+    return PV_OK;
+}
+static void fake_li(const char *what, pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *p, float *L, float *T) {
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t g = p->ray_index_base + i;
+        uint32_t h = (uint32_t)(g * 2654435761u) ^ (uint32_t)(g >> 32);
+        for (int b = 0; b < PV_NSPEC; ++b) {
+            L[PV_NSPEC * i + b] = (float)((h >> (b % 16)) & 0xffu) / 255.f * (rays[i].d[2] > 0.f ? 1.f : .5f);
+            T[PV_NSPEC * i + b] = 0.75f;
+        }
+    }
+    logf_("%s dev=%d base=%llu n=%llu\n", what, ctx->device, (unsigned long long)p->ray_index_base, (unsigned long long)n);
+}
+int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *p, float *L, float *T) { fake_li("gather", ctx, rays, n, p, L, T); return PV_OK; }
+int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, const pv_gather_params *p, float *L, float *T) {
+    fake_li(integrator == PV_VOLINT_SINGLE ? "volume_li_single" : "volume_li_emission", ctx, rays, n, p, L, T); return PV_OK;
+}
+int pv_last_kernel_ms(pv_ctx *ctx, float *ms) { (void)ctx; *ms = 0.f; return PV_OK; }
+/* surface-map entry points: present so the binary loads; the host-logic tests use scenes without surface photon maps */
+int pv_get_map_photons(pv_ctx *c, int m, float *a, float *b, float *d, uint64_t *e, uint64_t cap, uint64_t *n) { (void)c; (void)m; (void)a; (void)b; (void)d; (void)e; (void)cap; if (n) *n = 0; return PV_OK; }
+int pv_set_map_photons(pv_ctx *c, int m, const float *a, const float *b, const float *d, uint64_t n) { (void)c; (void)m; (void)a; (void)b; (void)d; (void)n; return PV_OK; }
+int pv_radiance_photons(pv_ctx *c, uint32_t k, float r2, const uint64_t *pc, float *Lo, uint64_t cap, uint64_t *n) { (void)c; (void)k; (void)r2; (void)pc; (void)Lo; (void)cap; if (n) *n = 0; return PV_OK; }
+int pv_set_radiance_lo(pv_ctx *c, const float *Lo, uint64_t n) { (void)c; (void)Lo; (void)n; return PV_OK; }
+int pv_select_map(pv_ctx *c, int m, float r, uint32_t k) { (void)c; (void)m; (void)r; (void)k; return PV_OK; }
+int pv_final_gather(pv_ctx *c, const pv_ray *r, uint64_t n, float step, uint64_t seed, uint64_t base, float *L, uint32_t *idx) {
+    (void)c; (void)r; (void)step; (void)seed; (void)base; memset(L, 0, sizeof(float) * PV_NSPEC * n); if (idx) memset(idx, 0xff, sizeof(uint32_t) * n); return PV_OK;
+}

@@ -1,0 +1,90 @@
+"""CPU: the HOST logic of the drop-in binary (cs348b-pbrt_b200/host/pv_pbrt_adapter.cpp linked into the reference renderer,
+baseline/_ref/pbrt_b200) run against a TEST DOUBLE of libpv.so (tests/mock/mock_libpv.c, put in front of the real library with
+LD_LIBRARY_PATH).  The double returns a hash of each ray's global stream index as "radiance" and logs every call, so these
+tests see what the adapter asks the device to do -- call order, which device gets which rays under which index, how results
+are stitched -- without a GPU.  Nothing here says anything about the CUDA path's numbers; that is tests/test_gpu_*.py."""
+import os
+import re
+import shutil
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "baseline", "_ref", "pbrt_b200")
+pytestmark = pytest.mark.skipif(not os.path.exists(BIN) or shutil.which("gcc") is None,
+                                reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
+
+
+@pytest.fixture(scope="module")
+def mock(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mockpv")
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "mock", "mock_libpv.c"), "-o", str(d / "libpv.so")])
+    return d
+
+
+def render(mock, tmp_path, name, text, devices=None):
+    scene = tmp_path / (name + ".pbrt")
+    scene.write_text(text)
+    log = tmp_path / (name + ".log")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+    env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+    if devices:
+        env["PV_DEVICES"] = devices
+    out = subprocess.run([BIN, "--quiet", "--ncores", "2", str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    img = (tmp_path / (name + ".pfm")).read_bytes()
+    return img, log.read_text().splitlines(), out.stderr
+
+
+def calls(log, what):
+    return [dict((k, int(v)) for k, v in re.findall(r"(\w+)=(\d+)", l)) for l in log if l.startswith(what + " ")]
+
+
+def test_frame_is_sharded_over_devices_by_global_ray_index(mock, tmp_path, pkg):
+    """VolumeIntegrator "single", PV_DEVICES=0,1,2: the scene goes to three contexts, the camera rays of the frame to three
+    concurrent pv_volume_li calls that partition [0, n) in order, each with its first ray's global index as stream base; the
+    stitched image is byte-identical to the one-device image."""
+    from cs348b_pbrt_b200 import scenes
+    vol = scenes.VOLINT_MEDIA["volint_homog"][0]
+    one, log1, _ = render(mock, tmp_path, "one", scenes.volint_pbrt("single", vol, xres=160, yres=160, outfile="one.pfm"))
+    three, log3, err = render(mock, tmp_path, "three", scenes.volint_pbrt("single", vol, xres=160, yres=160, outfile="three.pfm"), "0,1,2")
+    assert one[:20] == three[:20] and one == three
+    assert [c["dev"] for c in calls(log1, "create")] == [0] and len(calls(log1, "volume_li_single")) == 1
+    assert [c["dev"] for c in calls(log3, "create")] == [0, 1, 2]
+    assert sorted(c["dev"] for c in calls(log3, "set_scene")) == [0, 1, 2]
+    li = sorted(calls(log3, "volume_li_single"), key=lambda c: c["base"])
+    n = calls(log1, "volume_li_single")[0]["n"]
+    assert [c["dev"] for c in li] == [0, 1, 2]
+    assert li[0]["base"] == 0 and all(a["base"] + a["n"] == b["base"] for a, b in zip(li, li[1:])) and li[-1]["base"] + li[-1]["n"] == n
+    assert "replicated on 2 more device(s)" in err
+
+
+def test_photon_map_is_replicated_before_the_frame_is_sharded(mock, tmp_path, pkg):
+    """VolumeIntegrator "photonvolume", PV_DEVICES=2,0: photons are shot and the map built on the FIRST listed device, read back
+    once, installed and built on the other (same count, same checksum), then the frame is split between the two."""
+    from cs348b_pbrt_b200 import scenes
+    text = lambda out: scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=128, yres=128, outfile=out)
+    one, log1, _ = render(mock, tmp_path, "pone", text("pone.pfm"))
+    two, log2, _ = render(mock, tmp_path, "ptwo", text("ptwo.pfm"), "2,0")
+    assert one == two
+    assert [c["dev"] for c in calls(log2, "create")] == [2, 0]
+    assert [c["dev"] for c in calls(log2, "shoot")] == [2]
+    order = [l.split()[0] + ":" + re.search(r"dev=(\d+)", l).group(1) for l in log2]
+    assert order.index("build:2") < order.index("get_photons:2") < order.index("set_photons:0") < order.index("build:0") < order.index("gather:2")
+    got = re.search(r"sum=([0-9.]+)", [l for l in log2 if l.startswith("get_photons")][0]).group(1)
+    put = re.search(r"sum=([0-9.]+)", [l for l in log2 if l.startswith("set_photons")][0]).group(1)
+    assert got == put and calls(log2, "set_photons")[0]["n"] == 1000
+    g = sorted(calls(log2, "gather"), key=lambda c: c["base"])
+    assert [c["dev"] for c in g] == [2, 0] and g[0]["base"] == 0 and g[0]["n"] == g[1]["base"]
+    assert g[1]["base"] + g[1]["n"] == calls(log1, "gather")[0]["n"]
+
+
+def test_emission_scene_off_the_path_goes_down_with_its_medium_only(mock, tmp_path, pkg):
+    """pbrt's default volume integrator on a scene whose surfaces / lights the device path does not know (a disk-shaped area
+    light): the adapter exports the medium alone (no primitives, no lights) and the frame is one pv_volume_li(emission)."""
+    from cs348b_pbrt_b200 import scenes
+    _, log, _ = render(mock, tmp_path, "volint", scenes.volint_offpath_pbrt())
+    s = calls(log, "set_scene")
+    assert len(s) == 1 and s[0]["prims"] == 0 and s[0]["lights"] == 0
+    assert len(calls(log, "volume_li_emission")) == 1 and not calls(log, "volume_li_single") and not calls(log, "gather")
