@@ -405,8 +405,11 @@ static void pv_fill_ray(const RayDifferential &ray, float u_scatter, pv_ray *r) 
 // shading (SpecularReflect/Transmit -> Renderer::Li -> VolumeIntegrator::Li), on every render thread at once.  A device round
 // trip per ray, serialised by the context's mutex, is what such a render would spend its time on (measured: 3.2 of 3.3 s).
 // Instead the first thread that arrives opens a batch and waits a few tens of microseconds for the other threads' rays; the
-// batch is ONE pv_gather; everybody picks its own result up.  The result of a ray does not depend on who it shared a batch
-// with: every ray carries its own Philox stream index.
+// batch is ONE device call; everybody picks its own result up.  The ABI takes one stream base per call, so a ray's Philox
+// stream is (the batch leader's index + its slot in the batch): which random numbers a secondary ray sees depends on the batch
+// it joined -- the same distribution whatever the batching (and no dependence at all where Li is deterministic: homogeneous
+// medium, one light, no roulette), but such renders are not bit-reproducible from run to run, like the reference's own
+// multi-threaded renders.
 namespace {
 struct LiBatch {
     std::vector<pv_ray> rays; std::vector<uint64_t> index;
