@@ -88,3 +88,22 @@ def test_emission_scene_off_the_path_goes_down_with_its_medium_only(mock, tmp_pa
     s = calls(log, "set_scene")
     assert len(s) == 1 and s[0]["prims"] == 0 and s[0]["lights"] == 0
     assert len(calls(log, "volume_li_emission")) == 1 and not calls(log, "volume_li_single") and not calls(log, "gather")
+
+
+def test_secondary_rays_are_batched_across_render_threads_without_loss(mock, tmp_path, pkg):
+    """The glass wedge's specular bounces reach VolumeIntegrator::Li one ray at a time on every render thread; the adapter
+    gathers them into batches (one device call each).  Every such ray is in exactly one batch: the rays the adapter counted
+    equal the rays the device calls carried, batches hold at most 4096 rays, and the frame itself is still one call."""
+    from cs348b_pbrt_b200 import scenes
+    text = scenes.volint_e2e_pbrt("single", scenes.VOLINT_MEDIA["volint_homog"][0], xres=96, yres=96, spp=2, outfile="wedge.pfm")
+    _, log, err = render(mock, tmp_path, "wedge", text)
+    m = re.search(r"volume term of (\d+) secondary rays \(specular bounces\) in (\d+) batched device calls", err)
+    assert m, err[-1000:]
+    nsec, nbatches = int(m.group(1)), int(m.group(2))
+    li = calls(log, "volume_li_single")
+    frame = [c for c in li if c["base"] == 0]
+    assert len(frame) == 1 and frame[0]["n"] >= 96 * 96 * 2          # every camera sample of the frame (the film's sample extent)
+    small = [c for c in li if c is not frame[0]]
+    assert nsec > 1000 and len(small) == nbatches and sum(c["n"] for c in small) == nsec
+    assert max(c["n"] for c in small) <= 4096
+    assert all(c["base"] >> 63 for c in small)               # secondary rays live in the upper half of the stream-index space
