@@ -3,6 +3,7 @@
  * Not a CPU implementation of anything: the "radiance" it returns is a hash of the ray's global stream index, which is exactly
  * what makes it useful -- an image rendered through it changes if the adapter hands a ray to the device under another index,
  * drops a ray, or stitches device results back in the wrong place.  Every call is appended to $MOCK_PV_LOG.
+ * Photon maps it "shoots" are synthetic points on the floor of the test scenes' box.
  * Exports the entry points host/pv_pbrt_adapter.cpp binds (include/pv.h). */
 #include <stdio.h>
 #include <stdlib.h>
@@ -12,7 +13,7 @@
 #include <fcntl.h>
 #include "pv.h"
 
-struct pv_ctx { int device; uint64_t n_photons; double photon_sum; };
+struct pv_ctx { int device; uint64_t n_photons; double photon_sum; uint64_t n_map[5]; };
 
 static void logf_(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 #include <stdarg.h>
@@ -39,9 +40,18 @@ int pv_shoot(pv_ctx *ctx, uint64_t wanted, const pv_shoot_params *p, pv_shoot_st
     logf_("shoot dev=%d n=%llu\n", ctx->device, (unsigned long long)wanted);
     return PV_OK;
 }
+/* every map "filled" to what was asked for; 300 radiance-photon sites when final gathering is on */
 int pv_shoot_maps(pv_ctx *ctx, const pv_maps_params *mp, const pv_shoot_params *p, pv_maps_stats *st) {
-    (void)p; ctx->n_photons = mp->n_volume_wanted; if (st) { memset(st, 0, sizeof(*st)); st->n[0] = mp->n_volume_wanted; }
-    logf_("shoot_maps dev=%d n=%llu\n", ctx->device, (unsigned long long)mp->n_volume_wanted);
+    (void)p; ctx->n_photons = mp->n_volume_wanted;
+    ctx->n_map[PV_MAP_VOLUME] = mp->n_volume_wanted; ctx->n_map[PV_MAP_CAUSTIC] = mp->n_caustic_wanted;
+    ctx->n_map[PV_MAP_INDIRECT] = mp->n_indirect_wanted; ctx->n_map[PV_MAP_DIRECT] = 0; ctx->n_map[PV_MAP_RADIANCE] = mp->final_gather ? 300 : 0;
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        for (int k = 0; k < 5; ++k) st->n[k] = ctx->n_map[k];
+        st->nshot = 4096; st->blocks = 1; st->n_caustic_paths = st->n_indirect_paths = st->n_direct_paths = st->n_volume_paths = 4096;
+    }
+    logf_("shoot_maps dev=%d volume=%llu caustic=%llu indirect=%llu fg=%d\n", ctx->device, (unsigned long long)mp->n_volume_wanted,
+          (unsigned long long)mp->n_caustic_wanted, (unsigned long long)mp->n_indirect_wanted, (int)mp->final_gather);
     return PV_OK;
 }
 int pv_build(pv_ctx *ctx, float maxdist, uint32_t nused) { logf_("build dev=%d n=%llu maxdist=%g nused=%u\n", ctx->device, (unsigned long long)ctx->n_photons, maxdist, nused); return PV_OK; }
@@ -85,11 +95,42 @@ int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, co
 }
 int pv_last_kernel_ms(pv_ctx *ctx, float *ms) { (void)ctx; *ms = 0.f; return PV_OK; }
 /* surface-map entry points: present so the binary loads; the host-logic tests use scenes without surface photon maps */
-int pv_get_map_photons(pv_ctx *c, int m, float *a, float *b, float *d, uint64_t *e, uint64_t cap, uint64_t *n) { (void)c; (void)m; (void)a; (void)b; (void)d; (void)e; (void)cap; if (n) *n = 0; return PV_OK; }
-int pv_set_map_photons(pv_ctx *c, int m, const float *a, const float *b, const float *d, uint64_t n) { (void)c; (void)m; (void)a; (void)b; (void)d; (void)n; return PV_OK; }
-int pv_radiance_photons(pv_ctx *c, uint32_t k, float r2, const uint64_t *pc, float *Lo, uint64_t cap, uint64_t *n) { (void)c; (void)k; (void)r2; (void)pc; (void)Lo; (void)cap; if (n) *n = 0; return PV_OK; }
+/* surface photons / radiance-photon sites scattered over the floor of the Cornell box (y = -1), arriving from straight above */
+int pv_get_map_photons(pv_ctx *c, int m, float *pos, float *wi, float *alpha, uint64_t *ids, uint64_t cap, uint64_t *n) {
+    uint64_t k = cap < c->n_map[m] ? cap : c->n_map[m];
+    for (uint64_t i = 0; i < k; ++i) {
+        uint32_t h = (uint32_t)(i * 2654435761u + (uint32_t)m * 40503u);
+        if (pos) { pos[3 * i] = (float)(h & 0xffffu) / 32768.f - 1.f; pos[3 * i + 1] = -1.f; pos[3 * i + 2] = (float)(h >> 16) / 32768.f - 1.f; }
+        if (wi) { wi[3 * i] = 0.f; wi[3 * i + 1] = 1.f; wi[3 * i + 2] = 0.f; }
+        for (int b = 0; b < PV_NSPEC && alpha; ++b) alpha[PV_NSPEC * i + b] = 0.002f;
+        if (ids) ids[i] = ((uint64_t)m << 60) | i;
+    }
+    if (n) *n = k;
+    logf_("get_map_photons dev=%d map=%d n=%llu\n", c->device, m, (unsigned long long)k);
+    return PV_OK;
+}
+int pv_set_map_photons(pv_ctx *c, int m, const float *a, const float *b, const float *d, uint64_t n) {
+    (void)a; (void)b; (void)d; c->n_map[m] = n; logf_("set_map_photons dev=%d map=%d n=%llu\n", c->device, m, (unsigned long long)n); return PV_OK;
+}
+int pv_radiance_photons(pv_ctx *c, uint32_t k, float r2, const uint64_t *pc, float *Lo, uint64_t cap, uint64_t *n) {
+    (void)k; (void)r2; (void)pc;
+    uint64_t m = cap < c->n_map[PV_MAP_RADIANCE] ? cap : c->n_map[PV_MAP_RADIANCE];
+    for (uint64_t i = 0; i < m * PV_NSPEC && Lo; ++i) Lo[i] = 0.25f;
+    if (n) *n = m;
+    logf_("radiance_photons dev=%d n=%llu\n", c->device, (unsigned long long)m);
+    return PV_OK;
+}
 int pv_set_radiance_lo(pv_ctx *c, const float *Lo, uint64_t n) { (void)c; (void)Lo; (void)n; return PV_OK; }
-int pv_select_map(pv_ctx *c, int m, float r, uint32_t k) { (void)c; (void)m; (void)r; (void)k; return PV_OK; }
+int pv_select_map(pv_ctx *c, int m, float r, uint32_t k) { (void)r; (void)k; logf_("select_map dev=%d map=%d\n", c->device, m); return PV_OK; }
+/* "indirect radiance" of a final-gather ray = a hash of its global index, like fake_li */
 int pv_final_gather(pv_ctx *c, const pv_ray *r, uint64_t n, float step, uint64_t seed, uint64_t base, float *L, uint32_t *idx) {
-    (void)c; (void)r; (void)step; (void)seed; (void)base; memset(L, 0, sizeof(float) * PV_NSPEC * n); if (idx) memset(idx, 0xff, sizeof(uint32_t) * n); return PV_OK;
+    (void)r; (void)step; (void)seed;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t g = base + i;
+        uint32_t h = (uint32_t)(g * 2246822519u) ^ (uint32_t)(g >> 32);
+        for (int b = 0; b < PV_NSPEC; ++b) L[PV_NSPEC * i + b] = (float)((h >> (b % 16)) & 0xffu) / 2550.f;
+        if (idx) idx[i] = (uint32_t)(h % 300u);
+    }
+    logf_("final_gather dev=%d base=%llu n=%llu\n", c->device, (unsigned long long)base, (unsigned long long)n);
+    return PV_OK;
 }

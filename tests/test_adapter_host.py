@@ -107,3 +107,38 @@ def test_secondary_rays_are_batched_across_render_threads_without_loss(mock, tmp
     assert nsec > 1000 and len(small) == nbatches and sum(c["n"] for c in small) == nsec
     assert max(c["n"] for c in small) <= 4096
     assert all(c["base"] >> 63 for c in small)               # secondary rays live in the upper half of the stream-index space
+
+
+def test_final_gather_wavefront_is_reproducible_across_thread_counts(mock, tmp_path, pkg):
+    """All photon maps + final gathering (no specular surfaces): Preprocess is ONE pv_shoot_maps followed by the reads the untouched
+    PhotonIntegrator needs (caustic / indirect lists, radiance photons), the final-gather rays of primary hits go down as
+    pv_final_gather batches on a second context whose grid holds the radiance photons, in task order with consecutive global
+    indices -- so the frame does not depend on how many render threads produced it (1 vs 2 cores, same task count)."""
+    from cs348b_pbrt_b200 import scenes
+    def text(out):
+        t = scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=128, yres=128, outfile=out)
+        t = t.replace('"bool finalgather" ["false"]', '"bool finalgather" ["true"] "integer finalgathersamples" [4]')
+        return t.replace('"integer indirectphotons" [0]', '"integer indirectphotons" [500]')
+    imgs, logs, errs = [], [], []
+    for cores in ("1", "2"):
+        scene = tmp_path / ("fg%s.pbrt" % cores); scene.write_text(text("fg%s.pfm" % cores))
+        log = tmp_path / ("fg%s.log" % cores)
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+        env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", cores, str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        imgs.append((tmp_path / ("fg%s.pfm" % cores)).read_bytes()); logs.append(log.read_text().splitlines()); errs.append(out.stderr)
+    assert imgs[0] == imgs[1]
+    log, err = logs[1], errs[1]
+    names = [l.split()[0] for l in log]
+    # Preprocess: one pass for every map, then the lists the CPU surface integrator reads, radiance photons, the volume grid
+    assert names[:3] == ["create", "set_scene", "shoot_maps"] and names.count("shoot_maps") == 1 and "shoot" not in names
+    assert [c["map"] for c in calls(log, "get_map_photons")] == [2, 4]            # indirect (caustic map empty: not read), radiance sites
+    assert names.index("radiance_photons") < names.index("build")
+    # the final-gather context: scene + radiance photons + their grid, before the first batch
+    assert names.index("select_map") < names.index("final_gather") and calls(log, "select_map")[0]["map"] == 4
+    fg = calls(log, "final_gather")
+    m = re.search(r"final gathering of primary hits on the GPU: (\d+) gather rays", err)
+    assert m and sum(c["n"] for c in fg) == int(m.group(1)) > 10000
+    assert fg[0]["base"] == 0 and all(a["base"] + a["n"] == b["base"] for a, b in zip(fg, fg[1:]))
+    assert len(calls(log, "gather")) == 1                                        # the volume term of the frame: still one call
