@@ -91,6 +91,19 @@ def cpu_gather_baseline(W, cfg, scene, pos, wi, alpha, rays, nsample, threads, s
             "lookups_per_s": st.lookups / dt}, (sel, L, T)
 
 
+def cpu_shoot_baseline(scene, cfg, n_wanted, threads, seed):
+    """The CPU port's photon shooter (oracle; per-path Philox streams, 4096-path blocks spread over the host threads) on a bounded
+    sample in the same scene with the same parameters as the GPU sample above: the `shoot` rates' CPU counterpart."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    O.shoot(scene, 2000, 0.05, cfg["stepsize"], 5, seed=seed, rng_mode=O.PHILOX, nthreads=threads)       # untimed: library load, thread start
+    t0 = time.perf_counter()
+    r = O.shoot(scene, n_wanted, 0.05, cfg["stepsize"], 5, seed=seed, rng_mode=O.PHILOX, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"paths_per_s": r["nshot"] / dt, "photons_per_s": r["n"] / dt, "cores": threads, "kind": "port",
+            "sample": "%d volume photons from %d light paths, %.1f s" % (r["n"], r["nshot"], dt)}
+
+
 def run_reference(args, cfg, W, scene):
     """--impl reference: the reference's CPU implementation of the gather on the host cores (rank 0 only).
     Preferred: oracle/_ref/ref_harness = the UNMODIFIED reference (KdTree<Photon>, PhotonVolumeIntegrator::Li, its pthread
@@ -175,6 +188,7 @@ def main():
     ap.add_argument("--shoot-photons", type=int, default=400_000, help="bounded photon-shooting sample for the shoot rates")
     ap.add_argument("--maps-photons", type=int, default=200_000, help="volume-photon target of the all-maps shooting sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=600_000, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-shoot-photons", type=int, default=150_000, help="photons of the bounded CPU-baseline shooting sample (0 = skip)")
     ap.add_argument("--ref-rays", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=348)
@@ -366,6 +380,11 @@ def main():
         gL, gT = pv.Li(np.ascontiguousarray(rays[sel]))
         m = cL > 0
         cpu["max_rel_err_vs_gpu"] = float((np.abs(gL - cL)[m] / cL[m]).max()) if m.any() else 0.0
+        if shoot and args.cpu_shoot_photons > 0:
+            try:
+                shoot["cpu_baseline"] = cpu_shoot_baseline(scene, cfg, args.cpu_shoot_photons, threads, args.seed)
+            except Exception as e:                          # a reported baseline must never cost the bench line
+                shoot["cpu_baseline"] = {"error": repr(e)}
 
     if rank == 0:
         out = {"metric": "volume-gather rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
