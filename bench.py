@@ -127,6 +127,7 @@ def run_reference(args, cfg, W, scene):
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     kind = "reference" if os.path.exists(harness) and cfg["grid"] else "port"
     times = []
+    shoot_ref = None
     if kind == "reference":
         from cs348b_pbrt_b200 import sceneio, scenes
         with tempfile.TemporaryDirectory() as tmp:
@@ -153,6 +154,19 @@ def run_reference(args, cfg, W, scene):
             times = [float(t) for _, t, _ in found][args.warmup:]
             if found:
                 threads = int(found[-1][2])
+            # the reference's own multi-threaded photon shooting (PhotonShootingTask x cores, core/photonshooter.cpp:232-357) in the same
+            # scene with the parameters of the GPU arm's shooting sample: the `shoot` rates' reference counterpart
+            if args.cpu_shoot_photons > 0:
+                pbrt2 = os.path.join(tmp, "shoot.pbrt")
+                open(pbrt2, "w").write(scenes.cornell_pbrt(scenes.grid_volume_text(32, scenes.blob_density(32)), args.cpu_shoot_photons,
+                                                           stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], shoot_step=0.05))
+                o2 = subprocess.run([harness, pbrt2, "--ncores", str(threads), "--grid-file", str(cfg["grid"]), dens, "--shoot"],
+                                    capture_output=True, text=True)
+                m = re.search(r"shot: nshot=(\d+) volume=(\d+) .*tasks=(\d+) seconds=([0-9.]+)", o2.stderr)
+                if o2.returncode == 0 and m and float(m.group(4)) > 0:
+                    nshot, nvol, ntask, sec = int(m.group(1)), int(m.group(2)), int(m.group(3)), float(m.group(4))
+                    shoot_ref = {"paths_per_s": nshot / sec, "photons_per_s": nvol / sec, "cores": ntask, "kind": "reference",
+                                 "sample": "%d volume photons from %d light paths, %.1f s (shooter stepsize 0.05, maxphotondepth 5)" % (nvol, nshot, sec)}
     if not times:
         kind = "port"
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -173,7 +187,7 @@ def run_reference(args, cfg, W, scene):
            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
                             "sample": "%d camera rays per step (every %d-th of the %d-ray frame), full %d-photon map in the reference's KdTree"
                                       % (nsample, max(1, len(rays) // nsample), len(rays), n_ph)},
-           "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+           "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "shoot": shoot_ref}
     print(json.dumps(out), flush=True)
 
 
