@@ -394,14 +394,18 @@ static void li(SamplerRenderer *ren, const Scene *scene, const std::string &rfn,
 
 // Li of whichever volume integrator the scene file names ("single", "emission" or "photonvolume"), one RNG(seed + i) per ray,
 // the scatter sample taken from the ray record: the golden of SURVEY.md 8(f)-4's SingleScatteringIntegrator / EmissionIntegrator
+// where the volume integrator of the scene keeps its two 1-D samples (valid once a Sample was built for it)
+static void volint_offsets(VolumeIntegrator *vi, int *scat, int *tau) {
+    if (SingleScatteringIntegrator *s = dynamic_cast<SingleScatteringIntegrator *>(vi)) { *scat = s->scatterSampleOffset; *tau = s->tauSampleOffset; }
+    else if (EmissionIntegrator *e = dynamic_cast<EmissionIntegrator *>(vi)) { *scat = e->scatterSampleOffset; *tau = e->tauSampleOffset; }
+    else if (PhotonVolumeIntegrator *v = dynamic_cast<PhotonVolumeIntegrator *>(vi)) { *scat = v->scatterSampleOffset; *tau = v->tauSampleOffset; }
+    else { fprintf(stderr, "unknown volume integrator\n"); exit(4); }
+}
 static void vli(SamplerRenderer *ren, const Scene *scene, const std::string &rfn, uint32_t seed, const std::string &ofn) {
     std::vector<pv_ray> rays = read_rays(rfn);
     int scat = -1, tau = -1;
     Sample *sample = new Sample(ren->sampler, ren->surfaceIntegrator, ren->volumeIntegrator, scene);
-    if (SingleScatteringIntegrator *s = dynamic_cast<SingleScatteringIntegrator *>(ren->volumeIntegrator)) { scat = s->scatterSampleOffset; tau = s->tauSampleOffset; }
-    else if (EmissionIntegrator *e = dynamic_cast<EmissionIntegrator *>(ren->volumeIntegrator)) { scat = e->scatterSampleOffset; tau = e->tauSampleOffset; }
-    else if (PhotonVolumeIntegrator *v = dynamic_cast<PhotonVolumeIntegrator *>(ren->volumeIntegrator)) { scat = v->scatterSampleOffset; tau = v->tauSampleOffset; }
-    else { fprintf(stderr, "--vli: unknown volume integrator\n"); exit(4); }
+    volint_offsets(ren->volumeIntegrator, &scat, &tau);
     FILE *o = xopen(ofn, "wb");
     write_header(o, "PVLI0001", rays.size());
     MemoryArena arena;
@@ -442,14 +446,16 @@ public:
     LiTask(SamplerRenderer *r, const Scene *sc, const std::vector<pv_ray> *ry, size_t b, size_t e, uint32_t sd, float *o, Sample *orig)
         : ren(r), scene(sc), rays(ry), begin(b), end(e), seed(sd), out(o), origSample(orig) {}
     void Run() {
-        PhotonVolumeIntegrator *vi = dynamic_cast<PhotonVolumeIntegrator *>(ren->volumeIntegrator);
+        VolumeIntegrator *vi = ren->volumeIntegrator;          // photonvolume, single or emission: whichever the scene file names
+        int scat = -1, tau = -1;
+        volint_offsets(vi, &scat, &tau);
         Sample *sample = origSample->Duplicate(1);
         MemoryArena arena;
         for (size_t i = begin; i < end; ++i) {
             RayDifferential r(to_ray((*rays)[i]));
             RNG rng(seed + (uint32_t)i);
-            sample->oneD[vi->scatterSampleOffset][0] = (*rays)[i].u_scatter;
-            sample->oneD[vi->tauSampleOffset][0] = 0.5f;
+            sample->oneD[scat][0] = (*rays)[i].u_scatter;
+            sample->oneD[tau][0] = 0.5f;
             Spectrum T(1.f);
             Spectrum L = vi->Li(scene, ren, r, sample, rng, &T, arena);
             memcpy(out + 60 * i, L.c, 30 * sizeof(float)); memcpy(out + 60 * i + 30, T.c, 30 * sizeof(float));

@@ -18,3 +18,4 @@ python bench.py --workload config2 --steps 5 --warmup 3 --shoot-photons 0 --maps
 # thread-per-ray recurrence kernel (the first timed "single" launch)
 python tools/volint_bench.py > gpurun_out/${tag}_volint_bench.jsonl 2> gpurun_out/${tag}_volint_bench.err
 ncu --set full --clock-control none --import-source on -k regex:volint_thread_kernel --launch-skip 3 -c 1 -o gpurun_out/${tag}_volint -f python tools/volint_bench.py --no-cpu --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_volint.log 2>&1
+python tools/volint_bench.py --impl reference > gpurun_out/${tag}_volint_ref.jsonl 2> gpurun_out/${tag}_volint_ref.err     # the reference's own classes on the box's host cores

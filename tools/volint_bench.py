@@ -21,12 +21,51 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 
+def run_reference(args, cfg, scene, rays):
+    """The reference's own classes and pthread task system over a sample of the frame (CPU only; needs oracle/_ref/ref_harness)."""
+    import re
+    import subprocess
+    import tempfile
+    from cs348b_pbrt_b200 import sceneio, scenes
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    sub = np.ascontiguousarray(rays[::args.ref_stride])
+    threads = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        dens = os.path.join(tmp, "density.raw"); scene.density.astype(np.float32).tofile(dens)
+        rf = os.path.join(tmp, "rays.bin"); sceneio.write_rays(rf, sub)
+        for kind in ("single", "emission"):
+            # the same medium as load_scene()'s (sigma_a 1, sigma_s 2, g 0.3) made emitting like the GPU arm's (Le 0.3 per bin would need
+            # a spectrum; the grey "color Le" is close and the emission term costs the same)
+            vol = scenes.grid_volume_text(32, scenes.blob_density(32)).replace('"float g"', '"color Le" [.3 .3 .3] "float g"')
+            pbrt = os.path.join(tmp, kind + ".pbrt")
+            open(pbrt, "w").write(scenes.volint_pbrt(kind, vol, stepsize=cfg["stepsize"]))
+            ops = ["--ncores", str(threads), "--grid-file", str(cfg["grid"]), dens]
+            for it in range(args.warmup + args.steps):
+                ops += ["--li-parallel", rf, str(1000 + it), "-"]
+            out = subprocess.run([harness, pbrt] + ops, capture_output=True, text=True)
+            if out.returncode != 0:
+                raise RuntimeError("ref_harness failed: " + out.stderr[-2000:])
+            found = re.findall(r"li-parallel: (\d+) rays in ([0-9.]+) s on (\d+) cores", out.stderr)
+            times = [float(t) for _, t, _ in found][args.warmup:]
+            val = len(sub) * len(times) / sum(times)
+            print(json.dumps({"impl": "reference", "metric": "volume-integrator rays/s", "integrator": kind, "value": val, "unit": "rays/s",
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                              "config": {"workload": cfg["label"] + " (scene shape only)", "xres": cfg["xres"], "yres": cfg["yres"], "grid": cfg["grid"],
+                                         "stepsize": cfg["stepsize"]},
+                              "cpu_baseline": {"value": val, "unit": "rays/s", "cores": int(found[-1][2]), "kind": "reference",
+                                               "sample": "every %d-th camera ray of the frame (%d rays) per step" % (args.ref_stride, len(sub))}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="config3")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"],
+                    help="reference: the UNMODIFIED reference's SingleScatteringIntegrator / EmissionIntegrator on all host cores "
+                         "(oracle/_ref/ref_harness --li-parallel), same scene, every --ref-stride-th ray of the frame")
+    ap.add_argument("--ref-stride", type=int, default=5)
     args = ap.parse_args()
     pkg = load_package()
     from cs348b_pbrt_b200 import workloads as W
@@ -36,6 +75,8 @@ def main():
         scene.medium.le[b] = 0.3
     rays, _ = W.frame_rays(cfg)
     n = len(rays)
+    if args.impl == "reference":
+        return run_reference(args, cfg, scene, rays)
     peak = 6454.9
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
