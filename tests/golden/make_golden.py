@@ -271,6 +271,19 @@ def volint_goldens(tmp):
     run(f, "--export-medium", os.path.join(HERE, "volint_offpath_medium.scn"), "--vli", rf, 4000, os.path.join(tmp, "vli.bin"))
     li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
     out["volint_offpath_emission_L"], out["volint_offpath_emission_T"] = li[:, 0], li[:, 1]
+    # edge-case rays (CPU oracle pin only): origins inside and outside the medium, non-unit and axis-aligned directions, finite
+    # extents, mint > 0, rays that only graze or miss the box, zero-length medium intervals
+    erays = aggregate_test_rays(96, 29, (-1.6, 1.6))
+    erays["u_scatter"] = np.random.default_rng(31).random(len(erays)).astype(np.float32)
+    erays["o"][:4] = np.float32([[-1, 0.2, -3], [1, -0.3, -3], [0.5, 1, -3], [0, 0, -1]]); erays["d"][:4] = np.float32([0, 0, 1])   # along faces / from a face
+    erays["mint"][:4] = 0; erays["maxt"][:4] = np.float32([np.inf, np.inf, np.inf, 0.0])
+    out["edge_rays"] = erays
+    ef = os.path.join(tmp, "volint_edge_rays.bin"); sceneio.write_rays(ef, erays)
+    for name in ("volint_homog", "volint_grid"):
+        for kind in ("single", "emission"):
+            run(os.path.join(tmp, "%s_%s.pbrt" % (name, kind)), "--vli", ef, 5000, os.path.join(tmp, "vli.bin"))
+            li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
+            out["edge_%s_%s_L" % (name, kind)], out["edge_%s_%s_T" % (name, kind)] = li[:, 0], li[:, 1]
     out["mt_seed"] = np.array([4000], np.uint32)
     np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
     # end-to-end images of the unmodified reference binary (glass wedge: specular bounces call the volume integrator per ray)

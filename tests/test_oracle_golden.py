@@ -244,3 +244,22 @@ def test_emission_li_on_a_medium_only_export_matches_reference(golden, pkg):
     L, T, _ = O.volume_li(scene, g["rays"], 0.05, O.EMISSION, rng_mode=O.MT, mt_seed=int(g["mt_seed"][0]))
     assert (g["volint_offpath_emission_L"] > 0).any()
     assert np.array_equal(L, g["volint_offpath_emission_L"]) and np.array_equal(T, g["volint_offpath_emission_T"])
+
+
+@pytest.mark.parametrize("kind", ["single", "emission"])
+@pytest.mark.parametrize("name", ["volint_homog", "volint_grid"])
+def test_single_and_emission_li_edge_case_rays_match_reference(golden, pkg, name, kind):
+    """Rays a camera never makes: origins inside the medium, non-unit and axis-aligned directions, finite extents, mint > 0, rays
+    along a face of the medium box, a zero-length ray -- the oracle (MT replay, RNG(5000 + i)) against the reference, bit for bit."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    scene = pkg.sceneio.read_scene(os.path.join(GOLDEN, name + ".scn"))
+    L, T, _ = O.volume_li(scene, g["edge_rays"], float(g[name + "_stepsize"][0]), O.SINGLE if kind == "single" else O.EMISSION,
+                          rng_mode=O.MT, mt_seed=5000)
+    refL, refT = g["edge_%s_%s_L" % (name, kind)], g["edge_%s_%s_T" % (name, kind)]
+    assert (refL > 0).any() and (refT == 1).all(axis=1).any()             # some rays march, some miss the medium altogether
+    assert np.array_equal(np.isnan(L), np.isnan(refL))
+    ok = ~np.isnan(refL)
+    assert relerr(T[ok], refT[ok]).max() < 1e-6 and relerr(L[ok], refL[ok])[refL[ok] > 0].max() < 1e-5
+    assert np.array_equal(L[ok] == 0, refL[ok] == 0)
