@@ -311,12 +311,64 @@ static spec med_tau(const pv_medium *m, v3 o, v3 d, float mint, float maxt, floa
 }
 static spec s_exp_neg(const spec *tau) { spec r; for (int i = 0; i < NS; ++i) r.c[i] = expf(-tau->c[i]); return r; }
 
+/* ---------------------------------------------------------------- AggregateVolume (core/volume.cpp:178-261)
+ * What core/api.cpp:1200-1205 builds when a scene file has more than one Volume.  pv_scene_desc carries ONE medium (the device
+ * path has no aggregate yet), so the further regions are handed to the oracle on the side: region 0 is
+ * sc->medium, regions 1.. are pvo_set_more_media()'s.  With no further regions every vol_* below IS the single-medium
+ * function (a scene with one Volume is never wrapped in an AggregateVolume). */
+static const pv_medium *g_more_media = NULL;
+static uint32_t g_n_more = 0;
+void pvo_set_more_media(const pv_medium *more, uint32_t n) { g_more_media = n ? more : NULL; g_n_more = more ? n : 0; }
+enum { SEL_A = 0, SEL_S = 1, SEL_LE = 2 };
+static inline const float *med_sel(const pv_medium *m, int sel) { return sel == SEL_A ? m->sigma_a : (sel == SEL_S ? m->sigma_s : m->le); }
+static inline const pv_medium *vol_region(const pv_scene_desc *sc, uint32_t k) { return k == 0 ? sc->medium : &g_more_media[k - 1]; }
+static int vol_intersectp(const pv_scene_desc *sc, v3 o, v3 d, float mint, float maxt, float *t0, float *t1) {   /* :238-250 */
+    if (!g_n_more) return med_intersectp(sc->medium, o, d, mint, maxt, t0, t1);
+    *t0 = INFINITY; *t1 = -INFINITY;
+    for (uint32_t k = 0; k <= g_n_more; ++k) {
+        float tr0, tr1;
+        if (med_intersectp(vol_region(sc, k), o, d, mint, maxt, &tr0, &tr1)) { *t0 = *t0 < tr0 ? *t0 : tr0; *t1 = *t1 > tr1 ? *t1 : tr1; }
+    }
+    return *t0 < *t1;
+}
+static spec vol_sigma(const pv_scene_desc *sc, int sel, v3 p, med_counters *mc) {                                  /* :185-207 */
+    if (!g_n_more) return med_sigma(sc->medium, med_sel(sc->medium, sel), p, mc);
+    spec s = s_const(0.f);
+    for (uint32_t k = 0; k <= g_n_more; ++k) {
+        const pv_medium *m = vol_region(sc, k);
+        spec r = med_sigma(m, med_sel(m, sel), p, mc);
+        for (int i = 0; i < NS; ++i) s.c[i] += r.c[i];
+    }
+    return s;
+}
+static float vol_p(const pv_scene_desc *sc, v3 p, v3 w, v3 wp) {                                                  /* :210-219 */
+    if (!g_n_more) return med_p(sc->medium, p, w, wp);
+    float ph = 0, sumWt = 0;
+    for (uint32_t k = 0; k <= g_n_more; ++k) {
+        const pv_medium *m = vol_region(sc, k);
+        spec ss = med_sigma(m, m->sigma_s, p, NULL);
+        float wt = s_y(sc, &ss);
+        sumWt += wt;
+        ph += wt * med_p(m, p, w, wp);
+    }
+    return ph / sumWt;
+}
+static spec vol_tau(const pv_scene_desc *sc, v3 o, v3 d, float mint, float maxt, float stepSize, float u, med_counters *mc) {   /* :230-235 */
+    if (!g_n_more) return med_tau(sc->medium, o, d, mint, maxt, stepSize, u, mc);
+    spec t = s_const(0.f);
+    for (uint32_t k = 0; k <= g_n_more; ++k) {
+        spec r = med_tau(vol_region(sc, k), o, d, mint, maxt, stepSize, u, mc);
+        for (int i = 0; i < NS; ++i) t.c[i] += r.c[i];
+    }
+    return t;
+}
+
 int pvo_transmittance(const pv_scene_desc *sc, const pv_ray *rays, uint64_t n, float step, const float *offset_u, float *T) {
     for (uint64_t i = 0; i < n; ++i) {
         spec tr = s_const(1.f);
         if (sc->medium && sc->medium->type != PV_MEDIUM_NONE) {
             const pv_ray *r = &rays[i];
-            spec tau = med_tau(sc->medium, V(r->o[0], r->o[1], r->o[2]), V(r->d[0], r->d[1], r->d[2]), r->mint, r->maxt,
+            spec tau = vol_tau(sc, V(r->o[0], r->o[1], r->o[2]), V(r->d[0], r->d[1], r->d[2]), r->mint, r->maxt,
                                step, offset_u ? offset_u[i] : 0.5f, NULL);
             tr = s_exp_neg(&tau);
         }
@@ -676,7 +728,6 @@ static spec lphoton(const pv_scene_desc *sc, const pvo_kdtree *t, const float *w
     int nFound = (int)pr.nFound;
     if (st) { st->lookups++; st->photons_found += pr.nFound; if (pr.nFound == nLookup) st->heap_lookups++; }
     if (nFound < 10) return L;
-    const pv_medium *m = sc->medium;
     spec totalFlux = s_const(0.f);
     float maxmd = 0.0f;
     v3 nw = vneg(w);
@@ -685,13 +736,13 @@ static spec lphoton(const pv_scene_desc *sc, const pvo_kdtree *t, const float *w
         float distSq = buf[i].d2;
         if (distSq > maxmd) maxmd = distSq;
         v3 pwi = V(wi[3 * (size_t)orig], wi[3 * (size_t)orig + 1], wi[3 * (size_t)orig + 2]);
-        float ph = med_p(m, t->nodePos[node], pwi, nw);
+        float ph = vol_p(sc, t->nodePos[node], pwi, nw);
         const float *a = alpha + NS * (size_t)orig;
         for (int b = 0; b < NS; ++b) totalFlux.c[b] += a[b] * ph;
     }
     float distSq = maxmd;
     float dV = distSq * sqrtf(distSq);
-    spec scale = med_sigma(m, m->sigma_s, pt, NULL);
+    spec scale = vol_sigma(sc, SEL_S, pt, NULL);
     if (dV != 0.0 && !s_black(&scale)) {
         float f = (float)(4.0 / 3.0 * (double)PI_F * (double)dV);      /* double expr, converted at `float * Spectrum` */
         for (int b = 0; b < NS; ++b) L.c[b] += totalFlux.c[b] / (scale.c[b] * f);
@@ -779,11 +830,11 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
     v3 ro = V(ray->o[0], ray->o[1], ray->o[2]), rd = V(ray->d[0], ray->d[1], ray->d[2]);
     float t0, t1;
     if (st) st->rays++;
-    if (!vr || vr->type == PV_MEDIUM_NONE || !med_intersectp(vr, ro, rd, ray->mint, ray->maxt, &t0, &t1) || (t1 - t0) == 0.f) {
+    if (!vr || vr->type == PV_MEDIUM_NONE || !vol_intersectp(sc, ro, rd, ray->mint, ray->maxt, &t0, &t1) || (t1 - t0) == 0.f) {
         memcpy(Tout, Tr.c, sizeof(Tr.c)); memcpy(Lout, Lv.c, sizeof(Lv.c));
         return;
     }
-    int rainbow = vr->type == PV_MEDIUM_RAINBOW;
+    int rainbow = vr->type == PV_MEDIUM_RAINBOW && !g_n_more;      /* dynamic_cast<RainbowVolume*> of an AggregateVolume is NULL */
     float stepSize = prm->stepsize;
     int nSamples = (int)ceilf((t1 - t0) / stepSize);
     float step = (t1 - t0) / nSamples;
@@ -831,7 +882,7 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
         pPrev = p;
         p = ray_at(ro, rd, t0);
         float u_tau = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[0]);
-        spec stepTau = med_tau(vr, pPrev, vsub(p, pPrev), 0.f, 1.f, .5f * stepSize, u_tau, &mc);
+        spec stepTau = vol_tau(sc, pPrev, vsub(p, pPrev), 0.f, 1.f, .5f * stepSize, u_tau, &mc);
         Tr = s_exp_neg(&stepTau);
         if (s_y(sc, &Tr) < 1e-3) {
             const float continueProb = .5f;
@@ -840,8 +891,8 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
             for (int b = 0; b < NS; ++b) Tr.c[b] /= continueProb;
         }
         spec L_i = s_const(0.f), L_d = s_const(0.f), L_ii = s_const(0.f);
-        spec ss = med_sigma(vr, vr->sigma_s, p, &mc);
-        spec sa = med_sigma(vr, vr->sigma_a, p, &mc);
+        spec ss = vol_sigma(sc, SEL_S, p, &mc);
+        spec sa = vol_sigma(sc, SEL_A, p, &mc);
         if (!s_black(&ss) && nLights > 0 && !(prm->flags & PV_GATHER_NO_DIRECT)) {
             float u_l = rng_mode == PVO_RNG_MT ? lightNum[i]
                         : pv_van_der_corput(pv_permute((uint32_t)i, (uint32_t)nSamples, permkey), scramble);
@@ -855,7 +906,7 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
                     /* vis.Transmittance -> PhotonVolumeIntegrator::Transmittance(sample=NULL): step 4*stepSize, offset RandomFloat */
                     float u_sh = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[2]);
-                    spec tau = med_tau(vr, vis.o, vis.d, vis.mint, vis.maxt, 4.f * stepSize, u_sh, &mc);
+                    spec tau = vol_tau(sc, vis.o, vis.d, vis.mint, vis.maxt, 4.f * stepSize, u_sh, &mc);
                     spec Ld;
                     for (int b = 0; b < NS; ++b) Ld.c[b] = L.c[b] * expf(-tau.c[b]);
                     if (rainbow) {
@@ -891,7 +942,7 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
                             for (int b = 0; b < NS; ++b) L_d.c[b] = (Ld.c[b] * mistI + rb.c[b] * rainbowI) * I;
                         }
                     } else {
-                        float ph = med_p(vr, p, w, vneg(wo));
+                        float ph = vol_p(sc, p, w, vneg(wo));
                         for (int b = 0; b < NS; ++b) L_d.c[b] = ((Ld.c[b] * ph) * (float)nLights) / pdf;
                     }
                 }
@@ -905,7 +956,7 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
             for (int b = 0; b < NS; ++b) L_i.c[b] = L_d.c[b] + (ss.c[b] / (sa.c[b] + ss.c[b])) * L_ii.c[b];
         } else L_i = L_d;
         /* Lve */
-        spec lve = med_sigma(vr, vr->le, p, &mc);
+        spec lve = vol_sigma(sc, SEL_LE, p, &mc);
         for (int b = 0; b < NS; ++b)
             Lv.c[b] = ((sa.c[b] * lve.c[b]) * step) + ((ss.c[b] * L_i.c[b]) * step) + (Tr.c[b] * Lv.c[b]);
     }
@@ -980,7 +1031,7 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
     v3 ro = V(ray->o[0], ray->o[1], ray->o[2]), rd = V(ray->d[0], ray->d[1], ray->d[2]);
     float t0, t1;
     if (st) st->rays++;
-    if (!vr || vr->type == PV_MEDIUM_NONE || !med_intersectp(vr, ro, rd, ray->mint, ray->maxt, &t0, &t1) || (t1 - t0) == 0.f) {
+    if (!vr || vr->type == PV_MEDIUM_NONE || !vol_intersectp(sc, ro, rd, ray->mint, ray->maxt, &t0, &t1) || (t1 - t0) == 0.f) {
         memcpy(Tout, Tr.c, sizeof(Tr.c)); memcpy(Lout, Lv.c, sizeof(Lv.c));
         return;
     }
@@ -1028,7 +1079,7 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
         pPrev = p;
         p = ray_at(ro, rd, t0);
         float u_tau = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[0]);
-        spec stepTau = med_tau(vr, pPrev, vsub(p, pPrev), 0.f, 1.f, .5f * stepSize, u_tau, &mc);
+        spec stepTau = vol_tau(sc, pPrev, vsub(p, pPrev), 0.f, 1.f, .5f * stepSize, u_tau, &mc);
         for (int b = 0; b < NS; ++b) Tr.c[b] *= expf(-stepTau.c[b]);
         if (s_y(sc, &Tr) < 1e-3) {
             const float continueProb = .5f;
@@ -1036,10 +1087,10 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
             if (u_rr > continueProb) { Tr = s_const(0.f); break; }
             for (int b = 0; b < NS; ++b) Tr.c[b] /= continueProb;
         }
-        spec lve = med_sigma(vr, vr->le, p, &mc);
+        spec lve = vol_sigma(sc, SEL_LE, p, &mc);
         for (int b = 0; b < NS; ++b) Lv.c[b] += Tr.c[b] * lve.c[b];
         if (!single) continue;
-        spec ss = med_sigma(vr, vr->sigma_s, p, &mc);
+        spec ss = vol_sigma(sc, SEL_S, p, &mc);
         if (!s_black(&ss) && nLights > 0) {
             float u_l = rng_mode == PVO_RNG_MT ? lightNum[i]
                         : pv_van_der_corput(pv_permute((uint32_t)i, (uint32_t)nSamples, permkey), scramble);
@@ -1053,8 +1104,8 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
                     /* vis.Transmittance -> SingleScatteringIntegrator::Transmittance(sample = NULL): step 4 * stepSize (single.cpp:55-58) */
                     float u_sh = rng_mode == PVO_RNG_MT ? pv_u32_to_float(mt_next(&rg.mt)) : pv_u32_to_float(wds[2]);
-                    spec tau = med_tau(vr, vis.o, vis.d, vis.mint, vis.maxt, 4.f * stepSize, u_sh, &mc);
-                    float ph = med_p(vr, p, w, vneg(wo));
+                    spec tau = vol_tau(sc, vis.o, vis.d, vis.mint, vis.maxt, 4.f * stepSize, u_sh, &mc);
+                    float ph = vol_p(sc, p, w, vneg(wo));
                     for (int b = 0; b < NS; ++b) {
                         float Ld = L.c[b] * expf(-tau.c[b]);
                         Lv.c[b] += ((((Tr.c[b] * ss.c[b]) * ph) * Ld) * (float)nLights) / pdf;
@@ -1126,9 +1177,8 @@ typedef struct { v3 o, d; float mint, maxt; } ray_t;
 
 /* renderer->Transmittance(scene, ray, NULL, rng) -> photonvolume.cpp:15-30 with sample == NULL */
 static spec shoot_transmittance(shoot_ctx *c, const ray_t *r) {
-    const pv_medium *vr = c->sc->medium;
     float offset = st_float(c->rng);
-    spec tau = med_tau(vr, r->o, r->d, r->mint, r->maxt, 4.f * c->prm->integrator_stepsize, offset, &c->mc);
+    spec tau = vol_tau(c->sc, r->o, r->d, r->mint, r->maxt, 4.f * c->prm->integrator_stepsize, offset, &c->mc);
     return s_exp_neg(&tau);
 }
 
@@ -1174,7 +1224,6 @@ static void make_isect(const pv_scene_desc *sc, int prim, v3 o, v3 d, float t, i
 
 static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, spec alpha, int nIntersections, int specularPath) {
     const pv_scene_desc *sc = c->sc;
-    const pv_medium *vr = sc->medium;
     float thit = photonRay.maxt;
     c->segments++;
     int prim = bvh_intersect(sc, photonRay.o, photonRay.d, photonRay.mint, &thit, &c->bc);
@@ -1187,7 +1236,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
     if (length == 0.f) return;
     v3 rnd = vdiv(photonRay.d, length);
     float rn_mint = photonRay.mint * length, rn_maxt = photonRay.maxt * length;
-    if (!med_intersectp(vr, photonRay.o, rnd, rn_mint, rn_maxt, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
+    if (!vol_intersectp(sc, photonRay.o, rnd, rn_mint, rn_maxt, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
     t0 += st_float(c->rng) * c->prm->stepsize;
     float t_i = t0;
     float xi = st_float(c->rng);
@@ -1200,8 +1249,8 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
     }
     if (interaction) {
         v3 interactPt = ray_at(photonRay.o, rnd, t0);
-        spec sig_s = med_sigma(vr, vr->sigma_s, interactPt, &c->mc);
-        spec sig_a = med_sigma(vr, vr->sigma_a, interactPt, &c->mc);
+        spec sig_s = vol_sigma(sc, SEL_S, interactPt, &c->mc);
+        spec sig_a = vol_sigma(sc, SEL_A, interactPt, &c->mc);
         float ys = s_y(sc, &sig_s), ya = s_y(sc, &sig_a);
         int scatter = (st_float(c->rng) > (ys) / (ya + ys));     /* Q1: inverted test, photonshooter.cpp:88 */
         if (!scatter) return;
@@ -1215,7 +1264,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         float u2 = st_float(c->rng);
         v3 direction = uniform_sample_sphere(u1, u2);
         float pdf = 1.f / (4.f * PI_F);
-        float ref = med_p(vr, interactPt, rnd, direction);
+        float ref = vol_p(sc, interactPt, rnd, direction);
         if (ref == 0.f || pdf == 0.f) return;
         for (int b = 0; b < NS; ++b) alpha.c[b] *= ref;
         for (int b = 0; b < NS; ++b) alpha.c[b] /= pdf;
@@ -1740,7 +1789,7 @@ int pvo_final_gather(const pv_scene_desc *sc, const float *rp_pos, const float *
                 if (sc->medium && sc->medium->type != PV_MEDIUM_NONE) {
                     uint32_t w[4]; uint64_t ri = index_base + i;
                     pv_philox4x32_10((uint32_t)ri, (uint32_t)(ri >> 32), 0u, PV_RNG_FINAL_GATHER, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-                    spec tau = med_tau(sc->medium, o, d, r->mint, thit, step, pv_u32_to_float(w[0]), NULL);
+                    spec tau = vol_tau(sc, o, d, r->mint, thit, step, pv_u32_to_float(w[0]), NULL);
                     T = s_exp_neg(&tau);
                 }
                 for (int b = 0; b < NS; ++b) L.c[b] = rp_Lo[NS * (size_t)bi + b] * T.c[b];

@@ -64,6 +64,12 @@ int pvo_gather(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi,
                const pv_gather_params *prm, int rng_mode, uint32_t mt_seed,
                int nthreads, float *L, float *T, pv_gather_stats *stats);
 
+/* AggregateVolume (core/volume.cpp:178-261; what the reference builds for a scene with several Volume statements).
+ * pv_scene_desc carries one medium -- the device path has no aggregate yet -- so the regions after the
+ * first are handed to the oracle on the side; every function below then sees the aggregate.  (NULL, 0) switches it off.
+ * Not thread-safe with respect to the other calls: set it, call, reset it. */
+void pvo_set_more_media(const pv_medium *more, uint32_t n);
+
 /* The reference's other two volume integrators: SingleScatteringIntegrator::Li
  * (integrators/single.cpp:66-138) and EmissionIntegrator::Li (integrators/emission.cpp:63-106).  Only
  * prm->stepsize / seed / ray_index_base are read.  PVO_RNG_MT seeds RNG(mt_seed + i) for ray i like
