@@ -260,6 +260,16 @@ def volint_offpath_pbrt(stepsize=0.05):
                                     'Shape "disk" "float radius" [0.3]\nAttributeEnd\nWorldEnd')
 
 
+def aggregate_volumes(n=32):
+    """Two overlapping Volume statements => the reference wraps them in an AggregateVolume (core/api.cpp:1200-1205,
+    core/volume.cpp:178-261): an emitting, forward-scattering homogeneous slab in the left part of the box and the emitting blob
+    grid squeezed into the right part; they share the slice -0.2 < x < 0.3."""
+    homog = ('Volume "homogeneous" "color sigma_a" [.3 .3 .3] "color sigma_s" [.15 .2 .25] "color Le" [.4 .2 .1] "float g" [0.4]\n'
+             '  "point p0" [-1 -1 -1] "point p1" [0.3 1 1]')
+    grid = volint_grid_volume(n).replace('"point p0" [-1 -1 -1]', '"point p0" [-0.2 -1 -1]')
+    return homog + "\n" + grid
+
+
 def volint_grid_volume(n=32):
     """Emitting, forward-scattering density grid (the config-3 blobs at n^3)."""
     return grid_volume_text(n, blob_density(n)).replace('"float g"', '"color Le" [.3 .3 .1] "float g"')

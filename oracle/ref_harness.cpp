@@ -512,7 +512,23 @@ void pbrtWorldEnd() {
     for (size_t i = 0; i < g_ops.size(); ++i) {
         const std::string &op = g_ops[i];
         #define ARG(k) (i + (k) < g_ops.size() ? g_ops[i + (k)] : (fprintf(stderr, "missing arg for %s\n", op.c_str()), exit(2), g_ops[0]))
-        if (op == "--export-medium") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err, true)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
+        if (op == "--export-regions") {
+            // an AggregateVolume (several Volume statements): the whole scene once per region, with that region as its only medium
+            // -> <prefix>.<i>.scn; the oracle takes region 0's file as the scene and the media of the others on the side
+            AggregateVolume *agg = dynamic_cast<AggregateVolume *>(scene->volumeRegion);
+            if (!agg) { fprintf(stderr, "--export-regions needs a scene with more than one Volume\n"); exit(4); }
+            Scene *sc = const_cast<Scene *>(scene);
+            for (size_t k = 0; k < agg->regions.size(); ++k) {
+                sc->volumeRegion = agg->regions[k];
+                PvHostScene hs; std::string err;
+                if (!pv_export_scene(sc, hs, err)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); }
+                std::ostringstream fn; fn << ARG(1) << "." << k << ".scn";
+                if (!pv_write_scene_file(hs, fn.str())) exit(3);
+            }
+            sc->volumeRegion = agg;
+            i += 1;
+        }
+        else if (op == "--export-medium") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err, true)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
         else if (op == "--export-scene") { PvHostScene hs; std::string err; if (!pv_export_scene(scene, hs, err)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); } if (!pv_write_scene_file(hs, ARG(1))) exit(3); i += 1; }
         else if (op == "--shoot") { shoot(sh, scene, sr->camera, sr); }
         else if (op == "--load-photons") { load_photons(ARG(1)); install_volume_map(sh); i += 1; }

@@ -284,6 +284,22 @@ def volint_goldens(tmp):
             run(os.path.join(tmp, "%s_%s.pbrt" % (name, kind)), "--vli", ef, 5000, os.path.join(tmp, "vli.bin"))
             li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
             out["edge_%s_%s_L" % (name, kind)], out["edge_%s_%s_T" % (name, kind)] = li[:, 0], li[:, 1]
+    # AggregateVolume: two overlapping Volume statements, point + spot light; the scene is exported once per region
+    agg = scenes.aggregate_volumes(32)
+    for kind in ("single", "emission"):
+        f = os.path.join(tmp, "volint_agg_%s.pbrt" % kind)
+        open(f, "w").write(scenes.volint_pbrt(kind, agg, stepsize=0.0625, second_light=True))
+        ops = ["--vli", rf, 4000, os.path.join(tmp, "vli.bin"), "--vli", ef, 5000, os.path.join(tmp, "vli_e.bin")]
+        if kind == "single":
+            ops = ["--export-regions", os.path.join(HERE, "volint_agg"), "--transmittance", rf, 77, os.path.join(tmp, "tr.bin")] + ops
+        run(f, *ops)
+        li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
+        out["volint_agg_%s_L" % kind], out["volint_agg_%s_T" % kind] = li[:, 0], li[:, 1]
+        li = sceneio.read_spectra(os.path.join(tmp, "vli_e.bin"), b"PVLI0001", per=2)
+        out["edge_volint_agg_%s_L" % kind], out["edge_volint_agg_%s_T" % kind] = li[:, 0], li[:, 1]
+    tr = np.frombuffer(open(os.path.join(tmp, "tr.bin"), "rb").read(), np.float32, count=len(rays) * 31, offset=16).reshape(len(rays), 31)
+    out["volint_agg_tr_u"], out["volint_agg_tr_T"] = tr[:, 0].copy(), tr[:, 1:].copy()
+    out["volint_agg_stepsize"] = np.array([0.0625], np.float32)
     out["mt_seed"] = np.array([4000], np.uint32)
     np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
     # end-to-end images of the unmodified reference binary (glass wedge: specular bounces call the volume integrator per ray)

@@ -118,6 +118,25 @@ def gather(scene, tree, wi, alpha, rays, stepsize, nused, maxdist, seed=0, ray_i
 SINGLE, EMISSION = 0, 1
 
 
+class more_media:
+    """AggregateVolume for the oracle (core/volume.cpp:178-261): `with more_media(scene_b, scene_c): ...` makes every oracle call
+    inside see the medium of the scene it is given PLUS the media of these scenes as one aggregate.  pv_scene_desc carries one
+    medium (the device path has no aggregate yet), so the further regions travel on the side."""
+
+    def __init__(self, *scenes):
+        self.scenes = scenes
+
+    def __enter__(self):
+        descs = [s.desc() for s in self.scenes]               # keeps the density pointers alive through the scenes
+        self.arr = (A.Medium * len(descs))(*[d.medium.contents for d in descs])
+        lib().pvo_set_more_media(self.arr, C.c_uint32(len(descs)))
+        return self
+
+    def __exit__(self, *exc):
+        lib().pvo_set_more_media(None, C.c_uint32(0))
+        return False
+
+
 def volume_li(scene, rays, stepsize, kind, seed=0, ray_index_base=0, rng_mode=PHILOX, mt_seed=0):
     """SingleScatteringIntegrator::Li / EmissionIntegrator::Li (integrators/single.cpp:66-138, emission.cpp:63-106)."""
     n = len(rays); rays = np.ascontiguousarray(rays)

@@ -263,3 +263,31 @@ def test_single_and_emission_li_edge_case_rays_match_reference(golden, pkg, name
     ok = ~np.isnan(refL)
     assert relerr(T[ok], refT[ok]).max() < 1e-6 and relerr(L[ok], refL[ok])[refL[ok] > 0].max() < 1e-5
     assert np.array_equal(L[ok] == 0, refL[ok] == 0)
+
+
+@pytest.mark.parametrize("kind", ["single", "emission"])
+def test_aggregate_volume_li_matches_reference(golden, pkg, kind):
+    """Two overlapping Volume statements (the reference wraps them in an AggregateVolume, core/volume.cpp:178-261: summed sigma / Lve /
+    tau, union of the intervals, sigma_s.y()-weighted phase function), point + spot light: the oracle with region 0 as the scene's
+    medium and region 1 handed over on the side replays the reference's SingleScatteringIntegrator / EmissionIntegrator (MT stream)
+    on the camera rays and on the edge-case rays.  Groundwork for the device path's aggregate."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    r0 = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_agg.0.scn"))
+    r1 = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_agg.1.scn"))
+    step = float(g["volint_agg_stepsize"][0])
+    with O.more_media(r1):
+        L, T, _ = O.volume_li(r0, g["rays"], step, O.SINGLE if kind == "single" else O.EMISSION, rng_mode=O.MT, mt_seed=4000)
+        Le, Te, _ = O.volume_li(r0, g["edge_rays"], step, O.SINGLE if kind == "single" else O.EMISSION, rng_mode=O.MT, mt_seed=5000)
+        Tr = O.transmittance(r0, g["rays"], 4.0 * step, g["volint_agg_tr_u"]) if kind == "single" else None
+    # ... and without the second region the answer is another one (the test would notice a lost region)
+    L1, _, _ = O.volume_li(r0, g["rays"], step, O.SINGLE if kind == "single" else O.EMISSION, rng_mode=O.MT, mt_seed=4000)
+    refL, refT = g["volint_agg_%s_L" % kind], g["volint_agg_%s_T" % kind]
+    assert (refL > 0).any() and not np.allclose(L1, refL, rtol=1e-3)
+    assert relerr(T, refT)[refT > 0].max() < 1e-5 and np.array_equal(T == 0, refT == 0)
+    assert relerr(L, refL)[refL > 0].max() < 1e-5 and np.array_equal(L == 0, refL == 0)
+    eL, eT = g["edge_volint_agg_%s_L" % kind], g["edge_volint_agg_%s_T" % kind]
+    assert relerr(Te, eT)[eT > 0].max() < 1e-5 and relerr(Le, eL)[eL > 0].max() < 1e-5 and np.array_equal(Le == 0, eL == 0)
+    if Tr is not None:
+        assert relerr(Tr, g["volint_agg_tr_T"]).max() < 1e-6
