@@ -76,13 +76,15 @@ def aggregate_test_rays(n, seed, bound=(-1.2, 1.2), target=None):
 
 
 def golden_for_scene(tmp, name, scene_file, nused, maxdist, stepsize, n_li_rays, li_res, knn_k_list, camera=None, box=(-1.0, 1.0),
-                     wanted=0, shoot_step=0.05, hit_bound=(-1.2, 1.2), hit_target=None, q_near_photons=False):
+                     wanted=0, shoot_step=0.05, hit_bound=(-1.2, 1.2), hit_target=None, q_near_photons=False, regions=False):
     out = {}
     camera = camera or {}
     scn = os.path.join(HERE, name + ".scn")
     pho = os.path.join(tmp, name + ".pho")
     stats = os.path.join(tmp, name + ".json")
-    run(scene_file, "--export-scene", scn, "--shoot", "--dump-photons", pho, "--stats", stats)
+    # regions: the scene has several Volume statements (AggregateVolume) -> one <name>.<i>.scn per region instead of <name>.scn
+    export = ["--export-regions", os.path.join(HERE, name)] if regions else ["--export-scene", scn]
+    run(scene_file, *export, "--shoot", "--dump-photons", pho, "--stats", stats)
     pos, wi, alpha = sceneio.read_photons(pho)
     st = json.load(open(stats))
     out["shot_pos"], out["shot_wi"], out["shot_alpha"] = pos, wi, alpha
@@ -179,6 +181,7 @@ def main():
         sphere_goldens(tmp)
         exponential_goldens(tmp)
         volint_goldens(tmp)
+        aggregate_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -322,6 +325,14 @@ def volint_goldens(tmp):
             name, lum(img).mean(), 100 * abs(lum(img).mean() - lum(img2).mean()) / lum(img).mean(), 100 * (np.abs(b1 - b2)[lit] / b1[lit]).mean()))
 
 
+def aggregate_goldens(tmp):
+    """The photon-volume path under an AggregateVolume (two overlapping Volume statements, core/volume.cpp:178-261): the reference's
+    photon list, k-NN sets, LPhoton, Li, transmittance, hits -- for the oracle now, for the device path's aggregate next."""
+    f = os.path.join(tmp, "cornell_agg.pbrt")
+    open(f, "w").write(scenes.cornell_pbrt(scenes.aggregate_volumes(32), 2500, stepsize=0.0625, nused=50, maxdist=0.25, shoot_step=0.05))
+    golden_for_scene(tmp, "cornell_agg", f, 50, 0.25, 0.0625, 64, 64, [(50, 0.25 ** 2)], wanted=2500, regions=True)
+
+
 def read_radiance(fn):
     """PVRADP01 (oracle/ref_harness.cpp --dump-maps): p[3] n[3] Lo[30] rho_r[30] rho_t[30] per radiance photon."""
     buf = open(fn, "rb").read()
@@ -394,6 +405,10 @@ if __name__ == "__main__":
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             exponential_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "aggregate":        # only the AggregateVolume goldens of the photon-volume path
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            aggregate_goldens(tmp_)
     elif len(sys.argv) > 1 and sys.argv[1] == "volint":           # only the single / emission integrator goldens
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:

@@ -291,3 +291,29 @@ def test_aggregate_volume_li_matches_reference(golden, pkg, kind):
     assert relerr(Te, eT)[eT > 0].max() < 1e-5 and relerr(Le, eL)[eL > 0].max() < 1e-5 and np.array_equal(Le == 0, eL == 0)
     if Tr is not None:
         assert relerr(Tr, g["volint_agg_tr_T"]).max() < 1e-6
+
+
+def test_photon_volume_path_under_an_aggregate_volume_matches_reference(golden, pkg):
+    """The whole photon-volume path with two overlapping Volume statements (AggregateVolume): the reference's photon list
+    (one task, MT stream) replayed exactly by the oracle's shooter, then LPhoton, Li (MT stream) and transmittance on that
+    list -- every medium access of the path goes through the aggregate (free-flight transmittance, scatter test with the
+    summed sigma, the weighted phase function in the scattering weight and in the radiance estimate)."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("cornell_agg")
+    r0 = pkg.sceneio.read_scene(os.path.join(GOLDEN, "cornell_agg.0.scn"))
+    r1 = pkg.sceneio.read_scene(os.path.join(GOLDEN, "cornell_agg.1.scn"))
+    nused, maxdist, stepsize, wanted, shoot_step = int(g["params"][0]), float(g["params"][1]), float(g["params"][2]), int(g["params"][3]), float(g["params"][4])
+    with O.more_media(r1):
+        res = O.shoot(r0, wanted, shoot_step, stepsize, rng_mode=O.MT)
+        tree = O.KdTree(g["shot_pos"])
+        Lp = O.lphoton(r0, tree, g["shot_wi"], g["shot_alpha"], g["q_pts"], g["q_w"], nused, maxdist)
+        L, T, st = O.gather(r0, tree, g["shot_wi"], g["shot_alpha"], g["li_rays"], stepsize, nused, maxdist, rng_mode=O.MT, mt_seed=1000)
+        Tr = O.transmittance(r0, g["li_rays"], 4.0 * stepsize, g["tr_u"])
+    assert res["rc"] == 0 and res["nshot"] == int(g["nshot"][0]) and res["n"] == len(g["shot_pos"])
+    assert np.abs(res["pos"] - g["shot_pos"]).max() < 1e-5 and np.abs(res["wi"] - g["shot_wi"]).max() < 1e-5
+    assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-5
+    ref = g["lphoton_L"]
+    assert (ref > 0).any() and relerr(Lp, ref)[ref > 0].max() < 2e-6 and np.array_equal(Lp == 0, ref == 0)
+    assert (g["li_L"] > 0).any() and relerr(T, g["li_T"]).max() < 1e-6 and relerr(L, g["li_L"])[g["li_L"] > 0].max() < 1e-5
+    assert relerr(Tr, g["tr_T"]).max() < 1e-6 and st.lookups > 0
