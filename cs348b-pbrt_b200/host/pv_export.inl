@@ -42,7 +42,12 @@ static inline void pv_mat_out(const Transform &t, float *dst) {
 // medium_only: export the volume region and nothing else (no geometry, no lights) -- all that EmissionIntegrator::Li reads
 // (integrators/emission.cpp:63-106); lets "emission", pbrt's DEFAULT volume integrator (core/api.cpp:211), run on the device in
 // scenes whose surfaces or lights are off this path (area lights, other shapes, other accelerators).
-static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err, bool medium_only = false) {
+// keep_unknown_lights (the golden-vector harness only, never the drop-in): a light the device path does not know keeps its
+// slot in the light list as a placeholder of type PV_LIGHT_UNKNOWN_SLOT (power filled in) instead of failing the export, so the
+// oracle can be given such lights on the side under the reference's own light indices (area lights).
+#define PV_LIGHT_UNKNOWN_SLOT 100
+static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err, bool medium_only = false,
+                            bool keep_unknown_lights = false) {
     BVHAccel *bvh = medium_only ? NULL : dynamic_cast<BVHAccel *>(scene->aggregate);
     if (!bvh && !medium_only) { err = "pv: the scene aggregate is not the \"bvh\" accelerator"; return false; }
     const uint32_t nPrims = bvh ? (uint32_t)bvh->primitives.size() : 0u;
@@ -134,7 +139,8 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             pl.type = PV_LIGHT_DISTANT;
             pl.dir[0] = d->lightDir.x; pl.dir[1] = d->lightDir.y; pl.dir[2] = d->lightDir.z;
             pv_spec_out(d->L, pl.intensity);
-        } else { err = "pv: unsupported light type (point, spot and distant lights are on this path)"; return false; }
+        } else if (keep_unknown_lights) pl.type = PV_LIGHT_UNKNOWN_SLOT;
+        else { err = "pv: unsupported light type (point, spot and distant lights are on this path)"; return false; }
         hs.lights.push_back(pl);
     }
     hs.has_medium = false;

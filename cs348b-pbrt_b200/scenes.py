@@ -270,6 +270,16 @@ def aggregate_volumes(n=32):
     return homog + "\n" + grid
 
 
+AREA_QUAD = ('AttributeBegin\nAreaLightSource "diffuse" "color L" [6 5 4]\n'
+             'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-0.4 0.9 -0.4  0.4 0.9 -0.4  0.4 0.9 0.4  -0.4 0.9 0.4]\nAttributeEnd')
+
+
+def volint_area_pbrt(kind="single", stepsize=0.05):
+    """The Cornell box with a DiffuseAreaLight (a downward-facing quad under the ceiling = a ShapeSet of two triangles) next to the
+    point light: groundwork for area lights on the device path."""
+    return volint_pbrt(kind, VOLINT_MEDIA["volint_homog"][0], stepsize=stepsize).replace("WorldEnd", AREA_QUAD + "\nWorldEnd")
+
+
 def volint_grid_volume(n=32):
     """Emitting, forward-scattering density grid (the config-3 blobs at n^3)."""
     return grid_volume_text(n, blob_density(n)).replace('"float g"', '"color Le" [.3 .3 .1] "float g"')

@@ -794,6 +794,91 @@ static spec light_sample_L_point(const pv_light *l, v3 p, v3 *wi, float *pdf, vi
     return L;
 }
 
+/* ---------------------------------------------------------------- DiffuseAreaLight over triangles (lights/diffuse.cpp:69-86,
+ * ShapeSet core/light.cpp:114-172, Shape::Pdf core/shape.cpp:86-99, Triangle::Sample shapes/trianglemesh.cpp:444-456)
+ * pv_light has no area-light fields yet: such a light keeps its slot in sc->lights[] as a placeholder of type
+ * PVO_LIGHT_SLOT and its data comes in on the side (pvo_set_area_lights).  Point-query sampling only (the direct term of the
+ * volume integrators); MT stream only (the Philox assignment of the three light-sample numbers is a device-side decision). */
+static const pvo_area_light *g_area = NULL;
+static uint32_t g_n_area = 0;
+void pvo_set_area_lights(const pvo_area_light *t, uint32_t n) { g_area = n ? t : NULL; g_n_area = t ? n : 0; }
+static const pvo_area_light *area_of(const pv_scene_desc *sc, const pv_light *l) {
+    uint32_t slot = (uint32_t)(l - sc->lights);
+    for (uint32_t i = 0; i < g_n_area; ++i) if (g_area[i].slot == slot) return &g_area[i];
+    return NULL;
+}
+static float tri_area(const float *tv) {                                /* shapes/trianglemesh.cpp:284-290 */
+    v3 p1 = V(tv[0], tv[1], tv[2]), p2 = V(tv[3], tv[4], tv[5]), p3 = V(tv[6], tv[7], tv[8]);
+    return 0.5f * vlen(vcross(vsub(p2, p1), vsub(p3, p1)));
+}
+/* Triangle::Intersect's DifferentialGeometry normal for default uvs (trianglemesh.cpp:160-205, core/diffgeom.cpp:40-55) */
+static v3 tri_dg_nn(const float *tv, uint32_t flags) {
+    v3 p1 = V(tv[0], tv[1], tv[2]), p2 = V(tv[3], tv[4], tv[5]), p3 = V(tv[6], tv[7], tv[8]);
+    float du1 = 0.f - 1.f, du2 = 1.f - 1.f, dv1 = 0.f - 1.f, dv2 = 0.f - 1.f;
+    v3 dp1 = vsub(p1, p3), dp2 = vsub(p2, p3);
+    float determinant = du1 * dv2 - dv1 * du2;
+    float invdet = 1.f / determinant;
+    v3 dpdu = vmul(vsub(vmul(dp1, dv2), vmul(dp2, dv1)), invdet);
+    v3 dpdv = vmul(vadd(vmul(dp1, -du2), vmul(dp2, du1)), invdet);
+    v3 nn = vnorm(vcross(dpdu, dpdv));
+    if (((flags & 1u) != 0) ^ ((flags & 2u) != 0)) nn = vmul(nn, -1.f);   /* ReverseOrientation ^ TransformSwapsHandedness */
+    return nn;
+}
+static spec area_sample_L(const pv_scene_desc *sc, const pv_light *l, v3 p, float uComp, float u0, float u1, v3 *wi, float *pdf, visray *vis) {
+    const pvo_area_light *al = area_of(sc, l);
+    spec L = s_const(0.f);
+    *pdf = 0.f; *wi = V(0, 0, 1); vis->o = p; vis->d = *wi; vis->mint = 0.f; vis->maxt = 0.f;
+    if (!al || !al->n_tris) return L;
+    const uint32_t n = al->n_tris;
+    /* ShapeSet's area distribution (core/light.cpp:129-136, Distribution1D core/montecarlo.h:55-107) */
+    float *area = (float *)malloc(sizeof(float) * n), *cdf = (float *)malloc(sizeof(float) * (n + 1));
+    float sumArea = 0.f;
+    for (uint32_t i = 0; i < n; ++i) { area[i] = tri_area(al->tri + 9 * (size_t)i); sumArea += area[i]; }
+    cdf[0] = 0.f;
+    for (uint32_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + area[i - 1] / n;
+    float funcInt = cdf[n];
+    if (funcInt == 0.f) for (uint32_t i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+    else for (uint32_t i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    int lo = 0, hi = (int)n + 1;                                          /* SampleDiscrete: upper_bound - 1 */
+    while (lo < hi) { int mid = (lo + hi) / 2; if (uComp < cdf[mid]) hi = mid; else lo = mid + 1; }
+    int sn = lo - 1; if (sn < 0) sn = 0;
+    /* Triangle::Sample(u1, u2, Ns) */
+    const float *tv = al->tri + 9 * (size_t)sn;
+    v3 p1 = V(tv[0], tv[1], tv[2]), p2 = V(tv[3], tv[4], tv[5]), p3 = V(tv[6], tv[7], tv[8]);
+    float su1 = sqrtf(u0), b1 = 1.f - su1, b2 = u1 * su1;
+    v3 pt = vadd(vadd(vmul(p1, b1), vmul(p2, b2)), vmul(p3, 1.f - b1 - b2));
+    v3 ns = vnorm(vcross(vsub(p2, p1), vsub(p3, p1)));
+    if (al->flags & 1u) ns = vmul(ns, -1.f);
+    /* ShapeSet::Sample(p, ls, Ns) (core/light.cpp:145-158): ONE ray against every shape, thit / dg of the LAST shape it hits */
+    v3 rdir = vsub(pt, p);
+    float thit = 1.f;
+    int anyHit = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        float t;
+        if (tri_hit(al->tri + 9 * (size_t)i, p, rdir, 1e-3f, INFINITY, &t)) { anyHit = 1; thit = t; ns = tri_dg_nn(al->tri + 9 * (size_t)i, al->flags); }
+    }
+    (void)anyHit;
+    v3 ps = ray_at(p, rdir, thit);
+    *wi = vnorm(vsub(ps, p));
+    /* ShapeSet::Pdf(p, wi) (:167-172) with Shape::Pdf (core/shape.cpp:86-99) */
+    float pdfsum = 0.f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float t;
+        if (!tri_hit(al->tri + 9 * (size_t)i, p, *wi, 1e-3f, INFINITY, &t)) continue;
+        v3 nn = tri_dg_nn(al->tri + 9 * (size_t)i, al->flags);
+        float pd = dist2(p, ray_at(p, *wi, t)) / (fabsf(vdot(nn, vneg(*wi))) * area[i]);
+        if (isinf(pd)) pd = 0.f;
+        pdfsum += area[i] * pd;
+    }
+    *pdf = pdfsum / sumArea;
+    /* visibility->SetSegment(p, pEpsilon = 0, ps, 1e-3f, time) (core/light.h:85-93) */
+    float dist = vlen(vsub(p, ps));
+    vis->o = p; vis->d = vdiv(vsub(ps, p), dist); vis->mint = 0.f; vis->maxt = dist * (1.f - 1e-3f);
+    if (vdot(ns, vneg(*wi)) > 0.f) L = s_load(al->Lemit);                  /* DiffuseAreaLight::L (lights/diffuse.h:51-53) */
+    free(area); free(cdf);
+    return L;
+}
+
 /* RainbowVolume::rainbowReflection volumes/rainbow.cpp:12-78 */
 static float lerp_transfer(float x, float x0, float x1, float y0, float y1) {
     if (x <= x0) return y0;
@@ -900,7 +985,13 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
             if (ln > nLights - 1) ln = nLights - 1;
             const pv_light *light = &sc->lights[ln];
             float pdf; visray vis; v3 wo;
-            spec L = light_sample_L_point(light, p, &wo, &pdf, &vis);
+            spec L = light->type == PVO_LIGHT_SLOT
+                         ? (rng_mode == PVO_RNG_MT ? area_sample_L(sc, light, p, /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]):
+                                                                   the component number is the THIRD argument (core/light.h) */
+                                                                   lightNum[2 * (size_t)nSamples + 2 * i + 1], lightNum[nSamples + i],
+                                                                   lightNum[2 * (size_t)nSamples + 2 * i], &wo, &pdf, &vis)
+                                                   : (pdf = 0.f, s_const(0.f)))
+                         : light_sample_L_point(light, p, &wo, &pdf, &vis);
             if (!s_black(&L) && pdf > 0.f) {
                 if (st) st->shadow_rays++;
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
@@ -1098,7 +1189,13 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
             if (ln > nLights - 1) ln = nLights - 1;
             const pv_light *light = &sc->lights[ln];
             float pdf; visray vis; v3 wo;
-            spec L = light_sample_L_point(light, p, &wo, &pdf, &vis);
+            spec L = light->type == PVO_LIGHT_SLOT
+                         ? (rng_mode == PVO_RNG_MT ? area_sample_L(sc, light, p, /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]):
+                                                                   the component number is the THIRD argument (core/light.h) */
+                                                                   lightNum[2 * (size_t)nSamples + 2 * i + 1], lightNum[nSamples + i],
+                                                                   lightNum[2 * (size_t)nSamples + 2 * i], &wo, &pdf, &vis)
+                                                   : (pdf = 0.f, s_const(0.f)))
+                         : light_sample_L_point(light, p, &wo, &pdf, &vis);
             if (!s_black(&L) && pdf > 0.f) {
                 if (st) st->shadow_rays++;
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {

@@ -70,6 +70,21 @@ int pvo_gather(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi,
  * Not thread-safe with respect to the other calls: set it, call, reset it. */
 void pvo_set_more_media(const pv_medium *more, uint32_t n);
 
+/* DiffuseAreaLight over a triangle mesh (lights/diffuse.cpp, ShapeSet core/light.cpp:114-172), groundwork for DESIGN.md 11.2.
+ * pv_light has no area-light fields yet: the light keeps its slot in sc->lights[] as a placeholder of type PVO_LIGHT_SLOT
+ * (what oracle/ref_harness --export-area-lights writes) and its data is handed over here.  Covered: the point-query
+ * Sample_L of the volume integrators' direct term, with the reference's MT stream. */
+#define PVO_LIGHT_SLOT 100
+typedef struct pvo_area_light {
+    uint32_t slot;            /* index in the scene's light list */
+    uint32_t n_tris;
+    uint32_t flags;           /* 1 = ReverseOrientation, 2 = TransformSwapsHandedness */
+    uint32_t pad;
+    const float *tri;         /* 9 floats per triangle, world space, in the ShapeSet's (refine) order */
+    float Lemit[30];
+} pvo_area_light;
+void pvo_set_area_lights(const pvo_area_light *lights, uint32_t n);
+
 /* The reference's other two volume integrators: SingleScatteringIntegrator::Li
  * (integrators/single.cpp:66-138) and EmissionIntegrator::Li (integrators/emission.cpp:63-106).  Only
  * prm->stepsize / seed / ray_index_base are read.  PVO_RNG_MT seeds RNG(mt_seed + i) for ray i like

@@ -56,6 +56,7 @@
 #include "lights/point.h"
 #include "lights/spot.h"
 #include "lights/distant.h"
+#include "lights/diffuse.h"
 #include "volumes/homogeneous.h"
 #include "volumes/volumegrid.h"
 #include "volumes/exponential.h"
@@ -512,7 +513,35 @@ void pbrtWorldEnd() {
     for (size_t i = 0; i < g_ops.size(); ++i) {
         const std::string &op = g_ops[i];
         #define ARG(k) (i + (k) < g_ops.size() ? g_ops[i + (k)] : (fprintf(stderr, "missing arg for %s\n", op.c_str()), exit(2), g_ops[0]))
-        if (op == "--export-regions") {
+        if (op == "--export-area-lights") {
+            // scene with DiffuseAreaLights over triangle meshes: <scn> keeps a placeholder in each such light's slot, <side> lists per
+            // area light its slot, Lemit and the triangles of its ShapeSet in the ShapeSet's own (refine) order -- the order the
+            // area CDF samples by (core/light.cpp:114-137).  PVAREA01: n; per light: slot u32, n_tris u32, flags u32 (1 = reverse
+            // orientation, 2 = transform swaps handedness), Lemit f32[30], vertices f32[9 * n_tris] (world space).
+            PvHostScene hs; std::string err;
+            if (!pv_export_scene(scene, hs, err, false, true)) { fprintf(stderr, "%s\n", err.c_str()); exit(4); }
+            if (!pv_write_scene_file(hs, ARG(1))) exit(3);
+            FILE *f = xopen(ARG(2), "wb");
+            uint64_t n = 0;
+            for (size_t l = 0; l < scene->lights.size(); ++l) if (dynamic_cast<DiffuseAreaLight *>(scene->lights[l])) ++n;
+            write_header(f, "PVAREA01", n);
+            for (size_t l = 0; l < scene->lights.size(); ++l) {
+                DiffuseAreaLight *al = dynamic_cast<DiffuseAreaLight *>(scene->lights[l]);
+                if (!al) continue;
+                uint32_t slot = (uint32_t)l, nt = (uint32_t)al->shapeSet->shapes.size(), flags = 0;
+                std::vector<float> verts;
+                for (uint32_t k = 0; k < nt; ++k) {
+                    const Triangle *t = dynamic_cast<const Triangle *>(al->shapeSet->shapes[k].GetPtr());
+                    if (!t) { fprintf(stderr, "--export-area-lights: only triangle-mesh area lights\n"); exit(4); }
+                    flags = (t->ReverseOrientation ? 1u : 0u) | (t->TransformSwapsHandedness ? 2u : 0u);
+                    for (int c = 0; c < 3; ++c) { const Point &q = t->mesh->p[t->v[c]]; verts.push_back(q.x); verts.push_back(q.y); verts.push_back(q.z); }
+                }
+                wr(f, &slot, 1); wr(f, &nt, 1); wr(f, &flags, 1); wr(f, al->Lemit.c, 30); wr(f, verts.data(), verts.size());
+            }
+            fclose(f);
+            i += 2;
+        }
+        else if (op == "--export-regions") {
             // an AggregateVolume (several Volume statements): the whole scene once per region, with that region as its only medium
             // -> <prefix>.<i>.scn; the oracle takes region 0's file as the scene and the media of the others on the side
             AggregateVolume *agg = dynamic_cast<AggregateVolume *>(scene->volumeRegion);

@@ -303,6 +303,14 @@ def volint_goldens(tmp):
     tr = np.frombuffer(open(os.path.join(tmp, "tr.bin"), "rb").read(), np.float32, count=len(rays) * 31, offset=16).reshape(len(rays), 31)
     out["volint_agg_tr_u"], out["volint_agg_tr_T"] = tr[:, 0].copy(), tr[:, 1:].copy()
     out["volint_agg_stepsize"] = np.array([0.0625], np.float32)
+    # a DiffuseAreaLight next to the point light: scene with a placeholder in the area light's slot + the light's data on the side
+    f = os.path.join(tmp, "volint_area.pbrt"); open(f, "w").write(scenes.volint_area_pbrt("single"))
+    run(f, "--export-area-lights", os.path.join(HERE, "volint_area.scn"), os.path.join(HERE, "volint_area.lights"),
+        "--vli", rf, 4000, os.path.join(tmp, "vli.bin"), "--vli", ef, 5000, os.path.join(tmp, "vli_e.bin"))
+    li = sceneio.read_spectra(os.path.join(tmp, "vli.bin"), b"PVLI0001", per=2)
+    out["volint_area_single_L"], out["volint_area_single_T"] = li[:, 0], li[:, 1]
+    li = sceneio.read_spectra(os.path.join(tmp, "vli_e.bin"), b"PVLI0001", per=2)
+    out["edge_volint_area_single_L"], out["edge_volint_area_single_T"] = li[:, 0], li[:, 1]
     out["mt_seed"] = np.array([4000], np.uint32)
     np.savez_compressed(os.path.join(HERE, "volint.npz"), **out)
     # end-to-end images of the unmodified reference binary (glass wedge: specular bounces call the volume integrator per ray)

@@ -118,6 +118,42 @@ def gather(scene, tree, wi, alpha, rays, stepsize, nused, maxdist, seed=0, ray_i
 SINGLE, EMISSION = 0, 1
 
 
+class AreaLight(C.Structure):
+    _fields_ = [("slot", C.c_uint32), ("n_tris", C.c_uint32), ("flags", C.c_uint32), ("pad", C.c_uint32),
+                ("tri", C.POINTER(C.c_float)), ("Lemit", C.c_float * 30)]
+
+
+class area_lights:
+    """DiffuseAreaLights for the oracle: `with area_lights(path_of_PVAREA01_file): ...` (written by ref_harness --export-area-lights
+    next to a scene whose area-light slots hold placeholders).  pv_light has no area-light fields yet."""
+
+    def __init__(self, path):
+        buf = open(path, "rb").read()
+        assert buf[:8] == b"PVAREA01"
+        n = int(np.frombuffer(buf, np.uint64, 1, 8)[0])
+        off = 16
+        self.keep = []
+        self.arr = (AreaLight * n)()
+        for i in range(n):
+            slot, nt, flags = np.frombuffer(buf, np.uint32, 3, off); off += 12
+            lem = np.frombuffer(buf, np.float32, 30, off).copy(); off += 120
+            tri = np.frombuffer(buf, np.float32, 9 * int(nt), off).copy(); off += 36 * int(nt)
+            self.keep.append(tri)
+            a = self.arr[i]
+            a.slot, a.n_tris, a.flags, a.pad = int(slot), int(nt), int(flags), 0
+            a.tri = tri.ctypes.data_as(C.POINTER(C.c_float))
+            for b in range(30):
+                a.Lemit[b] = float(lem[b])
+
+    def __enter__(self):
+        lib().pvo_set_area_lights(self.arr, C.c_uint32(len(self.arr)))
+        return self
+
+    def __exit__(self, *exc):
+        lib().pvo_set_area_lights(None, C.c_uint32(0))
+        return False
+
+
 class more_media:
     """AggregateVolume for the oracle (core/volume.cpp:178-261): `with more_media(scene_b, scene_c): ...` makes every oracle call
     inside see the medium of the scene it is given PLUS the media of these scenes as one aggregate.  pv_scene_desc carries one

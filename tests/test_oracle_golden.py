@@ -317,3 +317,24 @@ def test_photon_volume_path_under_an_aggregate_volume_matches_reference(golden, 
     assert (ref > 0).any() and relerr(Lp, ref)[ref > 0].max() < 2e-6 and np.array_equal(Lp == 0, ref == 0)
     assert (g["li_L"] > 0).any() and relerr(T, g["li_T"]).max() < 1e-6 and relerr(L, g["li_L"])[g["li_L"] > 0].max() < 1e-5
     assert relerr(Tr, g["tr_T"]).max() < 1e-6 and st.lookups > 0
+
+
+def test_area_light_direct_term_matches_reference(golden, pkg):
+    """A DiffuseAreaLight (downward-facing quad = ShapeSet of two triangles) next to the point light under the single-scattering
+    integrator: area-CDF shape choice, Triangle::Sample, ShapeSet::Sample's re-intersection of every shape, ShapeSet::Pdf, the
+    shortened visibility segment -- and the call-site quirk that the integrators build LightSample(lightComp, lightPos[0],
+    lightPos[1]), i.e. the COMPONENT number is the second lightPos value (integrators/single.cpp:120-121, core/light.h:122-128).
+    Oracle with the reference's MT stream against the reference, bit for bit; groundwork for DESIGN.md 11.2."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    scene = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_area.scn"))
+    assert [l.type for l in scene.lights] == [0, 100]                     # point light, placeholder slot of the area light
+    with O.area_lights(os.path.join(GOLDEN, "volint_area.lights")):
+        L, T, st = O.volume_li(scene, g["rays"], 0.05, O.SINGLE, rng_mode=O.MT, mt_seed=4000)
+        Le, Te, _ = O.volume_li(scene, g["edge_rays"], 0.05, O.SINGLE, rng_mode=O.MT, mt_seed=5000)
+    L0, _, _ = O.volume_li(scene, g["rays"], 0.05, O.SINGLE, rng_mode=O.MT, mt_seed=4000)      # the slot without its light: dark
+    refL = g["volint_area_single_L"]
+    assert (refL > 0).any() and not np.allclose(L0, refL, rtol=1e-2)
+    assert np.array_equal(L, refL) and np.array_equal(T, g["volint_area_single_T"])
+    assert np.array_equal(Le, g["edge_volint_area_single_L"]) and np.array_equal(Te, g["edge_volint_area_single_T"])
