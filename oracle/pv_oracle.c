@@ -1532,6 +1532,43 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
 }
 
 /* Light::Sample_L(scene, ls, u1, u2, time, &ray, &Ns, &pdf): lights/point.cpp:80-88, spot.cpp:106-114, distant.cpp:82-102 */
+/* DiffuseAreaLight::Sample_L(scene, ls, u1, u2, ...) (lights/diffuse.cpp:89-100): a point by area (ShapeSet::Sample(ls, Ns),
+ * core/light.cpp:161-164), a direction uniform over the sphere flipped into the normal's hemisphere, pdf = ShapeSet::Pdf(org) / 2 pi
+ * where ShapeSet::Pdf(p) = sum_i areas[i] * (1 / areas[i]) / sumArea (:175-180, core/shape.cpp:80-82) -- the NUMBER of shapes over the
+ * total area, not 1 / area. */
+static spec area_emit(const pv_scene_desc *sc, const pv_light *l, float up0, float up1, float ucomp, float u1, float u2, ray_t *ray, v3 *Ns, float *pdf) {
+    const pvo_area_light *al = area_of(sc, l);
+    spec Le = s_const(0.f);
+    ray->o = V(0, 0, 0); ray->d = V(0, 0, 1); ray->mint = 1e-3f; ray->maxt = INFINITY; *Ns = ray->d; *pdf = 0.f;
+    if (!al || !al->n_tris) return Le;
+    const uint32_t n = al->n_tris;
+    float *area = (float *)malloc(sizeof(float) * n), *cdf = (float *)malloc(sizeof(float) * (n + 1));
+    float sumArea = 0.f;
+    for (uint32_t i = 0; i < n; ++i) { area[i] = tri_area(al->tri + 9 * (size_t)i); sumArea += area[i]; }
+    cdf[0] = 0.f;
+    for (uint32_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + area[i - 1] / n;
+    float funcInt = cdf[n];
+    if (funcInt == 0.f) for (uint32_t i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+    else for (uint32_t i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    int lo = 0, hi = (int)n + 1;
+    while (lo < hi) { int mid = (lo + hi) / 2; if (ucomp < cdf[mid]) hi = mid; else lo = mid + 1; }
+    int sn = lo - 1; if (sn < 0) sn = 0;
+    const float *tv = al->tri + 9 * (size_t)sn;
+    v3 p1 = V(tv[0], tv[1], tv[2]), p2 = V(tv[3], tv[4], tv[5]), p3 = V(tv[6], tv[7], tv[8]);
+    float su1 = sqrtf(up0), b1 = 1.f - su1, b2 = up1 * su1;
+    v3 org = vadd(vadd(vmul(p1, b1), vmul(p2, b2)), vmul(p3, 1.f - b1 - b2));
+    v3 ns = vnorm(vcross(vsub(p2, p1), vsub(p3, p1)));
+    if (al->flags & 1u) ns = vmul(ns, -1.f);
+    v3 dir = uniform_sample_sphere(u1, u2);
+    if (vdot(dir, ns) < 0.) dir = vmul(dir, -1.f);
+    float pd = 0.f;
+    for (uint32_t i = 0; i < n; ++i) pd += area[i] * (1.f / area[i]);
+    *pdf = (pd / sumArea) * 0.15915494309189533577f;                    /* INV_TWOPI */
+    ray->o = org; ray->d = dir; *Ns = ns;
+    if (vdot(ns, dir) > 0.f) Le = s_load(al->Lemit);
+    free(area); free(cdf);
+    return Le;
+}
 static spec light_emit(const pv_scene_desc *sc, const pv_light *l, float up0, float up1, ray_t *ray, v3 *Ns, float *pdf) {
     spec Le = s_load(l->intensity);
     if (l->type == PV_LIGHT_POINT) {
@@ -1589,7 +1626,8 @@ static void shoot_path(shoot_ctx *c, const halton6 *h, const distrib1d *ld, uint
     int lightNum = distrib_sample_discrete(ld, u[0], &lightPdf);
     const pv_light *light = &sc->lights[lightNum];
     ray_t photonRay; v3 Nl; float pdf;
-    spec Le = light_emit(sc, light, u[1], u[2], &photonRay, &Nl, &pdf);
+    spec Le = light->type == PVO_LIGHT_SLOT ? area_emit(sc, light, u[1], u[2], u[3], u[4], u[5], &photonRay, &Nl, &pdf)
+                                            : light_emit(sc, light, u[1], u[2], &photonRay, &Nl, &pdf);
     if (pdf == 0.f || s_black(&Le)) return;
     float ad = fabsf(vdot(Nl, photonRay.d));
     spec alpha; float den = pdf * lightPdf;

@@ -182,6 +182,7 @@ def main():
         exponential_goldens(tmp)
         volint_goldens(tmp)
         aggregate_goldens(tmp)
+        area_light_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -341,6 +342,21 @@ def aggregate_goldens(tmp):
     golden_for_scene(tmp, "cornell_agg", f, 50, 0.25, 0.0625, 64, 64, [(50, 0.25 ** 2)], wanted=2500, regions=True)
 
 
+def area_light_goldens(tmp):
+    """A DiffuseAreaLight next to the point light in the photon-volume scene: the reference's photon list of one task.  Photons now
+    start on the light's quad (area-CDF shape choice, Triangle::Sample, hemisphere direction, pdf = nShapes / sumArea / 2 pi)."""
+    f = os.path.join(tmp, "cornell_area.pbrt")
+    open(f, "w").write(scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 3000).replace("WorldEnd", scenes.AREA_QUAD + "\nWorldEnd"))
+    pho = os.path.join(tmp, "cornell_area.pho"); stats = os.path.join(tmp, "cornell_area.json")
+    run(f, "--export-area-lights", os.path.join(HERE, "cornell_area.scn"), os.path.join(HERE, "cornell_area.lights"),
+        "--shoot", "--dump-photons", pho, "--stats", stats)
+    pos, wi, alpha = sceneio.read_photons(pho)
+    st = json.load(open(stats))
+    print("  cornell_area: %d photons from %d paths" % (len(pos), st["nshot"]))
+    np.savez_compressed(os.path.join(HERE, "cornell_area.npz"), shot_pos=pos, shot_wi=wi, shot_alpha=alpha, nshot=np.array([st["nshot"]], np.uint64),
+                        params=np.array([50, 0.25, 0.05, 3000, 0.05], np.float64))
+
+
 def read_radiance(fn):
     """PVRADP01 (oracle/ref_harness.cpp --dump-maps): p[3] n[3] Lo[30] rho_r[30] rho_t[30] per radiance photon."""
     buf = open(fn, "rb").read()
@@ -413,6 +429,10 @@ if __name__ == "__main__":
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:
             exponential_goldens(tmp_)
+    elif len(sys.argv) > 1 and sys.argv[1] == "area":             # only the area-light photon list
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+        with tempfile.TemporaryDirectory() as tmp_:
+            area_light_goldens(tmp_)
     elif len(sys.argv) > 1 and sys.argv[1] == "aggregate":        # only the AggregateVolume goldens of the photon-volume path
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
         with tempfile.TemporaryDirectory() as tmp_:

@@ -338,3 +338,21 @@ def test_area_light_direct_term_matches_reference(golden, pkg):
     assert (refL > 0).any() and not np.allclose(L0, refL, rtol=1e-2)
     assert np.array_equal(L, refL) and np.array_equal(T, g["volint_area_single_T"])
     assert np.array_equal(Le, g["edge_volint_area_single_L"]) and np.array_equal(Te, g["edge_volint_area_single_T"])
+
+
+def test_shooter_with_an_area_light_reproduces_reference_photons(golden, pkg):
+    """Photon emission from a DiffuseAreaLight (lights/diffuse.cpp:89-100: point by area CDF + Triangle::Sample, direction uniform
+    over the sphere flipped into the normal's hemisphere, pdf = ShapeSet::Pdf(org) / 2 pi with ShapeSet::Pdf(p) = nShapes / sumArea)
+    next to the point light, chosen by the power CDF: the reference's photon list of one task (MT stream), replayed exactly."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("cornell_area")
+    scene = pkg.sceneio.read_scene(os.path.join(GOLDEN, "cornell_area.scn"))
+    assert [l.type for l in scene.lights] == [0, 100] and scene.lights[1].power_y > 0
+    with O.area_lights(os.path.join(GOLDEN, "cornell_area.lights")):
+        res = O.shoot(scene, int(g["params"][3]), float(g["params"][4]), float(g["params"][2]), rng_mode=O.MT)
+    dark = O.shoot(scene, int(g["params"][3]), float(g["params"][4]), float(g["params"][2]), rng_mode=O.MT)      # the slot without its light
+    assert res["rc"] == 0 and res["nshot"] == int(g["nshot"][0]) and res["n"] == len(g["shot_pos"])
+    assert np.array_equal(res["pos"], g["shot_pos"]) and np.array_equal(res["wi"], g["shot_wi"])
+    assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-6
+    assert dark["n"] != res["n"] or not np.array_equal(dark["pos"], res["pos"])
