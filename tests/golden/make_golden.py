@@ -353,8 +353,16 @@ def area_light_goldens(tmp):
     pos, wi, alpha = sceneio.read_photons(pho)
     st = json.load(open(stats))
     print("  cornell_area: %d photons from %d paths" % (len(pos), st["nshot"]))
+    # PhotonVolumeIntegrator::Li on that photon list: the direct term samples the area light too
+    rays = scenes.camera_rays(64, 64)
+    rng = np.random.default_rng(41)
+    rays = rays[np.sort(rng.choice(len(rays), size=64, replace=False))]
+    rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
+    rf = os.path.join(tmp, "area_rays.bin"); sceneio.write_rays(rf, rays)
+    run(f, "--load-photons", pho, "--li", rf, 1000, os.path.join(tmp, "area_li.bin"))
+    li = sceneio.read_spectra(os.path.join(tmp, "area_li.bin"), b"PVLI0001", per=2)
     np.savez_compressed(os.path.join(HERE, "cornell_area.npz"), shot_pos=pos, shot_wi=wi, shot_alpha=alpha, nshot=np.array([st["nshot"]], np.uint64),
-                        params=np.array([50, 0.25, 0.05, 3000, 0.05], np.float64))
+                        params=np.array([50, 0.25, 0.05, 3000, 0.05], np.float64), li_rays=rays, li_L=li[:, 0], li_T=li[:, 1])
 
 
 def read_radiance(fn):

@@ -356,3 +356,9 @@ def test_shooter_with_an_area_light_reproduces_reference_photons(golden, pkg):
     assert np.array_equal(res["pos"], g["shot_pos"]) and np.array_equal(res["wi"], g["shot_wi"])
     assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-6
     assert dark["n"] != res["n"] or not np.array_equal(dark["pos"], res["pos"])
+    # PhotonVolumeIntegrator::Li on the reference's list (MT stream, RNG(1000 + i)): its direct term samples the area light too
+    with O.area_lights(os.path.join(GOLDEN, "cornell_area.lights")):
+        tree = O.KdTree(g["shot_pos"])
+        L, T, _ = O.gather(scene, tree, g["shot_wi"], g["shot_alpha"], g["li_rays"], float(g["params"][2]), int(g["params"][0]), float(g["params"][1]),
+                           rng_mode=O.MT, mt_seed=1000)
+    assert (g["li_L"] > 0).any() and relerr(T, g["li_T"]).max() < 1e-6 and relerr(L, g["li_L"])[g["li_L"] > 0].max() < 1e-5
