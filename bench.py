@@ -408,7 +408,8 @@ def main():
                           "stepsize": cfg["stepsize"], "nused": cfg["nused"], "maxdist": cfg["maxdist"], "photon_record_bytes": 144,
                           "l2_policy": "inputs_exceed_l2 (photon map %.1f GB)" % (n_ph * 160 / 1e9), "ray_order": "8x8 tiles",
                           "parallelism": "tiles/%d" % world},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps,        # per pass: march_setup, publish_total, march_steps, gather_kernel (profiles/*_launches.csv)
+               "clocks": clocks,
                "shoot": shoot, "build": {"seconds": build_s, "photons": n_ph, "photon_gen_host_s": gen_s}, "allgather": allgather,
                "lookups_per_s": stats.lookups * world / (total_ms * 1e-3) if world == 1 else None, "checksum_L": check}
         print(json.dumps(out), flush=True)
