@@ -1319,7 +1319,10 @@ static void make_isect(const pv_scene_desc *sc, int prim, v3 o, v3 d, float t, i
     is->rayEpsilon = 1e-3f * t;
 }
 
-static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, spec alpha, int nIntersections, int specularPath) {
+/* split_lambda: the fork's Spectrum::lambda member as followPhoton sees it (photonshooter.cpp:141): -1 until splitSpectrum has made
+ * the photon one of its monochromatic children, >= 0 from then on -- whatever happens to the child's one bin afterwards (it can
+ * underflow to zero in a dense medium; the reference then keeps tracing, and depositing, a black photon). */
+static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, spec alpha, int nIntersections, int specularPath, int split_lambda) {
     const pv_scene_desc *sc = c->sc;
     float thit = photonRay.maxt;
     c->segments++;
@@ -1366,7 +1369,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         for (int b = 0; b < NS; ++b) alpha.c[b] *= ref;
         for (int b = 0; b < NS; ++b) alpha.c[b] /= pdf;
         photonRay.o = interactPt; photonRay.d = direction; photonRay.mint = 0.f; photonRay.maxt = INFINITY;
-        follow_photon(c, photonRay, photonIsect, alpha, nIntersections, specularPath);
+        follow_photon(c, photonRay, photonIsect, alpha, nIntersections, specularPath, split_lambda);
         /* Q2: falls through into the surface code with the scattered ray and the ORIGINAL isect */
         }
     }
@@ -1430,7 +1433,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         if (!c->want_indirect) return;
         spec an2; for (int b = 0; b < NS; ++b) an2.c[b] = anew.c[b] / continueProb;
         ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
-        follow_photon(c, nr, photonIsect, an2, nIntersections, 0);
+        follow_photon(c, nr, photonIsect, an2, nIntersections, 0, split_lambda);
         return;
     }
     /* glass: specular reflection + dispersive transmission (materials/glass.cpp:42-59,
@@ -1439,12 +1442,9 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         spec Rk = s_load(mat->kr), Tk = s_load(mat->kt);
         int hasR = !s_black(&Rk), hasT = !s_black(&Tk);
         int matching = hasR + hasT;
-        /* split (photonshooter.cpp:140-145): alpha.lambda<0 is tracked as "not yet monochromatic" */
-        int nz = 0, first = -1;
-        for (int b = 0; b < NS; ++b) if (alpha.c[b] > 0.f) { if (first < 0) first = b; nz++; }
-        int mono = (nz == 1);
+        /* split (photonshooter.cpp:140-145): hasTransmission && alpha.lambda < 0 && primitive->dispersive() */
         int nspec = 1; int binlist[NS];
-        int do_split = hasT && !mono && mat->vn > 0.f;
+        int do_split = hasT && split_lambda < 0 && mat->vn > 0.f;
         if (do_split) { nspec = 0; for (int b = 0; b < NS; ++b) if (alpha.c[b] != 0.f) binlist[nspec++] = b; }
         spec alpha_in = alpha;
         for (int si = 0; si < nspec; ++si) {
@@ -1526,7 +1526,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
             /* specular: specularPath stays as it was; `indirectDone && !specularPath` -> continue */
             if (!c->want_indirect && !specularPath) continue;
             ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
-            follow_photon(c, nr, photonIsect, an2, nIntersections, specularPath);
+            follow_photon(c, nr, photonIsect, an2, nIntersections, specularPath, do_split ? 400 + 10 * binlist[si] : split_lambda);
         }
     }
 }
@@ -1635,7 +1635,7 @@ static void shoot_path(shoot_ctx *c, const halton6 *h, const distrib1d *ld, uint
     if (s_black(&alpha)) return;
     isect_t is; memset(&is, 0, sizeof(is));
     c->path_index = path_index; c->deposit_seq = 0;
-    follow_photon(c, photonRay, is, alpha, 0, 1);
+    follow_photon(c, photonRay, is, alpha, 0, 1, -1);
 }
 
 typedef struct {

@@ -69,6 +69,21 @@ def random_area_quad(rng):
             % (col(rng, 2, 12), "  ".join("%g %g %g" % tuple(q) for q in P)))
 
 
+def random_glass(rng):
+    """A glass object in the box: a (possibly partial, scaled, rotated) sphere or the wedge mesh of the all-maps scene; random index,
+    dispersion (Vn = 0: none), reflectance / transmittance."""
+    mat = 'Material "glass" "float index" [%g] "float Vn" [%g] "color Kr" %s "color Kt" %s' % (
+        rng.uniform(1.1, 2.0), 0.0 if rng.random() < 0.4 else rng.uniform(1.5, 6.0), col(rng, 0, 1), col(rng, 0.2, 1))
+    xf = "Translate %g %g %g\nRotate %g %g %g %g\nScale %g %g %g" % (*rng.uniform(-0.4, 0.4, 3), rng.uniform(0, 360), *rng.normal(size=3), *rng.uniform(0.6, 1.3, 3))
+    if rng.random() < 0.5:
+        extra = "" if rng.random() < 0.5 else ' "float zmin" [%g] "float zmax" [%g] "float phimax" [%g]' % (rng.uniform(-0.3, -0.05), rng.uniform(0.05, 0.3), rng.uniform(120, 360))
+        shape = 'Shape "sphere" "float radius" [%g]%s' % (rng.uniform(0.2, 0.4), extra)
+    else:
+        shape = ('Scale 0.45 0.25 0.45\nShape "trianglemesh" "point P" [1 -1 -1  1 -1 1  -1 -1 1  -1 -1 -1  1 1 0  -1 1 0]\n'
+                 '  "integer indices" [0 1 2  0 2 3  1 4 5  1 5 2  0 4 1  2 5 3  4 0 3  4 3 5]')
+    return "AttributeBegin\n%s\n%s\n%s\nAttributeEnd" % (mat, xf, shape)
+
+
 def second_volume(rng):
     """A second, overlapping Volume statement => AggregateVolume."""
     lo = rng.uniform(-1, 0.2, 3); hi = lo + rng.uniform(0.5, 1.2, 3)
@@ -91,12 +106,14 @@ def main():
             rng = np.random.default_rng(1000 + seed)
             vol, lights = random_scene(rng)
             integ = ["single", "emission", "photonvolume"][seed % 3]
-            variant = ["plain", "plain", "area", "aggregate"][(seed // 3) % 4]
+            variant = ["plain", "glass", "area", "aggregate"][(seed // 3) % 4]
             tail = ""
             if variant == "area":
                 tail = random_area_quad(rng)
             elif variant == "aggregate":
                 vol = vol + "\n" + second_volume(rng)
+            elif variant == "glass":
+                tail = random_glass(rng)
             stepsize = round(float(rng.uniform(0.03, 0.2)), 4)          # 4 decimals: the scene text (%g) and the oracle see the same number
             rays = base[np.sort(rng.choice(len(base), size=48, replace=False))].copy()
             rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
@@ -113,7 +130,7 @@ def main():
                 ops = ["--vli", rf, "1000", out]
             text = text.replace("WorldEnd", tail + "\nWorldEnd")
             side = os.path.join(tmp, "s.lights"); reg = os.path.join(tmp, "reg")
-            export = {"plain": ["--export-scene", scn], "area": ["--export-area-lights", scn, side], "aggregate": ["--export-regions", reg]}[variant]
+            export = {"plain": ["--export-scene", scn], "glass": ["--export-scene", scn], "area": ["--export-area-lights", scn, side], "aggregate": ["--export-regions", reg]}[variant]
             ops = export + ops
             f = os.path.join(tmp, "s.pbrt"); open(f, "w").write(text)
             r = subprocess.run([HARNESS, f] + ops, capture_output=True, text=True)
