@@ -338,11 +338,11 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    kernel_ms = []; march_ms = []
+    kernel_ms = []; march_ms = []; phase_ms = []
     e0.record(ext)
     for _ in range(args.steps):
         pv.Li_dev(d_rays, n_local, d_L, d_T)
-        kernel_ms.append(pv.last_kernel_ms()); march_ms.append(pv.last_march_ms())
+        kernel_ms.append(pv.last_kernel_ms()); march_ms.append(pv.last_march_ms()); phase_ms.append(pv.last_phase_ms())
     e1.record(ext)
     barrier()
     clocks = sampler.stop()
@@ -360,6 +360,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_kind": peak_kind, "kernel": "gather_kernel", "avg_launch_ms": avg_kernel_ms,
                 "march_kernels_ms": float(np.mean(march_ms)),
+                "phase_ms": dict(zip(("step_sort", "cellgather_kernel", "overflow_pass", "recurrence"), [float(v) for v in np.mean(phase_ms, axis=0)])),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "b_ph": 144,
                 "lookups_per_launch": stats.lookups / args.steps, "photons_found_per_lookup": stats.photons_found / max(stats.lookups, 1),
                 "candidates_per_lookup": stats.candidates_tested / max(stats.lookups, 1)}

@@ -10,7 +10,7 @@ PV_OK, PV_EINVAL, PV_ECUDA, PV_ENOMEM, PV_ESTATE, PV_ENOPHOTONS = 0, -1, -2, -3,
 LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2
 MEDIUM_NONE, MEDIUM_HOMOGENEOUS, MEDIUM_GRID, MEDIUM_RAINBOW, MEDIUM_EXPONENTIAL = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_GLASS = 0, 1
-GATHER_NO_DIRECT, GATHER_NO_INDIRECT, GATHER_RAY_PARALLEL, GATHER_STEP_PARALLEL = 1, 2, 4, 8
+GATHER_NO_DIRECT, GATHER_NO_INDIRECT, GATHER_RAY_PARALLEL, GATHER_STEP_PARALLEL, GATHER_CELL_BATCHED = 1, 2, 4, 8, 16
 
 Spec = C.c_float * NSPEC
 Mat16 = C.c_float * 16
@@ -108,7 +108,7 @@ EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_set_scene", "pv_set_photons",
     "pv_set_photons_dev", "pv_get_photons", "pv_get_photons_dev", "pv_photon_count", "pv_build", "pv_knn",
     "pv_intersect", "pv_occluded", "pv_transmittance", "pv_gather", "pv_gather_dev", "pv_lphoton",
-    "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
+    "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_last_phase_ms", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
     "pv_shoot_maps", "pv_shoot_maps_ranks", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons", "pv_select_map", "pv_surface_lphoton", "pv_radiance_nearest", "pv_final_gather", "pv_set_radiance_lo",
     "pv_volume_li", "pv_volume_li_dev",
 ]

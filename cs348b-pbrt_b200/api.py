@@ -308,5 +308,11 @@ class PhotonVolume:
         self._chk(self.lib.pv_last_march_ms(self.ctx, C.byref(ms)))
         return ms.value
 
+    def last_phase_ms(self):
+        """Cell-batched schedule: device ms of (step sort, cellgather_kernel, overflow pass, recurrence) of the last Li."""
+        ms = (C.c_float * 4)()
+        self._chk(self.lib.pv_last_phase_ms(self.ctx, ms))
+        return [float(v) for v in ms]
+
     def stream(self):
         return self.lib.pv_stream(self.ctx)

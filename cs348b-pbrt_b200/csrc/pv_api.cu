@@ -46,6 +46,8 @@ int pv_create(pv_ctx **out, int device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess &&
+              cudaEventCreate(&ctx->tev[0]) == cudaSuccess && cudaEventCreate(&ctx->tev[1]) == cudaSuccess &&
+              cudaEventCreate(&ctx->tev[2]) == cudaSuccess && cudaEventCreate(&ctx->tev[3]) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dscene, sizeof(DevScene)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_stats, sizeof(pv_gather_stats)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->d_counters, 64 * sizeof(unsigned long long)) == cudaSuccess &&
@@ -61,7 +63,7 @@ void pv_destroy(pv_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
     if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
@@ -69,6 +71,7 @@ void pv_destroy(pv_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (int i = 0; i < 4; ++i) if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -405,7 +408,7 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays + a, rays + a, (b - a) * sizeof(pv_ray), cudaMemcpyHostToDevice, ctx->copy_in));
         PV_CUDA_CHECK(ctx, cudaEventRecord(in_done[s], ctx->copy_in));
     }
-    float ms = 0.f, march_ms = 0.f;
+    float ms = 0.f, march_ms = 0.f, phase_ms[4] = {0.f, 0.f, 0.f, 0.f};
     rc = PV_OK;
     for (int s = 0; s < nslices && rc == PV_OK; ++s) {
         const uint64_t a = lo(s), b = lo(s + 1);
@@ -414,6 +417,7 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
         rc = pvi_gather(ctx, d_rays + a, b - a, &p, d_L + a * PV_NSPEC, d_T + a * PV_NSPEC);
         if (rc) break;
         ms += ctx->last_ms; march_ms += ctx->last_march_ms;
+        for (int i = 0; i < 4; ++i) phase_ms[i] += ctx->phase_ms[i];
         PV_CUDA_CHECK(ctx, cudaEventRecord(comp_done[s], ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[s], 0));
         const size_t ob = (b - a) * PV_NSPEC * sizeof(float);
@@ -426,6 +430,7 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
     if (rc) return rc;
     if (e != cudaSuccess) { ctx->err = std::string("pv_gather: ") + cudaGetErrorString(e); return PV_ECUDA; }
     ctx->last_ms = ms; ctx->last_march_ms = march_ms;
+    for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = phase_ms[i];
     return PV_OK;
 }
 int pv_volume_li_dev(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, const pv_gather_params *params, float *L, float *T) {
@@ -464,6 +469,12 @@ int pv_last_kernel_ms(pv_ctx *ctx, float *ms) {
     LOCK(ctx);
     if (!ms) { ctx->err = "pv_last_kernel_ms: null out"; return PV_EINVAL; }
     *ms = ctx->last_ms;
+    return PV_OK;
+}
+int pv_last_phase_ms(pv_ctx *ctx, float ms[4]) {
+    LOCK(ctx);
+    if (!ms) { ctx->err = "pv_last_phase_ms: null out"; return PV_EINVAL; }
+    for (int i = 0; i < 4; ++i) ms[i] = ctx->phase_ms[i];
     return PV_OK;
 }
 int pv_last_march_ms(pv_ctx *ctx, float *ms) {

@@ -144,13 +144,12 @@ static int sort_pairs(pv_ctx *ctx, K *keys, uint32_t *vals, K *keys_tmp, uint32_
     uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
     uint64_t hist_n = (uint64_t)256 * nblocks;
     size_t need = (hist_n + scan_scratch_words(hist_n)) * sizeof(uint32_t);
-    void *hp = nullptr; size_t hcap = 0;
-    // dedicated allocation: ctx->scratch may already hold the key/value buffers
-    PV_CUDA_CHECK(ctx, cudaMalloc(&hp, need)); hcap = need; (void)hcap;
-    uint32_t *hist = (uint32_t *)hp, *sscratch = hist + hist_n;
+    // the histogram lives in its own context-owned buffer (ctx->scratch may hold the key/value arrays): no allocation, no
+    // synchronisation per sort
+    int rc = pv_ensure(ctx, &ctx->sort_hist, &ctx->sort_hist_bytes, need); if (rc) return rc;
+    uint32_t *hist = (uint32_t *)ctx->sort_hist, *sscratch = hist + hist_n;
     int passes = (key_bits + 7) / 8;
     K *kin = keys, *kout = keys_tmp; uint32_t *vin = vals, *vout = vals_tmp;
-    int rc = PV_OK;
     for (int p = 0; p < passes && rc == PV_OK; ++p) {
         int shift = 8 * p;
         rs_count_kernel<K><<<nblocks, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, hist, nblocks);
@@ -159,10 +158,8 @@ static int sort_pairs(pv_ctx *ctx, K *keys, uint32_t *vals, K *keys_tmp, uint32_
         rs_scatter_kernel<K><<<nblocks, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, hist, nblocks, kout, vout);
         std::swap(kin, kout); std::swap(vin, vout);
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(hp);
     if (rc) return rc;
-    if (e != cudaSuccess) { ctx->err = std::string("radix sort: ") + cudaGetErrorString(e); return PV_ECUDA; }
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
     *keys_out = kin; *vals_out = vin;
     return PV_OK;
 }

@@ -1,0 +1,370 @@
+// pv_cellgather.cu -- the photon lookups of a whole slice of march steps, batched by photon-grid cell.
+//
+// LPhoton (integrators/photonvolume.cpp:65-108) = KdTree::Lookup (core/kdtree.h:150-183) + PhotonProcess
+// (core/photonshooter.h:186-203) + the flux sum, for EVERY march step of the slice at once.  The lookups of a ray's steps
+// do not depend on one another (only the Lv/Tr recurrence is sequential, pv_gather.cu gather_kernel<true>), so they are
+// reordered: cg_keys_kernel gives each step the key of the photon-grid cell its sample point falls into, the radix sort of
+// pv_build.cu orders the steps by that key, and cellgather_kernel walks the sorted list in batches of 32 neighbouring
+// steps, ONE WARP PER BATCH:
+//
+//   stage   the photons {x, y, z, index} (and wi) of the cells within maxdist of the batch's bounding box go to shared
+//           memory ONCE for all 32 queries, one TMA bulk copy per contiguous cell row (cp.async.bulk -> UBLKCP, completion
+//           on an mbarrier), rows in ascending Morton order = ascending photon order;
+//   scan    lane == QUERY: every lane walks the staged candidates (a broadcast 128-bit shared-memory load per candidate),
+//           computes the reference's unfused (dx*dx + dy*dy) + dz*dz against its own query and appends the accepted
+//           candidate to its own list in shared memory -- no cross-lane traffic, 32 distance tests per ~13 instructions;
+//   weigh   lane == query: phase function per accepted photon (from the staged wi), photon index resolved;
+//   sum     8 lanes x float4 per 128-byte alpha line (128-bit loads), eight queries at a time; each (query, bin) sum runs
+//           over the query's photons in ascending photon order in one fma chain, so a step's result does not depend on
+//           which other steps share its batch (bit-identical under any sharding of the rays);
+//   finish  radius = largest accepted distance, estimate as in LPhoton's tail, one 128-byte row of L_ii per step.
+//
+// Exactness: the staged block is a superset of every query's search sphere (cell coordinates are monotone in the
+// coordinate, the box is widened by maxdist + the grid margin), and each candidate is tested with the reference's
+// arithmetic, so a step finds exactly the photons with d2 < r2.  A step with MORE than nused of them needs the k-nearest
+// selection (ties by photon index): it is handed to the warp-per-step kernel (gather_lii_kernel) through an overflow list.
+#include <algorithm>
+#include "pv_gather.cuh"
+
+#ifndef CG_WARPS
+#define CG_WARPS 2
+#endif
+#define CG_THREADS (CG_WARPS * 32)
+#ifndef CG_MIN_CTAS
+#define CG_MIN_CTAS 5
+#endif
+#ifndef CG_STAGE
+#define CG_STAGE 128                     // candidates per TMA round
+#endif
+#ifndef CG_CAP
+#define CG_CAP 32                        // accepted candidates per query between two sum phases
+#endif
+#ifndef CG_U
+#define CG_U 8                           // scan unroll
+#endif
+#ifndef CG_XSPAN
+#define CG_XSPAN 2                       // a sub-batch spans at most this many coarse cells along x
+#endif
+
+struct CgArgs {
+    MapView m;
+    const DevScene *sc;
+    const pv_ray *rays;
+    const StepRec *steps;
+    const uint32_t *order;               // march steps of the slice sorted by cell key
+    unsigned long long total;
+    float maxdist;
+    uint32_t nused;
+    float *lii;
+    uint32_t *overflow;
+    unsigned long long *counters;
+    pv_gather_stats *stats;
+};
+
+// per-warp shared memory
+#define CG_OFF_POS 0
+#define CG_OFF_WI (CG_OFF_POS + (CG_STAGE + CG_U) * 16)
+#define CG_OFF_LIDX (CG_OFF_WI + CG_STAGE * 16)
+#define CG_OFF_LW (CG_OFF_LIDX + CG_CAP * 32 * 4)
+#define CG_OFF_PART (CG_OFF_LW + CG_CAP * 32 * 4)
+#define CG_OFF_Q (CG_OFF_PART + 32 * 8 * 16)          // fcnt, qcnt, qmx, qdens, qstep, run_rs, run_len: 7 x 32 words
+#define CG_OFF_MBAR (CG_OFF_Q + 7 * 32 * 4)
+#define CG_WARP_BYTES (CG_OFF_MBAR + 16)
+static_assert(CG_WARP_BYTES % 16 == 0, "per-warp shared memory keeps 16-byte alignment");
+
+__device__ __forceinline__ int cg_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float cg_unordered(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ float cg_warp_min(float v) { return cg_unordered(__reduce_min_sync(PV_FULL, cg_ordered(v))); }
+__device__ __forceinline__ float cg_warp_max(float v) { return cg_unordered(__reduce_max_sync(PV_FULL, cg_ordered(v))); }
+
+// One thread per march step: sort key = cell of the sample point in the photon grid (clamped like the photons' own keys).
+__global__ void __launch_bounds__(256) cg_keys_kernel(GridParams g, const pv_ray *__restrict__ rays, const StepRec *__restrict__ steps,
+                                                      unsigned long long total, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const float4 ra = __ldg(reinterpret_cast<const float4 *>(steps + s)), rb = __ldg(reinterpret_cast<const float4 *>(steps + s) + 1);
+    uint32_t key = g.table_size - 1;                          // dead steps (behind a Russian-roulette stop): anywhere, never looked up
+    if (!(ra.z >= PV_RR_DEAD)) {
+        const uint32_t ri = __float_as_uint(rb.w);
+        const v3 ro = V3(__ldg(&rays[ri].o[0]), __ldg(&rays[ri].o[1]), __ldg(&rays[ri].o[2]));
+        const v3 rd = V3(__ldg(&rays[ri].d[0]), __ldg(&rays[ri].d[1]), __ldg(&rays[ri].d[2]));
+        const v3 q = ray_at(ro, rd, ra.x);
+        key = pv_cell_key(g.xbits, pv_cell_coord(q.x, g.origin[0], g.inv_hx, g.dims[0]), pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]),
+                          pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]));
+    }
+    keys[s] = key; vals[s] = (uint32_t)s;
+}
+
+__global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgArgs a) {
+    extern __shared__ __align__(128) unsigned char cg_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *base = cg_smem + (size_t)warp * CG_WARP_BYTES;
+    float4 *spos = reinterpret_cast<float4 *>(base + CG_OFF_POS);
+    const float4 *swi = reinterpret_cast<const float4 *>(base + CG_OFF_WI);
+    uint32_t *lidx = reinterpret_cast<uint32_t *>(base + CG_OFF_LIDX);
+    float *lw = reinterpret_cast<float *>(base + CG_OFF_LW);
+    float4 *part = reinterpret_cast<float4 *>(base + CG_OFF_PART);
+    uint32_t *fcnt = reinterpret_cast<uint32_t *>(base + CG_OFF_Q), *qcnt = fcnt + 32;
+    float *qmx = reinterpret_cast<float *>(qcnt + 32), *qdens = qmx + 32;
+    uint32_t *qstep = reinterpret_cast<uint32_t *>(qdens + 32), *run_rs = qstep + 32, *run_len = run_rs + 32;
+    const uint32_t mbar = smem_u32(base + CG_OFF_MBAR), spos_addr = smem_u32(spos), swi_addr = smem_u32(swi);
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+
+    const GridParams &g = a.m.g;
+    const DevMedium &med = a.sc->med;
+    const uint32_t grp = lane >> 3, sub = lane & 7, gmask8 = 0xFFu << (grp * 8);
+    float sg[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const uint32_t b = sub * 4 + c; sg[c] = b < PV_NSPEC ? med.sigma_s[b] : 0.f; }
+    const float hg = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - hg * hg), gg1 = 1.f + hg * hg, g2 = 2.f * hg;
+    const bool iso = hg == 0.f;
+    const float r2 = a.maxdist * a.maxdist, slack = a.maxdist + g.margin;
+    const float4 *a4 = reinterpret_cast<const float4 *>(a.m.alpha32) + sub;
+    const uint32_t xspan = (uint32_t)CG_XSPAN << g.xshift;
+    unsigned long long st_cand = 0;
+    uint32_t st_lookups = 0, st_found = 0, st_heap = 0;
+    const unsigned long long nbatch = (a.total + 31ull) >> 5;
+
+    for (;;) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(a.counters + CG_CNT_BATCH, 1ull);
+        b = __shfl_sync(PV_FULL, b, 0);
+        if (b >= nbatch) break;
+        const unsigned long long qi = b * 32ull + lane;
+        bool valid = qi < a.total;
+        uint32_t s = 0; float dens = 0.f;
+        v3 q = V3(0.f, 0.f, 0.f), w = V3(0.f, 0.f, 0.f);
+        if (valid) {
+            s = __ldg(a.order + qi);
+            const float4 ra = __ldg(reinterpret_cast<const float4 *>(a.steps + s)), rb = __ldg(reinterpret_cast<const float4 *>(a.steps + s) + 1);
+            if (ra.z >= PV_RR_DEAD) valid = false;
+            else {
+                const uint32_t ri = __float_as_uint(rb.w);
+                const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
+                const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
+                q = ray_at(ro, rd, ra.x); w = -rd; dens = ra.w;
+            }
+        }
+        int cxf = 0; uint32_t row = 0;
+        if (valid) {
+            cxf = pv_cell_coord(q.x, g.origin[0], g.inv_hx, g.dims[0]);
+            row = pv_morton2((uint32_t)pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]), (uint32_t)pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qstep[lane] = s; qdens[lane] = dens;
+        uint32_t tot = 0, pad_idx = 0; float mx = 0.f; bool handed_over = false;
+        uint32_t remaining = __ballot_sync(PV_FULL, valid);
+
+        while (remaining) {
+            // ---- sub-batch: the queries of the leader's cell row within CG_XSPAN coarse cells of it (normally all 32)
+            const int leader = __ffs(remaining) - 1;
+            const uint32_t lrow = __shfl_sync(PV_FULL, row, leader);
+            const int lx = __shfl_sync(PV_FULL, cxf, leader);
+            const bool in = valid && ((remaining >> lane) & 1u) && row == lrow && (uint32_t)(cxf - lx) <= xspan;
+            const uint32_t gm = __ballot_sync(PV_FULL, in);
+            remaining &= ~gm;
+            const v3 aq = in ? q : V3(INFINITY, INFINITY, INFINITY);          // lanes outside the sub-batch accept nothing
+            const float lox = cg_warp_min(in ? q.x : INFINITY), hix = cg_warp_max(in ? q.x : -INFINITY);
+            const float loy = cg_warp_min(in ? q.y : INFINITY), hiy = cg_warp_max(in ? q.y : -INFINITY);
+            const float loz = cg_warp_min(in ? q.z : INFINITY), hiz = cg_warp_max(in ? q.z : -INFINITY);
+            // ---- block of cells: every cell a photon within maxdist of one of the queries can be in (monotone cell coordinate)
+            const int xa = pv_cell_coord(lox - slack, g.origin[0], g.inv_hx, g.dims[0]), xb = pv_cell_coord(hix + slack, g.origin[0], g.inv_hx, g.dims[0]);
+            const int y0 = pv_cell_coord(loy - slack, g.origin[1], g.inv_h, g.dims[1]), y1 = pv_cell_coord(hiy + slack, g.origin[1], g.inv_h, g.dims[1]);
+            const int z0 = pv_cell_coord(loz - slack, g.origin[2], g.inv_h, g.dims[2]), z1 = pv_cell_coord(hiz + slack, g.origin[2], g.inv_h, g.dims[2]);
+            const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+            if (nrows > 32) {                                                  // radius far above the cell size: not this kernel's case
+                if (in) { handed_over = true; a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s; }
+                continue;
+            }
+            // lane j < nrows owns row (y0 + j % ny, z0 + j / ny): ONE contiguous photon run [rs, re).  Runs are then ordered by
+            // Morton index, i.e. by photon position in the map.
+            uint32_t rk = 0xFFFFFFFFu, rs = 0, re = 0;
+            if ((int)lane < nrows) {
+                rk = pv_morton2((uint32_t)(y0 + (int)lane % ny), (uint32_t)(z0 + (int)lane / ny));
+                const uint32_t rowkey = rk << g.xbits;
+                rs = __ldg(a.m.cell_start + (rowkey | (uint32_t)xa));
+                re = __ldg(a.m.cell_start + (rowkey | (uint32_t)xb) + 1);
+            }
+            uint32_t rank = 0;
+            for (int j = 0; j < nrows; ++j) rank += __shfl_sync(PV_FULL, rk, j) < rk ? 1u : 0u;
+            __syncwarp();
+            if ((int)lane < nrows) { run_rs[rank] = rs; run_len[rank] = re - rs; }
+            __syncwarp();
+            uint32_t my_rs = 0, my_len = 0;
+            if ((int)lane < nrows) { my_rs = run_rs[lane]; my_len = run_len[lane]; }
+            uint32_t inc = my_len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= (uint32_t)o) inc += t; }
+            const uint32_t T = __shfl_sync(PV_FULL, inc, 31), E = inc - my_len;
+            st_cand += (unsigned long long)T * __popc(gm);
+
+            for (uint32_t cb = 0; cb < T; cb += CG_STAGE) {
+                const uint32_t cend = min(T, cb + CG_STAGE), n = cend - cb;
+                // ---- stage: generic-proxy reads of the previous round are ordered before the async-proxy writes of this one
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(mbar, n * (iso ? 16u : 32u));
+                {
+                    const uint32_t lo = max(E, cb), hi = min(E + my_len, cend);
+                    if (lo < hi) {
+                        tma_bulk_g2s(spos_addr + (lo - cb) * 16u, a.m.pos4 + my_rs + (lo - E), (hi - lo) * 16u, mbar);
+                        if (!iso) tma_bulk_g2s(swi_addr + (lo - cb) * 16u, a.m.wi4 + my_rs + (lo - E), (hi - lo) * 16u, mbar);
+                    }
+                }
+                mbar_wait(mbar, phase);
+                phase ^= 1u;
+                if (lane < CG_U) spos[n + lane] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // the unrolled scan may read past n
+                __syncwarp();
+                // ---- scan (lane == query); a sum phase whenever a list could fill up, and at the end of the round.  A round of
+                // CG_U candidates adds at most CG_U entries to a list, so (CG_CAP - longest list) / CG_U rounds need no check.
+                uint32_t *lp = lidx + lane;                                        // next free slot of this lane's list
+                uint32_t c0 = 0;
+                for (;;) {
+                    const uint32_t longest = __reduce_max_sync(PV_FULL, (uint32_t)(lp - (lidx + lane)) >> 5);
+                    const uint32_t room = (CG_CAP - longest) / CG_U;               // rounds that cannot overflow any list
+                    if (c0 < n && room != 0) {
+                        const uint32_t stop = min(n, c0 + room * CG_U);
+                        for (; c0 < stop; c0 += CG_U) {
+                            float4 p[CG_U];
+#pragma unroll
+                            for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];   // broadcast loads first: their latencies overlap
+#pragma unroll
+                            for (int u = 0; u < CG_U; ++u) {
+                                const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
+                                const float d2 = dx * dx + dy * dy + dz * dz;      // (p1 - p2).LengthSquared(), geometry.h:116,526
+                                if (d2 < r2) { *lp = c0 + u; lp += 32; mx = fmaxf(mx, d2); }
+                            }
+                        }
+                        continue;
+                    }
+                    if (longest == 0) break;                                       // round finished, nothing pending
+                    const uint32_t cnt = (uint32_t)(lp - (lidx + lane)) >> 5;
+                    // ---- weigh (lane == query): phase function of each accepted photon, photon index resolved.  Every list is
+                    // padded to the same multiple of four with zero-weight entries (an exact no-op in the sums below).
+                    const uint32_t m4 = (longest + 3u) & ~3u;
+                    for (uint32_t e = 0; e < m4; ++e) {
+                        float ph = 0.f;
+                        if (e < cnt) {
+                            const uint32_t c = lidx[e * 32 + lane];
+                            ph = pc;
+                            if (!iso) {
+                                const float4 wv = swi[c];
+                                const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
+                                const float rsq = rsqrtf(gg1 - g2 * costheta);
+                                ph = pc * rsq * rsq * rsq;
+                            }
+                            pad_idx = __float_as_uint(spos[c].w);
+                        }
+                        lidx[e * 32 + lane] = pad_idx;                             // padding: this query's own last photon, weight 0
+                        lw[e * 32 + lane] = ph;
+                    }
+                    fcnt[lane] = cnt;
+                    __syncwarp();
+                    // ---- sum: 8 lanes x float4 per alpha line; each 8-lane group runs TWO queries' fma chains side by side
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t qa = grp + 4u * (uint32_t)i, qb = qa + 16u;
+                        const uint32_t nq = (max(fcnt[qa], fcnt[qb]) + 3u) & ~3u;
+                        if (nq == 0) continue;
+                        float4 A = part[qa * 8 + sub], B = part[qb * 8 + sub];
+                        const uint32_t *ia = lidx + qa; const float *wa = lw + qa;
+#pragma unroll 1
+                        for (uint32_t e = 0; e < nq; e += 4, ia += 128, wa += 128) {
+                            const uint32_t a0 = ia[0], a1 = ia[32], a2 = ia[64], a3 = ia[96], b0 = ia[16], b1 = ia[48], b2 = ia[80], b3 = ia[112];
+                            const float4 x0 = __ldg(a4 + (size_t)a0 * 8), y0 = __ldg(a4 + (size_t)b0 * 8), x1 = __ldg(a4 + (size_t)a1 * 8),
+                                         y1 = __ldg(a4 + (size_t)b1 * 8), x2 = __ldg(a4 + (size_t)a2 * 8), y2 = __ldg(a4 + (size_t)b2 * 8),
+                                         x3 = __ldg(a4 + (size_t)a3 * 8), y3 = __ldg(a4 + (size_t)b3 * 8);
+                            const float u0 = wa[0], u1 = wa[32], u2 = wa[64], u3 = wa[96], v0 = wa[16], v1 = wa[48], v2 = wa[80], v3 = wa[112];
+                            A.x = fmaf(x0.x, u0, A.x); A.y = fmaf(x0.y, u0, A.y); A.z = fmaf(x0.z, u0, A.z); A.w = fmaf(x0.w, u0, A.w);
+                            B.x = fmaf(y0.x, v0, B.x); B.y = fmaf(y0.y, v0, B.y); B.z = fmaf(y0.z, v0, B.z); B.w = fmaf(y0.w, v0, B.w);
+                            A.x = fmaf(x1.x, u1, A.x); A.y = fmaf(x1.y, u1, A.y); A.z = fmaf(x1.z, u1, A.z); A.w = fmaf(x1.w, u1, A.w);
+                            B.x = fmaf(y1.x, v1, B.x); B.y = fmaf(y1.y, v1, B.y); B.z = fmaf(y1.z, v1, B.z); B.w = fmaf(y1.w, v1, B.w);
+                            A.x = fmaf(x2.x, u2, A.x); A.y = fmaf(x2.y, u2, A.y); A.z = fmaf(x2.z, u2, A.z); A.w = fmaf(x2.w, u2, A.w);
+                            B.x = fmaf(y2.x, v2, B.x); B.y = fmaf(y2.y, v2, B.y); B.z = fmaf(y2.z, v2, B.z); B.w = fmaf(y2.w, v2, B.w);
+                            A.x = fmaf(x3.x, u3, A.x); A.y = fmaf(x3.y, u3, A.y); A.z = fmaf(x3.z, u3, A.z); A.w = fmaf(x3.w, u3, A.w);
+                            B.x = fmaf(y3.x, v3, B.x); B.y = fmaf(y3.y, v3, B.y); B.z = fmaf(y3.z, v3, B.z); B.w = fmaf(y3.w, v3, B.w);
+                        }
+                        part[qa * 8 + sub] = A; part[qb * 8 + sub] = B;
+                    }
+                    __syncwarp();
+                    tot += cnt; lp = lidx + lane;
+                }
+            }
+        }
+
+        // ---- finish: LPhoton's tail (photonvolume.cpp:83-104) per query, one 128-byte row of L_ii per step
+        const bool over = valid && !handed_over && tot > a.nused;
+        if (over) a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s;       // needs the k-nearest selection
+        const bool done = valid && !handed_over && !over;
+        st_found += __reduce_add_sync(PV_FULL, done ? tot : 0u);
+        st_heap += __popc(__ballot_sync(PV_FULL, done && tot == a.nused));
+        qcnt[lane] = tot; qmx[lane] = mx;
+        const uint32_t dmask = __ballot_sync(PV_FULL, done);
+        st_lookups += __popc(dmask);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t ql = grp + 4u * (uint32_t)i;
+            if (!((dmask >> ql) & 1u)) continue;
+            const uint32_t cq = qcnt[ql];
+            const float mq = qmx[ql], dn = qdens[ql];
+            const float4 acc = part[ql * 8 + sub];
+            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cq >= 10) {
+                const float dV = mq * __fsqrt_rn(mq);
+                const float s0 = sg[0] * dn, s1 = sg[1] * dn, s2 = sg[2] * dn, s3 = sg[3] * dn;       // sigma_s(pt)
+                const bool any_scale = __ballot_sync(gmask8, s0 != 0.f || s1 != 0.f || s2 != 0.f || s3 != 0.f) != 0;
+                if (dV != 0.f && any_scale) {
+                    const float f = (float)(4.0 / 3.0 * (double)PV_PI_F * (double)dV);                // 4.0/3.0*M_PI*dV is a double expression
+                    out.x = __fdiv_rn(acc.x, s0 * f); out.y = __fdiv_rn(acc.y, s1 * f);
+                    if (sub != 7) { out.z = __fdiv_rn(acc.z, s2 * f); out.w = __fdiv_rn(acc.w, s3 * f); }      // bins 30, 31 are padding
+                }
+            }
+            reinterpret_cast<float4 *>(a.lii + (size_t)qstep[ql] * 32)[sub] = out;
+        }
+        __syncwarp();
+    }
+    if (a.stats) {
+        st_cand = __shfl_sync(PV_FULL, st_cand, 0);
+        if (lane == 0) {
+            atomicAdd((unsigned long long *)&a.stats->lookups, (unsigned long long)st_lookups);
+            atomicAdd((unsigned long long *)&a.stats->photons_found, (unsigned long long)st_found);
+            atomicAdd((unsigned long long *)&a.stats->candidates_tested, st_cand);
+            atomicAdd((unsigned long long *)&a.stats->heap_lookups, (unsigned long long)st_heap);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
+    const unsigned long long total = ga.total_steps;
+    if (total == 0) return PV_OK;
+    if (total > 0xFFFFFFF0ull) { ctx->err = "pv_gather: too many march steps in one slice for 32-bit step indices"; return PV_ENOMEM; }
+    const GridParams &g = ga.m.g;
+    int rc = pv_ensure(ctx, &ctx->cg_sort, &ctx->cg_sort_bytes, (size_t)total * 4 * sizeof(uint32_t) + 256); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->cg_overflow, &ctx->cg_overflow_bytes, (size_t)total * sizeof(uint32_t) + 256); if (rc) return rc;
+    uint32_t *keys = (uint32_t *)ctx->cg_sort, *vals = keys + total, *keys_tmp = vals + total, *vals_tmp = keys_tmp + total;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters + CG_CNT_BATCH, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    cg_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(g, ga.rays, ga.steps, total, keys, vals);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    uint32_t *skeys, *svals;
+    rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, total, std::max(1, g.xbits + 2 * g.yzbits), &skeys, &svals); if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[0], ctx->stream));
+
+    CgArgs a;
+    a.m = ga.m; a.sc = ga.sc; a.rays = ga.rays; a.steps = ga.steps; a.order = svals; a.total = total; a.maxdist = ga.maxdist; a.nused = ga.nused;
+    a.lii = ga.lii; a.overflow = (uint32_t *)ctx->cg_overflow; a.counters = ctx->d_counters; a.stats = ga.stats;
+    const size_t smem = (size_t)CG_WARP_BYTES * CG_WARPS;
+    static_assert((size_t)CG_WARP_BYTES * CG_WARPS <= 227 * 1024, "cellgather: shared memory per CTA");
+    PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(cellgather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cellgather_kernel, CG_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    cellgather_kernel<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
+    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[1], ctx->stream));
+    return PV_OK;
+}

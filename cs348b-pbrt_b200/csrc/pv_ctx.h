@@ -70,6 +70,7 @@ struct pv_ctx {
 
     // scratch for sort / staging
     void *scratch = nullptr; size_t scratch_bytes = 0;
+    void *sort_hist = nullptr; size_t sort_hist_bytes = 0;   // digit histograms of the radix sort
     void *io = nullptr; size_t io_bytes = 0;       // device staging for host-pointer entry points
     void *io2 = nullptr; size_t io2_bytes = 0;
 
@@ -79,6 +80,10 @@ struct pv_ctx {
     void *march_hdr = nullptr; size_t march_hdr_bytes = 0;
     void *march_steps = nullptr; size_t march_steps_bytes = 0;
     void *lii = nullptr; size_t lii_bytes = 0;     // per-step in-scattered radiance of the step-parallel gather (32 floats per step)
+    void *cg_sort = nullptr; size_t cg_sort_bytes = 0;           // cell-batched gather: (cell key, step) pairs and their sort buffers
+    void *cg_overflow = nullptr; size_t cg_overflow_bytes = 0;   // steps left to the warp-per-step kernel (more than nused photons in range)
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};   // after sort / after cellgather_kernel / after the overflow pass
+    float phase_ms[4] = {0.f, 0.f, 0.f, 0.f};                    // last pv_gather: step sort, cellgather_kernel, overflow pass, recurrence
     unsigned long long *h_total = nullptr;         // mapped pinned word: step count of the slice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // around gather_kernel
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels

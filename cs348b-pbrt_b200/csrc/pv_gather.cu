@@ -18,8 +18,10 @@
 // identical fp32 positions, ties by photon index); radiance is within 1e-4 relative of the reference
 // (summation order and libm differ), see tests/test_gpu_parity.py.
 #include <algorithm>
+#include <cstdlib>
 #include "pv_grid.cuh"
 #include "pv_march.cuh"
+#include "pv_gather.cuh"
 
 #ifndef GW_WARPS
 #define GW_WARPS 4                       // warps per CTA
@@ -62,14 +64,6 @@
 #define GW_STR(x) #x
 #define GW_UNROLL(n) _Pragma(GW_STR(unroll n))
 
-struct MapView {
-    const float4 *pos4;            // x, y, z, sorted position of the photon (bits): a staged candidate carries its own address
-    const float4 *wi4; const float *alpha32; const uint32_t *cell_start;
-    const uint32_t *orig;          // sorted position -> original photon index (tie-breaks and the k-NN output only)
-    GridParams g;
-    uint64_t n;
-    int need_wi;                   // the medium's phase function depends on wi (g != 0)
-};
 // per-warp shared memory: candidate list of (d2 bits, photon position) pairs, select histogram, run tables of the
 // current batch, mbarrier, TMA staging buffer
 // layout per warp: ent[cap] | hist[256] | stats[8] | mbarrier (16 B) | stage[GW_STAGE]
@@ -91,33 +85,8 @@ __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(PV_FULL, v, o));
     return v;
 }
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t wb_mbar(const WarpBuf &b) { return smem_u32(b.hdr + 1024 + 32); }
 __device__ __forceinline__ uint32_t wb_stage_addr(const WarpBuf &b) { return smem_u32(b.hdr + WB_HDR_BYTES); }
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(mbar), "r"(phase) : "memory");
-}
-// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-
 // Keep the k smallest (d2, original index) entries of ent[0..count); returns the new count (== k) and the
 // k-th distance.  count > k on entry, entries hold photon positions.  MSB radix select over the fp32 bit pattern
 // (non-negative floats order like unsigned ints), 8-bit digits, histogram in shared memory.  Only reached when
@@ -962,23 +931,6 @@ __device__ __noinline__ float rainbow_bin(float Ld, v3 w, v3 wi, uint32_t lane) 
     return (Ld * mistI + rb * rainbowI) * I;
 }
 
-struct GatherArgs {
-    MapView m;
-    const DevScene *sc;
-    const pv_ray *rays;
-    const RayHdr *hdr;             // per ray: where its march steps are (pv_march.cu)
-    const StepRec *steps;
-    uint64_t n;
-    float maxdist;
-    uint32_t nused, flags, cap;
-    float *L, *T;
-    pv_gather_stats *stats;
-    unsigned long long *counter;
-    // step-parallel ("latency") form: in-scattered radiance of every march step, 32 floats per StepRec, filled by
-    // gather_lii_kernel and consumed by gather_kernel<true>
-    float *lii; unsigned long long total_steps;
-};
-
 // wo of Light::Sample_L(p, ...) recomputed in the spectral pass (rainbow media only)
 __device__ __forceinline__ v3 light_wo(const pv_light &l, v3 p) {
     if (l.type == PV_LIGHT_DISTANT) return V3(l.dir[0], l.dir[1], l.dir[2]);
@@ -1096,6 +1048,86 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_kernel(GatherA
     flush_stats(a.stats, b, nrays, lane);
 }
 
+// The Lv/Tr recurrence alone (photonvolume.cpp:147-217 without LPhoton): the in-scattered radiance of every march step was
+// computed beforehand (gather_lii_kernel / cellgather_kernel, 32 floats per step in a.lii).  Same arithmetic per step as
+// gather_kernel -- bit-identical results -- but no shared memory (full occupancy) and the L_ii rows of eight steps are
+// requested ahead of the sequential part, so the kernel streams instead of waiting for one row per step.
+#define RC_THREADS 256
+#define RC_AHEAD 8
+__global__ void __launch_bounds__(RC_THREADS) recurrence_kernel(GatherArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    const bool bin = lane < PV_NSPEC;
+    const float sig_a = bin ? med.sigma_a[lane] : 0.f, sig_s = bin ? med.sigma_s[lane] : 0.f, le = bin ? med.le[lane] : 0.f;
+    const float sig_t = sig_a + sig_s;
+    float y_sig_a = 0.f, y_sig_s = 0.f;
+    for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
+    const bool y_any = y_sig_a != 0.f || y_sig_s != 0.f;
+    const bool rainbow = med.type == PV_MEDIUM_RAINBOW;
+    const bool do_lookup = !rainbow && !(a.flags & PV_GATHER_NO_INDIRECT);
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * RC_THREADS) >> 5;
+    uint32_t nrays = 0;
+    for (unsigned long long ri = ((unsigned long long)blockIdx.x * RC_THREADS + threadIdx.x) >> 5; ri < a.n; ri += nwarps) {
+        nrays++;
+        const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri));
+        const int nSamples = __float_as_int(h0.z);
+        const float step = h0.w;
+        const unsigned long long first = ((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x);
+        const StepRec *recs = a.steps + first;
+        float Tr = 1.f, Lv = 0.f;
+        if (nSamples > 0) {
+            const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
+            const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
+            bool stop = false;
+            for (int c0 = 0; c0 < nSamples && !stop; c0 += 32) {
+                float c_t = 0.f, c_tau = 0.f, c_rr = -1.f, c_dens = 0.f, c_sh = 0.f, c_dfac = 0.f;
+                int c_ln = 0;
+                if (c0 + (int)lane < nSamples) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(recs + c0 + lane);
+                    const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
+                    c_t = ra.x; c_tau = ra.y; c_rr = ra.z; c_dens = ra.w; c_sh = rb.x; c_dfac = rb.y; c_ln = __float_as_int(rb.z);
+                }
+                const int nthis = min(32, nSamples - c0);
+                const float *lrow = a.lii + (first + (unsigned long long)c0) * 32 + lane;
+                for (int i0 = 0; i0 < nthis && !stop; i0 += RC_AHEAD) {
+                    float li[RC_AHEAD];
+#pragma unroll
+                    for (int k = 0; k < RC_AHEAD; ++k) li[k] = (do_lookup && i0 + k < nthis) ? __ldg(lrow + (size_t)(i0 + k) * 32) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < RC_AHEAD; ++k) {
+                        const int i = i0 + k;
+                        if (i >= nthis) break;
+                        const float s_tau = __shfl_sync(PV_FULL, c_tau, i);
+                        const float s_rr = __shfl_sync(PV_FULL, c_rr, i);
+                        Tr = expf(-(sig_t * s_tau));                          // Exp(-stepTau): per-step, not cumulative (:155)
+                        if (s_rr >= 0.f) {
+                            if (s_rr > .5f) { Tr = 0.f; stop = true; break; }
+                            Tr = Tr * 2.f;                                    // Tr /= continueProb (0.5): exact
+                        }
+                        const float s_dens = __shfl_sync(PV_FULL, c_dens, i);
+                        const float ss = sig_s * s_dens, sa = sig_a * s_dens;
+                        float L_d = 0.f;
+                        const float s_dfac = __shfl_sync(PV_FULL, c_dfac, i);
+                        if (s_dfac != 0.f) {
+                            const pv_light &lt = sc.lights[__shfl_sync(PV_FULL, c_ln, i)];
+                            const float I = bin ? lt.intensity[lane] : 0.f;
+                            const float Ld = (I * expf(-(sig_t * __shfl_sync(PV_FULL, c_sh, i)))) * s_dfac;
+                            L_d = rainbow ? rainbow_bin(Ld, rd, light_wo(lt, ray_at(ro, rd, __shfl_sync(PV_FULL, c_t, i))), lane) : Ld;
+                        }
+                        const float L_ii = li[k];
+                        // L_i = L_d + (ss/(sa+ss)) * L_ii unless sa.y() == 0 && ss.y() == 0 (photonvolume.cpp:210-213)
+                        const float L_i = (s_dens != 0.f && y_any) ? L_d + __fdiv_rn(ss, sa + ss) * L_ii : L_d;
+                        Lv = ((sa * (le * s_dens)) * step) + ((ss * L_i) * step) + (Tr * Lv);
+                    }
+                }
+            }
+        }
+        if (bin) { a.L[ri * PV_NSPEC + lane] = Lv; a.T[ri * PV_NSPEC + lane] = Tr; }
+    }
+    if (lane == 0 && a.stats && nrays) atomicAdd((unsigned long long *)&a.stats->rays, (unsigned long long)nrays);
+}
+
 // One warp per march STEP of the slice: the photon lookup and the radiance estimate of that step (the part of gather_kernel's
 // loop body that does not depend on the other steps of the ray).
 __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_lii_kernel(GatherArgs a) {
@@ -1105,11 +1137,13 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_lii_kernel(Gat
     const DevMedium &med = a.sc->med;
     const float sig_s = lane < PV_NSPEC ? med.sigma_s[lane] : 0.f;
     const float r2 = a.maxdist * a.maxdist;
+    const unsigned long long nsteps = a.list ? *a.list_count : a.total_steps;
     for (;;) {
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(a.counter + 3, 1ull);
         g = __shfl_sync(PV_FULL, g, 0);
-        if (g >= a.total_steps) break;
+        if (g >= nsteps) break;
+        if (a.list) g = __ldg(a.list + g);
         const float4 *rp = reinterpret_cast<const float4 *>(a.steps + g);
         const float4 ra = __ldg(rp), rb = __ldg(rp + 1);
         const uint32_t ri = __float_as_uint(rb.w);
@@ -1131,7 +1165,7 @@ static uint32_t lookup_cap(uint32_t k) {
     cap = (cap + 63u) & ~63u;
     return std::max<uint32_t>(cap, 256u);
 }
-static MapView map_view(pv_ctx *ctx) {
+MapView pvi_map_view(pv_ctx *ctx) {
     MapView m; m.pos4 = ctx->m_pos4; m.wi4 = ctx->m_wi4; m.alpha32 = ctx->m_alpha32; m.cell_start = ctx->cell_start; m.orig = ctx->m_orig; m.g = ctx->grid;
     m.n = ctx->map_n;
     m.need_wi = ctx->has_scene && ctx->hscene.med.g != 0.f;
@@ -1158,7 +1192,7 @@ int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, u
     int blocks; size_t smem;
     int rc = launch_cfg(ctx, knn_kernel, cap, &blocks, &smem); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
-    knn_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(map_view(ctx), d_pts, n, k, r2, cap, d_idx, d_d2, d_nfound, ctx->d_counters);
+    knn_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(pvi_map_view(ctx), d_pts, n, k, r2, cap, d_idx, d_d2, d_nfound, ctx->d_counters);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }
@@ -1173,7 +1207,7 @@ int pvi_surface_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_nf, uint
     int blocks; size_t smem;
     int rc = launch_cfg(ctx, surface_lphoton_kernel, cap, &blocks, &smem); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
-    MapView m = map_view(ctx); m.need_wi = 1;
+    MapView m = pvi_map_view(ctx); m.need_wi = 1;
     surface_lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(m, d_pts, d_nf, n, n_lookup, max_dist2, (float)(int)n_paths, cap, d_Lr, d_Lt,
                                                                     ctx->d_counters);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1185,7 +1219,7 @@ int pvi_radiance_nearest(pv_ctx *ctx, const float *d_pts, const float *d_n, uint
     }
     if (d_Lo30 && !ctx->rad_valid) { ctx->err = "pv_radiance_nearest: radiance not computed (call pv_radiance_photons)"; return PV_ESTATE; }
     if (n == 0) return PV_OK;
-    MapView m = map_view(ctx);
+    MapView m = pvi_map_view(ctx);
     radiance_nearest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(m, d_pts, d_n, n, d_idx);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     if (d_Lo30) {
@@ -1202,7 +1236,7 @@ int pvi_final_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, 
     if (!ctx->rad_valid) { ctx->err = "pv_final_gather: radiance not computed (call pv_radiance_photons)"; return PV_ESTATE; }
     if (!(step > 0.f)) { ctx->err = "pv_final_gather: step must be > 0"; return PV_EINVAL; }
     if (n == 0) return PV_OK;
-    MapView m = map_view(ctx);
+    MapView m = pvi_map_view(ctx);
     const unsigned blocks = (unsigned)((n + 127) / 128);
     if (ctx->hscene.n_spheres) final_gather_kernel<true><<<blocks, 128, 0, ctx->stream>>>(m, ctx->dscene, d_rays, n, step, (uint32_t)seed, (uint32_t)(seed >> 32),
                                                                                        index_base, ctx->rad_Lo, d_Lindir, d_idx);
@@ -1220,7 +1254,7 @@ int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, u
     int blocks; size_t smem;
     int rc = launch_cfg(ctx, lphoton_kernel, cap, &blocks, &smem); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream));
-    lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(map_view(ctx), ctx->dscene, d_pts, d_w, n, nused, maxdist, cap, d_L, ctx->d_counters);
+    lphoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(pvi_map_view(ctx), ctx->dscene, d_pts, d_w, n, nused, maxdist, cap, d_L, ctx->d_counters);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }
@@ -1253,7 +1287,7 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
             rc = launch_cfg(ctx, ephoton_kernel, cap, &blocks, &smem);
             if (rc == PV_OK) {
                 cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long), ctx->stream);
-                MapView m = map_view(ctx); m.need_wi = 1;
+                MapView m = pvi_map_view(ctx); m.need_wi = 1;
                 ephoton_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(m, rp.pos, rp.wi, rp.alpha, n, n_lookup, max_dist2, (float)(int)counts[k], cap, E32,
                                                                         ctx->d_counters);
                 if (cudaGetLastError() != cudaSuccess) { ctx->err = "ephoton_kernel launch failed"; rc = PV_ECUDA; }
@@ -1269,41 +1303,57 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
     ctx->rad_valid = true;
     return PV_OK;
 }
+static unsigned recurrence_blocks(pv_ctx *ctx, uint64_t n) {
+    return (unsigned)std::min<uint64_t>((n + RC_THREADS / 32 - 1) / (RC_THREADS / 32), (uint64_t)ctx->sm_count * 8 * 4);
+}
 // Li for rays [0, n): march records first (pv_march.cu), then the gather kernel.  Rays are taken in slices so that the
 // step records of one slice stay within PV_MARCH_MAX_BYTES / the free device memory.
 static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, float *d_L, float *d_T) {
     uint64_t total = 0;
     pv_gather_params p = *prm;
-    int rc = pvi_march(ctx, d_rays, n, &p, flags, &total);
-    if (rc == PV_ENOMEM && n > 4096) {                      // step records do not fit: two half slices
+    auto halves = [&]() -> int {                           // the records of the slice do not fit: two half slices
         const uint64_t h = n / 2;
-        rc = gather_slice(ctx, d_rays, h, prm, flags, d_L, d_T); if (rc) return rc;
-        p.ray_index_base = prm->ray_index_base + h;
-        return gather_slice(ctx, d_rays + h, n - h, &p, flags, d_L + h * PV_NSPEC, d_T + h * PV_NSPEC);
-    }
+        int r = gather_slice(ctx, d_rays, h, prm, flags, d_L, d_T); if (r) return r;
+        pv_gather_params p2 = *prm; p2.ray_index_base = prm->ray_index_base + h;
+        return gather_slice(ctx, d_rays + h, n - h, &p2, flags, d_L + h * PV_NSPEC, d_T + h * PV_NSPEC);
+    };
+    int rc = pvi_march(ctx, d_rays, n, &p, flags, &total);
+    if (rc == PV_ENOMEM && n > 4096) return halves();
     if (rc == PV_ENOMEM) ctx->err = "pv_gather: out of device memory for the march records";
     if (rc) return rc;
     GatherArgs a;
-    a.m = map_view(ctx); a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (const StepRec *)ctx->march_steps;
+    a.m = pvi_map_view(ctx); a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (const StepRec *)ctx->march_steps;
     a.n = n; a.maxdist = prm->maxdist;
     a.nused = prm->nused; a.flags = flags; a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
     a.L = d_L; a.T = d_T; a.stats = ctx->d_stats; a.counter = ctx->d_counters;
-    a.lii = nullptr; a.total_steps = total;
+    a.lii = nullptr; a.total_steps = total; a.list = nullptr; a.list_count = nullptr;
     int blocks; size_t smem;
-    // Which form?  Step-parallel when the rays are too few to fill the persistent grid (one warp per ray) and the per-step
-    // results fit comfortably; PV_GATHER_STEP_PARALLEL / PV_GATHER_RAY_PARALLEL in params->flags force one or the other.
-    const bool lookups = !(flags & PV_GATHER_NO_INDIRECT);
-    bool step_parallel = lookups && total > 0 && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
-    if (flags & PV_GATHER_STEP_PARALLEL) step_parallel = lookups && total > 0;
-    if (flags & PV_GATHER_RAY_PARALLEL) step_parallel = false;
-    if (step_parallel) {
-        rc = pv_ensure(ctx, &ctx->lii, &ctx->lii_bytes, (size_t)total * 32 * sizeof(float)); if (rc) return rc;
+    // Which schedule for the lookups?  (results: cell-batched sums each step's photons in photon order; the two warp forms are
+    // bit-identical to each other and agree with it to rounding)
+    //   cell-batched   steps sorted by photon-grid cell, one warp per batch of 32 (pv_cellgather.cu): the default whenever the
+    //                  search radius fits the cells (fixed-radius regime); steps with more than nused photons in range fall
+    //                  through to the warp-per-step kernel;
+    //   step-parallel  one warp per march step (k-nearest regime, small batches);
+    //   ray-parallel   one warp per ray, lookups fused with the recurrence (k-nearest regime, frames).
+    // PV_GATHER_CELL_BATCHED / PV_GATHER_STEP_PARALLEL / PV_GATHER_RAY_PARALLEL in params->flags force one.
+    const bool lookups = !(flags & PV_GATHER_NO_INDIRECT) && total > 0;
+    static const bool legacy_default = getenv("PV_GATHER_LEGACY") != nullptr;               // A/B knob: the round-1 schedules
+    bool cell = lookups && !legacy_default && a.m.n > 0 && prm->maxdist <= ctx->grid.h;
+    bool step_parallel = lookups && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
+    if (flags & PV_GATHER_STEP_PARALLEL) { step_parallel = lookups; cell = false; }
+    if (flags & PV_GATHER_RAY_PARALLEL) { step_parallel = false; cell = false; }
+    if (flags & PV_GATHER_CELL_BATCHED) cell = lookups && a.m.n > 0;
+    if (cell) step_parallel = false;
+    if (step_parallel || cell) {
+        rc = pv_ensure(ctx, &ctx->lii, &ctx->lii_bytes, (size_t)total * 32 * sizeof(float));
+        if (rc == PV_ENOMEM && n > 4096) return halves();
+        if (rc) return rc;
         a.lii = (float *)ctx->lii;
     }
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 #if GW_RANGES_PRE
-    if (!step_parallel && lookups && total > 0) {           // inside the ev0..ev1 bracket: the kernel time reported stays comparable
+    if (!step_parallel && !cell && lookups) {               // inside the ev0..ev1 bracket: the kernel time reported stays comparable
         rc = pv_ensure(ctx, &ctx->lii, &ctx->lii_bytes, (size_t)total * sizeof(StepRanges)); if (rc) return rc;
         a.lii = (float *)ctx->lii;
         ranges_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a.m, d_rays, a.steps, total, prm->maxdist, a.nused,
@@ -1311,12 +1361,23 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
 #endif
-    if (step_parallel) {
+    if (cell) {
+        rc = pvi_cellgather(ctx, a);                        // records tev[0] (steps sorted) and tev[1] (cellgather_kernel done)
+        if (rc == PV_ENOMEM && n > 4096) return halves();
+        if (rc) return rc;
+        // the steps it left over (more than nused photons in range): warp-per-step kernel over the overflow list
+        GatherArgs o = a;
+        o.list = (const uint32_t *)ctx->cg_overflow; o.list_count = ctx->d_counters + CG_CNT_OVERFLOW;
+        rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
+        gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(o);
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[2], ctx->stream));
+        recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
+    } else if (step_parallel) {
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
-        rc = launch_cfg(ctx, gather_kernel<true>, a.cap, &blocks, &smem); if (rc) return rc;
-        gather_kernel<true><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+        recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
     } else {
         rc = launch_cfg(ctx, gather_kernel<false>, a.cap, &blocks, &smem); if (rc) return rc;
         gather_kernel<false><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
@@ -1328,6 +1389,12 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms += ms;
     cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3); ctx->last_march_ms += ms;
+    if (cell) {
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->tev[0]); ctx->phase_ms[0] += ms;
+        cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]); ctx->phase_ms[1] += ms;
+        cudaEventElapsedTime(&ms, ctx->tev[1], ctx->tev[2]); ctx->phase_ms[2] += ms;
+        cudaEventElapsedTime(&ms, ctx->tev[2], ctx->ev1); ctx->phase_ms[3] += ms;
+    }
     return PV_OK;
 }
 int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, float *d_L, float *d_T) {
@@ -1337,6 +1404,7 @@ int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_pa
     if (need_map && ctx->map_which != PV_MAP_VOLUME) { ctx->err = "pv_gather: the grid is built over a surface photon map (call pv_build)"; return PV_ESTATE; }
     if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
     ctx->last_ms = 0.f; ctx->last_march_ms = 0.f;
+    for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0.f;
     if (n == 0) return PV_OK;
     const uint32_t flags = prm->flags | (need_map ? 0u : PV_GATHER_NO_INDIRECT);
     const uint64_t slice = PV_GATHER_SLICE_RAYS;

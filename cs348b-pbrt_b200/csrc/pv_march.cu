@@ -132,6 +132,14 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
             }
             out[0] = make_float4(c_t, c_tau, c_rr, c_dens);
             out[1] = make_float4(c_sh, c_dfac, __int_as_float(c_ln), __uint_as_float((uint32_t)ri));    // pad = the ray of the step (slice-relative)
+            if (c_rr > .5f && !(a.flags & PV_GATHER_NO_INDIRECT)) {   // the roulette ends the photon-volume march here (the volint kernels
+                                                                     // decide on the cumulative Tr instead): the remaining records are dead
+                for (++si, out += 2; si < nSamples; ++si, out += 2) {
+                    out[0] = make_float4(0.f, 0.f, PV_RR_DEAD, 0.f);
+                    out[1] = make_float4(0.f, 0.f, 0.f, __uint_as_float((uint32_t)ri));
+                }
+                break;
+            }
         }
     }
     ns = __reduce_add_sync(PV_FULL, ns); nshadow = __reduce_add_sync(PV_FULL, nshadow);

@@ -19,11 +19,14 @@ struct RayHdr {
 struct StepRec {
     float t;      // sample parameter: p = ray(t), t accumulated as the reference does (t0 += step)
     float tau;    // optical-depth scalar of the step segment: tau[b] = sigma_t[b] * tau
-    float rr;     // Russian-roulette draw if Tr.y() < 1e-3 at this step, else -1
+    float rr;     // Russian-roulette draw if Tr.y() < 1e-3 at this step, else -1; PV_RR_DEAD: the march ended at an earlier step
     float dens;   // density at p (1/0 inside/outside for homogeneous media)
     float sh;     // optical-depth scalar of the shadow ray
     float dfac;   // falloff / dist^2 * phase * nLights (0: unlit or occluded): L_d[b] = I[b] * exp(-sigma_t[b]*sh) * dfac
     int ln;       // light chosen for the step
     uint32_t pad; // index of the step's ray within the slice (the step-parallel gather finds its ray through it)
 };
+// rr of the records behind a step whose roulette draw ended the march (draw > continueProb = .5, photonvolume.cpp:160-163):
+// the recurrence never reaches them, the step-sorted lookups skip them
+#define PV_RR_DEAD 3.f
 static_assert(sizeof(RayHdr) == 32 && sizeof(StepRec) == 32, "march records are two 128-bit words");

@@ -873,6 +873,7 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split) {
     uint64_t *skeys; uint32_t *svals;
     rc = pvi_sort_pairs_u64(ctx, keys, vals, keys_tmp, vals_tmp, n, 64, &skeys, &svals); if (rc) return rc;
     (void)bits;
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the probes below are blocking copies on another stream
     // count survivors: ids <= (last_block * 4096) << 16 | 0xffff
     auto upper_bound = [&](uint64_t limit, uint64_t *out) -> int {  // first position with key > limit (few D2H probes)
         uint64_t probe = 0, lo = 0, hi = n;

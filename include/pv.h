@@ -140,11 +140,16 @@ typedef struct pv_gather_params {
 } pv_gather_params;
 #define PV_GATHER_NO_DIRECT   1u   /* skip the single-scattering term           */
 #define PV_GATHER_NO_INDIRECT 2u   /* skip LPhoton                               */
-/* Scheduling of the lookups (results are bit-identical either way; default: chosen from the number of rays): one warp per
- * RAY (throughput form, frames of camera rays) or one warp per march STEP followed by a recurrence pass (latency form, the
- * small batches of secondary rays: a call then no longer lasts as long as one warp needs for the longest ray).             */
+/* Scheduling of the lookups (default: chosen from the search radius and the number of rays).
+ *   cell-batched   every march step of the slice is sorted by photon-grid cell and one warp serves 32 neighbouring steps from
+ *                  one staged block of cells; the default in the fixed-radius regime (maxdist <= cell size);
+ *   step-parallel  one warp per march STEP followed by a recurrence pass (k-nearest regime, small batches of secondary rays);
+ *   ray-parallel   one warp per RAY, lookups fused with the recurrence (k-nearest regime, frames of camera rays).
+ * The two warp forms are bit-identical to each other; the cell-batched form sums a step's photons in photon order and agrees
+ * with them to rounding (1e-6 relative).  Each form's own result does not depend on how the rays are sharded.               */
 #define PV_GATHER_RAY_PARALLEL  4u
 #define PV_GATHER_STEP_PARALLEL 8u
+#define PV_GATHER_CELL_BATCHED  16u
 
 /* PhotonShooter params (core/photonshooter.cpp:529-548), volume branch. */
 typedef struct pv_shoot_params {
@@ -235,6 +240,10 @@ int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset);
  * kernels that precede it (per-step medium / shadow-ray work).                */
 int pv_last_kernel_ms(pv_ctx *ctx, float *ms);
 int pv_last_march_ms(pv_ctx *ctx, float *ms);
+/* Cell-batched schedule only, device times (ms) of the last call's parts: ms[0] sorting the march steps by cell, ms[1]
+ * cellgather_kernel (lookups + flux sums: the dominant kernel), ms[2] the overflow pass (steps with more than nused photons
+ * in range), ms[3] the recurrence pass.  All zero when another schedule ran.                                                */
+int pv_last_phase_ms(pv_ctx *ctx, float ms[4]);
 
 /* ---- SingleScatteringIntegrator::Li (integrators/single.cpp:66-138) and
  *      EmissionIntegrator::Li (integrators/emission.cpp:63-106) -------------

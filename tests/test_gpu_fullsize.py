@@ -51,7 +51,10 @@ def test_full_frame_is_deterministic_and_shards_exactly(frame):
     L1, T1, s1 = gather_dev(frame)
     L2, T2, s2 = gather_dev(frame)
     assert torch.equal(L1, L2) and torch.equal(T1, T2)
-    assert (s1.lookups, s1.photons_found, s1.candidates_tested) == (s2.lookups, s2.photons_found, s2.candidates_tested)
+    assert (s1.lookups, s1.photons_found) == (s2.lookups, s2.photons_found)
+    # candidates: the cell-batched schedule groups steps that share a cell in step-record order, which the march kernel's
+    # atomics assign per run -- the RESULT of a step does not depend on its batch, the number of distance tests does (slightly)
+    assert abs(s1.candidates_tested - s2.candidates_tested) < 1e-3 * s1.candidates_tested
     assert s1.rays == n and s1.lookups > 50_000_000
     assert bool(torch.isfinite(L1).all()) and float(L1.max()) > 0
     h = n // 2 + 7                                          # not tile aligned
