@@ -14,7 +14,8 @@
 //           computes the reference's unfused (dx*dx + dy*dy) + dz*dz against its own query and appends the accepted
 //           candidate to its own list in shared memory -- no cross-lane traffic, 32 distance tests per ~13 instructions;
 //   weigh   lane == query: phase function per accepted photon (from the staged wi), photon index resolved;
-//   sum     8 lanes x float4 per 128-byte alpha line (128-bit loads), eight queries at a time; each (query, bin) sum runs
+//   sum     when a list could overflow, and at the end of the batch: 8 lanes x float4 per 128-byte alpha line (128-bit
+//           loads), eight queries at a time, longest lists first; each (query, bin) sum runs
 //           over the query's photons in ascending photon order in one fma chain, so a step's result does not depend on
 //           which other steps share its batch (bit-identical under any sharding of the rays);
 //   finish  radius = largest accepted distance, estimate as in LPhoton's tail, one 128-byte row of L_ii per step.
@@ -34,10 +35,10 @@
 #define CG_MIN_CTAS 5
 #endif
 #ifndef CG_STAGE
-#define CG_STAGE 128                     // candidates per TMA round
+#define CG_STAGE 64                      // candidates per TMA round
 #endif
 #ifndef CG_CAP
-#define CG_CAP 32                        // accepted candidates per query between two sum phases
+#define CG_CAP 24                        // accepted candidates per query between two sum phases (multiple of 4)
 #endif
 #ifndef CG_U
 #define CG_U 8                           // scan unroll
@@ -62,15 +63,16 @@ struct CgArgs {
 };
 
 // per-warp shared memory
-#define CG_OFF_POS 0
-#define CG_OFF_WI (CG_OFF_POS + (CG_STAGE + CG_U) * 16)
-#define CG_OFF_LIDX (CG_OFF_WI + CG_STAGE * 16)
-#define CG_OFF_LW (CG_OFF_LIDX + CG_CAP * 32 * 4)
-#define CG_OFF_PART (CG_OFF_LW + CG_CAP * 32 * 4)
-#define CG_OFF_Q (CG_OFF_PART + 32 * 8 * 16)          // fcnt, qcnt, qmx, qdens, qstep, run_rs, run_len: 7 x 32 words
-#define CG_OFF_MBAR (CG_OFF_Q + 7 * 32 * 4)
+#define CG_OFF_POS 0                                                       // staged candidates {x, y, z, photon index}
+#define CG_OFF_WI (CG_OFF_POS + (CG_STAGE + CG_U) * 16)                   // their wi
+#define CG_OFF_LIDX (CG_OFF_WI + CG_STAGE * 16)                           // accepted candidates -> photon indices, [slot][lane]
+#define CG_OFF_LW (CG_OFF_LIDX + CG_CAP * 32 * 4)                         // their phase-function weights, [slot][lane]
+#define CG_OFF_PART (CG_OFF_LW + CG_CAP * 32 * 4)                         // running flux sums, [query][8 x float4]
+#define CG_OFF_Q (CG_OFF_PART + 32 * 8 * 16)                              // fcnt, perm, qcnt, qmx, qdens, qstep, run_rs, run_len
+#define CG_OFF_MBAR (CG_OFF_Q + 8 * 32 * 4)
 #define CG_WARP_BYTES (CG_OFF_MBAR + 16)
-static_assert(CG_WARP_BYTES % 16 == 0, "per-warp shared memory keeps 16-byte alignment");
+static_assert(CG_WARP_BYTES % 16 == 0 && CG_OFF_PART % 16 == 0 && CG_OFF_Q % 16 == 0, "16-byte alignment");
+static_assert(CG_CAP % 4 == 0 && CG_CAP >= CG_U && CG_STAGE % CG_U == 0, "list capacity / unroll");
 
 __device__ __forceinline__ int cg_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float cg_unordered(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
@@ -104,9 +106,10 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
     uint32_t *lidx = reinterpret_cast<uint32_t *>(base + CG_OFF_LIDX);
     float *lw = reinterpret_cast<float *>(base + CG_OFF_LW);
     float4 *part = reinterpret_cast<float4 *>(base + CG_OFF_PART);
-    uint32_t *fcnt = reinterpret_cast<uint32_t *>(base + CG_OFF_Q), *qcnt = fcnt + 32;
+    uint32_t *fcnt = reinterpret_cast<uint32_t *>(base + CG_OFF_Q), *perm = fcnt + 32, *qcnt = perm + 32;
     float *qmx = reinterpret_cast<float *>(qcnt + 32), *qdens = qmx + 32;
     uint32_t *qstep = reinterpret_cast<uint32_t *>(qdens + 32), *run_rs = qstep + 32, *run_len = run_rs + 32;
+    const uint32_t lidx_addr = smem_u32(lidx) + lane * 4u;
     const uint32_t mbar = smem_u32(base + CG_OFF_MBAR), spos_addr = smem_u32(spos), swi_addr = smem_u32(swi);
     if (lane == 0) mbar_init(mbar, 1);
     __syncwarp();
@@ -157,6 +160,83 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         qstep[lane] = s; qdens[lane] = dens;
         uint32_t tot = 0, pad_idx = 0; float mx = 0.f; bool handed_over = false;
         uint32_t remaining = __ballot_sync(PV_FULL, valid);
+        // Per-lane list of accepted candidates, [slot][lane]: entries [0, res) are resolved to (photon index, weight), entries
+        // [res, cnt) still hold the candidate's position in the current stage.  The lists live on across stages and sub-batches
+        // and are summed when one could overflow, and at the end of the batch.
+        uint32_t lp = lidx_addr, res = 0;                                          // shared-memory address of this lane's next free slot
+        // ---- weigh (lane == query): phase function of each newly accepted photon, photon index resolved
+        auto resolve = [&]() {
+            const uint32_t cnt = (lp - lidx_addr) >> 7;
+            const uint32_t lo = __reduce_min_sync(PV_FULL, res), hi = __reduce_max_sync(PV_FULL, cnt);
+            for (uint32_t e = lo; e < hi; ++e) {
+                if (e >= res && e < cnt) {
+                    const uint32_t c = lidx[e * 32 + lane];
+                    float ph = pc;
+                    if (!iso) {
+                        const float4 wv = swi[c];
+                        const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
+                        float rsq;                                                 // rsqrtf() of a normal number (the argument is >= (1 - |g|)^2)
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsq) : "f"(gg1 - g2 * costheta));
+                        ph = pc * rsq * rsq * rsq;
+                    }
+                    pad_idx = __float_as_uint(spos[c].w);
+                    lidx[e * 32 + lane] = pad_idx;
+                    lw[e * 32 + lane] = ph;
+                }
+            }
+            res = cnt;
+        };
+        // ---- sum: 8 lanes x float4 per alpha line; each 8-lane group runs TWO queries' fma chains side by side
+        auto sum = [&]() {
+            const uint32_t cnt = (lp - lidx_addr) >> 7;
+            const uint32_t longest = __reduce_max_sync(PV_FULL, cnt);
+            // every list is padded to the same multiple of four with zero-weight entries of the query's own last photon (an
+            // exact no-op in the sums)
+            const uint32_t m4 = (longest + 3u) & ~3u;
+            for (uint32_t e = __reduce_min_sync(PV_FULL, cnt); e < m4; ++e)
+                if (e >= cnt) { lidx[e * 32 + lane] = pad_idx; lw[e * 32 + lane] = 0.f; }
+            // queries in descending order of list length (in units of four entries, the granularity of the sums): the eight lists
+            // summed side by side then have nearly equal lengths, so few lanes idle on padding.  Counting sort with one ballot
+            // per possible length.
+            const uint32_t c4n = (cnt + 3u) >> 2;
+            uint32_t rank = 0, before = 0;
+#pragma unroll
+            for (int v = CG_CAP / 4; v >= 0; --v) {
+                const uint32_t mv = __ballot_sync(PV_FULL, c4n == (uint32_t)v);
+                if (c4n == (uint32_t)v) rank = before + __popc(mv & lanemask_lt());
+                before += __popc(mv);
+            }
+            fcnt[lane] = cnt; perm[rank] = lane;
+            __syncwarp();
+            // the trip count of a round is warp-uniform: the longest of its eight lists is the first one
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t nq = (fcnt[perm[8 * i]] + 3u) & ~3u;
+                if (nq == 0) break;
+                const uint32_t qa = perm[8 * i + grp], qb = perm[8 * i + 4 + grp];
+                float4 A = part[qa * 8 + sub], B = part[qb * 8 + sub];
+                const uint32_t *ia = lidx + qa, *ib = lidx + qb; const float *wa = lw + qa, *wb = lw + qb;
+#pragma unroll 1
+                for (uint32_t e = 0; e < nq; e += 4, ia += 128, ib += 128, wa += 128, wb += 128) {
+                    const uint32_t a0 = ia[0], a1 = ia[32], a2 = ia[64], a3 = ia[96], b0 = ib[0], b1 = ib[32], b2 = ib[64], b3 = ib[96];
+                    const float4 x0 = __ldg(a4 + (size_t)a0 * 8), y0 = __ldg(a4 + (size_t)b0 * 8), x1 = __ldg(a4 + (size_t)a1 * 8),
+                                 y1 = __ldg(a4 + (size_t)b1 * 8), x2 = __ldg(a4 + (size_t)a2 * 8), y2 = __ldg(a4 + (size_t)b2 * 8),
+                                 x3 = __ldg(a4 + (size_t)a3 * 8), y3 = __ldg(a4 + (size_t)b3 * 8);
+                    const float u0 = wa[0], u1 = wa[32], u2 = wa[64], u3 = wa[96], v0 = wb[0], v1 = wb[32], v2 = wb[64], v3 = wb[96];
+                    A.x = fmaf(x0.x, u0, A.x); A.y = fmaf(x0.y, u0, A.y); A.z = fmaf(x0.z, u0, A.z); A.w = fmaf(x0.w, u0, A.w);
+                    B.x = fmaf(y0.x, v0, B.x); B.y = fmaf(y0.y, v0, B.y); B.z = fmaf(y0.z, v0, B.z); B.w = fmaf(y0.w, v0, B.w);
+                    A.x = fmaf(x1.x, u1, A.x); A.y = fmaf(x1.y, u1, A.y); A.z = fmaf(x1.z, u1, A.z); A.w = fmaf(x1.w, u1, A.w);
+                    B.x = fmaf(y1.x, v1, B.x); B.y = fmaf(y1.y, v1, B.y); B.z = fmaf(y1.z, v1, B.z); B.w = fmaf(y1.w, v1, B.w);
+                    A.x = fmaf(x2.x, u2, A.x); A.y = fmaf(x2.y, u2, A.y); A.z = fmaf(x2.z, u2, A.z); A.w = fmaf(x2.w, u2, A.w);
+                    B.x = fmaf(y2.x, v2, B.x); B.y = fmaf(y2.y, v2, B.y); B.z = fmaf(y2.z, v2, B.z); B.w = fmaf(y2.w, v2, B.w);
+                    A.x = fmaf(x3.x, u3, A.x); A.y = fmaf(x3.y, u3, A.y); A.z = fmaf(x3.z, u3, A.z); A.w = fmaf(x3.w, u3, A.w);
+                    B.x = fmaf(y3.x, v3, B.x); B.y = fmaf(y3.y, v3, B.y); B.z = fmaf(y3.z, v3, B.z); B.w = fmaf(y3.w, v3, B.w);
+                }
+                part[qa * 8 + sub] = A; part[qb * 8 + sub] = B;
+            }
+            __syncwarp();
+            tot += cnt; lp = lidx_addr; res = 0;
+        };
 
         while (remaining) {
             // ---- sub-batch: the queries of the leader's cell row within CG_XSPAN coarse cells of it (normally all 32)
@@ -218,80 +298,30 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 phase ^= 1u;
                 if (lane < CG_U) spos[n + lane] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // the unrolled scan may read past n
                 __syncwarp();
-                // ---- scan (lane == query); a sum phase whenever a list could fill up, and at the end of the round.  A round of
-                // CG_U candidates adds at most CG_U entries to a list, so (CG_CAP - longest list) / CG_U rounds need no check.
-                uint32_t *lp = lidx + lane;                                        // next free slot of this lane's list
-                uint32_t c0 = 0;
-                for (;;) {
-                    const uint32_t longest = __reduce_max_sync(PV_FULL, (uint32_t)(lp - (lidx + lane)) >> 5);
+                // ---- scan (lane == query).  A round of CG_U candidates adds at most CG_U entries to a list, so
+                // (CG_CAP - longest list) / CG_U rounds need no check; when a list could overflow, the pending entries are
+                // resolved and all lists summed.
+                for (uint32_t c0 = 0; c0 < n;) {
+                    const uint32_t longest = __reduce_max_sync(PV_FULL, (lp - lidx_addr) >> 7);
                     const uint32_t room = (CG_CAP - longest) / CG_U;               // rounds that cannot overflow any list
-                    if (c0 < n && room != 0) {
-                        const uint32_t stop = min(n, c0 + room * CG_U);
-                        for (; c0 < stop; c0 += CG_U) {
-                            float4 p[CG_U];
+                    if (room == 0) { resolve(); sum(); continue; }
+                    const uint32_t stop = min(n, c0 + room * CG_U);
+                    for (; c0 < stop; c0 += CG_U) {
+                        float4 p[CG_U];
 #pragma unroll
-                            for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];   // broadcast loads first: their latencies overlap
+                        for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];       // broadcast loads first: their latencies overlap
 #pragma unroll
-                            for (int u = 0; u < CG_U; ++u) {
-                                const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
-                                const float d2 = dx * dx + dy * dy + dz * dz;      // (p1 - p2).LengthSquared(), geometry.h:116,526
-                                if (d2 < r2) { *lp = c0 + u; lp += 32; mx = fmaxf(mx, d2); }
+                        for (int u = 0; u < CG_U; ++u) {
+                            const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
+                            const float d2 = dx * dx + dy * dy + dz * dz;          // (p1 - p2).LengthSquared(), geometry.h:116,526
+                            if (d2 < r2) {
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(lp), "r"(c0 + u) : "memory");
+                                lp += 128u; mx = fmaxf(mx, d2);
                             }
                         }
-                        continue;
                     }
-                    if (longest == 0) break;                                       // round finished, nothing pending
-                    const uint32_t cnt = (uint32_t)(lp - (lidx + lane)) >> 5;
-                    // ---- weigh (lane == query): phase function of each accepted photon, photon index resolved.  Every list is
-                    // padded to the same multiple of four with zero-weight entries (an exact no-op in the sums below).
-                    const uint32_t m4 = (longest + 3u) & ~3u;
-                    for (uint32_t e = 0; e < m4; ++e) {
-                        float ph = 0.f;
-                        if (e < cnt) {
-                            const uint32_t c = lidx[e * 32 + lane];
-                            ph = pc;
-                            if (!iso) {
-                                const float4 wv = swi[c];
-                                const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
-                                const float rsq = rsqrtf(gg1 - g2 * costheta);
-                                ph = pc * rsq * rsq * rsq;
-                            }
-                            pad_idx = __float_as_uint(spos[c].w);
-                        }
-                        lidx[e * 32 + lane] = pad_idx;                             // padding: this query's own last photon, weight 0
-                        lw[e * 32 + lane] = ph;
-                    }
-                    fcnt[lane] = cnt;
-                    __syncwarp();
-                    // ---- sum: 8 lanes x float4 per alpha line; each 8-lane group runs TWO queries' fma chains side by side
-#pragma unroll 1
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t qa = grp + 4u * (uint32_t)i, qb = qa + 16u;
-                        const uint32_t nq = (max(fcnt[qa], fcnt[qb]) + 3u) & ~3u;
-                        if (nq == 0) continue;
-                        float4 A = part[qa * 8 + sub], B = part[qb * 8 + sub];
-                        const uint32_t *ia = lidx + qa; const float *wa = lw + qa;
-#pragma unroll 1
-                        for (uint32_t e = 0; e < nq; e += 4, ia += 128, wa += 128) {
-                            const uint32_t a0 = ia[0], a1 = ia[32], a2 = ia[64], a3 = ia[96], b0 = ia[16], b1 = ia[48], b2 = ia[80], b3 = ia[112];
-                            const float4 x0 = __ldg(a4 + (size_t)a0 * 8), y0 = __ldg(a4 + (size_t)b0 * 8), x1 = __ldg(a4 + (size_t)a1 * 8),
-                                         y1 = __ldg(a4 + (size_t)b1 * 8), x2 = __ldg(a4 + (size_t)a2 * 8), y2 = __ldg(a4 + (size_t)b2 * 8),
-                                         x3 = __ldg(a4 + (size_t)a3 * 8), y3 = __ldg(a4 + (size_t)b3 * 8);
-                            const float u0 = wa[0], u1 = wa[32], u2 = wa[64], u3 = wa[96], v0 = wa[16], v1 = wa[48], v2 = wa[80], v3 = wa[112];
-                            A.x = fmaf(x0.x, u0, A.x); A.y = fmaf(x0.y, u0, A.y); A.z = fmaf(x0.z, u0, A.z); A.w = fmaf(x0.w, u0, A.w);
-                            B.x = fmaf(y0.x, v0, B.x); B.y = fmaf(y0.y, v0, B.y); B.z = fmaf(y0.z, v0, B.z); B.w = fmaf(y0.w, v0, B.w);
-                            A.x = fmaf(x1.x, u1, A.x); A.y = fmaf(x1.y, u1, A.y); A.z = fmaf(x1.z, u1, A.z); A.w = fmaf(x1.w, u1, A.w);
-                            B.x = fmaf(y1.x, v1, B.x); B.y = fmaf(y1.y, v1, B.y); B.z = fmaf(y1.z, v1, B.z); B.w = fmaf(y1.w, v1, B.w);
-                            A.x = fmaf(x2.x, u2, A.x); A.y = fmaf(x2.y, u2, A.y); A.z = fmaf(x2.z, u2, A.z); A.w = fmaf(x2.w, u2, A.w);
-                            B.x = fmaf(y2.x, v2, B.x); B.y = fmaf(y2.y, v2, B.y); B.z = fmaf(y2.z, v2, B.z); B.w = fmaf(y2.w, v2, B.w);
-                            A.x = fmaf(x3.x, u3, A.x); A.y = fmaf(x3.y, u3, A.y); A.z = fmaf(x3.z, u3, A.z); A.w = fmaf(x3.w, u3, A.w);
-                            B.x = fmaf(y3.x, v3, B.x); B.y = fmaf(y3.y, v3, B.y); B.z = fmaf(y3.z, v3, B.z); B.w = fmaf(y3.w, v3, B.w);
-                        }
-                        part[qa * 8 + sub] = A; part[qb * 8 + sub] = B;
-                    }
-                    __syncwarp();
-                    tot += cnt; lp = lidx + lane;
                 }
+                resolve(); sum();                                                  // the stage is about to be overwritten
             }
         }
 

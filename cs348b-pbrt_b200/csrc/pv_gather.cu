@@ -1128,6 +1128,84 @@ __global__ void __launch_bounds__(RC_THREADS) recurrence_kernel(GatherArgs a) {
     if (lane == 0 && a.stats && nrays) atomicAdd((unsigned long long *)&a.stats->rays, (unsigned long long)nrays);
 }
 
+// The same recurrence with ONE THREAD PER RAY (frames of camera rays): the 30-bin Lv lives in registers, the medium and light
+// spectra in shared memory, a step's StepRec and L_ii row are requested one step ahead.  No shuffles, no idle padding lanes,
+// the per-step scalars are plain registers: a quarter of the warp form's instructions.  Same expressions per (step, bin):
+// bit-identical results.  Not for rainbow media (they take no photon lookups and never get here).
+#define RT_THREADS 128
+__global__ void __launch_bounds__(RT_THREADS, 4) recurrence_thread_kernel(GatherArgs a) {
+    __shared__ float s_sig_a[PV_NSPEC], s_sig_s[PV_NSPEC], s_le[PV_NSPEC], s_I[PV_MAX_LIGHTS][PV_NSPEC];
+    const DevScene &sc = *a.sc;
+    const DevMedium &med = sc.med;
+    for (int i = threadIdx.x; i < PV_NSPEC; i += RT_THREADS) { s_sig_a[i] = med.sigma_a[i]; s_sig_s[i] = med.sigma_s[i]; s_le[i] = med.le[i]; }
+    for (int i = threadIdx.x; i < (int)sc.n_lights * PV_NSPEC; i += RT_THREADS) s_I[i / PV_NSPEC][i % PV_NSPEC] = sc.lights[i / PV_NSPEC].intensity[i % PV_NSPEC];
+    __syncthreads();
+    const uint64_t ri = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    if (ri >= a.n) return;
+    float y_sig_a = 0.f, y_sig_s = 0.f;
+    for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
+    const bool y_any = y_sig_a != 0.f || y_sig_s != 0.f;
+    const float4 h0 = __ldg(reinterpret_cast<const float4 *>(a.hdr + ri));
+    const int nSamples = __float_as_int(h0.z);
+    const float step = h0.w;
+    const unsigned long long first = ((unsigned long long)__float_as_uint(h0.y) << 32) | __float_as_uint(h0.x);
+    float Lv[PV_NSPEC];
+#pragma unroll
+    for (int b = 0; b < PV_NSPEC; ++b) Lv[b] = 0.f;
+    float last_tau = 0.f, last_rr = -1.f;
+    bool stopped = false;
+    if (nSamples > 0) {
+        const float4 *rp = reinterpret_cast<const float4 *>(a.steps + first);
+        const float4 *lp = reinterpret_cast<const float4 *>(a.lii + first * 32);
+        float4 na = __ldg(rp), nb = __ldg(rp + 1), nl[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nl[k] = __ldg(lp + k);
+        for (int i = 0; i < nSamples; ++i, rp += 2, lp += 8) {
+            const float4 ra = na, rb = nb;
+            float l[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { l[4 * k] = nl[k].x; l[4 * k + 1] = nl[k].y; l[4 * k + 2] = nl[k].z; l[4 * k + 3] = nl[k].w; }
+            const float s_rr = ra.z;
+            if (s_rr > .5f) { stopped = true; break; }                     // the roulette ends the march (records behind it are dead)
+            if (i + 1 < nSamples) {                                          // the next step's records are in flight during this step's bins
+                na = __ldg(rp + 2); nb = __ldg(rp + 3);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nl[k] = __ldg(lp + 8 + k);
+            }
+            const float s_tau = ra.y, s_dens = ra.w, s_sh = rb.x, s_dfac = rb.y;
+            const bool rr = s_rr >= 0.f, lit = s_dfac != 0.f, mix = s_dens != 0.f && y_any;
+            const float *I = s_I[lit ? __float_as_int(rb.z) : 0];
+#pragma unroll
+            for (int b = 0; b < PV_NSPEC; ++b) {
+                const float sig_a = s_sig_a[b], sig_s = s_sig_s[b];
+                const float sig_t = sig_a + sig_s;
+                float Tr = expf(-(sig_t * s_tau));                           // Exp(-stepTau): per-step, not cumulative (:155)
+                if (rr) Tr = Tr * 2.f;                                       // Tr /= continueProb (0.5): exact
+                const float ss = sig_s * s_dens, sa = sig_a * s_dens;
+                float L_d = 0.f;
+                if (lit) L_d = (I[b] * expf(-(sig_t * s_sh))) * s_dfac;
+                // L_i = L_d + (ss/(sa+ss)) * L_ii unless sa.y() == 0 && ss.y() == 0 (photonvolume.cpp:210-213)
+                const float L_i = mix ? L_d + __fdiv_rn(ss, sa + ss) * l[b] : L_d;
+                Lv[b] = ((sa * (s_le[b] * s_dens)) * step) + ((ss * L_i) * step) + (Tr * Lv[b]);
+            }
+            last_tau = s_tau; last_rr = s_rr;
+        }
+    }
+    float *Lo = a.L + ri * PV_NSPEC, *To = a.T + ri * PV_NSPEC;
+#pragma unroll
+    for (int b = 0; b < PV_NSPEC; ++b) {
+        float Tr = 1.f;
+        if (nSamples > 0) {
+            Tr = expf(-((s_sig_a[b] + s_sig_s[b]) * last_tau));
+            if (last_rr >= 0.f) Tr = Tr * 2.f;
+            if (stopped) Tr = 0.f;
+        }
+        Lo[b] = Lv[b]; To[b] = Tr;
+    }
+    const uint32_t nr = __popc(__activemask());
+    if ((threadIdx.x & 31) == (uint32_t)(__ffs(__activemask()) - 1) && a.stats) atomicAdd((unsigned long long *)&a.stats->rays, (unsigned long long)nr);
+}
+
 // One warp per march STEP of the slice: the photon lookup and the radiance estimate of that step (the part of gather_kernel's
 // loop body that does not depend on the other steps of the ray).
 __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_lii_kernel(GatherArgs a) {
@@ -1306,6 +1384,13 @@ int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t
 static unsigned recurrence_blocks(pv_ctx *ctx, uint64_t n) {
     return (unsigned)std::min<uint64_t>((n + RC_THREADS / 32 - 1) / (RC_THREADS / 32), (uint64_t)ctx->sm_count * 8 * 4);
 }
+// frames: one thread per ray; small batches (fewer rays than resident threads) and rainbow media: one warp per ray
+static void launch_recurrence(pv_ctx *ctx, const GatherArgs &a, uint64_t n) {
+    if (n >= (uint64_t)ctx->sm_count * 256 && ctx->hscene.med.type != PV_MEDIUM_RAINBOW && ctx->hscene.n_lights <= PV_MAX_LIGHTS)
+        recurrence_thread_kernel<<<(unsigned)((n + RT_THREADS - 1) / RT_THREADS), RT_THREADS, 0, ctx->stream>>>(a);
+    else
+        recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
+}
 // Li for rays [0, n): march records first (pv_march.cu), then the gather kernel.  Rays are taken in slices so that the
 // step records of one slice stay within PV_MARCH_MAX_BYTES / the free device memory.
 static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_params *prm, uint32_t flags, float *d_L, float *d_T) {
@@ -1372,12 +1457,12 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(o);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[2], ctx->stream));
-        recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
+        launch_recurrence(ctx, a, n);
     } else if (step_parallel) {
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
-        recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
+        launch_recurrence(ctx, a, n);
     } else {
         rc = launch_cfg(ctx, gather_kernel<false>, a.cap, &blocks, &smem); if (rc) return rc;
         gather_kernel<false><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);

@@ -29,7 +29,8 @@ enum { ST_NEWPATH = 0, ST_TRACE = 1, ST_SURFACE = 2, ST_DONE = 3 };
 struct Frame {
     float o[3], d[3], mint, maxt;
     float ip[3], inn[3], idpdu[3], ieps;      // hit: dg.p, dg.nn, dg.dpdu, rayEpsilon
-    int prim, nI, spec, loop_i;
+    int prim, nI, spec, loop_i;                // spec: bit 0 = specularPath, bit 1 = the photon is a monochromatic child of
+                                               // splitSpectrum (the fork's Spectrum::lambda >= 0, core/spectrum.h:253-265)
     float alpha[PV_NSPEC];
 };
 
@@ -527,7 +528,7 @@ SH_UNROLL_BINS
                     }
                     if (nonspec) {
                         int cls = -1;
-                        if (cur.spec && cur.nI > 1) { if (a.flags & SF_WANT_CAUSTIC) cls = PC_CAUSTIC; }
+                        if ((cur.spec & 1) && cur.nI > 1) { if (a.flags & SF_WANT_CAUSTIC) cls = PC_CAUSTIC; }
                         else if (cur.nI == 1 && (a.flags & SF_WANT_INDIRECT) && (a.flags & SF_FINAL_GATHER)) cls = PC_DIRECT;
                         else if (cur.nI > 1 && (a.flags & SF_WANT_INDIRECT)) cls = PC_INDIRECT;
                         if (cls >= 0) {
@@ -591,7 +592,7 @@ SH_UNROLL_BINS
 SH_UNROLL_BINS
                                         for (int b = 0; b < PV_NSPEC; ++b)
                                             cur.alpha[b] = __fdiv_rn(__fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf), continueProb);
-                                        cur.spec = 0;
+                                        cur.spec &= 2;                       // specularPath = false; lambda travels with alpha
                                         cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
                                         cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
                                         cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
@@ -613,7 +614,10 @@ SH_UNROLL_BINS
                     int nz = 0;
 SH_UNROLL_BINS
                     for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) nz++;
-                    const bool do_split = hasT && nz != 1 && mat.vn > 0.f;       // alpha.lambda < 0 && dispersive()
+                    // hasTransmission && alpha.lambda < 0 && primitive->dispersive() (photonshooter.cpp:140-145).  lambda is path STATE,
+                    // not a property of the bins: a monochromatic child whose one bin underflowed to zero in a dense medium is traced
+                    // on as a black photon, not split again.
+                    const bool do_split = hasT && !(cur.spec & 2) && mat.vn > 0.f;
                     bool spawned = false;
                     for (;;) {
                         // next spectrum of the split (splitSpectrum core/spectrum.h:253-265): bins with c != 0, in order
@@ -674,9 +678,10 @@ SH_UNROLL_BINS
                         ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
                         float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
                         if (rng.next() > continueProb) continue;
-                        if (!cur.spec && !(SURF && (a.flags & SF_WANT_INDIRECT))) continue;   // indirectDone && !specularPath
+                        if (!(cur.spec & 1) && !(SURF && (a.flags & SF_WANT_INDIRECT))) continue;   // indirectDone && !specularPath
                         // spawn the child; this frame resumes at loop_i afterwards
                         if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
+                        if (do_split) cur.spec |= 2;                               // splitSpectrum set the child's lambda
 SH_UNROLL_BINS
                         for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(anew[b], continueProb);
                         cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];

@@ -62,6 +62,9 @@ def test_full_frame_is_deterministic_and_shards_exactly(frame):
     Lb, Tb, sb = gather_dev(frame, lo=h, hi=n, base=h)
     assert torch.equal(torch.cat([La, Lb]), L1) and torch.equal(torch.cat([Ta, Tb]), T1)
     assert sa.lookups + sb.lookups == s1.lookups and sa.photons_found + sb.photons_found == s1.photons_found
+    # a shard small enough for the warp-per-ray recurrence kernel (the frame takes the thread-per-ray one): same bits
+    Lc, Tc, _ = gather_dev(frame, lo=1000, hi=21000, base=1000)
+    assert torch.equal(Lc, L1[1000:21000]) and torch.equal(Tc, T1[1000:21000])
 
 
 @pytest.mark.parametrize("cell_scale", [2.3, 0.45])
