@@ -29,8 +29,10 @@ enum { ST_NEWPATH = 0, ST_TRACE = 1, ST_SURFACE = 2, ST_DONE = 3 };
 struct Frame {
     float o[3], d[3], mint, maxt;
     float ip[3], inn[3], idpdu[3], ieps;      // hit: dg.p, dg.nn, dg.dpdu, rayEpsilon
-    int prim, nI, spec, loop_i;                // spec: bit 0 = specularPath, bit 1 = the photon is a monochromatic child of
-                                               // splitSpectrum (the fork's Spectrum::lambda >= 0, core/spectrum.h:253-265)
+    int prim, nI, spec, loop_i;                // spec: bit 0 = specularPath; bit 1 = the fork's Spectrum::lambda >= 0, i.e. alpha had
+                                               // exactly one positive bin WHEN IT WAS LAST RE-MADE (emission, surface bounce:
+                                               // extractLambda in SampledSpectrum's converting constructor, core/spectrum.h:266-279,
+                                               // :339-343); in-place updates in between (scatter, transmittance) carry it along
     float alpha[PV_NSPEC];
 };
 
@@ -354,15 +356,17 @@ SH_UNROLL_BINS
             float ad = fabsf(vdot(rd, rd));                                // AbsDot(Nl, photonRay.d) with Nl == ray.d
             float den = pdf * lightPdf;
             bool black = true;
+            int npos = 0;
 SH_UNROLL_BINS
             for (int b = 0; b < PV_NSPEC; ++b) {
                 float Le = l.type == PV_LIGHT_SPOT ? l.intensity[b] * scale : l.intensity[b];
                 cur.alpha[b] = __fdiv_rn(Le * ad, den);
                 black = black && (cur.alpha[b] == 0.f);
+                npos += cur.alpha[b] > 0.f ? 1 : 0;
             }
             if (pdf == 0.f || black) continue;                             // stays in ST_NEWPATH
             cur.o[0] = ro.x; cur.o[1] = ro.y; cur.o[2] = ro.z; cur.d[0] = rd.x; cur.d[1] = rd.y; cur.d[2] = rd.z;
-            cur.mint = 0.f; cur.maxt = INFINITY; cur.nI = 0; cur.spec = 1; cur.loop_i = -1; cur.prim = -1;
+            cur.mint = 0.f; cur.maxt = INFINITY; cur.nI = 0; cur.spec = 1 | (npos == 1 ? 2 : 0); cur.loop_i = -1; cur.prim = -1;
             state = ST_TRACE;
             continue;
         }
@@ -589,10 +593,13 @@ SH_UNROLL_BINS
                                     const float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
                                     // specularPath &= false, then `indirectDone && !specularPath` ends the path (:216-219)
                                     if (!(rng.next() > continueProb) && (a.flags & SF_WANT_INDIRECT)) {
+                                        int npos = 0;
 SH_UNROLL_BINS
-                                        for (int b = 0; b < PV_NSPEC; ++b)
+                                        for (int b = 0; b < PV_NSPEC; ++b) {
                                             cur.alpha[b] = __fdiv_rn(__fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf), continueProb);
-                                        cur.spec &= 2;                       // specularPath = false; lambda travels with alpha
+                                            npos += cur.alpha[b] > 0.f ? 1 : 0;
+                                        }
+                                        cur.spec = npos == 1 ? 2 : 0;        // specularPath = false; alpha re-made: lambda = extractLambda()
                                         cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
                                         cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
                                         cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
@@ -614,9 +621,9 @@ SH_UNROLL_BINS
                     int nz = 0;
 SH_UNROLL_BINS
                     for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) nz++;
-                    // hasTransmission && alpha.lambda < 0 && primitive->dispersive() (photonshooter.cpp:140-145).  lambda is path STATE,
-                    // not a property of the bins: a monochromatic child whose one bin underflowed to zero in a dense medium is traced
-                    // on as a black photon, not split again.
+                    // hasTransmission && alpha.lambda < 0 && primitive->dispersive() (photonshooter.cpp:140-145).  lambda is path STATE
+                    // (see Frame::spec): a monochromatic child whose one bin underflowed to zero in a dense medium is not split again
+                    // here, it goes on as a black photon with lambda = -1 and ends at the next dispersive face.
                     const bool do_split = hasT && !(cur.spec & 2) && mat.vn > 0.f;
                     bool spawned = false;
                     for (;;) {
@@ -681,9 +688,10 @@ SH_UNROLL_BINS
                         if (!(cur.spec & 1) && !(SURF && (a.flags & SF_WANT_INDIRECT))) continue;   // indirectDone && !specularPath
                         // spawn the child; this frame resumes at loop_i afterwards
                         if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
-                        if (do_split) cur.spec |= 2;                               // splitSpectrum set the child's lambda
+                        int npos = 0;
 SH_UNROLL_BINS
-                        for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(anew[b], continueProb);
+                        for (int b = 0; b < PV_NSPEC; ++b) { cur.alpha[b] = __fdiv_rn(anew[b], continueProb); npos += cur.alpha[b] > 0.f ? 1 : 0; }
+                        cur.spec = (cur.spec & 1) | (npos == 1 ? 2 : 0);           // alpha re-made: lambda = extractLambda()
                         cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
                         cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
                         cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;

@@ -1319,9 +1319,23 @@ static void make_isect(const pv_scene_desc *sc, int prim, v3 o, v3 d, float t, i
     is->rayEpsilon = 1e-3f * t;
 }
 
-/* split_lambda: the fork's Spectrum::lambda member as followPhoton sees it (photonshooter.cpp:141): -1 until splitSpectrum has made
- * the photon one of its monochromatic children, >= 0 from then on -- whatever happens to the child's one bin afterwards (it can
- * underflow to zero in a dense medium; the reference then keeps tracing, and depositing, a black photon). */
+/* split_lambda: the fork's Spectrum::lambda member as followPhoton sees it (photonshooter.cpp:141).  It is STATE, not a function of
+ * the bins at the time of the test: every Spectrum produced by a binary operator is a CoefficientSpectrum converted back through
+ * SampledSpectrum(const CoefficientSpectrum&), which sets lambda = extractLambda() (core/spectrum.h:339-343: 400 + 10 i when exactly
+ * one bin is positive, else -1); compound assignments keep it.  So lambda is recomputed where alpha is re-made -- at emission
+ * (`alpha = AbsDot * Le / pdf`, :263) and after every surface bounce (`alpha = anew / continueProb`, :217) -- and merely carried
+ * through the in-place updates in between (`alpha *= ref; alpha /= pdf` at a scatter event :119-120, `alpha *= Transmittance` :133).
+ * A monochromatic child whose one bin underflows to zero in a dense medium therefore reaches the next glass face with lambda >= 0:
+ * no split, one BSDF sample, and (0/0 -> continueProb 1) the black photon is traced on -- now with lambda = -1, so that the NEXT
+ * dispersive face splits it into nothing and ends the path. */
+static int s_extract_lambda(const spec *a) {             /* CoefficientSpectrum::extractLambda, core/spectrum.h:266-279 */
+    int l = -1, first = 1;
+    for (int b = 0; b < NS; ++b) {
+        if (a->c[b] > 0.f && !first) return -1;
+        if (a->c[b] > 0.f && first) { l = 400 + b * 10; first = 0; }
+    }
+    return l;
+}
 static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, spec alpha, int nIntersections, int specularPath, int split_lambda) {
     const pv_scene_desc *sc = c->sc;
     float thit = photonRay.maxt;
@@ -1433,7 +1447,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
         if (!c->want_indirect) return;
         spec an2; for (int b = 0; b < NS; ++b) an2.c[b] = anew.c[b] / continueProb;
         ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
-        follow_photon(c, nr, photonIsect, an2, nIntersections, 0, split_lambda);
+        follow_photon(c, nr, photonIsect, an2, nIntersections, 0, s_extract_lambda(&an2));
         return;
     }
     /* glass: specular reflection + dispersive transmission (materials/glass.cpp:42-59,
@@ -1526,7 +1540,7 @@ static void follow_photon(shoot_ctx *c, ray_t photonRay, isect_t photonIsect, sp
             /* specular: specularPath stays as it was; `indirectDone && !specularPath` -> continue */
             if (!c->want_indirect && !specularPath) continue;
             ray_t nr = {photonIsect.p, wiW, photonIsect.rayEpsilon, INFINITY};
-            follow_photon(c, nr, photonIsect, an2, nIntersections, specularPath, do_split ? 400 + 10 * binlist[si] : split_lambda);
+            follow_photon(c, nr, photonIsect, an2, nIntersections, specularPath, s_extract_lambda(&an2));
         }
     }
 }
@@ -1635,7 +1649,7 @@ static void shoot_path(shoot_ctx *c, const halton6 *h, const distrib1d *ld, uint
     if (s_black(&alpha)) return;
     isect_t is; memset(&is, 0, sizeof(is));
     c->path_index = path_index; c->deposit_seq = 0;
-    follow_photon(c, photonRay, is, alpha, 0, 1, -1);
+    follow_photon(c, photonRay, is, alpha, 0, 1, s_extract_lambda(&alpha));
 }
 
 typedef struct {

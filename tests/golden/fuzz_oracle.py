@@ -95,6 +95,36 @@ def relerr(a, b):
     return np.abs(np.asarray(a, np.float64) - b) / np.maximum(np.abs(np.asarray(b, np.float64)), 1e-30)
 
 
+def scene_for_seed(seed, base=None):
+    """The random scene of `seed`: .pbrt text, camera rays and parameters (everything main() and make_golden.py need)."""
+    base = scenes.camera_rays(48, 48) if base is None else base
+    rng = np.random.default_rng(1000 + seed)
+    vol, lights = random_scene(rng)
+    integ = ["single", "emission", "photonvolume"][seed % 3]
+    variant = ["plain", "glass", "area", "aggregate"][(seed // 3) % 4]
+    tail = ""
+    if variant == "area":
+        tail = random_area_quad(rng)
+    elif variant == "aggregate":
+        vol = vol + "\n" + second_volume(rng)
+    elif variant == "glass":
+        tail = random_glass(rng)
+    stepsize = round(float(rng.uniform(0.03, 0.2)), 4)          # 4 decimals: the scene text (%g) and the oracle see the same number
+    rays = base[np.sort(rng.choice(len(base), size=48, replace=False))].copy()
+    rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
+    rays["maxt"][:8] = rng.uniform(2.5, 4.5, 8).astype(np.float32)
+    point = 'LightSource "point" "point from" [0 0.8 0] "color I" [20 20 20]'
+    d = dict(vol=vol, lights=lights, integ=integ, variant=variant, stepsize=stepsize, rays=rays)
+    if integ == "photonvolume":
+        nused, maxdist, wanted, shoot_step = int(rng.integers(10, 60)), round(float(rng.uniform(0.15, 0.4)), 4), int(rng.integers(500, 1500)), round(float(rng.uniform(0.04, 0.12)), 4)
+        text = scenes.cornell_pbrt(vol, wanted, stepsize=stepsize, nused=nused, maxdist=maxdist, shoot_step=shoot_step).replace(point, lights)
+        d.update(nused=nused, maxdist=maxdist, wanted=wanted, shoot_step=shoot_step)
+    else:
+        text = scenes.volint_pbrt(integ, vol, stepsize=stepsize).replace(point, lights)
+    d["text"] = text.replace("WorldEnd", tail + "\nWorldEnd")
+    return d
+
+
 def main():
     n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 24
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -103,32 +133,15 @@ def main():
     bad = 0
     with tempfile.TemporaryDirectory() as tmp:
         for seed in range(first, first + n_scenes):
-            rng = np.random.default_rng(1000 + seed)
-            vol, lights = random_scene(rng)
-            integ = ["single", "emission", "photonvolume"][seed % 3]
-            variant = ["plain", "glass", "area", "aggregate"][(seed // 3) % 4]
-            tail = ""
-            if variant == "area":
-                tail = random_area_quad(rng)
-            elif variant == "aggregate":
-                vol = vol + "\n" + second_volume(rng)
-            elif variant == "glass":
-                tail = random_glass(rng)
-            stepsize = round(float(rng.uniform(0.03, 0.2)), 4)          # 4 decimals: the scene text (%g) and the oracle see the same number
-            rays = base[np.sort(rng.choice(len(base), size=48, replace=False))].copy()
-            rays["u_scatter"] = rng.random(len(rays)).astype(np.float32)
-            rays["maxt"][:8] = rng.uniform(2.5, 4.5, 8).astype(np.float32)
+            d = scene_for_seed(seed, base)
+            vol, lights, integ, variant, stepsize, rays, text = d["vol"], d["lights"], d["integ"], d["variant"], d["stepsize"], d["rays"], d["text"]
             rf = os.path.join(tmp, "rays.bin"); sceneio.write_rays(rf, rays)
             scn = os.path.join(tmp, "s.scn"); out = os.path.join(tmp, "li.bin"); pho = os.path.join(tmp, "p.pho"); stats = os.path.join(tmp, "st.json")
-            point = 'LightSource "point" "point from" [0 0.8 0] "color I" [20 20 20]'
             if integ == "photonvolume":
-                nused, maxdist, wanted, shoot_step = int(rng.integers(10, 60)), round(float(rng.uniform(0.15, 0.4)), 4), int(rng.integers(500, 1500)), round(float(rng.uniform(0.04, 0.12)), 4)
-                text = scenes.cornell_pbrt(vol, wanted, stepsize=stepsize, nused=nused, maxdist=maxdist, shoot_step=shoot_step).replace(point, lights)
+                nused, maxdist, wanted, shoot_step = d["nused"], d["maxdist"], d["wanted"], d["shoot_step"]
                 ops = ["--shoot", "--dump-photons", pho, "--stats", stats, "--li", rf, "1000", out]
             else:
-                text = scenes.volint_pbrt(integ, vol, stepsize=stepsize).replace(point, lights)
                 ops = ["--vli", rf, "1000", out]
-            text = text.replace("WorldEnd", tail + "\nWorldEnd")
             side = os.path.join(tmp, "s.lights"); reg = os.path.join(tmp, "reg")
             export = {"plain": ["--export-scene", scn], "glass": ["--export-scene", scn], "area": ["--export-area-lights", scn, side], "aggregate": ["--export-regions", reg]}[variant]
             ops = export + ops

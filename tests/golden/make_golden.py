@@ -183,6 +183,7 @@ def main():
         volint_goldens(tmp)
         aggregate_goldens(tmp)
         area_light_goldens(tmp)
+        underflow_goldens(tmp)
 
 
 def project_goldens(tmp):
@@ -363,6 +364,24 @@ def area_light_goldens(tmp):
     li = sceneio.read_spectra(os.path.join(tmp, "area_li.bin"), b"PVLI0001", per=2)
     np.savez_compressed(os.path.join(HERE, "cornell_area.npz"), shot_pos=pos, shot_wi=wi, shot_alpha=alpha, nshot=np.array([st["nshot"]], np.uint64),
                         params=np.array([50, 0.25, 0.05, 3000, 0.05], np.float64), li_rays=rays, li_L=li[:, 0], li_T=li[:, 1])
+
+
+def underflow_goldens(tmp, seed=113):
+    """The scene on which the randomised cross-check (fuzz_oracle.py, seed 113) separated `Spectrum::lambda as path state` from
+    `lambda inferred from the bins`: a dispersive glass wedge in an exponential medium dense enough for photon weights of 1e-36 to
+    underflow to zero between two glass faces.  Stored: the flattened scene and the photon list of one reference task."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_oracle", os.path.join(HERE, "fuzz_oracle.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    d = fz.scene_for_seed(seed)
+    assert d["integ"] == "photonvolume" and d["variant"] == "glass"
+    f = os.path.join(tmp, "underflow_glass.pbrt"); open(f, "w").write(d["text"])
+    pho = os.path.join(tmp, "u.pho"); stats = os.path.join(tmp, "u.json")
+    run(f, "--ncores", 1, "--export-scene", os.path.join(HERE, "underflow_glass.scn"), "--shoot", "--dump-photons", pho, "--stats", stats)
+    pos, wi, alpha = sceneio.read_photons(pho); st = json.load(open(stats))
+    np.savez_compressed(os.path.join(HERE, "underflow_glass.npz"), shot_pos=pos, shot_wi=wi, shot_alpha=alpha, nshot=np.array([st["nshot"]], np.uint64),
+                        params=np.array([d["wanted"], d["shoot_step"], d["stepsize"]], np.float64))
+    print("underflow_glass: %d photons, %d black, nshot %d" % (len(pos), int((alpha.max(axis=1) == 0).sum()), st["nshot"]))
 
 
 def read_radiance(fn):

@@ -245,6 +245,30 @@ def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, 
     assert np.all(np.diff(ids.astype(np.int64)) > 0)        # deterministic order: sorted by (path, ordinal)
 
 
+def test_shooter_lambda_is_path_state_in_the_underflow_regime(golden, pv_factory):
+    """The regime that separates `Spectrum::lambda as path state` from `lambda inferred from the bins` (tests/golden/underflow_glass.*,
+    see test_oracle_golden.py): dispersive wedge in a dense exponential medium, photon weights underflow to zero between glass
+    faces.  GPU vs the pinned oracle on the same per-path Philox streams: identical id lists -- black photons included."""
+    g, scene = golden("underflow_glass")
+    wanted, sstep, istep = 3000, float(g["params"][1]), float(g["params"][2])
+    pv = pv_factory(stepsize=istep, seed=113)
+    pv.set_scene(scene)
+    st = pv.Preprocess(wanted, stepsize=sstep, max_photon_depth=5, build=False)
+    pos, wi, alpha, ids = pv.get_photons()
+    ref = O.shoot(scene, wanted, sstep, istep, seed=113, rng_mode=O.PHILOX, nthreads=8)
+    assert ref["rc"] == 0 and st.paths == ref["nshot"] and st.stack_overflows == 0
+    black_ref = ref["alpha"].max(axis=1) == 0
+    assert black_ref.sum() >= 5                                  # the regime is reached
+    common, ia, ib = np.intersect1d(ids, ref["ids"], return_indices=True)
+    assert len(common) >= 0.995 * max(len(ids), len(ref["ids"]))
+    assert abs(len(ids) - len(ref["ids"])) <= 0.005 * len(ref["ids"]) + 2
+    assert np.quantile(np.abs(pos[ia] - ref["pos"][ib]).max(axis=1), 0.99) < 1e-4
+    # the same photons are black on both sides (a path that was re-split or cut short would change the id list long before)
+    bg = alpha[ia].max(axis=1) == 0
+    assert (bg != black_ref[ib]).sum() <= 2
+    assert bg.sum() >= 5
+
+
 def test_shooter_sharded_blocks_reproduce_single_rank(golden, pv_factory, pkg):
     """Emission sharded by block over 2 'ranks' (run back to back on one GPU) gives the same photon set."""
     import ctypes as C

@@ -362,3 +362,21 @@ def test_shooter_with_an_area_light_reproduces_reference_photons(golden, pkg):
         L, T, _ = O.gather(scene, tree, g["shot_wi"], g["shot_alpha"], g["li_rays"], float(g["params"][2]), int(g["params"][0]), float(g["params"][1]),
                            rng_mode=O.MT, mt_seed=1000)
     assert (g["li_L"] > 0).any() and relerr(T, g["li_T"]).max() < 1e-6 and relerr(L, g["li_L"])[g["li_L"] > 0].max() < 1e-5
+
+
+def test_lambda_is_path_state_in_the_underflow_regime(golden):
+    """fuzz_oracle.py seed 113, committed as a fixture: a dispersive glass wedge in an exponential medium dense enough for the
+    weight of a monochromatic child of splitSpectrum to underflow to zero between two glass faces.  The reference re-makes
+    Spectrum::lambda only where alpha is re-made (emission, surface bounce: extractLambda in SampledSpectrum's converting
+    constructor, core/spectrum.h:266-279,:339-343), so the black child is NOT split at the next face, is traced on (15 black
+    photons are deposited) and ends one dispersive face later.  Inferring lambda from the bins at the face, or carrying it
+    unchanged down the path, both give other photon lists (2462 instead of 2250 photons)."""
+    g, scene = golden("underflow_glass")
+    wanted, sstep, istep = int(g["params"][0]), float(g["params"][1]), float(g["params"][2])
+    res = O.shoot(scene, wanted, sstep, istep, rng_mode=O.MT)
+    assert res["rc"] == 0 and res["nshot"] == int(g["nshot"][0])
+    assert res["n"] == len(g["shot_pos"]) == 2250
+    assert np.abs(res["pos"] - g["shot_pos"]).max() < 1e-5
+    assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-5
+    black = g["shot_alpha"].max(axis=1) == 0
+    assert black.sum() == 15 and np.array_equal(res["alpha"].max(axis=1) == 0, black)
