@@ -191,6 +191,48 @@ def run_reference(args, cfg, W, scene):
     print(json.dumps(out), flush=True)
 
 
+def extra_line(pkg, W, name, local, args, peak):
+    """A secondary workload through the same path, device-resident, one GPU: BASELINE config 2 (Cornell box + homogeneous medium,
+    1 M photons, 512x512, k = 50 nearest within 0.25 -- the k-nearest regime the reference's shipped scenes use)."""
+    import torch
+    cfg = W.CONFIGS[name]
+    scene = W.load_scene(cfg)
+    pv = pkg.PhotonVolume(device=local, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=args.seed)
+    try:
+        pv.set_scene(scene)
+        pos, wi, alpha = W.photons_from_density(scene, cfg["photons"])
+        pv.set_photons(pos, wi, alpha); pv.build()
+        rays, _ = W.frame_rays(cfg)
+        n = len(rays)
+        dev = torch.device("cuda", local)
+        d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)
+        d_L = torch.empty((n, 30), device=dev); d_T = torch.empty((n, 30), device=dev)
+        for _ in range(3):
+            pv.Li_dev(d_rays, n, d_L, d_T)
+        pv.gather_stats(reset=True)
+        ext = torch.cuda.ExternalStream(pv.stream(), device=dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        steps = 5; kms = []
+        torch.cuda.synchronize()
+        e0.record(ext)
+        for _ in range(steps):
+            pv.Li_dev(d_rays, n, d_L, d_T); kms.append(pv.last_kernel_ms())
+        e1.record(ext)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        st = pv.gather_stats(reset=True)
+        byts = W.gather_bytes(st, n * steps) / steps
+        ach = byts / (float(np.mean(kms)) * 1e-3) / 1e9
+        return {"workload": cfg["label"], "value": n / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps,
+                "lookups_per_step": st.lookups / steps, "photons_found_per_lookup": st.photons_found / max(st.lookups, 1),
+                "candidates_per_lookup": st.candidates_tested / max(st.lookups, 1),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "avg_launch_ms": float(np.mean(kms)), "algorithmic_bytes_per_launch": byts},
+                "L_sum": float(d_L.sum().item())}
+    finally:
+        pv.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,12 +241,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3")
     ap.add_argument("--photons", type=int, default=0, help="override the photon count (debug only; invalidates the number)")
-    ap.add_argument("--shoot-photons", type=int, default=400_000, help="bounded photon-shooting sample for the shoot rates")
+    ap.add_argument("--shoot-photons", type=int, default=-1, help="photons of the full-frame pass (shoot -> all-gather -> build -> gather); -1 = the workload's photon count, 0 = skip")
     ap.add_argument("--maps-photons", type=int, default=200_000, help="volume-photon target of the all-maps shooting sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=600_000, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-shoot-photons", type=int, default=150_000, help="photons of the bounded CPU-baseline shooting sample (0 = skip)")
     ap.add_argument("--ref-rays", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload lines (config 2: k-nearest gather)")
     ap.add_argument("--seed", type=int, default=348)
     args = ap.parse_args()
 
@@ -238,41 +281,101 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ------------------------------------------------------------------ photon shooting (bounded sample, sharded by block)
     import ctypes as C
-    shoot = {}
-    if args.shoot_photons > 0:
+
+    def shoot_pass(target, wave0):
+        """PhotonShooter::Preprocess, volume branch, sharded by 4096-path block over the ranks (pv_shoot_blocks / pv_shoot_finish):
+        returns (stats, wall seconds).  Per-wave deposit counts are summed over ranks so every rank stops at the same block."""
         prm = A.ShootParams(0.05, cfg["stepsize"], 5, args.seed, rank, world, 0, 0.0)
-        # untimed warm-up wave (first launch of the kernel: module load, local-memory reservation)
-        pv._chk(pv.lib.pv_shoot_blocks(pv.ctx, C.c_uint64(1), C.c_uint32(8 * world), C.byref(prm), (C.c_uint32 * (8 * world))(), C.byref(A.ShootStats())))
         st = A.ShootStats()
-        block, total, wave, last = 0, 0, 64 * world, 0
+        block, total, wave, last = 0, 0, wave0, 0
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         while not last:
             counts = (C.c_uint32 * wave)()
             pv._chk(pv.lib.pv_shoot_blocks(pv.ctx, C.c_uint64(block + 1), C.c_uint32(wave), C.byref(prm), counts, C.byref(st)))
-            cnt = torch.tensor(np.ctypeslib.as_array(counts).astype(np.int64), device=dev)
+            cnt = np.ctypeslib.as_array(counts).astype(np.int64)
             if dist is not None:
-                dist.all_reduce(cnt)                                   # deposits per block, summed over ranks
-            last, total, used = MG.last_block(cnt.cpu().numpy(), block + 1, total, args.shoot_photons)
+                t = torch.from_numpy(cnt).to(dev); dist.all_reduce(t); cnt = t.cpu().numpy()
+            last, total, used = MG.last_block(cnt, block + 1, total, target)
             block += used
             if not last:
-                wave = MG.next_wave(total, block, args.shoot_photons, world)
+                wave = MG.next_wave(total, block, target, world)
         pv._chk(pv.lib.pv_shoot_finish(pv.ctx, C.c_uint64(last)))
         torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        return st, last, time.perf_counter() - t0
+
+    def shoot_report(st, last, wall, target):
         sec = torch.tensor([st.seconds, float(st.paths_local), float(pv.photon_count()), float(st.nodes_visited), float(st.tri_tests),
                             float(st.density_samples), float(st.stack_overflows)], dtype=torch.float64, device=dev)
         mx = sec.clone()
         if dist is not None:
             dist.all_reduce(sec); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sec = sec.cpu().numpy(); dsec = float(mx.cpu().numpy()[0])
-        paths = last * 4096
         shoot_bytes = sec[3] * 32 + sec[4] * 36 + sec[5] * 32 + sec[2] * 144       # SURVEY 8d shoot formula
-        shoot = {"photons": int(sec[2]), "paths": int(paths), "paths_traced_incl_discarded": int(sec[1]), "device_s": dsec, "wall_s": wall,
-                 "paths_per_s": sec[1] / dsec, "photons_per_s": sec[2] / dsec,
-                 "stack_overflows": int(sec[6]), "hbm_frac_algorithmic": shoot_bytes / dsec / 1e9 / (peak * world),
-                 "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": args.shoot_photons}}
+        ach = shoot_bytes / dsec / 1e9
+        return {"photons": int(sec[2]), "paths": int(last * 4096), "paths_traced_incl_discarded": int(sec[1]), "device_s": dsec, "wall_s": wall,
+                "paths_per_s": sec[1] / dsec, "photons_per_s": sec[2] / dsec, "stack_overflows": int(sec[6]),
+                "roofline": {"bound": "hbm", "kernel": "shoot_kernel", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / (peak * world),
+                             "peak_kind": peak_kind, "algorithmic_bytes": shoot_bytes, "traffic": None,
+                             "note": "per GPU; bytes = nodes*32 + triangle tests*36 + density samples*32 + deposits*144 (SURVEY 8d); the kernel is "
+                                     "latency/issue-bound, not HBM-bound (profiles/)"},
+                "hbm_frac_algorithmic": ach / (peak * world),
+                "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": target}}
+
+    # ------------------------------------------------------------------ rays of this rank (image tiles dealt round-robin)
+    rays, order = W.frame_rays(cfg, rank, world)
+    n_local = len(rays)
+    n_total = cfg["xres"] * cfg["yres"]
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)
+    d_L = torch.empty((n_local, 30), device=dev); d_T = torch.empty((n_local, 30), device=dev)
+
+    # ------------------------------------------------------------------ the whole frame once, at FULL size: shoot -> all-gather -> build -> gather
+    # (the photon map the gather reads here is the one the shooter just made; NCCL and every kernel are warm before the timers start)
+    shoot, frame = {}, None
+    if dist is not None:
+        warm = torch.zeros(1, device=dev); dist.all_reduce(warm); torch.cuda.synchronize()     # lazy NCCL initialisation happens here
+    if args.shoot_photons != 0:
+        target = n_ph if args.shoot_photons < 0 else args.shoot_photons
+        shoot_pass(min(target, 20000 * world), 8 * world)                                       # untimed: module load, local-memory reservation
+        barrier()
+        t_frame = time.perf_counter()
+        st, last, wall = shoot_pass(target, 64 * world)
+        shoot = shoot_report(st, last, wall, target)
+        n_shot_local = pv.photon_count()
+        ag = None
+        if dist is not None:
+            # replicate the shot photons: one all-gather per plane over NVLink (pv_get_photons_dev -> torch tensors -> pv_set_photons_dev)
+            pl = [torch.empty((n_shot_local, k), device=dev) for k in (3, 3, 30)]
+            ids = torch.empty(n_shot_local, dtype=torch.int64, device=dev)
+            pv.get_photons_dev(pl[0], pl[1], pl[2], ids, n_shot_local)
+            t0 = time.perf_counter()
+            f_pos, f_wi, f_alpha, n_all, ag_s = MG.allgather_photons(dist, torch, pl[0], pl[1], pl[2], dev)
+            pv.set_photons_dev(f_pos, f_wi, f_alpha, n_all)
+            torch.cuda.synchronize()
+            ag = {"collective_ms": ag_s * 1e3, "wall_ms": (time.perf_counter() - t0) * 1e3, "photons": n_all}
+            del pl, ids, f_pos, f_wi, f_alpha
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pv.build()
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        pv.Li_dev(d_rays, n_local, d_L, d_T)
+        torch.cuda.synchronize()
+        gather_wall_ms = (time.perf_counter() - t0) * 1e3
+        gather_dev_ms = pv.last_kernel_ms() + pv.last_march_ms()
+        barrier()
+        frame_wall = time.perf_counter() - t_frame
+        vals = torch.tensor([shoot["device_s"] * 1e3, wall * 1e3, build_ms, gather_dev_ms, gather_wall_ms, frame_wall * 1e3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        v = [float(x) for x in vals.cpu().numpy()]
+        frame = {"what": "ONE frame end to end at full size, max over ranks: shoot %d photons (sharded by 4096-path block) -> all-gather -> grid build -> "
+                         "gather of the frame's camera rays against the map just shot" % shoot["photons"],
+                 "shoot_device_ms": v[0], "shoot_wall_ms": v[1], "allgather": ag, "build_wall_ms": v[2], "gather_device_ms": v[3],
+                 "gather_wall_ms": v[4], "frame_wall_ms": v[5], "gather_L_finite": bool(torch.isfinite(d_L).all().item()),
+                 "gather_L_sum": float(d_L.sum().item())}
 
         # the same pass with the SURFACE maps on (pv_shoot_maps + pv_radiance_photons, SURVEY 8(f)-2): every photon class of
         # the reference's shooter in the config-3 scene, bounded sample, single rank (rank 0 reports)
@@ -294,7 +397,7 @@ def main():
                                  "params": {"volume": n, "caustic": n // 4, "indirect": n // 2, "finalgather": True, "nlookup": 50, "maxdist": 0.05}}
             pvm.close()
 
-    # ------------------------------------------------------------------ the photon map of the gather workload
+    # ------------------------------------------------------------------ the photon map of the timed gather workload (same synthetic set as the reference arm)
     lo, hi = W.photon_slice(n_ph, rank, world)
     t0 = time.perf_counter()
     cache = os.environ.get("PV_BENCH_CACHE")               # tuning runs: keep the generated photon slice between processes
@@ -321,16 +424,12 @@ def main():
                      "nvlink_peer_gb_per_s": 770.0}
         del f_pos, f_wi, f_alpha
     torch.cuda.synchronize()
+    pv.build()                                                 # first build of this set: sizes the map's buffers
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pv.build()
+    pv.build()                                                 # timed on a warm context, inputs resident, no allocation inside
+    torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
-
-    # ------------------------------------------------------------------ rays of this rank (image tiles dealt round-robin)
-    rays, order = W.frame_rays(cfg, rank, world)
-    n_local = len(rays)
-    n_total = cfg["xres"] * cfg["yres"]
-    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)
-    d_L = torch.empty((n_local, 30), device=dev); d_T = torch.empty((n_local, 30), device=dev)
 
     for _ in range(max(args.warmup, 3)):
         pv.Li_dev(d_rays, n_local, d_L, d_T)
@@ -339,11 +438,13 @@ def main():
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     kernel_ms = []; march_ms = []; phase_ms = []
+    launches0 = pv.launch_count()
     e0.record(ext)
     for _ in range(args.steps):
         pv.Li_dev(d_rays, n_local, d_L, d_T)
         kernel_ms.append(pv.last_kernel_ms()); march_ms.append(pv.last_march_ms()); phase_ms.append(pv.last_phase_ms())
     e1.record(ext)
+    launches = pv.launch_count() - launches0
     barrier()
     clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -353,23 +454,24 @@ def main():
     stats = pv.gather_stats(reset=True)
     value = n_total * args.steps / (total_ms * 1e-3)
 
-    # roofline of the dominant kernel (gather_kernel), this rank
+    # roofline of the dominant kernel, this rank: cellgather_kernel (cell-batched schedule: lookups + flux sums of every march step)
+    # or gather_kernel (k-nearest regime: lookups fused with the recurrence), timed with CUDA events on the library's stream
     bytes_per_launch = W.gather_bytes(stats, n_local * args.steps) / args.steps
-    avg_kernel_ms = float(np.mean(kernel_ms))
+    ph = dict(zip(("step_sort", "cellgather_kernel", "overflow_pass", "recurrence"), [float(v) for v in np.mean(phase_ms, axis=0)]))
+    cell = ph["cellgather_kernel"] > 0
+    avg_kernel_ms = ph["cellgather_kernel"] if cell else float(np.mean(kernel_ms))
     achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_kind": peak_kind, "kernel": "gather_kernel", "avg_launch_ms": avg_kernel_ms,
-                "march_kernels_ms": float(np.mean(march_ms)),
-                "phase_ms": dict(zip(("step_sort", "cellgather_kernel", "overflow_pass", "recurrence"), [float(v) for v in np.mean(phase_ms, axis=0)])),
+                "peak_kind": peak_kind, "kernel": "cellgather_kernel" if cell else "gather_kernel", "avg_launch_ms": avg_kernel_ms,
+                "gather_ms": float(np.mean(kernel_ms)), "march_kernels_ms": float(np.mean(march_ms)), "phase_ms": ph,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "b_ph": 144,
                 "lookups_per_launch": stats.lookups / args.steps, "photons_found_per_lookup": stats.photons_found / max(stats.lookups, 1),
-                "candidates_per_lookup": stats.candidates_tested / max(stats.lookups, 1)}
-    tr = os.path.join(ROOT, "profiles", "r01_gather_traffic.json")
-    if os.path.exists(tr):
-        try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+                "candidates_per_lookup": stats.candidates_tested / max(stats.lookups, 1),
+                "candidates_staged_per_lookup": stats.candidates_tested / max(stats.lookups, 1) / (32.0 if cell else 1.0),
+                "note": "achieved = SURVEY 8d algorithmic bytes (every photon record a lookup uses counts, sum nFound*144 + lookups*28 + rays*272) / "
+                        "the kernel's CUDA-event time.  The cell-batched kernel stages a block of cells ONCE for 32 lookups and its alpha lines hit "
+                        "L1/L2, so the figure can exceed the HBM peak; traffic (dram bytes per launch) is not measurable inside this run: see the "
+                        "ncu captures under profiles/ (r02_*_summary.md)"}
 
     # ------------------------------------------------------------------ end to end through the host-pointer C ABI call
     h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10).copy()).pin_memory()
@@ -401,6 +503,12 @@ def main():
             except Exception as e:                          # a reported baseline must never cost the bench line
                 shoot["cpu_baseline"] = {"error": repr(e)}
 
+    extra = None
+    if world == 1 and not args.no_extra and args.workload == "config3":
+        try:
+            extra = {"config2": extra_line(pkg, W, "config2", local, args, peak)}
+        except Exception as e:                              # a secondary line must never cost the main one
+            extra = {"config2": {"error": repr(e)}}
     if rank == 0:
         out = {"metric": "volume-gather rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -409,9 +517,11 @@ def main():
                           "stepsize": cfg["stepsize"], "nused": cfg["nused"], "maxdist": cfg["maxdist"], "photon_record_bytes": 144,
                           "l2_policy": "inputs_exceed_l2 (photon map %.1f GB)" % (n_ph * 160 / 1e9), "ray_order": "8x8 tiles",
                           "parallelism": "tiles/%d" % world},
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps,        # per pass: march_setup, publish_total, march_steps, gather_kernel (profiles/*_launches.csv)
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),        # counted by the library at every launch site of the gather path (pv_launch_count): march x3, step keys, radix sort passes, cellgather, overflow pass, recurrence
                "clocks": clocks,
-               "shoot": shoot, "build": {"seconds": build_s, "photons": n_ph, "photon_gen_host_s": gen_s}, "allgather": allgather,
+               "shoot": shoot, "frame": frame, "extra": extra,
+               "build": {"seconds": build_s, "photons": n_ph, "photon_gen_host_s": gen_s, "note": "second pv_build of the resident set (warm, no allocation)"},
+               "allgather": allgather,
                "lookups_per_s": stats.lookups * world / (total_ms * 1e-3) if world == 1 else None, "checksum_L": check}
         print(json.dumps(out), flush=True)
     pv.close()

@@ -314,5 +314,10 @@ class PhotonVolume:
         self._chk(self.lib.pv_last_phase_ms(self.ctx, ms))
         return [float(v) for v in ms]
 
+    def launch_count(self):
+        n = C.c_uint64(0)
+        self._chk(self.lib.pv_launch_count(self.ctx, C.byref(n)))
+        return n.value
+
     def stream(self):
         return self.lib.pv_stream(self.ctx)

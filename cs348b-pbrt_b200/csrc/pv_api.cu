@@ -471,6 +471,12 @@ int pv_last_kernel_ms(pv_ctx *ctx, float *ms) {
     *ms = ctx->last_ms;
     return PV_OK;
 }
+int pv_launch_count(pv_ctx *ctx, uint64_t *n) {
+    LOCK(ctx);
+    if (!n) { ctx->err = "pv_launch_count: null out"; return PV_EINVAL; }
+    *n = ctx->launches;
+    return PV_OK;
+}
 int pv_last_phase_ms(pv_ctx *ctx, float ms[4]) {
     LOCK(ctx);
     if (!ms) { ctx->err = "pv_last_phase_ms: null out"; return PV_EINVAL; }

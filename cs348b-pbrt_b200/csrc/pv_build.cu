@@ -54,10 +54,12 @@ static int exclusive_scan_u32(pv_ctx *ctx, uint32_t *data, uint64_t n, uint32_t 
     if (n == 0) return PV_OK;
     uint32_t tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
     scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(data, n, scratch);
+    ctx->launches += 1;
     if (tiles > 1) {
         int rc = exclusive_scan_u32(ctx, scratch, tiles, scratch + tiles);
         if (rc) return rc;
         scan_add_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(data, n, scratch);
+        ctx->launches += 1;
     }
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
@@ -156,6 +158,7 @@ static int sort_pairs(pv_ctx *ctx, K *keys, uint32_t *vals, K *keys_tmp, uint32_
         rc = exclusive_scan_u32(ctx, hist, hist_n, sscratch);
         if (rc) break;
         rs_scatter_kernel<K><<<nblocks, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, hist, nblocks, kout, vout);
+        ctx->launches += 2;                                 // + rs_count_kernel above
         std::swap(kin, kout); std::swap(vin, vout);
     }
     if (rc) return rc;
@@ -285,6 +288,7 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io2, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
         int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
         bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(src_pos, n, (int *)ctx->io2);
+        ctx->launches += 1;
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_bounds, ctx->io2, sizeof(h_bounds), cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -349,6 +353,7 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
     int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
     uint32_t *keys = (uint32_t *)ctx->scratch, *vals = keys + nn, *keys_tmp = vals + nn, *vals_tmp = keys_tmp + nn;
     keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src_pos, n, g, keys, vals);
+    ctx->launches += 1;
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     uint32_t *skeys, *svals;
     rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, n, key_bits, &skeys, &svals); if (rc) return rc;
@@ -380,6 +385,7 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
         ctx->table_cap = g.table_size + 1;
     }
     cell_start_kernel<<<(g.table_size + 1 + 255) / 256, 256, 0, ctx->stream>>>(skeys, n, g.table_size, ctx->cell_start);
+    ctx->launches += 2;                                     // + gather_records_kernel above
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->grid = g;

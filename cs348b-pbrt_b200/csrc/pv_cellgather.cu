@@ -380,6 +380,7 @@ int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters + CG_CNT_BATCH, 0, 2 * sizeof(unsigned long long), ctx->stream));
     cg_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(g, ga.rays, ga.steps, total, keys, vals);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
+    ctx->launches += 1;
     uint32_t *skeys, *svals;
     rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, total, std::max(1, g.xbits + 2 * g.yzbits), &skeys, &svals); if (rc) return rc;
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[0], ctx->stream));
@@ -394,6 +395,7 @@ int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
     PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cellgather_kernel, CG_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     cellgather_kernel<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches += 1;
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[1], ctx->stream));
     return PV_OK;

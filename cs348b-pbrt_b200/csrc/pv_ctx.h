@@ -89,6 +89,7 @@ struct pv_ctx {
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels
     float last_ms = 0.f, last_march_ms = 0.f;
     int sm_count = 148;
+    uint64_t launches = 0;                         // kernels launched on the build / gather path (pv_launch_count)
 };
 
 #define PV_CUDA_CHECK(ctx, call)                                                                   \

@@ -1390,6 +1390,7 @@ static void launch_recurrence(pv_ctx *ctx, const GatherArgs &a, uint64_t n) {
         recurrence_thread_kernel<<<(unsigned)((n + RT_THREADS - 1) / RT_THREADS), RT_THREADS, 0, ctx->stream>>>(a);
     else
         recurrence_kernel<<<recurrence_blocks(ctx, n), RC_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
 }
 // Li for rays [0, n): march records first (pv_march.cu), then the gather kernel.  Rays are taken in slices so that the
 // step records of one slice stay within PV_MARCH_MAX_BYTES / the free device memory.
@@ -1455,17 +1456,20 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
         o.list = (const uint32_t *)ctx->cg_overflow; o.list_count = ctx->d_counters + CG_CNT_OVERFLOW;
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(o);
+        ctx->launches += 1;
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[2], ctx->stream));
         launch_recurrence(ctx, a, n);
     } else if (step_parallel) {
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+        ctx->launches += 1;
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         launch_recurrence(ctx, a, n);
     } else {
         rc = launch_cfg(ctx, gather_kernel<false>, a.cap, &blocks, &smem); if (rc) return rc;
         gather_kernel<false><<<blocks, GW_THREADS, smem, ctx->stream>>>(a);
+        ctx->launches += 1;
     }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     PV_CUDA_CHECK(ctx, cudaGetLastError());

@@ -158,6 +158,7 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
     const uint32_t blocks = (uint32_t)((n + MS_THREADS - 1) / MS_THREADS);
     march_setup_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(ctx->dscene, d_rays, n, prm->stepsize, (RayHdr *)ctx->march_hdr, d_total);
+    ctx->launches += 2;                                 // + publish_total_kernel below
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     // The step count comes back through mapped pinned memory, not a memcpy: a copy would queue on the device->host copy
     // engine behind the result download of the previous slice (pv_gather overlaps the two).
@@ -181,6 +182,7 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     if (total) {
         if (ctx->hscene.n_spheres) march_steps_kernel<true><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
         else march_steps_kernel<false><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev3, ctx->stream));

@@ -244,6 +244,9 @@ int pv_last_march_ms(pv_ctx *ctx, float *ms);
  * cellgather_kernel (lookups + flux sums: the dominant kernel), ms[2] the overflow pass (steps with more than nused photons
  * in range), ms[3] the recurrence pass.  All zero when another schedule ran.                                                */
 int pv_last_phase_ms(pv_ctx *ctx, float ms[4]);
+/* Kernels this context has launched so far on the map-build and gather paths (pv_build, pv_gather*): every launch site counts
+ * itself; the difference across a timed region is what bench.py reports as gpu_launches.                                   */
+int pv_launch_count(pv_ctx *ctx, uint64_t *n);
 
 /* ---- SingleScatteringIntegrator::Li (integrators/single.cpp:66-138) and
  *      EmissionIntegrator::Li (integrators/emission.cpp:63-106) -------------
