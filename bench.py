@@ -335,9 +335,17 @@ def main():
     shoot, frame = {}, None
     if dist is not None:
         warm = torch.zeros(1, device=dev); dist.all_reduce(warm); torch.cuda.synchronize()     # lazy NCCL initialisation happens here
+        # the library's own communicator (csrc/pv_comm.cu): rank 0 makes the NCCL id, torch.distributed only carries its 128 bytes
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.tensor(list(pkg.PhotonVolume.comm_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        pv.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
     if args.shoot_photons != 0:
         target = n_ph if args.shoot_photons < 0 else args.shoot_photons
         shoot_pass(min(target, 20000 * world), 8 * world)                                       # untimed: module load, local-memory reservation
+        if dist is not None:
+            pv.allgather_photons()                                                              # untimed: the communicator's first collective
         barrier()
         t_frame = time.perf_counter()
         st, last, wall = shoot_pass(target, 64 * world)
@@ -345,16 +353,15 @@ def main():
         n_shot_local = pv.photon_count()
         ag = None
         if dist is not None:
-            # replicate the shot photons: one all-gather per plane over NVLink (pv_get_photons_dev -> torch tensors -> pv_set_photons_dev)
-            pl = [torch.empty((n_shot_local, k), device=dev) for k in (3, 3, 30)]
-            ids = torch.empty(n_shot_local, dtype=torch.int64, device=dev)
-            pv.get_photons_dev(pl[0], pl[1], pl[2], ids, n_shot_local)
+            # replicate the shot photons: pv_allgather_photons = one grouped ncclAllGather per SoA plane, straight from the shooter's
+            # planes into the planes pv_build reads, then the sort by photon id that makes the set independent of the rank count
             t0 = time.perf_counter()
-            f_pos, f_wi, f_alpha, n_all, ag_s = MG.allgather_photons(dist, torch, pl[0], pl[1], pl[2], dev)
-            pv.set_photons_dev(f_pos, f_wi, f_alpha, n_all)
+            ag_ms = pv.allgather_photons()
             torch.cuda.synchronize()
-            ag = {"collective_ms": ag_s * 1e3, "wall_ms": (time.perf_counter() - t0) * 1e3, "photons": n_all}
-            del pl, ids, f_pos, f_wi, f_alpha
+            n_all = pv.photon_count()
+            nbytes = (world - 1) / world * n_all * 160
+            ag = {"collective_ms": ag_ms, "wall_ms": (time.perf_counter() - t0) * 1e3, "photons": n_all, "bytes_in_per_gpu": nbytes,
+                  "gb_per_s_per_gpu": nbytes / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None}
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         pv.build()
@@ -410,19 +417,16 @@ def main():
             os.makedirs(cache, exist_ok=True); np.savez(cfile, pos=pos, wi=wi, alpha=alpha)
     gen_s = time.perf_counter() - t0
     allgather = None
-    if world == 1:
-        pv.set_photons(pos, wi, alpha)
-    else:
+    pv.set_photons(pos, wi, alpha)                             # this rank's slice of the set
+    if world > 1:
         barrier()
-        f_pos, f_wi, f_alpha, n_all, ag_s = MG.allgather_photons(dist, torch, pos, wi, alpha, dev)
-        assert n_all == n_ph
-        ag_ms = torch.tensor([ag_s * 1e3], device=dev, dtype=torch.float64)
-        dist.all_reduce(ag_ms, op=dist.ReduceOp.MAX)
-        pv.set_photons_dev(f_pos, f_wi, f_alpha, n_ph)
-        nbytes = (world - 1) / world * n_ph * 144
-        allgather = {"ms": float(ag_ms.item()), "bytes_in_per_gpu": nbytes, "gb_per_s_per_gpu": nbytes / (float(ag_ms.item()) * 1e-3) / 1e9,
-                     "nvlink_peer_gb_per_s": 770.0}
-        del f_pos, f_wi, f_alpha
+        ag_ms = pv.allgather_photons(renumber=True)            # union in global photon order, photon i keeps index i
+        assert pv.photon_count() == n_ph
+        t = torch.tensor([ag_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = (world - 1) / world * n_ph * 160
+        allgather = {"ms": float(t.item()), "bytes_in_per_gpu": nbytes, "gb_per_s_per_gpu": nbytes / (float(t.item()) * 1e-3) / 1e9,
+                     "nvlink_peer_gb_per_s": 770.0, "how": "pv_allgather_photons: grouped ncclAllGather of the four SoA planes (160 B per photon)"}
     torch.cuda.synchronize()
     pv.build()                                                 # first build of this set: sizes the map's buffers
     torch.cuda.synchronize()

@@ -314,6 +314,30 @@ class PhotonVolume:
         self._chk(self.lib.pv_last_phase_ms(self.ctx, ms))
         return [float(v) for v in ms]
 
+    # ---- NCCL behind the C ABI (csrc/pv_comm.cu) ---------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes for pv_comm_init, made by rank 0 and handed to the other ranks by the caller's own means."""
+        lib = load_library()
+        buf = (C.c_uint8 * 128)()
+        rc = lib.pv_comm_unique_id(buf)
+        if rc != 0:
+            raise PVError(rc, (lib.pv_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(self.lib.pv_comm_init(self.ctx, buf, C.c_int(rank), C.c_int(world)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.pv_comm_destroy(self.ctx))
+
+    def allgather_photons(self, renumber=False):
+        """Every rank ends with the union of all ranks' photons ordered by id; returns the device ms of the collective."""
+        ms = C.c_float(0)
+        self._chk(self.lib.pv_allgather_photons(self.ctx, C.c_int(1 if renumber else 0), C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         n = C.c_uint64(0)
         self._chk(self.lib.pv_launch_count(self.ctx, C.byref(n)))

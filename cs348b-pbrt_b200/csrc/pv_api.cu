@@ -61,6 +61,7 @@ void pv_destroy(pv_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    pvi_comm_destroy(ctx);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
                     ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist};
@@ -170,11 +171,13 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
 static int reserve_photons(pv_ctx *ctx, uint64_t n) {
     if (n <= ctx->cap_photons) return PV_OK;
     uint64_t cap = std::max<uint64_t>(n, 1024);
-    float *np, *nw, *na; uint64_t *ni;
-    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&np, cap * 3 * sizeof(float)));
-    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&nw, cap * 3 * sizeof(float)));
-    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&na, cap * 32 * sizeof(float)));
-    PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ni, cap * sizeof(uint64_t)));
+    float *np = nullptr, *nw = nullptr, *na = nullptr; uint64_t *ni = nullptr;
+    if (cudaMalloc((void **)&np, cap * 3 * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&nw, cap * 3 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&na, cap * 32 * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&ni, cap * sizeof(uint64_t)) != cudaSuccess) {
+        cudaGetLastError();
+        if (np) cudaFree(np); if (nw) cudaFree(nw); if (na) cudaFree(na); if (ni) cudaFree(ni);      // nothing of a failed group stays behind
+        ctx->err = "out of device memory for " + std::to_string(cap) + " photons"; return PV_ENOMEM;
+    }
     if (ctx->n_photons) {
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(np, ctx->d_pos, ctx->n_photons * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(nw, ctx->d_wi, ctx->n_photons * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -470,6 +473,39 @@ int pv_last_kernel_ms(pv_ctx *ctx, float *ms) {
     if (!ms) { ctx->err = "pv_last_kernel_ms: null out"; return PV_EINVAL; }
     *ms = ctx->last_ms;
     return PV_OK;
+}
+int pv_comm_unique_id(uint8_t *id) {
+    if (!id) { g_err = "pv_comm_unique_id: null id"; return PV_EINVAL; }
+    return pvi_comm_unique_id(id, &g_err);
+}
+int pv_comm_init(pv_ctx *ctx, const uint8_t *id, int rank, int world) {
+    LOCK(ctx);
+    if (!id) { ctx->err = "pv_comm_init: null id"; return PV_EINVAL; }
+    return pvi_comm_init(ctx, id, rank, world);
+}
+int pv_comm_init_all(pv_ctx **ctxs, int n) {
+    if (!ctxs || n < 1) { g_err = "pv_comm_init_all: no contexts"; return PV_EINVAL; }
+    for (int i = 0; i < n; ++i) if (!ctxs[i]) { g_err = "pv_comm_init_all: null context"; return PV_EINVAL; }
+    int rc = pvi_comm_init_all(ctxs, n);
+    cudaSetDevice(ctxs[0]->device);
+    return rc;
+}
+int pv_comm_destroy(pv_ctx *ctx) {
+    LOCK(ctx);
+    return pvi_comm_destroy(ctx);
+}
+int pv_allgather_photons(pv_ctx *ctx, int renumber, float *collective_ms) {
+    LOCK(ctx);
+    return pvi_allgather_photons(ctx, renumber, collective_ms);
+}
+int pv_broadcast_photons(pv_ctx **ctxs, int n, int src, float *collective_ms) {
+    if (!ctxs || n < 1 || src < 0 || src >= n) { g_err = "pv_broadcast_photons: bad arguments"; return PV_EINVAL; }
+    for (int i = 0; i < n; ++i) if (!ctxs[i]) { g_err = "pv_broadcast_photons: null context"; return PV_EINVAL; }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int i = 0; i < n; ++i) locks.emplace_back(ctxs[i]->mu);
+    int rc = pvi_broadcast_photons(ctxs, n, src, collective_ms);
+    cudaSetDevice(ctxs[src]->device);
+    return rc;
 }
 int pv_launch_count(pv_ctx *ctx, uint64_t *n) {
     LOCK(ctx);

@@ -89,6 +89,7 @@ struct pv_ctx {
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;      // around the march kernels
     float last_ms = 0.f, last_march_ms = 0.f;
     int sm_count = 148;
+    void *comm = nullptr; int comm_rank = 0, comm_world = 0;     // ncclComm_t of pv_comm_init / pv_comm_init_all (pv_comm.cu)
     uint64_t launches = 0;                         // kernels launched on the build / gather path (pv_launch_count)
 };
 
@@ -127,6 +128,13 @@ int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit);
 int pvi_transmittance(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, const float *d_u, float *d_T);
 // pv_api.cu
 int pvi_reserve_photons(pv_ctx *ctx, uint64_t n);
+// pv_comm.cu
+int pvi_comm_unique_id(uint8_t *id, std::string *err);
+int pvi_comm_init(pv_ctx *ctx, const uint8_t *id, int rank, int world);
+int pvi_comm_init_all(pv_ctx **ctxs, int n);
+int pvi_comm_destroy(pv_ctx *ctx);
+int pvi_allgather_photons(pv_ctx *ctx, int renumber, float *collective_ms);
+int pvi_broadcast_photons(pv_ctx **ctxs, int n, int src, float *collective_ms);
 // pv_shoot.cu
 int pvi_shoot_blocks(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, const pv_shoot_params *prm, uint32_t *counts, pv_shoot_stats *stats);
 int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block);

@@ -866,7 +866,7 @@ __global__ void permute_photons_kernel(const uint32_t *__restrict__ order, uint6
 // set and its order then depend only on (scene, seed, target), not on thread scheduling or the number of ranks.
 // split: the ids carry a class in their top bits (pv_shoot_maps); class 0 stays the context's photon set, the others
 // move to ctx->surf[class - 1].
-static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split) {
+static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split, bool bound_always = false) {
     uint64_t n = ctx->n_photons;
     ctx->built = false;
     if (split) for (int c = 0; c < 4; ++c) ctx->surf[c].n = 0;
@@ -900,7 +900,7 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split) {
     };
     const uint64_t path_limit = last_block ? (((last_block * SH_BLOCK) << 16) | 0xffffull) : ((1ull << 60) - 1);
     uint64_t keep = n;
-    if (last_block || split) { rc = upper_bound(path_limit, &keep); if (rc) return rc; }
+    if (last_block || split || bound_always) { rc = upper_bound(path_limit, &keep); if (rc) return rc; }
     if (split) {
         for (uint32_t c = 1; c < PC_COUNT; ++c) {
             uint64_t lo = 0, hi = 0;
@@ -933,6 +933,9 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split) {
     return PV_OK;
 }
 int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) { return shoot_finish(ctx, last_block, false); }
+// order the context's photon set by id and drop the records whose id is not a volume-photon id (class bits set: the slack of
+// pv_allgather_photons carries id = ~0)
+int pvi_sort_photons_by_id(pv_ctx *ctx) { return shoot_finish(ctx, 0, false, true); }
 
 // Single-rank driver == PhotonShootingTask::Run's outer loop (photonshooter.cpp:245-356): waves of blocks until the
 // running photon count reaches the target at some block M; give-up rule of :285-299.

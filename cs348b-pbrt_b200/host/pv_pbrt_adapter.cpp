@@ -129,7 +129,7 @@ int pv_volume_term(const pv_ray *rays, size_t n, const pv_gather_params *prm, fl
     return pv_volume_term_on(g_pv.ctx, rays, n, prm, L, T);
 }
 
-// ---- several GPUs inside the drop-in (off unless PV_DEVICES lists more than one device; NOT yet run on a multi-GPU box) -----
+// ---- several GPUs inside the drop-in (off unless PV_DEVICES lists more than one device) -----
 // The scene and the volume photon map are replicated (the whole map is a few GB at most); the camera rays of
 // the frame are cut into one contiguous run per device, each with its global ray index as Philox stream base, so the image does
 // not depend on the number of devices.  Shooting, final gathering and the secondary rays of specular bounces stay on the first.
@@ -145,25 +145,33 @@ void pv_replicate(bool with_map, float maxdist, uint32_t nused) {
     for (size_t i = 0; i < g_pv.replicas.size(); ++i) pv_destroy(g_pv.replicas[i]);
     g_pv.replicas.clear();
     if (dev.size() < 2) return;
-    uint64_t n = 0;
-    std::vector<float> pos, wi, alpha;
-    if (with_map) {
-        int rc = pv_photon_count(g_pv.ctx, &n);
-        pos.resize(3 * n); wi.resize(3 * n); alpha.resize((size_t)PV_NSPEC * n);
-        if (!rc && n) rc = pv_get_photons(g_pv.ctx, pos.data(), wi.data(), alpha.data(), NULL, n, &n);
-        if (rc) pv_fail("pv_get_photons", rc);
-    }
     for (size_t i = 1; i < dev.size(); ++i) {
         pv_ctx *c = NULL;
         int rc = pv_create(&c, dev[i]);
         if (rc) Severe("pv_create on device %d failed (%d): %s", dev[i], rc, pv_last_error(NULL));
         rc = pv_set_scene(c, &g_pv.scene.desc);
-        if (!rc && with_map) rc = pv_set_photons(c, pos.data(), wi.data(), alpha.data(), n);
-        if (!rc && with_map) rc = pv_build(c, maxdist, nused);
-        if (rc) Severe("replica on device %d failed (%d): %s", dev[i], rc, pv_last_error(c));
+        if (rc) Severe("scene on device %d failed (%d): %s", dev[i], rc, pv_last_error(c));
         g_pv.replicas.push_back(c);
     }
-    fprintf(stderr, "[pv] scene%s replicated on %zu more device(s)\n", with_map ? " and volume photon map" : "", g_pv.replicas.size());
+    float ms = 0.f;
+    if (with_map) {
+        // the map goes GPU to GPU over NVLink: one NCCL communicator over the contexts, one grouped broadcast of the four SoA
+        // planes (pv_broadcast_photons, csrc/pv_comm.cu); every replica then builds its own grid
+        std::vector<pv_ctx *> all(1, g_pv.ctx);
+        all.insert(all.end(), g_pv.replicas.begin(), g_pv.replicas.end());
+        pv_comm_destroy(g_pv.ctx);                        // a second Preprocess of the same process starts from a fresh communicator
+        int rc = pv_comm_init_all(all.data(), (int)all.size());
+        if (rc) Severe("pv_comm_init_all over %zu devices failed (%d): %s", all.size(), rc, pv_last_error(g_pv.ctx));
+        rc = pv_broadcast_photons(all.data(), (int)all.size(), 0, &ms);
+        if (rc) Severe("pv_broadcast_photons failed (%d): %s", rc, pv_last_error(g_pv.ctx));
+        for (size_t i = 0; i < g_pv.replicas.size(); ++i) {
+            rc = pv_build(g_pv.replicas[i], maxdist, nused);
+            if (rc) Severe("map build on device %d failed (%d): %s", dev[i + 1], rc, pv_last_error(g_pv.replicas[i]));
+        }
+    }
+    fprintf(stderr, "[pv] scene%s replicated on %zu more device(s)", with_map ? " and volume photon map" : "", g_pv.replicas.size());
+    if (with_map) fprintf(stderr, " (NCCL broadcast %.2f ms)", ms);
+    fprintf(stderr, "\n");
 }
 // the volume term of a whole frame: one call per device, concurrently
 int pv_volume_term_frame(const pv_ray *rays, size_t n, const pv_gather_params *prm, float *L, float *T) {

@@ -366,6 +366,25 @@ int pv_radiance_nearest(pv_ctx *ctx, const float *pts, const float *normals, uin
 int pv_final_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step, uint64_t seed, uint64_t index_base,
                     float *Lindir, uint32_t *idx);
 
+/* ---- multi-GPU: replication of the photon map over NVLink ------------------------------------------
+ * The reference's photon map is one vector shared by its pthread tasks (core/photonshooter.cpp:333-337); with emission
+ * sharded over GPUs (pv_shoot_blocks) the map is replicated once per frame instead.  NCCL is opened at run time
+ * (libnccl.so.2); a single-GPU host never needs it.
+ *   one process per GPU: rank 0 calls pv_comm_unique_id and hands the 128 bytes to the others (MPI, a file, a TCP store),
+ *     every rank calls pv_comm_init, then pv_allgather_photons after shooting (or after pv_set_photons of its slice):
+ *     every rank ends with the union of all ranks' photons ordered by id -- for shot photons (renumber = 0) exactly the
+ *     single-rank set; renumber = 1 first gives rank r's photon i the id (photons of ranks < r) + i, i.e. the index it has
+ *     in the concatenated set (injected slices).  collective_ms (may be NULL): device time of the grouped all-gathers.
+ *   one process, several GPUs (the drop-in's PV_DEVICES): pv_comm_init_all over one context per device, then
+ *     pv_broadcast_photons sends ctxs[src]'s photon set to the others.                                               */
+#define PV_COMM_ID_BYTES 128
+int pv_comm_unique_id(uint8_t *id);
+int pv_comm_init(pv_ctx *ctx, const uint8_t *id, int rank, int world);
+int pv_comm_init_all(pv_ctx **ctxs, int n);
+int pv_comm_destroy(pv_ctx *ctx);
+int pv_allgather_photons(pv_ctx *ctx, int renumber, float *collective_ms);
+int pv_broadcast_photons(pv_ctx **ctxs, int n, int src, float *collective_ms);
+
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);
 

@@ -78,6 +78,20 @@ int pv_set_photons(pv_ctx *ctx, const float *pos, const float *wi, const float *
     logf_("set_photons dev=%d n=%llu sum=%.6f\n", ctx->device, (unsigned long long)n, sum);
     return PV_OK;
 }
+/* the map's replication inside one process (csrc/pv_comm.cu): one communicator over the contexts, one broadcast */
+static int g_comm_n = 0;
+int pv_comm_init_all(pv_ctx **ctxs, int n) {
+    char devs[128] = ""; for (int i = 0; i < n; ++i) { char t[16]; snprintf(t, sizeof t, "%s%d", i ? "," : "", ctxs[i]->device); strcat(devs, t); }
+    g_comm_n = n; logf_("comm_init_all n=%d devs=%s\n", n, devs); return PV_OK;
+}
+int pv_comm_destroy(pv_ctx *ctx) { (void)ctx; return PV_OK; }
+int pv_broadcast_photons(pv_ctx **ctxs, int n, int src, float *ms) {
+    if (n != g_comm_n) return PV_ESTATE;
+    for (int i = 0; i < n; ++i) { ctxs[i]->n_photons = ctxs[src]->n_photons; ctxs[i]->photon_sum = ctxs[src]->photon_sum; }
+    if (ms) *ms = 0.f;
+    logf_("broadcast_photons dev=%d n=%llu to=%d\n", ctxs[src]->device, (unsigned long long)ctxs[src]->n_photons, n - 1);
+    return PV_OK;
+}
 static void fake_li(const char *what, pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_params *p, float *L, float *T) {
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t g = p->ray_index_base + i;

@@ -61,8 +61,9 @@ def test_frame_is_sharded_over_devices_by_global_ray_index(mock, tmp_path, pkg):
 
 
 def test_photon_map_is_replicated_before_the_frame_is_sharded(mock, tmp_path, pkg):
-    """VolumeIntegrator "photonvolume", PV_DEVICES=2,0: photons are shot and the map built on the FIRST listed device, read back
-    once, installed and built on the other (same count, same checksum), then the frame is split between the two."""
+    """VolumeIntegrator "photonvolume", PV_DEVICES=2,0: photons are shot and the map built on the FIRST listed device, then
+    broadcast device to device (one communicator over both contexts, pv_broadcast_photons -- no read-back through host
+    memory) and built on the other, then the frame is split between the two."""
     from cs348b_pbrt_b200 import scenes
     text = lambda out: scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=128, yres=128, outfile=out)
     one, log1, _ = render(mock, tmp_path, "pone", text("pone.pfm"))
@@ -70,11 +71,12 @@ def test_photon_map_is_replicated_before_the_frame_is_sharded(mock, tmp_path, pk
     assert one == two
     assert [c["dev"] for c in calls(log2, "create")] == [2, 0]
     assert [c["dev"] for c in calls(log2, "shoot")] == [2]
-    order = [l.split()[0] + ":" + re.search(r"dev=(\d+)", l).group(1) for l in log2]
-    assert order.index("build:2") < order.index("get_photons:2") < order.index("set_photons:0") < order.index("build:0") < order.index("gather:2")
-    got = re.search(r"sum=([0-9.]+)", [l for l in log2 if l.startswith("get_photons")][0]).group(1)
-    put = re.search(r"sum=([0-9.]+)", [l for l in log2 if l.startswith("set_photons")][0]).group(1)
-    assert got == put and calls(log2, "set_photons")[0]["n"] == 1000
+    order = [l.split()[0] + ":" + re.search(r"dev[s]?=(\d+)", l).group(1) for l in log2]
+    assert order.index("build:2") < order.index("comm_init_all:2") < order.index("broadcast_photons:2") < order.index("build:0") < order.index("gather:2")
+    assert not calls(log2, "get_photons") and not calls(log2, "set_photons")            # nothing staged through the host
+    b = calls(log2, "broadcast_photons")
+    assert len(b) == 1 and b[0]["n"] == 1000 and b[0]["to"] == 1
+    assert [c["n"] for c in calls(log2, "build")] == [1000, 1000]
     g = sorted(calls(log2, "gather"), key=lambda c: c["base"])
     assert [c["dev"] for c in g] == [2, 0] and g[0]["base"] == 0 and g[0]["n"] == g[1]["base"]
     assert g[1]["base"] + g[1]["n"] == calls(log1, "gather")[0]["n"]
