@@ -74,6 +74,8 @@ struct pv_ctx {
     void *io = nullptr; size_t io_bytes = 0;       // device staging for host-pointer entry points
     void *io2 = nullptr; size_t io2_bytes = 0;
 
+    void *wf = nullptr; size_t wf_bytes = 0;       // slot state of the shooter's wavefront (pv_wavefront.cu)
+
     pv_gather_stats *d_stats = nullptr;
     unsigned long long *d_counters = nullptr;      // work-distribution counters
     // march records of the ray slice being gathered (pv_march.cu): RayHdr per ray, StepRec per march step

@@ -32,3 +32,16 @@ def golden():
             cache[name] = (dict(npz), p.sceneio.read_scene(scn) if os.path.exists(scn) else None)
         return cache[name]
     return get
+
+
+@pytest.fixture(scope="module")
+def pv_factory(pkg):
+    made = []
+
+    def make(**kw):
+        pv = pkg.PhotonVolume(device=0, **kw)
+        made.append(pv)
+        return pv
+    yield make
+    for pv in made:
+        pv.close()

@@ -20,17 +20,6 @@ def relerr(a, b, floor=1e-30):
     return np.abs(a - b) / np.maximum(np.abs(b), floor)
 
 
-@pytest.fixture(scope="module")
-def pv_factory(pkg):
-    made = []
-
-    def make(**kw):
-        pv = pkg.PhotonVolume(device=0, **kw)
-        made.append(pv)
-        return pv
-    yield make
-    for pv in made:
-        pv.close()
 
 
 def volint_scene(pkg, golden, name):
