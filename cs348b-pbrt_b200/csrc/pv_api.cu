@@ -64,7 +64,7 @@ void pv_destroy(pv_ctx *ctx) {
     pvi_comm_destroy(ctx);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
     if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
@@ -100,8 +100,29 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     if (s->n_spheres && (!s->spheres || !s->prim_shape)) { ctx->err = "pv_set_scene: spheres without a prim_shape table"; return PV_EINVAL; }
     for (uint32_t i = 0; s->n_spheres && i < s->n_prims; ++i)
         if (s->prim_shape[i] != PV_SHAPE_TRIANGLE && s->prim_shape[i] >= s->n_spheres) { ctx->err = "pv_set_scene: sphere index out of range"; return PV_EINVAL; }
+    // the flattened BVH (accelerators/bvh.cpp:154-164): every kernel walks it with a fixed 64-entry todo stack (bvh_traverse,
+    // like the reference's todo[64]) and indexes by child / primitive offsets, so a malformed or too deep tree is refused here
+    if (s->n_nodes) {
+        if (!s->nodes) { ctx->err = "pv_set_scene: null BVH nodes"; return PV_EINVAL; }
+        std::vector<std::pair<uint32_t, uint32_t>> todo(1, std::make_pair(0u, 0u));       // node, entries on the traversal stack when it is visited
+        std::vector<uint8_t> seen(s->n_nodes, 0);
+        while (!todo.empty()) {
+            const uint32_t i = todo.back().first, depth = todo.back().second; todo.pop_back();
+            if (i >= s->n_nodes || seen[i]) { ctx->err = "pv_set_scene: BVH child offset out of range or shared"; return PV_EINVAL; }
+            seen[i] = 1;
+            const pv_bvh_node &nd = s->nodes[i];
+            if (nd.n_primitives) {
+                if ((uint64_t)nd.offset + nd.n_primitives > s->n_prims) { ctx->err = "pv_set_scene: BVH leaf primitive range out of bounds"; return PV_EINVAL; }
+            } else {
+                if (nd.axis > 2) { ctx->err = "pv_set_scene: BVH split axis > 2"; return PV_EINVAL; }
+                if (nd.offset <= i + 1 || nd.offset >= s->n_nodes) { ctx->err = "pv_set_scene: BVH second child offset out of range"; return PV_EINVAL; }
+                if (depth + 1 > 64) { ctx->err = "pv_set_scene: BVH deeper than the 64-entry traversal stack"; return PV_EINVAL; }
+                todo.push_back(std::make_pair(i + 1, depth + 1)); todo.push_back(std::make_pair(nd.offset, depth + 1));
+            }
+        }
+    }
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->has_scene = false; ctx->built = false;
+    ctx->has_scene = false; ctx->built = false; ctx->shoot_yield[0] = ctx->shoot_yield[1] = 0.;
     int rc;
     if ((rc = upload(ctx, &ctx->d_nodes, s->nodes, sizeof(pv_bvh_node) * (size_t)s->n_nodes))) return rc;
     if (s->n_spheres) {
@@ -120,6 +141,13 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     } else if ((rc = upload(ctx, &ctx->d_tri, s->tri_verts, sizeof(float) * 9 * (size_t)s->n_prims))) return rc;
     if ((rc = upload(ctx, &ctx->d_prim_mat, s->prim_material, sizeof(uint32_t) * (size_t)s->n_prims))) return rc;
     if ((rc = upload(ctx, &ctx->d_mats, s->materials, sizeof(pv_material) * (size_t)s->n_materials))) return rc;
+    {
+        std::vector<uint8_t> mf(std::max<uint32_t>(s->n_materials, 1u), 0);
+        for (uint32_t i = 0; i < s->n_materials; ++i)
+            for (int b = 0; b < PV_NSPEC; ++b)
+                mf[i] |= (s->materials[i].kd[b] != 0.f ? PV_MATF_KD : 0) | (s->materials[i].kr[b] != 0.f ? PV_MATF_KR : 0) | (s->materials[i].kt[b] != 0.f ? PV_MATF_KT : 0);
+        if ((rc = upload(ctx, &ctx->d_mat_flags, mf.data(), mf.size()))) return rc;
+    }
     if ((rc = upload(ctx, &ctx->d_lights, s->lights, sizeof(pv_light) * (size_t)s->n_lights))) return rc;
     if ((rc = upload(ctx, &ctx->d_spheres, s->spheres, sizeof(pv_sphere) * (size_t)s->n_spheres))) return rc;
     DevScene &h = ctx->hscene;
@@ -129,6 +157,7 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     h.mats = (const pv_material *)ctx->d_mats; h.n_mats = s->n_materials;
     h.lights = (const pv_light *)ctx->d_lights; h.n_lights = s->n_lights;
     h.spheres = (const pv_sphere *)ctx->d_spheres; h.n_spheres = s->n_spheres;
+    h.mat_flags = (const uint8_t *)ctx->d_mat_flags;
     memcpy(h.world_bound, s->world_bound, sizeof(h.world_bound));
     memcpy(h.cie_y, s->cie_y, sizeof(h.cie_y));
     if (s->medium && s->medium->type != PV_MEDIUM_NONE) {

@@ -42,7 +42,7 @@ struct pv_ctx {
     DevScene hscene{};
     DevScene *dscene = nullptr;
     void *d_nodes = nullptr, *d_tri = nullptr, *d_prim_mat = nullptr, *d_mats = nullptr, *d_lights = nullptr, *d_density = nullptr;
-    void *d_spheres = nullptr;
+    void *d_spheres = nullptr, *d_mat_flags = nullptr;
     bool has_scene = false;
 
     // photons in deposit order, SoA planes: pos[3n], wi[3n], alpha[32n] (30 bins + 2 pad = one 128-byte line,
@@ -74,6 +74,8 @@ struct pv_ctx {
     void *io = nullptr; size_t io_bytes = 0;       // device staging for host-pointer entry points
     void *io2 = nullptr; size_t io2_bytes = 0;
 
+    double shoot_yield[2] = {0., 0.};              // deposits per light path seen so far (volume-only pass, all-maps pass): sizes the next wave's buffer
+    uint64_t wf_deep_pages = 0;                    // size of the wavefront's deep-stack page pool (grown when a wave runs it dry)
     void *wf = nullptr; size_t wf_bytes = 0;       // slot state of the shooter's wavefront (pv_wavefront.cu)
 
     pv_gather_stats *d_stats = nullptr;

@@ -45,7 +45,11 @@ struct DevScene {
     // the first float of its 9-float slot is a NaN whose low 22 bits are the index into spheres[] (pv_set_scene writes it),
     // so the leaf loop pays one compare on a value it loads anyway and triangle-only scenes load nothing extra.
     const pv_sphere *spheres; uint32_t n_spheres;
+    const uint8_t *mat_flags;          // per material: PV_MATF_* (which of Kd / Kr / Kt has a non-zero bin), made once by pv_set_scene
 };
+#define PV_MATF_KD 1
+#define PV_MATF_KR 2
+#define PV_MATF_KT 4
 #define PV_SPHERE_TAG 0x7FC00000u
 #define PV_SPHERE_INDEX_MASK 0x003FFFFFu
 

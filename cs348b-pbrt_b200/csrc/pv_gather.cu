@@ -1276,6 +1276,7 @@ int pvi_knn(pv_ctx *ctx, const float *d_pts, uint64_t n, uint32_t k, float r2, u
 }
 int pvi_surface_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_nf, uint64_t n, uint32_t n_lookup, float max_dist2, uint64_t n_paths,
                         float *d_Lr, float *d_Lt) {
+    if (n_paths > 0x7fffffffull) { ctx->err = "pv_surface_lphoton: n_paths beyond the reference's int"; return PV_EINVAL; }
     if (!ctx->built || ctx->map_which == PV_MAP_VOLUME || ctx->map_which == PV_MAP_RADIANCE) {
         ctx->err = "pv_surface_lphoton: select a surface photon map first (pv_select_map with PV_MAP_CAUSTIC / INDIRECT / DIRECT)"; return PV_ESTATE;
     }
@@ -1339,6 +1340,7 @@ int pvi_lphoton(pv_ctx *ctx, const float *d_pts, const float *d_w, uint64_t n, u
 // ComputeRadianceTask::Run (core/photonshooter.cpp:359-395) for all radiance-photon sites of the context: one grid build and
 // one ephoton_kernel launch per surface map, in the reference's summation order direct, indirect, caustic.
 int pvi_radiance(pv_ctx *ctx, uint32_t n_lookup, float max_dist2, const uint64_t counts[3]) {
+    for (int k = 0; k < 3; ++k) if (counts[k] > 0x7fffffffull) { ctx->err = "pv_radiance_photons: a path count beyond the reference's int"; return PV_EINVAL; }
     PhotonSet &rp = ctx->surf[3];
     ctx->rad_valid = false;
     const uint64_t n = rp.n;
@@ -1492,6 +1494,10 @@ int pvi_gather(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_pa
     if (need_map && !ctx->built) { ctx->err = "pv_gather: photon map not built (call pv_build)"; return PV_ESTATE; }
     if (need_map && ctx->map_which != PV_MAP_VOLUME) { ctx->err = "pv_gather: the grid is built over a surface photon map (call pv_build)"; return PV_ESTATE; }
     if (!(prm->stepsize > 0.f)) { ctx->err = "pv_gather: stepsize must be > 0"; return PV_EINVAL; }
+    if (need_map && !(prm->maxdist > 0.f)) { ctx->err = "pv_gather: maxdist must be > 0"; return PV_EINVAL; }
+    if (need_map && (prm->nused < 1 || warp_smem_bytes(lookup_cap(prm->nused)) * GW_WARPS > 200 * 1024)) {
+        ctx->err = "pv_gather: nused must be >= 1 and small enough for the shared-memory candidate list"; return PV_EINVAL;
+    }
     ctx->last_ms = 0.f; ctx->last_march_ms = 0.f;
     for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0.f;
     if (n == 0) return PV_OK;

@@ -628,8 +628,19 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
     int rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, sizeof(uint32_t) * (size_t)n_blocks * n_cls + 64); if (rc) return rc;
     uint32_t *d_counts = (uint32_t *)ctx->io2;
     unsigned long long *d_nout = ctx->d_counters + 1, *d_work = ctx->d_counters + 2, *d_stats = ctx->d_counters + 8;
-    // first guess of the capacity: 8% deposit yield on top of what is already stored
-    uint64_t want_cap = ctx->n_photons + (uint64_t)((double)n_local * SH_BLOCK * (surf ? 1.5 : 0.08)) + 65536;
+    // first guess of the capacity on top of what is already stored: the deposits per path seen in this context's earlier waves
+    // (with a margin), else 8% (volume only) / 150% (all maps); never more than half of the free device memory -- a wave that
+    // overflows its buffer is replayed with the exact size anyway
+    double &yield = ctx->shoot_yield[surf ? 1 : 0];
+    const double per_path = yield > 0. ? yield * 1.25 : (surf ? 1.5 : 0.08);
+    uint64_t want_cap = ctx->n_photons + (uint64_t)((double)n_local * SH_BLOCK * per_path) + 65536;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const uint64_t room = ctx->cap_photons + (uint64_t)(free_b / 2) / 160;         // 160 B per photon over the four planes
+            if (want_cap > room && room > ctx->n_photons + 65536) want_cap = room;
+        }
+    }
     for (int attempt = 0; attempt < 3; ++attempt) {
         rc = pvi_reserve_photons(ctx, want_cap); if (rc) return rc;
         ShootArgs a;
@@ -661,8 +672,9 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         int blocks = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (total + SH_THREADS - 1) / SH_THREADS);
         static const bool megakernel = getenv("PV_SHOOT_MEGAKERNEL") != nullptr;        // A/B knob: the persistent-thread kernel of round 1
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        bool replay = false;
         if (megakernel) kern<<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
-        else { rc = pvi_wavefront_run(ctx, a, surf, kind); if (rc) return rc; }
+        else { rc = pvi_wavefront_run(ctx, a, surf, kind, &replay); if (rc) return rc; }
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         unsigned long long h_nout = 0, h_stats[8];
@@ -670,8 +682,10 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * n_blocks * n_cls, cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (replay) { --attempt; continue; }               // (the pool is at most quadrupled log4(P) times)
         if (h_nout > ctx->cap_photons) { want_cap = h_nout + 65536; continue; }      // too small: grow and replay the (deterministic) wave
         float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        yield = std::max(yield, (double)(h_nout - ctx->n_photons) / ((double)n_local * SH_BLOCK));
         ctx->n_photons = h_nout;
         if (stats) {
             stats->nodes_visited += h_stats[0]; stats->tri_tests += h_stats[1]; stats->density_samples += h_stats[2];

@@ -44,7 +44,7 @@ enum { SF_WANT_CAUSTIC = 1, SF_WANT_INDIRECT = 2, SF_VOLUME_DONE = 4, SF_FINAL_G
 enum { PC_VOLUME = 0, PC_CAUSTIC = 1, PC_INDIRECT = 2, PC_DIRECT = 3, PC_RADIANCE = 4, PC_COUNT = 5 };
 
 // pv_wavefront.cu
-int pvi_wavefront_run(pv_ctx *ctx, const ShootArgs &a, bool surf, int kind);
+int pvi_wavefront_run(pv_ctx *ctx, const ShootArgs &a, bool surf, int kind, bool *replay);
 
 static __device__ __noinline__ uint4 path_philox_block(uint32_t c0, uint32_t c1, uint32_t j, uint32_t k0, uint32_t k1) {
     uint32_t out[4];

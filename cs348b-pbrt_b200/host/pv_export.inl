@@ -31,6 +31,11 @@ struct PvHostScene {
     std::vector<pv_sphere> spheres;
     pv_medium medium;
     bool has_medium;
+    // empty when the device description holds the scene's materials exactly; else what was approximated (the all-maps photon
+    // pass refuses such a scene).  has_unknown_specular: a material other than matte / glass was met -- it may have specular
+    // lobes, which matter even to the volume-only pass (a diffuse bounce ends a volume-only path whatever the BRDF is, Q6).
+    std::string inexact;
+    bool has_unknown_specular;
     pv_scene_desc desc;
 };
 
@@ -68,6 +73,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     hs.materials.clear();
     hs.prim_shape.assign(nPrims, PV_SHAPE_TRIANGLE);
     hs.spheres.clear();
+    hs.inexact.clear(); hs.has_unknown_specular = false;
     std::map<const Material *, uint32_t> matIndex;
     DifferentialGeometry dummy;
     bool warned_uv = false;
@@ -102,9 +108,14 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
                 pv_spec_out(mm->Kd->Evaluate(dummy).Clamp(), pm.kd);
                 // the device material is ONE reflectance: a spatially varying Kd texture is flattened to its value at (u, v) = (0, 0)
                 DifferentialGeometry probe; probe.u = 0.37f; probe.v = 0.61f; probe.p = Point(0.37f, 0.61f, 0.13f);
-                if (mm->Kd->Evaluate(probe).Clamp() != mm->Kd->Evaluate(dummy).Clamp())
+                if (mm->Kd->Evaluate(probe).Clamp() != mm->Kd->Evaluate(dummy).Clamp()) {
                     fprintf(stderr, "pv: warning: textured matte Kd on primitive %u is flattened to its value at uv = (0, 0) for photon shooting\n", i);
-                if (mm->sigma->Evaluate(dummy) != 0.f) fprintf(stderr, "pv: warning: matte sigma != 0 (Oren-Nayar) is treated as Lambertian\n");
+                    if (hs.inexact.empty()) hs.inexact = "a matte material has a textured Kd";
+                }
+                if (mm->sigma->Evaluate(dummy) != 0.f) {
+                    fprintf(stderr, "pv: warning: matte sigma != 0 (Oren-Nayar) is treated as Lambertian\n");
+                    if (hs.inexact.empty()) hs.inexact = "a matte material has sigma != 0 (Oren-Nayar)";
+                }
             } else if (const GlassMaterial *gm = dynamic_cast<const GlassMaterial *>(m)) {
                 pm.type = PV_MAT_GLASS;
                 pv_spec_out(gm->Kr->Evaluate(dummy).Clamp(), pm.kr);
@@ -114,6 +125,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             } else {
                 fprintf(stderr, "pv: warning: unsupported material on primitive %u, photons treat it as black matte\n", i);
                 pm.type = PV_MAT_MATTE;
+                hs.inexact = "a material is neither matte nor glass"; hs.has_unknown_specular = true;
             }
             matIndex[m] = (uint32_t)hs.materials.size(); hs.materials.push_back(pm);
         }

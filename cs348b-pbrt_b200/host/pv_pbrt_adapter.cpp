@@ -10,7 +10,8 @@
 //                                        untouched PhotonIntegrator reads (integrators/photonmap.cpp:159-164) are rebuilt as
 //                                        the reference's KdTree<> objects from the device's photon lists.  The rest of that TU
 //                                        is still the reference's, compiled with -DPreprocess=RefPreprocess: its CPU pass stays
-//                                        reachable for scenes off this path and under PV_SURFACE_MAPS=cpu.
+//                                        reachable for scenes off this path (and, in a -DPV_WITH_CPU_ROUTES debugging build only,
+//                                        under PV_SURFACE_MAPS=cpu).
 //   integrators/photonvolume.cpp         PhotonVolumeIntegrator::{RequestSamples, Transmittance, Li} and
 //                                        CreatePhotonVolumeIntegrator (same .pbrt parameters, :224-229).
 //   integrators/single.cpp, emission.cpp SingleScatteringIntegrator / EmissionIntegrator: Li over pv_volume_li.
@@ -297,9 +298,21 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
     pv_shoot_params prm; memset(&prm, 0, sizeof(prm));
     prm.stepsize = stepSize; prm.integrator_stepsize = vi->stepSize; prm.max_photon_depth = maxPhotonDepth;
     prm.seed = g_pv.seed; prm.rank = 0; prm.world = 1; prm.time = camera ? camera->shutterOpen : 0.f;
-    const char *surf_mode = getenv("PV_SURFACE_MAPS");                 // "cpu": keep the reference's CPU pass for the surface maps
     const bool surface_wanted = nCausticPhotonsWanted + nIndirectPhotonsWanted > 0;
+#ifdef PV_WITH_CPU_ROUTES          // debugging build only (host/Makefile CPU_ROUTES=1): PV_SURFACE_MAPS=cpu keeps the reference's CPU pass for the surface maps
+    const char *surf_mode = getenv("PV_SURFACE_MAPS");
     const bool surface_gpu = surface_wanted && !(surf_mode && !strcmp(surf_mode, "cpu"));
+#else
+    const bool surface_gpu = surface_wanted;
+#endif
+    // The surface maps are read by the unmodified PhotonIntegrator, so the device pass must trace exactly the materials the scene
+    // has.  A material the device description cannot hold (anything but Lambertian matte with one Kd and glass) would give wrong
+    // caustic / indirect / radiance maps without any sign of it in the image log: refuse instead.
+    if (surface_gpu && !g_pv.scene.inexact.empty())
+        Severe("pv: the photon maps of this scene cannot be traced on the device: %s (matte with a constant Kd and sigma = 0, and glass, are on this path)",
+               g_pv.scene.inexact.c_str());
+    if (!surface_gpu && g_pv.scene.has_unknown_specular)
+        Severe("pv: the volume photons of this scene cannot be traced on the device: %s", g_pv.scene.inexact.c_str());
     if (surface_gpu) {
         // ---- every map in ONE GPU pass (photonshooter.cpp:147-189, 232-357); the untouched PhotonIntegrator keeps reading
         // causticMap / indirectMap / radianceMap / nCausticPaths / nIndirectPaths (integrators/photonmap.cpp:159-164), so they
@@ -378,6 +391,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
     // PV_SURFACE_MAPS=cpu: the surface maps from the reference's own CPU pass instead.  That pass keeps scattering photons in
     // the medium only while its own volume map is not full (`scatter && !volumeDone`, photonshooter.cpp:96), so it is asked for
     // as many volume photons as surface photons, never for the full volume count; its volume photons are dropped.
+#ifdef PV_WITH_CPU_ROUTES
     if (surface_wanted && !surface_gpu) {
         uint32_t keep = nVolumePhotonsWanted;
         nVolumePhotonsWanted = std::min(keep, std::max(nCausticPhotonsWanted, nIndirectPhotonsWanted));
@@ -386,6 +400,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         nVolumePhotonsWanted = keep; nVolumePaths = keepPaths;
         delete volumeMap; volumeMap = NULL;
     }
+#endif
 }
 
 // ------------------------------------------------------------------ PhotonVolumeIntegrator (integrators/photonvolume.cpp)
@@ -694,7 +709,11 @@ void SamplerRenderer::Render(const Scene *scene) {
     PvFinalGather fg;
     PhotonVolumeIntegrator *pvi = dynamic_cast<PhotonVolumeIntegrator *>(volumeIntegrator);
     PhotonIntegrator *pmi = dynamic_cast<PhotonIntegrator *>(surfaceIntegrator);
-    const char *fg_mode = getenv("PV_FINAL_GATHER");                          // "cpu": keep the reference's per-ray final gather
+#ifdef PV_WITH_CPU_ROUTES
+    const char *fg_mode = getenv("PV_FINAL_GATHER");                          // "cpu": keep the reference's per-ray final gather (debugging build only)
+#else
+    const char *fg_mode = NULL;
+#endif
     if (g_pv.ready && pvi && pmi && pmi->finalGather && pmi->photonShooter && pmi->photonShooter->indirectMap && pmi->photonShooter->radianceMap &&
         !g_pv.rad_pos.empty() &&
         g_pv.n_indirect >= 50 && !(fg_mode && !strcmp(fg_mode, "cpu")) && !visualizeObjectIds) {

@@ -144,3 +144,20 @@ def test_final_gather_wavefront_is_reproducible_across_thread_counts(mock, tmp_p
     assert m and sum(c["n"] for c in fg) == int(m.group(1)) > 10000
     assert fg[0]["base"] == 0 and all(a["base"] + a["n"] == b["base"] for a, b in zip(fg, fg[1:]))
     assert len(calls(log, "gather")) == 1                                        # the volume term of the frame: still one call
+
+
+def test_material_off_the_path_is_refused_not_approximated(mock, tmp_path, pkg):
+    """A scene whose materials the device description cannot hold (here "plastic") must not get photon maps traced with a
+    stand-in material: the drop-in stops with an error naming the reason, before any photon is shot."""
+    from cs348b_pbrt_b200 import scenes
+    text = scenes.cornell_surf_pbrt(nphotons=500, caustic=200, indirect=500, finalgather=False, xres=32, yres=32, outfile="plastic.pfm")
+    assert 'Material "matte" "color Kd" [.6 .6 .6]' in text
+    text = text.replace('Material "matte" "color Kd" [.6 .6 .6]', 'Material "plastic" "color Kd" [.6 .6 .6] "color Ks" [.3 .3 .3]', 1)
+    scene = tmp_path / "plastic.pbrt"; scene.write_text(text)
+    log = tmp_path / "plastic.log"
+    env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+    out = subprocess.run([BIN, "--quiet", "--ncores", "2", str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0
+    assert "neither matte nor glass" in out.stderr
+    lines = log.read_text().splitlines() if log.exists() else []
+    assert not [l for l in lines if l.startswith("shoot")]

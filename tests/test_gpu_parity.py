@@ -615,3 +615,62 @@ def test_gather_step_parallel_equals_ray_parallel(golden, pv_factory, pkg, name)
     assert np.array_equal(L4.view(np.uint32), L2.view(np.uint32)) or np.array_equal(L4.view(np.uint32), L0.view(np.uint32))
     L3, T3 = pv.Li(rays[:1], ray_index_base=5, flags=A.GATHER_STEP_PARALLEL)          # one ray
     assert np.array_equal(L0[:1].view(np.uint32), L3.view(np.uint32))
+
+
+def test_malformed_bvh_is_refused(golden, pv_factory, pkg):
+    """pv_set_scene walks the flattened BVH once on the host: a child offset outside the node array, a leaf whose primitive range
+    leaves the primitive table, a split axis > 2 or a node reached twice is PV_EINVAL, not an out-of-bounds read in a kernel."""
+    import copy
+    g, scene = golden("cornell_homog")
+    pv = pv_factory()
+    pv.set_scene(scene)                                        # the real one is fine
+    nodes = np.frombuffer(np.ascontiguousarray(scene.nodes).tobytes(), dtype=np.uint8).reshape(scene.n_nodes, 32).copy()
+    interior = [i for i in range(scene.n_nodes) if nodes[i, 28] == 0]
+    leaves = [i for i in range(scene.n_nodes) if nodes[i, 28] != 0]
+    assert interior and leaves
+
+    def broken(edit):
+        s = copy.copy(scene)
+        n = nodes.copy(); edit(n)
+        s.nodes = n.reshape(-1)
+        with pytest.raises(pkg.PVError) as e:
+            pv.set_scene(s)
+        return str(e.value)
+
+    def set_offset(n, i, v): n[i, 24:28] = np.frombuffer(np.uint32(v).tobytes(), dtype=np.uint8)
+    assert "second child" in broken(lambda n: set_offset(n, interior[0], scene.n_nodes + 7))
+    assert "second child" in broken(lambda n: set_offset(n, interior[0], interior[0]))           # a cycle
+    assert "primitive range" in broken(lambda n: set_offset(n, leaves[0], scene.n_prims))
+    assert "axis" in broken(lambda n: n.__setitem__((interior[0], 29), 3))
+    pv.set_scene(scene)
+
+
+def test_shooter_deep_continuation_stacks(golden, pv_factory, monkeypatch):
+    """Paths that scatter again and again (Q1 inverted: a medium with sigma_a > sigma_s scatters MOST interactions, and every
+    scatter leaves a continuation frame behind, Q2): the frames above the fourth level live in pages from a pool, and a wave that
+    runs the pool dry is replayed with a larger one.  Started from a pool of ONE page the photon set is the same as with the
+    default pool, and it is the oracle's."""
+    import copy
+    g, scene = golden("cornell_grid32")
+    s = copy.copy(scene)
+    s.medium = type(scene.medium).from_buffer_copy(scene.medium)          # (a ctypes struct with a pointer: copied byte for byte)
+    for b in range(30):
+        s.medium.sigma_a[b] = 3.0; s.medium.sigma_s[b] = 2.0
+    istep = float(g["params"][2])
+    sets = []
+    for pages in (None, "1"):
+        if pages is None: monkeypatch.delenv("PV_WF_DEEP_PAGES", raising=False)
+        else: monkeypatch.setenv("PV_WF_DEEP_PAGES", pages)
+        pv = pv_factory(stepsize=istep, seed=5)
+        pv.set_scene(s)
+        st = pv.Preprocess(20000, stepsize=0.05, max_photon_depth=5, build=False)
+        assert st.stack_overflows == 0
+        sets.append(pv.get_photons())
+    for a, b in zip(*sets):
+        assert np.array_equal(a, b)
+    ref = O.shoot(s, 20000, 0.05, istep, seed=5, rng_mode=O.PHILOX, nthreads=8)
+    ids = sets[0][3]
+    common = np.intersect1d(ids, ref["ids"])
+    assert len(common) >= 0.995 * max(len(ids), len(ref["ids"]))
+    # deposit ordinals beyond 4 on one path = at least that many scatters deep
+    assert (ids & 0xffff).max() >= 5

@@ -9,7 +9,7 @@ scene = W.load_scene(cfg)
 pv = pkg.PhotonVolume(device=0, stepsize=cfg["stepsize"], nused=cfg["nused"], maxdist=cfg["maxdist"], seed=348)
 pv.set_scene(scene)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
-for it in range(3):
+for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     t0 = time.perf_counter()
     st = pv.Preprocess(n, stepsize=0.05, max_photon_depth=5, build=False)
     dt = time.perf_counter() - t0
