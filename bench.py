@@ -316,10 +316,11 @@ def main():
         ach = shoot_bytes / dsec / 1e9
         return {"photons": int(sec[2]), "paths": int(last * 4096), "paths_traced_incl_discarded": int(sec[1]), "device_s": dsec, "wall_s": wall,
                 "paths_per_s": sec[1] / dsec, "photons_per_s": sec[2] / dsec, "stack_overflows": int(sec[6]),
-                "roofline": {"bound": "hbm", "kernel": "shoot_kernel", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / (peak * world),
+                "roofline": {"bound": "hbm", "kernel": "wavefront shooter (wf_trace_kernel + wf_march_kernel + wf_event_kernel per generation)", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / (peak * world),
                              "peak_kind": peak_kind, "algorithmic_bytes": shoot_bytes, "traffic": None,
-                             "note": "per GPU; bytes = nodes*32 + triangle tests*36 + density samples*32 + deposits*144 (SURVEY 8d); the kernel is "
-                                     "latency/issue-bound, not HBM-bound (profiles/)"},
+                             "note": "per GPU; bytes = nodes*32 + triangle tests*36 + density samples*32 + deposits*144 (SURVEY 8d), counted by the kernels "
+                                     "for the work they do (transmittance marches whose result nothing reads are not done); the kernels are "
+                                     "instruction-issue-bound on the trilinear sampler, not HBM-bound (profiles/r02_*_summary.md)"},
                 "hbm_frac_algorithmic": ach / (peak * world),
                 "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": target}}
 
