@@ -24,6 +24,16 @@
 // coordinate, the box is widened by maxdist + the grid margin), and each candidate is tested with the reference's
 // arithmetic, so a step finds exactly the photons with d2 < r2.  A step with MORE than nused of them needs the k-nearest
 // selection (ties by photon index): it is handed to the warp-per-step kernel (gather_lii_kernel) through an overflow list.
+//
+// K-NEAREST MODE (template parameter KNN; nused <= CG_KMAX, maxdist larger than the cells -- the regime of the reference's shipped
+// scenes: "nused 50" inside a generous maxdist).  Same sort, staging and scan, but every lane searches its OWN trial radius -- 1.2 x
+// the radius that holds nused photons at the density of the 27 cells around the query, capped at maxdist and at the one-shell
+// radius of the grid -- and keeps the nused nearest candidates in a bounded max-heap of its own in shared memory
+// ((d2, sorted position), ties by original photon index like core/kdtree.h:150-183 + PhotonProcess).  A lane that ends with nused
+// photons has exactly the k nearest (everything closer than its k-th lies inside the trial sphere it scanned completely); a lane
+// with fewer whose trial radius was already maxdist has exactly the photons within maxdist; a lane with fewer and a smaller trial
+// radius goes to the warp-per-step kernel through the overflow list.  The heap's evolution depends only on the step (accepted
+// candidates arrive in ascending map order whatever else is staged), so its final layout is a canonical summation order.
 #include <algorithm>
 #include "pv_gather.cuh"
 
@@ -46,6 +56,7 @@
 #ifndef CG_XSPAN
 #define CG_XSPAN 2                       // a sub-batch spans at most this many coarse cells along x
 #endif
+#define CG_KMAX 64                       // largest nused of the k-nearest mode (heap: 2 x CG_KMAX x 32 words per warp)
 
 struct CgArgs {
     MapView m;
@@ -60,6 +71,7 @@ struct CgArgs {
     uint32_t *overflow;
     unsigned long long *counters;
     pv_gather_stats *stats;
+    float knn_rmax;                      // k-nearest mode: upper bound of a trial radius (the grid's one-shell radius, <= maxdist)
 };
 
 // per-warp shared memory
@@ -71,6 +83,8 @@ struct CgArgs {
 #define CG_OFF_Q (CG_OFF_PART + 32 * 8 * 16)                              // fcnt, perm, qcnt, qmx, qdens, qstep, run_rs, run_len
 #define CG_OFF_MBAR (CG_OFF_Q + 8 * 32 * 4)
 #define CG_WARP_BYTES (CG_OFF_MBAR + 16)
+#define CG_OFF_HEAP CG_WARP_BYTES                                          // k-nearest mode only: d2 [CG_KMAX][32], sorted position [CG_KMAX][32]
+#define CG_WARP_BYTES_KNN (CG_OFF_HEAP + 2 * CG_KMAX * 32 * 4)
 static_assert(CG_WARP_BYTES % 16 == 0 && CG_OFF_PART % 16 == 0 && CG_OFF_Q % 16 == 0, "16-byte alignment");
 static_assert(CG_CAP % 4 == 0 && CG_CAP >= CG_U && CG_STAGE % CG_U == 0, "list capacity / unroll");
 
@@ -97,10 +111,13 @@ __global__ void __launch_bounds__(256) cg_keys_kernel(GridParams g, const pv_ray
     keys[s] = key; vals[s] = (uint32_t)s;
 }
 
+template <bool KNN>
 __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgArgs a) {
     extern __shared__ __align__(128) unsigned char cg_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = cg_smem + (size_t)warp * CG_WARP_BYTES;
+    unsigned char *base = cg_smem + (size_t)warp * (KNN ? CG_WARP_BYTES_KNN : CG_WARP_BYTES);
+    float *hd2 = reinterpret_cast<float *>(base + CG_OFF_HEAP) + lane;                   // this lane's heap: entry e at [e * 32]
+    uint32_t *hpos = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP + CG_KMAX * 32 * 4) + lane;
     float4 *spos = reinterpret_cast<float4 *>(base + CG_OFF_POS);
     const float4 *swi = reinterpret_cast<const float4 *>(base + CG_OFF_WI);
     uint32_t *lidx = reinterpret_cast<uint32_t *>(base + CG_OFF_LIDX);
@@ -123,7 +140,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
     for (int c = 0; c < 4; ++c) { const uint32_t b = sub * 4 + c; sg[c] = b < PV_NSPEC ? med.sigma_s[b] : 0.f; }
     const float hg = med.g, pc = (1.f / (4.f * PV_PI_F)) * (1.f - hg * hg), gg1 = 1.f + hg * hg, g2 = 2.f * hg;
     const bool iso = hg == 0.f;
-    const float r2 = a.maxdist * a.maxdist, slack = a.maxdist + g.margin;
+    const float r2 = a.maxdist * a.maxdist, slack_fixed = a.maxdist + g.margin;
     const float4 *a4 = reinterpret_cast<const float4 *>(a.m.alpha32) + sub;
     const uint32_t xspan = (uint32_t)CG_XSPAN << g.xshift;
     unsigned long long st_cand = 0;
@@ -154,6 +171,27 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         if (valid) {
             cxf = pv_cell_coord(q.x, g.origin[0], g.inv_hx, g.dims[0]);
             row = pv_morton2((uint32_t)pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]), (uint32_t)pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]));
+        }
+        // ---- k-nearest mode: this query's trial radius from the photon count of the 27 (coarse) cells around it
+        float rq = a.maxdist, r2q = r2;
+        uint32_t hc = 0; float hroot = 0.f;                                        // heap size, d2 at its root once it is full
+        const uint32_t K = a.nused;
+        if (KNN && valid) {
+            const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]), cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
+            const int cxc = cxf >> g.xshift;
+            const int xlo = max((cxc - 1) << g.xshift, 0), xhi = min(((cxc + 2) << g.xshift) - 1, g.dims[0] - 1);
+            uint32_t n27 = 0;
+#pragma unroll 1
+            for (int j = 0; j < 9; ++j) {
+                const int y = cy + j % 3 - 1, z = cz + j / 3 - 1;
+                if (y < 0 || y >= g.dims[1] || z < 0 || z >= g.dims[2]) continue;
+                const uint32_t rowkey = pv_morton2((uint32_t)y, (uint32_t)z) << g.xbits;
+                n27 += __ldg(a.m.cell_start + (rowkey | (uint32_t)xhi) + 1) - __ldg(a.m.cell_start + (rowkey | (uint32_t)xlo));
+            }
+            // radius holding K photons at that density: h * cbrt(27 * 3 K / (4 pi n27)); 20 % on top for its fluctuation
+            const float rk = g.h * cbrtf(6.4458f * (float)K / (float)max(n27, 1u));
+            rq = fminf(fminf(1.2f * rk, a.knn_rmax), a.maxdist);
+            r2q = rq < a.maxdist ? rq * rq : r2;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) part[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,6 +285,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             const uint32_t gm = __ballot_sync(PV_FULL, in);
             remaining &= ~gm;
             const v3 aq = in ? q : V3(INFINITY, INFINITY, INFINITY);          // lanes outside the sub-batch accept nothing
+            const float slack = KNN ? cg_warp_max(in ? rq : 0.f) + g.margin : slack_fixed;
             const float lox = cg_warp_min(in ? q.x : INFINITY), hix = cg_warp_max(in ? q.x : -INFINITY);
             const float loy = cg_warp_min(in ? q.y : INFINITY), hiy = cg_warp_max(in ? q.y : -INFINITY);
             const float loz = cg_warp_min(in ? q.z : INFINITY), hiz = cg_warp_max(in ? q.z : -INFINITY);
@@ -298,6 +337,50 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 phase ^= 1u;
                 if (lane < CG_U) spos[n + lane] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // the unrolled scan may read past n
                 __syncwarp();
+                if (KNN) {
+                    // ---- scan, k-nearest mode: a candidate inside the trial sphere enters the lane's heap while it is not full,
+                    // afterwards only if it beats the root (ties at the root's distance by original photon index)
+                    for (uint32_t c0 = 0; c0 < n; c0 += CG_U) {
+                        float4 p[CG_U];
+#pragma unroll
+                        for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];
+#pragma unroll
+                        for (int u = 0; u < CG_U; ++u) {
+                            const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
+                            const float d2 = dx * dx + dy * dy + dz * dz;
+                            if (d2 < r2q && (hc < K || d2 <= hroot)) {
+                                const uint32_t pos = __float_as_uint(p[u].w);
+                                if (hc < K) {                                      // append, sift up
+                                    uint32_t i = hc++;
+                                    while (i > 0) {
+                                        const uint32_t pa = (i - 1) >> 1;
+                                        const float pd = hd2[pa * 32]; const uint32_t pp = hpos[pa * 32];
+                                        if (!(d2 > pd || (d2 == pd && __ldg(a.m.orig + pos) > __ldg(a.m.orig + pp)))) break;
+                                        hd2[i * 32] = pd; hpos[i * 32] = pp; i = pa;
+                                    }
+                                    hd2[i * 32] = d2; hpos[i * 32] = pos;
+                                    if (hc == K) hroot = hd2[0];
+                                } else if (d2 < hroot || __ldg(a.m.orig + pos) < __ldg(a.m.orig + hpos[0])) {      // replace the root, sift down
+                                    uint32_t i = 0;
+                                    for (;;) {
+                                        uint32_t c = 2 * i + 1;
+                                        if (c >= K) break;
+                                        float cd = hd2[c * 32]; uint32_t cp = hpos[c * 32];
+                                        if (c + 1 < K) {
+                                            const float ed = hd2[(c + 1) * 32]; const uint32_t ep = hpos[(c + 1) * 32];
+                                            if (ed > cd || (ed == cd && __ldg(a.m.orig + ep) > __ldg(a.m.orig + cp))) { c++; cd = ed; cp = ep; }
+                                        }
+                                        if (!(cd > d2 || (cd == d2 && __ldg(a.m.orig + cp) > __ldg(a.m.orig + pos)))) break;
+                                        hd2[i * 32] = cd; hpos[i * 32] = cp; i = c;
+                                    }
+                                    hd2[i * 32] = d2; hpos[i * 32] = pos;
+                                    hroot = hd2[0];
+                                }
+                            }
+                        }
+                    }
+                    continue;                                                      // next stage; the heap is summed at the end of the batch
+                }
                 // ---- scan (lane == query).  A round of CG_U candidates adds at most CG_U entries to a list, so
                 // (CG_CAP - longest list) / CG_U rounds need no check; when a list could overflow, the pending entries are
                 // resolved and all lists summed.
@@ -325,8 +408,34 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             }
         }
 
+        if (KNN) {
+            // a lane short of K photons whose trial sphere was smaller than maxdist has not seen everything: warp-per-step kernel
+            if (valid && !handed_over && hc < K && rq < a.maxdist) { handed_over = true; a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s; }
+            if (!valid || handed_over) hc = 0;
+            // ---- the heaps, CG_CAP entries at a time, through the same weigh + sum code as the lists
+            const uint32_t longest = __reduce_max_sync(PV_FULL, hc);
+            for (uint32_t e0 = 0; e0 < longest; e0 += CG_CAP) {
+                const uint32_t e1 = min(hc, e0 + CG_CAP);
+                for (uint32_t e = e0; e < e1; ++e) {
+                    const uint32_t pos = hpos[e * 32];
+                    float ph = pc;
+                    if (!iso) {
+                        const float4 wv = __ldg(a.m.wi4 + pos);
+                        const float costheta = -(wv.x * w.x + wv.y * w.y + wv.z * w.z);      // Dot(wi, -w)
+                        float rsq;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsq) : "f"(gg1 - g2 * costheta));
+                        ph = pc * rsq * rsq * rsq;
+                    }
+                    lidx[(e - e0) * 32 + lane] = pos; lw[(e - e0) * 32 + lane] = ph;
+                    pad_idx = pos; mx = fmaxf(mx, hd2[e * 32]);
+                    lp += 128u;
+                }
+                res = (lp - lidx_addr) >> 7;
+                sum();
+            }
+        }
         // ---- finish: LPhoton's tail (photonvolume.cpp:83-104) per query, one 128-byte row of L_ii per step
-        const bool over = valid && !handed_over && tot > a.nused;
+        const bool over = !KNN && valid && !handed_over && tot > a.nused;
         if (over) a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s;       // needs the k-nearest selection
         const bool done = valid && !handed_over && !over;
         st_found += __reduce_add_sync(PV_FULL, done ? tot : 0u);
@@ -388,13 +497,17 @@ int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
     CgArgs a;
     a.m = ga.m; a.sc = ga.sc; a.rays = ga.rays; a.steps = ga.steps; a.order = svals; a.total = total; a.maxdist = ga.maxdist; a.nused = ga.nused;
     a.lii = ga.lii; a.overflow = (uint32_t *)ctx->cg_overflow; a.counters = ctx->d_counters; a.stats = ga.stats;
-    const size_t smem = (size_t)CG_WARP_BYTES * CG_WARPS;
-    static_assert((size_t)CG_WARP_BYTES * CG_WARPS <= 227 * 1024, "cellgather: shared memory per CTA");
-    PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(cellgather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ga.maxdist > g.h && ga.nused > CG_KMAX) { ctx->err = "pv_gather: the cell-batched k-nearest mode holds at most 64 photons per lookup"; return PV_EINVAL; }
+    const bool knn = ga.maxdist > g.h;                     // the search radius does not fit the cells: k-nearest mode (gather_slice checked nused)
+    a.knn_rmax = g.one_shell_r;
+    void (*kern)(CgArgs) = knn ? cellgather_kernel<true> : cellgather_kernel<false>;
+    const size_t smem = (size_t)(knn ? CG_WARP_BYTES_KNN : CG_WARP_BYTES) * CG_WARPS;
+    static_assert((size_t)CG_WARP_BYTES_KNN * CG_WARPS <= 227 * 1024, "cellgather: shared memory per CTA");
+    PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cellgather_kernel, CG_THREADS, smem));
+    PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CG_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    cellgather_kernel<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
+    kern<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
     ctx->launches += 1;
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[1], ctx->stream));

@@ -208,8 +208,7 @@ int pvi_broadcast_photons(pv_ctx **ctxs, int n, int src, float *collective_ms) {
     for (int i = 0; i < n; ++i) {
         pv_ctx *c = ctxs[i];
         cudaSetDevice(c->device);
-        c->built = false;
-        if (i != src) { c->n_photons = 0; int rc = pvi_reserve_photons(c, cnt); if (rc) { s->err = c->err; return rc; } }
+        if (i != src) { c->built = false; c->n_photons = 0; int rc = pvi_reserve_photons(c, cnt); if (rc) { s->err = c->err; return rc; } }     // (the source keeps its map)
     }
     if (cnt == 0) { for (int i = 0; i < n; ++i) ctxs[i]->n_photons = 0; return PV_OK; }
     cudaSetDevice(s->device);

@@ -1426,7 +1426,9 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     // PV_GATHER_CELL_BATCHED / PV_GATHER_STEP_PARALLEL / PV_GATHER_RAY_PARALLEL in params->flags force one.
     const bool lookups = !(flags & PV_GATHER_NO_INDIRECT) && total > 0;
     static const bool legacy_default = getenv("PV_GATHER_LEGACY") != nullptr;               // A/B knob: the round-1 schedules
-    bool cell = lookups && !legacy_default && a.m.n > 0 && prm->maxdist <= ctx->grid.h;
+    // (k-nearest regime, maxdist above the cell size: the cell-batched kernel's k-nearest mode while nused fits its per-lane heap)
+    static const bool knn_legacy = getenv("PV_KNN_LEGACY") != nullptr;                       // A/B knob: warp-per-ray / warp-per-step k-nearest search
+    bool cell = lookups && !legacy_default && a.m.n > 0 && (prm->maxdist <= ctx->grid.h || (!knn_legacy && prm->nused <= 64 && prm->nused >= 1));
     bool step_parallel = lookups && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
     if (flags & PV_GATHER_STEP_PARALLEL) { step_parallel = lookups; cell = false; }
     if (flags & PV_GATHER_RAY_PARALLEL) { step_parallel = false; cell = false; }

@@ -19,6 +19,7 @@
 #include "pv_ctx.h"
 
 #include <cstdlib>
+#include <chrono>
 #include "pv_shoot.cuh"
 #ifndef SH_TAU_MED
 #define SH_TAU_MED const MV
@@ -575,6 +576,20 @@ SH_UNROLL_BINS
     }
 }
 
+// PV_TIMING=1: wall time of the host-side phases of shooting on stderr (tuning aid)
+namespace {
+struct PhaseTimer {
+    const char *what; bool on; std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(const char *w) : what(w), on(getenv("PV_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *phase) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pv timing] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}
+
 // ---------------------------------------------------------------- host: MT19937 only to reproduce task 0's Halton tables
 static void halton_tables_task0(uint32_t perm[41]) {
     // RNG rng(31 * taskNum) with taskNum == 0, then PermutedHalton(6, rng): core/rng.cpp:43-107, montecarlo.cpp:380-397
@@ -641,8 +656,10 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
             if (want_cap > room && room > ctx->n_photons + 65536) want_cap = room;
         }
     }
+    PhaseTimer tm("shoot_wave");
     for (int attempt = 0; attempt < 3; ++attempt) {
         rc = pvi_reserve_photons(ctx, want_cap); if (rc) return rc;
+        tm.lap("reserve");
         ShootArgs a;
         a.sc = ctx->dscene; a.b_start = b_start; a.n_local_blocks = n_local; a.world = prm->world; a.first_block = first_block;
         a.stepsize = prm->stepsize; a.istep4 = 4.f * prm->integrator_stepsize; a.max_depth = prm->max_photon_depth;
@@ -682,6 +699,7 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, sizeof(uint32_t) * n_blocks * n_cls, cudaMemcpyDeviceToHost, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        tm.lap("kernels + readback");
         if (replay) { --attempt; continue; }               // (the pool is at most quadrupled log4(P) times)
         if (h_nout > ctx->cap_photons) { want_cap = h_nout + 65536; continue; }      // too small: grow and replay the (deterministic) wave
         float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -749,6 +767,7 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split, bool bound
     int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
     uint64_t *keys = (uint64_t *)ctx->scratch, *keys_tmp = keys + n;
     uint32_t *vals = (uint32_t *)(keys_tmp + n), *vals_tmp = vals + n;
+    PhaseTimer tm("shoot_finish");
     id_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ids, n, keys, vals);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     // highest path index bounds the key width
@@ -760,6 +779,7 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split, bool bound
     rc = pvi_sort_pairs_u64(ctx, keys, vals, keys_tmp, vals_tmp, n, 64, &skeys, &svals); if (rc) return rc;
     (void)bits;
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the probes below are blocking copies on another stream
+    tm.lap("sort by id");
     // count survivors: ids <= (last_block * 4096) << 16 | 0xffff
     auto upper_bound = [&](uint64_t limit, uint64_t *out) -> int {  // first position with key > limit (few D2H probes)
         uint64_t probe = 0, lo = 0, hi = n;
@@ -789,20 +809,24 @@ static int shoot_finish(pv_ctx *ctx, uint64_t last_block, bool split, bool bound
             }
         }
     }
+    tm.lap("bounds");
     float *np, *nw, *na; uint64_t *ni;
     uint64_t cap = std::max<uint64_t>(keep, 1024);
     PV_CUDA_CHECK(ctx, cudaMalloc((void **)&np, cap * 3 * sizeof(float)));
     PV_CUDA_CHECK(ctx, cudaMalloc((void **)&nw, cap * 3 * sizeof(float)));
     PV_CUDA_CHECK(ctx, cudaMalloc((void **)&na, cap * 32 * sizeof(float)));
     PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ni, cap * sizeof(uint64_t)));
+    tm.lap("malloc");
     if (keep) {
         permute_photons_kernel<<<(unsigned)((keep * 8 + 255) / 256), 256, 0, ctx->stream>>>(svals, keep, ctx->d_pos, ctx->d_wi, ctx->d_alpha, ctx->d_ids,
                                                                                          np, nw, na, ni);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
     }
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    tm.lap("permute");
     cudaFree(ctx->d_pos); cudaFree(ctx->d_wi); cudaFree(ctx->d_alpha); cudaFree(ctx->d_ids);
     ctx->d_pos = np; ctx->d_wi = nw; ctx->d_alpha = na; ctx->d_ids = ni; ctx->cap_photons = cap; ctx->n_photons = keep;
+    tm.lap("free");
     return PV_OK;
 }
 int pvi_shoot_finish(pv_ctx *ctx, uint64_t last_block) { return shoot_finish(ctx, last_block, false); }

@@ -89,14 +89,41 @@ def tile_order(xres, yres, tile=8):
     return np.argsort(key.reshape(-1), kind="stable")
 
 
+def deal_tiles(rays, order, world, tile=8, group=8, medium_box=((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)), xres=None):
+    """Which rank gathers which rays (image tiles of camera rays are sharded).  The unit dealt is a block of
+    group x group tiles (64 x 64 pixels): big enough that a rank's march steps stay spatially dense -- the cell-batched gather
+    shares one staged block of photon cells among 32 neighbouring steps, and single 8 x 8 tiles dealt round-robin thin the steps
+    of a rank out (measured at 2 ranks: 340 instead of 291 distance tests per lookup) -- and dealt by COST, not round-robin: the
+    cost of a block is the total length of its rays inside the medium's bounding box (the number of march steps, i.e. lookups, up
+    to the constant step size), blocks go to the least-loaded rank in order of decreasing cost (LPT).  Same answer on every rank.
+    Returns rank_of_ray, aligned with `order`."""
+    o = rays["o"][order].astype(np.float64); d = rays["d"][order].astype(np.float64)
+    lo, hi = np.asarray(medium_box[0]), np.asarray(medium_box[1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0 = (lo - o) / d; t1 = (hi - o) / d
+    tn = np.nanmax(np.minimum(t0, t1), axis=1); tf = np.nanmin(np.maximum(t0, t1), axis=1)
+    chord = np.clip(tf - np.maximum(tn, 0.0), 0.0, None)
+    pix = order
+    gx = (pix % xres) // (tile * group); gy = (pix // xres) // (tile * group)
+    ngx = (xres + tile * group - 1) // (tile * group)
+    block = gy * ngx + gx
+    nblocks = int(block.max()) + 1
+    cost = np.bincount(block, weights=chord + 0.1, minlength=nblocks)        # + a fixed part per ray (march set-up, the 272 B of L and T): ~3 march steps' worth
+    load = np.zeros(world)
+    owner = np.zeros(nblocks, np.int64)
+    for b in np.argsort(-cost, kind="stable"):
+        r = int(np.argmin(load)); owner[b] = r; load[r] += cost[b] + 1e-9
+    return owner[block]
+
+
 def frame_rays(cfg, rank=0, world=1, tile=8):
-    """Camera rays of the frame in tile order; rank r takes tiles r, r+world, ... (interleaved).
+    """Camera rays of the frame in tile order; with several ranks, blocks of 8 x 8 tiles are dealt by cost (deal_tiles).
     Returns (rays, global ray indices)."""
     rays = scenes.camera_rays(cfg["xres"], cfg["yres"])
     order = tile_order(cfg["xres"], cfg["yres"], tile)
     if world > 1:
-        tile_id = np.arange(len(order)) // (tile * tile)
-        order = order[tile_id % world == rank]
+        owner = deal_tiles(rays, order, world, tile=tile, xres=cfg["xres"])
+        order = order[owner == rank]
     return np.ascontiguousarray(rays[order]), order
 
 

@@ -1,10 +1,22 @@
 """GPU (-m gpu): the drop-in end to end.  baseline/_ref/pbrt_b200 is the REFERENCE renderer (parser, camera, sampler, surface
-integrator, film, PFM writer all unchanged) linked with host/pv_pbrt_adapter.cpp + csrc/libpv.so in place of its photon-volume
-translation units.  It renders a .pbrt file; the image is compared with the one the unmodified reference rendered
-(tests/golden/cornell_e2e_ref.npy, made by `oracle/_ref/pbrt_ref --ncores 1 tests/scenes/cornell_e2e.pbrt`).
+integrator, film, image writers all unchanged) linked with host/pv_pbrt_adapter.cpp + csrc/libpv.so in place of its photon-volume
+translation units.  It renders a .pbrt file; the image is compared with the one the unmodified reference rendered from the same
+file (tests/golden/<name>_ref.npy, made by `oracle/_ref/pbrt_ref --ncores 1`, tests/golden/make_golden.py).
 
-Photon paths use different random streams on the two sides (MT19937 vs per-path Philox), so this is a statistical check:
-whole-image tolerance = 3 % on the mean luminance, 12 % mean relative error per pixel over lit pixels (100k photons, k=50)."""
+THE WHOLE-IMAGE TOLERANCE (one rule for every scene).  Photon paths and the stochastic parts of Li use different random streams on
+the two sides (MT19937 per task vs keyed Philox), so a render can only agree with the reference's as well as the reference agrees
+with ITSELF on other streams.  That spread is measured, per scene, from three more reference renders with other task counts
+(`--ncores 2, 3, 5`: the reference seeds its RNGs and scrambles its samples per task; tests/golden/make_ref2.py writes their
+distances from the primary render to tests/golden/ref_spread.json and keeps the --ncores 3 image as <name>_ref2.npy).  With
+    e_mean(a, b)  = |mean luminance(a) - mean luminance(b)| / mean luminance(b)
+    e_block(a, b) = mean over lit 6x6 blocks of |block mean(a) - block mean(b)| / block mean(b)      (lit: >= 5 % of the mean block)
+and spread_x = the LARGEST e_x(reference run, primary reference render) over those runs, a drop-in render passes iff
+    e_mean(drop-in, ref)  <= 2 * spread_mean  + 0.5 %      and      e_block(drop-in, ref) <= 2 * spread_block + 1 %.
+(Two runs are not enough to know the spread: volint_single_e2e has the point light's 1/d^2 peak on the ceiling inside ONE pixel, and
+the reference's mean luminance comes out as 1.3800, 1.3713, 1.3794, 1.3710 for --ncores 1, 2, 3, 5.)  The measured spreads are in
+ref_spread.json (mean / block): config1_volumescene 0.1 % / 1.2 %, config4_prism 4.5 % / 3.3 %, cornell_e2e 2.7 % / 3.2 %,
+cornell_surf_e2e 2.1 % / 4.9 %, sphere_e2e 2.9 % / 6.3 %, volint_emission_e2e 1.2 % / 0.6 %, volint_single_e2e 0.6 % / 0.7 %,
+volumescene_png (config 1 verbatim) 0.1 % / 1.4 %."""
 import os
 import subprocess
 import numpy as np
@@ -13,6 +25,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "baseline", "_ref", "pbrt_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TOL_FACTOR, TOL_FLOOR_MEAN, TOL_FLOOR_BLOCK = 2.0, 0.005, 0.01
+needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
 
 
 def read_pfm(path):
@@ -33,73 +48,121 @@ def block_mean(a, b):
     return a[:h, :w].reshape(h // b, b, w // b, b).mean(axis=(1, 3))
 
 
-@pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
-@pytest.mark.parametrize("name,tol_mean,tol_mre", [("config1_volumescene", 0.03, 0.10), ("config4_prism", 0.05, 0.15),
-                                                   ("cornell_surf_e2e", 0.04, 0.10), ("sphere_e2e", 0.05, 0.15)])
-def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name, tol_mean, tol_mre):
-    """BASELINE configs[0] (rainbow-volume scene with the shipped settings, 150x150) and configs[3] (glass-prism dispersion
-    scene, reduced to 20k photons / 96x96 / 8 spp) rendered by the drop-in and compared with the unmodified reference's
-    render of the same file (tests/golden/<name>_ref.npy, float16).  cornell_surf_e2e: every photon map on (glass wedge
-    caustics, indirect + direct photons, radiance photons, final gathering with 16 samples, 4 spp, 72x72).  ALL photon maps come
-    from the GPU pass (pv_shoot_maps / pv_radiance_photons); the unmodified PhotonIntegrator reads them through its own
-    KdTree<> objects.  sphere_e2e: the parameters of projectScene/scene.pbrt (glass SPHERE in a homogeneous medium, spot + point
-    light, caustic map + final gathering) at 100k volume photons / 96x96 / 4 spp.  Random streams differ (MT19937 vs keyed Philox), so the tolerance is statistical: mean luminance within
-    tol_mean, mean relative error of 6x6-pixel block means over lit blocks within tol_mre (two reference runs with different
-    task counts differ by 1 % / 4 % on cornell_surf_e2e, 1 % / 7 % on sphere_e2e)."""
+def image_errors(img, ref):
+    """(e_mean, e_block) of the module docstring"""
+    li, lr = luminance(img), luminance(ref)
+    bi, br = block_mean(li, 6), block_mean(lr, 6)
+    lit = br > 0.05 * br.mean()
+    return abs(li.mean() - lr.mean()) / lr.mean(), (np.abs(bi - br)[lit] / br[lit]).mean()
+
+
+def assert_within_the_whole_image_tolerance(img, ref, name):
+    import json
+    spread = json.load(open(os.path.join(GOLDEN, "ref_spread.json")))[name]
+    assert img.shape == ref.shape
+    assert np.isfinite(img).all()
+    e_mean, e_block = image_errors(img, ref)
+    assert e_mean <= TOL_FACTOR * spread["e_mean"] + TOL_FLOOR_MEAN, ("mean luminance", e_mean, "reference spread", spread["e_mean"])
+    assert e_block <= TOL_FACTOR * spread["e_block"] + TOL_FLOOR_BLOCK, ("block MRE", e_block, "reference spread", spread["e_block"])
+
+
+def golden_ref(name):
+    return np.load(os.path.join(GOLDEN, name + "_ref.npy")).astype(np.float32)
+
+
+def read_png_rgb8(path):
+    """8-bit RGB, non-interlaced PNG (what stb_image_write produces for the reference's film) -> uint8 [h, w, 3]; zlib + the five
+    scanline filters, no imaging library needed on the GPU box"""
+    import struct, zlib
+    buf = open(path, "rb").read()
+    assert buf[:8] == b"\x89PNG\r\n\x1a\n"
+    off, idat, w = 8, b"", 0
+    while off < len(buf):
+        n, kind = struct.unpack(">I4s", buf[off:off + 8])
+        body = buf[off + 8:off + 8 + n]
+        if kind == b"IHDR":
+            w, h, depth, ctype, _, _, interlace = struct.unpack(">IIBBBBB", body)
+            assert depth == 8 and ctype == 2 and interlace == 0
+        elif kind == b"IDAT":
+            idat += body
+        off += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)
+    out = np.zeros((h, 3 * w), np.int32)
+    prev = np.zeros(3 * w, np.int32)
+    for y in range(h):
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        if f == 0: cur = line
+        elif f == 2: cur = (line + prev) & 255
+        else:
+            cur = np.zeros(3 * w, np.int32)
+            for x in range(3 * w):
+                a = cur[x - 3] if x >= 3 else 0
+                b = prev[x]; c = prev[x - 3] if x >= 3 else 0
+                if f == 1: p = a
+                elif f == 3: p = (a + b) >> 1
+                else:
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    p = a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+                cur[x] = (line[x] + p) & 255
+        out[y] = cur; prev = cur
+    return out.reshape(h, w, 3).astype(np.uint8)
+
+
+@needs_bin
+@pytest.mark.parametrize("name", ["config1_volumescene", "config4_prism", "cornell_surf_e2e", "sphere_e2e"])
+def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name):
+    """BASELINE configs[0] (rainbow-volume scene with the shipped settings, 150x150 -- the verbatim file is the next test) and
+    configs[3] (glass-prism dispersion scene, reduced to 20k photons / 96x96 / 8 spp) rendered by the drop-in and compared with the
+    unmodified reference's render of the same file.  cornell_surf_e2e: every photon map on (glass wedge caustics, indirect + direct
+    photons, radiance photons, final gathering with 16 samples, 4 spp, 72x72).  ALL photon maps come from the GPU pass
+    (pv_shoot_maps / pv_radiance_photons); the unmodified PhotonIntegrator reads them through its own KdTree<> objects.
+    sphere_e2e: the parameters of projectScene/scene.pbrt (glass SPHERE in a homogeneous medium, spot + point light, caustic map +
+    final gathering) at 100k volume photons / 96x96 / 4 spp.  Tolerance: the module's one rule."""
     scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
     assert "Shooting photons" not in out.stderr                               # ... and the reference's CPU shooting pass did not
-    img = read_pfm(os.path.join(tmp_path, name + ".pfm"))
-    ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_ref.npy")).astype(np.float32)
-    assert img.shape == ref.shape
-    li, lr = luminance(img), luminance(ref)
-    assert np.isfinite(li).all()
-    assert abs(li.mean() - lr.mean()) / lr.mean() < tol_mean, (li.mean(), lr.mean())
-    bi, br = block_mean(li, 6), block_mean(lr, 6)
-    lit = br > 0.05 * br.mean()
-    mre = (np.abs(bi - br)[lit] / br[lit]).mean()
-    assert mre < tol_mre, mre
+    assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
 
 
-@pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
+@needs_bin
+def test_dropin_renders_config1_verbatim(tmp_path):
+    """BASELINE configs[0] VERBATIM: projectScene/volumescene_png.pbrt exactly as the reference project ships it (a byte-for-byte
+    copy of that data file is tests/scenes/volumescene_png.pbrt): photonmap surface integrator with final gathering, photonvolume
+    integrator, rainbow medium, distant light, 300 x 300, written as PNG by the reference's own film (gamma 2.2, 8 bit).  Compared,
+    after undoing the gamma, with the PNG the unmodified reference wrote from the same file (tests/golden/volumescene_png_ref.png;
+    _ref2.png = its second run on other streams)."""
+    scene = os.path.join(ROOT, "tests", "scenes", "volumescene_png.pbrt")
+    out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
+    lin = lambda path: (read_png_rgb8(path).astype(np.float32) / 255.0) ** 2.2
+    img = lin(os.path.join(tmp_path, "volume.png"))
+    assert img.shape == (300, 300, 3)
+    assert_within_the_whole_image_tolerance(img, lin(os.path.join(GOLDEN, "volumescene_png_ref.png")), "volumescene_png")
+
+
+@needs_bin
 def test_dropin_renders_the_config2_scene_like_the_reference(tmp_path):
+    """BASELINE configs[1] shape (Cornell box + homogeneous medium, k = 50) at 100 k photons / 64 x 64 through the drop-in."""
     scene = os.path.join(ROOT, "tests", "scenes", "cornell_e2e.pbrt")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] shot" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
-    img = read_pfm(os.path.join(tmp_path, "cornell_e2e.pfm"))
-    ref = np.load(os.path.join(ROOT, "tests", "golden", "cornell_e2e_ref.npy"))
-    assert img.shape == ref.shape
-    lum = lambda a: 0.2126 * a[..., 0] + 0.7152 * a[..., 1] + 0.0722 * a[..., 2]
-    li, lr = lum(img), lum(ref)
-    assert abs(li.mean() - lr.mean()) / lr.mean() < 0.03
-    lit = lr > 0.05 * lr.mean()
-    mre = (np.abs(li - lr)[lit] / lr[lit]).mean()
-    assert mre < 0.12, mre
+    assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, "cornell_e2e.pfm")), golden_ref("cornell_e2e"), "cornell_e2e")
 
 
-@pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
+@needs_bin
 @pytest.mark.parametrize("name,label", [("volint_single_e2e", "single-scattering volume term"), ("volint_emission_e2e", "emission volume term")])
 def test_dropin_renders_single_and_emission_scenes_like_the_reference(tmp_path, name, label):
     """VolumeIntegrator "single" (emitting homogeneous medium, point + spot light) and "emission" (emitting 32^3
     density grid) through the drop-in: all-maps Cornell geometry under the direct-lighting surface integrator, 72x72, 4 spp; the
-    glass wedge's specular bounces reach the volume integrator one ray at a time and go to the device in batches.  Compared with
-    the unmodified reference's render of the same file (tests/golden/<name>_ref.npy).  Only the light choice, the tau offsets and
-    the Russian roulette are random here: two reference runs with different task counts differ by 0.04 % / 0.5 % (single) and
-    1.2 % / 0.6 % (emission) in mean luminance / block MRE; tolerance 3 % / 3 %."""
+    glass wedge's specular bounces reach the volume integrator one ray at a time and go to the device in batches.  Only the light
+    choice, the tau offsets and the Russian roulette are random here, so the reference's own spread -- and with it the tolerance -- is
+    small (0.04 % / 0.5 % and 1.2 % / 0.6 %)."""
     scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert label in out.stderr and "batched device calls" in out.stderr       # pv_volume_li ran for camera AND secondary rays
-    img = read_pfm(os.path.join(tmp_path, name + ".pfm"))
-    ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_ref.npy")).astype(np.float32)
-    assert img.shape == ref.shape
-    li, lr = luminance(img), luminance(ref)
-    assert np.isfinite(li).all()
-    assert abs(li.mean() - lr.mean()) / lr.mean() < 0.03, (li.mean(), lr.mean())
-    bi, br = block_mean(li, 6), block_mean(lr, 6)
-    lit = br > 0.05 * br.mean()
-    mre = (np.abs(bi - br)[lit] / br[lit]).mean()
-    assert mre < 0.03, mre
+    assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
