@@ -307,10 +307,11 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
     double hk = std::cbrt(3.0 * (double)std::max<uint32_t>(nused, 1) / (4.0 * M_PI * rho));
     // a hair above maxdist, so that the 3x3x3 block provably holds every photon within maxdist (see one_shell_r)
     const double margin_est = 1.01e-4 * (double)maxdist + 4e-6 * (maxabs + maxext);
-    // k-nearest regime (the cell expected to hold nused photons is smaller than maxdist): measured on config 2 (k = 50,
-    // 1 M photons), cells of 0.5-0.8 hk halve the candidates scanned but cost more in extra shells and selections
-    // (48.7-57 ms vs 48.3 ms per frame), so the cell stays at hk; the knob remains for other k / density regimes.
-    double knn_cell = 1.0;
+    // k-nearest regime (the cell expected to hold nused photons is smaller than maxdist).  The cell-batched gather's k-nearest mode
+    // (nused <= 64, pv_cellgather.cu) searches a trial sphere of ~1.1 hk inside the 5 x 5 rows around the query's cell and wants
+    // cells of 0.75 hk (measured on config 2, k = 50, 1 M photons: 17.7 ms per frame; 1.0 hk 19.3 ms, 1.5 hk 21.4 ms); the
+    // warp-per-lookup search that larger nused falls back to is indifferent between 0.5 and 1.0 hk (48-57 ms) and keeps hk.
+    double knn_cell = nused <= 64 ? 0.75 : 1.0;
     if (const char *e = getenv("PV_KNN_CELL")) knn_cell = std::max(0.25, std::min(2.0, atof(e)));       // tuning knob
     double h = std::min((double)maxdist + 3.0 * margin_est, hk * knn_cell);
     const int max_dim = 256;                                  // key bits <= 24 -> cell table <= 64 MiB

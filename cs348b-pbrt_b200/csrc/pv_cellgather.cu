@@ -26,15 +26,19 @@
 // selection (ties by photon index): it is handed to the warp-per-step kernel (gather_lii_kernel) through an overflow list.
 //
 // K-NEAREST MODE (template parameter KNN; nused <= CG_KMAX, maxdist larger than the cells -- the regime of the reference's shipped
-// scenes: "nused 50" inside a generous maxdist).  Same sort, staging and scan, but every lane searches its OWN trial radius -- 1.2 x
-// the radius that holds nused photons at the density of the 27 cells around the query, capped at maxdist and at the one-shell
-// radius of the grid -- and keeps the nused nearest candidates in a bounded max-heap of its own in shared memory
-// ((d2, sorted position), ties by original photon index like core/kdtree.h:150-183 + PhotonProcess).  A lane that ends with nused
-// photons has exactly the k nearest (everything closer than its k-th lies inside the trial sphere it scanned completely); a lane
-// with fewer whose trial radius was already maxdist has exactly the photons within maxdist; a lane with fewer and a smaller trial
-// radius goes to the warp-per-step kernel through the overflow list.  The heap's evolution depends only on the step (accepted
-// candidates arrive in ascending map order whatever else is staged), so its final layout is a canonical summation order.
+// scenes: "nused 50" inside a generous maxdist).  Same sort, staging and scan, but every lane searches its OWN trial radius -- a
+// little more than the radius that holds nused photons at the density of the 27 cells around the query, capped at maxdist and at
+// what the 5 x 5 rows around a cell cover -- and appends what it accepts to an unsorted list of (d2, map position) of its own in
+// shared memory.  When a list could overflow, and at the end of the batch, every lane cuts its list down to its nused smallest
+// entries: the threshold is found by bisection on the bit pattern of d2 (a counting loop per pass, the same code for all lanes;
+// ties at the threshold by original photon index like core/kdtree.h:150-183 + PhotonProcess), the survivors keep their order and
+// later candidates are tested against the threshold.  A lane that ends with nused photons has exactly the k nearest (everything
+// closer than its k-th lies inside the trial sphere it scanned completely); a lane with fewer whose trial radius was already
+// maxdist has exactly the photons within maxdist; a lane with fewer and a smaller trial radius goes to the warp-per-step kernel
+// through the overflow list.  Accepted candidates arrive in ascending map order whatever else is staged, and the cut keeps that
+// order: the sums run over a step's photons in map order, like the fixed-radius mode's.
 #include <algorithm>
+#include <cstdlib>
 #include "pv_gather.cuh"
 
 #ifndef CG_WARPS
@@ -56,7 +60,11 @@
 #ifndef CG_XSPAN
 #define CG_XSPAN 2                       // a sub-batch spans at most this many coarse cells along x
 #endif
-#define CG_KMAX 64                       // largest nused of the k-nearest mode (heap: 2 x CG_KMAX x 32 words per warp)
+#define CG_KMAX 64                       // largest nused of the k-nearest mode
+#ifndef CG_KLIST
+#define CG_KLIST 96
+#endif
+//                      // capacity of a lane's candidate list in that mode (>= CG_KMAX + CG_U)
 
 struct CgArgs {
     MapView m;
@@ -71,7 +79,8 @@ struct CgArgs {
     uint32_t *overflow;
     unsigned long long *counters;
     pv_gather_stats *stats;
-    float knn_rmax;                      // k-nearest mode: upper bound of a trial radius (the grid's one-shell radius, <= maxdist)
+    float knn_rmax;                      // k-nearest mode: upper bound of a trial radius
+    float knn_trial;                     // ... and the factor on the radius expected to hold nused photons
 };
 
 // per-warp shared memory
@@ -83,8 +92,8 @@ struct CgArgs {
 #define CG_OFF_Q (CG_OFF_PART + 32 * 8 * 16)                              // fcnt, perm, qcnt, qmx, qdens, qstep, run_rs, run_len
 #define CG_OFF_MBAR (CG_OFF_Q + 8 * 32 * 4)
 #define CG_WARP_BYTES (CG_OFF_MBAR + 16)
-#define CG_OFF_HEAP CG_WARP_BYTES                                          // k-nearest mode only: d2 [CG_KMAX][32], sorted position [CG_KMAX][32]
-#define CG_WARP_BYTES_KNN (CG_OFF_HEAP + 2 * CG_KMAX * 32 * 4)
+#define CG_OFF_HEAP CG_WARP_BYTES                                          // k-nearest mode only: d2 bits [CG_KLIST][32], map position [CG_KLIST][32]
+#define CG_WARP_BYTES_KNN (CG_OFF_HEAP + 2 * CG_KLIST * 32 * 4)
 static_assert(CG_WARP_BYTES % 16 == 0 && CG_OFF_PART % 16 == 0 && CG_OFF_Q % 16 == 0, "16-byte alignment");
 static_assert(CG_CAP % 4 == 0 && CG_CAP >= CG_U && CG_STAGE % CG_U == 0, "list capacity / unroll");
 
@@ -116,8 +125,8 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
     extern __shared__ __align__(128) unsigned char cg_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *base = cg_smem + (size_t)warp * (KNN ? CG_WARP_BYTES_KNN : CG_WARP_BYTES);
-    float *hd2 = reinterpret_cast<float *>(base + CG_OFF_HEAP) + lane;                   // this lane's heap: entry e at [e * 32]
-    uint32_t *hpos = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP + CG_KMAX * 32 * 4) + lane;
+    uint32_t *hd2 = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP) + lane;             // this lane's candidate list: entry e at [e * 32]
+    uint32_t *hpos = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP + CG_KLIST * 32 * 4) + lane;
     float4 *spos = reinterpret_cast<float4 *>(base + CG_OFF_POS);
     const float4 *swi = reinterpret_cast<const float4 *>(base + CG_OFF_WI);
     uint32_t *lidx = reinterpret_cast<uint32_t *>(base + CG_OFF_LIDX);
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         }
         // ---- k-nearest mode: this query's trial radius from the photon count of the 27 (coarse) cells around it
         float rq = a.maxdist, r2q = r2;
-        uint32_t hc = 0; float hroot = 0.f;                                        // heap size, d2 at its root once it is full
+        uint32_t hc = 0; float hbound = INFINITY;                                  // list length; d2 of the K-th nearest so far once a cut has been made
         const uint32_t K = a.nused;
         if (KNN && valid) {
             const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]), cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
@@ -190,7 +199,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             }
             // radius holding K photons at that density: h * cbrt(27 * 3 K / (4 pi n27)); 20 % on top for its fluctuation
             const float rk = g.h * cbrtf(6.4458f * (float)K / (float)max(n27, 1u));
-            rq = fminf(fminf(1.2f * rk, a.knn_rmax), a.maxdist);
+            rq = fminf(fminf(a.knn_trial * rk, a.knn_rmax), a.maxdist);
             r2q = rq < a.maxdist ? rq * rq : r2;
         }
 #pragma unroll
@@ -276,6 +285,48 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             tot += cnt; lp = lidx_addr; res = 0;
         };
 
+        // ---- k-nearest mode: every lane cuts its list down to its K smallest (d2, original index) entries, order kept
+        auto knn_cut = [&]() {
+            const uint32_t nmax = __reduce_max_sync(PV_FULL, hc);
+            if (nmax <= K) return;
+            const bool need = hc > K;
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            for (uint32_t e = 0; e < nmax; ++e) if (need && e < hc) { const uint32_t key = hd2[e * 32]; lo = min(lo, key); hi = max(hi, key); }
+            // smallest threshold with at least K keys <= it (positive floats order like their bit patterns); a pass that counts
+            // exactly K ends the search at once
+            bool open = need && lo < hi;
+            while (__any_sync(PV_FULL, open)) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                uint32_t c = 0;
+                for (uint32_t e = 0; e < nmax; ++e) if (open && e < hc) c += hd2[e * 32] <= mid ? 1u : 0u;
+                if (open) {
+                    if (c == K) { lo = hi = mid; }
+                    else if (c < K) lo = mid + 1u; else hi = mid;
+                    open = lo < hi;
+                }
+            }
+            const uint32_t thr = lo;
+            if (need) {
+                uint32_t c_le = 0;
+                for (uint32_t e = 0; e < hc; ++e) c_le += hd2[e * 32] <= thr ? 1u : 0u;
+                // more than K at or below the threshold: the surplus are ties AT the threshold; those with the largest original index go
+                for (; c_le > K; --c_le) {
+                    uint32_t worst = 0, worst_orig = 0; bool any = false;
+                    for (uint32_t e = 0; e < hc; ++e)
+                        if (hd2[e * 32] == thr) { const uint32_t og = __ldg(a.m.orig + hpos[e * 32]); if (!any || og > worst_orig) { any = true; worst = e; worst_orig = og; } }
+                    hd2[worst * 32] = 0xffffffffu;
+                }
+                uint32_t j = 0;
+                for (uint32_t e = 0; e < hc; ++e) {
+                    const uint32_t key = hd2[e * 32];
+                    if (key <= thr) { const uint32_t pp = hpos[e * 32]; hd2[j * 32] = key; hpos[j * 32] = pp; ++j; }
+                }
+                hc = j;
+                hbound = __uint_as_float(thr);
+            }
+            __syncwarp();
+        };
+
         while (remaining) {
             // ---- sub-batch: the queries of the leader's cell row within CG_XSPAN coarse cells of it (normally all 32)
             const int leader = __ffs(remaining) - 1;
@@ -338,9 +389,10 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 if (lane < CG_U) spos[n + lane] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // the unrolled scan may read past n
                 __syncwarp();
                 if (KNN) {
-                    // ---- scan, k-nearest mode: a candidate inside the trial sphere enters the lane's heap while it is not full,
-                    // afterwards only if it beats the root (ties at the root's distance by original photon index)
+                    // ---- scan, k-nearest mode: a candidate inside the trial sphere and not beyond the K-th nearest known so far is
+                    // appended to the lane's list; a list that could overflow in the next round is cut first
                     for (uint32_t c0 = 0; c0 < n; c0 += CG_U) {
+                        if (__reduce_max_sync(PV_FULL, hc) + CG_U > CG_KLIST) knn_cut();
                         float4 p[CG_U];
 #pragma unroll
                         for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];
@@ -348,38 +400,10 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                         for (int u = 0; u < CG_U; ++u) {
                             const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
                             const float d2 = dx * dx + dy * dy + dz * dz;
-                            if (d2 < r2q && (hc < K || d2 <= hroot)) {
-                                const uint32_t pos = __float_as_uint(p[u].w);
-                                if (hc < K) {                                      // append, sift up
-                                    uint32_t i = hc++;
-                                    while (i > 0) {
-                                        const uint32_t pa = (i - 1) >> 1;
-                                        const float pd = hd2[pa * 32]; const uint32_t pp = hpos[pa * 32];
-                                        if (!(d2 > pd || (d2 == pd && __ldg(a.m.orig + pos) > __ldg(a.m.orig + pp)))) break;
-                                        hd2[i * 32] = pd; hpos[i * 32] = pp; i = pa;
-                                    }
-                                    hd2[i * 32] = d2; hpos[i * 32] = pos;
-                                    if (hc == K) hroot = hd2[0];
-                                } else if (d2 < hroot || __ldg(a.m.orig + pos) < __ldg(a.m.orig + hpos[0])) {      // replace the root, sift down
-                                    uint32_t i = 0;
-                                    for (;;) {
-                                        uint32_t c = 2 * i + 1;
-                                        if (c >= K) break;
-                                        float cd = hd2[c * 32]; uint32_t cp = hpos[c * 32];
-                                        if (c + 1 < K) {
-                                            const float ed = hd2[(c + 1) * 32]; const uint32_t ep = hpos[(c + 1) * 32];
-                                            if (ed > cd || (ed == cd && __ldg(a.m.orig + ep) > __ldg(a.m.orig + cp))) { c++; cd = ed; cp = ep; }
-                                        }
-                                        if (!(cd > d2 || (cd == d2 && __ldg(a.m.orig + cp) > __ldg(a.m.orig + pos)))) break;
-                                        hd2[i * 32] = cd; hpos[i * 32] = cp; i = c;
-                                    }
-                                    hd2[i * 32] = d2; hpos[i * 32] = pos;
-                                    hroot = hd2[0];
-                                }
-                            }
+                            if (d2 < r2q && d2 <= hbound) { hd2[hc * 32] = __float_as_uint(d2); hpos[hc * 32] = __float_as_uint(p[u].w); ++hc; }
                         }
                     }
-                    continue;                                                      // next stage; the heap is summed at the end of the batch
+                    continue;                                                      // next stage; the lists are cut and summed at the end of the batch
                 }
                 // ---- scan (lane == query).  A round of CG_U candidates adds at most CG_U entries to a list, so
                 // (CG_CAP - longest list) / CG_U rounds need no check; when a list could overflow, the pending entries are
@@ -409,6 +433,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         }
 
         if (KNN) {
+            knn_cut();
             // a lane short of K photons whose trial sphere was smaller than maxdist has not seen everything: warp-per-step kernel
             if (valid && !handed_over && hc < K && rq < a.maxdist) { handed_over = true; a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s; }
             if (!valid || handed_over) hc = 0;
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                         ph = pc * rsq * rsq * rsq;
                     }
                     lidx[(e - e0) * 32 + lane] = pos; lw[(e - e0) * 32 + lane] = ph;
-                    pad_idx = pos; mx = fmaxf(mx, hd2[e * 32]);
+                    pad_idx = pos; mx = fmaxf(mx, __uint_as_float(hd2[e * 32]));
                     lp += 128u;
                 }
                 res = (lp - lidx_addr) >> 7;
@@ -499,7 +524,9 @@ int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
     a.lii = ga.lii; a.overflow = (uint32_t *)ctx->cg_overflow; a.counters = ctx->d_counters; a.stats = ga.stats;
     if (ga.maxdist > g.h && ga.nused > CG_KMAX) { ctx->err = "pv_gather: the cell-batched k-nearest mode holds at most 64 photons per lookup"; return PV_EINVAL; }
     const bool knn = ga.maxdist > g.h;                     // the search radius does not fit the cells: k-nearest mode (gather_slice checked nused)
-    a.knn_rmax = g.one_shell_r;
+    a.knn_rmax = 2.f * g.h - 2.f * g.margin;        // what the 5 x 5 rows (and 5 coarse cells along x) around a query's cell are sure to cover
+    a.knn_trial = 1.1f;                              // measured on config 2: 1.05 -> 20.0 ms (3.5 ms of them in the fallback), 1.1 -> 17.7, 1.2 -> 23.1
+    if (const char *e = getenv("PV_KNN_TRIAL")) a.knn_trial = std::max(1.0f, std::min(3.0f, (float)atof(e)));       // tuning knob
     void (*kern)(CgArgs) = knn ? cellgather_kernel<true> : cellgather_kernel<false>;
     const size_t smem = (size_t)(knn ? CG_WARP_BYTES_KNN : CG_WARP_BYTES) * CG_WARPS;
     static_assert((size_t)CG_WARP_BYTES_KNN * CG_WARPS <= 227 * 1024, "cellgather: shared memory per CTA");
