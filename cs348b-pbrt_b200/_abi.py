@@ -7,7 +7,7 @@ import ctypes as C
 
 NSPEC = 30
 PV_OK, PV_EINVAL, PV_ECUDA, PV_ENOMEM, PV_ESTATE, PV_ENOPHOTONS = 0, -1, -2, -3, -4, -5
-LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT = 0, 1, 2
+LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT, LIGHT_AREA = 0, 1, 2, 3
 MEDIUM_NONE, MEDIUM_HOMOGENEOUS, MEDIUM_GRID, MEDIUM_RAINBOW, MEDIUM_EXPONENTIAL = 0, 1, 2, 3, 4
 MAT_MATTE, MAT_GLASS = 0, 1
 GATHER_NO_DIRECT, GATHER_NO_INDIRECT, GATHER_RAY_PARALLEL, GATHER_STEP_PARALLEL, GATHER_CELL_BATCHED = 1, 2, 4, 8, 16
@@ -56,7 +56,8 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(Material)), ("n_materials", C.c_uint32),
                 ("lights", C.POINTER(Light)), ("n_lights", C.c_uint32),
                 ("medium", C.POINTER(Medium)), ("world_bound", C.c_float * 6), ("cie_y", Spec),
-                ("prim_shape", C.POINTER(C.c_uint32)), ("spheres", C.POINTER(Sphere)), ("n_spheres", C.c_uint32)]
+                ("prim_shape", C.POINTER(C.c_uint32)), ("spheres", C.POINTER(Sphere)), ("n_spheres", C.c_uint32),
+                ("light_tris", C.POINTER(C.c_float)), ("n_light_tris", C.c_uint32)]
 
 
 class GatherParams(C.Structure):

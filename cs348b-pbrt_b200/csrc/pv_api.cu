@@ -1,5 +1,6 @@
 // pv_api.cu -- the extern "C" layer of include/pv.h: argument checks, host<->device staging,
 // context lifetime.  No arithmetic of the path lives here.
+#include <cmath>
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +65,7 @@ void pv_destroy(pv_ctx *ctx) {
     pvi_comm_destroy(ctx);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags, ctx->d_ltris, ctx->d_ltri_area, ctx->d_ltri_cdf};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
     if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
@@ -100,6 +101,14 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     if (s->n_spheres && (!s->spheres || !s->prim_shape)) { ctx->err = "pv_set_scene: spheres without a prim_shape table"; return PV_EINVAL; }
     for (uint32_t i = 0; s->n_spheres && i < s->n_prims; ++i)
         if (s->prim_shape[i] != PV_SHAPE_TRIANGLE && s->prim_shape[i] >= s->n_spheres) { ctx->err = "pv_set_scene: sphere index out of range"; return PV_EINVAL; }
+    for (uint32_t i = 0; i < s->n_lights; ++i) {
+        const pv_light &l = s->lights[i];
+        if (l.type != PV_LIGHT_AREA) continue;
+        if (!s->light_tris || (uint64_t)l.area.first_tri + l.area.n_tris > s->n_light_tris || l.area.n_tris == 0) {
+            ctx->err = "pv_set_scene: area light without triangles in light_tris"; return PV_EINVAL;
+        }
+        if (s->medium && s->medium->type == PV_MEDIUM_RAINBOW) { ctx->err = "pv_set_scene: area lights in a rainbow medium are not on this path"; return PV_EINVAL; }
+    }
     // the flattened BVH (accelerators/bvh.cpp:154-164): every kernel walks it with a fixed 64-entry todo stack (bvh_traverse,
     // like the reference's todo[64]) and indexes by child / primitive offsets, so a malformed or too deep tree is refused here
     if (s->n_nodes) {
@@ -150,8 +159,41 @@ int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
     }
     if ((rc = upload(ctx, &ctx->d_lights, s->lights, sizeof(pv_light) * (size_t)s->n_lights))) return rc;
     if ((rc = upload(ctx, &ctx->d_spheres, s->spheres, sizeof(pv_sphere) * (size_t)s->n_spheres))) return rc;
+    // area lights: triangle areas (shapes/trianglemesh.cpp:284-290), ShapeSet's area distribution (core/light.cpp:129-136,
+    // Distribution1D core/montecarlo.h:55-83) and the sums ShapeSet::Pdf uses, in the reference's float operations
+    std::vector<float> lt_area(s->n_light_tris, 0.f), lt_cdf;
+    float la_sum[PV_MAX_LIGHTS] = {0}, la_pd[PV_MAX_LIGHTS] = {0}; uint32_t la_off[PV_MAX_LIGHTS] = {0};
+    for (uint32_t i = 0; i < s->n_lights; ++i) {
+        const pv_light &l = s->lights[i];
+        if (l.type != PV_LIGHT_AREA) continue;
+        const uint32_t n = l.area.n_tris;
+        float sumArea = 0.f, pd = 0.f;
+        for (uint32_t k = 0; k < n; ++k) {
+            const float *tv = s->light_tris + 9 * (size_t)(l.area.first_tri + k);
+            const double ax = (double)(tv[3] - tv[0]), ay = (double)(tv[4] - tv[1]), az = (double)(tv[5] - tv[2]);
+            const double bx = (double)(tv[6] - tv[0]), by = (double)(tv[7] - tv[1]), bz = (double)(tv[8] - tv[2]);
+            const float cx = (float)(ay * bz - az * by), cy = (float)(az * bx - ax * bz), cz = (float)(ax * by - ay * bx);      // Cross() in double, geometry.h:477-484
+            const float ar = 0.5f * sqrtf(cx * cx + cy * cy + cz * cz);
+            lt_area[l.area.first_tri + k] = ar; sumArea += ar;
+        }
+        la_off[i] = (uint32_t)lt_cdf.size();
+        lt_cdf.resize(lt_cdf.size() + n + 1);
+        float *cdf = lt_cdf.data() + la_off[i];
+        cdf[0] = 0.f;
+        for (uint32_t k = 1; k < n + 1; ++k) cdf[k] = cdf[k - 1] + lt_area[l.area.first_tri + k - 1] / n;
+        const float funcInt = cdf[n];
+        if (funcInt == 0.f) for (uint32_t k = 1; k < n + 1; ++k) cdf[k] = (float)k / (float)n;
+        else for (uint32_t k = 1; k < n + 1; ++k) cdf[k] /= funcInt;
+        for (uint32_t k = 0; k < n; ++k) pd += lt_area[l.area.first_tri + k] * (1.f / lt_area[l.area.first_tri + k]);
+        la_sum[i] = sumArea; la_pd[i] = pd;
+    }
+    if ((rc = upload(ctx, &ctx->d_ltris, s->light_tris, sizeof(float) * 9 * (size_t)s->n_light_tris))) return rc;
+    if ((rc = upload(ctx, &ctx->d_ltri_area, lt_area.data(), sizeof(float) * lt_area.size()))) return rc;
+    if ((rc = upload(ctx, &ctx->d_ltri_cdf, lt_cdf.data(), sizeof(float) * lt_cdf.size()))) return rc;
     DevScene &h = ctx->hscene;
     memset(&h, 0, sizeof(h));
+    h.ltris = (const float *)ctx->d_ltris; h.ltri_area = (const float *)ctx->d_ltri_area; h.ltri_cdf = (const float *)ctx->d_ltri_cdf;
+    memcpy(h.larea_sum, la_sum, sizeof(la_sum)); memcpy(h.larea_pd, la_pd, sizeof(la_pd)); memcpy(h.lcdf_off, la_off, sizeof(la_off));
     h.nodes = (const pv_bvh_node *)ctx->d_nodes; h.n_nodes = s->n_nodes;
     h.tri = (const float *)ctx->d_tri; h.prim_mat = (const uint32_t *)ctx->d_prim_mat; h.n_prims = s->n_prims;
     h.mats = (const pv_material *)ctx->d_mats; h.n_mats = s->n_materials;

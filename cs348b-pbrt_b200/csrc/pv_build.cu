@@ -241,12 +241,15 @@ __global__ void gather_records_kernel(const uint32_t *__restrict__ order, uint64
         }
     }
 }
+// cell_start[c] = number of photons whose key is < c, for c in [0, table_size]: ONE pass over the sorted keys -- thread i looks
+// at keys i - 1 and i and, where they differ, writes i to every cell in (key[i-1], key[i]] (cells in between are empty and start
+// where the next occupied one does); the last thread closes the table.
 __global__ void cell_start_kernel(const uint32_t *__restrict__ sorted_keys, uint64_t n, uint32_t table_size, uint32_t *__restrict__ cell_start) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > table_size) return;
-    uint64_t lo = 0, hi = n;                    // lower_bound(sorted_keys, c)
-    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < c) lo = mid + 1; else hi = mid; }
-    cell_start[c] = (uint32_t)lo;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const uint32_t hi = i < n ? sorted_keys[i] : table_size;                 // cells up to and including hi start at i
+    const long long lo = i == 0 ? -1ll : (long long)sorted_keys[i - 1];      // ... beyond the previous photon's cell
+    for (long long c = lo + 1; c <= (long long)hi; ++c) cell_start[c] = (uint32_t)i;
 }
 
 static int ceil_log2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
@@ -385,7 +388,7 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
         PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->cell_start, ((size_t)g.table_size + 1) * sizeof(uint32_t)));
         ctx->table_cap = g.table_size + 1;
     }
-    cell_start_kernel<<<(g.table_size + 1 + 255) / 256, 256, 0, ctx->stream>>>(skeys, n, g.table_size, ctx->cell_start);
+    cell_start_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(skeys, n, g.table_size, ctx->cell_start);
     ctx->launches += 2;                                     // + gather_records_kernel above
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

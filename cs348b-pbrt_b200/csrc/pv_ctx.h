@@ -42,7 +42,7 @@ struct pv_ctx {
     DevScene hscene{};
     DevScene *dscene = nullptr;
     void *d_nodes = nullptr, *d_tri = nullptr, *d_prim_mat = nullptr, *d_mats = nullptr, *d_lights = nullptr, *d_density = nullptr;
-    void *d_spheres = nullptr, *d_mat_flags = nullptr;
+    void *d_spheres = nullptr, *d_mat_flags = nullptr, *d_ltris = nullptr, *d_ltri_area = nullptr, *d_ltri_cdf = nullptr;
     bool has_scene = false;
 
     // photons in deposit order, SoA planes: pos[3n], wi[3n], alpha[32n] (30 bins + 2 pad = one 128-byte line,

@@ -46,6 +46,12 @@ struct DevScene {
     // so the leaf loop pays one compare on a value it loads anyway and triangle-only scenes load nothing extra.
     const pv_sphere *spheres; uint32_t n_spheres;
     const uint8_t *mat_flags;          // per material: PV_MATF_* (which of Kd / Kr / Kt has a non-zero bin), made once by pv_set_scene
+    // area lights (PV_LIGHT_AREA): the triangles of every ShapeSet, their areas, and per light the normalised area CDF
+    // (n_tris + 1 entries at ltri_cdf + lcdf_off[light]), the total area and ShapeSet::Pdf(Point)'s numerator -- all computed once
+    // by pv_set_scene with the reference's own float operations (core/light.cpp:114-137, core/montecarlo.h:55-83)
+    const float *ltris, *ltri_area, *ltri_cdf;
+    float larea_sum[PV_MAX_LIGHTS], larea_pd[PV_MAX_LIGHTS];
+    uint32_t lcdf_off[PV_MAX_LIGHTS];
 };
 #define PV_MATF_KD 1
 #define PV_MATF_KR 2
@@ -419,6 +425,68 @@ __device__ __forceinline__ float light_L_bin(const pv_light &l, const LightQuery
     if (!q.point_like) return I;
     if (l.type == PV_LIGHT_SPOT) return __fdiv_rn(I * q.falloff, q.inv_mode_d2);
     return __fdiv_rn(I, q.inv_mode_d2);
+}
+
+// ---------------------------------------------------------------- DiffuseAreaLight over triangles
+// Triangle::Intersect's DifferentialGeometry normal for default uvs (shapes/trianglemesh.cpp:160-205, core/diffgeom.cpp:40-55)
+__device__ __forceinline__ v3 tri_dg_nn(const float *tv, uint32_t flags) {
+    const v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
+    const v3 dp1 = p1 - p3, dp2 = p2 - p3;
+    const v3 dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                       // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1, det = 1
+    const v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;                       // (-du2*dp1 + du1*dp2) * invdet, du2 = 0, du1 = -1
+    v3 nn = vnorm(vcross(dpdu, dpdv));
+    if (((flags & PV_AREA_REVERSE_ORIENTATION) != 0) ^ ((flags & PV_AREA_SWAPS_HANDEDNESS) != 0)) nn = nn * -1.f;
+    return nn;
+}
+// the triangle ShapeSet::Sample picks for the component sample u (SampleDiscrete: upper_bound on the CDF - 1), its point for
+// (u0, u1) (Triangle::Sample shapes/trianglemesh.cpp:444-456) and the geometric normal there
+__device__ __forceinline__ v3 area_sample_point(const DevScene &sc, const pv_light &l, int li, float uComp, float u0, float u1, v3 *ns) {
+    const int n = (int)l.area.n_tris;
+    const float *cdf = sc.ltri_cdf + sc.lcdf_off[li];
+    int lo = 0, hi = n + 1;
+    while (lo < hi) { const int mid = (lo + hi) / 2; if (uComp < cdf[mid]) hi = mid; else lo = mid + 1; }
+    const int sn = max(lo - 1, 0);
+    const float *tv = sc.ltris + 9 * (size_t)(l.area.first_tri + sn);
+    const v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
+    const float su1 = __fsqrt_rn(u0), b1 = 1.f - su1, b2 = u1 * su1;
+    *ns = vnorm(vcross(p2 - p1, p3 - p1));
+    if (l.area.flags & PV_AREA_REVERSE_ORIENTATION) *ns = *ns * -1.f;
+    return (p1 * b1 + p2 * b2) + p3 * (1.f - b1 - b2);
+}
+// DiffuseAreaLight::Sample_L(p, pEpsilon, ls, time, &wi, &pdf, &vis) (lights/diffuse.cpp:69-86) with ShapeSet::Sample(p, ls, Ns)
+// (core/light.cpp:139-158: ONE ray towards the sampled point against every shape, hit and normal of the LAST shape it hits) and
+// ShapeSet::Pdf(p, wi) (:167-172 over Shape::Pdf core/shape.cpp:86-99).  Returns whether the light faces p (L = Lemit, else 0).
+static __device__ __noinline__ bool area_sample_L(const DevScene &sc, int li, v3 p, float uComp, float u0, float u1, v3 *wi, float *pdf,
+                                           v3 *vis_d, float *vis_maxt) {
+    const pv_light &l = sc.lights[li];
+    const uint32_t n = l.area.n_tris;
+    *pdf = 0.f; *wi = V3(0.f, 0.f, 1.f); *vis_d = *wi; *vis_maxt = 0.f;
+    if (!n) return false;
+    const float *tris = sc.ltris + 9 * (size_t)l.area.first_tri, *area = sc.ltri_area + l.area.first_tri;
+    v3 ns;
+    const v3 pt = area_sample_point(sc, l, li, uComp, u0, u1, &ns);
+    const v3 rdir = pt - p;
+    float thit = 1.f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float t;
+        if (tri_hit(tris + 9 * (size_t)i, p, rdir, 1e-3f, INFINITY, &t)) { thit = t; ns = tri_dg_nn(tris + 9 * (size_t)i, l.area.flags); }
+    }
+    const v3 ps = ray_at(p, rdir, thit);
+    *wi = vnorm(ps - p);
+    float pdfsum = 0.f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float t;
+        if (!tri_hit(tris + 9 * (size_t)i, p, *wi, 1e-3f, INFINITY, &t)) continue;
+        const v3 nn = tri_dg_nn(tris + 9 * (size_t)i, l.area.flags);
+        float pd = __fdiv_rn(dist2(p, ray_at(p, *wi, t)), fabsf(vdot(nn, -(*wi))) * area[i]);
+        if (isinf(pd)) pd = 0.f;
+        pdfsum += area[i] * pd;
+    }
+    *pdf = __fdiv_rn(pdfsum, sc.larea_sum[li]);
+    // visibility->SetSegment(p, pEpsilon = 0, ps, 1e-3f, time) (core/light.h:85-93)
+    const float dist = vlen(p - ps);
+    *vis_d = vdiv(ps - p, dist); *vis_maxt = dist * (1.f - 1e-3f);
+    return vdot(ns, -(*wi)) > 0.f;                                       // DiffuseAreaLight::L (lights/diffuse.h:51-53)
 }
 
 // core/spectrum.h:433-439 for a per-thread 30-float array

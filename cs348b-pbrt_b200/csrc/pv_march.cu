@@ -118,15 +118,35 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
             if (c_dens != 0.f && do_direct) {
                 const float u_l = pv_van_der_corput(pv_permute((uint32_t)si, (uint32_t)nSamples, rw[1]), rw[0]);
                 c_ln = min((int)floorf(u_l * nLights), nLights - 1);
-                LightQuery lq;
-                light_query(sc.lights[c_ln], p, &lq);
-                if (lq.falloff != 0.f) {
-                    nshadow++;
-                    float mt = lq.vis_maxt;
-                    if (bvh_traverse<true, SPH>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
-                        c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize, pv_u32_to_float(sw[2]), &ns);
-                        const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
-                        c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
+                if (sc.lights[c_ln].type == PV_LIGHT_AREA) {
+                    // DiffuseAreaLight: the light sample of the step is (lightComp, lightPos[0], lightPos[1]) handed to LightSample in
+                    // the integrators' argument order -- LightSample(up0, up1, ucomp) called as ls(comp, pos0, pos1), i.e. the
+                    // component number is the THIRD number (integrators/single.cpp:116, photonvolume.cpp:183); three words of a
+                    // Philox block of its own here
+                    uint32_t aw[4];
+                    pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)si, PV_RNG_AREA, a.k0, a.k1, aw);
+                    v3 wi, vis_d; float pdf, vis_maxt;
+                    const bool facing = area_sample_L(sc, c_ln, p, pv_u32_to_float(aw[2]), pv_u32_to_float(aw[0]), pv_u32_to_float(aw[1]), &wi, &pdf,
+                                                      &vis_d, &vis_maxt);
+                    if (facing && pdf > 0.f) {
+                        nshadow++;
+                        float mt = vis_maxt;
+                        if (bvh_traverse<true, SPH>(sc, p, vis_d, 0.f, &mt, nullptr) < 0) {
+                            c_sh = med_tau_scalar(med, p, vis_d, 0.f, vis_maxt, 4.f * a.stepsize, pv_u32_to_float(sw[2]), &ns);
+                            c_dfac = __fdiv_rn(med_phase(med, p, -rd, -wi) * (float)nLights, pdf);      // p * Ld * nLights / pdf, Ld = Lemit * Tr
+                        }
+                    }
+                } else {
+                    LightQuery lq;
+                    light_query(sc.lights[c_ln], p, &lq);
+                    if (lq.falloff != 0.f) {
+                        nshadow++;
+                        float mt = lq.vis_maxt;
+                        if (bvh_traverse<true, SPH>(sc, lq.vis_o, lq.vis_d, lq.vis_mint, &mt, nullptr) < 0) {
+                            c_sh = med_tau_scalar(med, lq.vis_o, lq.vis_d, lq.vis_mint, lq.vis_maxt, 4.f * a.stepsize, pv_u32_to_float(sw[2]), &ns);
+                            const float geom = lq.point_like ? __fdiv_rn(lq.falloff, lq.inv_mode_d2) : 1.f;
+                            c_dfac = rainbow ? geom : (geom * med_phase(med, p, -rd, -lq.wi)) * (float)nLights;
+                        }
                     }
                 }
             }

@@ -1,18 +1,10 @@
-// pv_shoot.cu -- photon shooting (K1-K3): PhotonShootingTask::Run / followPhoton
-// (core/photonshooter.cpp:47-357) as one persistent-thread sm_100a kernel.  Two instantiations: the volume-photon
-// branch alone (surface maps off: diffuse bounces end the path, nothing but volume photons is stored) and the
-// pass with the surface maps on (caustic / indirect / direct deposits, radiance-photon sites, :147-189).
-//
-// Each thread is a small state machine {NEWPATH, TRACE, SURFACE}; all lanes of a warp meet at the head of the
-// same loop every iteration (path regeneration happens in-loop), so divergence is confined to one iteration.
-// The reference's recursion -- including its quirks Q1 (inverted scatter test), Q2 (after a scattered sub-path
-// returns, control falls through into the surface code with the scattered ray and the ORIGINAL hit), Q3
-// (transmittance re-marched from the segment start at every step, fresh offset), Q5, Q6 -- is unrolled onto an
-// explicit per-thread stack of continuation frames that preserves the depth-first draw order, so a path consumes
-// its Philox stream in exactly the order the CPU oracle does (tests compare the photon sets one to one).
-// Light paths are dealt in the reference's blocks of 4096; a deposit of global block b is divided by
-// nshot = 4096*b (Q4), independent of the number of ranks.  Deposits are appended with warp-aggregated atomics
-// (one atomicAdd per coalesced group) into SoA planes; the 30-bin alpha goes out as one 128-byte line (8 x float4).
+// pv_shoot.cu -- photon shooting (K1-K3), host side: PhotonShooter::Preprocess / PhotonShootingTask::Run's outer loop
+// (core/photonshooter.cpp:232-357, 457-503).  Light paths are dealt in the reference's blocks of 4096; a deposit of global block b
+// is divided by nshot = 4096*b (Q4), independent of the number of ranks.  A WAVE of blocks is traced by the wavefront kernels of
+// pv_wavefront.cu (followPhoton itself, :47-229); the host sizes the photon buffer, replays a wave whose buffer or continuation-stack
+// pool turned out too small (waves are deterministic), replays the reference's per-block bookkeeping of the done flags over the
+// per-block deposit counts, and finally orders the photons by id = (class, path, deposit ordinal) so that the set depends only on
+// (scene, seed, target).
 #include <algorithm>
 #include <type_traits>
 #include <vector>
@@ -21,561 +13,6 @@
 #include <cstdlib>
 #include <chrono>
 #include "pv_shoot.cuh"
-#ifndef SH_TAU_MED
-#define SH_TAU_MED const MV
-#endif
-// One copy of DensityRegion::tau for the shooter's two call sites (free-flight march, surface transmittance)
-template <class MV>
-__device__ __noinline__ float shoot_tau(SH_TAU_MED m, float ox, float oy, float oz, float dx, float dy, float dz, float mint, float maxt,
-                                        float stepSize, float u, uint32_t *nsamples) {
-    return med_tau_scalar(m, V3(ox, oy, oz), V3(dx, dy, dz), mint, maxt, stepSize, u, nsamples);
-}
-// EXPERIMENT (SH_COOP_TAU=1, off by default; see DESIGN.md "Shooter experiments"): warp-cooperative DensityRegion::tau
-// (core/volume.cpp:296-310) for a density-grid medium.  The lanes of a full warp pool the samples of all their pending tau
-// evaluations: each owner lane enumerates its sample parameters t_j exactly as the scalar loop does (SH_SLOTS at a time) into
-// its row of `vals`; the rows are flattened with a prefix sum and the lanes take the samples round-robin (owner by binary
-// search over the prefix table, the owner's ray by shuffle, result written over t_j); each owner adds its row up IN ORDER.
-// Same sample points, same summation order: bit-identical to med_tau_scalar.  Every lane of the warp must call.
-#ifndef SH_SLOTS
-#define SH_SLOTS 16
-#endif
-#ifndef SH_COOP_TAU
-#define SH_COOP_TAU 0
-#endif
-template <class Med>
-__device__ __forceinline__ float coop_tau(const Med &m, uint32_t lane, bool want, v3 o, v3 d, float mint, float maxt,
-                                          float stepSize, float u, float *vals, uint32_t *pref, uint32_t *nsamples) {
-    float tcur = 0.f, tend = 0.f, sum = 0.f;
-    v3 dn = V3(0.f, 0.f, 0.f);
-    bool has = false;
-    if (want) {
-        const float length = vlen(d);
-        if (length != 0.f) {
-            dn = vdiv(d, length);
-            float t0, t1;
-            if (med_intersectp(m, o, dn, mint * length, maxt * length, &t0, &t1)) { has = true; tcur = t0 + u * stepSize; tend = t1; }
-        }
-    }
-    for (;;) {
-        uint32_t n = 0;
-        if (has) while (n < SH_SLOTS && tcur < tend) { vals[lane * SH_SLOTS + n] = tcur; tcur += stepSize; ++n; }
-        uint32_t inc = n;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(PV_FULL, inc, off); if (lane >= (uint32_t)off) inc += t; }
-        const uint32_t total = __shfl_sync(PV_FULL, inc, 31);
-        if (total == 0) break;
-        pref[lane] = inc - n;
-        if (lane == 0) pref[32] = total;
-        __syncwarp();
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t i = base + lane;
-            const bool valid = i < total;
-            uint32_t owner = 0;
-            if (valid) {
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) if (pref[owner + sft] <= i) owner += sft;
-            }
-            const float ox = __shfl_sync(PV_FULL, o.x, owner), oy = __shfl_sync(PV_FULL, o.y, owner), oz = __shfl_sync(PV_FULL, o.z, owner);
-            const float dx = __shfl_sync(PV_FULL, dn.x, owner), dy = __shfl_sync(PV_FULL, dn.y, owner), dz = __shfl_sync(PV_FULL, dn.z, owner);
-            if (valid) {
-                float *slot = vals + owner * SH_SLOTS + (i - pref[owner]);
-                *slot = grid_density(m, med_to_volume_p(m, ray_at(V3(ox, oy, oz), V3(dx, dy, dz), *slot)));
-            }
-        }
-        __syncwarp();
-        for (uint32_t k = 0; k < n; ++k) sum += vals[lane * SH_SLOTS + k];
-        if (nsamples) *nsamples += n;
-        __syncwarp();
-    }
-    return sum * stepSize;
-}
-
-// The 30-bin spectrum loops stay ROLLED: unrolled (with an IEEE division or an expf per bin) they made the kernel 12 k
-// instructions (197 KB) and the instruction cache missed on a third of the fetches; rolled, alpha[] is indexed dynamically
-// and lives in local memory, which the free-flight march -- where the time goes -- never touches.
-#ifndef SH_BIN_UNROLL
-#define SH_BIN_UNROLL 1
-#endif
-#define SH_STR(x) #x
-#define SH_PRAGMA_UNROLL(n) _Pragma(SH_STR(unroll n))
-#define SH_UNROLL_BINS SH_PRAGMA_UNROLL(SH_BIN_UNROLL)
-#ifndef SH_MIN_CTAS
-#define SH_MIN_CTAS 8                // 32 warps/SM at 64 registers: latency-bound on density taps, the spills cost less than the occupancy gains (measured 4: 40.9 ms, 6: 36.1 ms, 8: 35.2 ms)
-#endif
-// KIND: bit 0 = the scene holds sphere primitives, bit 1 = the medium is exponential.  Plain scenes (triangles; homogeneous,
-// rainbow or grid medium) run an instantiation that carries no trace of the other cases.
-template <bool SURF, int KIND>
-__global__ void __launch_bounds__(SH_THREADS, SH_MIN_CTAS) shoot_kernel(ShootArgs a) {
-    constexpr bool SPH = (KIND & 1) != 0;
-    typedef typename std::conditional<(KIND & 2) != 0, MedView, MedViewPlain>::type MV;
-    __shared__ float s_cie[PV_NSPEC], s_sa[PV_NSPEC], s_ss[PV_NSPEC], s_st[PV_NSPEC];
-    __shared__ uint32_t s_perm[41];
-    __shared__ float s_minmax[3];
-#if SH_COOP_TAU
-    __shared__ float s_tau_vals[SH_THREADS / 32][32 * SH_SLOTS];
-    __shared__ uint32_t s_tau_pref[SH_THREADS / 32][33];
-#endif
-    const DevScene &sc = *a.sc;
-    const DevMedium &gmed = sc.med;
-    const MV med = make_medview<MV>(gmed);             // extent / grid dimensions / grid pointer in registers
-    if (threadIdx.x < PV_NSPEC) {
-        s_cie[threadIdx.x] = sc.cie_y[threadIdx.x]; s_sa[threadIdx.x] = gmed.sigma_a[threadIdx.x];
-        s_ss[threadIdx.x] = gmed.sigma_s[threadIdx.x]; s_st[threadIdx.x] = gmed.sigma_a[threadIdx.x] + gmed.sigma_s[threadIdx.x];
-    }
-    if (threadIdx.x < 41) s_perm[threadIdx.x] = a.perm[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mn = INFINITY, mx = 0.f, y1 = 0.f;
-SH_UNROLL_BINS
-        for (int b = 0; b < PV_NSPEC; ++b) { mn = fminf(mn, s_st[b]); mx = fmaxf(mx, s_st[b]); y1 += s_cie[b]; }
-        s_minmax[0] = mn; s_minmax[1] = mx; s_minmax[2] = __fdiv_rn(y1 * 300.f, 106.856895f * (float)PV_NSPEC);
-    }
-    __syncthreads();
-    const float st_min = s_minmax[0], st_max = s_minmax[1], y_one = s_minmax[2];
-    const uint64_t total = (uint64_t)a.n_local_blocks * SH_BLOCK;
-    const uint32_t halton_base[6] = {2, 3, 5, 7, 11, 13};
-
-    Frame cur;
-    Frame stack[SH_MAXDEPTH];
-    int sp = 0, state = ST_NEWPATH;
-    PathRng rng; rng.reset(0, a.k0, a.k1);
-    uint64_t path = 0, gblock = 0; uint32_t lblock = 0, dep_seq = 0;
-    uint32_t c_nodes = 0, c_tris = 0, c_dens = 0, c_seg = 0, c_ovf = 0, c_paths = 0;
-
-    for (;;) {
-        // Warp-wide meeting point of every iteration (all paths below end in `continue` or fall through to here).  The
-        // votes are what makes the lanes RE-CONVERGE: without them independent thread scheduling lets each lane run its own
-        // state sequence alone (measured: 2.2 active lanes per instruction).  Rounds alternate: while any lane is in a short
-        // state (NEWPATH, SURFACE) only those lanes run and the lanes already at TRACE wait; once every live lane is at
-        // TRACE they all trace together -- the segment march, where nearly all the time goes, runs with full warps.
-        if (__all_sync(PV_FULL, state == ST_DONE)) break;
-        const bool short_round = __any_sync(PV_FULL, state == ST_NEWPATH || state == ST_SURFACE);
-#if SH_COOP_TAU
-        const uint32_t part = __ballot_sync(PV_FULL, state == ST_TRACE);      // the lanes of a TRACE round (all of them, except at the very end)
-#endif
-        if (state == ST_DONE || (short_round && state == ST_TRACE)) continue;
-        if (state == ST_NEWPATH) {
-            // ---- fetch a light path (warp-aggregated counter) and emit it: photonshooter.cpp:248-275
-            cg::coalesced_group g = cg::coalesced_threads();
-            unsigned long long w = 0;
-            if (g.thread_rank() == 0) w = atomicAdd(a.work, (unsigned long long)g.size());
-            w = g.shfl(w, 0) + g.thread_rank();
-            if (w >= total) { state = ST_DONE; continue; }
-            lblock = (uint32_t)(w / SH_BLOCK);
-            gblock = a.b_start + (uint64_t)lblock * a.world;
-            path = (gblock - 1) * SH_BLOCK + (w % SH_BLOCK) + 1;
-            rng.reset(path, a.k0, a.k1);
-            dep_seq = 0; sp = 0; c_paths++;
-            float u[6];
-            {
-                const uint32_t *p = s_perm;
-#pragma unroll
-                for (int dmn = 0; dmn < 6; ++dmn) {
-                    uint32_t base = halton_base[dmn], n = (uint32_t)path;
-                    double val = 0, invBase = 1. / base, invBi = invBase;
-                    while (n > 0) {
-                        uint32_t d_i = p[n % base];
-                        val += d_i * invBi;
-                        n = __double2uint_rz((double)n * invBase);
-                        invBi *= invBase;
-                    }
-                    u[dmn] = fminf((float)val, PV_ONE_MINUS_EPS);
-                    p += base;
-                }
-            }
-            // SampleDiscrete (montecarlo.h:99-107): upper_bound on the CDF
-            int nl = (int)sc.n_lights, lo = 0, hi = nl + 1;
-            while (lo < hi) { int mid = (lo + hi) / 2; if (u[0] < sc.light_cdf[mid]) hi = mid; else lo = mid + 1; }
-            int lightNum = max(lo - 1, 0);
-            float lightPdf = __fdiv_rn(sc.light_func[lightNum], sc.light_func_int * nl);
-            const pv_light &l = sc.lights[lightNum];
-            v3 ro, rd; float pdf, scale = 1.f;
-            if (l.type == PV_LIGHT_POINT) {                                // lights/point.cpp:80-88
-                ro = V3(l.pos[0], l.pos[1], l.pos[2]); rd = uniform_sample_sphere(u[1], u[2]);
-                pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
-            } else if (l.type == PV_LIGHT_SPOT) {                          // lights/spot.cpp:106-114
-                v3 v = uniform_sample_cone(u[1], u[2], l.cos_total_width);
-                ro = V3(l.pos[0], l.pos[1], l.pos[2]); rd = xf_vec(l.light_to_world, v);
-                pdf = __fdiv_rn(1.f, 2.f * PV_PI_F * (1.f - l.cos_total_width));
-                scale = spot_falloff(l, rd);
-            } else {                                                       // lights/distant.cpp:82-102
-                const float *wb = sc.world_bound;
-                v3 pmin = V3(wb[0], wb[1], wb[2]), pmax = V3(wb[3], wb[4], wb[5]);
-                v3 wc = pmin * .5f + pmax * .5f;
-                float wr = bbox_inside(wb, wb + 3, wc) ? vlen(wc - pmax) : 0.f;
-                v3 ld = V3(l.dir[0], l.dir[1], l.dir[2]), v1, v2;
-                coordinate_system(ld, &v1, &v2);
-                float d1, d2;
-                concentric_sample_disk(u[1], u[2], &d1, &d2);
-                v3 Pdisk = wc + (v1 * d1 + v2 * d2) * wr;
-                ro = Pdisk + ld * wr; rd = -ld;
-                pdf = __fdiv_rn(1.f, PV_PI_F * wr * wr);
-            }
-            float ad = fabsf(vdot(rd, rd));                                // AbsDot(Nl, photonRay.d) with Nl == ray.d
-            float den = pdf * lightPdf;
-            bool black = true;
-            int npos = 0;
-SH_UNROLL_BINS
-            for (int b = 0; b < PV_NSPEC; ++b) {
-                float Le = l.type == PV_LIGHT_SPOT ? l.intensity[b] * scale : l.intensity[b];
-                cur.alpha[b] = __fdiv_rn(Le * ad, den);
-                black = black && (cur.alpha[b] == 0.f);
-                npos += cur.alpha[b] > 0.f ? 1 : 0;
-            }
-            if (pdf == 0.f || black) continue;                             // stays in ST_NEWPATH
-            cur.o[0] = ro.x; cur.o[1] = ro.y; cur.o[2] = ro.z; cur.d[0] = rd.x; cur.d[1] = rd.y; cur.d[2] = rd.z;
-            cur.mint = 0.f; cur.maxt = INFINITY; cur.nI = 0; cur.spec = 1 | (npos == 1 ? 2 : 0); cur.loop_i = -1; cur.prim = -1;
-            state = ST_TRACE;
-            continue;
-        }
-        const v3 o = V3(cur.o[0], cur.o[1], cur.o[2]), d = V3(cur.d[0], cur.d[1], cur.d[2]);
-        bool pop = false;
-        if (state == ST_TRACE) {
-            // ---- followPhoton head: intersect, march the medium (photonshooter.cpp:54-128)
-            c_seg++;
-            float thit = cur.maxt;
-            BvhCounters bc = {0, 0};
-            int prim = bvh_traverse<false, SPH>(sc, o, d, cur.mint, &thit, &bc);
-            c_nodes += bc.nodes; c_tris += bc.tris;
-#if SH_COOP_TAU
-            bool marching = false, interaction = false;
-            v3 rnd = V3(0.f, 0.f, 0.f);
-            float t0 = 1.0f, t1 = 0.0f, t_i = 0.f, xi = 0.f;
-#endif
-            if (prim < 0) pop = true;
-            else {
-                // hit record: shapes/trianglemesh.cpp:160-205 with default uvs, core/diffgeom.cpp:40-55
-                v3 dpdu, nn, hp; float eps;
-                const float *tv = sc.tri + 9 * (size_t)prim;
-                if (!SPH || tv[0] == tv[0]) {
-                    v3 p1 = V3(tv[0], tv[1], tv[2]), p2 = V3(tv[3], tv[4], tv[5]), p3 = V3(tv[6], tv[7], tv[8]);
-                    v3 dp1 = p1 - p3, dp2 = p2 - p3;
-                    dpdu = (dp1 * -1.f - dp2 * -1.f) * 1.f;                     // (dv2*dp1 - dv1*dp2) * invdet, dv1 = dv2 = -1
-                    v3 dpdv = (dp1 * -0.f + dp2 * -1.f) * 1.f;                  // (-du2*dp1 + du1*dp2) * invdet, du2 = 0, du1 = -1
-                    nn = vnorm(vcross(dpdu, dpdv));
-                    hp = ray_at(o, d, thit);
-                    eps = 1e-3f * thit;
-                } else sphere_dg(sc.spheres + (__float_as_uint(tv[0]) & PV_SPHERE_INDEX_MASK), o, d, thit, &hp, &nn, &dpdu, &eps);   // NaN-tagged slot: shapes/sphere.cpp:112-163
-                cur.prim = prim; cur.ip[0] = hp.x; cur.ip[1] = hp.y; cur.ip[2] = hp.z;
-                cur.inn[0] = nn.x; cur.inn[1] = nn.y; cur.inn[2] = nn.z;
-                cur.idpdu[0] = dpdu.x; cur.idpdu[1] = dpdu.y; cur.idpdu[2] = dpdu.z;
-                cur.ieps = eps;
-                cur.maxt = thit;                                            // GeometricPrimitive::Intersect: r.maxt = thit
-                cur.nI++;
-                float length = vlen(d);
-                if (length == 0.f) pop = true;
-                else {
-#if SH_COOP_TAU
-                    rnd = vdiv(d, length);
-                    if (!med_intersectp(med, o, rnd, cur.mint * length, cur.maxt * length, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
-                    t0 += rng.next() * a.stepsize;
-                    t_i = t0;
-                    xi = rng.next();
-                    marching = true;
-                }
-            }
-            {
-                {
-                    const bool coop = med.type == PV_MEDIUM_GRID && part == PV_FULL;
-                    for (;;) {
-                        const bool step = marching && !interaction && t0 < t1;
-                        if (coop ? !__any_sync(PV_FULL, step) : !step) break;
-                        float uo = 0.f;
-                        if (step) uo = rng.next();
-                        uint32_t ns = 0;
-                        float s;
-                        if (coop) s = coop_tau(med, threadIdx.x & 31, step, o, rnd, t_i, t0, a.istep4, uo, s_tau_vals[threadIdx.x >> 5],
-                                               s_tau_pref[threadIdx.x >> 5], &ns);
-                        else s = shoot_tau(med, o.x, o.y, o.z, rnd.x, rnd.y, rnd.z, t_i, t0, a.istep4, uo, &ns);
-                        c_dens += ns;
-                        if (!step) continue;
-#else
-                    v3 rnd = vdiv(d, length);
-                    float t0, t1;
-                    if (!med_intersectp(med, o, rnd, cur.mint * length, cur.maxt * length, &t0, &t1)) { t0 = 1.0f; t1 = 0.0f; }
-                    t0 += rng.next() * a.stepsize;
-                    const float t_i = t0;
-                    const float xi = rng.next();
-                    bool interaction = false;
-                    while (t0 < t1) {
-                        float uo = rng.next();                               // Transmittance(sample == NULL): offset = RandomFloat()
-                        uint32_t ns = 0;
-                        float s = shoot_tau(med, o.x, o.y, o.z, rnd.x, rnd.y, rnd.z, t_i, t0, a.istep4, uo, &ns);
-                        c_dens += ns;
-#endif
-                        // xi > Tr.y() ?  y(exp(-sig_t s)) lies between exp(-st_max s) y1 and exp(-st_min s) y1
-                        bool hitv;
-                        float elo = expf(-(st_max * s)) * y_one, ehi = expf(-(st_min * s)) * y_one;
-                        if (xi > ehi * 1.0001f) hitv = true;
-                        else if (xi < elo * 0.9999f) hitv = false;
-                        else {
-                            float yy = 0.f;
-SH_UNROLL_BINS
-                            for (int b = 0; b < PV_NSPEC; ++b) yy += s_cie[b] * expf(-(s_st[b] * s));
-                            hitv = xi > __fdiv_rn(yy * 300.f, 106.856895f * (float)PV_NSPEC);
-                        }
-#if SH_COOP_TAU
-                        if (hitv) { interaction = true; continue; }
-#else
-                        if (hitv) { interaction = true; break; }
-#endif
-                        t0 += a.stepsize;
-                    }
-#if SH_COOP_TAU
-                    if (!marching) { /* no segment to march: pop is set */ } else
-#endif
-                    if (interaction) {
-                        v3 pt = ray_at(o, rnd, t0);
-                        uint32_t ns = 0;
-                        float dens = med_density(med, pt, &ns);
-                        c_dens += 2 * ns;
-                        float ys = 0.f, ya = 0.f;
-SH_UNROLL_BINS
-                        for (int b = 0; b < PV_NSPEC; ++b) { ys += s_cie[b] * (s_ss[b] * dens); ya += s_cie[b] * (s_sa[b] * dens); }
-                        ys = __fdiv_rn(ys * 300.f, 106.856895f * (float)PV_NSPEC); ya = __fdiv_rn(ya * 300.f, 106.856895f * (float)PV_NSPEC);
-                        bool scatter = rng.next() > __fdiv_rn(ys, ya + ys);     // Q1 (photonshooter.cpp:88)
-                        if (!scatter) pop = true;
-                        else if (SURF && (a.flags & SF_VOLUME_DONE)) {
-                            // `if (scatter && !volumeDone)` (:96): with the volume map full the event is ignored and the
-                            // surface code runs with the unscattered ray
-                            state = ST_SURFACE; cur.loop_i = -1;
-                            continue;
-                        } else {
-                            if (cur.nI > 1) {
-                                // ---- deposit (photonshooter.cpp:98-102), normalised by nshot of its block (:333)
-                                deposit_photon(a, PC_VOLUME, gblock, path, dep_seq, pt, rnd, cur.alpha, (float)(gblock * SH_BLOCK));
-                                dep_seq++;
-                            } else if (SURF) atomicAdd(&a.block_counts[PC_COUNT * a.wave_blocks + (uint32_t)(gblock - a.first_block)], 1u);   // shooter->nVolumePaths++ (:104)
-                            float u1 = rng.next(), u2 = rng.next();
-                            v3 dir = uniform_sample_sphere(u1, u2);
-                            const float pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
-                            float ref = med_phase(med, pt, rnd, dir);
-                            if (ref == 0.f) pop = true;
-                            else {
-SH_UNROLL_BINS
-                                for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] = __fdiv_rn(cur.alpha[b] * ref, pdf);
-                                cur.o[0] = pt.x; cur.o[1] = pt.y; cur.o[2] = pt.z; cur.d[0] = dir.x; cur.d[1] = dir.y; cur.d[2] = dir.z;
-                                cur.mint = 0.f; cur.maxt = INFINITY; cur.loop_i = -1;
-                                // Q2: after the scattered sub-path, the surface code runs with this ray and the hit above
-                                if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
-                                // the recursive call itself: same ray, state TRACE
-                                state = ST_TRACE;
-                                continue;
-                            }
-                        }
-                    } else {
-                        state = ST_SURFACE; cur.loop_i = -1;
-                        continue;
-                    }
-                }
-            }
-        } else {
-            // ---- surface part (photonshooter.cpp:131-227); caustic/indirect/direct maps are off on this path
-            if (cur.loop_i < 0) {
-                float uo = rng.next();
-                uint32_t ns = 0;
-                float s = shoot_tau(med, o.x, o.y, o.z, d.x, d.y, d.z, cur.mint, cur.maxt, a.istep4, uo, &ns);
-                c_dens += ns;
-SH_UNROLL_BINS
-                for (int b = 0; b < PV_NSPEC; ++b) cur.alpha[b] *= expf(-(s_st[b] * s));
-                cur.loop_i = 0;
-                if (SURF) {
-                    // ---- surface deposits (photonshooter.cpp:147-189).  hasNonSpecular == matte with a non-black Kd
-                    // (materials/matte.cpp:55); glass has only specular components.
-                    const pv_material &dm = sc.mats[sc.prim_mat[cur.prim]];
-                    bool nonspec = false;
-                    if (dm.type == PV_MAT_MATTE) {
-SH_UNROLL_BINS
-                        for (int b = 0; b < PV_NSPEC; ++b) nonspec = nonspec || dm.kd[b] != 0.f;
-                    }
-                    if (nonspec) {
-                        int cls = -1;
-                        if ((cur.spec & 1) && cur.nI > 1) { if (a.flags & SF_WANT_CAUSTIC) cls = PC_CAUSTIC; }
-                        else if (cur.nI == 1 && (a.flags & SF_WANT_INDIRECT) && (a.flags & SF_FINAL_GATHER)) cls = PC_DIRECT;
-                        else if (cur.nI > 1 && (a.flags & SF_WANT_INDIRECT)) cls = PC_INDIRECT;
-                        if (cls >= 0) {
-                            const v3 hp = V3(cur.ip[0], cur.ip[1], cur.ip[2]);
-                            deposit_photon(a, (uint32_t)cls, gblock, path, dep_seq, hp, -d, cur.alpha, 1.f);
-                            dep_seq++;
-                            // radiance-photon site (:178-188): p, Faceforward(n, -d), rho_r = Kd (Lambertian::rho), rho_t = 0;
-                            // the two BSDF::rho calls draw 2 x 2 x StratifiedSample2D(6 x 6) = 288 floats
-                            if ((a.flags & SF_FINAL_GATHER) && rng.next() < .125f) {
-                                v3 rn = V3(cur.inn[0], cur.inn[1], cur.inn[2]);
-                                if (vdot(rn, -d) < 0.f) rn = -rn;
-                                deposit_photon(a, PC_RADIANCE, gblock, path, dep_seq, hp, rn, dm.kd, 1.f);
-                                dep_seq++;
-                                rng.skip(288);
-                            }
-                        }
-                    }
-                }
-                if (cur.nI >= a.max_depth) pop = true;
-            }
-            if (!pop) {
-                const pv_material &mat = sc.mats[sc.prim_mat[cur.prim]];
-                const v3 wo = -d;
-                const v3 nn = V3(cur.inn[0], cur.inn[1], cur.inn[2]);
-                const v3 sn = vnorm(V3(cur.idpdu[0], cur.idpdu[1], cur.idpdu[2]));        // BSDF frame, reflection.cpp:619-627
-                const v3 tn = vcross(nn, sn);
-                if (mat.type == PV_MAT_MATTE) {
-                    // Lambertian bounce (reflection.cpp:323-330,534-598).  With the surface maps off the path always dies
-                    // here (Q6: indirectDone && !specularPath), but frames still on the stack keep drawing from this path's
-                    // stream, so the number of draws consumed must match the reference: 3 for BSDFSample, then the Russian
-                    // roulette draw only if the sample is valid.
-                    float u0 = rng.next(), u1 = rng.next(); rng.next();
-                    bool kd_black = true;
-SH_UNROLL_BINS
-                    for (int b = 0; b < PV_NSPEC; ++b) kd_black = kd_black && mat.kd[b] == 0.f;
-                    if (!kd_black) {
-                        v3 wol = V3(vdot(wo, sn), vdot(wo, tn), vdot(wo, nn));
-                        v3 wil;
-                        concentric_sample_disk(u0, u1, &wil.x, &wil.y);
-                        wil.z = __fsqrt_rn(fmaxf(0.f, 1.f - wil.x * wil.x - wil.y * wil.y));
-                        if (wol.z < 0.f) wil.z *= -1.f;
-                        float pdf = (wol.z * wil.z > 0.f) ? fabsf(wil.z) * PV_INV_PI_F : 0.f;
-                        if (pdf != 0.f) {
-                            v3 wiW = V3(sn.x * wil.x + tn.x * wil.y + nn.x * wil.z, sn.y * wil.x + tn.y * wil.y + nn.y * wil.z,
-                                        sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
-                            if (vdot(wiW, nn) * vdot(wo, nn) > 0.f) {
-                                if (!SURF) rng.next();                              // continueProb draw
-                                else {
-                                    // anew = alpha * f * |wi.n| / pdf, f = Kd / pi; Russian roulette on y(anew) / y(alpha) (:204-213)
-                                    const float adn = fabsf(vdot(wiW, nn));
-                                    float ynew = 0.f, yold = 0.f;
-SH_UNROLL_BINS
-                                    for (int b = 0; b < PV_NSPEC; ++b) {
-                                        const float an = __fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf);
-                                        ynew += s_cie[b] * an; yold += s_cie[b] * cur.alpha[b];
-                                    }
-                                    ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
-                                    const float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
-                                    // specularPath &= false, then `indirectDone && !specularPath` ends the path (:216-219)
-                                    if (!(rng.next() > continueProb) && (a.flags & SF_WANT_INDIRECT)) {
-                                        int npos = 0;
-SH_UNROLL_BINS
-                                        for (int b = 0; b < PV_NSPEC; ++b) {
-                                            cur.alpha[b] = __fdiv_rn(__fdiv_rn((cur.alpha[b] * (mat.kd[b] * PV_INV_PI_F)) * adn, pdf), continueProb);
-                                            npos += cur.alpha[b] > 0.f ? 1 : 0;
-                                        }
-                                        cur.spec = npos == 1 ? 2 : 0;        // specularPath = false; alpha re-made: lambda = extractLambda()
-                                        cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
-                                        cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
-                                        cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
-                                        // the loop over `spectrums` has one entry here (no transmission, no split): a tail call
-                                        state = ST_TRACE;
-                                        continue;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    pop = true;
-                } else {
-                    // glass: SpecularReflection + dispersive SpecularTransmission (materials/glass.cpp:42-59)
-                    bool hasR = false, hasT = false;
-SH_UNROLL_BINS
-                    for (int b = 0; b < PV_NSPEC; ++b) { hasR = hasR || mat.kr[b] != 0.f; hasT = hasT || mat.kt[b] != 0.f; }
-                    const int matching = (hasR ? 1 : 0) + (hasT ? 1 : 0);
-                    int nz = 0;
-SH_UNROLL_BINS
-                    for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) nz++;
-                    // hasTransmission && alpha.lambda < 0 && primitive->dispersive() (photonshooter.cpp:140-145).  lambda is path STATE
-                    // (see Frame::spec): a monochromatic child whose one bin underflowed to zero in a dense medium is not split again
-                    // here, it goes on as a black photon with lambda = -1 and ends at the next dispersive face.
-                    const bool do_split = hasT && !(cur.spec & 2) && mat.vn > 0.f;
-                    bool spawned = false;
-                    for (;;) {
-                        // next spectrum of the split (splitSpectrum core/spectrum.h:253-265): bins with c != 0, in order
-                        int bin = -1;
-                        if (do_split) {
-                            int seen = 0;
-SH_UNROLL_BINS
-                            for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] != 0.f) { if (seen == cur.loop_i) { bin = b; break; } seen++; }
-                            if (bin < 0) break;
-                        } else if (cur.loop_i > 0) break;
-                        cur.loop_i++;
-                        float u0 = rng.next(), u1 = rng.next(), uc = rng.next();
-                        (void)u0; (void)u1;
-                        if (matching == 0) continue;
-                        int which = min((int)floorf(uc * matching), matching - 1);
-                        bool pickT = hasR ? (which == 1) : true;
-                        v3 wol = V3(vdot(wo, sn), vdot(wo, tn), vdot(wo, nn));
-                        v3 wil; float F = fresnel_dielectric(wol.z, mat.index);
-                        float fpdf = 1.f;
-                        if (!pickT) wil = V3(-wol.x, -wol.y, wol.z);
-                        else {
-                            bool entering = wol.z > 0.f;
-                            float ei = 1.f, et = mat.index;
-                            int lam = -1;
-                            if (do_split) lam = 400 + bin * 10;                    // extractLambda: integer step (700-400)/29 == 10
-                            else if (nz == 1) {
-SH_UNROLL_BINS
-                                for (int b = 0; b < PV_NSPEC; ++b) if (cur.alpha[b] > 0.f) lam = 400 + b * 10; }
-                            if (lam > 0 && mat.vn > 0.f) {                         // Cauchy, reflection.cpp:155-161
-                                float lmu = __fdiv_rn((float)lam, 1000.f);
-                                float B = (float)((double)__fdiv_rn(et - 1.f, mat.vn) * 0.52345);
-                                float A = (float)((double)et - ((double)B / 0.34522792));
-                                et = (float)((double)A + (double)B / ((double)lmu * (double)lmu));
-                            }
-                            if (!entering) { float t = ei; ei = et; et = t; }
-                            float sini2 = fmaxf(0.f, 1.f - wol.z * wol.z);
-                            float eta = __fdiv_rn(ei, et);
-                            float sint2 = eta * eta * sini2;
-                            if (sint2 >= 1.f) continue;                            // total internal reflection: pdf stays 0
-                            float cost = __fsqrt_rn(fmaxf(0.f, 1.f - sint2));
-                            if (entering) cost = -cost;
-                            wil = V3(eta * -wol.x, eta * -wol.y, cost);
-                        }
-                        if (matching > 1) fpdf = __fdiv_rn(fpdf, (float)matching);
-                        v3 wiW = V3(sn.x * wil.x + tn.x * wil.y + nn.x * wil.z, sn.y * wil.x + tn.y * wil.y + nn.y * wil.z,
-                                    sn.z * wil.x + tn.z * wil.y + nn.z * wil.z);
-                        float adn = fabsf(vdot(wiW, nn));
-                        float anew[PV_NSPEC], ynew = 0.f, yold = 0.f; bool fblack = true;
-SH_UNROLL_BINS
-                        for (int b = 0; b < PV_NSPEC; ++b) {
-                            float ab = do_split ? (b == bin ? cur.alpha[b] : 0.f) : cur.alpha[b];
-                            float fb = pickT ? __fdiv_rn((1.f - F) * mat.kt[b], fabsf(wil.z)) : __fdiv_rn(F * mat.kr[b], fabsf(wil.z));
-                            fblack = fblack && fb == 0.f;
-                            anew[b] = __fdiv_rn((ab * fb) * adn, fpdf);
-                            ynew += s_cie[b] * anew[b]; yold += s_cie[b] * ab;
-                        }
-                        if (fblack) continue;
-                        ynew = __fdiv_rn(ynew * 300.f, 106.856895f * (float)PV_NSPEC); yold = __fdiv_rn(yold * 300.f, 106.856895f * (float)PV_NSPEC);
-                        float continueProb = fminf(1.f, __fdiv_rn(ynew, yold));
-                        if (rng.next() > continueProb) continue;
-                        if (!(cur.spec & 1) && !(SURF && (a.flags & SF_WANT_INDIRECT))) continue;   // indirectDone && !specularPath
-                        // spawn the child; this frame resumes at loop_i afterwards
-                        if (sp < SH_MAXDEPTH) stack[sp++] = cur; else c_ovf++;
-                        int npos = 0;
-SH_UNROLL_BINS
-                        for (int b = 0; b < PV_NSPEC; ++b) { cur.alpha[b] = __fdiv_rn(anew[b], continueProb); npos += cur.alpha[b] > 0.f ? 1 : 0; }
-                        cur.spec = (cur.spec & 1) | (npos == 1 ? 2 : 0);           // alpha re-made: lambda = extractLambda()
-                        cur.o[0] = cur.ip[0]; cur.o[1] = cur.ip[1]; cur.o[2] = cur.ip[2];
-                        cur.d[0] = wiW.x; cur.d[1] = wiW.y; cur.d[2] = wiW.z;
-                        cur.mint = cur.ieps; cur.maxt = INFINITY; cur.loop_i = -1;
-                        spawned = true;
-                        break;
-                    }
-                    if (spawned) { state = ST_TRACE; continue; }
-                    pop = true;
-                }
-            }
-        }
-        if (pop) {
-            if (sp == 0) state = ST_NEWPATH;
-            else { cur = stack[--sp]; state = ST_SURFACE; }
-        }
-    }
-    // ---- counters
-    unsigned long long vals[6] = {c_nodes, c_tris, c_dens, c_seg, c_ovf, c_paths};
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        unsigned long long v = vals[i];
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(PV_FULL, v, off);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&a.stats[i], v);
-    }
-}
-
 // PV_TIMING=1: wall time of the host-side phases of shooting on stderr (tuning aid)
 namespace {
 struct PhaseTimer {
@@ -673,25 +110,10 @@ static int shoot_wave(pv_ctx *ctx, uint64_t first_block, uint32_t n_blocks, cons
         PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_work, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
         PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n_blocks * n_cls, ctx->stream));
-        int per_sm = 0;
         const int kind = (ctx->hscene.n_spheres != 0 ? 1 : 0) | (ctx->hscene.med.type == PV_MEDIUM_EXPONENTIAL ? 2 : 0);
-        static void (*const kerns[2][4])(ShootArgs) = {
-            {shoot_kernel<false, 0>, shoot_kernel<false, 1>, shoot_kernel<false, 2>, shoot_kernel<false, 3>},
-            {shoot_kernel<true, 0>, shoot_kernel<true, 1>, shoot_kernel<true, 2>, shoot_kernel<true, 3>}};
-        void (*kern)(ShootArgs) = kerns[surf ? 1 : 0][kind];
-        {   // CUDA loads a kernel lazily at its first launch; do it here so that the load does not sit between the two timing events
-            cudaFuncAttributes fa;
-            PV_CUDA_CHECK(ctx, cudaFuncGetAttributes(&fa, kern));
-        }
-        PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SH_THREADS, 0));
-        if (per_sm < 1) per_sm = 1;
-        uint64_t total = (uint64_t)n_local * SH_BLOCK;
-        int blocks = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, (total + SH_THREADS - 1) / SH_THREADS);
-        static const bool megakernel = getenv("PV_SHOOT_MEGAKERNEL") != nullptr;        // A/B knob: the persistent-thread kernel of round 1
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         bool replay = false;
-        if (megakernel) kern<<<blocks, SH_THREADS, 0, ctx->stream>>>(a);
-        else { rc = pvi_wavefront_run(ctx, a, surf, kind, &replay); if (rc) return rc; }
+        rc = pvi_wavefront_run(ctx, a, surf, kind, &replay); if (rc) return rc;
         PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         PV_CUDA_CHECK(ctx, cudaGetLastError());
         unsigned long long h_nout = 0, h_stats[8];

@@ -22,20 +22,22 @@ __global__ void occluded_kernel(const DevScene *__restrict__ sc, const pv_ray *_
     float maxt = r.maxt;
     hit[i] = bvh_traverse<true, SPH>(*sc, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, &maxt, nullptr) >= 0 ? 1 : 0;
 }
-// one warp per ray: lane 0..29 own a spectral bin; the optical-depth scalar is computed redundantly (uniform loads)
+// one thread per ray: the optical-depth scalar is marched once, then the 30 bins of exp(-sigma_t s) go out (neighbouring threads
+// are neighbouring rays: their density taps share sectors)
 __global__ void transmittance_kernel(const DevScene *__restrict__ sc, const pv_ray *__restrict__ rays, uint64_t n, float step,
                                      const float *__restrict__ u, float *__restrict__ T) {
-    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (w >= n) return;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     const DevMedium &med = sc->med;
-    float tr = 1.f;
-    if (med.type != PV_MEDIUM_NONE) {
-        pv_ray r = rays[w];
-        float s = med_tau_scalar(med, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, step, u ? u[w] : 0.5f, nullptr);
-        if (lane < PV_NSPEC) tr = expf(-((med.sigma_a[lane] + med.sigma_s[lane]) * s));
+    float s = 0.f;
+    const bool has = med.type != PV_MEDIUM_NONE;
+    if (has) {
+        const pv_ray r = rays[i];
+        s = med_tau_scalar(med, V3(r.o[0], r.o[1], r.o[2]), V3(r.d[0], r.d[1], r.d[2]), r.mint, r.maxt, step, u ? u[i] : 0.5f, nullptr);
     }
-    if (lane < PV_NSPEC) T[w * PV_NSPEC + lane] = tr;
+    float *out = T + i * PV_NSPEC;
+#pragma unroll 1
+    for (int b = 0; b < PV_NSPEC; ++b) out[b] = has ? expf(-((med.sigma_a[b] + med.sigma_s[b]) * s)) : 1.f;
 }
 
 int pvi_intersect(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint32_t *d_prim, float *d_t) {
@@ -57,7 +59,7 @@ int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit) 
 int pvi_transmittance(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, const float *d_u, float *d_T) {
     if (!ctx->has_scene) { ctx->err = "pv_transmittance: no scene"; return PV_ESTATE; }
     if (!n) return PV_OK;
-    transmittance_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays, n, step, d_u, d_T);
+    transmittance_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->dscene, d_rays, n, step, d_u, d_T);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     return PV_OK;
 }

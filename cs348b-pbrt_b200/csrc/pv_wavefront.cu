@@ -183,7 +183,16 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(ShootArgs a, WaveS
             float lightPdf = __fdiv_rn(sc.light_func[lightNum], sc.light_func_int * nl);
             const pv_light &l = sc.lights[lightNum];
             v3 ro, rd; float pdf, scale = 1.f;
-            if (l.type == PV_LIGHT_POINT) {                                // lights/point.cpp:80-88
+            v3 lnrm = V3(0.f, 0.f, 0.f); bool own_normal = false, facing = true;
+            if (l.type == PV_LIGHT_AREA) {                                 // lights/diffuse.cpp:89-100, ShapeSet::Sample(ls, Ns) core/light.cpp:161-164
+                ro = area_sample_point(sc, l, lightNum, u[3], u[1], u[2], &lnrm);
+                rd = uniform_sample_sphere(u[4], u[5]);
+                if (vdot(rd, lnrm) < 0.f) rd = rd * -1.f;
+                // ShapeSet::Pdf(Point) (:175-180) sums areas[i] * (1 / areas[i]) over the shapes: the NUMBER of shapes over the total area
+                pdf = __fdiv_rn(sc.larea_pd[lightNum], sc.larea_sum[lightNum]) * 0.15915494309189533577f;
+                own_normal = true; facing = vdot(lnrm, rd) > 0.f;           // DiffuseAreaLight::L: Lemit towards the normal's side only
+                mint = 1e-3f;                                              // Ray(org, dir, 1e-3f, INFINITY, time)
+            } else if (l.type == PV_LIGHT_POINT) {                         // lights/point.cpp:80-88
                 ro = V3(l.pos[0], l.pos[1], l.pos[2]); rd = uniform_sample_sphere(u[1], u[2]);
                 pdf = __fdiv_rn(1.f, 4.f * PV_PI_F);
             } else if (l.type == PV_LIGHT_SPOT) {                          // lights/spot.cpp:106-114
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(ShootArgs a, WaveS
                 ro = Pdisk + ld * wr; rd = -ld;
                 pdf = __fdiv_rn(1.f, PV_PI_F * wr * wr);
             }
-            const float ad = fabsf(vdot(rd, rd));                          // AbsDot(Nl, photonRay.d) with Nl == ray.d
+            const float ad = fabsf(vdot(own_normal ? lnrm : rd, rd));        // AbsDot(Nl, photonRay.d); Nl == ray.d for the delta lights
             const float den = pdf * lightPdf;
             bool black = true;
             int npos = 0;
@@ -215,8 +224,8 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(ShootArgs a, WaveS
                 black = black && (al == 0.f);
                 npos += al > 0.f ? 1 : 0;
             }
-            if (!(pdf == 0.f || black)) {                                  // else: the slot stays free and draws the next path
-                o = ro; d = rd; mint = 0.f; maxt = INFINITY; nI = 0; spec = 1 | (npos == 1 ? 2 : 0) | WF_SPEC_PRISTINE;
+            if (!(pdf == 0.f || black || !facing)) {                       // else: the slot stays free and draws the next path
+                o = ro; d = rd; if (!own_normal) mint = 0.f; maxt = INFINITY; nI = 0; spec = 1 | (npos == 1 ? 2 : 0) | WF_SPEC_PRISTINE;
                 em = make_float4(ad, den, scale, __uint_as_float((uint32_t)lightNum));
                 w.path[slot] = path;
                 w.misc[slot] = make_uint2(0u, 0u);

@@ -31,6 +31,7 @@ class Scene:
         self.cie_y = np.zeros(A.NSPEC, dtype=np.float32)
         self.prim_shape = None              # uint32 per primitive: SHAPE_TRIANGLE or an index into spheres
         self.spheres = (A.Sphere * 0)()
+        self.light_tris = None              # float32 [n, 9]: triangles of the area lights (PV_LIGHT_AREA), see attach_area_lights
 
     @property
     def n_prims(self):
@@ -60,12 +61,41 @@ class Scene:
             d.prim_shape = self.prim_shape.ctypes.data_as(C.POINTER(C.c_uint32))
             d.spheres = C.cast(self.spheres, C.POINTER(A.Sphere))
             d.n_spheres = len(self.spheres)
+        if self.light_tris is not None and len(self.light_tris):
+            self.light_tris = np.ascontiguousarray(self.light_tris, dtype=np.float32)
+            d.light_tris = self.light_tris.ctypes.data_as(C.POINTER(C.c_float))
+            d.n_light_tris = self.light_tris.size // 9
         for i in range(6):
             d.world_bound[i] = float(self.world_bound[i])
         for i in range(A.NSPEC):
             d.cie_y[i] = float(self.cie_y[i])
         self._desc = d
         return d
+
+
+def attach_area_lights(scene, path):
+    """PVAREA01 side file (oracle/ref_harness --export-area-lights: per DiffuseAreaLight its slot in the light list, Lemit and the
+    triangles of its ShapeSet in refine order) -> the placeholder slots of `scene` become PV_LIGHT_AREA lights over scene.light_tris."""
+    buf = open(path, "rb").read()
+    assert buf[:8] == b"PVAREA01"
+    n = int(np.frombuffer(buf, np.uint64, 1, 8)[0])
+    off = 16
+    tris = [] if scene.light_tris is None else [np.asarray(scene.light_tris, np.float32).reshape(-1, 9)]
+    first = sum(len(t) for t in tris)
+    for _ in range(n):
+        slot, nt, flags = (int(v) for v in np.frombuffer(buf, np.uint32, 3, off)); off += 12
+        lem = np.frombuffer(buf, np.float32, 30, off); off += 120
+        tri = np.frombuffer(buf, np.float32, 9 * nt, off).reshape(nt, 9); off += 36 * nt
+        l = scene.lights[slot]
+        l.type = A.LIGHT_AREA
+        bits = np.array([first, nt, flags], np.uint32).view(np.float32)        # pv_light::area shares storage with pos[3]
+        for k in range(3):
+            l.pos[k] = bits[k]
+        for b in range(A.NSPEC):
+            l.intensity[b] = float(lem[b])
+        tris.append(tri); first += nt
+    scene.light_tris = np.concatenate(tris) if tris else None
+    return scene
 
 
 def read_scene(path):

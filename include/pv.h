@@ -59,10 +59,18 @@ typedef struct pv_ray {
     float u_scatter;
 } pv_ray;
 
-enum { PV_LIGHT_POINT = 0, PV_LIGHT_SPOT = 1, PV_LIGHT_DISTANT = 2 };
+/* PV_LIGHT_AREA: DiffuseAreaLight over a triangle mesh (lights/diffuse.cpp:39-106, its ShapeSet core/light.cpp:114-172):
+ * intensity[] = Lemit, `area` names its triangles in pv_scene_desc::light_tris (the ShapeSet's own refine order -- the order the
+ * area distribution samples by).  The same triangles are ordinary primitives of the scene's BVH.                       */
+enum { PV_LIGHT_POINT = 0, PV_LIGHT_SPOT = 1, PV_LIGHT_DISTANT = 2, PV_LIGHT_AREA = 3 };
+#define PV_AREA_REVERSE_ORIENTATION 1u
+#define PV_AREA_SWAPS_HANDEDNESS 2u
 typedef struct pv_light {
     int32_t type;
-    float   pos[3];                 /* point/spot lightPos (lights/point.cpp:43) */
+    union {
+        float pos[3];               /* point/spot lightPos (lights/point.cpp:43) */
+        struct { uint32_t first_tri, n_tris, flags; } area;     /* PV_LIGHT_AREA: range in light_tris, PV_AREA_* flags */
+    };
     float   dir[3];                 /* distant lightDir (lights/distant.cpp:43)  */
     float   cos_total_width;        /* spot (lights/spot.cpp:45-46)              */
     float   cos_falloff_start;
@@ -125,6 +133,8 @@ typedef struct pv_scene_desc {
      * tri_verts slot of a sphere primitive is ignored).                           */
     const uint32_t    *prim_shape;
     const pv_sphere   *spheres;     uint32_t n_spheres;
+    /* optional: the triangles of the area lights, 9 floats each, world space (see PV_LIGHT_AREA) */
+    const float       *light_tris;  uint32_t n_light_tris;
 } pv_scene_desc;
 
 /* PhotonVolumeIntegrator ctor params (integrators/photonvolume.h:17-20) +

@@ -33,6 +33,7 @@
 #define PV_RNG_RAY  0x7261u
 #define PV_RNG_STEP 0x6761u
 #define PV_RNG_PATH 0x7368u
+#define PV_RNG_AREA 0x6172u           /* area-light sample of a march step: ctr = (ray_lo, ray_hi, step, tag) -> w0, w1 = position on the light, w2 = component */
 #define PV_RNG_FINAL_GATHER 0x6667u   /* final-gather ray: ctr = (ray_lo, ray_hi, 0, tag) -> w0 = transmittance offset */
 
 PV_HD void pv_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -802,7 +802,15 @@ static spec light_sample_L_point(const pv_light *l, v3 p, v3 *wi, float *pdf, vi
 static const pvo_area_light *g_area = NULL;
 static uint32_t g_n_area = 0;
 void pvo_set_area_lights(const pvo_area_light *t, uint32_t n) { g_area = n ? t : NULL; g_n_area = t ? n : 0; }
+#define IS_AREA_LIGHT(l) ((l)->type == PVO_LIGHT_SLOT || (l)->type == PV_LIGHT_AREA)
 static const pvo_area_light *area_of(const pv_scene_desc *sc, const pv_light *l) {
+    if (l->type == PV_LIGHT_AREA) {                                         /* an area light of the scene description itself (include/pv.h) */
+        static __thread pvo_area_light view;
+        view.slot = (uint32_t)(l - sc->lights); view.n_tris = l->area.n_tris; view.flags = l->area.flags; view.pad = 0;
+        view.tri = sc->light_tris + 9 * (size_t)l->area.first_tri;
+        memcpy(view.Lemit, l->intensity, sizeof(view.Lemit));
+        return &view;
+    }
     uint32_t slot = (uint32_t)(l - sc->lights);
     for (uint32_t i = 0; i < g_n_area; ++i) if (g_area[i].slot == slot) return &g_area[i];
     return NULL;
@@ -985,13 +993,19 @@ static void li_one(const pv_scene_desc *sc, const pvo_kdtree *t, const float *wi
             if (ln > nLights - 1) ln = nLights - 1;
             const pv_light *light = &sc->lights[ln];
             float pdf; visray vis; v3 wo;
-            spec L = light->type == PVO_LIGHT_SLOT
-                         ? (rng_mode == PVO_RNG_MT ? area_sample_L(sc, light, p, /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]):
-                                                                   the component number is the THIRD argument (core/light.h) */
-                                                                   lightNum[2 * (size_t)nSamples + 2 * i + 1], lightNum[nSamples + i],
-                                                                   lightNum[2 * (size_t)nSamples + 2 * i], &wo, &pdf, &vis)
-                                                   : (pdf = 0.f, s_const(0.f)))
-                         : light_sample_L_point(light, p, &wo, &pdf, &vis);
+            spec L;
+            if (IS_AREA_LIGHT(light)) {
+                /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]): the component number is the THIRD
+                 * argument (core/light.h).  Philox mode: words 0, 1 (position) and 2 (component) of the step's PV_RNG_AREA block */
+                float uc, ua, ub;
+                if (rng_mode == PVO_RNG_MT) { uc = lightNum[2 * (size_t)nSamples + 2 * i + 1]; ua = lightNum[nSamples + i]; ub = lightNum[2 * (size_t)nSamples + 2 * i]; }
+                else {
+                    uint32_t aw[4];
+                    pv_philox4x32_10(rg.r0, rg.r1, (uint32_t)i, PV_RNG_AREA, rg.k0, rg.k1, aw);
+                    uc = pv_u32_to_float(aw[2]); ua = pv_u32_to_float(aw[0]); ub = pv_u32_to_float(aw[1]);
+                }
+                L = area_sample_L(sc, light, p, uc, ua, ub, &wo, &pdf, &vis);
+            } else L = light_sample_L_point(light, p, &wo, &pdf, &vis);
             if (!s_black(&L) && pdf > 0.f) {
                 if (st) st->shadow_rays++;
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
@@ -1189,13 +1203,19 @@ static void vli_one(const pv_scene_desc *sc, const pv_ray *ray, uint64_t ray_ind
             if (ln > nLights - 1) ln = nLights - 1;
             const pv_light *light = &sc->lights[ln];
             float pdf; visray vis; v3 wo;
-            spec L = light->type == PVO_LIGHT_SLOT
-                         ? (rng_mode == PVO_RNG_MT ? area_sample_L(sc, light, p, /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]):
-                                                                   the component number is the THIRD argument (core/light.h) */
-                                                                   lightNum[2 * (size_t)nSamples + 2 * i + 1], lightNum[nSamples + i],
-                                                                   lightNum[2 * (size_t)nSamples + 2 * i], &wo, &pdf, &vis)
-                                                   : (pdf = 0.f, s_const(0.f)))
-                         : light_sample_L_point(light, p, &wo, &pdf, &vis);
+            spec L;
+            if (IS_AREA_LIGHT(light)) {
+                /* LightSample(up0, up1, ucomp) is called as ls(lightComp, lightPos[0], lightPos[1]): the component number is the THIRD
+                 * argument (core/light.h).  Philox mode: words 0, 1 (position) and 2 (component) of the step's PV_RNG_AREA block */
+                float uc, ua, ub;
+                if (rng_mode == PVO_RNG_MT) { uc = lightNum[2 * (size_t)nSamples + 2 * i + 1]; ua = lightNum[nSamples + i]; ub = lightNum[2 * (size_t)nSamples + 2 * i]; }
+                else {
+                    uint32_t aw[4];
+                    pv_philox4x32_10(rg.r0, rg.r1, (uint32_t)i, PV_RNG_AREA, rg.k0, rg.k1, aw);
+                    uc = pv_u32_to_float(aw[2]); ua = pv_u32_to_float(aw[0]); ub = pv_u32_to_float(aw[1]);
+                }
+                L = area_sample_L(sc, light, p, uc, ua, ub, &wo, &pdf, &vis);
+            } else L = light_sample_L_point(light, p, &wo, &pdf, &vis);
             if (!s_black(&L) && pdf > 0.f) {
                 if (st) st->shadow_rays++;
                 if (!bvh_intersectp(sc, vis.o, vis.d, vis.mint, vis.maxt, NULL)) {
@@ -1640,7 +1660,7 @@ static void shoot_path(shoot_ctx *c, const halton6 *h, const distrib1d *ld, uint
     int lightNum = distrib_sample_discrete(ld, u[0], &lightPdf);
     const pv_light *light = &sc->lights[lightNum];
     ray_t photonRay; v3 Nl; float pdf;
-    spec Le = light->type == PVO_LIGHT_SLOT ? area_emit(sc, light, u[1], u[2], u[3], u[4], u[5], &photonRay, &Nl, &pdf)
+    spec Le = IS_AREA_LIGHT(light) ? area_emit(sc, light, u[1], u[2], u[3], u[4], u[5], &photonRay, &Nl, &pdf)
                                             : light_emit(sc, light, u[1], u[2], &photonRay, &Nl, &pdf);
     if (pdf == 0.f || s_black(&Le)) return;
     float ad = fabsf(vdot(Nl, photonRay.d));

@@ -380,3 +380,26 @@ def test_lambda_is_path_state_in_the_underflow_regime(golden):
     assert relerr(res["alpha"], g["shot_alpha"]).max() < 1e-5
     black = g["shot_alpha"].max(axis=1) == 0
     assert black.sum() == 15 and np.array_equal(res["alpha"].max(axis=1) == 0, black)
+
+
+def test_area_light_through_the_scene_description_is_the_same_light(golden, pkg):
+    """PV_LIGHT_AREA (include/pv.h: the light's triangles in pv_scene_desc::light_tris, attached by sceneio.attach_area_lights from
+    the harness's PVAREA01 file) must be the same light as the oracle's side table: the reference's single-scattering Li and its
+    photon list with an area light in the scene, bit for bit, through the ABI's own description."""
+    import os
+    from conftest import GOLDEN
+    g, _ = golden("volint")
+    scene = pkg.sceneio.attach_area_lights(pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_area.scn")), os.path.join(GOLDEN, "volint_area.lights"))
+    assert [l.type for l in scene.lights] == [pkg._abi.LIGHT_POINT, pkg._abi.LIGHT_AREA] and scene.light_tris.shape == (2, 9)
+    L, T, _ = O.volume_li(scene, g["rays"], 0.05, O.SINGLE, rng_mode=O.MT, mt_seed=4000)
+    assert np.array_equal(L, g["volint_area_single_L"]) and np.array_equal(T, g["volint_area_single_T"])
+    gc, _ = golden("cornell_area")
+    sc2 = pkg.sceneio.attach_area_lights(pkg.sceneio.read_scene(os.path.join(GOLDEN, "cornell_area.scn")), os.path.join(GOLDEN, "cornell_area.lights"))
+    res = O.shoot(sc2, int(gc["params"][3]), float(gc["params"][4]), float(gc["params"][2]), rng_mode=O.MT)
+    assert res["rc"] == 0 and res["nshot"] == int(gc["nshot"][0]) and np.array_equal(res["pos"], gc["shot_pos"])
+    # the Philox stream gives the area light's direct term other sample points, not another estimator: same mean over many rays
+    from cs348b_pbrt_b200 import scenes
+    rays = scenes.camera_rays(48, 48)
+    mt = np.mean([O.volume_li(scene, rays, 0.05, O.SINGLE, rng_mode=O.MT, mt_seed=s)[0].mean(dtype=np.float64) for s in range(1, 9)])
+    ph = np.mean([O.volume_li(scene, rays, 0.05, O.SINGLE, seed=s, rng_mode=O.PHILOX)[0].mean(dtype=np.float64) for s in range(1, 9)])
+    assert mt > 0 and abs(ph - mt) / mt < 0.02
