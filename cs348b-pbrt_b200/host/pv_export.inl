@@ -29,6 +29,7 @@ struct PvHostScene {
     std::vector<float> density;
     std::vector<uint32_t> prim_shape;          // PV_SHAPE_TRIANGLE or an index into spheres
     std::vector<pv_sphere> spheres;
+    std::vector<float> light_tris;             // triangles of the DiffuseAreaLights' ShapeSets (PV_LIGHT_AREA), 9 floats each
     pv_medium medium;
     bool has_medium;
     // empty when the device description holds the scene's materials exactly; else what was approximated (the all-maps photon
@@ -131,7 +132,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
         }
         hs.prim_material[i] = matIndex[m];
     }
-    hs.lights.clear();
+    hs.lights.clear(); hs.light_tris.clear();
     for (size_t i = 0; !medium_only && i < scene->lights.size(); ++i) {
         pv_light pl; memset(&pl, 0, sizeof(pl));
         Light *l = scene->lights[i];
@@ -151,8 +152,21 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
             pl.type = PV_LIGHT_DISTANT;
             pl.dir[0] = d->lightDir.x; pl.dir[1] = d->lightDir.y; pl.dir[2] = d->lightDir.z;
             pv_spec_out(d->L, pl.intensity);
+        } else if (DiffuseAreaLight *al = keep_unknown_lights ? NULL : dynamic_cast<DiffuseAreaLight *>(l)) {
+            // lights/diffuse.cpp:39-106: Lemit and the triangles of its ShapeSet in the ShapeSet's own (refine) order -- the order the
+            // area distribution samples by (core/light.cpp:114-137)
+            pl.type = PV_LIGHT_AREA;
+            pv_spec_out(al->Lemit, pl.intensity);
+            pl.area.first_tri = (uint32_t)(hs.light_tris.size() / 9); pl.area.n_tris = (uint32_t)al->shapeSet->shapes.size(); pl.area.flags = 0;
+            for (uint32_t k = 0; k < pl.area.n_tris; ++k) {
+                const Triangle *t = dynamic_cast<const Triangle *>(al->shapeSet->shapes[k].GetPtr());
+                if (!t) { err = "pv: an area light over a shape that is not a triangle mesh (triangle-mesh area lights are on this path)"; return false; }
+                pl.area.flags = (t->ReverseOrientation ? PV_AREA_REVERSE_ORIENTATION : 0u) | (t->TransformSwapsHandedness ? PV_AREA_SWAPS_HANDEDNESS : 0u);
+                for (int c = 0; c < 3; ++c) { const Point &q = t->mesh->p[t->v[c]]; hs.light_tris.push_back(q.x); hs.light_tris.push_back(q.y); hs.light_tris.push_back(q.z); }
+            }
+            if (dynamic_cast<RainbowVolume *>(scene->volumeRegion)) { err = "pv: an area light in a rainbow medium is not on this path"; return false; }
         } else if (keep_unknown_lights) pl.type = PV_LIGHT_UNKNOWN_SLOT;
-        else { err = "pv: unsupported light type (point, spot and distant lights are on this path)"; return false; }
+        else { err = "pv: unsupported light type (point, spot, distant and triangle-mesh area lights are on this path)"; return false; }
         hs.lights.push_back(pl);
     }
     hs.has_medium = false;
@@ -201,6 +215,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     d.world_bound[3] = wb.pMax.x; d.world_bound[4] = wb.pMax.y; d.world_bound[5] = wb.pMax.z;
     memcpy(d.cie_y, SampledSpectrum::Y.c, sizeof(d.cie_y));
     if (!hs.spheres.empty()) { d.prim_shape = hs.prim_shape.data(); d.spheres = hs.spheres.data(); d.n_spheres = (uint32_t)hs.spheres.size(); }
+    if (!hs.light_tris.empty()) { d.light_tris = hs.light_tris.data(); d.n_light_tris = (uint32_t)(hs.light_tris.size() / 9); }
     return true;
 }
 
@@ -209,7 +224,7 @@ static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
     FILE *f = fopen(fn.c_str(), "wb");
     if (!f) { perror(fn.c_str()); return false; }
     const pv_scene_desc &d = hs.desc;
-    uint32_t hdr[8] = {d.n_nodes, d.n_prims, d.n_materials, d.n_lights, hs.has_medium ? 1u : 0u, d.n_spheres, 0, 0};
+    uint32_t hdr[8] = {d.n_nodes, d.n_prims, d.n_materials, d.n_lights, hs.has_medium ? 1u : 0u, d.n_spheres, d.n_light_tris, 0};
     bool ok = fwrite("PVSCN001", 1, 8, f) == 8 && fwrite(hdr, 4, 8, f) == 8 && fwrite(d.world_bound, 4, 6, f) == 6 &&
               fwrite(d.cie_y, 4, PV_NSPEC, f) == PV_NSPEC;
     ok = ok && fwrite(hs.nodes.data(), sizeof(pv_bvh_node), hs.nodes.size(), f) == hs.nodes.size();
@@ -228,6 +243,7 @@ static bool pv_write_scene_file(const PvHostScene &hs, const std::string &fn) {
     if (ok && d.n_spheres)
         ok = fwrite(hs.prim_shape.data(), 4, hs.prim_shape.size(), f) == hs.prim_shape.size() &&
              fwrite(hs.spheres.data(), sizeof(pv_sphere), hs.spheres.size(), f) == hs.spheres.size();
+    if (ok && d.n_light_tris) ok = fwrite(hs.light_tris.data(), 4, hs.light_tris.size(), f) == hs.light_tris.size();
     fclose(f);
     if (!ok) fprintf(stderr, "pv: short write on %s\n", fn.c_str());
     else fprintf(stderr, "[pv] exported scene: %u nodes, %u prims, %u materials, %u lights -> %s\n", d.n_nodes, d.n_prims, d.n_materials,

@@ -60,6 +60,7 @@
 #include "lights/point.h"
 #include "lights/spot.h"
 #include "lights/distant.h"
+#include "lights/diffuse.h"
 #include "volumes/homogeneous.h"
 #include "volumes/volumegrid.h"
 #include "volumes/exponential.h"

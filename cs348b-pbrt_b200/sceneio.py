@@ -3,7 +3,8 @@
 PVSCN001  flattened scene exported from the reference's host objects
           (LinearBVHNode[], triangle table, materials, lights, medium [+ grid],
           optional sphere table: header word 5 = sphere count, prim_shape[] and
-          pv_sphere[] appended at the end of the file)
+          pv_sphere[] appended at the end of the file; header word 6 = number of
+          area-light triangles, 9 floats each after that)
 PVPHOT01  photon set: n x {p.xyz, wi.xyz, alpha[30]}  (core/photonshooter.h:20-27
           minus the fork's unused lambda/intensity)
 PVRAY001  rays: n x pv_ray (40 B)
@@ -105,7 +106,7 @@ def read_scene(path):
         raise ValueError("not a PVSCN001 file: %s" % path)
     off = 8
     hdr = struct.unpack_from("<8I", buf, off); off += 32
-    n_nodes, n_prims, n_mat, n_lights, has_medium, n_spheres = hdr[:6]
+    n_nodes, n_prims, n_mat, n_lights, has_medium, n_spheres, n_light_tris = hdr[:7]
     s = Scene()
     s.world_bound = np.frombuffer(buf, dtype=np.float32, count=6, offset=off).copy(); off += 24
     s.cie_y = np.frombuffer(buf, dtype=np.float32, count=A.NSPEC, offset=off).copy(); off += 4 * A.NSPEC
@@ -134,13 +135,16 @@ def read_scene(path):
     if n_spheres:
         s.prim_shape = np.frombuffer(buf, dtype=np.uint32, count=n_prims, offset=off).copy(); off += 4 * n_prims
         s.spheres = (A.Sphere * n_spheres).from_buffer_copy(buf, off); off += C.sizeof(A.Sphere) * n_spheres
+    if n_light_tris:
+        s.light_tris = np.frombuffer(buf, dtype=np.float32, count=9 * n_light_tris, offset=off).reshape(-1, 9).copy(); off += 36 * n_light_tris
     return s
 
 
 def write_scene(path, s):
     with open(path, "wb") as f:
         f.write(b"PVSCN001")
-        f.write(struct.pack("<8I", s.n_nodes, s.n_prims, len(s.materials), len(s.lights), 1 if s.medium is not None else 0, len(s.spheres), 0, 0))
+        f.write(struct.pack("<8I", s.n_nodes, s.n_prims, len(s.materials), len(s.lights), 1 if s.medium is not None else 0, len(s.spheres),
+                            0 if s.light_tris is None else len(np.asarray(s.light_tris).reshape(-1, 9)), 0))
         f.write(np.asarray(s.world_bound, dtype=np.float32).tobytes())
         f.write(np.asarray(s.cie_y, dtype=np.float32).tobytes())
         f.write(np.asarray(s.nodes, dtype=np.uint8).tobytes())
@@ -157,6 +161,8 @@ def write_scene(path, s):
                 f.write(np.asarray(s.density, dtype=np.float32).tobytes())
         if len(s.spheres):
             f.write(np.asarray(s.prim_shape, dtype=np.uint32).tobytes()); f.write(bytes(s.spheres))
+        if s.light_tris is not None and len(s.light_tris):
+            f.write(np.asarray(s.light_tris, dtype=np.float32).tobytes())
 
 
 def _hdr(magic, n):

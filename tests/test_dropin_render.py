@@ -7,7 +7,7 @@ THE WHOLE-IMAGE TOLERANCE (one rule for every scene).  Photon paths and the stoc
 the two sides (MT19937 per task vs keyed Philox), so a render can only agree with the reference's as well as the reference agrees
 with ITSELF on other streams.  That spread is measured, per scene, from three more reference renders with other task counts
 (`--ncores 2, 3, 5`: the reference seeds its RNGs and scrambles its samples per task; tests/golden/make_ref2.py writes their
-distances from the primary render to tests/golden/ref_spread.json and keeps the --ncores 3 image as <name>_ref2.npy).  With
+distances from the primary render to tests/golden/ref_spread.json).  With
     e_mean(a, b)  = |mean luminance(a) - mean luminance(b)| / mean luminance(b)
     e_block(a, b) = mean over lit 6x6 blocks of |block mean(a) - block mean(b)| / block mean(b)      (lit: >= 5 % of the mean block)
 and spread_x = the LARGEST e_x(reference run, primary reference render) over those runs, a drop-in render passes iff
@@ -132,7 +132,7 @@ def test_dropin_renders_config1_verbatim(tmp_path):
     copy of that data file is tests/scenes/volumescene_png.pbrt): photonmap surface integrator with final gathering, photonvolume
     integrator, rainbow medium, distant light, 300 x 300, written as PNG by the reference's own film (gamma 2.2, 8 bit).  Compared,
     after undoing the gamma, with the PNG the unmodified reference wrote from the same file (tests/golden/volumescene_png_ref.png;
-    _ref2.png = its second run on other streams)."""
+    the reference's own spread on this file is in ref_spread.json)."""
     scene = os.path.join(ROOT, "tests", "scenes", "volumescene_png.pbrt")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -166,3 +166,15 @@ def test_dropin_renders_single_and_emission_scenes_like_the_reference(tmp_path, 
     assert out.returncode == 0, out.stderr[-2000:]
     assert label in out.stderr and "batched device calls" in out.stderr       # pv_volume_li ran for camera AND secondary rays
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
+
+
+@needs_bin
+def test_dropin_renders_a_scene_with_an_area_light(tmp_path):
+    """A DiffuseAreaLight (quad under the ceiling) next to the point light, photonvolume integrator, 20 k photons, 64 x 64: the
+    exporter hands the light down as PV_LIGHT_AREA, photons are emitted from it on the device and the direct term of Li samples it
+    (the surface integrator's own area-light code stays the reference's)."""
+    scene = os.path.join(ROOT, "tests", "scenes", "cornell_area_e2e.pbrt")
+    out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[pv] shot" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
+    assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, "cornell_area_e2e.pfm")), golden_ref("cornell_area_e2e"), "cornell_area_e2e")
