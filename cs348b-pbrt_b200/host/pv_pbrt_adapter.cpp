@@ -718,12 +718,13 @@ void SamplerRenderer::Render(const Scene *scene) {
     if (g_pv.ready && pvi && pmi && pmi->finalGather && pmi->photonShooter && pmi->photonShooter->indirectMap && pmi->photonShooter->radianceMap &&
         !g_pv.rad_pos.empty() &&
         g_pv.n_indirect >= 50 && !(fg_mode && !strcmp(fg_mode, "cpu")) && !visualizeObjectIds) {
-        PhotonShooter *bare = (PhotonShooter *)malloc(sizeof(PhotonShooter));       // shallow clones, never destroyed (they own nothing)
-        memcpy((void *)bare, (const void *)pmi->photonShooter, sizeof(PhotonShooter));
+        // member-wise copies made by the classes' own (implicit) copy constructors: a shooter that shows no indirect map, and an
+        // integrator that looks at it.  They share the maps with the originals and are never destroyed (their destructors would
+        // delete those maps a second time).
+        PhotonShooter *bare = new PhotonShooter(*pmi->photonShooter);
         bare->indirectMap = NULL;
         fg.full = pmi;
-        fg.primary = (PhotonIntegrator *)malloc(sizeof(PhotonIntegrator));
-        memcpy((void *)fg.primary, (const void *)pmi, sizeof(PhotonIntegrator));
+        fg.primary = new PhotonIntegrator(*pmi);
         fg.primary->photonShooter = bare;
         fg.rays.resize(nTasks);
         if (!g_pv.fg_ctx) {

@@ -33,8 +33,12 @@ def test_single_scattering_li_with_an_area_light_vs_oracle(golden, pkg, pv_facto
         L, T = pv.VolumeLi("single", rays, ray_index_base=base)
         oL, oT, st = O.volume_li(scene, rays, 0.05, O.SINGLE, seed=0xA2EA, ray_index_base=base)
         assert st.shadow_rays > 0
-        lit = oL > 1e-6 * oL.max()
-        assert lit.any() and relerr(L, oL)[lit].max() < 1e-4 and np.abs(T - oT).max() < 1e-5
+        # (edge rays: a sample point in the plane of the light, or the sampled point itself, makes ShapeSet::Pdf 0/0 -- the
+        # reference's own arithmetic, reproduced by the oracle under either stream; such rays are compared for being the same rays)
+        fin = np.isfinite(oL).all(axis=1)
+        assert fin.sum() >= 0.9 * len(rays) and np.array_equal(np.isfinite(L).all(axis=1), fin)
+        lit = (oL > 1e-6 * oL[fin].max()) & fin[:, None]
+        assert lit.any() and relerr(L, oL)[lit].max() < 1e-4 and np.abs(T - oT)[fin].max() < 1e-5
     # the area light contributes: without it (its slot dark) the radiance is visibly lower
     dark = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_area.scn"))
     dL, _, _ = O.volume_li(dark, g["rays"], 0.05, O.SINGLE, seed=0xA2EA, ray_index_base=11)
