@@ -373,6 +373,7 @@ def main():
         torch.cuda.synchronize()
         gather_wall_ms = (time.perf_counter() - t0) * 1e3
         gather_dev_ms = pv.last_kernel_ms() + pv.last_march_ms()
+        gather_phases = dict(zip(("step_sort", "cellgather_kernel", "overflow_pass", "recurrence"), pv.last_phase_ms())); gather_phases["march_kernels"] = pv.last_march_ms()
         barrier()
         frame_wall = time.perf_counter() - t_frame
         vals = torch.tensor([shoot["device_s"] * 1e3, wall * 1e3, build_ms, gather_dev_ms, gather_wall_ms, frame_wall * 1e3], dtype=torch.float64, device=dev)
@@ -382,7 +383,7 @@ def main():
         frame = {"what": "ONE frame end to end at full size, max over ranks: shoot %d photons (sharded by 4096-path block) -> all-gather -> grid build -> "
                          "gather of the frame's camera rays against the map just shot" % shoot["photons"],
                  "shoot_device_ms": v[0], "shoot_wall_ms": v[1], "allgather": ag, "build_wall_ms": v[2], "gather_device_ms": v[3],
-                 "gather_wall_ms": v[4], "frame_wall_ms": v[5], "gather_L_finite": bool(torch.isfinite(d_L).all().item()),
+                 "gather_wall_ms": v[4], "gather_phase_ms_rank0": gather_phases, "frame_wall_ms": v[5], "gather_L_finite": bool(torch.isfinite(d_L).all().item()),
                  "gather_L_sum": float(d_L.sum().item())}
 
         # the same pass with the SURFACE maps on (pv_shoot_maps + pv_radiance_photons): every photon class of

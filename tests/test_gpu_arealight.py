@@ -43,7 +43,7 @@ def test_single_scattering_li_with_an_area_light_vs_oracle(golden, pkg, pv_facto
     dark = pkg.sceneio.read_scene(os.path.join(GOLDEN, "volint_area.scn"))
     dL, _, _ = O.volume_li(dark, g["rays"], 0.05, O.SINGLE, seed=0xA2EA, ray_index_base=11)
     L, _ = pv.VolumeLi("single", g["rays"], ray_index_base=11)
-    assert L.sum() > 1.05 * dL.sum()
+    assert L.sum() > 1.02 * dL.sum() and (np.abs(L - dL) > 1e-3 * dL.max()).any(axis=1).mean() > 0.3
 
 
 def test_shooter_and_gather_with_an_area_light_vs_oracle(golden, pkg, pv_factory):

@@ -3,7 +3,7 @@
 # SWEEP=1), the drop-in binary with PV_DEVICES over all N devices, BASELINE config 5 (128 M photons, 3840x2160) at N.
 cd /root/repo
 N=${1:-8}
-for n in $( [ -n "$SWEEP" ] && echo "1 2 4 $N" | tr ' ' '\n' | awk -v N=$N '$1<=N' | sort -nu | tr '\n' ' ' || echo $N ); do
+for n in $( [ -n "$SWEEP" ] && echo "2 4 $N" | tr ' ' '\n' | awk -v N=$N '$1<=N' | sort -nu | tr '\n' ' ' || echo $N ); do
   if [ "$n" = 1 ]; then python bench.py --no-cpu-baseline > gpurun_out/r02_scale_n1.log 2>&1
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n > gpurun_out/r02_scale_n$n.log 2>&1; fi
   python - $n <<'PY'
