@@ -325,7 +325,7 @@ def main():
                 "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": target}}
 
     # ------------------------------------------------------------------ rays of this rank (image tiles dealt round-robin)
-    rays, order = W.frame_rays(cfg, rank, world)
+    rays, order = W.frame_rays(cfg, rank, world, density=scene.density)
     n_local = len(rays)
     n_total = cfg["xres"] * cfg["yres"]
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)
