@@ -26,6 +26,20 @@
 
 enum { WS_NEW = 0, WS_TRACE = 1, WS_MARCHING = 2, WS_HIT = 3, WS_MISS = 4, WS_POP = 5, WS_IDLE = 6 };
 #define WF_F4 13                       // float4s of a frame: o|mint, d|maxt, ip|ieps, inn|prim, idpdu|(nI, spec, loop_i), 8 x alpha
+// Where float4 k of slot `slot` lives in a frame array of P slots.  Frames are RECORDS (AoS, 14 float4 = 224 B = seven 32-byte
+// sectors each): the event kernel reads and writes whole frames of slots in queue order, i.e. at random, and a 16-byte access into
+// a plane per component (SoA) moved a 32-byte sector for every 16 bytes used -- 5.2 GB of DRAM traffic per generation of 4 M slots.
+// The slot-parallel kernels read o|mint + d|maxt (one sector) and write ip..idpdu (two and a half).
+#ifndef WF_FRAME_SOA
+#define WF_FRAME_SOA 0
+#endif
+#define WF_STRIDE 14
+#if WF_FRAME_SOA
+#define WF_AT(P, slot, k) ((size_t)(k) * (size_t)(P) + (slot))
+#else
+#define WF_AT(P, slot, k) ((size_t)(slot) * WF_STRIDE + (k))
+#endif
+#define WF_FRAME_F4S(P) ((size_t)WF_STRIDE * (size_t)(P))      // float4s of a frame array of P slots
 #define WF_THREADS 128
 #define WF_FAST_LEVELS 4                // stack levels every slot owns; deeper ones (a path scattering again and again) come out of a page pool
 #ifndef WF_EVENT_MIN_CTAS
@@ -41,8 +55,8 @@ enum { WS_NEW = 0, WS_TRACE = 1, WS_MARCHING = 2, WS_HIT = 3, WS_MISS = 4, WS_PO
 struct WaveState {
     uint32_t P;
     uint32_t volume_only;              // the surface maps are off: a diffuse bounce ends the path (Q6), nothing but volume photons is stored
-    float4 *frame;                     // [WF_F4][P]
-    float4 *stack;                     // [WF_FAST_LEVELS][WF_F4][P]: the first levels of every slot's continuation stack
+    float4 *frame;                     // P frames, float4 k of slot s at WF_AT(P, s, k)
+    float4 *stack;                     // [WF_FAST_LEVELS] frame arrays: the first levels of every slot's continuation stack
     float4 *deep;                      // [deep_pages][SH_MAXDEPTH - WF_FAST_LEVELS][WF_F4]: the levels above, one page per slot that ever needs them
     uint32_t *deep_page;               // [P] page of the slot (~0 = none yet); pages are handed out by a bump counter and kept for the whole wave
     uint32_t deep_pages;
@@ -59,29 +73,29 @@ struct WaveState {
 
 __device__ __forceinline__ uint32_t pack_meta(int nI, int spec, int loop_i) { return (uint32_t)nI | ((uint32_t)spec << 20) | ((uint32_t)(loop_i + 1) << 24); }
 __device__ __forceinline__ void frame_store(float4 *base, uint32_t P, uint32_t slot, const Frame &f) {
-    base[0 * (size_t)P + slot] = make_float4(f.o[0], f.o[1], f.o[2], f.mint);
-    base[1 * (size_t)P + slot] = make_float4(f.d[0], f.d[1], f.d[2], f.maxt);
-    base[2 * (size_t)P + slot] = make_float4(f.ip[0], f.ip[1], f.ip[2], f.ieps);
-    base[3 * (size_t)P + slot] = make_float4(f.inn[0], f.inn[1], f.inn[2], __int_as_float(f.prim));
-    base[4 * (size_t)P + slot] = make_float4(f.idpdu[0], f.idpdu[1], f.idpdu[2], __uint_as_float(pack_meta(f.nI, f.spec, f.loop_i)));
+    base[WF_AT(P, slot, 0)] = make_float4(f.o[0], f.o[1], f.o[2], f.mint);
+    base[WF_AT(P, slot, 1)] = make_float4(f.d[0], f.d[1], f.d[2], f.maxt);
+    base[WF_AT(P, slot, 2)] = make_float4(f.ip[0], f.ip[1], f.ip[2], f.ieps);
+    base[WF_AT(P, slot, 3)] = make_float4(f.inn[0], f.inn[1], f.inn[2], __int_as_float(f.prim));
+    base[WF_AT(P, slot, 4)] = make_float4(f.idpdu[0], f.idpdu[1], f.idpdu[2], __uint_as_float(pack_meta(f.nI, f.spec, f.loop_i)));
 #pragma unroll 1
-    for (int q = 0; q < 7; ++q) base[(5 + q) * (size_t)P + slot] = make_float4(f.alpha[4 * q], f.alpha[4 * q + 1], f.alpha[4 * q + 2], f.alpha[4 * q + 3]);
-    base[12 * (size_t)P + slot] = make_float4(f.alpha[28], f.alpha[29], 0.f, 0.f);
+    for (int q = 0; q < 7; ++q) base[WF_AT(P, slot, 5 + q)] = make_float4(f.alpha[4 * q], f.alpha[4 * q + 1], f.alpha[4 * q + 2], f.alpha[4 * q + 3]);
+    base[WF_AT(P, slot, 12)] = make_float4(f.alpha[28], f.alpha[29], 0.f, 0.f);
 }
 // spec bit 2 of a slot's CURRENT frame (never of a stacked one): alpha is still the emission weight Le * |cos| / (pdf * lightPdf)
 // (photonshooter.cpp:262-264), which the slot does not store -- float4 12 holds {|cos|, pdf * lightPdf, spot falloff, light number}
 // and wf_event_kernel re-makes the 30 bins from the light's spectrum when it first needs them (most paths end without)
 #define WF_SPEC_PRISTINE 4
 __device__ __forceinline__ void frame_load(const float4 *base, uint32_t P, uint32_t slot, Frame &f, const DevScene *sc = nullptr) {
-    float4 v = base[0 * (size_t)P + slot]; f.o[0] = v.x; f.o[1] = v.y; f.o[2] = v.z; f.mint = v.w;
-    v = base[1 * (size_t)P + slot]; f.d[0] = v.x; f.d[1] = v.y; f.d[2] = v.z; f.maxt = v.w;
-    v = base[2 * (size_t)P + slot]; f.ip[0] = v.x; f.ip[1] = v.y; f.ip[2] = v.z; f.ieps = v.w;
-    v = base[3 * (size_t)P + slot]; f.inn[0] = v.x; f.inn[1] = v.y; f.inn[2] = v.z; f.prim = __float_as_int(v.w);
-    v = base[4 * (size_t)P + slot]; f.idpdu[0] = v.x; f.idpdu[1] = v.y; f.idpdu[2] = v.z;
+    float4 v = base[WF_AT(P, slot, 0)]; f.o[0] = v.x; f.o[1] = v.y; f.o[2] = v.z; f.mint = v.w;
+    v = base[WF_AT(P, slot, 1)]; f.d[0] = v.x; f.d[1] = v.y; f.d[2] = v.z; f.maxt = v.w;
+    v = base[WF_AT(P, slot, 2)]; f.ip[0] = v.x; f.ip[1] = v.y; f.ip[2] = v.z; f.ieps = v.w;
+    v = base[WF_AT(P, slot, 3)]; f.inn[0] = v.x; f.inn[1] = v.y; f.inn[2] = v.z; f.prim = __float_as_int(v.w);
+    v = base[WF_AT(P, slot, 4)]; f.idpdu[0] = v.x; f.idpdu[1] = v.y; f.idpdu[2] = v.z;
     const uint32_t m = __float_as_uint(v.w);
     f.nI = (int)(m & 0xfffffu); f.spec = (int)((m >> 20) & 0xfu); f.loop_i = (int)(m >> 24) - 1;
     if (sc && (f.spec & WF_SPEC_PRISTINE)) {
-        v = base[12 * (size_t)P + slot];
+        v = base[WF_AT(P, slot, 12)];
         const pv_light &l = sc->lights[__float_as_uint(v.w)];
         const float ad = v.x, den = v.y, scale = v.z;
         const bool spot = l.type == PV_LIGHT_SPOT;
@@ -91,8 +105,8 @@ __device__ __forceinline__ void frame_load(const float4 *base, uint32_t P, uint3
         return;
     }
 #pragma unroll 1
-    for (int q = 0; q < 7; ++q) { v = base[(5 + q) * (size_t)P + slot]; f.alpha[4 * q] = v.x; f.alpha[4 * q + 1] = v.y; f.alpha[4 * q + 2] = v.z; f.alpha[4 * q + 3] = v.w; }
-    v = base[12 * (size_t)P + slot]; f.alpha[28] = v.x; f.alpha[29] = v.y;
+    for (int q = 0; q < 7; ++q) { v = base[WF_AT(P, slot, 5 + q)]; f.alpha[4 * q] = v.x; f.alpha[4 * q + 1] = v.y; f.alpha[4 * q + 2] = v.z; f.alpha[4 * q + 3] = v.w; }
+    v = base[WF_AT(P, slot, 12)]; f.alpha[28] = v.x; f.alpha[29] = v.y;
 }
 __device__ __forceinline__ void rng_store(const WaveState &w, uint32_t slot, const PathRng &r) {
     w.rng_buf[slot] = make_uint4(r.buf[0], r.buf[1], r.buf[2], r.buf[3]);
@@ -233,9 +247,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(ShootArgs a, WaveS
             }
         }
     } else if (st == WS_TRACE) {
-        const float4 f0 = w.frame[slot], f1 = w.frame[(size_t)w.P + slot];
+        const float4 f0 = w.frame[WF_AT(w.P, slot, 0)], f1 = w.frame[WF_AT(w.P, slot, 1)];
         o = V3(f0.x, f0.y, f0.z); mint = f0.w; d = V3(f1.x, f1.y, f1.z); maxt = f1.w;
-        const uint32_t m = __float_as_uint(w.frame[4 * (size_t)w.P + slot].w);
+        const uint32_t m = __float_as_uint(w.frame[WF_AT(w.P, slot, 4)].w);
         nI = (int)(m & 0xfffffu); spec = (int)((m >> 20) & 0xfu);
         path = w.path[slot];
         sp = w.misc[slot].y;
@@ -288,17 +302,17 @@ __global__ void __launch_bounds__(WF_THREADS) wf_trace_kernel(ShootArgs a, WaveS
                 }
             } else if (dies) ns = WS_NEW;
             if (ns != WS_NEW) {
-                w.frame[2 * (size_t)w.P + slot] = make_float4(hp.x, hp.y, hp.z, eps);
-                w.frame[3 * (size_t)w.P + slot] = make_float4(nn.x, nn.y, nn.z, __int_as_float(prim));
-                w.frame[4 * (size_t)w.P + slot] = make_float4(dpdu.x, dpdu.y, dpdu.z, __uint_as_float(pack_meta(nI, spec, -1)));
+                w.frame[WF_AT(w.P, slot, 2)] = make_float4(hp.x, hp.y, hp.z, eps);
+                w.frame[WF_AT(w.P, slot, 3)] = make_float4(nn.x, nn.y, nn.z, __int_as_float(prim));
+                w.frame[WF_AT(w.P, slot, 4)] = make_float4(dpdu.x, dpdu.y, dpdu.z, __uint_as_float(pack_meta(nI, spec, -1)));
             }
         } else if (sp == 0) ns = WS_NEW;                                    // left the scene, nothing to resume: the path is over
         if (ns != WS_NEW) {
             if (fresh || prim >= 0) {
-                w.frame[slot] = make_float4(o.x, o.y, o.z, mint);
-                w.frame[(size_t)w.P + slot] = make_float4(d.x, d.y, d.z, maxt);
+                w.frame[WF_AT(w.P, slot, 0)] = make_float4(o.x, o.y, o.z, mint);
+                w.frame[WF_AT(w.P, slot, 1)] = make_float4(d.x, d.y, d.z, maxt);
             }
-            if (fresh) w.frame[12 * (size_t)w.P + slot] = em;
+            if (fresh) w.frame[WF_AT(w.P, slot, 12)] = em;
             rng_store(w, slot, rng);
             if (ns != WS_MARCHING) event_push(w, slot);
         }
@@ -473,7 +487,7 @@ __global__ void __launch_bounds__(WF_MARCH_THREADS, WF_MARCH_MIN_CTAS) wf_march_
             if (qi >= n_q) { ms = MS_DONE; continue; }
             slot = w.queue[qi];
             dies = (slot >> 31) != 0; slot &= 0x7fffffffu;
-            const float4 f0 = w.frame[slot], f1 = w.frame[(size_t)w.P + slot], m = w.march[slot];
+            const float4 f0 = w.frame[WF_AT(w.P, slot, 0)], f1 = w.frame[WF_AT(w.P, slot, 1)], m = w.march[slot];
             o = V3(f0.x, f0.y, f0.z);
             const v3 d = V3(f1.x, f1.y, f1.z);
             const v3 rnd = vdiv(d, vlen(d));
@@ -513,20 +527,20 @@ __global__ void __launch_bounds__(WF_MARCH_THREADS, WF_MARCH_MIN_CTAS) wf_march_
 // live in a page the slot takes from a pool the first time it gets that deep.  Returns false when the pool is empty: the frame is
 // dropped, ctr[7] is raised and the host replays the (deterministic) wave with a larger pool.
 __device__ __forceinline__ bool stack_store(const WaveState &w, uint32_t slot, int sp, const Frame &f) {
-    if (sp < WF_FAST_LEVELS) { frame_store(w.stack + (size_t)sp * WF_F4 * w.P, w.P, slot, f); return true; }
+    if (sp < WF_FAST_LEVELS) { frame_store(w.stack + (size_t)sp * WF_FRAME_F4S(w.P), w.P, slot, f); return true; }
     uint32_t page = w.deep_page[slot];
     if (page == 0xffffffffu) {
         page = atomicAdd(&w.ctr[6], 1u);
         if (page >= w.deep_pages) { w.ctr[7] = 1u; return false; }
         w.deep_page[slot] = page;
     }
-    frame_store(w.deep + ((size_t)page * (SH_MAXDEPTH - WF_FAST_LEVELS) + (size_t)(sp - WF_FAST_LEVELS)) * WF_F4, 1u, 0u, f);
+    frame_store(w.deep + ((size_t)page * (SH_MAXDEPTH - WF_FAST_LEVELS) + (size_t)(sp - WF_FAST_LEVELS)) * WF_STRIDE, 1u, 0u, f);
     return true;
 }
 __device__ __forceinline__ void stack_load(const WaveState &w, uint32_t slot, int sp, Frame &f) {
-    if (sp < WF_FAST_LEVELS) { frame_load(w.stack + (size_t)sp * WF_F4 * w.P, w.P, slot, f); return; }
+    if (sp < WF_FAST_LEVELS) { frame_load(w.stack + (size_t)sp * WF_FRAME_F4S(w.P), w.P, slot, f); return; }
     const uint32_t page = w.deep_page[slot];
-    frame_load(w.deep + ((size_t)page * (SH_MAXDEPTH - WF_FAST_LEVELS) + (size_t)(sp - WF_FAST_LEVELS)) * WF_F4, 1u, 0u, f);
+    frame_load(w.deep + ((size_t)page * (SH_MAXDEPTH - WF_FAST_LEVELS) + (size_t)(sp - WF_FAST_LEVELS)) * WF_STRIDE, 1u, 0u, f);
 }
 
 template <class MV>
@@ -832,7 +846,7 @@ int pvi_wavefront_run(pv_ctx *ctx, const ShootArgs &a, bool surf, int kind, bool
     // carve the slot arrays out of one allocation
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_frame = take(sizeof(float4) * WF_F4 * (size_t)P), o_stack = take(sizeof(float4) * WF_F4 * (size_t)P * WF_FAST_LEVELS),
+    const size_t o_frame = take(sizeof(float4) * WF_FRAME_F4S(P)), o_stack = take(sizeof(float4) * WF_FRAME_F4S(P) * WF_FAST_LEVELS),
                  o_state = take(4 * (size_t)P), o_path = take(8 * (size_t)P), o_rb = take(16 * (size_t)P), o_rj = take(4 * (size_t)P),
                  o_misc = take(8 * (size_t)P), o_march = take(16 * (size_t)P), o_queue = take(4 * (size_t)P), o_equeue = take(8 * (size_t)P), o_ctr = take(64), o_dpage = take(4 * (size_t)P);
     uint64_t floor_pages = P / 16;
@@ -842,7 +856,7 @@ int pvi_wavefront_run(pv_ctx *ctx, const ShootArgs &a, bool surf, int kind, bool
     }
     if (ctx->wf_deep_pages == 0) ctx->wf_deep_pages = 4096;
     const uint32_t deep_pages = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ctx->wf_deep_pages, floor_pages), P);
-    const size_t o_deep = take(sizeof(float4) * WF_F4 * (size_t)(SH_MAXDEPTH - WF_FAST_LEVELS) * deep_pages);
+    const size_t o_deep = take(sizeof(float4) * WF_STRIDE * (size_t)(SH_MAXDEPTH - WF_FAST_LEVELS) * deep_pages);
     int rc = pv_ensure(ctx, &ctx->wf, &ctx->wf_bytes, off); if (rc) return rc;
     char *b = (char *)ctx->wf;
     WaveState w;

@@ -216,21 +216,20 @@ def test_shooter_vs_oracle_same_philox_stream(golden, pv_factory, name, wanted, 
     assert ref["rc"] == 0
     assert st.paths == ref["nshot"]
     assert st.stack_overflows == 0
-    # one-to-one on ids; libm differences may flip a handful of discrete decisions
-    common, ia, ib = np.intersect1d(ids, ref["ids"], return_indices=True)
-    assert len(common) >= 0.995 * max(len(ids), len(ref["ids"]))
-    assert abs(len(ids) - len(ref["ids"])) <= 0.005 * len(ref["ids"]) + 2
-    dpos = np.abs(pos[ia] - ref["pos"][ib]).max(axis=1)
-    assert np.quantile(dpos, 0.99) < 1e-4
-    ok = dpos < 1e-4
-    e = relerr(alpha[ia][ok], ref["alpha"][ib][ok]).max(axis=1)
+    # one to one on ids.  Measured (tools/shoot_mismatch.py, all eight scenes): the id lists are IDENTICAL, positions agree to 3e-6
+    # (3e-5 on the spheres), weights to 1e-6 -- libm vs CUDA differences (sincosf, expf, acosf) are there but flip no decision on
+    # these streams.  The bars are those measurements with a margin, not a statistical allowance.
+    assert np.array_equal(ids, ref["ids"])
+    dpos = np.abs(pos - ref["pos"]).max(axis=1)
+    assert dpos.max() < 1e-4 and np.quantile(dpos, 0.99) < 5e-6
+    e = relerr(alpha, ref["alpha"]).max(axis=1)
     if name.startswith("sphere"):
         # curved glass: the normal comes out of acosf / sinf / atan2f (libm vs CUDA, last-ulp differences), and the Fresnel term
         # has a square-root singularity at the critical angle that internal reflections in the ball do reach -- a 1e-7 change
-        # of the normal moves F by ~sqrt(1e-7) there.  Nearly all photons agree to 1e-3, the rest to a few per cent.
-        assert np.quantile(e, 0.99) < 1e-3 and e.max() < 5e-2, (np.quantile(e, 0.99), e.max())
+        # of the normal moves F by ~sqrt(1e-7) there.  99 % of the photons agree to 1e-5, the worst to 1.5 per cent.
+        assert np.quantile(e, 0.99) < 1e-5 and e.max() < 5e-2, (np.quantile(e, 0.99), e.max())
     else:
-        assert e.max() < 1e-3
+        assert e.max() < 1e-5
     assert np.all(np.diff(ids.astype(np.int64)) > 0)        # deterministic order: sorted by (path, ordinal)
 
 
@@ -248,14 +247,12 @@ def test_shooter_lambda_is_path_state_in_the_underflow_regime(golden, pv_factory
     assert ref["rc"] == 0 and st.paths == ref["nshot"] and st.stack_overflows == 0
     black_ref = ref["alpha"].max(axis=1) == 0
     assert black_ref.sum() >= 5                                  # the regime is reached
-    common, ia, ib = np.intersect1d(ids, ref["ids"], return_indices=True)
-    assert len(common) >= 0.995 * max(len(ids), len(ref["ids"]))
-    assert abs(len(ids) - len(ref["ids"])) <= 0.005 * len(ref["ids"]) + 2
-    assert np.quantile(np.abs(pos[ia] - ref["pos"][ib]).max(axis=1), 0.99) < 1e-4
-    # the same photons are black on both sides (a path that was re-split or cut short would change the id list long before)
-    bg = alpha[ia].max(axis=1) == 0
-    assert (bg != black_ref[ib]).sum() <= 2
-    assert bg.sum() >= 5
+    assert np.array_equal(ids, ref["ids"])                       # identical id lists (measured; a re-split or cut-short path would change them)
+    assert np.abs(pos - ref["pos"]).max() < 1e-5
+    assert relerr(alpha, ref["alpha"], floor=1e-38).max() < 1e-4
+    # the same photons are black on both sides
+    bg = alpha.max(axis=1) == 0
+    assert np.array_equal(bg, black_ref) and bg.sum() >= 5
 
 
 def test_shooter_sharded_blocks_reproduce_single_rank(golden, pv_factory, pkg):
