@@ -347,6 +347,8 @@ def main():
         shoot_pass(min(target, 20000 * world), 8 * world)                                       # untimed: module load, local-memory reservation
         if dist is not None:
             pv.allgather_photons()                                                              # untimed: the communicator's first collective
+        pv.build(); pv.Li_dev(d_rays, n_local, d_L, d_T)                                        # untimed: the gather's step / L_ii / sort buffers (about 10 GB of cudaMalloc for a 1080p frame,
+                                                                                                # 3-190 ms depending on the driver's mood) exist before the frame is timed, as in a renderer's second frame
         barrier()
         t_frame = time.perf_counter()
         st, last, wall = shoot_pass(target, 64 * world)
