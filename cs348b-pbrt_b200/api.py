@@ -273,6 +273,20 @@ class PhotonVolume:
         self._chk(self.lib.pv_gather(self.ctx, _vp(rays), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
         return L, T
 
+    def LiIndexed(self, rays, ray_index, flags=0, integrator=None):
+        """pv_gather_indexed / pv_volume_li_indexed: ray i draws from the stream ray_index[i]."""
+        rays = np.ascontiguousarray(rays); n = len(rays)
+        idx = np.ascontiguousarray(ray_index, dtype=np.uint64)
+        assert len(idx) == n
+        L = np.zeros((n, A.NSPEC), np.float32); T = np.zeros((n, A.NSPEC), np.float32)
+        prm = self.gather_params(0, flags)
+        if integrator is None:
+            self._chk(self.lib.pv_gather_indexed(self.ctx, _vp(rays), _vp(idx), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
+        else:
+            kind = {"single": A.VOLINT_SINGLE, "emission": A.VOLINT_EMISSION}[integrator]
+            self._chk(self.lib.pv_volume_li_indexed(self.ctx, C.c_int(kind), _vp(rays), _vp(idx), C.c_uint64(n), C.byref(prm), _vp(L), _vp(T)))
+        return L, T
+
     def VolumeLi(self, integrator, rays, ray_index_base=0, flags=0):
         """SingleScatteringIntegrator::Li / EmissionIntegrator::Li (integrators/single.cpp:66-138, emission.cpp:63-106):
         integrator = "single" | "emission"; uses this object's stepsize and seed, no photon map."""

@@ -65,7 +65,7 @@ void pv_destroy(pv_ctx *ctx) {
     pvi_comm_destroy(ctx);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags, ctx->d_ltris, ctx->d_ltri_area, ctx->d_ltri_cdf};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags, ctx->d_ltris, ctx->d_ltri_area, ctx->d_ltri_cdf, ctx->io3};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
     if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);
@@ -530,6 +530,39 @@ int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, co
     }
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PV_OK;
+}
+// Li of n rays with a stream index of its own per ray: what a caller that collects rays from many threads into one call needs for its
+// results not to depend on who shared a call with whom.  integrator < 0: PhotonVolumeIntegrator::Li, else pv_volume_li's.
+static int gather_indexed(pv_ctx *ctx, int integrator, const pv_ray *rays, const uint64_t *ray_index, uint64_t n, const pv_gather_params *params,
+                          float *L, float *T) {
+    if (!params || (n && (!rays || !ray_index || !L || !T))) { ctx->err = "pv_gather_indexed: null pointer"; return PV_EINVAL; }
+    if (!n) return PV_OK;
+    const size_t rb = n * sizeof(pv_ray), sb = n * PV_NSPEC * sizeof(float);
+    int rc = pv_ensure(ctx, &ctx->io, &ctx->io_bytes, rb); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 2 * sb); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->io3, &ctx->io3_bytes, n * sizeof(uint64_t)); if (rc) return rc;
+    pv_ray *d_rays = (pv_ray *)ctx->io;
+    float *d_L = (float *)ctx->io2, *d_T = d_L + n * PV_NSPEC;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->io3, ray_index, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->d_ray_index = (const uint64_t *)ctx->io3; ctx->ray_index_rays = d_rays;
+    rc = integrator < 0 ? pvi_gather(ctx, d_rays, n, params, d_L, d_T) : pvi_volume_li(ctx, integrator, d_rays, n, params, d_L, d_T);
+    ctx->d_ray_index = nullptr; ctx->ray_index_rays = nullptr;
+    if (rc) return rc;
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(L, d_L, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemcpyAsync(T, d_T, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pv_gather_indexed(pv_ctx *ctx, const pv_ray *rays, const uint64_t *ray_index, uint64_t n, const pv_gather_params *params, float *L, float *T) {
+    LOCK(ctx);
+    return gather_indexed(ctx, -1, rays, ray_index, n, params, L, T);
+}
+int pv_volume_li_indexed(pv_ctx *ctx, int integrator, const pv_ray *rays, const uint64_t *ray_index, uint64_t n, const pv_gather_params *params,
+                         float *L, float *T) {
+    LOCK(ctx);
+    if (integrator < 0) { ctx->err = "pv_volume_li_indexed: bad integrator"; return PV_EINVAL; }
+    return gather_indexed(ctx, integrator, rays, ray_index, n, params, L, T);
 }
 int pv_gather_stats_get(pv_ctx *ctx, pv_gather_stats *out, int reset) {
     LOCK(ctx);

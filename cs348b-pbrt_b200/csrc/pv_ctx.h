@@ -75,6 +75,9 @@ struct pv_ctx {
     void *io2 = nullptr; size_t io2_bytes = 0;
 
     double shoot_yield[2] = {0., 0.};              // deposits per light path seen so far (volume-only pass, all-maps pass): sizes the next wave's buffer
+    // pv_gather_indexed / pv_volume_li_indexed: stream index of every ray of the call in flight (device), and the ray array it belongs to
+    const uint64_t *d_ray_index = nullptr; const pv_ray *ray_index_rays = nullptr;
+    void *io3 = nullptr; size_t io3_bytes = 0;
     uint64_t wf_deep_pages = 0;                    // size of the wavefront's deep-stack page pool (grown when a wave runs it dry)
     void *wf = nullptr; size_t wf_bytes = 0;       // slot state of the shooter's wavefront (pv_wavefront.cu)
 

@@ -64,6 +64,7 @@ struct MarchArgs {
     uint32_t flags;
     uint32_t k0, k1;               // Philox key
     uint64_t ray_index_base;
+    const uint64_t *ray_index;     // per-ray stream indices (pv_gather_indexed) or null: ray i draws from ray_index_base + i
     pv_gather_stats *stats;
 };
 
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
         const float step = h0.w, t_first = h1.x;
         const pv_ray ray = a.rays[ri];
         const v3 ro = V3(ray.o[0], ray.o[1], ray.o[2]), rd = V3(ray.d[0], ray.d[1], ray.d[2]);
-        const uint64_t gidx = a.ray_index_base + ri;
+        const uint64_t gidx = a.ray_index ? a.ray_index[ri] : a.ray_index_base + ri;
         uint32_t rw[4] = {0u, 0u, 0u, 0u};
         if (do_direct) pv_philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, PV_RNG_RAY, a.k0, a.k1, rw);
         float c_t = h1.y;                                   // t0 + u * step; then t0 += step per sample (photonvolume.cpp:135,147)
@@ -199,6 +200,7 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (StepRec *)ctx->march_steps; a.n = n;
     a.stepsize = prm->stepsize; a.flags = flags; a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
     a.ray_index_base = prm->ray_index_base; a.stats = ctx->d_stats;
+    a.ray_index = ctx->d_ray_index ? ctx->d_ray_index + (d_rays - ctx->ray_index_rays) : nullptr;
     if (total) {
         if (ctx->hscene.n_spheres) march_steps_kernel<true><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
         else march_steps_kernel<false><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);

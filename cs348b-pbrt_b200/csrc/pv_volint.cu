@@ -33,6 +33,7 @@ struct VolIntArgs {
     uint64_t n;
     uint32_t k0, k1;               // Philox key
     uint64_t ray_index_base;
+    const uint64_t *ray_index;     // per-ray stream indices (pv_volume_li_indexed) or null
     float *L, *T;
 };
 
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(VI_THREADS) volint_kernel(VolIntArgs a) {
     if (nSamples > 0) {
         const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
         const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
-        const uint64_t gidx = a.ray_index_base + ri;
+        const uint64_t gidx = a.ray_index ? a.ray_index[ri] : a.ray_index_base + ri;
         float S = 0.f;                                      // sum of the step optical-depth scalars: Tr[b] >= exp(-sig_t[b] * S)
         bool stop = false;
         for (int c0 = 0; c0 < nSamples && !stop; c0 += 32) {
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(VT_THREADS) volint_thread_kernel(VolIntArgs a)
     if (nSamples > 0) {
         const v3 ro = V3(__ldg(&a.rays[ri].o[0]), __ldg(&a.rays[ri].o[1]), __ldg(&a.rays[ri].o[2]));
         const v3 rd = V3(__ldg(&a.rays[ri].d[0]), __ldg(&a.rays[ri].d[1]), __ldg(&a.rays[ri].d[2]));
-        const uint64_t gidx = a.ray_index_base + ri;
+        const uint64_t gidx = a.ray_index ? a.ray_index[ri] : a.ray_index_base + ri;
         float S = 0.f;
         float4 na = __ldg(rp), nb = __ldg(rp + 1);                        // t, tau, rr, dens | sh, dfac, ln, ray
         for (int i = 0; i < nSamples; ++i, rp += 2) {
@@ -221,6 +222,7 @@ static int volint_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     VolIntArgs a;
     a.sc = ctx->dscene; a.rays = d_rays; a.hdr = (const RayHdr *)ctx->march_hdr; a.steps = (const StepRec *)ctx->march_steps; a.n = n;
     a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32); a.ray_index_base = prm->ray_index_base;
+    a.ray_index = ctx->d_ray_index ? ctx->d_ray_index + (d_rays - ctx->ray_index_rays) : nullptr;
     a.L = d_L; a.T = d_T;
     // Which schedule?  One thread per ray once the rays alone fill the machine (a few resident warps on every SM), one warp per
     // ray below that; PV_VOLINT_THREAD_PER_RAY / PV_VOLINT_WARP_PER_RAY in params->flags force one or the other.

@@ -429,11 +429,8 @@ static void pv_fill_ray(const RayDifferential &ray, float u_scatter, pv_ray *r) 
 // shading (SpecularReflect/Transmit -> Renderer::Li -> VolumeIntegrator::Li), on every render thread at once.  A device round
 // trip per ray, serialised by the context's mutex, is what such a render would spend its time on (measured: 3.2 of 3.3 s).
 // Instead the first thread that arrives opens a batch and waits a few tens of microseconds for the other threads' rays; the
-// batch is ONE device call; everybody picks its own result up.  The ABI takes one stream base per call, so a ray's Philox
-// stream is (the batch leader's index + its slot in the batch): which random numbers a secondary ray sees depends on the batch
-// it joined -- the same distribution whatever the batching (and no dependence at all where Li is deterministic: homogeneous
-// medium, one light, no roulette), but such renders are not bit-reproducible from run to run, like the reference's own
-// multi-threaded renders.
+// batch is ONE device call; everybody picks its own result up.  Every ray goes down with a stream index of its own
+// (pv_gather_indexed), drawn from its render task's RNG, so what a ray sees does not depend on the batch it joined.
 namespace {
 struct LiBatch {
     std::vector<pv_ray> rays; std::vector<uint64_t> index;
@@ -486,11 +483,12 @@ static int pv_li_batched(const pv_ray &r, uint64_t index, const pv_gather_params
         const size_t n = b->rays.size();
         b->L.resize(n * PV_NSPEC); b->T.resize(n * PV_NSPEC);
         lock.unlock();
-        // rays of one call get consecutive stream indices: sort the batch into runs? -- simpler: one stream base per ray is what
-        // the ABI offers per CALL, so the batch goes down as ONE call whose base is the leader's index; ray i uses base + i
-        pv_gather_params prm = prm0; prm.ray_index_base = b->index[0];
+        // every ray of the batch keeps the stream index its own thread gave it (pv_gather_indexed): what a ray sees does not depend
+        // on the batch it joined
+        pv_gather_params prm = prm0; prm.ray_index_base = 0;
         const double t0 = now_s();
-        int rc = pv_volume_term(b->rays.data(), n, &prm, b->L.data(), b->T.data());
+        int rc = g_pv.volint < 0 ? pv_gather_indexed(g_pv.ctx, b->rays.data(), b->index.data(), n, &prm, b->L.data(), b->T.data())
+                                 : pv_volume_li_indexed(g_pv.ctx, g_pv.volint, b->rays.data(), b->index.data(), n, &prm, b->L.data(), b->T.data());
         const double dt = now_s() - t0;
         lock.lock();
         g_li.seconds += dt;

@@ -395,6 +395,16 @@ int pv_comm_destroy(pv_ctx *ctx);
 int pv_allgather_photons(pv_ctx *ctx, int renumber, float *collective_ms);
 int pv_broadcast_photons(pv_ctx **ctxs, int n, int src, float *collective_ms);
 
+/* Li with a stream index of its own per ray: ray i draws from the stream ray_index[i] (params->ray_index_base is not read), so the
+ * result of a ray does not depend on which other rays share the call.  For callers that collect rays from many threads -- the rays
+ * specular bounces spawn deep inside the reference's recursive surface shading (SpecularReflect -> Renderer::Li ->
+ * VolumeIntegrator::Li, core/integrator.cpp:280-340) reach the volume integrator one at a time on every render thread.  Host
+ * pointers.  pv_volume_li_indexed: integrator = PV_VOLINT_*.                                                                */
+int pv_gather_indexed(pv_ctx *ctx, const pv_ray *rays, const uint64_t *ray_index, uint64_t n, const pv_gather_params *params,
+                      float *L, float *T);
+int pv_volume_li_indexed(pv_ctx *ctx, int integrator, const pv_ray *rays, const uint64_t *ray_index, uint64_t n,
+                         const pv_gather_params *params, float *L, float *T);
+
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing */
 void *pv_stream(pv_ctx *ctx);
 

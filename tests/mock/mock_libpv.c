@@ -107,6 +107,26 @@ int pv_gather(pv_ctx *ctx, const pv_ray *rays, uint64_t n, const pv_gather_param
 int pv_volume_li(pv_ctx *ctx, int integrator, const pv_ray *rays, uint64_t n, const pv_gather_params *p, float *L, float *T) {
     fake_li(integrator == PV_VOLINT_SINGLE ? "volume_li_single" : "volume_li_emission", ctx, rays, n, p, L, T); return PV_OK;
 }
+/* the indexed forms: every ray under its own stream index */
+static void fake_li_indexed(const char *what, pv_ctx *ctx, const pv_ray *rays, const uint64_t *idx, uint64_t n, float *L, float *T) {
+    for (uint64_t i = 0; i < n; ++i) {
+        pv_gather_params p; memset(&p, 0, sizeof(p)); p.ray_index_base = idx[i];
+        const char *keep = getenv("MOCK_PV_LOG"); (void)keep;
+        uint64_t g = idx[i];
+        uint32_t h = (uint32_t)(g * 2654435761u) ^ (uint32_t)(g >> 32);
+        for (int b = 0; b < PV_NSPEC; ++b) {
+            L[PV_NSPEC * i + b] = (float)((h >> (b % 16)) & 0xffu) / 255.f * (rays[i].d[2] > 0.f ? 1.f : .5f);
+            T[PV_NSPEC * i + b] = 0.75f;
+        }
+    }
+    logf_("%s dev=%d base=%llu n=%llu indexed=1\n", what, ctx->device, (unsigned long long)(n ? idx[0] : 0), (unsigned long long)n);
+}
+int pv_gather_indexed(pv_ctx *ctx, const pv_ray *rays, const uint64_t *idx, uint64_t n, const pv_gather_params *p, float *L, float *T) {
+    (void)p; fake_li_indexed("gather", ctx, rays, idx, n, L, T); return PV_OK;
+}
+int pv_volume_li_indexed(pv_ctx *ctx, int integrator, const pv_ray *rays, const uint64_t *idx, uint64_t n, const pv_gather_params *p, float *L, float *T) {
+    (void)p; fake_li_indexed(integrator == PV_VOLINT_SINGLE ? "volume_li_single" : "volume_li_emission", ctx, rays, idx, n, L, T); return PV_OK;
+}
 int pv_last_kernel_ms(pv_ctx *ctx, float *ms) { (void)ctx; *ms = 0.f; return PV_OK; }
 /* surface-map entry points: present so the binary loads; the host-logic tests use scenes without surface photon maps */
 /* surface photons / radiance-photon sites scattered over the floor of the Cornell box (y = -1), arriving from straight above */

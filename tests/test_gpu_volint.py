@@ -180,3 +180,32 @@ def test_full_frame_volume_li_properties(full_frame, pkg, kind):
     gL, gT = pv.VolumeLi(kind, sub, flags=A.VOLINT_THREAD_PER_RAY)
     oL, oT, _ = O.volume_li(scene, sub, cfg["stepsize"], KINDS[kind], seed=348)
     check(gL, gT, oL, oT)
+
+
+def test_indexed_calls_give_every_ray_its_own_stream(golden, pkg, pv_factory):
+    """pv_gather_indexed / pv_volume_li_indexed: ray i draws from the stream ray_index[i], so a ray's result is the one it gets
+    alone under that index -- whatever rays share the call, in whatever order (what the drop-in's batching of secondary rays across
+    render threads needs for reproducible renders).  Two lights + a grid medium: light choice, tau offsets and roulette all draw."""
+    g, scene, stepsize = volint_scene(pkg, golden, "volint_homog")
+    rays = g["rays"][:64]
+    rng = np.random.default_rng(5)
+    idx = rng.integers(1 << 40, 1 << 62, size=len(rays), dtype=np.uint64) | np.uint64(1 << 63)
+    pv = pv_factory(stepsize=stepsize, seed=0xBEEF)
+    pv.set_scene(scene)
+    L, T = pv.LiIndexed(rays, idx, integrator="single")
+    for i in (0, 7, 63):
+        Li, Ti = pv.VolumeLi("single", rays[i:i + 1], ray_index_base=int(idx[i]))
+        assert np.array_equal(Li[0], L[i]) and np.array_equal(Ti[0], T[i])
+    perm = rng.permutation(len(rays))
+    Lp, Tp = pv.LiIndexed(np.ascontiguousarray(rays[perm]), idx[perm], integrator="single")
+    assert np.array_equal(Lp, L[perm]) and np.array_equal(Tp, T[perm])
+    # the photon-volume integrator's indexed form, on a shot map
+    g2, scene2 = golden("cornell_grid32")
+    pv2 = pv_factory(stepsize=float(g2["params"][2]), nused=int(g2["params"][0]), maxdist=float(g2["params"][1]), seed=3)
+    pv2.set_scene(scene2)
+    pv2.set_photons(g2["shot_pos"], g2["shot_wi"], g2["shot_alpha"]); pv2.build()
+    r2 = g2["li_rays"][:48]; i2 = idx[:48]
+    L2, T2 = pv2.LiIndexed(r2, i2)
+    for i in (0, 20, 47):
+        Li, Ti = pv2.Li(r2[i:i + 1], ray_index_base=int(i2[i]))
+        assert np.array_equal(Li[0], L2[i]) and np.array_equal(Ti[0], T2[i])
