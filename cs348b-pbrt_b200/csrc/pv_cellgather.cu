@@ -60,6 +60,7 @@
 #ifndef CG_XSPAN
 #define CG_XSPAN 2                       // a sub-batch spans at most this many coarse cells along x
 #endif
+#define CG_NB 64                         // histogram bins of MODE 2 (they share the list's storage: CG_NB <= CG_KLIST)
 #define CG_KMAX 64                       // largest nused of the k-nearest mode
 #ifndef CG_KLIST
 #define CG_KLIST 96
@@ -81,6 +82,8 @@ struct CgArgs {
     pv_gather_stats *stats;
     float knn_rmax;                      // k-nearest mode: upper bound of a trial radius
     float knn_trial;                     // ... and the factor on the radius expected to hold nused photons
+    const unsigned long long *total_dev; // when set: the number of entries of `order` is read from the device (a list made by an earlier launch)
+    uint32_t cnt_batch, cnt_overflow;    // which of `counters` this launch uses for its batch counter and for the steps it hands over
 };
 
 // per-warp shared memory
@@ -120,11 +123,18 @@ __global__ void __launch_bounds__(256) cg_keys_kernel(GridParams g, const pv_ray
     keys[s] = key; vals[s] = (uint32_t)s;
 }
 
-template <bool KNN>
+// MODE 0: fixed radius (lists + streaming sums).  MODE 1: k-nearest, per-lane candidate lists cut by bisection (nused <= CG_KMAX).
+// MODE 2: k-nearest by RADIUS -- two passes over the staged block: the first counts every lane's candidates into a histogram of
+// d2 (CG_NB bins over its trial sphere), from which the lane reads the bin b* its nused-th photon falls into; the second is the
+// fixed-radius accumulation of everything in the bins below b*, while the few candidates IN bin b* go to a small list that is cut
+// to the (nused - taken) nearest and added last.  Any nused; also what finishes the steps the fixed-radius mode hands over (more
+// than nused photons within maxdist: the dense end of a shot map).
+template <int MODE>
 __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgArgs a) {
+    constexpr bool KNN = MODE == 1, HIST = MODE == 2;
     extern __shared__ __align__(128) unsigned char cg_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = cg_smem + (size_t)warp * (KNN ? CG_WARP_BYTES_KNN : CG_WARP_BYTES);
+    unsigned char *base = cg_smem + (size_t)warp * (MODE ? CG_WARP_BYTES_KNN : CG_WARP_BYTES);
     uint32_t *hd2 = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP) + lane;             // this lane's candidate list: entry e at [e * 32]
     uint32_t *hpos = reinterpret_cast<uint32_t *>(base + CG_OFF_HEAP + CG_KLIST * 32 * 4) + lane;
     float4 *spos = reinterpret_cast<float4 *>(base + CG_OFF_POS);
@@ -154,15 +164,16 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
     const uint32_t xspan = (uint32_t)CG_XSPAN << g.xshift;
     unsigned long long st_cand = 0;
     uint32_t st_lookups = 0, st_found = 0, st_heap = 0;
-    const unsigned long long nbatch = (a.total + 31ull) >> 5;
+    const unsigned long long total = a.total_dev ? *a.total_dev : a.total;
+    const unsigned long long nbatch = (total + 31ull) >> 5;
 
     for (;;) {
         unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(a.counters + CG_CNT_BATCH, 1ull);
+        if (lane == 0) b = atomicAdd(a.counters + a.cnt_batch, 1ull);
         b = __shfl_sync(PV_FULL, b, 0);
         if (b >= nbatch) break;
         const unsigned long long qi = b * 32ull + lane;
-        bool valid = qi < a.total;
+        bool valid = qi < total;
         uint32_t s = 0; float dens = 0.f;
         v3 q = V3(0.f, 0.f, 0.f), w = V3(0.f, 0.f, 0.f);
         if (valid) {
@@ -185,7 +196,9 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         float rq = a.maxdist, r2q = r2;
         uint32_t hc = 0; float hbound = INFINITY;                                  // list length; d2 of the K-th nearest so far once a cut has been made
         const uint32_t K = a.nused;
-        if (KNN && valid) {
+        uint32_t kcut = K;                                                         // how many entries of its list a lane keeps at a cut
+        uint32_t bstar = CG_NB; float hscale = 0.f;                                // MODE 2: the lane's boundary bin, bins per unit of d2
+        if ((KNN || (HIST && a.maxdist > g.h)) && valid) {
             const int cy = pv_cell_coord(q.y, g.origin[1], g.inv_h, g.dims[1]), cz = pv_cell_coord(q.z, g.origin[2], g.inv_h, g.dims[2]);
             const int cxc = cxf >> g.xshift;
             const int xlo = max((cxc - 1) << g.xshift, 0), xhi = min(((cxc + 2) << g.xshift) - 1, g.dims[0] - 1);
@@ -201,6 +214,11 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             const float rk = g.h * cbrtf(6.4458f * (float)K / (float)max(n27, 1u));
             rq = fminf(fminf(a.knn_trial * rk, a.knn_rmax), a.maxdist);
             r2q = rq < a.maxdist ? rq * rq : r2;
+        }
+        if (HIST) {
+            hscale = r2q > 0.f ? (float)CG_NB / r2q : 0.f;
+#pragma unroll 1
+            for (int bq = 0; bq < CG_NB; ++bq) hd2[bq * 32] = 0u;                  // this lane's histogram (the storage becomes its boundary list in pass 2)
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) part[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,8 +306,8 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
         // ---- k-nearest mode: every lane cuts its list down to its K smallest (d2, original index) entries, order kept
         auto knn_cut = [&]() {
             const uint32_t nmax = __reduce_max_sync(PV_FULL, hc);
-            if (nmax <= K) return;
-            const bool need = hc > K;
+            const bool need = hc > kcut;
+            if (!__any_sync(PV_FULL, need)) return;
             uint32_t lo = 0xffffffffu, hi = 0u;
             for (uint32_t e = 0; e < nmax; ++e) if (need && e < hc) { const uint32_t key = hd2[e * 32]; lo = min(lo, key); hi = max(hi, key); }
             // smallest threshold with at least K keys <= it (positive floats order like their bit patterns); a pass that counts
@@ -300,8 +318,8 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 uint32_t c = 0;
                 for (uint32_t e = 0; e < nmax; ++e) if (open && e < hc) c += hd2[e * 32] <= mid ? 1u : 0u;
                 if (open) {
-                    if (c == K) { lo = hi = mid; }
-                    else if (c < K) lo = mid + 1u; else hi = mid;
+                    if (c == kcut) { lo = hi = mid; }
+                    else if (c < kcut) lo = mid + 1u; else hi = mid;
                     open = lo < hi;
                 }
             }
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 uint32_t c_le = 0;
                 for (uint32_t e = 0; e < hc; ++e) c_le += hd2[e * 32] <= thr ? 1u : 0u;
                 // more than K at or below the threshold: the surplus are ties AT the threshold; those with the largest original index go
-                for (; c_le > K; --c_le) {
+                for (; c_le > kcut; --c_le) {
                     uint32_t worst = 0, worst_orig = 0; bool any = false;
                     for (uint32_t e = 0; e < hc; ++e)
                         if (hd2[e * 32] == thr) { const uint32_t og = __ldg(a.m.orig + hpos[e * 32]); if (!any || og > worst_orig) { any = true; worst = e; worst_orig = og; } }
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             const uint32_t gm = __ballot_sync(PV_FULL, in);
             remaining &= ~gm;
             const v3 aq = in ? q : V3(INFINITY, INFINITY, INFINITY);          // lanes outside the sub-batch accept nothing
-            const float slack = KNN ? cg_warp_max(in ? rq : 0.f) + g.margin : slack_fixed;
+            const float slack = MODE ? cg_warp_max(in ? rq : 0.f) + g.margin : slack_fixed;
             const float lox = cg_warp_min(in ? q.x : INFINITY), hix = cg_warp_max(in ? q.x : -INFINITY);
             const float loy = cg_warp_min(in ? q.y : INFINITY), hiy = cg_warp_max(in ? q.y : -INFINITY);
             const float loz = cg_warp_min(in ? q.z : INFINITY), hiz = cg_warp_max(in ? q.z : -INFINITY);
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             const int z0 = pv_cell_coord(loz - slack, g.origin[2], g.inv_h, g.dims[2]), z1 = pv_cell_coord(hiz + slack, g.origin[2], g.inv_h, g.dims[2]);
             const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
             if (nrows > 32) {                                                  // radius far above the cell size: not this kernel's case
-                if (in) { handed_over = true; a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s; }
+                if (in) { handed_over = true; a.overflow[atomicAdd(a.counters + a.cnt_overflow, 1ull)] = s; }
                 continue;
             }
             // lane j < nrows owns row (y0 + j % ny, z0 + j / ny): ONE contiguous photon run [rs, re).  Runs are then ordered by
@@ -371,6 +389,21 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             const uint32_t T = __shfl_sync(PV_FULL, inc, 31), E = inc - my_len;
             st_cand += (unsigned long long)T * __popc(gm);
 
+            for (int pass = 0; pass < (HIST ? 2 : 1); ++pass) {
+            if (HIST && pass == 1) {
+                // ---- between the passes: where does the lane's K-th photon fall?  b* = the first bin at which the running count
+                // reaches K; the bins below it hold n_below < K photons, all taken; K - n_below more come from bin b*
+                uint32_t nb = 0, bs = CG_NB, nbelow = 0, inb = 0;
+                if (in) {
+#pragma unroll 1
+                    for (int bq = 0; bq < CG_NB; ++bq) { const uint32_t c = hd2[bq * 32]; if (bs == CG_NB && c > 0 && nb + c >= K) { bs = (uint32_t)bq; nbelow = nb; inb = c; } nb += c; }
+                    if (nb <= K) { bs = CG_NB; nbelow = nb; inb = 0; }                // K or fewer in the whole trial sphere: every one of them
+                    // not this kernel's case: too few inside a trial sphere smaller than maxdist, or a boundary bin that does not fit the list
+                    if ((nb < K && rq < a.maxdist) || inb + CG_U > CG_KLIST) { handed_over = true; a.overflow[atomicAdd(a.counters + a.cnt_overflow, 1ull)] = s; r2q = -1.f; }
+                    bstar = bs; kcut = bs == CG_NB ? 0u : K - nbelow; hc = 0;
+                }
+                __syncwarp();
+            }
             for (uint32_t cb = 0; cb < T; cb += CG_STAGE) {
                 const uint32_t cend = min(T, cb + CG_STAGE), n = cend - cb;
                 // ---- stage: generic-proxy reads of the previous round are ordered before the async-proxy writes of this one
@@ -388,6 +421,21 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 phase ^= 1u;
                 if (lane < CG_U) spos[n + lane] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);      // the unrolled scan may read past n
                 __syncwarp();
+                if (HIST && pass == 0) {
+                    // ---- scan, pass 1 of MODE 2: count the candidates inside the lane's trial sphere by bin of d2
+                    for (uint32_t c0 = 0; c0 < n; c0 += CG_U) {
+                        float4 p[CG_U];
+#pragma unroll
+                        for (int u = 0; u < CG_U; ++u) p[u] = spos[c0 + u];
+#pragma unroll
+                        for (int u = 0; u < CG_U; ++u) {
+                            const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
+                            const float d2 = dx * dx + dy * dy + dz * dz;
+                            if (d2 < r2q) { const uint32_t bq = min((uint32_t)(CG_NB - 1), (uint32_t)(d2 * hscale)); hd2[bq * 32] += 1u; }
+                        }
+                    }
+                    continue;
+                }
                 if (KNN) {
                     // ---- scan, k-nearest mode: a candidate inside the trial sphere and not beyond the K-th nearest known so far is
                     // appended to the lane's list; a list that could overflow in the next round is cut first
@@ -421,7 +469,15 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                         for (int u = 0; u < CG_U; ++u) {
                             const float dx = p[u].x - aq.x, dy = p[u].y - aq.y, dz = p[u].z - aq.z;
                             const float d2 = dx * dx + dy * dy + dz * dz;          // (p1 - p2).LengthSquared(), geometry.h:116,526
-                            if (d2 < r2) {
+                            if (HIST) {
+                                if (d2 < r2q) {
+                                    const uint32_t bq = min((uint32_t)(CG_NB - 1), (uint32_t)(d2 * hscale));
+                                    if (bq < bstar) {
+                                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(lp), "r"(c0 + u) : "memory");
+                                        lp += 128u; mx = fmaxf(mx, d2);
+                                    } else if (bq == bstar) { hd2[hc * 32] = __float_as_uint(d2); hpos[hc * 32] = __float_as_uint(p[u].w); ++hc; }
+                                }
+                            } else if (d2 < r2) {
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(lp), "r"(c0 + u) : "memory");
                                 lp += 128u; mx = fmaxf(mx, d2);
                             }
@@ -430,12 +486,13 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
                 }
                 resolve(); sum();                                                  // the stage is about to be overwritten
             }
+            }
         }
 
-        if (KNN) {
+        if (MODE) {
             knn_cut();
             // a lane short of K photons whose trial sphere was smaller than maxdist has not seen everything: warp-per-step kernel
-            if (valid && !handed_over && hc < K && rq < a.maxdist) { handed_over = true; a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s; }
+            if (KNN && valid && !handed_over && hc < K && rq < a.maxdist) { handed_over = true; a.overflow[atomicAdd(a.counters + a.cnt_overflow, 1ull)] = s; }
             if (!valid || handed_over) hc = 0;
             // ---- the heaps, CG_CAP entries at a time, through the same weigh + sum code as the lists
             const uint32_t longest = __reduce_max_sync(PV_FULL, hc);
@@ -460,8 +517,17 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
             }
         }
         // ---- finish: LPhoton's tail (photonvolume.cpp:83-104) per query, one 128-byte row of L_ii per step
-        const bool over = !KNN && valid && !handed_over && tot > a.nused;
-        if (over) a.overflow[atomicAdd(a.counters + CG_CNT_OVERFLOW, 1ull)] = s;       // needs the k-nearest selection
+        const bool over = !MODE && valid && !handed_over && tot > a.nused;
+        {   // needs the k-nearest selection: handed over as ONE run per batch (a single atomic), so that the list keeps the batches'
+            // spatial order and the launch that takes it over finds neighbouring steps next to each other
+            const uint32_t om = __ballot_sync(PV_FULL, over);
+            if (om) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(a.counters + a.cnt_overflow, (unsigned long long)__popc(om));
+                at = __shfl_sync(PV_FULL, at, 0);
+                if (over) a.overflow[at + __popc(om & lanemask_lt())] = s;
+            }
+        }
         const bool done = valid && !handed_over && !over;
         st_found += __reduce_add_sync(PV_FULL, done ? tot : 0u);
         st_heap += __popc(__ballot_sync(PV_FULL, done && tot == a.nused));
@@ -503,15 +569,15 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MIN_CTAS) cellgather_kernel(CgA
 }
 
 // ------------------------------------------------------------------ host side
-int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
+int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga, const uint32_t **leftover_list, int *leftover_count) {
     const unsigned long long total = ga.total_steps;
     if (total == 0) return PV_OK;
     if (total > 0xFFFFFFF0ull) { ctx->err = "pv_gather: too many march steps in one slice for 32-bit step indices"; return PV_ENOMEM; }
     const GridParams &g = ga.m.g;
     int rc = pv_ensure(ctx, &ctx->cg_sort, &ctx->cg_sort_bytes, (size_t)total * 4 * sizeof(uint32_t) + 256); if (rc) return rc;
-    rc = pv_ensure(ctx, &ctx->cg_overflow, &ctx->cg_overflow_bytes, (size_t)total * sizeof(uint32_t) + 256); if (rc) return rc;
+    rc = pv_ensure(ctx, &ctx->cg_overflow, &ctx->cg_overflow_bytes, (size_t)total * 2 * sizeof(uint32_t) + 256); if (rc) return rc;
     uint32_t *keys = (uint32_t *)ctx->cg_sort, *vals = keys + total, *keys_tmp = vals + total, *vals_tmp = keys_tmp + total;
-    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters + CG_CNT_BATCH, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_counters + CG_CNT_BATCH, 0, 4 * sizeof(unsigned long long), ctx->stream));
     cg_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(g, ga.rays, ga.steps, total, keys, vals);
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     ctx->launches += 1;
@@ -522,21 +588,39 @@ int pvi_cellgather(pv_ctx *ctx, const GatherArgs &ga) {
     CgArgs a;
     a.m = ga.m; a.sc = ga.sc; a.rays = ga.rays; a.steps = ga.steps; a.order = svals; a.total = total; a.maxdist = ga.maxdist; a.nused = ga.nused;
     a.lii = ga.lii; a.overflow = (uint32_t *)ctx->cg_overflow; a.counters = ctx->d_counters; a.stats = ga.stats;
-    if (ga.maxdist > g.h && ga.nused > CG_KMAX) { ctx->err = "pv_gather: the cell-batched k-nearest mode holds at most 64 photons per lookup"; return PV_EINVAL; }
-    const bool knn = ga.maxdist > g.h;                     // the search radius does not fit the cells: k-nearest mode (gather_slice checked nused)
+    // Which form?  Search radius within the cells: MODE 0, then MODE 2 over the steps it hands over (more than nused photons in
+    // range).  Search radius above the cells (k-nearest regime): MODE 1 while nused fits its per-lane lists, else MODE 2.  What
+    // the last launch hands over is left in *leftover_list (count in d_counters[*leftover_count]) for the warp-per-step kernel.
+    const bool knn_regime = ga.maxdist > g.h;
     a.knn_rmax = 2.f * g.h - 2.f * g.margin;        // what the 5 x 5 rows (and 5 coarse cells along x) around a query's cell are sure to cover
     a.knn_trial = 1.1f;                              // measured on config 2: 1.05 -> 20.0 ms (3.5 ms of them in the fallback), 1.1 -> 17.7, 1.2 -> 23.1
     if (const char *e = getenv("PV_KNN_TRIAL")) a.knn_trial = std::max(1.0f, std::min(3.0f, (float)atof(e)));       // tuning knob
-    void (*kern)(CgArgs) = knn ? cellgather_kernel<true> : cellgather_kernel<false>;
-    const size_t smem = (size_t)(knn ? CG_WARP_BYTES_KNN : CG_WARP_BYTES) * CG_WARPS;
-    static_assert((size_t)CG_WARP_BYTES_KNN * CG_WARPS <= 227 * 1024, "cellgather: shared memory per CTA");
-    PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CG_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    kern<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
-    ctx->launches += 1;
-    PV_CUDA_CHECK(ctx, cudaGetLastError());
+    uint32_t *ov1 = (uint32_t *)ctx->cg_overflow, *ov2 = ov1 + total;
+    static_assert((size_t)CG_WARP_BYTES_KNN * CG_WARPS <= 227 * 1024 && CG_NB <= CG_KLIST, "cellgather: shared memory per CTA");
+    auto launch = [&](int mode, const uint32_t *order, const unsigned long long *total_dev, uint32_t cnt_batch, uint32_t *overflow, uint32_t cnt_overflow) -> int {
+        void (*kern)(CgArgs) = mode == 0 ? cellgather_kernel<0> : mode == 1 ? cellgather_kernel<1> : cellgather_kernel<2>;
+        const size_t smem = (size_t)(mode ? CG_WARP_BYTES_KNN : CG_WARP_BYTES) * CG_WARPS;
+        a.order = order; a.total_dev = total_dev; a.cnt_batch = cnt_batch; a.overflow = overflow; a.cnt_overflow = cnt_overflow;
+        PV_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        PV_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CG_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        kern<<<ctx->sm_count * per_sm, CG_THREADS, smem, ctx->stream>>>(a);
+        ctx->launches += 1;
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        return PV_OK;
+    };
+    static const bool hist_off = getenv("PV_KNN_NOHIST") != nullptr;          // A/B knob: leave the handed-over steps to the warp-per-step kernel
+    if (!knn_regime) {
+        rc = launch(0, svals, nullptr, CG_CNT_BATCH, ov1, CG_CNT_OVERFLOW); if (rc) return rc;
+        if (!hist_off) {
+            rc = launch(2, ov1, ctx->d_counters + CG_CNT_OVERFLOW, CG_CNT_BATCH2, ov2, CG_CNT_OVERFLOW2); if (rc) return rc;
+            *leftover_list = ov2; *leftover_count = CG_CNT_OVERFLOW2;
+        } else { *leftover_list = ov1; *leftover_count = CG_CNT_OVERFLOW; }
+    } else {
+        rc = launch(ga.nused <= CG_KMAX ? 1 : 2, svals, nullptr, CG_CNT_BATCH, ov1, CG_CNT_OVERFLOW); if (rc) return rc;
+        *leftover_list = ov1; *leftover_count = CG_CNT_OVERFLOW;
+    }
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->tev[1], ctx->stream));
     return PV_OK;
 }

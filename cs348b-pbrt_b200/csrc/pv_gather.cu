@@ -1428,7 +1428,7 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     static const bool legacy_default = getenv("PV_GATHER_LEGACY") != nullptr;               // A/B knob: the round-1 schedules
     // (k-nearest regime, maxdist above the cell size: the cell-batched kernel's k-nearest mode while nused fits its per-lane heap)
     static const bool knn_legacy = getenv("PV_KNN_LEGACY") != nullptr;                       // A/B knob: warp-per-ray / warp-per-step k-nearest search
-    bool cell = lookups && !legacy_default && a.m.n > 0 && (prm->maxdist <= ctx->grid.h || (!knn_legacy && prm->nused <= 64 && prm->nused >= 1));
+    bool cell = lookups && !legacy_default && a.m.n > 0 && (prm->maxdist <= ctx->grid.h || (!knn_legacy && prm->nused >= 1));
     bool step_parallel = lookups && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
     if (flags & PV_GATHER_STEP_PARALLEL) { step_parallel = lookups; cell = false; }
     if (flags & PV_GATHER_RAY_PARALLEL) { step_parallel = false; cell = false; }
@@ -1452,12 +1452,13 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     }
 #endif
     if (cell) {
-        rc = pvi_cellgather(ctx, a);                        // records tev[0] (steps sorted) and tev[1] (cellgather_kernel done)
+        const uint32_t *left = nullptr; int left_cnt = CG_CNT_OVERFLOW;
+        rc = pvi_cellgather(ctx, a, &left, &left_cnt);      // records tev[0] (steps sorted) and tev[1] (cellgather kernels done)
         if (rc == PV_ENOMEM && n > 4096) return halves();
         if (rc) return rc;
-        // the steps it left over (more than nused photons in range): warp-per-step kernel over the overflow list
+        // the steps they left over: warp-per-step kernel over that list
         GatherArgs o = a;
-        o.list = (const uint32_t *)ctx->cg_overflow; o.list_count = ctx->d_counters + CG_CNT_OVERFLOW;
+        o.list = left; o.list_count = ctx->d_counters + left_cnt;
         rc = launch_cfg(ctx, gather_lii_kernel, a.cap, &blocks, &smem); if (rc) return rc;
         gather_lii_kernel<<<blocks, GW_THREADS, smem, ctx->stream>>>(o);
         ctx->launches += 1;

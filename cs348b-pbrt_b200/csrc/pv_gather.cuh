@@ -63,5 +63,5 @@ MapView pvi_map_view(pv_ctx *ctx);
 // pv_cellgather.cu: fills a.lii (32 floats per march step) for every live step of the slice whose neighbour count stays within
 // a.nused; the steps it could not finish (more than nused photons in range: the k-nearest selection is needed) are appended to
 // ctx->cg_overflow (count in ctx->d_counters[CG_CNT_OVERFLOW]) for gather_lii_kernel.
-enum { CG_CNT_BATCH = 16, CG_CNT_OVERFLOW = 17 };
-int pvi_cellgather(pv_ctx *ctx, const GatherArgs &a);
+enum { CG_CNT_BATCH = 16, CG_CNT_OVERFLOW = 17, CG_CNT_BATCH2 = 18, CG_CNT_OVERFLOW2 = 19 };
+int pvi_cellgather(pv_ctx *ctx, const GatherArgs &a, const uint32_t **leftover_list, int *leftover_count);
