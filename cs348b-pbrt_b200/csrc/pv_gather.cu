@@ -1428,7 +1428,10 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     static const bool legacy_default = getenv("PV_GATHER_LEGACY") != nullptr;               // A/B knob: the round-1 schedules
     // (k-nearest regime, maxdist above the cell size: the cell-batched kernel's k-nearest mode while nused fits its per-lane heap)
     static const bool knn_legacy = getenv("PV_KNN_LEGACY") != nullptr;                       // A/B knob: warp-per-ray / warp-per-step k-nearest search
-    bool cell = lookups && !legacy_default && a.m.n > 0 && (prm->maxdist <= ctx->grid.h || (!knn_legacy && prm->nused >= 1));
+    // (nused > 64 in the k-nearest regime stays with the warp-per-ray search: the radius-histogram mode of the batched kernel handles
+    // any nused, but on pinkfloyd.pbrt -- 5 M photons crowded into a spot beam inside a 15^3 medium, cells at the 256-per-axis limit --
+    // its two passes over blocks of tens of thousands of candidates were an order of magnitude SLOWER than the 35 s of that search)
+    bool cell = lookups && !legacy_default && a.m.n > 0 && (prm->maxdist <= ctx->grid.h || (!knn_legacy && prm->nused <= 64 && prm->nused >= 1));
     bool step_parallel = lookups && n < (uint64_t)ctx->sm_count * 16 * 2 && total <= (4ull << 20);
     if (flags & PV_GATHER_STEP_PARALLEL) { step_parallel = lookups; cell = false; }
     if (flags & PV_GATHER_RAY_PARALLEL) { step_parallel = false; cell = false; }
