@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload lines (config 2: k-nearest gather)")
     ap.add_argument("--seed", type=int, default=348)
+    ap.add_argument("--slice-of", type=int, default=0, help="tuning aid: gather only the rays rank 0 of that many ranks would get (one process; invalidates the number)")
     args = ap.parse_args()
 
     pkg = load_package()
@@ -325,7 +326,7 @@ def main():
                 "params": {"shooter_stepsize": 0.05, "maxphotondepth": 5, "target": target}}
 
     # ------------------------------------------------------------------ rays of this rank (image tiles dealt round-robin)
-    rays, order = W.frame_rays(cfg, rank, world, density=scene.density)
+    rays, order = W.frame_rays(cfg, rank, world, density=scene.density) if not args.slice_of else W.frame_rays(cfg, 0, args.slice_of, density=scene.density)
     n_local = len(rays)
     n_total = cfg["xres"] * cfg["yres"]
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 10)).to(dev)

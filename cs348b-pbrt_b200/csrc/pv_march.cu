@@ -13,7 +13,9 @@
 #include "pv_ctx.h"
 #include "pv_march.cuh"
 
+#ifndef MS_THREADS
 #define MS_THREADS 128
+#endif
 #ifndef MS_MIN_CTAS
 #define MS_MIN_CTAS 8
 #endif
