@@ -65,7 +65,7 @@ void pv_destroy(pv_ctx *ctx) {
     pvi_comm_destroy(ctx);
     void *ptrs[] = {ctx->dscene, ctx->d_nodes, ctx->d_tri, ctx->d_prim_mat, ctx->d_mats, ctx->d_lights, ctx->d_density, ctx->d_spheres, ctx->d_pos, ctx->d_wi,
                     ctx->d_alpha, ctx->d_ids, ctx->m_pos4, ctx->m_wi4, ctx->m_alpha32, ctx->m_orig, ctx->cell_start, ctx->scratch, ctx->io, ctx->io2,
-                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags, ctx->d_ltris, ctx->d_ltri_area, ctx->d_ltri_cdf, ctx->io3};
+                    ctx->d_stats, ctx->d_counters, ctx->march_hdr, ctx->march_steps, ctx->lii, ctx->cg_sort, ctx->cg_overflow, ctx->sort_hist, ctx->wf, ctx->d_mat_flags, ctx->d_ltris, ctx->d_ltri_area, ctx->d_ltri_cdf, ctx->io3, ctx->march_blk};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int c = 0; c < 4; ++c) pvi_free_set(&ctx->surf[c]);
     if (ctx->rad_Lo) cudaFree(ctx->rad_Lo);

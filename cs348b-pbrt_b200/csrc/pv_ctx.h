@@ -86,6 +86,7 @@ struct pv_ctx {
     // march records of the ray slice being gathered (pv_march.cu): RayHdr per ray, StepRec per march step
     void *march_hdr = nullptr; size_t march_hdr_bytes = 0;
     void *march_steps = nullptr; size_t march_steps_bytes = 0;
+    void *march_blk = nullptr; size_t march_blk_bytes = 0;      // per block of 128 rays of the slice: its march steps, and the blocks in order of decreasing steps
     void *lii = nullptr; size_t lii_bytes = 0;     // per-step in-scattered radiance of the step-parallel gather (32 floats per step)
     void *cg_sort = nullptr; size_t cg_sort_bytes = 0;           // cell-batched gather: (cell key, step) pairs and their sort buffers
     void *cg_overflow = nullptr; size_t cg_overflow_bytes = 0;   // steps left to the warp-per-step kernel (more than nused photons in range)

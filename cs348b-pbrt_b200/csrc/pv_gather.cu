@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(RT_THREADS, 4) recurrence_thread_kernel(Gather
     for (int i = threadIdx.x; i < PV_NSPEC; i += RT_THREADS) { s_sig_a[i] = med.sigma_a[i]; s_sig_s[i] = med.sigma_s[i]; s_le[i] = med.le[i]; }
     for (int i = threadIdx.x; i < (int)sc.n_lights * PV_NSPEC; i += RT_THREADS) s_I[i / PV_NSPEC][i % PV_NSPEC] = sc.lights[i / PV_NSPEC].intensity[i % PV_NSPEC];
     __syncthreads();
-    const uint64_t ri = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+    const uint64_t ri = (uint64_t)(a.block_order ? a.block_order[blockIdx.x] : blockIdx.x) * RT_THREADS + threadIdx.x;
     if (ri >= a.n) return;
     float y_sig_a = 0.f, y_sig_s = 0.f;
     for (int bb = 0; bb < PV_NSPEC; ++bb) { y_sig_a += sc.cie_y[bb] * med.sigma_a[bb]; y_sig_s += sc.cie_y[bb] * med.sigma_s[bb]; }
@@ -1415,6 +1415,8 @@ static int gather_slice(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_
     a.nused = prm->nused; a.flags = flags; a.cap = lookup_cap(std::max<uint32_t>(prm->nused, 1u));
     a.L = d_L; a.T = d_T; a.stats = ctx->d_stats; a.counter = ctx->d_counters;
     a.lii = nullptr; a.total_steps = total; a.list = nullptr; a.list_count = nullptr;
+    static_assert(RT_THREADS == 128, "recurrence_thread_kernel shares the march kernels' blocks of 128 rays");
+    a.block_order = ctx->march_blk ? (const uint32_t *)ctx->march_blk + (n + 127) / 128 : nullptr;
     int blocks; size_t smem;
     // Which schedule for the lookups?  (results: cell-batched sums each step's photons in photon order; the two warp forms are
     // bit-identical to each other and agree with it to rounding)

@@ -56,6 +56,7 @@ struct GatherArgs {
     float *lii; unsigned long long total_steps;
     // gather_lii_kernel over a LIST of steps (the cell-batched gather's overflow): list[0 .. *list_count)
     const uint32_t *list; const unsigned long long *list_count;
+    const uint32_t *block_order;   // recurrence_thread_kernel: CTA i takes the rays of block block_order[i] (pv_march.cu block_order_kernel), or null
 };
 
 

@@ -21,7 +21,8 @@
 #endif
 
 __global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene *__restrict__ scp, const pv_ray *__restrict__ rays, uint64_t n,
-                                                                float stepsize, RayHdr *__restrict__ hdr, unsigned long long *total) {
+                                                                float stepsize, RayHdr *__restrict__ hdr, unsigned long long *total,
+                                                                uint32_t *__restrict__ block_cost) {
     const DevMedium &med = scp->med;
     const uint64_t ri = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene 
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(PV_FULL, inc, o); if (lane >= o) inc += t; }
     unsigned long long base = 0;
-    if (lane == 31 && inc) base = atomicAdd(total, (unsigned long long)inc);
+    if (lane == 31 && inc) { base = atomicAdd(total, (unsigned long long)inc); atomicAdd(block_cost + blockIdx.x, inc); }    // (block_cost is zeroed by the host)
     base = __shfl_sync(PV_FULL, base, 31);
     if (ri < n) {
         RayHdr h;
@@ -52,6 +53,27 @@ __global__ void __launch_bounds__(MS_THREADS) march_setup_kernel(const DevScene 
         reinterpret_cast<float4 *>(hdr + ri)[0] = reinterpret_cast<const float4 *>(&h)[0];
         reinterpret_cast<float4 *>(hdr + ri)[1] = reinterpret_cast<const float4 *>(&h)[1];
     }
+}
+
+// Blocks of MS_THREADS rays in order of decreasing march steps, for the thread-per-ray kernels that follow (march_steps_kernel,
+// recurrence_thread_kernel): the hardware hands CTAs out in index order, so with the heaviest blocks first the tail of a launch is
+// made of light blocks.  On a full frame (16 k blocks) the tail does not matter; on one GPU's share of a frame spread over eight
+// (2 k blocks = 1.7 waves) it was a third of the march.  Counting sort over 64 cost classes, one CTA.
+__global__ void __launch_bounds__(1024) block_order_kernel(const uint32_t *__restrict__ cost, uint32_t nblocks, uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_max, s_cnt[64], s_off[64];
+    if (threadIdx.x == 0) s_max = 1u;
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t mx = 0;
+    for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) mx = max(mx, cost[b]);
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    const float scale = 63.999f / (float)s_max;
+    for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) atomicAdd(&s_cnt[63u - min(63u, (uint32_t)((float)cost[b] * scale))], 1u);     // class 0 = heaviest
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t acc = 0; for (int c = 0; c < 64; ++c) { s_off[c] = acc; acc += s_cnt[c]; } }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) order[atomicAdd(&s_off[63u - min(63u, (uint32_t)((float)cost[b] * scale))], 1u)] = b;
 }
 
 __global__ void publish_total_kernel(const unsigned long long *total, unsigned long long *host_mapped) { *host_mapped = *total; }
@@ -67,6 +89,7 @@ struct MarchArgs {
     uint32_t k0, k1;               // Philox key
     uint64_t ray_index_base;
     const uint64_t *ray_index;     // per-ray stream indices (pv_gather_indexed) or null: ray i draws from ray_index_base + i
+    const uint32_t *block_order;   // CTA i takes the rays of block block_order[i] (block_order_kernel)
     pv_gather_stats *stats;
 };
 
@@ -85,7 +108,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) march_steps_kernel(Ma
     const bool do_direct = any_sig_s && sc.n_lights > 0 && !(a.flags & PV_GATHER_NO_DIRECT);
     const int nLights = (int)sc.n_lights;
     uint32_t ns = 0, nshadow = 0;
-    const uint64_t ri = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x;
+    const uint64_t ri = (uint64_t)a.block_order[blockIdx.x] * MS_THREADS + threadIdx.x;
     int nSamples = 0;
     float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
     if (ri < a.n) {
@@ -180,8 +203,12 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     PV_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), ctx->stream));
     PV_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
     const uint32_t blocks = (uint32_t)((n + MS_THREADS - 1) / MS_THREADS);
-    march_setup_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(ctx->dscene, d_rays, n, prm->stepsize, (RayHdr *)ctx->march_hdr, d_total);
-    ctx->launches += 2;                                 // + publish_total_kernel below
+    rc = pv_ensure(ctx, &ctx->march_blk, &ctx->march_blk_bytes, (size_t)blocks * 2 * sizeof(uint32_t)); if (rc) return rc;
+    uint32_t *blk_cost = (uint32_t *)ctx->march_blk, *blk_order = blk_cost + blocks;
+    PV_CUDA_CHECK(ctx, cudaMemsetAsync(blk_cost, 0, (size_t)blocks * sizeof(uint32_t), ctx->stream));
+    march_setup_kernel<<<blocks, MS_THREADS, 0, ctx->stream>>>(ctx->dscene, d_rays, n, prm->stepsize, (RayHdr *)ctx->march_hdr, d_total, blk_cost);
+    block_order_kernel<<<1, 1024, 0, ctx->stream>>>(blk_cost, blocks, blk_order);
+    ctx->launches += 3;                                 // + publish_total_kernel below
     PV_CUDA_CHECK(ctx, cudaGetLastError());
     // The step count comes back through mapped pinned memory, not a memcpy: a copy would queue on the device->host copy
     // engine behind the result download of the previous slice (pv_gather overlaps the two).
@@ -203,6 +230,7 @@ int pvi_march(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, const pv_gather_par
     a.stepsize = prm->stepsize; a.flags = flags; a.k0 = (uint32_t)prm->seed; a.k1 = (uint32_t)(prm->seed >> 32);
     a.ray_index_base = prm->ray_index_base; a.stats = ctx->d_stats;
     a.ray_index = ctx->d_ray_index ? ctx->d_ray_index + (d_rays - ctx->ray_index_rays) : nullptr;
+    a.block_order = blk_order;
     if (total) {
         if (ctx->hscene.n_spheres) march_steps_kernel<true><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
         else march_steps_kernel<false><<<blocks, MS_THREADS, 0, ctx->stream>>>(a);
