@@ -215,6 +215,21 @@ def project_goldens(tmp):
         open(os.path.join(ROOT, "tests", "scenes", name + ".pbrt"), "w").write(text)
         subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)
         np.save(os.path.join(HERE, name + "_ref.npy"), read_pfm(os.path.join(tmp, name + ".pfm")).astype(np.float16))
+    exr_check(tmp, ref_bin)
+
+
+def exr_check(tmp, ref_bin):
+    """The reference's EXR writer (core/imageio.cpp:171-197, compiled in by oracle/Makefile from the vendored OpenEXR): config 1's
+    scene with an .exr file name decodes to exactly the fp16 golden made from its .pfm -- so config1_volumescene_ref.npy IS the
+    reference's EXR image and the drop-in's .exr is compared with it (tests/test_dropin_render.py)."""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    f = os.path.join(tmp, "config1_volumescene_exr.pbrt")
+    open(f, "w").write(scenes.volumescene_pbrt(outfile="config1_volumescene.exr", xres=150, yres=150))
+    subprocess.check_call([ref_bin, "--ncores", "1", "--quiet", f], cwd=tmp)
+    bgra = cv2.imread(os.path.join(tmp, "config1_volumescene.exr"), cv2.IMREAD_UNCHANGED)
+    gold = np.load(os.path.join(HERE, "config1_volumescene_ref.npy")).astype(np.float32)
+    assert bgra.shape == (150, 150, 4) and np.array_equal(bgra[..., [2, 1, 0]], gold) and np.all(bgra[..., 3] == 1.0)
 
 
 def sphere_goldens(tmp):

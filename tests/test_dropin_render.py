@@ -178,3 +178,57 @@ def test_dropin_renders_a_scene_with_an_area_light(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] shot" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, "cornell_area_e2e.pfm")), golden_ref("cornell_area_e2e"), "cornell_area_e2e")
+
+
+def read_exr_header(path):
+    """OpenEXR 1.x/2.x single-part scanline header -> {attribute name: (type, raw bytes)}; channel list decoded under "_channels"
+    as [(name, pixel type)], pixel type 1 = HALF"""
+    import struct
+    buf = open(path, "rb").read(4096)
+    assert struct.unpack("<I", buf[:4])[0] == 20000630                       # magic (ImfVersion.h)
+    off, attrs = 8, {}
+    cstr = lambda o: (buf[o:buf.index(b"\0", o)].decode(), buf.index(b"\0", o) + 1)
+    while buf[off] != 0:
+        name, off = cstr(off)
+        kind, off = cstr(off)
+        n = struct.unpack("<I", buf[off:off + 4])[0]
+        attrs[name] = (kind, buf[off + 4:off + 4 + n])
+        off += 4 + n
+    ch, o, raw = [], 0, attrs["channels"][1]
+    while raw[o] != 0:
+        e = raw.index(b"\0", o)
+        ch.append((raw[o:e].decode(), struct.unpack("<i", raw[e + 1:e + 5])[0]))
+        o = e + 1 + 16
+    attrs["_channels"] = ch
+    return attrs
+
+
+@needs_bin
+def test_dropin_writes_exr_like_the_reference(tmp_path):
+    """SURVEY 8(f)-3, "same EXR/PNG film output": the project's shipped scenes (pinkfloyd.pbrt, scene.pbrt, darkside.pbrt) name .exr
+    files.  The drop-in is linked with the reference's film and image writers AND with the OpenEXR / IlmBase / zlib the reference
+    vendors under 3rdparty/ (oracle/Makefile compiles them from there into oracle/_ref/libexr_ref.a and core/imageio.cpp with
+    PBRT_HAS_OPENEXR), so WriteImageEXR (core/imageio.cpp:171-197) is the reference's own code.  Config 1's scene with an .exr file
+    name: the header must be what RgbaOutputFile(WRITE_RGBA) writes (A, B, G, R as HALF, PIZ compression, data window = display
+    window = the film), the pixels must meet the whole-image tolerance against the unmodified reference's render (whose .exr,
+    written here with `pbrt_ref --ncores 1`, decodes to exactly the fp16 golden config1_volumescene_ref.npy -- checked when
+    that golden was made, tests/golden/make_golden.py) and alpha must be the film's (1 where a camera sample landed)."""
+    import struct
+    src = open(os.path.join(ROOT, "tests", "scenes", "config1_volumescene.pbrt")).read()
+    assert "config1_volumescene.pfm" in src
+    scene = os.path.join(tmp_path, "config1_volumescene_exr.pbrt")
+    open(scene, "w").write(src.replace("config1_volumescene.pfm", "config1_volumescene.exr"))
+    out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
+    path = os.path.join(tmp_path, "config1_volumescene.exr")
+    hdr = read_exr_header(path)
+    assert hdr["_channels"] == [("A", 1), ("B", 1), ("G", 1), ("R", 1)]
+    assert hdr["compression"] == ("compression", b"\x04")                     # PIZ, RgbaOutputFile's default
+    assert struct.unpack("<4i", hdr["dataWindow"][1]) == (0, 0, 149, 149) == struct.unpack("<4i", hdr["displayWindow"][1])
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    bgra = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert bgra is not None and bgra.shape == (150, 150, 4)
+    assert_within_the_whole_image_tolerance(bgra[..., [2, 1, 0]].astype(np.float32), golden_ref("config1_volumescene"), "config1_volumescene")
+    assert np.all(bgra[..., 3] == 1.0)
