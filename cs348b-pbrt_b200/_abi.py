@@ -111,5 +111,5 @@ EXPORTS = [
     "pv_intersect", "pv_occluded", "pv_transmittance", "pv_gather", "pv_gather_dev", "pv_lphoton",
     "pv_gather_stats_get", "pv_last_kernel_ms", "pv_last_march_ms", "pv_last_phase_ms", "pv_launch_count", "pv_comm_unique_id", "pv_comm_init", "pv_comm_init_all", "pv_comm_destroy", "pv_allgather_photons", "pv_broadcast_photons", "pv_shoot", "pv_shoot_blocks", "pv_shoot_finish", "pv_stream",
     "pv_shoot_maps", "pv_shoot_maps_ranks", "pv_get_map_photons", "pv_set_map_photons", "pv_radiance_photons", "pv_select_map", "pv_surface_lphoton", "pv_radiance_nearest", "pv_final_gather", "pv_set_radiance_lo",
-    "pv_volume_li", "pv_volume_li_dev", "pv_gather_indexed", "pv_volume_li_indexed",
+    "pv_volume_li", "pv_volume_li_dev", "pv_gather_indexed", "pv_volume_li_indexed", "pv_build_bvh",
 ]

@@ -240,6 +240,17 @@ class PhotonVolume:
         self._chk(self.lib.pv_lphoton(self.ctx, _vp(pts), _vp(w), C.c_uint64(n), C.c_uint32(self.nused), C.c_float(self.maxdist), _vp(L)))
         return L
 
+    # ---- BVHAccel::BVHAccel on the device (accelerators/bvh.cpp:196-577) --------
+    def build_bvh(self, prim_bounds, max_prims_in_node=4):
+        """LBVH over primitive bounds [n, 6] (pMin, pMax) -> (nodes: uint8 [32 * n_nodes] in the LinearBVHNode layout,
+        prim_order: uint32 [n], kernel time in ms).  max_prims_in_node as the reference's "maxnodeprims" (default 4, bvh.cpp:694)."""
+        pb = _f32(prim_bounds).reshape(-1, 6); n = len(pb)
+        nodes = np.zeros(32 * max(2 * n - 1, 1), np.uint8); order = np.zeros(n, np.uint32)
+        n_nodes = C.c_uint32(0); ms = C.c_float(0.0)
+        self._chk(self.lib.pv_build_bvh(self.ctx, _vp(pb), C.c_uint32(n), C.c_uint32(max_prims_in_node), _vp(nodes),
+                                        C.c_uint32(max(2 * n - 1, 1)), C.byref(n_nodes), _vp(order), C.byref(ms)))
+        return nodes[:32 * n_nodes.value].copy(), order, float(ms.value)
+
     # ---- Scene::Intersect / IntersectP -----------------------------------
     def Intersect(self, rays):
         rays = np.ascontiguousarray(rays); n = len(rays)

@@ -404,6 +404,15 @@ int pv_intersect(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint32_t *prim, fl
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PV_OK;
 }
+int pv_build_bvh(pv_ctx *ctx, const float *prim_bounds, uint32_t n_prims, uint32_t max_prims_in_node, pv_bvh_node *nodes, uint32_t nodes_cap,
+                 uint32_t *n_nodes, uint32_t *prim_order, float *device_ms) {
+    LOCK(ctx);
+    if (!n_nodes || (n_prims && (!prim_bounds || !nodes || !prim_order))) { ctx->err = "pv_build_bvh: null pointer"; return PV_EINVAL; }
+    if (max_prims_in_node < 1 || max_prims_in_node > 255) {       // BVHAccel clamps to 255 too (bvh.cpp:198): nPrimitives is a byte
+        ctx->err = "pv_build_bvh: max_prims_in_node must be in [1, 255]"; return PV_EINVAL;
+    }
+    return pvi_build_bvh(ctx, prim_bounds, n_prims, max_prims_in_node, nodes, nodes_cap, n_nodes, prim_order, device_ms);
+}
 int pv_occluded(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint8_t *hit) {
     LOCK(ctx);
     if (n && (!rays || !hit)) { ctx->err = "pv_occluded: null pointer"; return PV_EINVAL; }

@@ -134,6 +134,9 @@ int pvi_volume_li(pv_ctx *ctx, int integrator, const pv_ray *d_rays, uint64_t n,
 int pvi_intersect(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint32_t *d_prim, float *d_t);
 int pvi_occluded(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, uint8_t *d_hit);
 int pvi_transmittance(pv_ctx *ctx, const pv_ray *d_rays, uint64_t n, float step, const float *d_u, float *d_T);
+// pv_lbvh.cu
+int pvi_build_bvh(pv_ctx *ctx, const float *prim_bounds, uint32_t n, uint32_t max_prims, pv_bvh_node *nodes, uint32_t nodes_cap,
+                  uint32_t *n_nodes, uint32_t *prim_order, float *device_ms);
 // pv_api.cu
 int pvi_reserve_photons(pv_ctx *ctx, uint64_t n);
 // pv_comm.cu

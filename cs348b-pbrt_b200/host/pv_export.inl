@@ -52,23 +52,59 @@ static inline void pv_mat_out(const Transform &t, float *dst) {
 // slot in the light list as a placeholder of type PV_LIGHT_UNKNOWN_SLOT (power filled in) instead of failing the export, so the
 // oracle can be given such lights on the side under the reference's own light indices (area lights).
 #define PV_LIGHT_UNKNOWN_SLOT 100
+// A BVH builder the exporter can call for a scene whose aggregate does not hold a LinearBVHNode array (Accelerator "kdtree" /
+// "grid"), or when the caller wants the device's tree in place of the reference's (PV_BVH=gpu): the adapter passes one that calls
+// pv_build_bvh on its context.  bounds: 6 floats per primitive; fills nodes and order (position in the reordered primitive array
+// -> index into the list the bounds came from).
+struct PvBvhBuilder {
+    virtual bool build(const float *bounds, uint32_t n, uint32_t max_prims_in_node, std::vector<pv_bvh_node> &nodes,
+                       std::vector<uint32_t> &order, std::string &err) = 0;
+    bool force;                 // use it even when the aggregate is a BVHAccel
+    PvBvhBuilder() : force(false) {}
+    virtual ~PvBvhBuilder() {}
+};
+
 static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &err, bool medium_only = false,
-                            bool keep_unknown_lights = false) {
+                            bool keep_unknown_lights = false, PvBvhBuilder *builder = NULL) {
     BVHAccel *bvh = medium_only ? NULL : dynamic_cast<BVHAccel *>(scene->aggregate);
-    if (!bvh && !medium_only) { err = "pv: the scene aggregate is not the \"bvh\" accelerator"; return false; }
-    const uint32_t nPrims = bvh ? (uint32_t)bvh->primitives.size() : 0u;
-    const LinearBVHNode *nodes = bvh ? (const LinearBVHNode *)bvh->nodes : NULL;
-    uint32_t nNodes = 0;
-    if (nodes) {   // depth-first layout (flattenBVHTree bvh.cpp:559-577): the node count is the largest index reached + 1
-        std::vector<uint32_t> todo; todo.push_back(0);
-        while (!todo.empty()) {
-            uint32_t i = todo.back(); todo.pop_back();
-            if (i + 1 > nNodes) nNodes = i + 1;
-            if (nodes[i].nPrimitives == 0) { todo.push_back(i + 1); todo.push_back(nodes[i].secondChildOffset); }
+    // the fully refined primitives and, per position of the device's primitive array, which of them sits there
+    std::vector<Reference<Primitive> > refined;
+    const std::vector<Reference<Primitive> > *prims = bvh ? &bvh->primitives : NULL;
+    std::vector<uint32_t> order;
+    hs.nodes.clear();
+    if (!medium_only && (!bvh || (builder && builder->force))) {
+        if (!builder) { err = "pv: the scene aggregate is not the \"bvh\" accelerator (and no device BVH builder was given)"; return false; }
+        uint32_t max_prims = 4;                                   // the reference's "maxnodeprims" default (accelerators/bvh.cpp:694)
+        if (bvh) max_prims = bvh->maxPrimsInNode;
+        else if (KdTreeAccel *kd = dynamic_cast<KdTreeAccel *>(scene->aggregate)) prims = &kd->primitives;   // refined by its ctor (kdtreeaccel.cpp:96-98)
+        else if (GridAccel *ga = dynamic_cast<GridAccel *>(scene->aggregate)) {
+            for (size_t i = 0; i < ga->primitives.size(); ++i) ga->primitives[i]->FullyRefine(refined);       // grid.cpp:46-51 may leave them unrefined
+            prims = &refined;
+        } else { err = "pv: the scene aggregate is none of the \"bvh\", \"kdtree\", \"grid\" accelerators"; return false; }
+        std::vector<float> bounds(6 * prims->size());
+        for (size_t i = 0; i < prims->size(); ++i) {
+            BBox b = (*prims)[i]->WorldBound();
+            bounds[6 * i + 0] = b.pMin.x; bounds[6 * i + 1] = b.pMin.y; bounds[6 * i + 2] = b.pMin.z;
+            bounds[6 * i + 3] = b.pMax.x; bounds[6 * i + 4] = b.pMax.y; bounds[6 * i + 5] = b.pMax.z;
         }
+        if (!builder->build(bounds.data(), (uint32_t)prims->size(), max_prims, hs.nodes, order, err)) return false;
+    } else if (bvh) {
+        const LinearBVHNode *nodes = (const LinearBVHNode *)bvh->nodes;
+        uint32_t nNodes = 0;
+        if (nodes) {   // depth-first layout (flattenBVHTree bvh.cpp:559-577): the node count is the largest index reached + 1
+            std::vector<uint32_t> todo; todo.push_back(0);
+            while (!todo.empty()) {
+                uint32_t i = todo.back(); todo.pop_back();
+                if (i + 1 > nNodes) nNodes = i + 1;
+                if (nodes[i].nPrimitives == 0) { todo.push_back(i + 1); todo.push_back(nodes[i].secondChildOffset); }
+            }
+        }
+        hs.nodes.resize(nNodes);
+        if (nNodes) memcpy(hs.nodes.data(), nodes, sizeof(pv_bvh_node) * nNodes);
     }
-    hs.nodes.resize(nNodes);
-    if (nNodes) memcpy(hs.nodes.data(), nodes, sizeof(pv_bvh_node) * nNodes);
+    const uint32_t nPrims = prims ? (uint32_t)prims->size() : 0u;
+    const uint32_t nNodes = (uint32_t)hs.nodes.size();
+    if (order.empty()) { order.resize(nPrims); for (uint32_t i = 0; i < nPrims; ++i) order[i] = i; }
     hs.tri.assign(9 * (size_t)nPrims, 0.f);
     hs.prim_material.assign(nPrims, 0u);
     hs.materials.clear();
@@ -79,7 +115,7 @@ static bool pv_export_scene(const Scene *scene, PvHostScene &hs, std::string &er
     DifferentialGeometry dummy;
     bool warned_uv = false;
     for (uint32_t i = 0; i < nPrims; ++i) {
-        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
+        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>((*prims)[order[i]].GetPtr());
         if (!gp) { err = "pv: a primitive is not a GeometricPrimitive (instancing is out of scope)"; return false; }
         const Triangle *t = dynamic_cast<const Triangle *>(gp->shape.GetPtr());
         const Sphere *sph = t ? NULL : dynamic_cast<const Sphere *>(gp->shape.GetPtr());

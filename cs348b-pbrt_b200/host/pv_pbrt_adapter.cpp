@@ -55,6 +55,8 @@
 #include "core/progressreporter.h"
 #include "core/photonshooter.h"
 #include "accelerators/bvh.h"
+#include "accelerators/kdtreeaccel.h"
+#include "accelerators/grid.h"
 #include "shapes/trianglemesh.h"
 #include "shapes/sphere.h"
 #include "lights/point.h"
@@ -108,6 +110,39 @@ double now_s() { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 
 
 void pv_fail(const char *what, int rc) {
     Severe("%s failed (%d): %s", what, rc, pv_last_error(g_pv.ctx));
+}
+
+// The scene BVH built on the device (pv_build_bvh, csrc/pv_lbvh.cu) for scenes whose aggregate holds no LinearBVHNode array
+// (Accelerator "kdtree", pbrt's own default, and "grid"), or for every scene under PV_BVH=gpu.  The reference's per-ray CPU code
+// (surface integrator) keeps using the scene's own aggregate; the device kernels use this tree.
+struct PvDeviceBvh : PvBvhBuilder {
+    bool build(const float *bounds, uint32_t n, uint32_t max_prims, std::vector<pv_bvh_node> &nodes, std::vector<uint32_t> &order,
+               std::string &err) {
+        nodes.resize(n ? 2 * (size_t)n - 1 : 0); order.resize(n);
+        uint32_t n_nodes = 0; float ms = 0.f;
+        double t0 = now_s();
+        int rc = pv_build_bvh(g_pv.ctx, bounds, n, max_prims, nodes.data(), (uint32_t)nodes.size(), &n_nodes, order.data(), &ms);
+        if (rc) { err = std::string("pv_build_bvh: ") + pv_last_error(g_pv.ctx); return false; }
+        nodes.resize(n_nodes);
+        fprintf(stderr, "[pv] scene BVH built on the GPU: %u primitives -> %u nodes (leaves of <= %u), %.2f ms of kernels, %.1f ms with copies\n",
+                n, n_nodes, max_prims, ms, 1e3 * (now_s() - t0));
+        return true;
+    }
+};
+std::vector<int> pv_device_list();
+// export + pv_create + pv_set_scene, the common start of every device path
+bool pv_export_and_set(const Scene *scene, std::string &err, bool medium_only = false) {
+    if (!g_pv.ctx) {
+        int rc = pv_create(&g_pv.ctx, pv_device_list()[0]);
+        if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
+    }
+    PvDeviceBvh builder;
+    const char *mode = getenv("PV_BVH");
+    builder.force = mode && !strcmp(mode, "gpu");
+    if (!pv_export_scene(scene, g_pv.scene, err, medium_only, false, &builder)) return false;
+    int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
+    if (rc) pv_fail("pv_set_scene", rc);
+    return true;
 }
 
 // The three VolumeIntegrator plugins whose Li runs on the device, seen through one pair of glasses.
@@ -286,13 +321,8 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         return;
     }
     std::string err;
-    if (!pv_export_scene(scene, g_pv.scene, err)) Severe("%s", err.c_str());
-    if (!g_pv.ctx) {
-        int rc = pv_create(&g_pv.ctx, pv_device_list()[0]);
-        if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
-    }
-    int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
-    if (rc) pv_fail("pv_set_scene", rc);
+    if (!pv_export_and_set(scene, err)) Severe("%s", err.c_str());
+    int rc;
     g_pv.stepsize = vi->stepSize; g_pv.maxdist = vi->maxDist; g_pv.nused = (uint32_t)vi->nUsed; g_pv.volint = -1;
     const char *seed = getenv("PV_SEED");
     g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
@@ -576,19 +606,13 @@ EmissionIntegrator *CreateEmissionVolumeIntegrator(const ParamSet &params) {
 // a scene file unless the surface integrator is a photon map, whose CPU pass is then the reference's own).
 static void pv_setup_volint(const Scene *scene, const PvVolInt &vi) {
     std::string err;
-    if (!pv_export_scene(scene, g_pv.scene, err)) {
+    if (!pv_export_and_set(scene, err)) {
         // "emission" is pbrt's default volume integrator and reads only the medium: a scene whose surfaces or lights are off
         // this path (area lights, other shapes ...) still runs on the device, with the medium alone exported
         std::string err2;
-        if (vi.kind != PV_VOLINT_EMISSION || !pv_export_scene(scene, g_pv.scene, err2, true)) Severe("%s", err.c_str());
+        if (vi.kind != PV_VOLINT_EMISSION || !pv_export_and_set(scene, err2, true)) Severe("%s", err.c_str());
         Warning("%s -- the emission integrator needs the medium only, exporting that", err.c_str());
     }
-    if (!g_pv.ctx) {
-        int rc = pv_create(&g_pv.ctx, pv_device_list()[0]);
-        if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
-    }
-    int rc = pv_set_scene(g_pv.ctx, &g_pv.scene.desc);
-    if (rc) pv_fail("pv_set_scene", rc);
     const char *seed = getenv("PV_SEED");
     g_pv.seed = seed ? strtoull(seed, NULL, 0) : 0;
     g_pv.stepsize = vi.stepSize; g_pv.volint = vi.kind; g_pv.ready = true;

@@ -38,6 +38,36 @@ class Scene:
     def n_prims(self):
         return len(self.prim_material)
 
+    def prim_bounds(self):
+        """WorldBound() of every primitive, float32 [n, 6]: a triangle's is the bound of its vertices (shapes/trianglemesh.cpp:116-121);
+        a sphere's is its object-space box [-r, r]^2 x [zmin, zmax] through ObjectToWorld (shapes/sphere.cpp:53-56,
+        core/transform.cpp:171-181)"""
+        v = np.asarray(self.tri_verts, np.float32).reshape(-1, 3, 3)
+        b = np.concatenate([v.min(axis=1), v.max(axis=1)], axis=1).astype(np.float32)
+        if self.prim_shape is not None and len(self.spheres):
+            for i in np.nonzero(np.asarray(self.prim_shape) != A.SHAPE_TRIANGLE)[0]:
+                sp = self.spheres[int(self.prim_shape[i])]
+                m = np.array(list(sp.object_to_world), np.float32).reshape(4, 4)
+                r = np.float32(sp.radius)
+                c = np.array([[x, y, z, 1.0] for x in (-r, r) for y in (-r, r) for z in (sp.zmin, sp.zmax)], np.float32)
+                w = c @ m.T
+                w = w[:, :3] / w[:, 3:4]
+                b[i, :3] = w.min(axis=0); b[i, 3:] = w.max(axis=0)
+        return b
+
+    def with_bvh(self, nodes, prim_order):
+        """the same scene over another BVH: `nodes` (uint8, 32 bytes per node) whose leaves index the primitives permuted by
+        prim_order (new position -> old index), as pv_build_bvh returns them"""
+        import copy
+        s = copy.copy(self)
+        o = np.asarray(prim_order, np.int64)
+        s.nodes = np.ascontiguousarray(nodes, np.uint8); s.n_nodes = len(s.nodes) // 32
+        s.tri_verts = np.ascontiguousarray(np.asarray(self.tri_verts, np.float32).reshape(-1, 9)[o].reshape(-1))
+        s.prim_material = np.ascontiguousarray(np.asarray(self.prim_material, np.uint32)[o])
+        if self.prim_shape is not None:
+            s.prim_shape = np.ascontiguousarray(np.asarray(self.prim_shape, np.uint32)[o])
+        return s
+
     def desc(self):
         d = A.SceneDesc()
         self._nodes_buf = np.ascontiguousarray(self.nodes)

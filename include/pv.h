@@ -230,6 +230,23 @@ int pv_intersect(pv_ctx *ctx, const pv_ray *rays, uint64_t n,
                  uint32_t *prim, float *t);
 int pv_occluded(pv_ctx *ctx, const pv_ray *rays, uint64_t n, uint8_t *hit);
 
+/* ---- BVHAccel::BVHAccel (accelerators/bvh.cpp:196-300: bounds ->
+ *      recursiveBuild :301-556 -> flattenBVHTree :559-577), built on the
+ *      device as a Morton-code LBVH -------------------------- */
+/* prim_bounds: 6 floats per primitive (WorldBound(): pMin.xyz, pMax.xyz).
+ * nodes: the reference's depth-first LinearBVHNode array, nodes_cap >=
+ * 2*n_prims - 1 always suffices; *n_nodes = nodes written.  prim_order[i] =
+ * index of the caller's primitive that sits at position i of the reordered
+ * primitive array the leaves point into (the caller permutes tri_verts /
+ * prim_material / prim_shape by it before pv_set_scene, as BVHAccel swaps
+ * its `primitives` with orderedPrims, bvh.cpp:287).  A subtree of at most
+ * max_prims_in_node (1..255) primitives becomes one leaf.  device_ms
+ * (optional): time of the build's kernels.                                   */
+int pv_build_bvh(pv_ctx *ctx, const float *prim_bounds, uint32_t n_prims,
+                 uint32_t max_prims_in_node, pv_bvh_node *nodes,
+                 uint32_t nodes_cap, uint32_t *n_nodes, uint32_t *prim_order,
+                 float *device_ms);
+
 /* ---- PhotonVolumeIntegrator::Transmittance (photonvolume.cpp:15-30) ----- */
 /* step is the tau() step (stepSize or 4*stepSize), offset_u[n] the jitter.  */
 int pv_transmittance(pv_ctx *ctx, const pv_ray *rays, uint64_t n, float step,

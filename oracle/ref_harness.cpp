@@ -51,6 +51,8 @@
 #include "core/camera.h"
 #include "core/intersection.h"
 #include "accelerators/bvh.h"
+#include "accelerators/kdtreeaccel.h"
+#include "accelerators/grid.h"
 #include "shapes/trianglemesh.h"
 #include "shapes/sphere.h"
 #include "lights/point.h"

@@ -34,7 +34,36 @@ int pv_create(pv_ctx **out, int device) {
     return PV_OK;
 }
 void pv_destroy(pv_ctx *ctx) { if (ctx) logf_("destroy dev=%d\n", ctx->device); free(ctx); }
-int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) { logf_("set_scene dev=%d prims=%u lights=%u\n", ctx->device, s->n_prims, s->n_lights); return PV_OK; }
+int pv_set_scene(pv_ctx *ctx, const pv_scene_desc *s) {
+    /* order= : per position of the primitive array, a fingerprint of the triangle there (so a test sees a permutation) */
+    char buf[4096]; int o = 0; buf[0] = 0;
+    for (uint32_t i = 0; i < s->n_prims && i < 64 && o < 4000; ++i) {
+        double f = 0.; for (int k = 0; k < 9; ++k) f += (k + 1) * (double)s->tri_verts[9 * i + k];
+        o += snprintf(buf + o, sizeof(buf) - o, "%s%ld", i ? "," : "", (long)(1000. * f) * 8 + (long)(1000.f * s->materials[s->prim_material[i]].kd[29]) % 8);
+    }
+    logf_("set_scene dev=%d prims=%u lights=%u nodes=%u order:%s\n", ctx->device, s->n_prims, s->n_lights, s->n_nodes, buf);
+    return PV_OK;
+}
+/* the double's "BVH": one leaf holding everything (scenes of the host tests have a dozen triangles); MOCK_PV_BVH_REVERSE=1 hands the
+ * primitives back in reverse order */
+int pv_build_bvh(pv_ctx *ctx, const float *pb, uint32_t n, uint32_t max_prims, pv_bvh_node *nodes, uint32_t cap, uint32_t *n_nodes,
+                 uint32_t *order, float *ms) {
+    const char *rev = getenv("MOCK_PV_BVH_REVERSE");
+    logf_("build_bvh dev=%d n=%u maxprims=%u cap=%u\n", ctx->device, n, max_prims, cap);
+    if (n > 255 || cap < 1) return PV_EINVAL;
+    memset(&nodes[0], 0, sizeof(nodes[0]));
+    for (int k = 0; k < 3; ++k) { nodes[0].bounds[k] = 1e30f; nodes[0].bounds[3 + k] = -1e30f; }
+    for (uint32_t i = 0; i < n; ++i) {
+        order[i] = (rev && rev[0] == '1') ? n - 1 - i : i;
+        for (int k = 0; k < 3; ++k) {
+            if (pb[6 * i + k] < nodes[0].bounds[k]) nodes[0].bounds[k] = pb[6 * i + k];
+            if (pb[6 * i + 3 + k] > nodes[0].bounds[3 + k]) nodes[0].bounds[3 + k] = pb[6 * i + 3 + k];
+        }
+    }
+    nodes[0].offset = 0; nodes[0].n_primitives = (uint8_t)n;
+    *n_nodes = n ? 1 : 0; if (ms) *ms = 0.f;
+    return PV_OK;
+}
 int pv_shoot(pv_ctx *ctx, uint64_t wanted, const pv_shoot_params *p, pv_shoot_stats *st) {
     (void)p; ctx->n_photons = wanted; if (st) { memset(st, 0, sizeof(*st)); st->paths = 4096; }
     logf_("shoot dev=%d n=%llu\n", ctx->device, (unsigned long long)wanted);

@@ -161,3 +161,45 @@ def test_material_off_the_path_is_refused_not_approximated(mock, tmp_path, pkg):
     assert "neither matte nor glass" in out.stderr
     lines = log.read_text().splitlines() if log.exists() else []
     assert not [l for l in lines if l.startswith("shoot")]
+
+
+@pytest.mark.parametrize("accel", ["kdtree", "grid", "bvh+PV_BVH=gpu"])
+def test_scene_without_a_reference_bvh_gets_one_from_the_device(mock, tmp_path, pkg, accel):
+    """Accelerator "kdtree" (pbrt's own default) and "grid" hold no LinearBVHNode array to export: the adapter hands the bounds of
+    the refined primitives to pv_build_bvh (max 4 per leaf, the reference's "maxnodeprims" default), and describes the scene to the
+    device with the primitives IN THE ORDER THE BUILDER RETURNED and the builder's node array.  PV_BVH=gpu asks for the same with
+    the "bvh" accelerator.  The double returns a one-leaf tree, with the primitives reversed under MOCK_PV_BVH_REVERSE=1."""
+    from cs348b_pbrt_b200 import scenes
+    vol = scenes.VOLINT_MEDIA["volint_homog"][0]
+    text = scenes.volint_pbrt("single", vol, xres=32, yres=32, outfile="acc.pfm")
+    assert "WorldBegin" in text and "Accelerator" not in text
+    env_extra = {}
+    if accel.startswith("bvh"):
+        env_extra["PV_BVH"] = "gpu"
+    else:
+        text = text.replace("WorldBegin", 'Accelerator "%s"\nWorldBegin' % accel, 1)
+    orders = []
+    for rev in ("0", "1"):
+        scene = tmp_path / ("acc%s.pbrt" % rev); scene.write_text(text)
+        log = tmp_path / ("acc%s.log" % rev)
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log), MOCK_PV_BVH_REVERSE=rev, **env_extra)
+        env.pop("PV_DEVICES", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", "2", str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = log.read_text().splitlines()
+        b = calls(lines, "build_bvh")
+        assert len(b) == 1 and b[0]["n"] == 12 and b[0]["maxprims"] == 4 and b[0]["cap"] >= 2 * 12 - 1
+        assert "scene BVH built on the GPU: 12 primitives -> 1 nodes" in out.stderr
+        s = [l for l in lines if l.startswith("set_scene ")]
+        assert len(s) == 1 and calls(lines, "set_scene")[0]["prims"] == 12 and calls(lines, "set_scene")[0]["nodes"] == 1
+        assert lines.index(s[0]) > lines.index([l for l in lines if l.startswith("build_bvh ")][0])
+        orders.append(s[0].split("order:")[1].split(","))
+    assert len(orders[0]) == 12 and orders[0] == orders[1][::-1] and orders[0] != orders[1]
+
+
+def test_the_reference_bvh_is_exported_when_there_is_one(mock, tmp_path, pkg):
+    """default route: Accelerator "bvh" -> the reference's own node array, no device build"""
+    from cs348b_pbrt_b200 import scenes
+    vol = scenes.VOLINT_MEDIA["volint_homog"][0]
+    _, log, err = render(mock, tmp_path, "refbvh", scenes.volint_pbrt("single", vol, xres=32, yres=32, outfile="refbvh.pfm"))
+    assert not calls(log, "build_bvh") and calls(log, "set_scene")[0]["nodes"] > 1

@@ -1,0 +1,191 @@
+"""GPU (-m gpu): pv_build_bvh, the scene BVH built on the device as a Morton-code LBVH (replaces BVHAccel's constructor,
+accelerators/bvh.cpp:196-577).  The reference has no LBVH to compare node for node, so parity is stated on what a BVH is FOR:
+  * the node array is a valid depth-first LinearBVHNode tree over exactly the given primitives (checked on the CPU, below), and
+  * Scene::Intersect / IntersectP through it return the SAME hits as through the reference's own SAH BVH: t bit for bit, primitive
+    ids identical after mapping through prim_order (the golden rays of tests/golden/*.npz were answered by the reference), and the
+    same as a brute-force tree evaluated by the CPU oracle on a triangle soup the reference never saw."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ALL_SCENES = ["cornell_homog", "cornell_grid32", "rainbow_vol", "prism_small", "sphere_glass", "sphere_disp", "cornell_exp"]
+NODE = np.dtype([("bounds", "<f4", 6), ("offset", "<u4"), ("n_primitives", "u1"), ("axis", "u1"), ("pad", "u1", 2)])
+
+
+def check_tree(nodes_u8, order, bounds, max_prims, morton_ordered=True):
+    """every invariant bvh_traverse relies on (accelerators/bvh.cpp:559-577, 585-636)"""
+    nd = np.frombuffer(nodes_u8.tobytes(), dtype=NODE)
+    n = len(bounds)
+    assert sorted(order.tolist()) == list(range(n))                       # a permutation of the caller's primitives
+    pb = bounds[order]
+    seen = np.zeros(n, np.int32)
+    depth_max = 0
+
+    def union(a, b):
+        return np.concatenate([np.minimum(a[:3], b[:3]), np.maximum(a[3:], b[3:])])
+
+    # explicit stack: (node, depth); children results gathered in post-order
+    result, order_ok = {}, [True]
+    stack = [(0, 1, False)]
+    end_of = {}
+    while stack:
+        i, depth, done = stack.pop()
+        depth_max = max(depth_max, depth)
+        node = nd[i]
+        if node["n_primitives"] > 0:
+            first, cnt = int(node["offset"]), int(node["n_primitives"])
+            assert cnt <= max_prims and first + cnt <= n
+            seen[first:first + cnt] += 1
+            b = pb[first]
+            for k in range(1, cnt):
+                b = union(b, pb[first + k])
+            assert np.array_equal(node["bounds"], b), ("leaf bounds", i)
+            result[i] = b; end_of[i] = i + 1
+        elif not done:
+            assert node["axis"] < 3 and i + 1 < len(nd) and i + 1 < node["offset"] < len(nd)
+            stack.append((i, depth, True)); stack.append((int(node["offset"]), depth + 1, False)); stack.append((i + 1, depth + 1, False))
+        else:
+            second = int(node["offset"])
+            assert end_of[i + 1] == second, ("depth-first layout", i)     # the first subtree ends where the second begins
+            b = union(result[i + 1], result[second])
+            assert np.array_equal(node["bounds"], b), ("interior bounds", i)
+            # the first child lies on the low side of the split axis (what `dirIsNeg[node->axis]` assumes, bvh.cpp:622-629)
+            a = int(node["axis"])
+            c0 = 0.5 * result[i + 1][a] + 0.5 * result[i + 1][3 + a]; c1 = 0.5 * result[second][a] + 0.5 * result[second][3 + a]
+            result[i] = b; end_of[i] = end_of[second]
+            del result[i + 1], result[second]
+            order_ok.append(c0 <= c1)
+    assert end_of[0] == len(nd)
+    assert np.all(seen == 1)                                              # every primitive in exactly one leaf
+    assert depth_max <= 64                                                # the traversal stack (pv_set_scene refuses deeper trees)
+    if morton_ordered:                                                    # first children on the low side of their axis: what makes front-to-back
+        assert np.mean(order_ok) > 0.9                                    # traversal cheap (a quality condition, not a correctness one)
+    return len(nd), depth_max
+
+
+def soup(n, seed, size=0.05):
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    # clustered: half of the triangles crowd into a small region, as meshes do
+    c[: n // 2] = (c[: n // 2] * np.float32(0.1) + np.float32(0.4)).astype(np.float32)
+    v = (c + rs.uniform(-size, size, (n, 3, 3)).astype(np.float32)).astype(np.float32)
+    return v.reshape(n, 9)
+
+
+def rays_into(n, seed, pkg):
+    rs = np.random.RandomState(seed)
+    o = rs.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    tgt = rs.uniform(-0.8, 0.8, (n, 3)).astype(np.float32)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+def brute_tree(bounds):
+    """an independent, trivially correct tree: leaves of up to 255 consecutive primitives IN THE CALLER'S ORDER under a balanced
+    hierarchy -- boxes overlap almost completely, so a traversal tests (nearly) every primitive"""
+    n = len(bounds)
+    out = []
+
+    def build(first, last):
+        i = len(out); out.append(None)
+        b = np.concatenate([bounds[first:last, :3].min(axis=0), bounds[first:last, 3:].max(axis=0)])
+        if last - first <= 255:
+            out[i] = (b, first, last - first, 0)
+        else:
+            mid = (first + last) // 2
+            build(first, mid)
+            second = len(out)
+            build(mid, last)
+            out[i] = (b, second, 0, 0)
+    build(0, n)
+    nd = np.zeros(len(out), dtype=NODE)
+    for i, (b, off, cnt, axis) in enumerate(out):
+        nd[i]["bounds"] = b; nd[i]["offset"] = off; nd[i]["n_primitives"] = cnt; nd[i]["axis"] = axis
+    return np.frombuffer(nd.tobytes(), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+@pytest.mark.parametrize("max_prims", [1, 4])
+def test_lbvh_gives_the_reference_hits(golden, pv_factory, name, max_prims):
+    g, scene = golden(name)
+    pv = pv_factory()
+    bounds = scene.prim_bounds()
+    nodes, order, _ = pv.build_bvh(bounds, max_prims)
+    check_tree(nodes, order, bounds, max_prims)
+    pv.set_scene(scene.with_bvh(nodes, order))
+    rays = g["hit_rays"]
+    prim, t = pv.Intersect(rays)
+    # closest hit: bit for bit.  One kind of ray may differ, and only in one direction: a ray that STARTS on a surface (a hit at
+    # exactly t == mint, which Triangle::Intersect accepts, trianglemesh.cpp:161) is seen or not depending on the box of the leaf
+    # that holds the surface -- the reference's slab test ends in the strict `tmax > ray.mint` (bvh.cpp:186-188), so a flat
+    # one-triangle box misses it and a box shared with other primitives finds it.  The goldens hold such rays on purpose.
+    same = t.view(np.uint32) == g["hit_t"].view(np.uint32)
+    on_surface = ~same & (t == rays["mint"])
+    assert np.all(same | on_surface) and on_surface.sum() <= 3
+    hit = (prim != 0xFFFFFFFF) & same
+    assert np.array_equal(prim[same] != 0xFFFFFFFF, g["hit_prim"][same] != 0xFFFFFFFF)
+    # ids: the golden ids index the REFERENCE's reordered primitive array, which is the order the scene file holds; ours map back
+    # through prim_order
+    assert np.array_equal(order[prim[hit]], g["hit_prim"][hit])
+    assert np.array_equal(pv.IntersectP(rays).astype(np.uint32)[same], g["hit_occluded"][same])
+
+
+def test_lbvh_on_a_triangle_soup_vs_brute_force(pkg, pv_factory, golden):
+    """20 000 random triangles, half of them crowded into 1/1000 of the volume: tree invariants, and hits against the CPU oracle
+    walking a brute-force tree over the same triangles"""
+    import oracle_lib as O
+    _, base = golden("cornell_homog")
+    tri = soup(20000, 7)
+    import copy
+    scene = copy.copy(base)
+    scene.tri_verts = tri.reshape(-1); scene.prim_material = np.zeros(len(tri), np.uint32); scene.prim_shape = None
+    scene.spheres = type(base.spheres)() if len(base.spheres) == 0 else base.spheres
+    bounds = scene.prim_bounds()
+    flat = copy.copy(scene); flat.nodes = brute_tree(bounds); flat.n_nodes = len(flat.nodes) // 32
+    g, _ = golden("cornell_homog")
+    rays = g["hit_rays"][:1500].copy()
+    o, d = rays_into(len(rays), 3, pkg)
+    rays["o"] = o; rays["d"] = d; rays["mint"] = 0.0; rays["maxt"] = np.inf
+    ref_prim, ref_t, ref_occ = O.intersect(flat, rays)
+    assert (ref_prim != 0xFFFFFFFF).mean() > 0.2
+    pv = pv_factory()
+    for max_prims in (1, 4, 16):
+        nodes, order, ms = pv.build_bvh(bounds, max_prims)
+        n_nodes, depth = check_tree(nodes, order, bounds, max_prims)
+        assert n_nodes <= 2 * len(tri) - 1
+        pv.set_scene(scene.with_bvh(nodes, order))
+        prim, t = pv.Intersect(rays)
+        assert np.array_equal(t.view(np.uint32), ref_t.view(np.uint32))
+        hit = prim != 0xFFFFFFFF
+        assert np.array_equal(hit, ref_prim != 0xFFFFFFFF)
+        same = order[prim[hit]] == ref_prim[hit]
+        assert same.mean() > 0.999                           # an exact tie between two triangles may resolve either way
+        assert np.array_equal(pv.IntersectP(rays), ref_occ)
+    # degenerate inputs
+    nodes, order, _ = pv.build_bvh(bounds[:1], 4)
+    assert len(nodes) == 32 and order.tolist() == [0]
+    nodes, order, _ = pv.build_bvh(np.repeat(bounds[:1], 300, axis=0), 4)        # 300 identical boxes: equal keys, split by position
+    check_tree(nodes, order, np.repeat(bounds[:1], 300, axis=0), 4)
+    with pytest.raises(pkg.PVError):
+        pv.build_bvh(bounds, 0)
+    bad = bounds.copy(); bad[5, 0] = np.nan
+    with pytest.raises(pkg.PVError):
+        pv.build_bvh(bad, 4)
+
+
+def test_lbvh_large_mesh_build_time(pv_factory):
+    """2 M triangles: the build is a handful of O(n) kernels + a 4-pass radix sort; the same tree on every call"""
+    tri = soup(2_000_000, 11, size=0.004)
+    v = tri.reshape(-1, 3, 3)
+    bounds = np.concatenate([v.min(axis=1), v.max(axis=1)], axis=1).astype(np.float32)
+    pv = pv_factory()
+    pv.build_bvh(bounds, 4)
+    nodes, order, ms = pv.build_bvh(bounds, 4)
+    nodes2, order2, _ = pv.build_bvh(bounds, 4)
+    assert np.array_equal(nodes, nodes2) and np.array_equal(order, order2)
+    nd = np.frombuffer(nodes.tobytes(), dtype=NODE)
+    leaves = nd["n_primitives"] > 0
+    assert nd["n_primitives"][leaves].sum() == len(bounds)
+    print("LBVH 2M triangles: %.2f ms device, %d nodes" % (ms, len(nd)))
+    assert ms < 50.0
