@@ -102,7 +102,11 @@ struct PvBridge {
     // (replicate the map, shard the camera rays).  Empty unless PV_DEVICES names more than one device.
     std::vector<pv_ctx *> replicas;
     std::vector<float> rad_pos, rad_nrm, rad_Lo;
-    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), volint(-1), fg_ctx(NULL) {}
+    // the caustic and indirect maps as the device pass left them (planes), for the LPhoton lookups of primary hits; and the
+    // contexts that hold them with their grids (one lookup grid per context)
+    std::vector<float> surf_pos[2], surf_wi[2], surf_alpha[2];
+    pv_ctx *surf_ctx[2];
+    PvBridge() : ctx(NULL), stepsize(1.f), maxdist(.1f), nused(250), seed(0), n_indirect(0), ready(false), volint(-1), fg_ctx(NULL) { surf_ctx[0] = surf_ctx[1] = NULL; }
 };
 PvBridge g_pv;
 
@@ -246,11 +250,19 @@ std::vector<std::vector<PvRecord> > *g_records = NULL;
 // shooter has no indirect map (so that Li adds neither the final gather nor the indirect estimate); rays spawned by specular
 // bounces re-enter through SamplerRenderer::Li and use the unmodified integrator, final gathering included.
 struct PvGatherRay { uint32_t rec; Spectrum C; pv_ray ray; };
+// One LPhoton lookup of a primary hit (photonmap.cpp:62-108, diffuse branch): where, the faceforwarded shading normal, and the
+// two reflectances the sums are multiplied with afterwards.
+struct PvLookup { uint32_t rec; float p[3], nf[3]; Spectrum rr, rt; };
 struct PvFinalGather {
-    PhotonIntegrator *full, *primary;      // the scene's integrator, and its clone without the indirect map
+    PhotonIntegrator *full, *primary;      // the scene's integrator, and its clone without the maps whose terms run on the device
+    bool gather_rays;                      // final gathering of primary hits as one pv_final_gather per group
+    bool lookup[2];                        // LPhoton of primary hits on the caustic map (:179) / on the indirect map when final gathering is off (:308)
     std::vector<std::vector<PvGatherRay> > rays;      // per render task
-    uint64_t next_index, total_rays; double gpu_seconds;
-    PvFinalGather() : full(NULL), primary(NULL), next_index(0), total_rays(0), gpu_seconds(0) {}
+    std::vector<std::vector<PvLookup> > lookups;      // per render task; caustic and indirect lookups of a hit share the record
+    uint64_t next_index, total_rays, total_lookups; double gpu_seconds, lookup_seconds;
+    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
+        lookup[0] = lookup[1] = false;
+    }
 };
 PvFinalGather *g_fg = NULL;
 
@@ -308,6 +320,27 @@ void pv_queue_final_gather(const PhotonIntegrator *pi, const RayDifferential &ra
             out.push_back(g);
         }
 }
+// The host half of LPhoton for one shaded point (photonmap.cpp:62-108).  On this path a surface is Lambertian or purely specular
+// (any other material stops the drop-in before a photon is shot), so a point with non-specular components takes the DIFFUSE
+// branch: L = Lr * rho_r / pi + Lt * rho_t / pi, with Lr / Lt the kernel-weighted flux of the nLookup nearest photons arriving on
+// either side of Nf -- those two sums are pv_surface_lphoton; the reflectances are the reference's own BSDF::rho (which draws its
+// 2 x 36 stratified samples from the task's RNG exactly as LPhoton does, whatever the BxDFs then do with them).
+bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG &rng, MemoryArena &arena, uint32_t rec,
+                     std::vector<PvLookup> &out) {
+    BSDF *bsdf = isect.GetBSDF(ray, arena);
+    const BxDFType nonSpecular = BxDFType(BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_DIFFUSE | BSDF_GLOSSY);
+    if (bsdf->NumComponents(nonSpecular) == 0) return true;                    // LPhoton adds nothing (:68)
+    if (bsdf->NumComponents(BxDFType(BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_GLOSSY)) > 0) return false;   // glossy branch: not on this path
+    const Vector wo = -ray.d;
+    const Normal Nf = Faceforward(bsdf->dgShading.nn, wo);
+    PvLookup q; q.rec = rec;
+    q.p[0] = isect.dg.p.x; q.p[1] = isect.dg.p.y; q.p[2] = isect.dg.p.z;
+    q.nf[0] = Nf.x; q.nf[1] = Nf.y; q.nf[2] = Nf.z;
+    q.rr = bsdf->rho(wo, rng, BSDF_ALL_REFLECTION) * INV_PI;
+    q.rt = bsdf->rho(wo, rng, BSDF_ALL_TRANSMISSION) * INV_PI;
+    out.push_back(q);
+    return true;
+}
 }  // namespace
 
 // ------------------------------------------------------------------ PhotonShooter::Preprocess (core/photonshooter.cpp:457-526)
@@ -363,6 +396,7 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
         for (int k = 0; k < 2; ++k) {
             uint64_t n = ms.n[which[k]], got = 0;
             delete *maps[k]; *maps[k] = NULL;
+            g_pv.surf_pos[k].clear(); g_pv.surf_wi[k].clear(); g_pv.surf_alpha[k].clear();
             if (!n) continue;
             std::vector<float> pos(3 * n), wi(3 * n), alpha((size_t)PV_NSPEC * n);
             rc = pv_get_map_photons(g_pv.ctx, which[k], pos.data(), wi.data(), alpha.data(), NULL, n, &got);
@@ -374,6 +408,9 @@ void PhotonShooter::Preprocess(const Scene *scene, const Camera *camera, const R
                 p.alpha = Spectrum(0.f); memcpy(p.alpha.c, &alpha[(size_t)PV_NSPEC * i], sizeof(float) * PV_NSPEC);
             }
             *maps[k] = new KdTree<Photon>(photons);
+            // kept for the LPhoton lookups of primary hits (SamplerRenderer::Render)
+            g_pv.surf_pos[k].assign(pos.begin(), pos.begin() + 3 * got); g_pv.surf_wi[k].assign(wi.begin(), wi.begin() + 3 * got);
+            g_pv.surf_alpha[k].assign(alpha.begin(), alpha.begin() + (size_t)PV_NSPEC * got);
         }
         delete radianceMap; radianceMap = NULL;
         uint64_t nrad = ms.n[PV_MAP_RADIANCE];
@@ -628,11 +665,15 @@ SamplerRenderer::~SamplerRenderer() {
 }
 
 static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Sample *sample, RNG &rng,
-                                MemoryArena &arena, Intersection *isect, std::vector<PvGatherRay> *fg_out = NULL, uint32_t rec = 0) {
+                                MemoryArena &arena, Intersection *isect, int fg_task = -1, uint32_t rec = 0) {
     // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
     if (scene->Intersect(ray, isect)) {
-        if (fg_out) {       // a primary hit: Li without the final gather, whose rays are queued for the GPU
-            pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, *fg_out);
+        if (fg_task >= 0) {  // a primary hit: Li without the terms that run on the device, whose rays / lookups are queued
+            if (g_fg->gather_rays) pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, g_fg->rays[fg_task]);
+            if (g_fg->lookup[0] || g_fg->lookup[1]) {
+                if (!pv_queue_lookup(ray, *isect, rng, arena, rec, g_fg->lookups[fg_task]))
+                    Severe("pv: a surface with glossy components reached the device LPhoton (materials other than matte / glass are off this path)");
+            }
             return g_fg->primary->Li(scene, r, ray, *isect, sample, rng, arena);
         }
         return r->surfaceIntegrator->Li(scene, r, ray, *isect, sample, rng, arena);
@@ -683,7 +724,7 @@ void SamplerRendererTask::Run() {
                 rec.imageX = samples[i].imageX; rec.imageY = samples[i].imageY; rec.rayWeight = rayWeight;
                 rec.Ls = 0.f;
                 if (rayWeight > 0.f)
-                    rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i], g_fg ? &g_fg->rays[taskNum] : NULL,
+                    rec.Ls = pv_surface_term(sr, scene, rays[i], &samples[i], rng, arena, &isects[i], g_fg ? taskNum : -1,
                                              (uint32_t)out->size());
                 pv_fill_ray(rays[i], samples[i].oneD[vi.scatterSampleOffset][0], &rec.ray);
                 out->push_back(rec);
@@ -737,18 +778,43 @@ void SamplerRenderer::Render(const Scene *scene) {
 #else
     const char *fg_mode = NULL;
 #endif
-    if (g_pv.ready && pvi && pmi && pmi->finalGather && pmi->photonShooter && pmi->photonShooter->indirectMap && pmi->photonShooter->radianceMap &&
-        !g_pv.rad_pos.empty() &&
-        g_pv.n_indirect >= 50 && !(fg_mode && !strcmp(fg_mode, "cpu")) && !visualizeObjectIds) {
-        // member-wise copies made by the classes' own (implicit) copy constructors: a shooter that shows no indirect map, and an
-        // integrator that looks at it.  They share the maps with the originals and are never destroyed (their destructors would
-        // delete those maps a second time).
+    const bool fg_on = g_pv.ready && pvi && pmi && pmi->finalGather && pmi->photonShooter && pmi->photonShooter->indirectMap &&
+                       pmi->photonShooter->radianceMap && !g_pv.rad_pos.empty() && g_pv.n_indirect >= 50 &&
+                       !(fg_mode && !strcmp(fg_mode, "cpu")) && !visualizeObjectIds;
+    // ---- LPhoton of primary hits on the GPU: the caustic term (photonmap.cpp:179) whenever the device pass made a caustic map, and
+    // the indirect term (:308) when final gathering is off (with it on, the indirect map only guides the gather rays).  Both maps
+    // came from pv_shoot_maps, so the scene's materials are matte / glass and every lookup takes LPhoton's diffuse branch.
+    bool lp_on[2] = {false, false};
+    if (g_pv.ready && pvi && pmi && pmi->photonShooter && !visualizeObjectIds && !(fg_mode && !strcmp(fg_mode, "cpu"))) {
+        lp_on[0] = pmi->photonShooter->causticMap && !g_pv.surf_pos[0].empty();
+        lp_on[1] = !pmi->finalGather && pmi->photonShooter->indirectMap && !g_pv.surf_pos[1].empty();
+    }
+    if (fg_on || lp_on[0] || lp_on[1]) {
+        // member-wise copies made by the classes' own (implicit) copy constructors: a shooter that does not show the maps whose
+        // terms run on the device, and an integrator that looks at it.  They share the maps with the originals and are never
+        // destroyed (their destructors would delete those maps a second time).
         PhotonShooter *bare = new PhotonShooter(*pmi->photonShooter);
-        bare->indirectMap = NULL;
+        if (fg_on || lp_on[1]) bare->indirectMap = NULL;
+        if (lp_on[0]) bare->causticMap = NULL;
         fg.full = pmi;
         fg.primary = new PhotonIntegrator(*pmi);
         fg.primary->photonShooter = bare;
-        fg.rays.resize(nTasks);
+        fg.gather_rays = fg_on; fg.lookup[0] = lp_on[0]; fg.lookup[1] = lp_on[1];
+        fg.rays.resize(nTasks); fg.lookups.resize(nTasks);
+        const int map_id[2] = {PV_MAP_CAUSTIC, PV_MAP_INDIRECT};
+        for (int m = 0; m < 2; ++m) {
+            if (!lp_on[m]) continue;
+            if (!g_pv.surf_ctx[m]) {
+                int rc = pv_create(&g_pv.surf_ctx[m], pv_device_list()[0]);
+                if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
+            }
+            int rc = pv_set_map_photons(g_pv.surf_ctx[m], map_id[m], g_pv.surf_pos[m].data(), g_pv.surf_wi[m].data(), g_pv.surf_alpha[m].data(),
+                                        g_pv.surf_pos[m].size() / 3);
+            if (!rc) rc = pv_select_map(g_pv.surf_ctx[m], map_id[m], sqrtf(pmi->maxDistSquared), pmi->nLookup);
+            if (rc) Severe("surface-lookup context failed (%d): %s", rc, pv_last_error(g_pv.surf_ctx[m]));
+        }
+    }
+    if (fg_on) {
         if (!g_pv.fg_ctx) {
             int rc = pv_create(&g_pv.fg_ctx, pv_device_list()[0]);
             if (rc) Severe("pv_create failed (%d): %s", rc, pv_last_error(NULL));
@@ -760,12 +826,12 @@ void SamplerRenderer::Render(const Scene *scene) {
         if (!rc) rc = pv_set_radiance_lo(g_pv.fg_ctx, g_pv.rad_Lo.data(), nrad);
         if (!rc) rc = pv_select_map(g_pv.fg_ctx, PV_MAP_RADIANCE, sqrtf(pmi->maxDistSquared), pmi->nLookup);
         if (rc) Severe("final-gather context failed (%d): %s", rc, pv_last_error(g_pv.fg_ctx));
-        g_fg = &fg;
     }
+    if (fg.primary) g_fg = &fg;
     {
         ProgressReporter reporter(nTasks, "Rendering");
         // tasks run in groups so that the queued gather rays of a group (160 B each) stay within ~0.7 GB
-        const double raysPerTask = g_fg ? 2.0 * pmi->gatherSamples * sampler->samplesPerPixel * (double)nPixels / nTasks : 0.0;
+        const double raysPerTask = g_fg ? ((fg.gather_rays ? 2.0 * pmi->gatherSamples : 0.0) + 2.0) * sampler->samplesPerPixel * (double)nPixels / nTasks : 0.0;
         const int group = g_fg ? max(1, min(nTasks, (int)(4.0e6 / max(raysPerTask, 1.0)))) : nTasks;
         std::vector<float> Lindir;
         std::vector<pv_ray> grays;
@@ -779,6 +845,36 @@ void SamplerRenderer::Render(const Scene *scene) {
             WaitForAllTasks();
             for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
             if (!g_fg) continue;
+            // ---- the LPhoton lookups of this group: ONE pv_surface_lphoton per map, then Ls += Lr * rho_r / pi + Lt * rho_t / pi
+            size_t nl = 0;
+            for (int t = 0; t < nTasks; ++t) nl += fg.lookups[t].size();
+            if (nl) {
+                std::vector<float> pts(3 * nl), nfs(3 * nl), Lr(nl * PV_NSPEC), Lt(nl * PV_NSPEC);
+                size_t q = 0;
+                for (int t = 0; t < nTasks; ++t)
+                    for (size_t i = 0; i < fg.lookups[t].size(); ++i, ++q) {
+                        memcpy(&pts[3 * q], fg.lookups[t][i].p, 3 * sizeof(float)); memcpy(&nfs[3 * q], fg.lookups[t][i].nf, 3 * sizeof(float));
+                    }
+                const uint64_t paths[2] = {(uint64_t)pmi->photonShooter->nCausticPaths, (uint64_t)pmi->photonShooter->nIndirectPaths};
+                double tl = now_s();
+                for (int m = 0; m < 2; ++m) {
+                    if (!fg.lookup[m]) continue;
+                    int rc = pv_surface_lphoton(g_pv.surf_ctx[m], pts.data(), nfs.data(), nl, (uint32_t)pmi->nLookup, pmi->maxDistSquared, paths[m],
+                                                Lr.data(), Lt.data());
+                    if (rc) Severe("pv_surface_lphoton failed (%d): %s", rc, pv_last_error(g_pv.surf_ctx[m]));
+                    q = 0;
+                    for (int t = 0; t < nTasks; ++t)
+                        for (size_t i = 0; i < fg.lookups[t].size(); ++i, ++q) {
+                            const PvLookup &lk = fg.lookups[t][i];
+                            Spectrum sr(0.f), st(0.f);
+                            memcpy(sr.c, &Lr[q * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(st.c, &Lt[q * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                            records[t][lk.rec].Ls += sr * lk.rr + st * lk.rt;                     // photonmap.cpp:101-102
+                        }
+                    fg.total_lookups += nl;
+                }
+                fg.lookup_seconds += now_s() - tl;
+                for (int t = 0; t < nTasks; ++t) std::vector<PvLookup>().swap(fg.lookups[t]);
+            }
             // ---- the gather rays of this group: ONE pv_final_gather, then Ls += sum C * Lindir
             size_t ng = 0;
             for (int t = 0; t < nTasks; ++t) ng += fg.rays[t].size();
@@ -809,8 +905,12 @@ void SamplerRenderer::Render(const Scene *scene) {
         g_li.calls = g_li.batches = 0; g_li.seconds = 0;
     }
     if (g_fg) {
-        fprintf(stderr, "[pv] final gathering of primary hits on the GPU: %llu gather rays in %.3f s\n", (unsigned long long)fg.total_rays,
-                fg.gpu_seconds);
+        if (fg.gather_rays)
+            fprintf(stderr, "[pv] final gathering of primary hits on the GPU: %llu gather rays in %.3f s\n", (unsigned long long)fg.total_rays,
+                    fg.gpu_seconds);
+        if (fg.lookup[0] || fg.lookup[1])
+            fprintf(stderr, "[pv] LPhoton of primary hits on the GPU (%s%s%s map): %llu lookups in %.3f s\n", fg.lookup[0] ? "caustic" : "",
+                    fg.lookup[0] && fg.lookup[1] ? " + " : "", fg.lookup[1] ? "indirect" : "", (unsigned long long)fg.total_lookups, fg.lookup_seconds);
         g_fg = NULL;
     }
     g_records = NULL;

@@ -203,3 +203,43 @@ def test_the_reference_bvh_is_exported_when_there_is_one(mock, tmp_path, pkg):
     vol = scenes.VOLINT_MEDIA["volint_homog"][0]
     _, log, err = render(mock, tmp_path, "refbvh", scenes.volint_pbrt("single", vol, xres=32, yres=32, outfile="refbvh.pfm"))
     assert not calls(log, "build_bvh") and calls(log, "set_scene")[0]["nodes"] > 1
+
+
+@pytest.mark.parametrize("final_gather", [True, False])
+def test_lphoton_of_primary_hits_goes_to_the_device(mock, tmp_path, pkg, final_gather):
+    """photonmap.cpp:179 (caustic term) and, with final gathering off, :308 (indirect term): the LPhoton lookups of the primary hits
+    of a group of tasks go down as ONE pv_surface_lphoton per map, on a context of their own that holds that map and its grid
+    (k = the integrator's nused, path count = the shooter's for that map), and the sums come back multiplied with the surface's
+    rho / pi.  The clone of the integrator that shades primary hits no longer sees those maps (no CPU kd-tree lookup is left for
+    them); the frame is the same for 1 and 2 render threads."""
+    from cs348b_pbrt_b200 import scenes
+    def text(out):
+        t = scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=96, yres=96, outfile=out)
+        if final_gather:
+            t = t.replace('"bool finalgather" ["false"]', '"bool finalgather" ["true"] "integer finalgathersamples" [4]')
+        t = t.replace('"integer indirectphotons" [0]', '"integer indirectphotons" [500]')
+        assert '"integer causticphotons" [0]' in t
+        return t.replace('"integer causticphotons" [0]', '"integer causticphotons" [300]')
+    imgs, logs, errs = [], [], []
+    for cores in ("1", "2"):
+        name = "lp%s%d" % (cores, final_gather)
+        scene = tmp_path / (name + ".pbrt"); scene.write_text(text(name + ".pfm"))
+        log = tmp_path / (name + ".log")
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+        env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", cores, str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        imgs.append((tmp_path / (name + ".pfm")).read_bytes()); logs.append(log.read_text().splitlines()); errs.append(out.stderr)
+    assert imgs[0] == imgs[1]
+    log, err = logs[1], errs[1]
+    maps = [1] if final_gather else [1, 2]
+    sm = [c for c in calls(log, "set_map_photons") if c["map"] in (1, 2)]
+    assert [c["map"] for c in sm] == maps and [c["n"] for c in sm] == ([300] if final_gather else [300, 500])
+    lp = calls(log, "surface_lphoton")
+    assert sorted(set(c["map"] for c in lp)) == maps
+    assert all(c["k"] == 50 and c["paths"] == 4096 for c in lp)                  # nused default 50; the double's path count
+    per_map = [sum(c["n"] for c in lp if c["map"] == m) for m in maps]
+    m = re.search(r"LPhoton of primary hits on the GPU \((.*) map\): (\d+) lookups", err)
+    assert m and m.group(1) == ("caustic" if final_gather else "caustic + indirect") and int(m.group(2)) == sum(per_map)
+    assert per_map[0] > 2000 and len(set(per_map)) == 1                          # one lookup per primary hit on a diffuse surface, per map
+    assert bool(calls(log, "final_gather")) == final_gather

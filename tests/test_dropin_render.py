@@ -123,6 +123,8 @@ def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name):
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr        # the CUDA path ran, not a fallback
     assert "Shooting photons" not in out.stderr                               # ... and the reference's CPU shooting pass did not
+    if name in ("cornell_surf_e2e", "sphere_e2e"):                             # caustic map + final gathering: both terms of primary hits on the device
+        assert "LPhoton of primary hits on the GPU (caustic map)" in out.stderr and "final gathering of primary hits on the GPU" in out.stderr
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
 
 
@@ -255,3 +257,19 @@ def test_dropin_builds_the_scene_bvh_on_the_device(tmp_path, route):
     assert "scene BVH built on the GPU" in out.stderr
     assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, "cornell_surf_e2e.pfm")), golden_ref("cornell_surf_e2e"), "cornell_surf_e2e")
+
+
+@needs_bin
+def test_dropin_runs_lphoton_of_primary_hits_on_the_device(tmp_path):
+    """integrators/photonmap.cpp:179 and :308 -- the caustic AND (final gathering off) the indirect radiance estimate at primary hits:
+    every photon map from the device pass, glass wedge, 20 k indirect + 5 k caustic photons, 72 x 72, 4 spp.  The lookups of a group
+    of render tasks are ONE pv_surface_lphoton per map (surface_lphoton_kernel on a grid over that map), the sums times rho / pi are
+    added to the sample; the reference's kd-tree lookups are left with the rays behind specular bounces."""
+    name = "cornell_surf_nofg_e2e"
+    scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
+    out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
+    assert "LPhoton of primary hits on the GPU (caustic + indirect map)" in out.stderr
+    assert "final gathering of primary hits" not in out.stderr
+    assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
