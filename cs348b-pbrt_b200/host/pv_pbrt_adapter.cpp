@@ -85,6 +85,8 @@
 extern "C" void _ZN13PhotonShooter13RefPreprocessEPK5ScenePK6CameraPK8Renderer(PhotonShooter *, const Scene *, const Camera *,
                                                                               const Renderer *);
 
+static void pv_fill_ray(const RayDifferential &ray, float u_scatter, pv_ray *r);
+
 namespace {
 struct PvBridge {
     pv_ctx *ctx;
@@ -253,14 +255,21 @@ struct PvGatherRay { uint32_t rec; Spectrum C; pv_ray ray; };
 // One LPhoton lookup of a primary hit (photonmap.cpp:62-108, diffuse branch): where, the faceforwarded shading normal, and the
 // two reflectances the sums are multiplied with afterwards.
 struct PvLookup { uint32_t rec; float p[3], nf[3]; Spectrum rr, rt; };
+// One light sample of the direct lighting of a primary hit (EstimateDirect, core/integrator.cpp:137-163, delta light): the
+// VisibilityTester's segment, the jitter of the transmittance march (the rng.RandomFloat() of photonvolume.cpp:26) and the
+// spectrum C = f * Li * |wi . n| / pdf the visibility V * Tr is multiplied with.
+struct PvShadow { uint32_t rec; Spectrum C; pv_ray ray; float u; };
 struct PvFinalGather {
     PhotonIntegrator *full, *primary;      // the scene's integrator, and its clone without the maps whose terms run on the device
     bool gather_rays;                      // final gathering of primary hits as one pv_final_gather per group
     bool lookup[2];                        // LPhoton of primary hits on the caustic map (:179) / on the indirect map when final gathering is off (:308)
+    bool direct;                           // direct lighting of primary hits: shadow rays + their transmittance as one device batch per group
+    std::vector<std::vector<PvShadow> > shadows;      // per render task
+    uint64_t total_shadows; double shadow_seconds;
     std::vector<std::vector<PvGatherRay> > rays;      // per render task
     std::vector<std::vector<PvLookup> > lookups;      // per render task; caustic and indirect lookups of a hit share the record
     uint64_t next_index, total_rays, total_lookups; double gpu_seconds, lookup_seconds;
-    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
+    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), direct(false), total_shadows(0), shadow_seconds(0), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
         lookup[0] = lookup[1] = false;
     }
 };
@@ -340,6 +349,59 @@ bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG 
     q.rt = bsdf->rho(wo, rng, BSDF_ALL_TRANSMISSION) * INV_PI;
     out.push_back(q);
     return true;
+}
+// PhotonIntegrator::Li for a PRIMARY hit when every term that costs time runs on the device (integrators/photonmap.cpp:154-319):
+//   emission                       isect.Le(wo), here                                                              (:170)
+//   direct lighting                UniformSampleAllLights -> EstimateDirect (core/integrator.cpp:47-79, 137-163) for delta lights:
+//                                  Sample_L, the BSDF value and the cosine / pdf factor here with the reference's own objects; the
+//                                  shadow ray (VisibilityTester::Unoccluded = !scene->IntersectP) and its transmittance through
+//                                  the medium (VisibilityTester::Transmittance -> VolumeIntegrator::Transmittance, sample == NULL:
+//                                  step 4 * stepSize, offset rng.RandomFloat()) queued: pv_occluded + pv_transmittance per group
+//   caustic / indirect LPhoton     queued (pv_queue_lookup)                                                        (:179, :308)
+//   final gathering                queued (pv_queue_final_gather)                                                  (:183-296)
+//   specular bounces               the reference's SpecularReflect / SpecularTransmit, here: their rays re-enter through
+//                                  SamplerRenderer::Li and see the unmodified integrator                           (:310-317)
+// Used when all lights of the scene are delta lights (an area light's BSDF-sampling half needs the identity of the surface the
+// sampled ray hits; such scenes keep the clone route, with the reference's own UniformSampleAllLights).
+Spectrum pv_primary_li(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Intersection &isect, const Sample *sample,
+                       RNG &rng, MemoryArena &arena, int task, uint32_t rec) {
+    const PhotonIntegrator *pi = g_fg->full;
+    Spectrum L(0.f);
+    const Vector wo = -ray.d;
+    L += isect.Le(wo);
+    BSDF *bsdf = isect.GetBSDF(ray, arena);
+    const Point &p = bsdf->dgShading.p;
+    const Normal &n = bsdf->dgShading.nn;
+    std::vector<PvShadow> &out = g_fg->shadows[task];
+    for (uint32_t i = 0; i < scene->lights.size(); ++i) {
+        const Light *light = scene->lights[i];
+        const int nSamples = pi->lightSampleOffsets ? pi->lightSampleOffsets[i].nSamples : 1;
+        for (int j = 0; j < nSamples; ++j) {
+            LightSample lightSample = pi->lightSampleOffsets ? LightSample(sample, pi->lightSampleOffsets[i], j) : LightSample(rng);
+            Vector wi; float lightPdf; VisibilityTester visibility;
+            Spectrum Li = light->Sample_L(p, isect.rayEpsilon, lightSample, ray.time, &wi, &lightPdf, &visibility);
+            if (lightPdf > 0.f && !Li.IsBlack()) {
+                Spectrum f = bsdf->f(wo, wi, BxDFType(BSDF_ALL & ~BSDF_SPECULAR));
+                if (!f.IsBlack()) {
+                    PvShadow sh; sh.rec = rec;
+                    sh.C = f * Li * (AbsDot(wi, n) / lightPdf) / (float)nSamples;
+                    pv_fill_ray(RayDifferential(visibility.r), 0.f, &sh.ray);
+                    sh.u = rng.RandomFloat();
+                    out.push_back(sh);
+                }
+            }
+        }
+    }
+    if (g_fg->gather_rays) pv_queue_final_gather(pi, ray, isect, sample, arena, rec, g_fg->rays[task]);
+    if (g_fg->lookup[0] || g_fg->lookup[1]) {
+        if (!pv_queue_lookup(ray, isect, rng, arena, rec, g_fg->lookups[task]))
+            Severe("pv: a surface with glossy components reached the device LPhoton (materials other than matte / glass are off this path)");
+    }
+    if (ray.depth + 1 < pi->maxSpecularDepth) {
+        L += SpecularReflect(ray, bsdf, rng, isect, r, scene, sample, arena);
+        L += SpecularTransmit(ray, bsdf, rng, isect, r, scene, sample, arena);
+    }
+    return L;
 }
 }  // namespace
 
@@ -669,6 +731,7 @@ static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, co
     // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
     if (scene->Intersect(ray, isect)) {
         if (fg_task >= 0) {  // a primary hit: Li without the terms that run on the device, whose rays / lookups are queued
+            if (g_fg->direct) return pv_primary_li(r, scene, ray, *isect, sample, rng, arena, fg_task, rec);
             if (g_fg->gather_rays) pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, g_fg->rays[fg_task]);
             if (g_fg->lookup[0] || g_fg->lookup[1]) {
                 if (!pv_queue_lookup(ray, *isect, rng, arena, rec, g_fg->lookups[fg_task]))
@@ -789,7 +852,18 @@ void SamplerRenderer::Render(const Scene *scene) {
         lp_on[0] = pmi->photonShooter->causticMap && !g_pv.surf_pos[0].empty();
         lp_on[1] = !pmi->finalGather && pmi->photonShooter->indirectMap && !g_pv.surf_pos[1].empty();
     }
-    if (fg_on || lp_on[0] || lp_on[1]) {
+    // ---- direct lighting of primary hits on the GPU: when every light is a delta light (point / spot / distant) and every other
+    // term of Li that costs time is on the device as well, primary hits are shaded by pv_primary_li instead of the clone
+    bool direct_on = false;
+    if (g_pv.ready && pvi && pmi && pmi->photonShooter && !visualizeObjectIds && !(fg_mode && !strcmp(fg_mode, "cpu")) &&
+        scene->lights.size() > 0 && g_pv.scene.desc.n_nodes > 0) {
+        direct_on = true;
+        for (size_t i = 0; i < scene->lights.size(); ++i) direct_on = direct_on && scene->lights[i]->IsDeltaLight();
+        const PhotonShooter *psh = pmi->photonShooter;
+        if (psh->causticMap && !lp_on[0]) direct_on = false;
+        if (psh->indirectMap && !(pmi->finalGather ? fg_on : lp_on[1])) direct_on = false;
+    }
+    if (fg_on || lp_on[0] || lp_on[1] || direct_on) {
         // member-wise copies made by the classes' own (implicit) copy constructors: a shooter that does not show the maps whose
         // terms run on the device, and an integrator that looks at it.  They share the maps with the originals and are never
         // destroyed (their destructors would delete those maps a second time).
@@ -799,8 +873,8 @@ void SamplerRenderer::Render(const Scene *scene) {
         fg.full = pmi;
         fg.primary = new PhotonIntegrator(*pmi);
         fg.primary->photonShooter = bare;
-        fg.gather_rays = fg_on; fg.lookup[0] = lp_on[0]; fg.lookup[1] = lp_on[1];
-        fg.rays.resize(nTasks); fg.lookups.resize(nTasks);
+        fg.gather_rays = fg_on; fg.lookup[0] = lp_on[0]; fg.lookup[1] = lp_on[1]; fg.direct = direct_on;
+        fg.rays.resize(nTasks); fg.lookups.resize(nTasks); fg.shadows.resize(nTasks);
         const int map_id[2] = {PV_MAP_CAUSTIC, PV_MAP_INDIRECT};
         for (int m = 0; m < 2; ++m) {
             if (!lp_on[m]) continue;
@@ -831,7 +905,7 @@ void SamplerRenderer::Render(const Scene *scene) {
     {
         ProgressReporter reporter(nTasks, "Rendering");
         // tasks run in groups so that the queued gather rays of a group (160 B each) stay within ~0.7 GB
-        const double raysPerTask = g_fg ? ((fg.gather_rays ? 2.0 * pmi->gatherSamples : 0.0) + 2.0) * sampler->samplesPerPixel * (double)nPixels / nTasks : 0.0;
+        const double raysPerTask = g_fg ? ((fg.gather_rays ? 2.0 * pmi->gatherSamples : 0.0) + 2.0 + (fg.direct ? 1.2 * scene->lights.size() : 0.0)) * sampler->samplesPerPixel * (double)nPixels / nTasks : 0.0;
         const int group = g_fg ? max(1, min(nTasks, (int)(4.0e6 / max(raysPerTask, 1.0)))) : nTasks;
         std::vector<float> Lindir;
         std::vector<pv_ray> grays;
@@ -845,6 +919,31 @@ void SamplerRenderer::Render(const Scene *scene) {
             WaitForAllTasks();
             for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
             if (!g_fg) continue;
+            // ---- the shadow rays of this group's direct lighting: ONE pv_occluded + ONE pv_transmittance, then Ls += C * V * Tr
+            size_t nsh = 0;
+            for (int t = 0; t < nTasks; ++t) nsh += fg.shadows[t].size();
+            if (nsh) {
+                std::vector<pv_ray> srays(nsh); std::vector<float> su(nsh), sT(nsh * PV_NSPEC); std::vector<uint8_t> occ(nsh);
+                size_t q = 0;
+                for (int t = 0; t < nTasks; ++t)
+                    for (size_t i = 0; i < fg.shadows[t].size(); ++i, ++q) { srays[q] = fg.shadows[t][i].ray; su[q] = fg.shadows[t][i].u; }
+                double ts = now_s();
+                int rc = pv_occluded(g_pv.ctx, srays.data(), nsh, occ.data());
+                if (!rc) rc = pv_transmittance(g_pv.ctx, srays.data(), nsh, 4.f * pvi->stepSize, su.data(), sT.data());
+                if (rc) Severe("direct lighting on the device failed (%d): %s", rc, pv_last_error(g_pv.ctx));
+                fg.shadow_seconds += now_s() - ts; fg.total_shadows += nsh;
+                q = 0;
+                for (int t = 0; t < nTasks; ++t) {
+                    for (size_t i = 0; i < fg.shadows[t].size(); ++i, ++q) {
+                        if (occ[q]) continue;                                                     // !visibility.Unoccluded(scene)
+                        const PvShadow &sh = fg.shadows[t][i];
+                        Spectrum Tr(0.f);
+                        memcpy(Tr.c, &sT[q * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                        records[t][sh.rec].Ls += sh.C * Tr;                                        // Ld += f * Li * Tr * |wi.n| / pdf
+                    }
+                    std::vector<PvShadow>().swap(fg.shadows[t]);
+                }
+            }
             // ---- the LPhoton lookups of this group: ONE pv_surface_lphoton per map, then Ls += Lr * rho_r / pi + Lt * rho_t / pi
             size_t nl = 0;
             for (int t = 0; t < nTasks; ++t) nl += fg.lookups[t].size();
@@ -908,6 +1007,9 @@ void SamplerRenderer::Render(const Scene *scene) {
         if (fg.gather_rays)
             fprintf(stderr, "[pv] final gathering of primary hits on the GPU: %llu gather rays in %.3f s\n", (unsigned long long)fg.total_rays,
                     fg.gpu_seconds);
+        if (fg.direct)
+            fprintf(stderr, "[pv] direct lighting of primary hits on the GPU: %llu shadow rays (occlusion + transmittance) in %.3f s\n",
+                    (unsigned long long)fg.total_shadows, fg.shadow_seconds);
         if (fg.lookup[0] || fg.lookup[1])
             fprintf(stderr, "[pv] LPhoton of primary hits on the GPU (%s%s%s map): %llu lookups in %.3f s\n", fg.lookup[0] ? "caustic" : "",
                     fg.lookup[0] && fg.lookup[1] ? " + " : "", fg.lookup[1] ? "indirect" : "", (unsigned long long)fg.total_lookups, fg.lookup_seconds);

@@ -186,6 +186,22 @@ int pv_radiance_photons(pv_ctx *c, uint32_t k, float r2, const uint64_t *pc, flo
 }
 int pv_set_radiance_lo(pv_ctx *c, const float *Lo, uint64_t n) { (void)c; (void)Lo; (void)n; return PV_OK; }
 int pv_select_map(pv_ctx *c, int m, float r, uint32_t k) { (void)r; (void)k; c->selected = m; logf_("select_map dev=%d map=%d\n", c->device, m); return PV_OK; }
+/* shadow rays: a ray is "occluded" iff a hash of its origin says so (1 in 4); "transmittance" = a function of its length */
+int pv_occluded(pv_ctx *c, const pv_ray *r, uint64_t n, uint8_t *hit) {
+    for (uint64_t i = 0; i < n; ++i) hit[i] = ((int)(fabsf(r[i].o[0] * 13.f + r[i].o[1] * 5.f + r[i].o[2] * 3.f) * 8.f) % 4) == 0;
+    logf_("occluded dev=%d n=%llu\n", c->device, (unsigned long long)n);
+    return PV_OK;
+}
+int pv_transmittance(pv_ctx *c, const pv_ray *r, uint64_t n, float step, const float *u, float *T) {
+    int with_u = u != NULL;
+    for (uint64_t i = 0; i < n; ++i) {
+        float len = r[i].maxt < 1e30f ? r[i].maxt : 1.f;
+        for (int b = 0; b < PV_NSPEC; ++b) T[PV_NSPEC * i + b] = 1.f / (1.f + 0.1f * len);
+        if (u && !(u[i] >= 0.f && u[i] < 1.f)) with_u = 2;
+    }
+    logf_("transmittance dev=%d n=%llu step1000=%d u=%d\n", c->device, (unsigned long long)n, (int)(step * 1000.f + .5f), with_u);
+    return PV_OK;
+}
 /* "flux sums" of a surface lookup = a function of the query point alone (so the image does not depend on batching or thread count):
  * Lr from the position, Lt = 0 */
 int pv_surface_lphoton(pv_ctx *c, const float *pts, const float *nf, uint64_t n, uint32_t k, float r2, uint64_t paths, float *Lr, float *Lt) {

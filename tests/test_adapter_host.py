@@ -243,3 +243,37 @@ def test_lphoton_of_primary_hits_goes_to_the_device(mock, tmp_path, pkg, final_g
     assert m and m.group(1) == ("caustic" if final_gather else "caustic + indirect") and int(m.group(2)) == sum(per_map)
     assert per_map[0] > 2000 and len(set(per_map)) == 1                          # one lookup per primary hit on a diffuse surface, per map
     assert bool(calls(log, "final_gather")) == final_gather
+
+
+def test_direct_lighting_of_primary_hits_goes_to_the_device(mock, tmp_path, pkg):
+    """UniformSampleAllLights / EstimateDirect for delta lights (core/integrator.cpp:47-79, 137-163) at primary hits: the light sample,
+    BSDF value and cosine / pdf factor are the reference's own code per hit; the shadow rays of a group of render tasks and their
+    transmittance through the medium (VolumeIntegrator::Transmittance with sample == NULL: step = 4 * stepsize, a random offset
+    per ray) are ONE pv_occluded + ONE pv_transmittance.  Same frame for 1 and 2 render threads.  With an area light in the scene
+    the reference's own per-ray direct lighting stays (its BSDF-sampling half needs the identity of the surface a ray hits)."""
+    from cs348b_pbrt_b200 import scenes
+    def text(out, area=False):
+        t = scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=96, yres=96, outfile=out)
+        t = t.replace('"integer causticphotons" [0]', '"integer causticphotons" [300]')
+        return t.replace("WorldEnd", scenes.AREA_QUAD + "\nWorldEnd") if area else t
+    imgs, logs, errs = [], [], []
+    for name, cores, area in (("dl1", "1", False), ("dl2", "2", False), ("dla", "2", True)):
+        scene = tmp_path / (name + ".pbrt"); scene.write_text(text(name + ".pfm", area))
+        log = tmp_path / (name + ".log")
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+        env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", cores, str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        imgs.append((tmp_path / (name + ".pfm")).read_bytes()); logs.append(log.read_text().splitlines()); errs.append(out.stderr)
+    assert imgs[0] == imgs[1]
+    log, err = logs[1], errs[1]
+    occ, tr = calls(log, "occluded"), calls(log, "transmittance")
+    assert len(occ) == len(tr) >= 1 and [c["n"] for c in occ] == [c["n"] for c in tr]
+    assert all(c["step1000"] == 200 and c["u"] == 1 for c in tr)                  # 4 * stepsize (0.05); offsets in [0, 1)
+    m = re.search(r"direct lighting of primary hits on the GPU: (\d+) shadow rays", err)
+    assert m and int(m.group(1)) == sum(c["n"] for c in occ) > 2000               # one per lit diffuse primary hit and light
+    names = [l.split()[0] for l in log]
+    assert names.index("occluded") > names.index("build") and names.index("occluded") < names.index("gather")
+    # area light in the scene: no device direct lighting, the other device terms stay
+    assert not calls(logs[2], "occluded") and "direct lighting of primary hits" not in errs[2]
+    assert calls(logs[2], "surface_lphoton")

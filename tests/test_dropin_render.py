@@ -125,6 +125,7 @@ def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name):
     assert "Shooting photons" not in out.stderr                               # ... and the reference's CPU shooting pass did not
     if name in ("cornell_surf_e2e", "sphere_e2e"):                             # caustic map + final gathering: both terms of primary hits on the device
         assert "LPhoton of primary hits on the GPU (caustic map)" in out.stderr
+        assert "direct lighting of primary hits on the GPU" in out.stderr            # delta lights only: shadow rays + transmittance batched
         assert ("final gathering of primary hits on the GPU" in out.stderr) == (name == "cornell_surf_e2e")      # sphere_e2e has no indirect map
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
 
@@ -272,5 +273,6 @@ def test_dropin_runs_lphoton_of_primary_hits_on_the_device(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
     assert "LPhoton of primary hits on the GPU (caustic + indirect map)" in out.stderr
+    assert "direct lighting of primary hits on the GPU" in out.stderr
     assert "final gathering of primary hits" not in out.stderr
     assert_within_the_whole_image_tolerance(read_pfm(os.path.join(tmp_path, name + ".pfm")), golden_ref(name), name)
