@@ -350,7 +350,9 @@ bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG 
     out.push_back(q);
     return true;
 }
-// PhotonIntegrator::Li for a PRIMARY hit when every term that costs time runs on the device (integrators/photonmap.cpp:154-319):
+// PhotonIntegrator::Li for a hit whose every costly term runs on the device (integrators/photonmap.cpp:154-319) -- a primary hit
+// (throughput W = 1) or a hit behind specular bounces (W = the product of f * |wi . n| / pdf and of the volume transmittances
+// along the chain up to here):
 //   emission                       isect.Le(wo), here                                                              (:170)
 //   direct lighting                UniformSampleAllLights -> EstimateDirect (core/integrator.cpp:47-79, 137-163) for delta lights:
 //                                  Sample_L, the BSDF value and the cosine / pdf factor here with the reference's own objects; the
@@ -359,12 +361,17 @@ bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG 
 //                                  step 4 * stepSize, offset rng.RandomFloat()) queued: pv_occluded + pv_transmittance per group
 //   caustic / indirect LPhoton     queued (pv_queue_lookup)                                                        (:179, :308)
 //   final gathering                queued (pv_queue_final_gather)                                                  (:183-296)
-//   specular bounces               the reference's SpecularReflect / SpecularTransmit, here: their rays re-enter through
-//                                  SamplerRenderer::Li and see the unmodified integrator                           (:310-317)
+//   specular bounces               the reference's SpecularReflect / SpecularTransmit, here (:310-317).  Their rays re-enter through
+//                                  SamplerRenderer::Li, which finds the throughput of the bounce in tl_path and shades the next hit
+//                                  with this function again: the recursion only carries Le and the volume term back up, every
+//                                  queued term goes straight to the pixel's record with its throughput folded into its weight.
 // Used when all lights of the scene are delta lights (an area light's BSDF-sampling half needs the identity of the surface the
 // sampled ray hits; such scenes keep the clone route, with the reference's own UniformSampleAllLights).
-Spectrum pv_primary_li(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Intersection &isect, const Sample *sample,
-                       RNG &rng, MemoryArena &arena, int task, uint32_t rec) {
+struct PvPath { bool on; Spectrum W; int task; uint32_t rec; PvPath() : on(false), W(1.f), task(-1), rec(0) {} };
+thread_local PvPath tl_path;
+
+Spectrum pv_hit_li(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Intersection &isect, const Sample *sample,
+                   RNG &rng, MemoryArena &arena, int task, uint32_t rec, const Spectrum &W) {
     const PhotonIntegrator *pi = g_fg->full;
     Spectrum L(0.f);
     const Vector wo = -ray.d;
@@ -384,7 +391,7 @@ Spectrum pv_primary_li(const SamplerRenderer *r, const Scene *scene, const RayDi
                 Spectrum f = bsdf->f(wo, wi, BxDFType(BSDF_ALL & ~BSDF_SPECULAR));
                 if (!f.IsBlack()) {
                     PvShadow sh; sh.rec = rec;
-                    sh.C = f * Li * (AbsDot(wi, n) / lightPdf) / (float)nSamples;
+                    sh.C = W * (f * Li * (AbsDot(wi, n) / lightPdf) / (float)nSamples);
                     pv_fill_ray(RayDifferential(visibility.r), 0.f, &sh.ray);
                     sh.u = rng.RandomFloat();
                     out.push_back(sh);
@@ -392,14 +399,33 @@ Spectrum pv_primary_li(const SamplerRenderer *r, const Scene *scene, const RayDi
             }
         }
     }
-    if (g_fg->gather_rays) pv_queue_final_gather(pi, ray, isect, sample, arena, rec, g_fg->rays[task]);
+    if (g_fg->gather_rays) {
+        std::vector<PvGatherRay> &gr = g_fg->rays[task];
+        const size_t first = gr.size();
+        pv_queue_final_gather(pi, ray, isect, sample, arena, rec, gr);
+        for (size_t k = first; k < gr.size(); ++k) gr[k].C *= W;
+    }
     if (g_fg->lookup[0] || g_fg->lookup[1]) {
-        if (!pv_queue_lookup(ray, isect, rng, arena, rec, g_fg->lookups[task]))
+        std::vector<PvLookup> &lk = g_fg->lookups[task];
+        const size_t first = lk.size();
+        if (!pv_queue_lookup(ray, isect, rng, arena, rec, lk))
             Severe("pv: a surface with glossy components reached the device LPhoton (materials other than matte / glass are off this path)");
+        for (size_t k = first; k < lk.size(); ++k) { lk[k].rr *= W; lk[k].rt *= W; }
     }
     if (ray.depth + 1 < pi->maxSpecularDepth) {
-        L += SpecularReflect(ray, bsdf, rng, isect, r, scene, sample, arena);
-        L += SpecularTransmit(ray, bsdf, rng, isect, r, scene, sample, arena);
+        // the factor SpecularReflect / SpecularTransmit will multiply the next hit's radiance with (core/integrator.cpp:184-187,209;
+        // 223-226,254), known before they run: a perfectly specular BxDF's Sample_f ignores its sample values
+        for (int kind = 0; kind < 2; ++kind) {
+            Vector wi; float pdf;
+            const BxDFType type = BxDFType((kind == 0 ? BSDF_REFLECTION : BSDF_TRANSMISSION) | BSDF_SPECULAR);
+            Spectrum f = bsdf->Sample_f(wo, &wi, BSDFSample(.5f, .5f, .5f), &pdf, type);
+            const bool traced = pdf > 0.f && !f.IsBlack() && AbsDot(wi, n) != 0.f;       // else the reference function returns 0 without a ray
+            const PvPath saved = tl_path;
+            if (traced) { tl_path.on = true; tl_path.W = W * (f * (AbsDot(wi, n) / pdf)); tl_path.task = task; tl_path.rec = rec; }
+            L += kind == 0 ? SpecularReflect(ray, bsdf, rng, isect, r, scene, sample, arena)
+                           : SpecularTransmit(ray, bsdf, rng, isect, r, scene, sample, arena);
+            tl_path = saved;
+        }
     }
     return L;
 }
@@ -731,7 +757,7 @@ static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, co
     // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
     if (scene->Intersect(ray, isect)) {
         if (fg_task >= 0) {  // a primary hit: Li without the terms that run on the device, whose rays / lookups are queued
-            if (g_fg->direct) return pv_primary_li(r, scene, ray, *isect, sample, rng, arena, fg_task, rec);
+            if (g_fg->direct) return pv_hit_li(r, scene, ray, *isect, sample, rng, arena, fg_task, rec, Spectrum(1.f));
             if (g_fg->gather_rays) pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, g_fg->rays[fg_task]);
             if (g_fg->lookup[0] || g_fg->lookup[1]) {
                 if (!pv_queue_lookup(ray, *isect, rng, arena, rec, g_fg->lookups[fg_task]))
@@ -750,6 +776,18 @@ Spectrum SamplerRenderer::Li(const Scene *scene, const RayDifferential &ray, con
                              Intersection *isect, Spectrum *T) const {
     Spectrum localT; if (!T) T = &localT;
     Intersection localIsect; if (!isect) isect = &localIsect;
+    if (tl_path.on && g_fg && g_fg->direct) {
+        // a ray behind a specular bounce of a hit shaded by pv_hit_li: same three steps as below (:239-249), the volume term before
+        // the surface shading because its transmittance is part of the throughput of everything the next hit queues
+        const PvPath here = tl_path;
+        const bool hit = scene->Intersect(ray, isect);                       // shrinks ray.maxt to the hit (primitive.cpp:172)
+        Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
+        Spectrum Ls(0.f);
+        if (hit) Ls = pv_hit_li(this, scene, ray, *isect, sample, rng, arena, here.task, here.rec, here.W * *T);
+        else for (uint32_t i = 0; i < scene->lights.size(); ++i) Ls += scene->lights[i]->Le(ray);
+        tl_path = here;
+        return *T * Ls + Lvi;
+    }
     Spectrum Li = pv_surface_term(this, scene, ray, sample, rng, arena, isect);
     Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
     return *T * Li + Lvi;

@@ -277,3 +277,35 @@ def test_direct_lighting_of_primary_hits_goes_to_the_device(mock, tmp_path, pkg)
     # area light in the scene: no device direct lighting, the other device terms stay
     assert not calls(logs[2], "occluded") and "direct lighting of primary hits" not in errs[2]
     assert calls(logs[2], "surface_lphoton")
+
+
+def test_surface_terms_behind_specular_bounces_are_queued_too(mock, tmp_path, pkg):
+    """Glass wedge in the box, every photon map, final gathering: a camera ray that meets the glass is followed by the reference's
+    SpecularReflect / SpecularTransmit, and the hit BEHIND the bounce is shaded like a primary hit -- its shadow rays, LPhoton
+    lookups and final-gather rays join the same device batches, their weights carrying the throughput of the bounce (BSDF factor x
+    volume transmittance of the secondary ray, which the batched pv_gather_indexed call delivers).  So the batches hold MORE work
+    than with "maxspeculardepth 1" (no bounce is followed), and the frame is the same for 1 and 2 render threads."""
+    from cs348b_pbrt_b200 import scenes
+    def text(out, depth=None):
+        t = scenes.cornell_surf_pbrt(nphotons=1000, caustic=300, indirect=500, finalgather=True, fgsamples=4, xres=96, yres=96, outfile=out)   # 96 x 96: the same 64 tasks for 1 and 2 cores
+        if depth is not None:
+            assert 'SurfaceIntegrator "photonmap"' in t
+            t = t.replace('SurfaceIntegrator "photonmap"', 'SurfaceIntegrator "photonmap" "integer maxspeculardepth" [%d]' % depth, 1)
+        return t
+    res = {}
+    for name, cores, depth in (("sp1", "1", None), ("sp2", "2", None), ("sp0", "2", 1)):
+        scene = tmp_path / (name + ".pbrt"); scene.write_text(text(name + ".pfm", depth))
+        log = tmp_path / (name + ".log")
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+        env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", cores, str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = log.read_text().splitlines()
+        res[name] = dict(img=(tmp_path / (name + ".pfm")).read_bytes(), err=out.stderr,
+                         shadows=sum(c["n"] for c in calls(lines, "occluded")), lookups=sum(c["n"] for c in calls(lines, "surface_lphoton")),
+                         fg=sum(c["n"] for c in calls(lines, "final_gather")), secondary=len([c for c in calls(lines, "gather") if c.get("indexed")]))
+    assert res["sp1"]["img"] == res["sp2"]["img"]
+    assert res["sp2"]["secondary"] > 0 and res["sp0"]["secondary"] == 0            # volume term of the rays behind the bounces: batched device calls
+    for k in ("shadows", "lookups", "fg"):
+        assert res["sp2"][k] > res["sp0"][k] > 0, k                               # the hits behind the glass queued their terms as well
+        assert res["sp1"][k] == res["sp2"][k]
