@@ -233,6 +233,31 @@ def extra_line(pkg, W, name, local, args, peak):
         pv.close()
 
 
+def lbvh_line(pkg, local, peak, n=2_000_000):
+    """pv_build_bvh (csrc/pv_lbvh.cu) on a synthetic mesh of n small triangles, half of them crowded into 1/1000 of the
+    volume: device time of the build's kernels (CUDA events inside the library), second call (warm), and the call's wall time with
+    its host copies.  Algorithmic bytes: DESIGN.md 4 K6 (~512 B per primitive)."""
+    import time
+    rs = np.random.RandomState(11)
+    c = rs.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    c[: n // 2] = c[: n // 2] * np.float32(0.1) + np.float32(0.4)
+    v = c + rs.uniform(-0.004, 0.004, (n, 3, 3)).astype(np.float32)
+    bounds = np.concatenate([v.min(axis=1), v.max(axis=1)], axis=1).astype(np.float32)
+    pv = pkg.PhotonVolume(device=local)
+    try:
+        pv.build_bvh(bounds, 4)
+        t0 = time.perf_counter()
+        nodes, order, ms = pv.build_bvh(bounds, 4)
+        wall = time.perf_counter() - t0
+        ach = 512.0 * n / (ms * 1e-3) / 1e9
+        return {"workload": "LBVH over %d synthetic triangles, leaves of <= 4" % n, "primitives": n, "nodes": len(nodes) // 32, "kernels_ms": ms,
+                "call_wall_ms": wall * 1e3, "primitives_per_s": n / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "algorithmic_bytes_per_launch": 512.0 * n, "note": "27 launches; launch / latency bound at this size"}}
+    finally:
+        pv.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -518,6 +543,10 @@ def main():
             extra = {"config2": extra_line(pkg, W, "config2", local, args, peak)}
         except Exception as e:                              # a secondary line must never cost the main one
             extra = {"config2": {"error": repr(e)}}
+        try:
+            extra["lbvh_build"] = lbvh_line(pkg, local, peak)
+        except Exception as e:
+            extra["lbvh_build"] = {"error": repr(e)}
     if rank == 0:
         out = {"metric": "volume-gather rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

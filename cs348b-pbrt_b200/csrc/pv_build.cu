@@ -242,17 +242,43 @@ __global__ void gather_records_kernel(const uint32_t *__restrict__ order, uint64
     }
 }
 // cell_start[c] = number of photons whose key is < c, for c in [0, table_size]: ONE pass over the sorted keys -- thread i looks
-// at keys i - 1 and i and, where they differ, writes i to every cell in (key[i-1], key[i]] (cells in between are empty and start
-// where the next occupied one does); the last thread closes the table.
-__global__ void cell_start_kernel(const uint32_t *__restrict__ sorted_keys, uint64_t n, uint32_t table_size, uint32_t *__restrict__ cell_start) {
+// at keys i - 1 and i and, where they differ, i is written to every cell in (key[i-1], key[i]] (cells in between are empty and start
+// where the next occupied one does); the last thread closes the table.  Short runs of empty cells are filled by the thread itself;
+// a long one (the padding of the Morton-ordered key space, the empty space around a crowded map: millions of cells) is filled by
+// its whole warp, 32 cells per step -- one thread doing that alone took 0.1-0.3 s per build on a 2^24-cell table.
+__global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t *__restrict__ sorted_keys, uint64_t n, uint32_t table_size,
+                                                         uint32_t *__restrict__ cell_start) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    const uint32_t hi = i < n ? sorted_keys[i] : table_size;                 // cells up to and including hi start at i
-    const long long lo = i == 0 ? -1ll : (long long)sorted_keys[i - 1];      // ... beyond the previous photon's cell
-    for (long long c = lo + 1; c <= (long long)hi; ++c) cell_start[c] = (uint32_t)i;
+    const uint32_t lane = threadIdx.x & 31;
+    long long lo = 0, hi = -1;                                                // cells lo .. hi start at i
+    if (i <= n) {
+        hi = i < n ? (long long)sorted_keys[i] : (long long)table_size;
+        lo = i == 0 ? 0ll : (long long)sorted_keys[i - 1] + 1;
+    }
+    const bool big = hi - lo >= 64;
+    if (!big) for (long long c = lo; c <= hi; ++c) cell_start[c] = (uint32_t)i;
+    uint32_t todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {
+        const int src = __ffs(todo) - 1; todo &= todo - 1;
+        const long long l = __shfl_sync(0xffffffffu, lo, src), h = __shfl_sync(0xffffffffu, hi, src);
+        const uint32_t v = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
+        for (long long c = l + lane; c <= h; c += 32) cell_start[c] = v;
+    }
 }
 
 static int ceil_log2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
+
+// sum over cells of (photons in the cell)^2: divided by n it is the occupancy of the cell a photon picked at random sits in, i.e.
+// what a lookup near the photons has to scan per cell -- the mean occupancy says nothing about a map whose photons crowd along a beam
+__global__ void __launch_bounds__(256) occupancy_kernel(const uint32_t *__restrict__ cell_start, uint32_t table_size, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < table_size; i += gridDim.x * blockDim.x) {
+        const unsigned long long c = __ldg(cell_start + i + 1) - __ldg(cell_start + i);
+        s += c * c;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
 
 int pvi_build(pv_ctx *ctx, float maxdist, uint32_t nused) { return pvi_build_map(ctx, PV_MAP_VOLUME, maxdist, nused); }
 
@@ -320,47 +346,81 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
     const int max_dim = 256;                                  // key bits <= 24 -> cell table <= 64 MiB
     h = std::max(h, maxext / (max_dim - 1));
     h = std::max(h, 1e-6);
-    g.h = (float)h; g.inv_h = 1.f / g.h;
-    int maxd = 1;
-    for (int a = 0; a < 3; ++a) {
-        g.origin[a] = mn[a];
-        g.dims[a] = std::min(max_dim, std::max(1, (int)std::floor(ext[a] / h) + 1));
-        maxd = std::max(maxd, g.dims[a]);
-    }
-    g.yzbits = ceil_log2(std::max(g.dims[1], g.dims[2]));
-    // finer cells along x (up to two halvings) while the key stays within 24 (26) bits and cells are not much
-    // more numerous than photons
-    g.xshift = 0;
-    {
-        const int coarse = g.dims[0];
-        const int max_key_bits = n >= (1ull << 25) ? 26 : 24;      // cell table <= 64 MiB, 256 MiB for very large maps
-        int xs_max = 2;
-        if (const char *e = getenv("PV_XSHIFT_MAX")) xs_max = std::max(0, std::min(4, atoi(e)));      // tuning knob
-        for (int xs = 1; xs <= xs_max; ++xs) {
-            const int fine = coarse << xs;
-            if (ceil_log2(fine) + 2 * g.yzbits > max_key_bits) break;
-            if ((double)fine * g.dims[1] * g.dims[2] > 8.0 * (double)n) break;
-            g.xshift = xs;
-        }
-    }
-    g.hx = g.h / (float)(1 << g.xshift); g.inv_hx = 1.f / g.hx;       // exact: a power of two
-    g.dims[0] = std::max(1, (int)std::floor(ext[0] / (double)g.hx) + 1);
-    g.xbits = ceil_log2(g.dims[0]);
-    g.table_size = (uint32_t)1 << (g.xbits + 2 * g.yzbits);
-    g.margin = (float)(1e-4 * h + 4e-6 * (maxabs + maxext));
-    g.one_shell_r = g.h - 2.f * g.margin;            // lookups with r <= this never need more than the 3x3x3 block
-    int key_bits = std::max(1, g.xbits + 2 * g.yzbits);
-
-    // 3. keys + sort
+    // Crowded maps (photons along a spot beam, around a light): when the k-nearest search is the warp-per-lookup one (nused > 64)
+    // and the cell a photon sits in holds many times nused photons, halve the cells (at most twice) -- every lookup near the crowd
+    // scans whole cells.  Measured on projectScene/pinkfloyd.pbrt at its shipped size (5 M photons, nused 500, 0.8 degree spot):
+    // gather of a 512 x 512 frame 1122 ms at the mean-density cell, 619 ms at half, 611 ms at a quarter of it; the batched
+    // volume calls of the rays behind the prism 1.43 / 0.84 / 0.59 s.  Maps of even density (BASELINE configs 2, 3) never get here.
+    const bool adaptive = nused > 64 && !getenv("PV_KNN_CELL");
+    const auto t_build0 = std::chrono::steady_clock::now();
+    int attempts = 0;
+    const double h_min = std::max(maxext / (max_dim - 1), 1e-6);
+    uint32_t *skeys = nullptr, *svals = nullptr;
     size_t nn = (size_t)n;
-    size_t need = nn * 4 * sizeof(uint32_t) + 256;
-    int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
-    uint32_t *keys = (uint32_t *)ctx->scratch, *vals = keys + nn, *keys_tmp = vals + nn, *vals_tmp = keys_tmp + nn;
-    keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src_pos, n, g, keys, vals);
-    ctx->launches += 1;
-    PV_CUDA_CHECK(ctx, cudaGetLastError());
-    uint32_t *skeys, *svals;
-    rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, n, key_bits, &skeys, &svals); if (rc) return rc;
+    for (int attempt = 0;; ++attempt) {
+        g.h = (float)h; g.inv_h = 1.f / g.h;
+        int maxd = 1;
+        for (int a = 0; a < 3; ++a) {
+            g.origin[a] = mn[a];
+            g.dims[a] = std::min(max_dim, std::max(1, (int)std::floor(ext[a] / h) + 1));
+            maxd = std::max(maxd, g.dims[a]);
+        }
+        g.yzbits = ceil_log2(std::max(g.dims[1], g.dims[2]));
+        // finer cells along x (up to two halvings) while the key stays within 24 (26) bits and cells are not much
+        // more numerous than photons
+        g.xshift = 0;
+        {
+            const int coarse = g.dims[0];
+            const int max_key_bits = n >= (1ull << 25) ? 26 : 24;      // cell table <= 64 MiB, 256 MiB for very large maps
+            int xs_max = 2;
+            if (const char *e = getenv("PV_XSHIFT_MAX")) xs_max = std::max(0, std::min(4, atoi(e)));      // tuning knob
+            for (int xs = 1; xs <= xs_max; ++xs) {
+                const int fine = coarse << xs;
+                if (ceil_log2(fine) + 2 * g.yzbits > max_key_bits) break;
+                if ((double)fine * g.dims[1] * g.dims[2] > 8.0 * (double)n) break;
+                g.xshift = xs;
+            }
+        }
+        g.hx = g.h / (float)(1 << g.xshift); g.inv_hx = 1.f / g.hx;       // exact: a power of two
+        g.dims[0] = std::max(1, (int)std::floor(ext[0] / (double)g.hx) + 1);
+        g.xbits = ceil_log2(g.dims[0]);
+        g.table_size = (uint32_t)1 << (g.xbits + 2 * g.yzbits);
+        g.margin = (float)(1e-4 * h + 4e-6 * (maxabs + maxext));
+        g.one_shell_r = g.h - 2.f * g.margin;            // lookups with r <= this never need more than the 3x3x3 block
+        int key_bits = std::max(1, g.xbits + 2 * g.yzbits);
+
+        // 3. keys + sort
+        size_t need = nn * 4 * sizeof(uint32_t) + 256;
+        int rc = pv_ensure(ctx, &ctx->scratch, &ctx->scratch_bytes, need); if (rc) return rc;
+        uint32_t *keys = (uint32_t *)ctx->scratch, *vals = keys + nn, *keys_tmp = vals + nn, *vals_tmp = keys_tmp + nn;
+        keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src_pos, n, g, keys, vals);
+        ctx->launches += 1;
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        rc = pvi_sort_pairs_u32(ctx, keys, vals, keys_tmp, vals_tmp, n, key_bits, &skeys, &svals); if (rc) return rc;
+
+        // 5. cell table
+        if (ctx->table_cap < g.table_size + 1) {
+            if (ctx->cell_start) cudaFree(ctx->cell_start);
+            ctx->cell_start = nullptr; ctx->table_cap = 0;
+            PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->cell_start, ((size_t)g.table_size + 1) * sizeof(uint32_t)));
+            ctx->table_cap = g.table_size + 1;
+        }
+        cell_start_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(skeys, n, g.table_size, ctx->cell_start);
+        ctx->launches += 1;
+        PV_CUDA_CHECK(ctx, cudaGetLastError());
+        attempts = attempt + 1;
+        if (!adaptive || attempt >= 2 || 0.5 * h < h_min) break;
+        // occupancy of the cell a photon sits in, against what a lookup wants
+        rc = pv_ensure(ctx, &ctx->io2, &ctx->io2_bytes, 64); if (rc) return rc;
+        PV_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->io2, 0, sizeof(unsigned long long), ctx->stream));
+        occupancy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->cell_start, g.table_size, (unsigned long long *)ctx->io2);
+        ctx->launches += 1;
+        unsigned long long sumsq = 0;
+        PV_CUDA_CHECK(ctx, cudaMemcpyAsync(&sumsq, ctx->io2, sizeof(sumsq), cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((double)sumsq / (double)n <= 8.0 * (double)nused) break;
+        h *= 0.5;
+    }
 
     // 4. records in sorted order
     if (ctx->map_cap < n) {
@@ -380,18 +440,13 @@ int pvi_build_map(pv_ctx *ctx, int which, float maxdist, uint32_t nused) {
         gather_records_kernel<<<blocks, 256, 0, ctx->stream>>>(svals, n, src_pos, src_wi, src_alpha, ctx->m_pos4, ctx->m_wi4,
                                                              ctx->m_alpha32, ctx->m_orig, ctx->has_scene && is_volume ? ctx->dscene : nullptr);
         PV_CUDA_CHECK(ctx, cudaGetLastError());
+        ctx->launches += 1;
     }
-    // 5. cell table
-    if (ctx->table_cap < g.table_size + 1) {
-        if (ctx->cell_start) cudaFree(ctx->cell_start);
-        ctx->cell_start = nullptr; ctx->table_cap = 0;
-        PV_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->cell_start, ((size_t)g.table_size + 1) * sizeof(uint32_t)));
-        ctx->table_cap = g.table_size + 1;
-    }
-    cell_start_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(skeys, n, g.table_size, ctx->cell_start);
-    ctx->launches += 2;                                     // + gather_records_kernel above
-    PV_CUDA_CHECK(ctx, cudaGetLastError());
     PV_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (getenv("PV_TIMING"))
+        fprintf(stderr, "[pv timing] build of map %d: %llu photons, cell %.4g (x %.4g), %d x %d x %d cells, table 2^%d, %d pass(es), %.1f ms\n", which,
+                (unsigned long long)n, (double)g.h, (double)g.hx, g.dims[0], g.dims[1], g.dims[2], g.xbits + 2 * g.yzbits, attempts,
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count());
     ctx->grid = g;
     ctx->built = true;
     return PV_OK;
