@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(LB_THREADS) lbvh_refit_kernel(const float *__r
     while (cur != 0xFFFFFFFFu) {
         __threadfence();
         if (atomicAdd(flag + cur, 1u) == 0u) return;          // the sibling subtree is not done: its thread will pass here later
+        __threadfence();                                         // acquire side: the sibling's box / size stores precede its atomic
         uint32_t l = lb_node_id(__ldg(left + cur), n), r = lb_node_id(__ldg(right + cur), n);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {                            // Union(Bounds, Bounds) core/geometry.cpp:53-63
