@@ -49,6 +49,8 @@
 #include "core/sampler.h"
 #include "core/camera.h"
 #include "core/film.h"
+#include "film/image.h"
+#include "core/filter.h"
 #include "core/intersection.h"
 #include "core/paramset.h"
 #include "core/montecarlo.h"
@@ -1071,19 +1073,65 @@ void SamplerRenderer::Render(const Scene *scene) {
         fprintf(stderr, "[pv] surface pass %.3f s on %d cores; %s of %zu camera rays %.3f s (kernel %.3f ms)\n", t1 - t0, NumSystemCores(),
                 g_pv.volint < 0 ? "volume gather" : (g_pv.volint == PV_VOLINT_SINGLE ? "single-scattering volume term" : "emission volume term"),
                 total, now_s() - t1, ms);
-        k = 0;
-        for (int t = 0; t < nTasks; ++t)
-            for (size_t i = 0; i < records[t].size(); ++i, ++k) {
-                const PvRecord &rec = records[t][i];
-                Spectrum Lv(0.f), Tr(1.f), Lo(0.f);
-                if (rec.rayWeight > 0.f) {
-                    memcpy(Lv.c, &L[k * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &T[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
-                    Lo = rec.rayWeight * (Tr * rec.Ls + Lv);                  // Ls[i] = rayWeight * (T * Li + Lvi), :111,:249
+        // ---- the film: Ls[i] = rayWeight * (T * Li + Lvi) per sample (:111,:249), the NaN / negative / infinite guard (:118-133),
+        // Film::AddSample.  One thread doing that for a 26 M-sample frame (darkside.pbrt: 800 x 500 x 64 spp) took half a
+        // minute, so the tiles go to the reference's task pool -- in FOUR rounds, the tiles of one colour of a 2 x 2 checkerboard per
+        // round: two tiles of a round are a whole tile apart, the filter supports of their samples cannot meet, and every pixel
+        // receives its contributions in an order that depends on the tile layout alone (its own tile's samples in sample order,
+        // neighbouring tiles' by colour) -- the image is the same bit for bit for any number of threads.
+        std::vector<size_t> first_k(nTasks + 1, 0);
+        for (int t = 0; t < nTasks; ++t) first_k[t + 1] = first_k[t] + records[t].size();
+        struct FilmTile : Task {
+            const std::vector<PvRecord> *recs; const float *L, *T; size_t k0; Film *film;
+            void Run() {
+                for (size_t i = 0; i < recs->size(); ++i) {
+                    const PvRecord &rec = (*recs)[i];
+                    const size_t k = k0 + i;
+                    Spectrum Lv(0.f), Tr(1.f), Lo(0.f);
+                    if (rec.rayWeight > 0.f) {
+                        memcpy(Lv.c, &L[k * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &T[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                        Lo = rec.rayWeight * (Tr * rec.Ls + Lv);                  // Ls[i] = rayWeight * (T * Li + Lvi), :111,:249
+                    }
+                    if (Lo.HasNaNs() || Lo.y() < -1e-5 || isinf(Lo.y())) Lo = Spectrum(0.f);      // :118-133
+                    CameraSample cs; cs.imageX = rec.imageX; cs.imageY = rec.imageY; cs.lensU = cs.lensV = 0.f; cs.time = rec.ray.time;
+                    film->AddSample(cs, Lo);
                 }
-                if (Lo.HasNaNs() || Lo.y() < -1e-5 || isinf(Lo.y())) Lo = Spectrum(0.f);      // :118-133
-                CameraSample cs; cs.imageX = rec.imageX; cs.imageY = rec.imageY; cs.lensU = cs.lensV = 0.f; cs.time = rec.ray.time;
-                camera->film->AddSample(cs, Lo);
             }
+        };
+        // tile layout of the tasks (Sampler::ComputeSubWindow, core/sampler.cpp:55-74): nx tiles per row, read off the windows themselves
+        int nx = nTasks, min_w = 1 << 30, min_h = 1 << 30;
+        {
+            int x0, x1, y0, y1, fy0 = 0;
+            for (int t = 0; t < nTasks; ++t) {
+                sampler->ComputeSubWindow(t, nTasks, &x0, &x1, &y0, &y1);
+                if (t == 0) fy0 = y0;
+                else if (nx == nTasks && y0 != fy0) nx = t;
+                if (x1 > x0 && y1 > y0) { min_w = min(min_w, x1 - x0); min_h = min(min_h, y1 - y0); }
+            }
+        }
+        const ImageFilm *ifilm = dynamic_cast<const ImageFilm *>(camera->film);
+        const int reach = ifilm ? 2 * Ceil2Int(max(ifilm->filter->xWidth, ifilm->filter->yWidth)) + 1 : 1 << 30;
+        const double tf = now_s();
+        if (ifilm && min_w >= reach && min_h >= reach && nTasks % nx == 0) {
+            for (int colour = 0; colour < 4; ++colour) {
+                vector<Task *> tiles;
+                for (int t = 0; t < nTasks; ++t) {
+                    if ((((t % nx) & 1) | (((t / nx) & 1) << 1)) != colour || records[t].empty()) continue;
+                    FilmTile *ft = new FilmTile; ft->recs = &records[t]; ft->L = L.data(); ft->T = T.data(); ft->k0 = first_k[t]; ft->film = camera->film;
+                    tiles.push_back(ft);
+                }
+                if (tiles.empty()) continue;
+                EnqueueTasks(tiles);
+                WaitForAllTasks();
+                for (size_t i = 0; i < tiles.size(); ++i) delete tiles[i];
+            }
+        } else {
+            for (int t = 0; t < nTasks; ++t) {                                    // tiles too small for the filter (tiny images): in task order
+                FilmTile ft; ft.recs = &records[t]; ft.L = L.data(); ft.T = T.data(); ft.k0 = first_k[t]; ft.film = camera->film;
+                ft.Run();
+            }
+        }
+        if (total > 4000000) fprintf(stderr, "[pv] film: %zu samples added in %.3f s\n", total, now_s() - tf);
     }
     delete sample;
     camera->film->WriteImage();

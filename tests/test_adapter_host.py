@@ -309,3 +309,43 @@ def test_surface_terms_behind_specular_bounces_are_queued_too(mock, tmp_path, pk
     for k in ("shadows", "lookups", "fg"):
         assert res["sp2"][k] > res["sp0"][k] > 0, k                               # the hits behind the glass queued their terms as well
         assert res["sp1"][k] == res["sp2"][k]
+
+
+PROJECT_SCENES = "/root/reference/projectScene"
+
+
+@pytest.mark.skipif(not os.path.isdir(PROJECT_SCENES), reason="the reference's data files are not here (this container only)")
+def test_every_scene_the_project_ships_is_accepted_and_takes_the_device_routes(mock, tmp_path, pkg):
+    """All ten .pbrt files of the reference's projectScene/ (read from the reference tree, resolution cut to 64 x 64 and 1 spp so the
+    CPU side takes a second; photon counts, integrators, lights, materials, shapes, includes and output formats as shipped) run
+    through the drop-in against the double: none is refused, every one shoots its photons with ONE device call (all maps when
+    the scene asks for caustic photons, volume-only else), builds the volume map, sends the frame's volume term down as one gather
+    and its shadow rays / caustic lookups as device batches; the files that name .exr / .png outputs write them."""
+    import glob, shutil
+    work = tmp_path / "proj"; work.mkdir()
+    for sub in ("obj", "textures"):
+        shutil.copytree(os.path.join(PROJECT_SCENES, sub), work / sub)
+    files = sorted(glob.glob(os.path.join(PROJECT_SCENES, "*.pbrt")))
+    assert len(files) == 10
+    for f in files:
+        name = os.path.basename(f)[:-5]
+        text = open(f).read()
+        text = re.sub(r'"integer pixelsamples" \[\d+\]', '"integer pixelsamples" [1]', text)
+        text = re.sub(r'"integer ([xy])resolution" \[\d+\]', r'"integer \1resolution" [64]', text)
+        (work / (name + ".pbrt")).write_text(text)
+        log = work / (name + ".log")
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log))
+        env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", "4", name + ".pbrt"], cwd=work, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (name, out.stderr[-1500:])
+        lines = log.read_text().splitlines()
+        names = [l.split()[0] for l in lines]
+        wants_surface_maps = int(re.search(r'"integer causticphotons"\s*\[?\s*(\d+)', text).group(1)) > 0 if "causticphotons" in text else True
+        assert names.count("shoot_maps" if wants_surface_maps else "shoot") == 1 and "Shooting photons" not in out.stderr, name
+        assert names.count("build") == 1 and names.count("set_scene") == 1, name
+        frame = [c for c in calls(lines, "gather") if not c.get("indexed")]
+        assert len(frame) == 1 and frame[0]["n"] >= 64 * 64, name                 # the camera rays of the frame: one call
+        outfile = re.search(r'"string filename"\s+"([^"]+)"', text).group(1)
+        assert (work / outfile).exists() and (work / outfile).stat().st_size > 1000, (name, outfile)
+        if outfile.endswith(".exr"):
+            assert (work / outfile).read_bytes()[:4] == b"\x76\x2f\x31\x01"       # OpenEXR magic
