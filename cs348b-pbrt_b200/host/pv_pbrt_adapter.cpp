@@ -253,14 +253,21 @@ std::vector<std::vector<PvRecord> > *g_records = NULL;
 // lighting, the caustic estimate, specular bounces) is the reference's own code, run through a clone of the integrator whose
 // shooter has no indirect map (so that Li adds neither the final gather nor the indirect estimate); rays spawned by specular
 // bounces re-enter through SamplerRenderer::Li and use the unmodified integrator, final gathering included.
-struct PvGatherRay { uint32_t rec; Spectrum C; pv_ray ray; };
+struct PvGatherRay { uint32_t rec; int tslot; Spectrum C; pv_ray ray; };   // tslot: see PvSecondary
 // One LPhoton lookup of a primary hit (photonmap.cpp:62-108, diffuse branch): where, the faceforwarded shading normal, and the
 // two reflectances the sums are multiplied with afterwards.
-struct PvLookup { uint32_t rec; float p[3], nf[3]; Spectrum rr, rt; };
+struct PvLookup { uint32_t rec; int tslot; float p[3], nf[3]; Spectrum rr, rt; };
 // One light sample of the direct lighting of a primary hit (EstimateDirect, core/integrator.cpp:137-163, delta light): the
 // VisibilityTester's segment, the jitter of the transmittance march (the rng.RandomFloat() of photonvolume.cpp:26) and the
 // spectrum C = f * Li * |wi . n| / pdf the visibility V * Tr is multiplied with.
-struct PvShadow { uint32_t rec; Spectrum C; pv_ray ray; float u; };
+struct PvShadow { uint32_t rec; int tslot; Spectrum C; pv_ray ray; float u; };
+// A ray behind a specular bounce (SpecularReflect / SpecularTransmit): its volume term Lv, T is ONE ray of the group's single
+// pv_gather_indexed call instead of a blocking call of its own.  W = the product of the bounce factors f * |wi . n| / pdf up to
+// this ray (no transmittances), parent = the secondary ray of the same task this one was spawned behind (-1: behind a primary hit).
+// What the ray contributes: W * P(parent) * Lv with P(j) = P(parent(j)) * T(j) the product of the volume transmittances along the
+// chain, P(-1) = 1.  The terms queued at the hit this ray ends in carry tslot = the ray's number: their weights are multiplied
+// with P(tslot) once the call is back.
+struct PvSecondary { uint32_t rec; int parent; Spectrum W; pv_ray ray; uint64_t index; };
 struct PvFinalGather {
     PhotonIntegrator *full, *primary;      // the scene's integrator, and its clone without the maps whose terms run on the device
     bool gather_rays;                      // final gathering of primary hits as one pv_final_gather per group
@@ -268,10 +275,13 @@ struct PvFinalGather {
     bool direct;                           // direct lighting of primary hits: shadow rays + their transmittance as one device batch per group
     std::vector<std::vector<PvShadow> > shadows;      // per render task
     uint64_t total_shadows; double shadow_seconds;
+    std::vector<std::vector<PvSecondary> > secondary; // per render task (direct mode: the rays behind specular bounces are deferred too)
+    uint64_t total_secondary, secondary_calls; double secondary_seconds;
+    int scatter_offset; pv_gather_params vol_prm;     // of the scene's PhotonVolumeIntegrator
     std::vector<std::vector<PvGatherRay> > rays;      // per render task
     std::vector<std::vector<PvLookup> > lookups;      // per render task; caustic and indirect lookups of a hit share the record
     uint64_t next_index, total_rays, total_lookups; double gpu_seconds, lookup_seconds;
-    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), direct(false), total_shadows(0), shadow_seconds(0), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
+    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), direct(false), total_shadows(0), shadow_seconds(0), total_secondary(0), secondary_calls(0), secondary_seconds(0), scatter_offset(0), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
         lookup[0] = lookup[1] = false;
     }
 };
@@ -302,7 +312,7 @@ void pv_queue_final_gather(const PhotonIntegrator *pi, const RayDifferential &ra
     for (uint32_t i = 0; i < nDirs; ++i) dirs[i] = close[i].photon->wi;
     const int gs = pi->gatherSamples;
     const float cosGA = pi->cosGatherAngle, conePdf = UniformConePdf(cosGA);
-    PvGatherRay g; memset(&g.ray, 0, sizeof(g.ray)); g.rec = rec;
+    PvGatherRay g; memset(&g.ray, 0, sizeof(g.ray)); g.rec = rec; g.tslot = -1;
     g.ray.o[0] = p.x; g.ray.o[1] = p.y; g.ray.o[2] = p.z; g.ray.mint = isect.rayEpsilon; g.ray.maxt = INFINITY; g.ray.time = ray.time;
     for (int half = 0; half < 2; ++half)
         for (int i = 0; i < gs; ++i) {
@@ -344,7 +354,7 @@ bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG 
     if (bsdf->NumComponents(BxDFType(BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_GLOSSY)) > 0) return false;   // glossy branch: not on this path
     const Vector wo = -ray.d;
     const Normal Nf = Faceforward(bsdf->dgShading.nn, wo);
-    PvLookup q; q.rec = rec;
+    PvLookup q; q.rec = rec; q.tslot = -1;
     q.p[0] = isect.dg.p.x; q.p[1] = isect.dg.p.y; q.p[2] = isect.dg.p.z;
     q.nf[0] = Nf.x; q.nf[1] = Nf.y; q.nf[2] = Nf.z;
     q.rr = bsdf->rho(wo, rng, BSDF_ALL_REFLECTION) * INV_PI;
@@ -369,11 +379,11 @@ bool pv_queue_lookup(const RayDifferential &ray, const Intersection &isect, RNG 
 //                                  queued term goes straight to the pixel's record with its throughput folded into its weight.
 // Used when all lights of the scene are delta lights (an area light's BSDF-sampling half needs the identity of the surface the
 // sampled ray hits; such scenes keep the clone route, with the reference's own UniformSampleAllLights).
-struct PvPath { bool on; Spectrum W; int task; uint32_t rec; PvPath() : on(false), W(1.f), task(-1), rec(0) {} };
+struct PvPath { bool on; Spectrum W; int task; uint32_t rec; int slot; PvPath() : on(false), W(1.f), task(-1), rec(0), slot(-1) {} };
 thread_local PvPath tl_path;
 
 Spectrum pv_hit_li(const SamplerRenderer *r, const Scene *scene, const RayDifferential &ray, const Intersection &isect, const Sample *sample,
-                   RNG &rng, MemoryArena &arena, int task, uint32_t rec, const Spectrum &W) {
+                   RNG &rng, MemoryArena &arena, int task, uint32_t rec, const Spectrum &W, int tslot) {
     const PhotonIntegrator *pi = g_fg->full;
     Spectrum L(0.f);
     const Vector wo = -ray.d;
@@ -392,7 +402,7 @@ Spectrum pv_hit_li(const SamplerRenderer *r, const Scene *scene, const RayDiffer
             if (lightPdf > 0.f && !Li.IsBlack()) {
                 Spectrum f = bsdf->f(wo, wi, BxDFType(BSDF_ALL & ~BSDF_SPECULAR));
                 if (!f.IsBlack()) {
-                    PvShadow sh; sh.rec = rec;
+                    PvShadow sh; sh.rec = rec; sh.tslot = tslot;
                     sh.C = W * (f * Li * (AbsDot(wi, n) / lightPdf) / (float)nSamples);
                     pv_fill_ray(RayDifferential(visibility.r), 0.f, &sh.ray);
                     sh.u = rng.RandomFloat();
@@ -405,14 +415,14 @@ Spectrum pv_hit_li(const SamplerRenderer *r, const Scene *scene, const RayDiffer
         std::vector<PvGatherRay> &gr = g_fg->rays[task];
         const size_t first = gr.size();
         pv_queue_final_gather(pi, ray, isect, sample, arena, rec, gr);
-        for (size_t k = first; k < gr.size(); ++k) gr[k].C *= W;
+        for (size_t k = first; k < gr.size(); ++k) { gr[k].C *= W; gr[k].tslot = tslot; }
     }
     if (g_fg->lookup[0] || g_fg->lookup[1]) {
         std::vector<PvLookup> &lk = g_fg->lookups[task];
         const size_t first = lk.size();
         if (!pv_queue_lookup(ray, isect, rng, arena, rec, lk))
             Severe("pv: a surface with glossy components reached the device LPhoton (materials other than matte / glass are off this path)");
-        for (size_t k = first; k < lk.size(); ++k) { lk[k].rr *= W; lk[k].rt *= W; }
+        for (size_t k = first; k < lk.size(); ++k) { lk[k].rr *= W; lk[k].rt *= W; lk[k].tslot = tslot; }
     }
     if (ray.depth + 1 < pi->maxSpecularDepth) {
         // the factor SpecularReflect / SpecularTransmit will multiply the next hit's radiance with (core/integrator.cpp:184-187,209;
@@ -423,7 +433,7 @@ Spectrum pv_hit_li(const SamplerRenderer *r, const Scene *scene, const RayDiffer
             Spectrum f = bsdf->Sample_f(wo, &wi, BSDFSample(.5f, .5f, .5f), &pdf, type);
             const bool traced = pdf > 0.f && !f.IsBlack() && AbsDot(wi, n) != 0.f;       // else the reference function returns 0 without a ray
             const PvPath saved = tl_path;
-            if (traced) { tl_path.on = true; tl_path.W = W * (f * (AbsDot(wi, n) / pdf)); tl_path.task = task; tl_path.rec = rec; }
+            if (traced) { tl_path.on = true; tl_path.W = W * (f * (AbsDot(wi, n) / pdf)); tl_path.task = task; tl_path.rec = rec; tl_path.slot = tslot; }
             L += kind == 0 ? SpecularReflect(ray, bsdf, rng, isect, r, scene, sample, arena)
                            : SpecularTransmit(ray, bsdf, rng, isect, r, scene, sample, arena);
             tl_path = saved;
@@ -759,7 +769,7 @@ static Spectrum pv_surface_term(const SamplerRenderer *r, const Scene *scene, co
     // first half of SamplerRenderer::Li (:239-246): note scene->Intersect shrinks ray.maxt to the hit (primitive.cpp:172)
     if (scene->Intersect(ray, isect)) {
         if (fg_task >= 0) {  // a primary hit: Li without the terms that run on the device, whose rays / lookups are queued
-            if (g_fg->direct) return pv_hit_li(r, scene, ray, *isect, sample, rng, arena, fg_task, rec, Spectrum(1.f));
+            if (g_fg->direct) return pv_hit_li(r, scene, ray, *isect, sample, rng, arena, fg_task, rec, Spectrum(1.f), -1);
             if (g_fg->gather_rays) pv_queue_final_gather(g_fg->full, ray, *isect, sample, arena, rec, g_fg->rays[fg_task]);
             if (g_fg->lookup[0] || g_fg->lookup[1]) {
                 if (!pv_queue_lookup(ray, *isect, rng, arena, rec, g_fg->lookups[fg_task]))
@@ -779,16 +789,23 @@ Spectrum SamplerRenderer::Li(const Scene *scene, const RayDifferential &ray, con
     Spectrum localT; if (!T) T = &localT;
     Intersection localIsect; if (!isect) isect = &localIsect;
     if (tl_path.on && g_fg && g_fg->direct) {
-        // a ray behind a specular bounce of a hit shaded by pv_hit_li: same three steps as below (:239-249), the volume term before
-        // the surface shading because its transmittance is part of the throughput of everything the next hit queues
+        // A ray behind a specular bounce of a hit shaded by pv_hit_li.  Nothing is evaluated here: the ray's volume term joins the
+        // group's ONE pv_gather_indexed call (PvSecondary), the hit it ends in queues its terms under the ray's number, and what
+        // this function would hand back up the reference's recursion -- T * (Le + deeper bounces) + Lv -- reaches the pixel's record
+        // through those queues.  (Le is zero on every surface and on every miss here: the direct mode is on only in scenes whose
+        // lights are all delta lights.)
         const PvPath here = tl_path;
         const bool hit = scene->Intersect(ray, isect);                       // shrinks ray.maxt to the hit (primitive.cpp:172)
-        Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
-        Spectrum Ls(0.f);
-        if (hit) Ls = pv_hit_li(this, scene, ray, *isect, sample, rng, arena, here.task, here.rec, here.W * *T);
-        else for (uint32_t i = 0; i < scene->lights.size(); ++i) Ls += scene->lights[i]->Le(ray);
+        PvSecondary sr; sr.rec = here.rec; sr.parent = here.slot; sr.W = here.W;
+        pv_fill_ray(ray, sample->oneD[g_fg->scatter_offset][0], &sr.ray);
+        sr.index = ((uint64_t)rng.RandomUInt() << 20) | 0x8000000000000000ull;    // a stream of its own, from the task's RNG (as pv_li_one draws it)
+        std::vector<PvSecondary> &sec = g_fg->secondary[here.task];
+        const int slot = (int)sec.size();
+        sec.push_back(sr);
+        if (hit) pv_hit_li(this, scene, ray, *isect, sample, rng, arena, here.task, here.rec, here.W, slot);
         tl_path = here;
-        return *T * Ls + Lvi;
+        *T = Spectrum(1.f);
+        return Spectrum(0.f);
     }
     Spectrum Li = pv_surface_term(this, scene, ray, sample, rng, arena, isect);
     Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
@@ -914,7 +931,10 @@ void SamplerRenderer::Render(const Scene *scene) {
         fg.primary = new PhotonIntegrator(*pmi);
         fg.primary->photonShooter = bare;
         fg.gather_rays = fg_on; fg.lookup[0] = lp_on[0]; fg.lookup[1] = lp_on[1]; fg.direct = direct_on;
-        fg.rays.resize(nTasks); fg.lookups.resize(nTasks); fg.shadows.resize(nTasks);
+        fg.rays.resize(nTasks); fg.lookups.resize(nTasks); fg.shadows.resize(nTasks); fg.secondary.resize(nTasks);
+        fg.scatter_offset = pvi->scatterSampleOffset;
+        memset(&fg.vol_prm, 0, sizeof(fg.vol_prm));
+        fg.vol_prm.stepsize = pvi->stepSize; fg.vol_prm.nused = (uint32_t)pvi->nUsed; fg.vol_prm.maxdist = pvi->maxDist; fg.vol_prm.seed = g_pv.seed;
         const int map_id[2] = {PV_MAP_CAUSTIC, PV_MAP_INDIRECT};
         for (int m = 0; m < 2; ++m) {
             if (!lp_on[m]) continue;
@@ -959,6 +979,37 @@ void SamplerRenderer::Render(const Scene *scene) {
             WaitForAllTasks();
             for (uint32_t i = 0; i < renderTasks.size(); ++i) delete renderTasks[i];
             if (!g_fg) continue;
+            // ---- the rays behind specular bounces of this group: ONE pv_gather_indexed for their volume terms; Ls += W * P(parent) * Lv,
+            // and P(j) = P(parent) * T(j) for the terms queued at the hits those rays end in (PvSecondary)
+            std::vector<std::vector<Spectrum> > chainT(nTasks);
+            {
+                size_t nsec = 0;
+                for (int t = 0; t < nTasks; ++t) nsec += fg.secondary[t].size();
+                if (nsec) {
+                    std::vector<pv_ray> rr(nsec); std::vector<uint64_t> ri(nsec); std::vector<float> sL(nsec * PV_NSPEC), sT(nsec * PV_NSPEC);
+                    size_t q = 0;
+                    for (int t = 0; t < nTasks; ++t)
+                        for (size_t i = 0; i < fg.secondary[t].size(); ++i, ++q) { rr[q] = fg.secondary[t][i].ray; ri[q] = fg.secondary[t][i].index; }
+                    double ts = now_s();
+                    int rc = pv_gather_indexed(g_pv.ctx, rr.data(), ri.data(), nsec, &fg.vol_prm, sL.data(), sT.data());
+                    if (rc) pv_fail("pv_gather_indexed", rc);
+                    fg.secondary_seconds += now_s() - ts; fg.total_secondary += nsec; fg.secondary_calls++;
+                    q = 0;
+                    for (int t = 0; t < nTasks; ++t) {
+                        std::vector<Spectrum> &P = chainT[t];
+                        P.resize(fg.secondary[t].size());
+                        for (size_t i = 0; i < fg.secondary[t].size(); ++i, ++q) {
+                            const PvSecondary &sr = fg.secondary[t][i];
+                            Spectrum Lv(0.f), Tr(1.f);
+                            memcpy(Lv.c, &sL[q * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &sT[q * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                            const Spectrum Pp = sr.parent >= 0 ? Spectrum(P[sr.parent]) : Spectrum(1.f);     // parents precede their children in the list
+                            records[t][sr.rec].Ls += sr.W * Pp * Lv;
+                            P[i] = Pp * Tr;
+                        }
+                        std::vector<PvSecondary>().swap(fg.secondary[t]);
+                    }
+                }
+            }
             // ---- the shadow rays of this group's direct lighting: ONE pv_occluded + ONE pv_transmittance, then Ls += C * V * Tr
             size_t nsh = 0;
             for (int t = 0; t < nTasks; ++t) nsh += fg.shadows[t].size();
@@ -979,7 +1030,7 @@ void SamplerRenderer::Render(const Scene *scene) {
                         const PvShadow &sh = fg.shadows[t][i];
                         Spectrum Tr(0.f);
                         memcpy(Tr.c, &sT[q * PV_NSPEC], sizeof(float) * PV_NSPEC);
-                        records[t][sh.rec].Ls += sh.C * Tr;                                        // Ld += f * Li * Tr * |wi.n| / pdf
+                        records[t][sh.rec].Ls += sh.tslot >= 0 ? Spectrum(sh.C * Tr * chainT[t][sh.tslot]) : Spectrum(sh.C * Tr);       // Ld += f * Li * Tr * |wi.n| / pdf
                     }
                     std::vector<PvShadow>().swap(fg.shadows[t]);
                 }
@@ -1007,7 +1058,8 @@ void SamplerRenderer::Render(const Scene *scene) {
                             const PvLookup &lk = fg.lookups[t][i];
                             Spectrum sr(0.f), st(0.f);
                             memcpy(sr.c, &Lr[q * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(st.c, &Lt[q * PV_NSPEC], sizeof(float) * PV_NSPEC);
-                            records[t][lk.rec].Ls += sr * lk.rr + st * lk.rt;                     // photonmap.cpp:101-102
+                            const Spectrum Ll = sr * lk.rr + st * lk.rt;                                  // photonmap.cpp:101-102
+                            records[t][lk.rec].Ls += lk.tslot >= 0 ? Spectrum(Ll * chainT[t][lk.tslot]) : Ll;
                         }
                     fg.total_lookups += nl;
                 }
@@ -1031,7 +1083,7 @@ void SamplerRenderer::Render(const Scene *scene) {
                     const PvGatherRay &g = fg.rays[t][i];
                     Spectrum Li(0.f);
                     memcpy(Li.c, &Lindir[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
-                    records[t][g.rec].Ls += g.C * Li;
+                    records[t][g.rec].Ls += g.tslot >= 0 ? Spectrum(g.C * Li * chainT[t][g.tslot]) : Spectrum(g.C * Li);
                 }
                 std::vector<PvGatherRay>().swap(fg.rays[t]);
             }
@@ -1047,6 +1099,9 @@ void SamplerRenderer::Render(const Scene *scene) {
         if (fg.gather_rays)
             fprintf(stderr, "[pv] final gathering of primary hits on the GPU: %llu gather rays in %.3f s\n", (unsigned long long)fg.total_rays,
                     fg.gpu_seconds);
+        if (fg.total_secondary)
+            fprintf(stderr, "[pv] volume term of %llu rays behind specular bounces: %llu device call(s) (one per group of render tasks), %.3f s\n",
+                    (unsigned long long)fg.total_secondary, (unsigned long long)fg.secondary_calls, fg.secondary_seconds);
         if (fg.direct)
             fprintf(stderr, "[pv] direct lighting of primary hits on the GPU: %llu shadow rays (occlusion + transmittance) in %.3f s\n",
                     (unsigned long long)fg.total_shadows, fg.shadow_seconds);

@@ -283,7 +283,9 @@ def test_surface_terms_behind_specular_bounces_are_queued_too(mock, tmp_path, pk
     """Glass wedge in the box, every photon map, final gathering: a camera ray that meets the glass is followed by the reference's
     SpecularReflect / SpecularTransmit, and the hit BEHIND the bounce is shaded like a primary hit -- its shadow rays, LPhoton
     lookups and final-gather rays join the same device batches, their weights carrying the throughput of the bounce (BSDF factor x
-    volume transmittance of the secondary ray, which the batched pv_gather_indexed call delivers).  So the batches hold MORE work
+    volume transmittance of the secondary ray).  The secondary rays themselves are deferred as well: their volume terms are ONE
+    pv_gather_indexed call per group, and the transmittances it returns are folded into the queued weights afterwards, chain by chain
+    (checked against the previous, recursive evaluation of the same frame: equal to 1e-6).  So the batches hold MORE work
     than with "maxspeculardepth 1" (no bounce is followed), and the frame is the same for 1 and 2 render threads."""
     from cs348b_pbrt_b200 import scenes
     def text(out, depth=None):
@@ -305,7 +307,10 @@ def test_surface_terms_behind_specular_bounces_are_queued_too(mock, tmp_path, pk
                          shadows=sum(c["n"] for c in calls(lines, "occluded")), lookups=sum(c["n"] for c in calls(lines, "surface_lphoton")),
                          fg=sum(c["n"] for c in calls(lines, "final_gather")), secondary=len([c for c in calls(lines, "gather") if c.get("indexed")]))
     assert res["sp1"]["img"] == res["sp2"]["img"]
-    assert res["sp2"]["secondary"] > 0 and res["sp0"]["secondary"] == 0            # volume term of the rays behind the bounces: batched device calls
+    # volume term of the rays behind the bounces: ONE indexed device call per group of render tasks (here one group), not one per ray
+    assert res["sp2"]["secondary"] == 1 and res["sp0"]["secondary"] == 0
+    m = re.search(r"volume term of (\d+) rays behind specular bounces: 1 device call", res["sp2"]["err"])
+    assert m and int(m.group(1)) > 1000
     for k in ("shadows", "lookups", "fg"):
         assert res["sp2"][k] > res["sp0"][k] > 0, k                               # the hits behind the glass queued their terms as well
         assert res["sp1"][k] == res["sp2"][k]
