@@ -1130,26 +1130,32 @@ void SamplerRenderer::Render(const Scene *scene) {
                 total, now_s() - t1, ms);
         // ---- the film: Ls[i] = rayWeight * (T * Li + Lvi) per sample (:111,:249), the NaN / negative / infinite guard (:118-133),
         // Film::AddSample.  One thread doing that for a 26 M-sample frame (darkside.pbrt: 800 x 500 x 64 spp) took half a
-        // minute, so the tiles go to the reference's task pool -- in FOUR rounds, the tiles of one colour of a 2 x 2 checkerboard per
-        // round: two tiles of a round are a whole tile apart, the filter supports of their samples cannot meet, and every pixel
-        // receives its contributions in an order that depends on the tile layout alone (its own tile's samples in sample order,
-        // neighbouring tiles' by colour) -- the image is the same bit for bit for any number of threads.
+        // minute, so the tiles go to the reference's task pool -- grouped into blocks at least as wide as the pixel filter reaches, in
+        // FOUR rounds, the blocks of one colour of a 2 x 2 checkerboard per round: two blocks of a round are a whole block apart, the
+        // filter supports of their samples cannot meet, and every pixel receives its contributions in an order that depends on the
+        // tile layout alone (its own block's samples in task and sample order, neighbouring blocks' by colour) -- the image is the
+        // same bit for bit for any number of threads.
         std::vector<size_t> first_k(nTasks + 1, 0);
         for (int t = 0; t < nTasks; ++t) first_k[t + 1] = first_k[t] + records[t].size();
         struct FilmTile : Task {
-            const std::vector<PvRecord> *recs; const float *L, *T; size_t k0; Film *film;
+            std::vector<int> tasks;                      // render tasks (tiles) of this block, in task order
+            const std::vector<std::vector<PvRecord> > *records; const size_t *first_k; const float *L, *T; Film *film;
             void Run() {
-                for (size_t i = 0; i < recs->size(); ++i) {
-                    const PvRecord &rec = (*recs)[i];
-                    const size_t k = k0 + i;
-                    Spectrum Lv(0.f), Tr(1.f), Lo(0.f);
-                    if (rec.rayWeight > 0.f) {
-                        memcpy(Lv.c, &L[k * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &T[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
-                        Lo = rec.rayWeight * (Tr * rec.Ls + Lv);                  // Ls[i] = rayWeight * (T * Li + Lvi), :111,:249
+                for (size_t j = 0; j < tasks.size(); ++j) {
+                    const std::vector<PvRecord> &recs = (*records)[tasks[j]];
+                    const size_t k0 = first_k[tasks[j]];
+                    for (size_t i = 0; i < recs.size(); ++i) {
+                        const PvRecord &rec = recs[i];
+                        const size_t k = k0 + i;
+                        Spectrum Lv(0.f), Tr(1.f), Lo(0.f);
+                        if (rec.rayWeight > 0.f) {
+                            memcpy(Lv.c, &L[k * PV_NSPEC], sizeof(float) * PV_NSPEC); memcpy(Tr.c, &T[k * PV_NSPEC], sizeof(float) * PV_NSPEC);
+                            Lo = rec.rayWeight * (Tr * rec.Ls + Lv);                  // Ls[i] = rayWeight * (T * Li + Lvi), :111,:249
+                        }
+                        if (Lo.HasNaNs() || Lo.y() < -1e-5 || isinf(Lo.y())) Lo = Spectrum(0.f);      // :118-133
+                        CameraSample cs; cs.imageX = rec.imageX; cs.imageY = rec.imageY; cs.lensU = cs.lensV = 0.f; cs.time = rec.ray.time;
+                        film->AddSample(cs, Lo);
                     }
-                    if (Lo.HasNaNs() || Lo.y() < -1e-5 || isinf(Lo.y())) Lo = Spectrum(0.f);      // :118-133
-                    CameraSample cs; cs.imageX = rec.imageX; cs.imageY = rec.imageY; cs.lensU = cs.lensV = 0.f; cs.time = rec.ray.time;
-                    film->AddSample(cs, Lo);
                 }
             }
         };
@@ -1165,26 +1171,32 @@ void SamplerRenderer::Render(const Scene *scene) {
             }
         }
         const ImageFilm *ifilm = dynamic_cast<const ImageFilm *>(camera->film);
-        const int reach = ifilm ? 2 * Ceil2Int(max(ifilm->filter->xWidth, ifilm->filter->yWidth)) + 1 : 1 << 30;
         const double tf = now_s();
-        if (ifilm && min_w >= reach && min_h >= reach && nTasks % nx == 0) {
+        if (ifilm && nTasks % nx == 0 && min_w < (1 << 30)) {
+            // blocks of gx x gy tiles, each at least as wide as the filter reaches across it; a block is added by one thread, tile by tile
+            const int reach = 2 * Ceil2Int(max(ifilm->filter->xWidth, ifilm->filter->yWidth)) + 1;
+            const int gx = (reach + min_w - 1) / min_w, gy = (reach + min_h - 1) / min_h;
+            const int ny = nTasks / nx, bx = (nx + gx - 1) / gx, by = (ny + gy - 1) / gy;
             for (int colour = 0; colour < 4; ++colour) {
-                vector<Task *> tiles;
-                for (int t = 0; t < nTasks; ++t) {
-                    if ((((t % nx) & 1) | (((t / nx) & 1) << 1)) != colour || records[t].empty()) continue;
-                    FilmTile *ft = new FilmTile; ft->recs = &records[t]; ft->L = L.data(); ft->T = T.data(); ft->k0 = first_k[t]; ft->film = camera->film;
-                    tiles.push_back(ft);
+                vector<Task *> blocks;
+                for (int b = 0; b < bx * by; ++b) {
+                    const int cx = b % bx, cy = b / bx;
+                    if (((cx & 1) | ((cy & 1) << 1)) != colour) continue;
+                    FilmTile *ft = new FilmTile; ft->records = &records; ft->first_k = first_k.data(); ft->L = L.data(); ft->T = T.data(); ft->film = camera->film;
+                    for (int ty = cy * gy; ty < min(ny, (cy + 1) * gy); ++ty)
+                        for (int tx = cx * gx; tx < min(nx, (cx + 1) * gx); ++tx)
+                            if (!records[ty * nx + tx].empty()) ft->tasks.push_back(ty * nx + tx);
+                    if (ft->tasks.empty()) delete ft; else blocks.push_back(ft);
                 }
-                if (tiles.empty()) continue;
-                EnqueueTasks(tiles);
+                if (blocks.empty()) continue;
+                EnqueueTasks(blocks);
                 WaitForAllTasks();
-                for (size_t i = 0; i < tiles.size(); ++i) delete tiles[i];
+                for (size_t i = 0; i < blocks.size(); ++i) delete blocks[i];
             }
         } else {
-            for (int t = 0; t < nTasks; ++t) {                                    // tiles too small for the filter (tiny images): in task order
-                FilmTile ft; ft.recs = &records[t]; ft.L = L.data(); ft.T = T.data(); ft.k0 = first_k[t]; ft.film = camera->film;
-                ft.Run();
-            }
+            FilmTile ft; ft.records = &records; ft.first_k = first_k.data(); ft.L = L.data(); ft.T = T.data(); ft.film = camera->film;
+            for (int t = 0; t < nTasks; ++t) ft.tasks.push_back(t);                 // another film class: in task order, one thread
+            ft.Run();
         }
         if (total > 4000000) fprintf(stderr, "[pv] film: %zu samples added in %.3f s\n", total, now_s() - tf);
     }

@@ -354,3 +354,23 @@ def test_every_scene_the_project_ships_is_accepted_and_takes_the_device_routes(m
         assert (work / outfile).exists() and (work / outfile).stat().st_size > 1000, (name, outfile)
         if outfile.endswith(".exr"):
             assert (work / outfile).read_bytes()[:4] == b"\x76\x2f\x31\x01"       # OpenEXR magic
+
+
+def test_film_accumulation_is_the_same_for_any_thread_count(mock, tmp_path, pkg):
+    """The frame's samples are added to the film by the task pool, blocks of tiles at least as wide as the pixel filter reaches, one
+    colour of a 2 x 2 checkerboard of blocks per round (no two threads of a round can touch the same pixel, every pixel gets its
+    contributions in an order fixed by the tile layout).  A gaussian filter 9 pixels wide over 16 x 16-pixel tiles needs blocks of
+    2 x 2 tiles: byte-identical frames from 1 and 2 render threads (128 x 128 image: 64 tasks in both runs)."""
+    from cs348b_pbrt_b200 import scenes
+    imgs = []
+    for cores in ("1", "2"):
+        name = "film" + cores
+        t = scenes.cornell_pbrt(scenes.HOMOG_VOLUME, 1000, xres=128, yres=128, outfile=name + ".pfm")
+        assert 'PixelFilter "box"' in t
+        t = t.replace('PixelFilter "box"', 'PixelFilter "gaussian" "float xwidth" [9] "float ywidth" [9]')
+        scene = tmp_path / (name + ".pbrt"); scene.write_text(t)
+        env = dict(os.environ, LD_LIBRARY_PATH=str(mock)); env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+        out = subprocess.run([BIN, "--quiet", "--ncores", cores, str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-1500:]
+        imgs.append((tmp_path / (name + ".pfm")).read_bytes())
+    assert imgs[0] == imgs[1] and len(imgs[0]) > 128 * 128 * 12
