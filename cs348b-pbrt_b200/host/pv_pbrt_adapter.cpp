@@ -873,21 +873,6 @@ void SamplerRenderer::Render(const Scene *scene) {
     if (have_vint && vint.kind >= 0 && scene->volumeRegion && !visualizeObjectIds) pv_setup_volint(scene, vint);
     Sample *sample = new Sample(sampler, surfaceIntegrator, volumeIntegrator, scene);
     camera->AutoFocus(this, scene, sample);
-    // With the volume term on the GPU a render thread spends most of a specular bounce waiting for the device, and the batches
-    // of secondary rays are as large as there are threads waiting (one warp marches one ray, so the device wants thousands of
-    // rays at once and a call lasts as long as its longest ray): run 16 threads per core unless the user chose a count
-    // (--ncores) or PV_THREADS says otherwise.  (The pool is created at the first EnqueueTasks, core/parallel.cpp:728-737.)
-    if (g_pv.ready && scene->volumeRegion) {
-        const char *th = getenv("PV_THREADS");
-        if (th && atoi(th) > 0) PbrtOptions.nCores = atoi(th);
-        else if (PbrtOptions.nCores == 0) PbrtOptions.nCores = min(1024, 16 * NumSystemCores());
-    }
-    int nPixels = camera->film->xResolution * camera->film->yResolution;
-    int nTasks = max(32 * NumSystemCores(), nPixels / (16 * 16));
-    nTasks = RoundUpPow2(nTasks);
-    std::vector<std::vector<PvRecord> > records(nTasks);
-    g_records = &records;
-    double t0 = now_s();
     // ---- final gathering of primary hits on the GPU?  Needs the photon-volume context, a PhotonIntegrator with final gathering, an
     // indirect map with at least the 50 photons the importance lookup insists on (photonmap.cpp:209-214) and radiance photons.
     PvFinalGather fg;
@@ -920,6 +905,22 @@ void SamplerRenderer::Render(const Scene *scene) {
         if (psh->causticMap && !lp_on[0]) direct_on = false;
         if (psh->indirectMap && !(pmi->finalGather ? fg_on : lp_on[1])) direct_on = false;
     }
+    // Render threads.  In the direct mode nothing a render thread does waits for the device (every device call is made between
+    // groups of tasks), so the reference's own thread count stands.  Otherwise (a scene with an area light, or a volume integrator
+    // other than photonvolume under a recursive surface integrator) a thread spends most of a specular bounce waiting for a batched
+    // device call, and the batches are as large as there are threads waiting: 16 threads per core then, unless the user chose a
+    // count (--ncores) or PV_THREADS says otherwise.  (The pool is created at the first EnqueueTasks, core/parallel.cpp:728-737.)
+    if (g_pv.ready && scene->volumeRegion) {
+        const char *th = getenv("PV_THREADS");
+        if (th && atoi(th) > 0) PbrtOptions.nCores = atoi(th);
+        else if (PbrtOptions.nCores == 0 && !direct_on) PbrtOptions.nCores = min(1024, 16 * NumSystemCores());
+    }
+    int nPixels = camera->film->xResolution * camera->film->yResolution;
+    int nTasks = max(32 * NumSystemCores(), nPixels / (16 * 16));
+    nTasks = RoundUpPow2(nTasks);
+    std::vector<std::vector<PvRecord> > records(nTasks);
+    g_records = &records;
+    double t0 = now_s();
     if (fg_on || lp_on[0] || lp_on[1] || direct_on) {
         // member-wise copies made by the classes' own (implicit) copy constructors: a shooter that does not show the maps whose
         // terms run on the device, and an integrator that looks at it.  They share the maps with the originals and are never
