@@ -1241,6 +1241,14 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MIN_CTAS) gather_lii_kernel(Gat
 static uint32_t lookup_cap(uint32_t k) {
     uint32_t cap = k + 64u;                          // the list must hold k entries plus one more iteration of 64 candidates
     cap = (cap + 63u) & ~63u;
+    // ... and should hold about 2k: a list of k + 64 entries is cut back to the k nearest (warp_select_k: four histogram passes and a
+    // compaction over the whole list) after every few dozen accepted candidates once it has filled -- with nused = 500 in a crowded
+    // cell that was 25-100 selects per lookup and a third of the kernel's stall samples (profiles/r02_v6_k500_summary.md); with 2k
+    // entries a select buys room for k more.  The final list is the same either way (the k nearest in arrival order), so results do
+    // not change by a bit.  Bounded by what still lets four CTAs share an SM's shared memory (1088 entries per warp).
+    const uint32_t room = (uint32_t)((((227u * 1024u) / 4u - 1024u) / GW_WARPS - WB_HDR_BYTES - GW_STAGE * 16u) / 8u) & ~63u;
+    const uint32_t twice = (2u * k + 64u + 63u) & ~63u;
+    cap = std::max(cap, std::min(twice, room));
     return std::max<uint32_t>(cap, 256u);
 }
 MapView pvi_map_view(pv_ctx *ctx) {
