@@ -273,6 +273,7 @@ struct PvFinalGather {
     bool gather_rays;                      // final gathering of primary hits as one pv_final_gather per group
     bool lookup[2];                        // LPhoton of primary hits on the caustic map (:179) / on the indirect map when final gathering is off (:308)
     bool direct;                           // direct lighting of primary hits: shadow rays + their transmittance as one device batch per group
+    bool defer;                            // rays behind specular bounces are deferred to one call per group (PvSecondary); PV_DEFER_SECONDARY=0: blocking batched calls (A/B)
     std::vector<std::vector<PvShadow> > shadows;      // per render task
     uint64_t total_shadows; double shadow_seconds;
     std::vector<std::vector<PvSecondary> > secondary; // per render task (direct mode: the rays behind specular bounces are deferred too)
@@ -281,7 +282,7 @@ struct PvFinalGather {
     std::vector<std::vector<PvGatherRay> > rays;      // per render task
     std::vector<std::vector<PvLookup> > lookups;      // per render task; caustic and indirect lookups of a hit share the record
     uint64_t next_index, total_rays, total_lookups; double gpu_seconds, lookup_seconds;
-    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), direct(false), total_shadows(0), shadow_seconds(0), total_secondary(0), secondary_calls(0), secondary_seconds(0), scatter_offset(0), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
+    PvFinalGather() : full(NULL), primary(NULL), gather_rays(false), direct(false), defer(true), total_shadows(0), shadow_seconds(0), total_secondary(0), secondary_calls(0), secondary_seconds(0), scatter_offset(0), next_index(0), total_rays(0), total_lookups(0), gpu_seconds(0), lookup_seconds(0) {
         lookup[0] = lookup[1] = false;
     }
 };
@@ -796,6 +797,16 @@ Spectrum SamplerRenderer::Li(const Scene *scene, const RayDifferential &ray, con
         // lights are all delta lights.)
         const PvPath here = tl_path;
         const bool hit = scene->Intersect(ray, isect);                       // shrinks ray.maxt to the hit (primitive.cpp:172)
+        if (!g_fg->defer) {
+            // A/B route (PV_DEFER_SECONDARY=0): the ray's volume term as a blocking batched call, its transmittance folded into the
+            // throughput of the next hit at once, Le and Lv handed back up the reference's recursion
+            Spectrum Lvi = volumeIntegrator->Li(scene, this, ray, sample, rng, T, arena);
+            Spectrum Ls(0.f);
+            if (hit) Ls = pv_hit_li(this, scene, ray, *isect, sample, rng, arena, here.task, here.rec, here.W * *T, -1);
+            else for (uint32_t i = 0; i < scene->lights.size(); ++i) Ls += scene->lights[i]->Le(ray);
+            tl_path = here;
+            return *T * Ls + Lvi;
+        }
         PvSecondary sr; sr.rec = here.rec; sr.parent = here.slot; sr.W = here.W;
         pv_fill_ray(ray, sample->oneD[g_fg->scatter_offset][0], &sr.ray);
         sr.index = ((uint64_t)rng.RandomUInt() << 20) | 0x8000000000000000ull;    // a stream of its own, from the task's RNG (as pv_li_one draws it)
@@ -932,6 +943,7 @@ void SamplerRenderer::Render(const Scene *scene) {
         fg.primary = new PhotonIntegrator(*pmi);
         fg.primary->photonShooter = bare;
         fg.gather_rays = fg_on; fg.lookup[0] = lp_on[0]; fg.lookup[1] = lp_on[1]; fg.direct = direct_on;
+        { const char *d = getenv("PV_DEFER_SECONDARY"); fg.defer = !(d && !strcmp(d, "0")); }
         fg.rays.resize(nTasks); fg.lookups.resize(nTasks); fg.shadows.resize(nTasks); fg.secondary.resize(nTasks);
         fg.scatter_offset = pvi->scatterSampleOffset;
         memset(&fg.vol_prm, 0, sizeof(fg.vol_prm));

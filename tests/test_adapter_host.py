@@ -374,3 +374,31 @@ def test_film_accumulation_is_the_same_for_any_thread_count(mock, tmp_path, pkg)
         assert out.returncode == 0, out.stderr[-1500:]
         imgs.append((tmp_path / (name + ".pfm")).read_bytes())
     assert imgs[0] == imgs[1] and len(imgs[0]) > 128 * 128 * 12
+
+
+def test_deferred_secondary_rays_equal_the_recursive_evaluation(mock, tmp_path, pkg):
+    """A/B of the two ways the drop-in evaluates what lies behind a specular bounce.  PV_DEFER_SECONDARY=0: the ray's volume term is a
+    blocking batched call inside the reference's recursion, its transmittance multiplies the throughput of the next hit at once, and
+    T * Ls + Lv travels back up through SpecularReflect / SpecularTransmit.  Default: the ray is deferred to the group's single
+    pv_gather_indexed call and the transmittances are folded into the queued weights afterwards, chain by chain.  Same random
+    numbers, same device answers (the double's volume term is a function of the ray's stream index with T = 0.75) -- the frames
+    must agree to float rounding, with final gathering on and off."""
+    import numpy as np
+    from cs348b_pbrt_b200 import scenes
+    from test_dropin_render import read_pfm
+    for fg in (True, False):
+        t = scenes.cornell_surf_pbrt(nphotons=1000, caustic=300, indirect=500, finalgather=fg, fgsamples=4, xres=96, yres=96, outfile="ab.pfm")
+        scene = tmp_path / "ab.pbrt"; scene.write_text(t)
+        imgs, calls_n = [], []
+        for defer in ("0", "1"):
+            log = tmp_path / ("ab%s%d.log" % (defer, fg))
+            env = dict(os.environ, LD_LIBRARY_PATH=str(mock), MOCK_PV_LOG=str(log), PV_DEFER_SECONDARY=defer)
+            env.pop("PV_DEVICES", None); env.pop("PV_DEVICE", None)
+            out = subprocess.run([BIN, "--quiet", "--ncores", "2", str(scene)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-1500:]
+            imgs.append(read_pfm(str(tmp_path / "ab.pfm")))
+            calls_n.append(len([c for c in calls(log.read_text().splitlines(), "gather") if c.get("indexed")]))
+        assert calls_n[0] > 100 and calls_n[1] == 1                                # thousands of blocking calls vs one per group of tasks
+        a, b = imgs
+        assert a.mean() > 0.1 and np.abs(a - b).max() <= 2e-5 * max(1.0, float(np.abs(a).max()))
+        assert (np.abs(a - b) / (np.abs(a) + 1e-6)).max() < 1e-5
