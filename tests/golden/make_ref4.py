@@ -1,8 +1,7 @@
 """BASELINE configs[3] at its SHIPPED SIZE: projectScene/pinkfloyd.pbrt exactly as the reference project ships it (5 M volume photons,
 512 x 512, nused 500, maxdist .4, glass prism with dispersion, spot + point light, EXR output) with ONE change: 1 sample per pixel
 instead of 32 (the unmodified reference needs 67 s of shooting + 136 s of rendering PER SAMPLE on this container's 8 cores; the photon
-count, resolution and lookup size are what load the device path).  Copies the scene (and obj/prism.pbrt it includes) next to the
-other test scenes, renders it with the unmodified reference (--ncores 1) into tests/golden/pinkfloyd_1spp_ref.npy (fp16, = the
+count, resolution and lookup size are what load the device path).  Renders it with the unmodified reference (--ncores 1) into tests/golden/pinkfloyd_1spp_ref.npy (fp16, = the
 decoded .exr) and measures the reference's own spread on other random streams into tests/golden/ref_spread.json.  For a 512 x 512
 frame the reference cuts the image into max(32 * ncores, pixels / 256) = 1024 tasks for any ncores <= 32, and a task's RNG seed and
 sample window depend on the task number alone -- so --ncores 2, 3, 5 re-draw the PHOTONS but render with the very same random
@@ -23,11 +22,10 @@ name = "pinkfloyd_1spp"
 text = open(os.path.join(SRC, "pinkfloyd.pbrt")).read()
 assert '"integer pixelsamples" [32]' in text
 text = text.replace('"integer pixelsamples" [32]', '"integer pixelsamples" [1]')
-scenes_dir = os.path.join(ROOT, "tests", "scenes")
-open(os.path.join(scenes_dir, name + ".pbrt"), "w").write(text)
-os.makedirs(os.path.join(scenes_dir, "obj"), exist_ok=True)
-shutil.copyfile(os.path.join(SRC, "obj", "prism.pbrt"), os.path.join(scenes_dir, "obj", "prism.pbrt"))
 tmp = tempfile.mkdtemp()
+scenes_dir = tmp                                  # the 1-spp variant lives in the scratch directory only (the test makes its own)
+open(os.path.join(scenes_dir, name + ".pbrt"), "w").write(text)
+shutil.copytree(os.path.join(SRC, "obj"), os.path.join(scenes_dir, "obj"))
 
 
 def render(cores):

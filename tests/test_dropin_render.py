@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "baseline", "_ref", "pbrt_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 TOL_FACTOR, TOL_FLOOR_MEAN, TOL_FLOOR_BLOCK = 2.0, 0.005, 0.01
+PROJECT = os.path.join(ROOT, "baseline", "_ref", "projectScene")     # the reference project's own scene files, staged unmodified by
+                                                                      # __graft_entry__.build() (git-ignored, travels to the GPU box)
 needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="baseline/_ref/pbrt_b200 not built (needs the reference sources: make -C cs348b-pbrt_b200/host)")
 
 
@@ -132,12 +134,14 @@ def test_dropin_renders_the_project_scenes_like_the_reference(tmp_path, name):
 
 @needs_bin
 def test_dropin_renders_config1_verbatim(tmp_path):
-    """BASELINE configs[0] VERBATIM: projectScene/volumescene_png.pbrt exactly as the reference project ships it (a byte-for-byte
-    copy of that data file is tests/scenes/volumescene_png.pbrt): photonmap surface integrator with final gathering, photonvolume
+    """BASELINE configs[0] VERBATIM: projectScene/volumescene_png.pbrt exactly as the reference project ships it (the file itself,
+    staged under baseline/_ref/projectScene): photonmap surface integrator with final gathering, photonvolume
     integrator, rainbow medium, distant light, 300 x 300, written as PNG by the reference's own film (gamma 2.2, 8 bit).  Compared,
     after undoing the gamma, with the PNG the unmodified reference wrote from the same file (tests/golden/volumescene_png_ref.png;
     the reference's own spread on this file is in ref_spread.json)."""
-    scene = os.path.join(ROOT, "tests", "scenes", "volumescene_png.pbrt")
+    scene = os.path.join(PROJECT, "volumescene_png.pbrt")
+    if not os.path.exists(scene):
+        pytest.skip("baseline/_ref/projectScene not staged (__graft_entry__.build() in the container that has the reference)")
     out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "[pv] all maps on the GPU" in out.stderr and "volume gather" in out.stderr and "Shooting photons" not in out.stderr
@@ -280,8 +284,8 @@ def test_dropin_runs_lphoton_of_primary_hits_on_the_device(tmp_path):
 
 @needs_bin
 def test_dropin_renders_config4_at_its_shipped_size(tmp_path):
-    """BASELINE configs[3] at the size the project ships it: projectScene/pinkfloyd.pbrt (tests/scenes/pinkfloyd_1spp.pbrt is that
-    file with ONE change, 1 sample per pixel instead of 32; obj/prism.pbrt is its include) -- 5 M volume photons shot through the
+    """BASELINE configs[3] at the size the project ships it: projectScene/pinkfloyd.pbrt (the staged file itself, with ONE change made
+    here: 1 sample per pixel instead of 32; obj/prism.pbrt is its include) -- 5 M volume photons shot through the
     dispersive glass prism under a 0.8 degree spot + a point light, 512 x 512, nused 500 (the k-nearest regime with a lookup
     larger than the batched kernel's 64: the warp-per-lookup search on a grid whose cells followed the photon crowding), maxdist .4,
     EXR output.  Against the unmodified reference's render of the same file (--ncores 1: 22 minutes on this container;
@@ -299,7 +303,15 @@ def test_dropin_renders_config4_at_its_shipped_size(tmp_path):
     import re
     os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
     cv2 = pytest.importorskip("cv2")
-    scene = os.path.join(ROOT, "tests", "scenes", name + ".pbrt")
+    src = os.path.join(PROJECT, "pinkfloyd.pbrt")
+    if not os.path.exists(src):
+        pytest.skip("baseline/_ref/projectScene not staged (__graft_entry__.build() in the container that has the reference)")
+    import shutil
+    text = open(src).read()
+    assert '"integer pixelsamples" [32]' in text
+    scene = os.path.join(tmp_path, name + ".pbrt")
+    open(scene, "w").write(text.replace('"integer pixelsamples" [32]', '"integer pixelsamples" [1]'))
+    shutil.copytree(os.path.join(PROJECT, "obj"), os.path.join(tmp_path, "obj"))
     acc = None
     for seed in (0, 1, 2):
         out = subprocess.run([BIN, "--quiet", scene], cwd=tmp_path, env=dict(os.environ, PV_SEED=str(seed)), capture_output=True, text=True, timeout=1200)
